@@ -1,0 +1,148 @@
+"""draco-oxide_b200 — B200-native drop-in for draco-oxide's attribute-encoding hot path.
+
+Host-side mirror of the reference's public interface for this path:
+
+    encode(mesh, writer, Config.default())        encode/mod.rs:59-97
+    Config                                         encode/mod.rs:22-43
+    Err                                            encode/mod.rs:44-56
+
+Everything below the boundary runs in csrc/libdxo_b200.so (C++ host + CUDA
+sm_100a kernels) through the C ABI in include/dxo.h. There is no CPU fallback:
+calls raise when the library or a CUDA device is missing.
+"""
+import ctypes as C
+
+from . import _capi
+from .mesh import Attribute, AttributeDomain, AttributeType, ComponentDataType, Mesh  # noqa: F401
+
+
+class Err(Exception):
+    """encode::Err — carries the dxo_status code of the leaf error."""
+
+    def __init__(self, status, message):
+        super().__init__(f"{message} (dxo status {status})")
+        self.status = status
+
+
+class Config:
+    """encode::Config: only `default()` exists in the reference. Quantization bit
+    counts are exposed for the qp sweep; only 11/10 is reference behaviour."""
+
+    def __init__(self, position_bits=11, texcoord_bits=10, generic_bits=11, device=-1):
+        self.position_bits = position_bits
+        self.texcoord_bits = texcoord_bits
+        self.generic_bits = generic_bits
+        self.device = device
+
+    @classmethod
+    def default(cls):
+        return cls()
+
+    def as_c(self):
+        c = _capi.dxo_config()
+        _capi.lib().dxo_config_default(C.byref(c))
+        c.position_bits = self.position_bits
+        c.texcoord_bits = self.texcoord_bits
+        c.generic_bits = self.generic_bits
+        c.device = self.device
+        return c
+
+
+def _check(status):
+    if status != 0:
+        raise Err(status, _capi.lib().dxo_strerror(status).decode())
+
+
+def _take(b):
+    out = C.string_at(b.data, b.len) if b.len else b""
+    _capi.lib().dxo_free_bytes(C.byref(b))
+    return out
+
+
+def encode(mesh, writer, cfg=None):
+    """encode::encode(mesh, &mut writer, cfg). `writer` is any object with
+    `extend(bytes)` (bytearray, list) or `write(bytes)`; bytes are appended."""
+    cfg = cfg or Config.default()
+    L = _capi.lib()
+    cm, cc, out = mesh.as_c(), cfg.as_c(), _capi.dxo_bytes()
+    _check(L.dxo_encode(C.byref(cm), C.byref(cc), C.byref(out)))
+    data = _take(out)
+    if hasattr(writer, "extend"):
+        writer.extend(data)
+    else:
+        writer.write(data)
+
+
+def encode_batch(meshes, cfg=None, first_gpu=0, num_gpus=1):
+    """The transcoder loop (io/gltf/encode.rs:941-953): one stream per mesh."""
+    cfg = cfg or Config.default()
+    L = _capi.lib()
+    n = len(meshes)
+    cms = [m.as_c() for m in meshes]
+    arr = (_capi.dxo_mesh * max(n, 1))(*cms)
+    outs = (_capi.dxo_bytes * max(n, 1))()
+    sts = (C.c_int * max(n, 1))()
+    cc = cfg.as_c()
+    st = L.dxo_encode_batch(arr, n, C.byref(cc), outs, sts, first_gpu, num_gpus)
+    res = [_take(outs[i]) for i in range(n)]
+    _check(st)
+    return res
+
+
+class Session:
+    """Resident session: connectivity done on the host once, every array the
+    attribute kernels read kept in HBM. run() executes the device hot path."""
+
+    def __init__(self, mesh, cfg=None):
+        cfg = cfg or Config.default()
+        self._mesh_c = mesh.as_c()
+        self._h = C.c_void_p()
+        cc = cfg.as_c()
+        _check(_capi.lib().dxo_session_create(C.byref(self._mesh_c), C.byref(cc), C.byref(self._h)))
+
+    def run(self, want_bytes=True):
+        out = _capi.dxo_bytes()
+        _check(_capi.lib().dxo_session_run(self._h, C.byref(out) if want_bytes else None))
+        return _take(out) if want_bytes else None
+
+    def set_trace(self, on=True):
+        _capi.lib().dxo_session_set_trace(self._h, int(on))
+
+    def trace(self, key, dtype):
+        import numpy as np
+        p, n = C.c_void_p(), C.c_uint64()
+        st = _capi.lib().dxo_session_trace_get(self._h, key.encode(), C.byref(p), C.byref(n))
+        if st != 0:
+            raise KeyError(key)
+        return np.frombuffer(C.string_at(p, n.value), dtype=dtype).copy()
+
+    def close(self):
+        if self._h:
+            _capi.lib().dxo_session_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def set_profiling(on):
+    _capi.lib().dxo_set_profiling(int(on))
+
+
+def last_timing():
+    t = _capi.dxo_timing()
+    _check(_capi.lib().dxo_last_timing(C.byref(t)))
+    return {
+        "device_ms": t.device_ms, "host_connectivity_ms": t.host_connectivity_ms, "h2d_ms": t.h2d_ms,
+        "d2h_ms": t.d2h_ms, "total_ms": t.total_ms, "h2d_bytes": t.h2d_bytes, "d2h_bytes": t.d2h_bytes,
+        "num_launches": t.num_launches,
+        "kernels": [{"name": t.kernels[i].name.decode(), "ms": t.kernels[i].ms,
+                     "algorithmic_bytes": t.kernels[i].algorithmic_bytes} for i in range(t.num_kernels)],
+    }
+
+
+def device_count():
+    return _capi.lib().dxo_device_count()

@@ -1,0 +1,204 @@
+/*
+ * dxo.h — C ABI of the B200-native Draco attribute-encoding path.
+ *
+ * This header is the drop-in boundary for draco-oxide's
+ *   pub fn encode<W: ByteWriter>(mesh: Mesh, writer: &mut W, cfg: Config) -> Result<(), Err>
+ *   (reference: draco-oxide/src/encode/mod.rs:59-97)
+ * and for the per-primitive call the glTF transcoder makes
+ *   (reference: draco-oxide/src/io/gltf/encode.rs:932-955).
+ *
+ * Plain C types only: pointers, sizes, fixed-width integers. No CUDA, torch or
+ * C++ types appear in any signature. All inputs are borrowed for the duration
+ * of the call; outputs are owned by the library until dxo_free_bytes().
+ *
+ * The byte stream produced is the Draco v2.2 Edgebreaker mesh stream of the
+ * reference, byte for byte (layout: DESIGN.md "Byte layout").
+ *
+ * There is no CPU fallback: every entry point that does attribute work fails
+ * with DXO_ERR_NO_DEVICE / DXO_ERR_CUDA when no sm_100a device is usable.
+ */
+#ifndef DXO_H_
+#define DXO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DXO_ABI_VERSION 1
+
+/* ---- enums (numeric ids are the ones the reference writes to the stream) ---- */
+
+/* AttributeType::get_id — draco-oxide/src/core/attribute/mod.rs:652-665 */
+enum dxo_attribute_type {
+  DXO_ATT_POSITION = 0,
+  DXO_ATT_NORMAL = 1,
+  DXO_ATT_COLOR = 2,
+  DXO_ATT_TEXCOORD = 3,
+  DXO_ATT_CUSTOM = 4,
+  DXO_ATT_TANGENT = 5,
+  DXO_ATT_MATERIAL = 6,
+  DXO_ATT_JOINT = 7,
+  DXO_ATT_WEIGHT = 8
+};
+
+/* ComponentDataType::get_id — draco-oxide/src/core/attribute/mod.rs:565-579 */
+enum dxo_component_type {
+  DXO_U8 = 1,
+  DXO_I8 = 2,
+  DXO_U16 = 3,
+  DXO_I16 = 4,
+  DXO_U32 = 5,
+  DXO_I32 = 6,
+  DXO_U64 = 7,
+  DXO_I64 = 8,
+  DXO_F32 = 9,
+  DXO_F64 = 10
+};
+
+/* AttributeDomain — draco-oxide/src/core/attribute/mod.rs:700-716 */
+enum dxo_domain { DXO_DOMAIN_POSITION = 0, DXO_DOMAIN_CORNER = 1 };
+
+/* ---- error codes: one per leaf of encode::Err (encode/mod.rs:44-56) ---- */
+enum dxo_status {
+  DXO_OK = 0,
+  DXO_ERR_INVALID_ARGUMENT = -1,     /* NULL pointer, bad sizes, index out of range */
+  DXO_ERR_UNSUPPORTED_INPUT = -2,    /* inputs on which the reference panics / unimplemented!() */
+  DXO_ERR_UNSUPPORTED_DATA_TYPE = -3,/* attribute_encoder.rs:33  Err::UnsupportedDataType */
+  DXO_ERR_UNSUPPORTED_NUM_COMPONENTS = -4, /* attribute_encoder.rs:35 */
+  DXO_ERR_TOO_MANY_ATTRIBUTES = -5,  /* connectivity/mod.rs:110 TooManyConnectivityAttributes */
+  DXO_ERR_RANS_INVALID_SYMBOL = -6,  /* entropy/rans.rs:261 InvalidSymbolIndex */
+  DXO_ERR_RANS_STATE_TOO_LARGE = -7, /* entropy/rans.rs:265 StateTooLarge */
+  DXO_ERR_RANS_FREQ_TABLE = -8,      /* shared/entropy/mod.rs:69 FrequencyCountNotCompatibleWithRansPrecision */
+  DXO_ERR_ZERO_NORMAL = -9,          /* geom.rs:45 assert!(v != zero) */
+  DXO_ERR_UNUSED_VERTICES = -10,     /* corner_table/mod.rs:105-108 panic */
+  DXO_ERR_NO_DEVICE = -20,           /* no usable CUDA device: there is no CPU fallback */
+  DXO_ERR_CUDA = -21,                /* a CUDA runtime call or kernel failed */
+  DXO_ERR_OUT_OF_MEMORY = -22,
+  DXO_ERR_INTERNAL = -99
+};
+
+/* ---- mesh handed over the boundary ----
+ * Mirrors Mesh{faces, attributes} and Attribute{id, buffer, att_type, domain,
+ * parents, point_to_att_val_map} (core/mesh/mod.rs:13-23, core/attribute/mod.rs:26-49).
+ * A Rust shim converts usize indices to u32 and fills these from &Mesh.
+ */
+typedef struct dxo_attribute {
+  uint32_t att_type;        /* enum dxo_attribute_type */
+  uint32_t component_type;  /* enum dxo_component_type */
+  uint32_t num_components;  /* 1..4 */
+  uint32_t domain;          /* enum dxo_domain */
+  uint32_t unique_id;       /* AttributeId */
+  uint32_t num_parents;
+  const uint32_t* parent_ids;       /* AttributeId of each parent */
+  uint64_t num_unique_values;       /* Attribute::num_unique_values() */
+  const void* values;               /* AoS little-endian, num_unique_values * num_components components */
+  uint64_t num_points;              /* Attribute::len() */
+  const uint32_t* point_to_value;   /* point -> unique value index; NULL = identity map */
+} dxo_attribute;
+
+typedef struct dxo_mesh {
+  uint64_t num_faces;
+  const uint32_t* faces;            /* 3 point indices per face */
+  uint32_t num_attributes;
+  const dxo_attribute* attributes;  /* attributes[0] is the position attribute (MeshBuilder::get_sorted_attributes) */
+} dxo_mesh;
+
+/* encode::Config (encode/mod.rs:22-43) has only default(); the quantization bit
+ * counts are constants in the reference (portabilization/mod.rs:116-142). They
+ * are parameters here; only 11/10 is reference behaviour. Octahedral normal
+ * quantization is fixed at 8 bits (the reference hard-codes 255/127). */
+typedef struct dxo_config {
+  uint32_t abi_version;       /* DXO_ABI_VERSION */
+  uint32_t position_bits;     /* default 11 */
+  uint32_t texcoord_bits;     /* default 10 */
+  uint32_t generic_bits;      /* default 11: other quantized attribute types */
+  int32_t  device;            /* CUDA device ordinal; -1 = current device */
+  uint32_t flags;             /* reserved, 0 */
+} dxo_config;
+
+typedef struct dxo_bytes {
+  uint8_t* data;
+  size_t len;
+} dxo_bytes;
+
+/* Fills *cfg with the reference defaults (encode::Config::default()). */
+void dxo_config_default(dxo_config* cfg);
+
+/* encode::encode — one mesh, host buffers in, owned byte buffer out. */
+int dxo_encode(const dxo_mesh* mesh, const dxo_config* cfg, dxo_bytes* out);
+
+/* The transcoder loop (io/gltf/encode.rs:941-953 called once per primitive):
+ * n independent meshes, sharded over GPUs [first_gpu, first_gpu+num_gpus) with
+ * no exchange between them. outs[i] corresponds to meshes[i]; statuses[i]
+ * (optional) receives the per-mesh status. Returns the first non-OK status. */
+int dxo_encode_batch(const dxo_mesh* meshes, size_t n, const dxo_config* cfg,
+                     dxo_bytes* outs, int* statuses, int first_gpu, int num_gpus);
+
+void dxo_free_bytes(dxo_bytes* b);
+const char* dxo_strerror(int status);
+
+/* Number of visible CUDA devices (0 when none / no driver). */
+int dxo_device_count(void);
+
+/* ---- resident sessions: the measured hot path with inputs already in HBM ----
+ * A session owns the host-side connectivity results (corner tables, Edgebreaker
+ * bytes, attribute sequences) and the device copies of every array the
+ * attribute kernels read. dxo_session_run() executes only the device hot path
+ * (quantize -> predict -> symbolize -> histogram -> table -> rANS) plus the
+ * D2H of its results, and reassembles the stream. */
+typedef struct dxo_session dxo_session;
+
+int dxo_session_create(const dxo_mesh* mesh, const dxo_config* cfg, dxo_session** out);
+/* Runs the device hot path once. out may be NULL (results are discarded after
+ * the D2H completes). */
+int dxo_session_run(dxo_session* s, dxo_bytes* out);
+void dxo_session_destroy(dxo_session* s);
+
+/* Timing of the last dxo_session_run / dxo_encode on this thread, measured with
+ * CUDA events on the stream the kernels were launched on. */
+typedef struct dxo_kernel_time {
+  const char* name;        /* kernel label, static storage */
+  float ms;                /* device time of this launch */
+  uint64_t algorithmic_bytes; /* bytes per DESIGN.md "Algorithmic bytes" for this launch */
+} dxo_kernel_time;
+
+typedef struct dxo_timing {
+  float device_ms;         /* first kernel start -> last kernel end */
+  float host_connectivity_ms; /* corner tables + Edgebreaker + sequencer (host) */
+  float h2d_ms;
+  float d2h_ms;
+  float total_ms;          /* wall clock of the call */
+  uint64_t h2d_bytes;
+  uint64_t d2h_bytes;
+  uint32_t num_launches;   /* kernels launched by this library in the call */
+  uint32_t num_kernels;    /* entries valid in kernels[] */
+  dxo_kernel_time kernels[64];
+} dxo_timing;
+
+/* Enables per-kernel event timing (adds event records between launches). */
+void dxo_set_profiling(int enabled);
+int dxo_last_timing(dxo_timing* out);
+
+/* ---- stage access for parity tests (GPU results, copied back) ----
+ * After dxo_session_run with tracing enabled, intermediate device results can
+ * be read by key ("att0.quantized", "att0.symbols", "att1.flips", ...). The
+ * pointer stays valid until the next run or session destroy. */
+void dxo_session_set_trace(dxo_session* s, int enabled);
+int dxo_session_trace_get(dxo_session* s, const char* key, const void** data, uint64_t* nbytes);
+
+/* Corner-table build on the device (half-edge matching by radix sort;
+ * replaces CornerTable::compute_table, core/corner_table/mod.rs:252-340).
+ * vertex_of_corner: 3*num_faces vertex ids. opposite_out: 3*num_faces entries,
+ * 0xFFFFFFFF = none. *exact_out = 1 when the mesh is on the manifold fast path
+ * (result equals the reference's order-dependent matcher); 0 means the caller
+ * must use the sequential matcher. */
+int dxo_corner_table_opposites(const uint32_t* vertex_of_corner, uint64_t num_faces,
+                               uint32_t* opposite_out, int* exact_out, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DXO_H_ */
