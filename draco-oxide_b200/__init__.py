@@ -93,12 +93,13 @@ class Session:
     """Resident session: connectivity done on the host once, every array the
     attribute kernels read kept in HBM. run() executes the device hot path."""
 
-    def __init__(self, mesh, cfg=None):
+    def __init__(self, mesh, cfg=None, host_only=False):
         cfg = cfg or Config.default()
         self._mesh_c = mesh.as_c()
         self._h = C.c_void_p()
         cc = cfg.as_c()
-        _check(_capi.lib().dxo_session_create(C.byref(self._mesh_c), C.byref(cc), C.byref(self._h)))
+        make = _capi.lib().dxo_connectivity_create if host_only else _capi.lib().dxo_session_create
+        _check(make(C.byref(self._mesh_c), C.byref(cc), C.byref(self._h)))
 
     def run(self, want_bytes=True):
         out = _capi.dxo_bytes()

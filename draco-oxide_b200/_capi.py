@@ -70,7 +70,7 @@ class dxo_timing(C.Structure):
 # every symbol include/dxo.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = [
     "dxo_config_default", "dxo_encode", "dxo_encode_batch", "dxo_free_bytes", "dxo_strerror",
-    "dxo_device_count", "dxo_session_create", "dxo_session_run", "dxo_session_destroy",
+    "dxo_device_count", "dxo_session_create", "dxo_connectivity_create", "dxo_session_run", "dxo_session_destroy",
     "dxo_set_profiling", "dxo_last_timing", "dxo_session_set_trace", "dxo_session_trace_get",
     "dxo_corner_table_opposites",
 ]
@@ -104,6 +104,8 @@ def lib():
     L.dxo_device_count.restype = C.c_int
     L.dxo_session_create.argtypes = [C.POINTER(dxo_mesh), C.POINTER(dxo_config), C.POINTER(C.c_void_p)]
     L.dxo_session_create.restype = C.c_int
+    L.dxo_connectivity_create.argtypes = [C.POINTER(dxo_mesh), C.POINTER(dxo_config), C.POINTER(C.c_void_p)]
+    L.dxo_connectivity_create.restype = C.c_int
     L.dxo_session_run.argtypes = [C.c_void_p, C.POINTER(dxo_bytes)]
     L.dxo_session_run.restype = C.c_int
     L.dxo_session_destroy.argtypes = [C.c_void_p]

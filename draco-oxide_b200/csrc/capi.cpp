@@ -1,0 +1,313 @@
+// extern "C" surface declared in include/dxo.h.
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
+#include <numeric>
+#include <thread>
+
+#include "encoder.hpp"
+
+using namespace dxo;
+
+namespace {
+
+using Clock = std::chrono::steady_clock;
+double ms_since(Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); }
+
+thread_local dxo_timing g_timing{};
+thread_local std::string g_error;
+std::atomic<int> g_profiling{0};
+
+template <class F> int guarded(F&& f) {
+  try { f(); return DXO_OK; }
+  catch (const Error& e) { g_error = e.what(); return e.status; }
+  catch (const std::bad_alloc&) { g_error = "out of host memory"; return DXO_ERR_OUT_OF_MEMORY; }
+  catch (const std::exception& e) { g_error = e.what(); return DXO_ERR_INTERNAL; }
+}
+
+int give(std::vector<uint8_t>& bytes, dxo_bytes* out) {
+  out->data = (uint8_t*)malloc(bytes.size() ? bytes.size() : 1);
+  if (!out->data) return DXO_ERR_OUT_OF_MEMORY;
+  memcpy(out->data, bytes.data(), bytes.size());
+  out->len = bytes.size();
+  return DXO_OK;
+}
+
+dxo_config effective_config(const dxo_config* cfg) {
+  dxo_config c;
+  dxo_config_default(&c);
+  if (cfg) {
+    if (cfg->abi_version != DXO_ABI_VERSION) throw Error(DXO_ERR_INVALID_ARGUMENT, "dxo_config.abi_version mismatch");
+    c = *cfg;
+  }
+  return c;
+}
+
+// Runs launch + download + assemble for a job whose inputs are already on the device,
+// filling the thread's timing record.
+void run_device_phase(MeshJob& job, DeviceContext& ctx, Profile& prof, std::vector<uint8_t>& bytes, dxo_timing& tm) {
+  prof.reset();
+  prof.enabled = g_profiling.load() != 0;
+  cudaStream_t s0 = ctx.stream[0];
+  cuda_check(cudaEventRecord(ctx.ev_begin, s0), "cudaEventRecord");
+  for (int k = 1; k < 3; ++k) cuda_check(cudaStreamWaitEvent(ctx.stream[k], ctx.ev_begin, 0), "cudaStreamWaitEvent");
+  job.launch(ctx, prof);
+  for (int k = 1; k < 3; ++k) {
+    cuda_check(cudaEventRecord(ctx.ev_join[k], ctx.stream[k]), "cudaEventRecord");
+    cuda_check(cudaStreamWaitEvent(s0, ctx.ev_join[k], 0), "cudaStreamWaitEvent");
+  }
+  cuda_check(cudaEventRecord(ctx.ev_end, s0), "cudaEventRecord");
+  if (prof.enabled) cuda_check(cudaEventSynchronize(ctx.ev_end), "cudaEventSynchronize");
+  const auto t_d2h = Clock::now();
+  job.download(ctx);
+  tm.d2h_ms = (float)ms_since(t_d2h);
+  cuda_check(cudaEventSynchronize(ctx.ev_end), "cudaEventSynchronize");
+  cuda_check(cudaEventElapsedTime(&tm.device_ms, ctx.ev_begin, ctx.ev_end), "cudaEventElapsedTime");
+  job.assemble(bytes);
+  tm.num_launches = prof.launches;
+  tm.num_kernels = 0;
+  for (const KernelRecord& r : prof.records) {
+    if (tm.num_kernels >= 64) break;
+    dxo_kernel_time& k = tm.kernels[tm.num_kernels++];
+    k.name = r.name;
+    k.algorithmic_bytes = r.bytes;
+    cuda_check(cudaEventElapsedTime(&k.ms, r.a, r.b), "cudaEventElapsedTime");
+  }
+  tm.d2h_bytes = job.d2h_bytes;
+}
+
+thread_local Profile g_profile;
+
+void encode_one(const dxo_mesh* mesh, const dxo_config& cfg, std::vector<uint8_t>& bytes, dxo_timing& tm) {
+  tm = dxo_timing{};
+  const auto t0 = Clock::now();
+  MeshJob job(mesh, cfg);
+  job.build_connectivity();
+  tm.host_connectivity_ms = (float)ms_since(t0);
+  DeviceContext& ctx = DeviceContext::get(cfg.device);
+  const auto t1 = Clock::now();
+  job.upload(ctx);
+  if (g_profiling.load()) cuda_check(cudaStreamSynchronize(ctx.stream[0]), "cudaStreamSynchronize");
+  tm.h2d_ms = (float)ms_since(t1);
+  tm.h2d_bytes = job.h2d_bytes;
+  try { run_device_phase(job, ctx, g_profile, bytes, tm); }
+  catch (...) { job.release(ctx); cudaStreamSynchronize(ctx.stream[0]); throw; }
+  job.release(ctx);
+  tm.total_ms = (float)ms_since(t0);
+}
+
+}  // namespace
+
+struct dxo_session {
+  std::unique_ptr<MeshJob> job;
+  dxo_config cfg;
+  int device = 0;
+};
+
+extern "C" {
+
+void dxo_config_default(dxo_config* cfg) {
+  if (!cfg) return;
+  cfg->abi_version = DXO_ABI_VERSION;
+  cfg->position_bits = 11;   // portabilization/mod.rs:107-112
+  cfg->texcoord_bits = 10;   // :127-130
+  cfg->generic_bits = 11;
+  cfg->device = -1;
+  cfg->flags = 0;
+}
+
+int dxo_encode(const dxo_mesh* mesh, const dxo_config* cfg, dxo_bytes* out) {
+  if (!out) return DXO_ERR_INVALID_ARGUMENT;
+  out->data = nullptr; out->len = 0;
+  return guarded([&] {
+    const dxo_config c = effective_config(cfg);
+    std::vector<uint8_t> bytes;
+    encode_one(mesh, c, bytes, g_timing);
+    if (int st = give(bytes, out)) throw Error(st, "out of memory");
+  });
+}
+
+int dxo_encode_batch(const dxo_mesh* meshes, size_t n, const dxo_config* cfg, dxo_bytes* outs, int* statuses, int first_gpu, int num_gpus) {
+  if ((!meshes || !outs) && n) return DXO_ERR_INVALID_ARGUMENT;
+  for (size_t i = 0; i < n; ++i) { outs[i].data = nullptr; outs[i].len = 0; if (statuses) statuses[i] = DXO_OK; }
+  int first_error = DXO_OK;
+  int st = guarded([&] {
+    const dxo_config base = effective_config(cfg);
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { cudaGetLastError(); throw Error(DXO_ERR_NO_DEVICE, "no CUDA device available (this path has no CPU fallback)"); }
+    if (num_gpus <= 0) num_gpus = 1;
+    if (first_gpu < 0 || first_gpu + num_gpus > count) throw Error(DXO_ERR_NO_DEVICE, "GPU range out of bounds");
+    // longest-processing-time-first order over a shared queue
+    std::vector<size_t> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return meshes[a].num_faces > meshes[b].num_faces; });
+    std::atomic<size_t> next{0};
+    std::vector<int> sts(n, DXO_OK);
+    const char* env = getenv("DXO_WORKERS_PER_GPU");
+    int per_gpu = env ? atoi(env) : 3;  // host connectivity of one mesh overlaps device work of another
+    if (per_gpu < 1) per_gpu = 1;
+    const int workers = (int)std::min<size_t>((size_t)num_gpus * per_gpu, std::max<size_t>(n, 1));
+    std::vector<std::thread> pool;
+    for (int w = 0; w < workers; ++w) {
+      pool.emplace_back([&, w] {
+        dxo_config c = base;
+        c.device = first_gpu + w % num_gpus;
+        dxo_timing tm;
+        for (;;) {
+          const size_t k = next.fetch_add(1);
+          if (k >= n) break;
+          const size_t i = order[k];
+          sts[i] = guarded([&] {
+            std::vector<uint8_t> bytes;
+            encode_one(&meshes[i], c, bytes, tm);
+            if (int s2 = give(bytes, &outs[i])) throw Error(s2, "out of memory");
+          });
+        }
+      });
+    }
+    for (auto& t : pool) t.join();
+    for (size_t i = 0; i < n; ++i) { if (statuses) statuses[i] = sts[i]; if (sts[i] != DXO_OK && first_error == DXO_OK) first_error = sts[i]; }
+  });
+  return st != DXO_OK ? st : first_error;
+}
+
+void dxo_free_bytes(dxo_bytes* b) {
+  if (b && b->data) { free(b->data); b->data = nullptr; b->len = 0; }
+}
+
+const char* dxo_strerror(int status) {
+  switch (status) {
+    case DXO_OK: return "ok";
+    case DXO_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case DXO_ERR_UNSUPPORTED_INPUT: return "unsupported input (the reference panics or is unimplemented here)";
+    case DXO_ERR_UNSUPPORTED_DATA_TYPE: return "unsupported data type";
+    case DXO_ERR_UNSUPPORTED_NUM_COMPONENTS: return "attribute data has too many components";
+    case DXO_ERR_TOO_MANY_ATTRIBUTES: return "too many connectivity attributes";
+    case DXO_ERR_RANS_INVALID_SYMBOL: return "rANS: invalid symbol index";
+    case DXO_ERR_RANS_STATE_TOO_LARGE: return "rANS: state too large";
+    case DXO_ERR_RANS_FREQ_TABLE: return "rANS: frequency table not compatible with the precision";
+    case DXO_ERR_ZERO_NORMAL: return "zero vector cannot be transformed to octahedron space";
+    case DXO_ERR_UNUSED_VERTICES: return "mesh contains unused vertices";
+    case DXO_ERR_NO_DEVICE: return "no usable CUDA device (no CPU fallback on this path)";
+    case DXO_ERR_CUDA: return "CUDA error";
+    case DXO_ERR_OUT_OF_MEMORY: return "out of memory";
+    default: return "internal error";
+  }
+}
+
+int dxo_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return count;
+}
+
+int dxo_session_create(const dxo_mesh* mesh, const dxo_config* cfg, dxo_session** out) {
+  if (!out) return DXO_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded([&] {
+    auto s = std::make_unique<dxo_session>();
+    s->cfg = effective_config(cfg);
+    g_timing = dxo_timing{};
+    const auto t0 = Clock::now();
+    s->job = std::make_unique<MeshJob>(mesh, s->cfg);
+    s->job->build_connectivity();
+    g_timing.host_connectivity_ms = (float)ms_since(t0);
+    DeviceContext& ctx = DeviceContext::get(s->cfg.device);
+    s->device = ctx.device;
+    const auto t1 = Clock::now();
+    s->job->upload(ctx);
+    cuda_check(cudaStreamSynchronize(ctx.stream[0]), "cudaStreamSynchronize");
+    g_timing.h2d_ms = (float)ms_since(t1);
+    g_timing.h2d_bytes = s->job->h2d_bytes;
+    *out = s.release();
+  });
+}
+
+int dxo_connectivity_create(const dxo_mesh* mesh, const dxo_config* cfg, dxo_session** out) {
+  if (!out) return DXO_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded([&] {
+    auto s = std::make_unique<dxo_session>();
+    s->cfg = effective_config(cfg);
+    s->job = std::make_unique<MeshJob>(mesh, s->cfg);
+    s->job->build_connectivity();
+    s->job->capture_host_trace();
+    s->device = -1;
+    *out = s.release();
+  });
+}
+
+int dxo_session_run(dxo_session* s, dxo_bytes* out) {
+  if (!s) return DXO_ERR_INVALID_ARGUMENT;
+  if (s->device < 0) return DXO_ERR_NO_DEVICE;  // host-only session (dxo_connectivity_create)
+  if (out) { out->data = nullptr; out->len = 0; }
+  return guarded([&] {
+    DeviceContext& ctx = DeviceContext::get(s->device);
+    const float conn = g_timing.host_connectivity_ms, h2d = g_timing.h2d_ms;
+    const uint64_t h2db = g_timing.h2d_bytes;
+    const auto t0 = Clock::now();
+    std::vector<uint8_t> bytes;
+    s->job->d2h_bytes = 0;
+    run_device_phase(*s->job, ctx, g_profile, bytes, g_timing);
+    g_timing.host_connectivity_ms = conn; g_timing.h2d_ms = h2d; g_timing.h2d_bytes = h2db;
+    g_timing.total_ms = (float)ms_since(t0);
+    if (out) { if (int st = give(bytes, out)) throw Error(st, "out of memory"); }
+  });
+}
+
+void dxo_session_destroy(dxo_session* s) {
+  if (!s) return;
+  if (s->device >= 0) guarded([&] {
+    DeviceContext& ctx = DeviceContext::get(s->device);
+    s->job->release(ctx);
+    cudaStreamSynchronize(ctx.stream[0]);
+  });
+  delete s;
+}
+
+void dxo_set_profiling(int enabled) { g_profiling.store(enabled ? 1 : 0); }
+
+int dxo_last_timing(dxo_timing* out) {
+  if (!out) return DXO_ERR_INVALID_ARGUMENT;
+  *out = g_timing;
+  return DXO_OK;
+}
+
+void dxo_session_set_trace(dxo_session* s, int enabled) { if (s) s->job->trace = enabled != 0; }
+
+int dxo_session_trace_get(dxo_session* s, const char* key, const void** data, uint64_t* nbytes) {
+  if (!s || !key || !data || !nbytes) return DXO_ERR_INVALID_ARGUMENT;
+  auto it = s->job->trace_items.find(key);
+  if (it == s->job->trace_items.end()) return DXO_ERR_INVALID_ARGUMENT;
+  *data = it->second.data();
+  *nbytes = it->second.size();
+  return DXO_OK;
+}
+
+int dxo_corner_table_opposites(const uint32_t* vertex_of_corner, uint64_t num_faces, uint32_t* opposite_out, int* exact_out, int device) {
+  if (!vertex_of_corner || !opposite_out || !exact_out || num_faces == 0 || num_faces > 0x2AAAAAAAull) return DXO_ERR_INVALID_ARGUMENT;
+  return guarded([&] {
+    DeviceContext& ctx = DeviceContext::get(device);
+    cudaStream_t s = ctx.stream[0];
+    const uint64_t C = num_faces * 3;
+    uint32_t *d_cv = nullptr, *d_opp = nullptr, *d_flag = nullptr;
+    void* scratch = nullptr;
+    const size_t sb = gpu::corner_table_scratch_bytes(C);
+    cuda_check(cudaMallocAsync((void**)&d_cv, C * 4, s), "cudaMallocAsync");
+    cuda_check(cudaMallocAsync((void**)&d_opp, C * 4, s), "cudaMallocAsync");
+    cuda_check(cudaMallocAsync((void**)&d_flag, 4, s), "cudaMallocAsync");
+    cuda_check(cudaMallocAsync(&scratch, sb, s), "cudaMallocAsync");
+    cuda_check(cudaMemcpyAsync(d_cv, vertex_of_corner, C * 4, cudaMemcpyHostToDevice, s), "H2D");
+    cuda_check(cudaMemsetAsync(d_flag, 0, 4, s), "memset");
+    cuda_check(cudaMemsetAsync(d_opp, 0xFF, C * 4, s), "memset");
+    gpu::launch_corner_table_opposites(d_cv, C, d_opp, d_flag, scratch, sb, s);
+    uint32_t flag = 0;
+    cuda_check(cudaMemcpyAsync(opposite_out, d_opp, C * 4, cudaMemcpyDeviceToHost, s), "D2H");
+    cuda_check(cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, s), "D2H");
+    cudaFreeAsync(d_cv, s); cudaFreeAsync(d_opp, s); cudaFreeAsync(d_flag, s); cudaFreeAsync(scratch, s);
+    cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    *exact_out = flag ? 0 : 1;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// Product host code — shared definitions, byte sinks and the binary rANS (rABS) coder.
+// Reference paths are relative to /root/reference/draco-oxide/src/.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/dxo.h"
+
+namespace dxo {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+struct Error : std::runtime_error {
+  int status;
+  Error(int st, const std::string& what) : std::runtime_error(what), status(st) {}
+};
+
+// corner navigation inside a triangle (core/corner_table/mod.rs:503-523)
+static inline uint32_t corner_next(uint32_t c) { return (c % 3u == 2u) ? c - 2u : c + 1u; }
+static inline uint32_t corner_prev(uint32_t c) { return (c % 3u == 0u) ? c + 2u : c - 1u; }
+
+// Append-only little-endian byte sink (ByteWriter for Vec<u8>, core/bit_coder.rs:28-48).
+class ByteSink {
+ public:
+  std::vector<uint8_t> data;
+  void u8(uint8_t v) { data.push_back(v); }
+  void u16(uint16_t v) { data.push_back((uint8_t)v); data.push_back((uint8_t)(v >> 8)); }
+  void u24(uint32_t v) { u8((uint8_t)v); u8((uint8_t)(v >> 8)); u8((uint8_t)(v >> 16)); }
+  void u32(uint32_t v) { u16((uint16_t)v); u16((uint16_t)(v >> 16)); }
+  void i32(int32_t v) { u32((uint32_t)v); }
+  void f32(float f) { uint32_t b; memcpy(&b, &f, 4); u32(b); }
+  void bytes(const uint8_t* p, size_t n) { data.insert(data.end(), p, p + n); }
+  void bytes(const std::vector<uint8_t>& v) { data.insert(data.end(), v.begin(), v.end()); }
+  // LEB128 (utils/bit_coder.rs:20-33)
+  void varint(uint64_t v) {
+    do {
+      uint8_t b = (uint8_t)(v & 0x7F);
+      v >>= 7;
+      data.push_back(v ? (uint8_t)(b | 0x80) : b);
+    } while (v);
+  }
+  size_t size() const { return data.size(); }
+};
+
+// LSB-first bit packer with the reference BitWriter<LsbFirst> byte behaviour
+// (core/bit_coder.rs:113-188): bits fill each byte from bit 0 upwards; a partial
+// last byte is flushed by finish().
+class BitPacker {
+ public:
+  explicit BitPacker(ByteSink& s) : sink_(s) {}
+  void put(unsigned nbits, uint32_t value) {
+    acc_ |= (uint64_t)value << fill_;
+    fill_ += nbits;
+    while (fill_ >= 8) { sink_.u8((uint8_t)acc_); acc_ >>= 8; fill_ -= 8; }
+  }
+  void finish() { if (fill_) { sink_.u8((uint8_t)acc_); acc_ = 0; fill_ = 0; } }
+ private:
+  ByteSink& sink_;
+  uint64_t acc_ = 0;
+  unsigned fill_ = 0;
+};
+
+// Tail of an ANS stream: state - base with a 2-bit length tag (encode/entropy/rans.rs:48-68).
+static inline void ans_write_tail(uint32_t x, ByteSink& out) {
+  if (x < (1u << 6)) out.u8((uint8_t)x);
+  else if (x < (1u << 14)) out.u16((uint16_t)(0x4000u + x));
+  else if (x < (1u << 22)) out.u24(0x800000u + x);
+  else if (x < (1u << 30)) out.u32(0xC0000000u + x);
+  else throw Error(DXO_ERR_RANS_STATE_TOO_LARGE, "rANS state too large");
+}
+
+// Probability of a zero bit used by all binary side streams (Appendix B.8 of SURVEY.md):
+// (((n0 as f32 / len as f32) * 256.0 + 0.5) as u16).clamp(1, 255) — all in f32;
+// an empty stream gives NaN -> 0 -> 1. edgebreaker.rs:595,640; mesh_normal_prediction.rs:151.
+static inline uint8_t side_stream_zero_prob(uint64_t zeros, float len_as_f32) {
+  volatile float ratio = (float)zeros / len_as_f32;  // volatile: keep the f32 rounding steps separate
+  volatile float scaled = ratio * 256.0f;
+  float p = scaled + 0.5f;
+  uint32_t v;
+  if (!(p == p) || p <= 0.0f) v = 0;
+  else if (p >= 65535.0f) v = 65535;
+  else v = (uint32_t)p;
+  if (v < 1) v = 1;
+  if (v > 255) v = 255;
+  return (uint8_t)v;
+}
+
+// Binary rANS coder, precision 8, base 4096 (RabsCoder, encode/entropy/rans.rs:71-127).
+// Encodes a whole bit sequence in the order given and returns the byte stream.
+static inline void rabs_encode(const uint8_t* bits, size_t n, bool reversed, uint8_t zero_prob, ByteSink& out) {
+  const uint32_t f0 = zero_prob, f1 = 256u - f0;
+  uint32_t x = 4096u;
+  auto step = [&](uint8_t bit) {
+    const uint32_t f = bit ? f1 : f0;
+    if (f == 0) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "rABS: zero frequency");
+    if (x >= ((16u * f) << 8)) { out.u8((uint8_t)x); x >>= 8; }  // single renormalisation step (:98-101)
+    const uint32_t q = x / f, r = x - q * f;
+    x = (q << 8) + r + (bit ? 0u : f1);
+  };
+  if (reversed) for (size_t i = n; i-- > 0;) step(bits[i]);
+  else for (size_t i = 0; i < n; ++i) step(bits[i]);
+  ans_write_tail(x - 4096u, out);
+}
+
+// zero_prob byte + leb128 length + rABS bytes: the framing every side stream uses.
+static inline void write_side_stream(const uint8_t* bits, size_t n, bool reversed, uint8_t zero_prob, ByteSink& w) {
+  w.u8(zero_prob);
+  ByteSink tmp;
+  rabs_encode(bits, n, reversed, zero_prob, tmp);
+  w.varint(tmp.size());
+  w.bytes(tmp.data);
+}
+
+}  // namespace dxo

@@ -1,0 +1,539 @@
+// Product host code — see connectivity.hpp. Results must equal the reference's
+// order-dependent algorithms exactly (the Edgebreaker symbols, split events and
+// attribute sequences all depend on them), so each routine keeps the reference's
+// visiting order while working on flat arrays.
+// Reference paths are relative to /root/reference/draco-oxide/src/.
+#include "connectivity.hpp"
+
+namespace dxo {
+
+// ---------------------------------------------------------------------------------------
+// CornerTable::new — core/corner_table/mod.rs:84-118
+void UniversalTable::build(const uint32_t* faces, uint32_t nfaces, const AttrView& pos) {
+  num_faces = nfaces;
+  num_corners = nfaces * 3u;
+  corner_point = faces;
+  corner_vertex.resize(num_corners);
+  uint32_t max_v = 0;
+  for (uint32_t c = 0; c < num_corners; ++c) {
+    const uint32_t p = faces[c];
+    if (p >= pos.num_points) throw Error(DXO_ERR_INVALID_ARGUMENT, "face references a point outside the position attribute");
+    const uint32_t v = pos.value_of(p);
+    if (v >= pos.num_unique) throw Error(DXO_ERR_INVALID_ARGUMENT, "point_to_value entry out of range");
+    corner_vertex[c] = v;
+    max_v = std::max(max_v, v);
+  }
+  num_vertices = num_corners ? max_v + 1u : 0u;
+  // every vertex id up to the maximum must be used (get_unused_vertices, :236-250; panic :105-108)
+  {
+    std::vector<uint8_t> used(num_vertices, 0);
+    for (uint32_t c = 0; c < num_corners; ++c) used[corner_vertex[c]] = 1;
+    for (uint32_t v = 0; v < num_vertices; ++v)
+      if (!used[v]) throw Error(DXO_ERR_UNUSED_VERTICES, "mesh contains unused vertices");
+  }
+  match_half_edges();
+  if (has_non_manifold_edge()) break_non_manifold_edges();
+  assign_left_most_corners();
+}
+
+// compute_table — :252-340. Per-source-vertex buckets of open half edges; a corner
+// looks in the bucket of its sink vertex for the first half edge coming back to its
+// source vertex. Corner order and first-match semantics are the reference's.
+void UniversalTable::match_half_edges() {
+  const uint32_t C = num_corners, V = num_vertices;
+  opposite.assign(C, kNone);
+  std::vector<uint32_t> start(V + 1u, 0);
+  for (uint32_t c = 0; c < C; ++c) start[corner_vertex[c] + 1u]++;
+  for (uint32_t v = 0; v < V; ++v) start[v + 1u] += start[v];
+  std::vector<uint32_t> he_far(C, kNone), he_corner(C, kNone);
+  const uint32_t* cv = corner_vertex.data();
+  for (uint32_t f = 0, c = 0; f < num_faces; ++f) {
+    const uint32_t v3[3] = {cv[c], cv[c + 1], cv[c + 2]};
+    for (uint32_t k = 0; k < 3; ++k, ++c) {
+      const uint32_t tip = v3[k], src = v3[(k + 1) % 3], snk = v3[(k + 2) % 3];
+      if (k == 0 && (tip == src || tip == snk || src == snk)) continue;  // :289-295 (first corner only)
+      uint32_t found = kNone;
+      const uint32_t n = start[snk + 1u] - start[snk];
+      uint32_t off = start[snk];
+      for (uint32_t i = 0; i < n; ++i, ++off) {
+        const uint32_t far = he_far[off];
+        if (far == kNone) break;
+        if (far != src) continue;
+        // :308-310 — a candidate with the same tip blocks the search for this corner.
+        if (tip == cv[he_corner[off]]) break;
+        found = he_corner[off];
+        for (uint32_t j = i + 1; j < n; ++j) {  // close the gap (:312-319)
+          he_far[off] = he_far[off + 1];
+          he_corner[off] = he_corner[off + 1];
+          if (he_far[off] == kNone) break;
+          ++off;
+        }
+        he_far[off] = kNone;
+        break;
+      }
+      if (found == kNone) {
+        for (uint32_t s = start[src], e = start[src + 1u]; s < e; ++s)
+          if (he_far[s] == kNone) { he_far[s] = snk; he_corner[s] = c; break; }
+      } else {
+        opposite[c] = found;
+        opposite[found] = c;
+      }
+    }
+  }
+}
+
+// contains_non_manifold_edges — :121-145: some undirected edge is used by 3+ face sides.
+bool UniversalTable::has_non_manifold_edge() const {
+  const uint32_t C = num_corners, V = num_vertices;
+  std::vector<uint32_t> start(V + 1u, 0);
+  const uint32_t* cv = corner_vertex.data();
+  auto lo_hi = [&](uint32_t c, uint32_t& lo, uint32_t& hi) {
+    const uint32_t a = cv[c], b = cv[corner_next(c)];
+    lo = std::min(a, b); hi = std::max(a, b);
+  };
+  for (uint32_t c = 0; c < C; ++c) { uint32_t lo, hi; lo_hi(c, lo, hi); start[lo + 1u]++; }
+  for (uint32_t v = 0; v < V; ++v) start[v + 1u] += start[v];
+  std::vector<uint32_t> fill(start.begin(), start.end() - 1), far(C);
+  for (uint32_t c = 0; c < C; ++c) { uint32_t lo, hi; lo_hi(c, lo, hi); far[fill[lo]++] = hi; }
+  for (uint32_t v = 0; v < V; ++v) {
+    uint32_t* b = far.data() + start[v];
+    const uint32_t n = start[v + 1u] - start[v];
+    if (n < 3) continue;
+    std::sort(b, b + n);
+    for (uint32_t i = 2; i < n; ++i) if (b[i] == b[i - 1] && b[i] == b[i - 2]) return true;
+  }
+  return false;
+}
+
+// handle_no_manifold_edges — :149-234.
+void UniversalTable::break_non_manifold_edges() {
+  const uint32_t C = num_corners;
+  std::vector<uint8_t> seen(C, 0);
+  std::vector<uint32_t> sink_v, sink_c;
+  for (bool changed = true; changed;) {
+    changed = false;
+    for (uint32_t c0 = 0; c0 < C; ++c0) {
+      if (seen[c0]) continue;
+      sink_v.clear(); sink_c.clear();
+      uint32_t first = c0, cur = c0;
+      for (uint32_t nx; (nx = swing_left(cur)) != kNone;) {
+        if (nx == first || seen[nx]) break;
+        cur = nx;
+      }
+      first = cur;
+      for (;;) {
+        seen[cur] = 1;
+        const uint32_t s_c = corner_next(cur), s_v = corner_vertex[s_c], edge_c = corner_prev(cur);
+        bool updated = false;
+        for (size_t k = 0; k < sink_v.size(); ++k) {
+          if (sink_v[k] != s_v) continue;
+          const uint32_t other_edge = sink_c[k];
+          const uint32_t opp_edge = opposite[edge_c];
+          if (opp_edge != kNone && opp_edge == other_edge) continue;
+          const uint32_t opp_other = opposite[other_edge];
+          if (opp_edge != kNone) opposite[opp_edge] = kNone;
+          if (opp_other != kNone) opposite[opp_other] = kNone;
+          opposite[edge_c] = kNone;
+          opposite[other_edge] = kNone;
+          updated = true;
+          break;
+        }
+        if (updated) { changed = true; break; }
+        sink_v.push_back(corner_vertex[corner_prev(cur)]);
+        sink_c.push_back(s_c);
+        const uint32_t nx = swing_right(cur);
+        if (nx == kNone) break;
+        cur = nx;
+        if (cur == first) break;
+      }
+    }
+  }
+}
+
+// compute_left_most_corners — :342-416. A second fan met at an already visited vertex
+// becomes a new vertex (ids appended in face order); its corners are re-labelled in place.
+void UniversalTable::assign_left_most_corners() {
+  const uint32_t C = num_corners;
+  left_most.assign(num_vertices, kNone);
+  std::vector<uint8_t> vertex_seen(num_vertices, 0), corner_seen(C, 0);
+  for (uint32_t c = 0; c < C; ++c) {
+    if (corner_seen[c]) continue;
+    uint32_t v = corner_vertex[c];
+    bool split = false;
+    if (vertex_seen[v]) {
+      left_most.push_back(kNone);
+      vertex_seen.push_back(0);
+      v = num_vertices++;
+      split = true;
+    }
+    vertex_seen[v] = 1;
+    corner_seen[c] = 1;
+    left_most[v] = c;
+    if (split) corner_vertex[c] = v;
+    uint32_t a = swing_left(c);
+    while (a != kNone && a != c) {
+      corner_seen[a] = 1;
+      left_most[v] = a;
+      if (split) corner_vertex[a] = v;
+      a = swing_left(a);
+    }
+    if (a == kNone) {  // open fan: mark the corners to the right as well
+      for (a = c; a != kNone; a = swing_right(a)) {
+        corner_seen[a] = 1;
+        if (split) corner_vertex[a] = v;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// AttributeCornerTable::new + recompute_vertices — attribute_corner_table.rs:16-137
+void SeamTable::build(const UniversalTable& ut, const AttrView& att) {
+  const uint32_t C = ut.num_corners;
+  seam.assign(C, 0);
+  std::vector<uint8_t> vertex_on_seam(ut.num_vertices, 0);
+  const uint32_t* pt = ut.corner_point;
+  const uint32_t* cv = ut.corner_vertex.data();
+  auto val = [&](uint32_t corner) {
+    const uint32_t p = pt[corner];
+    if (p >= att.num_points) throw Error(DXO_ERR_INVALID_ARGUMENT, "face references a point outside an attribute");
+    return att.value_of(p);
+  };
+  for (uint32_t c = 0; c < C; ++c) {
+    const uint32_t o = ut.opposite[c];
+    if (o == kNone) {  // mesh boundary counts as a seam
+      seam[c] = 1;
+      vertex_on_seam[cv[corner_next(c)]] = 1;
+      vertex_on_seam[cv[corner_prev(c)]] = 1;
+      continue;
+    }
+    if (o < c) continue;
+    // the two end points of the shared edge must carry the same values on both faces
+    const uint32_t cn = corner_next(c), cp = corner_prev(c), on = corner_next(o), op = corner_prev(o);
+    if (val(cn) != val(op) || val(cp) != val(on)) {
+      seam[c] = seam[o] = 1;
+      vertex_on_seam[cv[cn]] = vertex_on_seam[cv[cp]] = 1;
+      vertex_on_seam[cv[on]] = vertex_on_seam[cv[op]] = 1;
+    }
+  }
+  auto a_opp = [&](uint32_t c) { return seam[c] ? kNone : ut.opposite[c]; };
+  auto a_swing_left = [&](uint32_t c) { const uint32_t o = a_opp(corner_next(c)); return o == kNone ? kNone : corner_next(o); };
+
+  corner_vertex.assign(C, 0);
+  left_most.clear();
+  left_most.reserve(ut.num_vertices);
+  uint32_t next_id = 0;
+  for (uint32_t v = 0; v < ut.num_vertices; ++v) {
+    const uint32_t c = ut.left_most[v];
+    uint32_t id = next_id++;
+    uint32_t first = c;
+    if (vertex_on_seam[v]) {  // rotate to the first corner after a seam, counter-clockwise
+      for (uint32_t s = a_swing_left(first); s != kNone; s = a_swing_left(s)) {
+        first = s;
+        if (s == c) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "seam vertex whose fan closes on itself");
+      }
+    }
+    corner_vertex[first] = id;
+    left_most.push_back(first);
+    for (uint32_t s = ut.swing_right(first); s != kNone && s != first; s = ut.swing_right(s)) {
+      if (seam[corner_next(s)]) {  // crossing a seam starts a new attribute vertex
+        id = next_id++;
+        left_most.push_back(s);
+      }
+      corner_vertex[s] = id;
+    }
+  }
+  num_vertices = next_id;
+}
+
+// ---------------------------------------------------------------------------------------
+// Edgebreaker — encode/connectivity/edgebreaker.rs
+namespace {
+
+enum : uint8_t { kC = 0, kS = 1, kL = 2, kR = 3, kE = 4 };
+
+struct SplitEvent { uint64_t merge_symbol, split_symbol; uint8_t right; };
+
+class EdgebreakerRun {
+ public:
+  EdgebreakerRun(const UniversalTable& ut, const std::vector<SeamTable>& seams) : ut_(ut), seams_(seams) {
+    vertex_done_.assign(ut.num_vertices, 0);
+    face_done_.assign(ut.num_faces, 0);
+    split_symbol_of_face_.assign(ut.num_faces, kNoSymbol);
+  }
+
+  std::vector<uint32_t> run(ByteSink& w) {
+    w.u8(0);  // EdgebreakerKind::Standard (:467)
+    find_boundaries();
+    w.varint(ut_.num_vertices);
+    w.varint(ut_.num_faces);
+    w.u8((uint8_t)seams_.size());
+    for (uint32_t c = 0; c < ut_.num_corners; ++c) {  // one traversal per connected component (:478-511)
+      const uint32_t face = c / 3u;
+      if (face_done_[face]) continue;
+      bool interior;
+      const uint32_t start = start_corner(face, interior);
+      start_face_interior_.push_back(interior ? 1 : 0);
+      if (interior) {
+        vertex_done_[vtx(start)] = vertex_done_[vtx(corner_next(start))] = vertex_done_[vtx(corner_prev(start))] = 1;
+        face_done_[face] = 1;
+        init_face_corners_.push_back(corner_next(start));
+        const uint32_t o = ut_.opposite[corner_next(start)];
+        if (o == kNone) throw Error(DXO_ERR_INTERNAL, "interior start face without neighbour");
+        traverse(o);
+      } else {
+        walk_boundary(corner_next(start), true);
+        traverse(start);
+      }
+    }
+    w.varint(symbols_.size());
+    w.varint(num_splits_);
+    write_split_events(w);
+    write_symbols_and_side_streams(w);
+    std::vector<uint32_t> out(init_face_corners_.rbegin(), init_face_corners_.rend());
+    out.insert(out.end(), visit_order_.begin(), visit_order_.end());
+    return out;
+  }
+
+ private:
+  static constexpr uint64_t kNoSymbol = ~(uint64_t)0;
+  const UniversalTable& ut_;
+  const std::vector<SeamTable>& seams_;
+  std::vector<uint8_t> vertex_done_, face_done_, hole_done_, symbols_, start_face_interior_;
+  std::vector<uint32_t> hole_of_vertex_, stack_, visit_order_, init_face_corners_;
+  std::vector<uint64_t> split_symbol_of_face_;
+  std::vector<SplitEvent> split_events_;
+  uint64_t symbol_index_ = ~(uint64_t)0;  // usize::MAX, incremented with wrap before use (:150,:276)
+  uint64_t num_splits_ = 0;
+
+  uint32_t vtx(uint32_t c) const { return ut_.corner_vertex[c]; }
+  uint32_t right_of(uint32_t c) const { return ut_.opposite[corner_next(c)]; }
+  uint32_t left_of(uint32_t c) const { return ut_.opposite[corner_prev(c)]; }
+
+  // compute_boundaries — :195-224. The inner walk advances with next(c) inside the face
+  // (not through the opposite corner), so in practice each boundary edge opens a new hole id.
+  void find_boundaries() {
+    hole_of_vertex_.assign(ut_.num_vertices, kNone);
+    for (uint32_t c0 = 0; c0 < ut_.num_corners; ++c0) {
+      if (ut_.opposite[c0] != kNone) continue;
+      uint32_t v = vtx(corner_next(c0));
+      if (hole_of_vertex_[v] != kNone) continue;
+      const uint32_t id = (uint32_t)hole_done_.size();
+      hole_done_.push_back(0);
+      uint32_t c = c0;
+      while (hole_of_vertex_[v] == kNone) {
+        hole_of_vertex_[v] = id;
+        c = corner_next(c);
+        while (ut_.opposite[c] != kNone) c = corner_next(c);
+        v = vtx(corner_next(c));
+      }
+    }
+  }
+
+  // process_boundary — :226-256
+  void walk_boundary(uint32_t start, bool mark_first) {
+    uint32_t c = corner_prev(start);
+    for (uint32_t o; (o = ut_.opposite[c]) != kNone;) c = corner_next(o);
+    const uint32_t v0 = vtx(start);
+    if (mark_first) vertex_done_[v0] = 1;
+    if (hole_of_vertex_[v0] == kNone) throw Error(DXO_ERR_INTERNAL, "boundary walk from a vertex that is not on a hole");
+    hole_done_[hole_of_vertex_[v0]] = 1;
+    for (uint32_t v = vtx(corner_prev(c)); v != v0; v = vtx(corner_prev(c))) {
+      vertex_done_[v] = 1;
+      c = corner_next(c);
+      for (uint32_t o; (o = ut_.opposite[c]) != kNone;) c = corner_next(o);
+    }
+  }
+
+  // begin_from — :411-431
+  uint32_t start_corner(uint32_t face, bool& interior) const {
+    uint32_t c = 3u * face;
+    for (int k = 0; k < 3; ++k, c = corner_next(c)) {
+      if (ut_.opposite[c] == kNone) { interior = false; return c; }
+      if (hole_of_vertex_[vtx(c)] != kNone) {
+        for (uint32_t r = c; r != kNone; r = ut_.swing_right(r)) c = r;
+        interior = false;
+        return corner_prev(c);
+      }
+    }
+    interior = true;
+    return c;
+  }
+
+  void note_split_event(uint8_t right, uint32_t neighbour_corner) {  // check_and_store_topology_split_event — :434-448
+    if (neighbour_corner == kNone) return;
+    const uint64_t s = split_symbol_of_face_[neighbour_corner / 3u];
+    if (s != kNoSymbol) split_events_.push_back({symbol_index_, s, right});
+  }
+
+  // edgebreaker_from — :261-350
+  void traverse(uint32_t c) {
+    stack_.clear();
+    stack_.push_back(c);
+    const uint64_t face_budget = ut_.num_faces;
+    while (!stack_.empty()) {
+      c = stack_.back();
+      if (face_done_[c / 3u]) { stack_.pop_back(); continue; }
+      for (uint64_t n = 0; n < face_budget; ++n) {
+        ++symbol_index_;
+        const uint32_t face = c / 3u;
+        face_done_[face] = 1;
+        visit_order_.push_back(c);
+        const uint32_t v = vtx(c);
+        if (!vertex_done_[v]) {
+          vertex_done_[v] = 1;
+          if (hole_of_vertex_[v] == kNone) {
+            symbols_.push_back(kC);
+            c = right_of(c);
+            if (c == kNone) throw Error(DXO_ERR_INTERNAL, "C symbol without a right neighbour");
+            continue;
+          }
+        }
+        const uint32_t rc = right_of(c), lc = left_of(c);
+        const bool right_done = rc == kNone || face_done_[rc / 3u];
+        const bool left_done = lc == kNone || face_done_[lc / 3u];
+        if (right_done) {
+          note_split_event(1, rc);
+          if (left_done) {
+            note_split_event(0, lc);
+            symbols_.push_back(kE);
+            stack_.pop_back();
+            break;
+          }
+          symbols_.push_back(kR);
+          c = lc;
+        } else if (left_done) {
+          note_split_event(0, lc);
+          symbols_.push_back(kL);
+          c = rc;
+        } else {
+          symbols_.push_back(kS);
+          ++num_splits_;
+          const uint32_t hole = hole_of_vertex_[v];
+          if (hole != kNone && !hole_done_[hole]) walk_boundary(c, false);
+          split_symbol_of_face_[face] = symbol_index_;
+          stack_.back() = lc;
+          stack_.push_back(rc);
+          break;
+        }
+      }
+    }
+  }
+
+  void write_split_events(ByteSink& w) const {  // encode_topology_splits — :375-403
+    w.varint(split_events_.size());
+    uint64_t last = 0;
+    for (const SplitEvent& e : split_events_) {
+      w.varint(e.merge_symbol - last);
+      w.varint(e.merge_symbol - e.split_symbol);
+      last = e.merge_symbol;
+    }
+    BitPacker bits(w);
+    for (const SplitEvent& e : split_events_) bits.put(1, e.right);
+    bits.finish();
+  }
+
+  // DefaultTraversal::encode — :575-656
+  void write_symbols_and_side_streams(ByteSink& w) const {
+    {  // CLERS codes, last symbol first, LSB-first bit packing (symbol_encoder.rs:50-58)
+      static const uint8_t kBits[5] = {1, 3, 3, 3, 3};
+      static const uint8_t kCode[5] = {0b0, 0b001, 0b011, 0b101, 0b111};
+      ByteSink tmp;
+      tmp.data.reserve(symbols_.size() / 3 + 8);
+      BitPacker bits(tmp);
+      for (size_t i = symbols_.size(); i-- > 0;) bits.put(kBits[symbols_[i]], kCode[symbols_[i]]);
+      bits.finish();
+      w.varint(tmp.size());
+      w.bytes(tmp.data);
+    }
+    {  // start-face configurations (:592-607)
+      uint64_t zeros = 0;
+      for (uint8_t b : start_face_interior_) zeros += b ? 0 : 1;
+      const uint8_t p0 = side_stream_zero_prob(zeros, (float)start_face_interior_.size());
+      write_side_stream(start_face_interior_.data(), start_face_interior_.size(), true, p0, w);
+    }
+    // attribute seams, one stream per non-position attribute (:610-653)
+    std::vector<uint8_t> face_seen(ut_.num_faces, 0);
+    std::vector<std::vector<uint8_t>> flags(seams_.size());
+    for (auto& f : flags) f.reserve(ut_.num_corners / 2);
+    for (size_t i = visit_order_.size(); i-- > 0;) {
+      const uint32_t c = visit_order_[i];
+      const uint32_t tri[3] = {c, corner_next(c), corner_prev(c)};
+      face_seen[c / 3u] = 1;
+      for (uint32_t k : tri) {
+        const uint32_t o = ut_.opposite[k];
+        if (o == kNone || face_seen[o / 3u]) continue;
+        for (size_t a = 0; a < seams_.size(); ++a) flags[a].push_back(seams_[a].seam[k]);
+      }
+    }
+    for (auto& f : flags) {
+      uint64_t zeros = 0;
+      for (uint8_t b : f) zeros += b ? 0 : 1;
+      const uint8_t p0 = side_stream_zero_prob(zeros, (float)f.size());
+      write_side_stream(f.data(), f.size(), true, p0, w);
+    }
+  }
+};
+
+}  // namespace
+
+std::vector<uint32_t> encode_edgebreaker(const UniversalTable& ut, const std::vector<SeamTable>& seams, ByteSink& w) {
+  if (seams.size() > 255) throw Error(DXO_ERR_TOO_MANY_ATTRIBUTES, "too many connectivity attributes");
+  EdgebreakerRun r(ut, seams);
+  return r.run(w);
+}
+
+// ---------------------------------------------------------------------------------------
+// Traverser::compute_seqeunce — shared/attribute/sequence.rs:48-151.
+// The reference also deletes stack entries of the face it has just finished
+// (:98-131). Such entries can only be popped later, when the face is already marked
+// visited, and are dropped at :56-58 before they have any effect — so they are simply
+// left on the stack here (lazy deletion, identical output).
+std::vector<uint32_t> attribute_sequence(const TableRef& t, const std::vector<uint32_t>& corners_of_edgebreaker) {
+  std::vector<uint8_t> vertex_seen(t.num_vertices, 0), face_seen(t.num_faces, 0);
+  std::vector<uint32_t> stack(corners_of_edgebreaker), out;
+  out.reserve(t.num_vertices);
+  const uint32_t* cv = t.corner_vertex;
+  auto emit = [&](uint32_t v, uint32_t c) { if (!vertex_seen[v]) { out.push_back(c); vertex_seen[v] = 1; } };
+  while (!stack.empty()) {
+    const uint32_t c = stack.back();
+    stack.pop_back();
+    const uint32_t face = c / 3u;
+    if (face_seen[face]) continue;
+    const uint32_t nc = corner_next(c), pc = corner_prev(c);
+    const uint32_t v = cv[c], nv = cv[nc], pv = cv[pc];
+    if (!vertex_seen[nv] || !vertex_seen[pv]) {  // first face of a component: next, prev, then the tip
+      emit(nv, nc);
+      emit(pv, pc);
+      stack.push_back(c);
+      continue;
+    }
+    face_seen[face] = 1;
+    if (!vertex_seen[v]) {
+      emit(v, c);
+      // is_on_boundary(v): swing_left(left_most_corner(v)) is None (corner_table/mod.rs:36-38)
+      const uint32_t lm = t.left_most[v];
+      const uint32_t o = t.opp(corner_next(lm));
+      if (o != kNone) {  // interior vertex: keep going to the right
+        const uint32_t r = t.opp(nc);
+        if (r == kNone) throw Error(DXO_ERR_INTERNAL, "sequencer: interior vertex without right neighbour");
+        stack.push_back(r);
+        continue;
+      }
+    }
+    const uint32_t rc = t.opp(nc), lc = t.opp(pc);
+    const bool right_seen = rc != kNone && face_seen[rc / 3u];
+    const bool left_seen = lc != kNone && face_seen[lc / 3u];
+    if (right_seen) {
+      if (!left_seen && lc != kNone) stack.push_back(lc);
+    } else if (left_seen) {
+      if (rc != kNone) stack.push_back(rc);
+    } else {
+      if (lc != kNone) stack.push_back(lc);
+      if (rc != kNone) stack.push_back(rc);
+    }
+  }
+  return out;
+}
+
+}  // namespace dxo

@@ -1,0 +1,77 @@
+// Product host code — connectivity side of encode(): corner tables, per-attribute
+// seam tables, the Edgebreaker CLERS traversal and the attribute sequencer.
+// north_star keeps these pointer-chasing passes on the host; everything here is
+// flat uint32 arrays (no maps, no per-face vectors) so the device uploads are
+// plain memcpys of the same buffers.
+//
+// Reference paths are relative to /root/reference/draco-oxide/src/.
+#pragma once
+#include <algorithm>
+#include "common.hpp"
+
+namespace dxo {
+
+// Validated, borrowed view of one dxo_attribute.
+struct AttrView {
+  const dxo_attribute* raw = nullptr;
+  uint32_t num_points = 0;   // Attribute::len()
+  uint32_t num_unique = 0;
+  const uint32_t* map = nullptr;  // nullptr = identity
+  uint32_t value_of(uint32_t point) const { return map ? map[point] : point; }
+};
+
+// Universal (position) corner table — CornerTable, core/corner_table/mod.rs:54-529.
+struct UniversalTable {
+  uint32_t num_faces = 0, num_corners = 0, num_vertices = 0;
+  const uint32_t* corner_point = nullptr;  // faces, 3 per face (borrowed)
+  std::vector<uint32_t> corner_vertex;     // vertex_idx(c), non-manifold splits applied
+  std::vector<uint32_t> opposite;          // kNone = boundary
+  std::vector<uint32_t> left_most;         // per vertex
+
+  uint32_t swing_left(uint32_t c) const { uint32_t o = opposite[corner_next(c)]; return o == kNone ? kNone : corner_next(o); }
+  uint32_t swing_right(uint32_t c) const { uint32_t o = opposite[corner_prev(c)]; return o == kNone ? kNone : corner_prev(o); }
+
+  void build(const uint32_t* faces, uint32_t nfaces, const AttrView& pos);
+
+ private:
+  void match_half_edges();
+  bool has_non_manifold_edge() const;
+  void break_non_manifold_edges();
+  void assign_left_most_corners();
+};
+
+// Per-attribute seam table — AttributeCornerTable, core/corner_table/attribute_corner_table.rs:4-192.
+struct SeamTable {
+  uint32_t num_vertices = 0;
+  std::vector<uint32_t> corner_vertex;  // attribute vertex of each corner
+  std::vector<uint8_t> seam;            // edge opposite to the corner is a seam (or boundary)
+  std::vector<uint32_t> left_most;      // per attribute vertex
+  void build(const UniversalTable& ut, const AttrView& att);
+};
+
+// What the traversal-order consumers need from either kind of table
+// (GenericCornerTable, core/corner_table/mod.rs:8-52).
+struct TableRef {
+  uint32_t num_faces, num_corners, num_vertices;
+  const uint32_t* corner_vertex;
+  const uint32_t* opposite;   // universal opposites
+  const uint8_t* seam;        // nullptr for the universal table
+  const uint32_t* left_most;
+  uint32_t opp(uint32_t c) const { return (seam && seam[c]) ? kNone : opposite[c]; }
+};
+inline TableRef table_ref(const UniversalTable& u) {
+  return {u.num_faces, u.num_corners, u.num_vertices, u.corner_vertex.data(), u.opposite.data(), nullptr, u.left_most.data()};
+}
+inline TableRef table_ref(const UniversalTable& u, const SeamTable& s) {
+  return {u.num_faces, u.num_corners, s.num_vertices, s.corner_vertex.data(), u.opposite.data(), s.seam.data(), s.left_most.data()};
+}
+
+// Edgebreaker<DefaultTraversal>::encode_connectivity — encode/connectivity/edgebreaker.rs:458-657.
+// Appends the connectivity section to `w` and returns corners_of_edgebreaker.
+std::vector<uint32_t> encode_edgebreaker(const UniversalTable& ut, const std::vector<SeamTable>& seams, ByteSink& w);
+
+// Traverser::compute_seqeunce — shared/attribute/sequence.rs:48-151.
+// One corner per attribute vertex, in the order the decoder will reconstruct them.
+std::vector<uint32_t> attribute_sequence(const TableRef& t, const std::vector<uint32_t>& corners_of_edgebreaker);
+
+}  // namespace dxo

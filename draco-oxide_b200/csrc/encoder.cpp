@@ -1,0 +1,506 @@
+// Product host code — see encoder.hpp. Mirrors the order of operations of
+// encode::encode (encode/mod.rs:59-97), encode_attributes (encode/attribute/mod.rs:13-93)
+// and AttributeEncoder (encode/attribute/attribute_encoder.rs:158-389); the per-element
+// loops of the latter run as CUDA kernels (kernels.cu). No CPU implementation of those
+// loops exists in this library: without a device the job fails.
+#include "encoder.hpp"
+
+#include <algorithm>
+#include <cmath>
+
+namespace dxo {
+
+void cuda_check(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return;
+  const int st = (e == cudaErrorMemoryAllocation) ? DXO_ERR_OUT_OF_MEMORY
+               : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) ? DXO_ERR_NO_DEVICE
+               : DXO_ERR_CUDA;
+  throw Error(st, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+DeviceContext& DeviceContext::get(int device) {
+  static thread_local std::map<int, std::unique_ptr<DeviceContext>> ctxs;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    throw Error(DXO_ERR_NO_DEVICE, "no CUDA device available (this path has no CPU fallback)");
+  }
+  if (device < 0) cuda_check(cudaGetDevice(&device), "cudaGetDevice");
+  if (device >= count) throw Error(DXO_ERR_NO_DEVICE, "CUDA device ordinal out of range");
+  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  auto it = ctxs.find(device);
+  if (it != ctxs.end()) return *it->second;
+  auto c = std::make_unique<DeviceContext>();
+  c->device = device;
+  for (auto& s : c->stream) cuda_check(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
+  cuda_check(cudaEventCreate(&c->ev_begin), "cudaEventCreate");
+  cuda_check(cudaEventCreate(&c->ev_end), "cudaEventCreate");
+  cuda_check(cudaEventCreateWithFlags(&c->ev_pos_ready, cudaEventDisableTiming), "cudaEventCreate");
+  for (auto& ev : c->ev_join) cuda_check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate");
+  // keep freed blocks in the stream-ordered pool: repeated encodes reuse them without cudaMalloc
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  DeviceContext& ref = *c;
+  ctxs[device] = std::move(c);
+  return ref;
+}
+
+cudaEvent_t Profile::take() {
+  if (pool_used == pool.size()) { cudaEvent_t e; cuda_check(cudaEventCreate(&e), "cudaEventCreate"); pool.push_back(e); }
+  return pool[pool_used++];
+}
+void Profile::begin(const char* name, uint64_t bytes, cudaStream_t s) {
+  ++launches;
+  if (!enabled) return;
+  KernelRecord r{name, bytes, take(), take()};
+  cuda_check(cudaEventRecord(r.a, s), "cudaEventRecord");
+  records.push_back(r);
+}
+void Profile::end(cudaStream_t s) {
+  if (!enabled) return;
+  cuda_check(cudaEventRecord(records.back().b, s), "cudaEventRecord");
+}
+Profile::~Profile() { for (cudaEvent_t e : pool) cudaEventDestroy(e); }
+
+// ---------------------------------------------------------------------------------------
+namespace {
+
+size_t component_size(uint32_t ct) {
+  switch (ct) {
+    case DXO_U8: case DXO_I8: return 1;
+    case DXO_U16: case DXO_I16: return 2;
+    case DXO_U32: case DXO_I32: case DXO_F32: return 4;
+    case DXO_U64: case DXO_I64: case DXO_F64: return 8;
+    default: return 0;
+  }
+}
+
+int status_from_flags(uint32_t f) {
+  if (f & gpu::kErrZeroNormal) return DXO_ERR_ZERO_NORMAL;
+  if (f & gpu::kErrNegativeSymbol) return DXO_ERR_RANS_INVALID_SYMBOL;
+  if (f & gpu::kErrRansFreq) return DXO_ERR_RANS_FREQ_TABLE;
+  if (f & gpu::kErrRansState) return DXO_ERR_RANS_STATE_TOO_LARGE;
+  if (f & (gpu::kErrAlphabet | gpu::kErrFanWalk)) return DXO_ERR_UNSUPPORTED_INPUT;
+  return DXO_OK;
+}
+
+}  // namespace
+
+MeshJob::MeshJob(const dxo_mesh* mesh, const dxo_config& cfg) : mesh_(mesh), cfg_(cfg) {
+  if (!mesh || (mesh->num_faces && !mesh->faces) || (mesh->num_attributes && !mesh->attributes))
+    throw Error(DXO_ERR_INVALID_ARGUMENT, "null mesh / faces / attributes");
+  if (mesh->num_faces == 0 || mesh->num_faces > 0x55555554ull) throw Error(DXO_ERR_INVALID_ARGUMENT, "face count must be in [1, 2^32/3)");
+  if (mesh->num_attributes == 0 || mesh->attributes[0].att_type != DXO_ATT_POSITION)
+    throw Error(DXO_ERR_UNSUPPORTED_INPUT, "attributes[0] must be the position attribute");  // edgebreaker.rs:132-134 unwrap
+  if (mesh->num_attributes > 255) throw Error(DXO_ERR_TOO_MANY_ATTRIBUTES, "too many attributes");
+  auto check_bits = [](uint32_t b) { if (b < 1 || b > 20) throw Error(DXO_ERR_INVALID_ARGUMENT, "quantization bits must be in [1, 20]"); };
+  check_bits(cfg.position_bits); check_bits(cfg.texcoord_bits); check_bits(cfg.generic_bits);
+
+  plans_.resize(mesh->num_attributes);
+  for (uint32_t i = 0; i < mesh->num_attributes; ++i) {
+    const dxo_attribute& a = mesh->attributes[i];
+    AttrPlan& p = plans_[i];
+    if (component_size(a.component_type) == 0) throw Error(DXO_ERR_UNSUPPORTED_DATA_TYPE, "unsupported component type");
+    if (a.num_components < 1 || a.num_components > 4) throw Error(DXO_ERR_UNSUPPORTED_NUM_COMPONENTS, "attribute must have 1..4 components");
+    if (!a.values && a.num_unique_values) throw Error(DXO_ERR_INVALID_ARGUMENT, "attribute without values");
+    if (a.num_unique_values == 0 || a.num_unique_values > 0xFFFFFFFEull || a.num_points > 0xFFFFFFFEull)
+      throw Error(DXO_ERR_INVALID_ARGUMENT, "attribute value / point count out of range");
+    if (i > 0 && a.att_type == DXO_ATT_POSITION) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "more than one position attribute");
+    p.view.raw = &a;
+    p.view.num_unique = (uint32_t)a.num_unique_values;
+    p.view.map = a.point_to_value;
+    p.view.num_points = a.point_to_value ? (uint32_t)a.num_points : (uint32_t)a.num_unique_values;  // Attribute::len()
+    p.ncomp_in = a.num_components;
+    // GroupConfig::default_for (attribute_encoder.rs:59-108) + portabilization::Config::default_for (portabilization/mod.rs:116-142)
+    switch (a.att_type) {
+      case DXO_ATT_POSITION: p.scheme = Scheme::Parallelogram; p.transform = Transform::Wrapped; p.port = Portabilization::Quantize; p.bits = cfg.position_bits; break;
+      case DXO_ATT_NORMAL: p.scheme = Scheme::Normal; p.transform = Transform::OctOrthogonal; p.port = Portabilization::Octahedral; p.bits = 8; break;
+      case DXO_ATT_TEXCOORD: p.scheme = Scheme::TexCoord; p.transform = Transform::Wrapped; p.port = Portabilization::Quantize; p.bits = cfg.texcoord_bits; break;
+      case DXO_ATT_CUSTOM: p.scheme = Scheme::Parallelogram; p.transform = Transform::Wrapped; p.port = Portabilization::ToBits; break;
+      default:
+        if (a.att_type > DXO_ATT_WEIGHT) throw Error(DXO_ERR_INVALID_ARGUMENT, "unknown attribute type");
+        p.scheme = Scheme::Delta; p.transform = Transform::Difference; p.port = Portabilization::Quantize; p.bits = cfg.generic_bits; break;
+    }
+    if (p.port == Portabilization::ToBits) {
+      if (component_size(a.component_type) != 4) throw Error(DXO_ERR_UNSUPPORTED_DATA_TYPE, "ToBits attributes must have 4-byte components");
+    } else if (a.component_type != DXO_F32) {
+      throw Error(DXO_ERR_UNSUPPORTED_DATA_TYPE, "quantized attributes must be f32 on this path");
+    }
+    p.ncomp_q = p.port == Portabilization::Octahedral ? 2 : a.num_components;
+    if (p.port == Portabilization::Octahedral && a.num_components != 3) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "normals must have 3 components");
+    if (p.scheme == Scheme::TexCoord && a.num_components != 2) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "texture coordinates must have 2 components");
+    // parents are looked up among already encoded attributes by id (encode/attribute/mod.rs:63-66)
+    if (p.scheme == Scheme::Normal || p.scheme == Scheme::TexCoord) {
+      if (!a.parent_ids || a.num_parents < 1 || (p.scheme == Scheme::Normal && a.num_parents != 1))
+        throw Error(DXO_ERR_UNSUPPORTED_INPUT, "normal / texcoord attributes need a position parent");
+      for (uint32_t j = 0; j < i; ++j) if (mesh->attributes[j].unique_id == a.parent_ids[0]) { p.parent = (int)j; break; }
+      if (p.parent < 0) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "parent attribute must precede its child");
+      const dxo_attribute& par = mesh->attributes[p.parent];
+      if (p.scheme == Scheme::Normal && par.att_type != DXO_ATT_POSITION) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "normal parent must be the position attribute");
+      if (par.num_components != 3 || plans_[p.parent].port != Portabilization::Quantize) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "parent must be a quantized 3-component attribute");
+    }
+    // alphabet bound (DESIGN.md "Histogram capacity")
+    if (p.transform == Transform::OctOrthogonal) p.hist_capacity = 512;
+    else if (p.port == Portabilization::Quantize) p.hist_capacity = (2u << p.bits) + 4u;
+    else {  // ToBits: bound from the raw value range
+      const int32_t* v = (const int32_t*)a.values;
+      int32_t mn = v[0], mx = v[0];
+      const uint64_t cnt = a.num_unique_values * a.num_components;
+      for (uint64_t k = 1; k < cnt; ++k) { mn = std::min(mn, v[k]); mx = std::max(mx, v[k]); }
+      const uint64_t span = (uint64_t)((int64_t)mx - (int64_t)mn) + 1;
+      if (span > (1ull << 22)) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "custom attribute value range too large for the symbol histogram");
+      p.hist_capacity = (uint32_t)(2 * span + 4);
+    }
+  }
+}
+
+MeshJob::~MeshJob() {}
+
+// ---------------------------------------------------------------------------------------
+void MeshJob::build_connectivity() {
+  const uint32_t nfaces = (uint32_t)mesh_->num_faces;
+  // header (encode/header/mod.rs:26-54)
+  for (char ch : std::string("DRACO")) head_.u8((uint8_t)ch);
+  head_.u8(2); head_.u8(2);
+  head_.u8(1);    // EncodedGeometryType::TrianglarMesh
+  head_.u8(1);    // EncoderMethod::Edgebreaker
+  head_.u16(0);   // flags: no metadata
+
+  ut_.build(mesh_->faces, nfaces, plans_[0].view);
+  seams_.resize(plans_.size() - 1);
+  for (size_t i = 1; i < plans_.size(); ++i) seams_[i - 1].build(ut_, plans_[i].view);
+  corners_of_edgebreaker_ = encode_edgebreaker(ut_, seams_, head_);
+
+  // attribute section headers (encode/attribute/mod.rs:26-57)
+  head_.u8((uint8_t)plans_.size());
+  for (size_t i = 0; i < plans_.size(); ++i) {
+    head_.u8((uint8_t)((uint8_t)i - 1u));
+    head_.u8((uint8_t)plans_[i].view.raw->domain);
+    head_.u8(0);  // TraversalType::DepthFirst
+  }
+  for (const AttrPlan& p : plans_) {
+    const dxo_attribute& a = *p.view.raw;
+    head_.u8(1);
+    head_.u8((uint8_t)a.att_type);
+    head_.u8((uint8_t)a.component_type);
+    head_.u8((uint8_t)a.num_components);
+    head_.u8(0);
+    head_.u8((uint8_t)a.unique_id);
+    head_.u8((uint8_t)p.port);
+  }
+
+  // one table view + traversal sequence per attribute (attribute_encoder.rs:236-253)
+  table_refs_.clear();
+  table_refs_.reserve(plans_.size());
+  table_refs_.push_back(table_ref(ut_));
+  for (size_t i = 1; i < plans_.size(); ++i) table_refs_.push_back(table_ref(ut_, seams_[i - 1]));
+  for (size_t i = 0; i < plans_.size(); ++i) {
+    plans_[i].table = &table_refs_[i];
+    plans_[i].sequence = attribute_sequence(table_refs_[i], corners_of_edgebreaker_);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+template <class T> T* MeshJob::dalloc(size_t count, cudaStream_t s) {
+  void* p = nullptr;
+  cuda_check(cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T), s), "cudaMallocAsync");
+  allocations_.push_back(p);
+  return (T*)p;
+}
+template <class T> T* MeshJob::dupload(const T* host, size_t count, cudaStream_t s) {
+  T* d = dalloc<T>(count, s);
+  if (count) cuda_check(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D");
+  h2d_bytes += count * sizeof(T);
+  return d;
+}
+
+void MeshJob::upload(DeviceContext& ctx) {
+  cudaStream_t s = ctx.stream[0];
+  const size_t C = ut_.num_corners;
+  d_faces_ = dupload(mesh_->faces, C, s);
+  d_opposite_ = dupload(ut_.opposite.data(), C, s);
+  d_corner_vertex_ = dupload(ut_.corner_vertex.data(), C, s);
+  d_left_most_ = dupload(ut_.left_most.data(), ut_.left_most.size(), s);
+  dev_.assign(plans_.size(), AttrDevice{});
+  for (size_t i = 0; i < plans_.size(); ++i) {
+    const AttrPlan& p = plans_[i];
+    AttrDevice& d = dev_[i];
+    const dxo_attribute& a = *p.view.raw;
+    const size_t U = p.view.num_unique, M = p.sequence.size();
+    d.values = (float*)dupload((const uint32_t*)a.values, U * p.ncomp_in, s);
+    if (p.view.map) d.map = dupload(p.view.map, p.view.num_points, s);
+    if (i > 0) {
+      const SeamTable& st = seams_[i - 1];
+      d.corner_vertex = dupload(st.corner_vertex.data(), C, s);
+      d.seam = dupload(st.seam.data(), C, s);
+      d.left_most = dupload(st.left_most.data(), st.left_most.size(), s);
+    }
+    d.seq = dupload(p.sequence.data(), M, s);
+    const uint32_t V = p.table->num_vertices;
+    d.quant = p.port == Portabilization::ToBits ? (int32_t*)d.values : dalloc<int32_t>(U * p.ncomp_q, s);
+    d.rank = dalloc<uint32_t>(V, s);
+    d.symbols = dalloc<uint32_t>(M * p.ncomp_q, s);
+    d.side = dalloc<uint8_t>(M, s);
+    d.hist = dalloc<uint32_t>(p.hist_capacity, s);
+    d.work = dalloc<uint32_t>(3 * (size_t)p.hist_capacity, s);
+    d.rans_table = dalloc<uint4>(p.hist_capacity, s);
+    d.table_capacity = 3 * p.hist_capacity + 16;
+    d.table_bytes = dalloc<uint8_t>(d.table_capacity, s);
+    d.payload_capacity = 3 * (uint64_t)M * p.ncomp_q + 16;  // <= P/8 <= 2.5 bytes per symbol + tail
+    d.payload = dalloc<uint8_t>(d.payload_capacity, s);
+    d.stats = dalloc<gpu::AttrStats>(1, s);
+  }
+  cuda_check(cudaEventRecord(ctx.ev_join[0], s), "cudaEventRecord");
+  for (int k = 1; k < 3; ++k) cuda_check(cudaStreamWaitEvent(ctx.stream[k], ctx.ev_join[0], 0), "cudaStreamWaitEvent");
+  uploaded_ = true;
+}
+
+gpu::TableDev MeshJob::table_dev(size_t att) const {
+  gpu::TableDev t;
+  t.corner_point = d_faces_;
+  t.opposite = d_opposite_;
+  t.num_corners = ut_.num_corners;
+  if (att == 0) { t.corner_vertex = d_corner_vertex_; t.seam = nullptr; t.left_most = d_left_most_; t.num_vertices = ut_.num_vertices; }
+  else { t.corner_vertex = dev_[att].corner_vertex; t.seam = dev_[att].seam; t.left_most = dev_[att].left_most; t.num_vertices = seams_[att - 1].num_vertices; }
+  return t;
+}
+
+// Algorithmic bytes per launch follow SURVEY.md §8(d): each distinct input array read
+// once, each output written once.
+void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
+  const uint64_t C = ut_.num_corners;
+  const uint64_t Upos = plans_[0].view.num_unique;
+  for (size_t i = 0; i < plans_.size(); ++i) {
+    const AttrPlan& p = plans_[i];
+    AttrDevice& d = dev_[i];
+    cudaStream_t s = ctx.stream[std::min<size_t>(i, 2)];
+    const uint64_t U = p.view.num_unique, V = p.table->num_vertices;
+    const uint32_t M = (uint32_t)p.sequence.size();
+    const uint64_t S = (uint64_t)M * p.ncomp_q;
+    const gpu::TableDev t = table_dev(i);
+    const gpu::QuantDev q{d.quant, d.map, p.ncomp_q};
+
+    gpu::init_stats(d.stats, s);
+    ++prof.launches;
+    cuda_check(cudaMemsetAsync(d.hist, 0, sizeof(uint32_t) * p.hist_capacity, s), "cudaMemsetAsync");
+    cuda_check(cudaMemsetAsync(d.rank, 0xFF, sizeof(uint32_t) * V, s), "cudaMemsetAsync");
+
+    if (p.port == Portabilization::Quantize) {
+      prof.begin("K1_minmax", 4 * p.ncomp_in * U, s);
+      gpu::launch_minmax(d.values, U, p.ncomp_in, d.stats, s);
+      prof.end(s);
+      prof.begin("K2_quantize", 8 * p.ncomp_in * U, s);
+      gpu::launch_quantize(d.values, U, p.ncomp_in, p.bits, d.quant, d.stats, s);
+      prof.end(s);
+    } else if (p.port == Portabilization::Octahedral) {
+      prof.begin("K3_oct_quantize", 20 * U, s);
+      gpu::launch_oct_quantize(d.values, U, d.quant, d.stats, s);
+      prof.end(s);
+    }
+    if (i == 0) cuda_check(cudaEventRecord(ctx.ev_pos_ready, s), "cudaEventRecord");
+    if (p.parent >= 0) cuda_check(cudaStreamWaitEvent(s, ctx.ev_pos_ready, 0), "cudaStreamWaitEvent");
+
+    const bool wrapped = p.transform == Transform::Wrapped;
+    if (p.scheme == Scheme::Parallelogram || p.scheme == Scheme::TexCoord) {
+      prof.begin("seq_prepare", 4ull * M + 4 * V + (wrapped ? 4ull * p.ncomp_q * U : 0), s);
+      gpu::launch_seq_prepare(d.seq, M, t, q, d.rank, wrapped, d.stats, s);
+      prof.end(s);
+    }
+    switch (p.scheme) {
+      case Scheme::Parallelogram:
+        prof.begin("K4_predict_parallelogram", 4ull * M + 4 * C + 4 * C + 4 * V + 4 * V + 4ull * p.ncomp_q * U + 4 * S, s);
+        gpu::launch_predict_parallelogram(d.seq, M, t, q, d.rank, d.symbols, d.stats, s);
+        prof.end(s);
+        break;
+      case Scheme::Normal: {
+        const AttrDevice& pd = dev_[p.parent];
+        const gpu::QuantDev pos{pd.quant, pd.map, 3};
+        prof.begin("K5_predict_normal", 4ull * M + 4 * C + C + 4 * C + 4 * C + 12 * Upos + 8 * U + 4 * S + M, s);
+        gpu::launch_predict_normal(d.seq, M, t, q, pos, d.symbols, d.side, d.stats, s);
+        prof.end(s);
+        break;
+      }
+      case Scheme::TexCoord: {
+        const AttrDevice& pd = dev_[p.parent];
+        const gpu::QuantDev pos{pd.quant, pd.map, 3};
+        prof.begin("K6_predict_texcoord", 4ull * M + 4 * C + 4 * C + 4 * V + 4 * V + 12 * Upos + 8 * U + 4 * S + M, s);
+        gpu::launch_predict_texcoord(d.seq, M, t, q, pos, plans_[p.parent].view.num_points, d.rank, d.symbols, d.side, d.stats, s);
+        prof.end(s);
+        break;
+      }
+      case Scheme::Delta:
+        prof.begin("K7_predict_delta", 4ull * M + 4 * V + 4ull * p.ncomp_q * U + 4 * S, s);
+        gpu::launch_predict_delta(d.seq, M, t, q, d.symbols, d.stats, s);
+        prof.end(s);
+        break;
+    }
+    prof.begin("K8_histogram", 4 * S, s);
+    gpu::launch_histogram(d.symbols, S, d.hist, p.hist_capacity, d.stats, s);
+    prof.end(s);
+    prof.begin("K9_build_table", 4ull * p.hist_capacity, s);
+    gpu::launch_build_table(d.hist, p.hist_capacity, S, d.work, d.rans_table, d.table_bytes, d.table_capacity, d.stats, s);
+    prof.end(s);
+    prof.begin("K10_rans_encode", 4 * S, s);
+    gpu::launch_rans_encode(d.symbols, S, d.rans_table, d.payload, d.stats, s);
+    prof.end(s);
+  }
+  cuda_check(cudaGetLastError(), "kernel launch");
+}
+
+void MeshJob::download(DeviceContext& ctx) {
+  results_.assign(plans_.size(), AttrResult{});
+  for (size_t i = 0; i < plans_.size(); ++i) {
+    cudaStream_t s = ctx.stream[std::min<size_t>(i, 2)];
+    cuda_check(cudaMemcpyAsync(&results_[i].stats, dev_[i].stats, sizeof(gpu::AttrStats), cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+    d2h_bytes += sizeof(gpu::AttrStats);
+  }
+  for (size_t i = 0; i < plans_.size(); ++i) {
+    cudaStream_t s = ctx.stream[std::min<size_t>(i, 2)];
+    cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    AttrResult& r = results_[i];
+    if (int st = status_from_flags(r.stats.error_flags)) throw Error(st, "device reported an encoding error");
+    if (r.stats.table_bytes > dev_[i].table_capacity || r.stats.payload_bytes > dev_[i].payload_capacity)
+      throw Error(DXO_ERR_INTERNAL, "device output exceeds its buffer");
+    r.table_bytes.resize(r.stats.table_bytes);
+    r.payload.resize(r.stats.payload_bytes);
+    cuda_check(cudaMemcpyAsync(r.table_bytes.data(), dev_[i].table_bytes, r.table_bytes.size(), cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+    cuda_check(cudaMemcpyAsync(r.payload.data(), dev_[i].payload, r.payload.size(), cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+    d2h_bytes += r.table_bytes.size() + r.payload.size();
+    if (plans_[i].scheme == Scheme::Normal || plans_[i].scheme == Scheme::TexCoord) {
+      r.side.resize(plans_[i].sequence.size());
+      cuda_check(cudaMemcpyAsync(r.side.data(), dev_[i].side, r.side.size(), cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+      d2h_bytes += r.side.size();
+    }
+  }
+  for (int k = 0; k < 3; ++k) cuda_check(cudaStreamSynchronize(ctx.stream[k]), "cudaStreamSynchronize");
+  if (trace) capture_trace(ctx);
+}
+
+// ---------------------------------------------------------------------------------------
+void MeshJob::assemble(std::vector<uint8_t>& out) {
+  ByteSink w;
+  size_t total = head_.size() + 64;
+  for (const AttrResult& r : results_) total += r.table_bytes.size() + r.payload.size() + r.side.size() / 4 + 64;
+  w.data.reserve(total);
+  w.bytes(head_.data);
+  for (size_t i = 0; i < plans_.size(); ++i) {
+    const AttrPlan& p = plans_[i];
+    const AttrResult& r = results_[i];
+    w.u8((uint8_t)p.scheme);     // attribute_encoder.rs:159
+    w.u8((uint8_t)p.transform);  // :160
+    w.u8(1);                     // rans_encoding (:344)
+    w.u8(1);                     // SymbolEncodingMethod::DirectCoded (symbol_coding.rs:22)
+    w.u8((uint8_t)r.stats.bit_length);
+    w.bytes(r.table_bytes);      // leb128 #symbols + frequency table (rans.rs:193-230)
+    w.varint(r.payload.size());  // RansSymbolEncoder::flush (rans.rs:248-255)
+    w.bytes(r.payload);
+    // metadata: order depends on the scheme (:362-386)
+    auto transform_info = [&] {
+      if (p.transform == Transform::Wrapped) { w.i32(r.stats.wrap_min); w.i32(r.stats.wrap_max); }   // wrapped_difference.rs:95-96
+      else if (p.transform == Transform::OctOrthogonal) { w.u32(255); w.u32(127); }                  // oct_orthogonal.rs:80-82
+    };
+    if (p.scheme == Scheme::Normal) {
+      transform_info();
+      // flips, in sequence order (mesh_normal_prediction.rs:147-163)
+      uint64_t zeros = 0;
+      for (uint8_t f : r.side) zeros += f ? 0 : 1;
+      const uint8_t p0 = side_stream_zero_prob(zeros, (float)r.side.size());
+      write_side_stream(r.side.data(), r.side.size(), false, p0, w);
+    } else if (p.scheme == Scheme::TexCoord) {
+      // orientation bits exist only where the main branch ran: order-preserving compaction,
+      // then the forward-transition probability / backward-delta bits of :221-260
+      std::vector<uint8_t> orient;
+      orient.reserve(r.side.size());
+      for (uint8_t f : r.side) if (f) orient.push_back(f == 2 ? 1 : 0);
+      uint64_t transitions = 0;
+      { uint8_t last = 1; for (uint8_t o : orient) if (o != last) { last = o; ++transitions; } }
+      const uint8_t p0 = side_stream_zero_prob(transitions, (float)orient.size() + 0.001f);
+      std::vector<uint8_t> bits(orient.size());
+      { uint8_t next = 1; for (size_t k = orient.size(); k-- > 0;) { bits[k] = orient[k] == next ? 1 : 0; next = orient[k]; } }
+      w.u32((uint32_t)orient.size());
+      write_side_stream(bits.data(), bits.size(), false, p0, w);
+      transform_info();
+    } else {
+      transform_info();
+    }
+    // portabilization metadata (:384-386)
+    if (p.port == Portabilization::Quantize) {
+      for (uint32_t k = 0; k < p.ncomp_in; ++k) w.u32(r.stats.vmin_bits[k]);  // min values (quantization_coordinate_wise.rs:57)
+      w.f32(r.stats.range);
+      w.u8((uint8_t)p.bits);
+    } else if (p.port == Portabilization::Octahedral) {
+      w.u8(8);  // octahedral_quantization.rs:40
+    }
+  }
+  out = std::move(w.data);
+}
+
+void MeshJob::release(DeviceContext& ctx) {
+  for (void* p : allocations_) cudaFreeAsync(p, ctx.stream[0]);
+  allocations_.clear();
+  uploaded_ = false;
+}
+
+// Copies intermediate device results back under the same keys / layouts the oracle's
+// trace uses, for stage-by-stage parity tests.
+void MeshJob::capture_host_trace() {
+  auto put = [&](const std::string& key, const void* p, size_t bytes) { auto& v = trace_items[key]; v.assign((const uint8_t*)p, (const uint8_t*)p + bytes); };
+  put("head_bytes", head_.data.data(), head_.data.size());
+  put("opposite", ut_.opposite.data(), ut_.opposite.size() * 4);
+  put("corner_to_vertex", ut_.corner_vertex.data(), ut_.corner_vertex.size() * 4);
+  put("left_most", ut_.left_most.data(), ut_.left_most.size() * 4);
+  { uint64_t nv = ut_.num_vertices; put("num_vertices", &nv, 8); }
+  put("corners_of_edgebreaker", corners_of_edgebreaker_.data(), corners_of_edgebreaker_.size() * 4);
+  for (size_t i = 0; i < plans_.size(); ++i) {
+    const std::string k = "att" + std::to_string(i) + ".";
+    if (i > 0) {
+      put(k + "c2v", seams_[i - 1].corner_vertex.data(), seams_[i - 1].corner_vertex.size() * 4);
+      put(k + "left_most", seams_[i - 1].left_most.data(), seams_[i - 1].left_most.size() * 4);
+      put(k + "seam", seams_[i - 1].seam.data(), seams_[i - 1].seam.size());
+    }
+    put(k + "sequence", plans_[i].sequence.data(), plans_[i].sequence.size() * 4);
+  }
+}
+
+void MeshJob::capture_trace(DeviceContext& ctx) {
+  capture_host_trace();
+
+  auto put = [&](const std::string& key, const void* p, size_t bytes) { auto& v = trace_items[key]; v.assign((const uint8_t*)p, (const uint8_t*)p + bytes); };
+  auto fetch = [&](const std::string& key, const void* dptr, size_t bytes) {
+    auto& v = trace_items[key];
+    v.resize(bytes);
+    if (bytes) cuda_check(cudaMemcpy(v.data(), dptr, bytes, cudaMemcpyDeviceToHost), "cudaMemcpy trace");
+  };
+  (void)ctx;
+  for (size_t i = 0; i < plans_.size(); ++i) {
+    const AttrPlan& p = plans_[i];
+    const AttrResult& r = results_[i];
+    const std::string k = "att" + std::to_string(i) + ".";
+    fetch(k + "quantized", dev_[i].quant, (size_t)p.view.num_unique * p.ncomp_q * 4);
+    fetch(k + "symbols", dev_[i].symbols, p.sequence.size() * p.ncomp_q * 4);
+    {
+      std::vector<uint32_t> h(r.stats.num_table_symbols);
+      if (!h.empty()) cuda_check(cudaMemcpy(h.data(), dev_[i].hist, h.size() * 4, cudaMemcpyDeviceToHost), "cudaMemcpy trace");
+      std::vector<uint64_t> h64(h.begin(), h.end());
+      put(k + "histogram", h64.data(), h64.size() * 8);
+      std::vector<uint32_t> d(r.stats.num_table_symbols);
+      if (!d.empty()) cuda_check(cudaMemcpy(d.data(), dev_[i].work, d.size() * 4, cudaMemcpyDeviceToHost), "cudaMemcpy trace");
+      std::vector<uint64_t> d64(d.begin(), d.end());
+      put(k + "distribution", d64.data(), d64.size() * 8);
+    }
+    put(k + "table_bytes", r.table_bytes.data(), r.table_bytes.size());
+    put(k + "payload", r.payload.data(), r.payload.size());
+    { int32_t mm[2] = {r.stats.wrap_min, r.stats.wrap_max}; put(k + "wrap_minmax", mm, 8); }
+    { uint32_t bl[2] = {r.stats.bit_length, r.stats.precision}; put(k + "bit_length", bl, 8); }
+    std::vector<uint8_t> side;
+    if (p.scheme == Scheme::Normal) side = r.side;
+    else if (p.scheme == Scheme::TexCoord) for (uint8_t f : r.side) if (f) side.push_back(f == 2 ? 1 : 0);
+    put(k + "side_bits", side.data(), side.size());
+  }
+}
+
+}  // namespace dxo

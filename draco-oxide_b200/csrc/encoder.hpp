@@ -1,0 +1,118 @@
+// Product host code — per-mesh encode job: host connectivity, device upload, the
+// attribute kernels, download and stream assembly. See DESIGN.md for the data flow.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <string>
+
+#include "connectivity.hpp"
+#include "kernels.cuh"
+
+namespace dxo {
+
+void cuda_check(cudaError_t e, const char* what);
+
+// One per (host thread, device): streams, events and the launch / timing log.
+struct DeviceContext {
+  int device = 0;
+  cudaStream_t stream[3] = {nullptr, nullptr, nullptr};  // attribute i runs on stream[min(i,2)]
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_pos_ready = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  static DeviceContext& get(int device);  // thread-local; throws DXO_ERR_NO_DEVICE when there is no usable GPU
+};
+
+struct KernelRecord { const char* name; uint64_t bytes; cudaEvent_t a, b; };
+
+struct Profile {
+  bool enabled = false;
+  std::vector<KernelRecord> records;
+  std::vector<cudaEvent_t> pool;
+  size_t pool_used = 0;
+  uint32_t launches = 0;
+  cudaEvent_t take();
+  void begin(const char* name, uint64_t bytes, cudaStream_t s);
+  void end(cudaStream_t s);
+  void reset() { records.clear(); pool_used = 0; launches = 0; }
+  ~Profile();
+};
+
+enum class Scheme : uint8_t { Delta = 0, Parallelogram = 1, TexCoord = 5, Normal = 6 };           // prediction_scheme/mod.rs:74-86
+enum class Transform : uint8_t { Difference = 0, Wrapped = 1, OctOrthogonal = 3 };                // prediction_transform/mod.rs:92-102
+enum class Portabilization : uint8_t { ToBits = 1, Quantize = 2, Octahedral = 3 };                // portabilization/mod.rs:85-92
+
+struct AttrPlan {
+  AttrView view;
+  Scheme scheme;
+  Transform transform;
+  Portabilization port;
+  uint32_t bits = 0;          // quantization bits
+  uint32_t ncomp_in = 0;      // components of the original values
+  uint32_t ncomp_q = 0;       // components after portabilization
+  int parent = -1;            // index of the position attribute this one predicts from
+  uint32_t hist_capacity = 0; // upper bound of the alphabet
+  const TableRef* table = nullptr;
+  std::vector<uint32_t> sequence;
+};
+
+struct AttrDevice {
+  // inputs
+  float* values = nullptr; uint32_t* map = nullptr;
+  uint32_t *corner_vertex = nullptr, *left_most = nullptr, *seq = nullptr; uint8_t* seam = nullptr;
+  // intermediates / outputs
+  int32_t* quant = nullptr; uint32_t *rank = nullptr, *symbols = nullptr, *hist = nullptr, *work = nullptr;
+  uint8_t *side = nullptr, *table_bytes = nullptr, *payload = nullptr; uint4* rans_table = nullptr;
+  gpu::AttrStats* stats = nullptr;
+  uint64_t payload_capacity = 0; uint32_t table_capacity = 0;
+};
+
+struct AttrResult {
+  gpu::AttrStats stats;
+  std::vector<uint8_t> table_bytes, payload, side;
+};
+
+class MeshJob {
+ public:
+  MeshJob(const dxo_mesh* mesh, const dxo_config& cfg);
+  ~MeshJob();
+  // phase 1: host only — corner tables, Edgebreaker bytes, attribute sequences
+  void build_connectivity();
+  // phase 2: device
+  void upload(DeviceContext& ctx);
+  void launch(DeviceContext& ctx, Profile& prof);
+  void download(DeviceContext& ctx);  // D2H of stats, tables, payloads, side bits (synchronises)
+  // phase 3: host — assemble the Draco stream
+  void assemble(std::vector<uint8_t>& out);
+  void release(DeviceContext& ctx);
+
+  bool trace = false;
+  std::map<std::string, std::vector<uint8_t>> trace_items;
+  uint64_t h2d_bytes = 0, d2h_bytes = 0;
+  uint64_t num_position_vertices() const { return plans_.empty() ? 0 : plans_[0].sequence.size(); }
+
+ private:
+  const dxo_mesh* mesh_;
+  dxo_config cfg_;
+  std::vector<AttrPlan> plans_;
+  UniversalTable ut_;
+  std::vector<SeamTable> seams_;
+  std::vector<TableRef> table_refs_;
+  ByteSink head_;  // header + connectivity + attribute section headers
+  std::vector<uint32_t> corners_of_edgebreaker_;
+  // device
+  uint32_t *d_faces_ = nullptr, *d_opposite_ = nullptr, *d_corner_vertex_ = nullptr, *d_left_most_ = nullptr;
+  std::vector<AttrDevice> dev_;
+  std::vector<AttrResult> results_;
+  std::vector<void*> allocations_;
+  bool uploaded_ = false;
+
+  template <class T> T* dalloc(size_t count, cudaStream_t s);
+  template <class T> T* dupload(const T* host, size_t count, cudaStream_t s);
+  gpu::TableDev table_dev(size_t att) const;
+  void capture_trace(DeviceContext& ctx);
+ public:
+  void capture_host_trace();  // host-side results only (no device needed)
+  bool has_device_buffers() const { return uploaded_; }
+};
+
+}  // namespace dxo

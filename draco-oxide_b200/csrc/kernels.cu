@@ -1,0 +1,982 @@
+// Attribute hot path kernels for sm_100a (B200). Hand-written CUDA; compiled with
+// -fmad=false (no FMA contraction) and default IEEE division/sqrt so that integer
+// outputs are bit-identical to the reference's Rust arithmetic.
+//
+// Every kernel cites the reference loop it replaces (paths relative to
+// /root/reference/draco-oxide/src/). None of this work is a dense contraction, so
+// tensor cores are not used; the kernels are HBM-bound gathers/streams (K1-K8), one
+// small single-CTA table kernel (K9) and a latency-bound serial coder (K10).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "kernels.cuh"
+
+namespace dxo {
+namespace gpu {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxBlocks = 148 * 8;  // 148 SMs x 8 resident CTAs of 256 threads
+
+inline int grid_for(uint64_t work_items, int per_block = kThreads) {
+  uint64_t b = (work_items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > (uint64_t)kMaxBlocks) b = kMaxBlocks;
+  return (int)b;
+}
+
+__device__ __forceinline__ uint32_t cnext(uint32_t c) { return (c % 3u == 2u) ? c - 2u : c + 1u; }
+__device__ __forceinline__ uint32_t cprev(uint32_t c) { return (c % 3u == 0u) ? c + 2u : c - 1u; }
+
+// streaming loads (read once): bypass L1 allocation
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) { return __ldcs(p); }
+
+__device__ __forceinline__ uint32_t opp_of(const TableDev& t, uint32_t c) {
+  if (t.seam && t.seam[c]) return kNoneDev;
+  return __ldg(t.opposite + c);
+}
+__device__ __forceinline__ uint32_t value_index(const QuantDev& q, uint32_t point) { return q.map ? __ldg(q.map + point) : point; }
+
+// to_positive_i32 — utils/mod.rs:152-158 (wrapping arithmetic)
+__device__ __forceinline__ uint32_t zigzag(int32_t v) {
+  return v >= 0 ? ((uint32_t)v << 1) : ((((uint32_t)(-(v + 1))) << 1) + 1u);
+}
+
+// Block-wide accumulation of (nonzero count, max symbol) into the stats block.
+__device__ __forceinline__ void accumulate_symbol_stats(uint32_t nonzero, uint32_t maxsym, uint32_t errs, AttrStats* stats) {
+  nonzero = __reduce_add_sync(0xFFFFFFFFu, nonzero);
+  maxsym = __reduce_max_sync(0xFFFFFFFFu, maxsym);
+  errs = __reduce_or_sync(0xFFFFFFFFu, errs);
+  __shared__ uint32_t s_nz, s_mx, s_er;
+  if (threadIdx.x == 0) { s_nz = 0; s_mx = 0; s_er = 0; }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+    if (nonzero) atomicAdd(&s_nz, nonzero);
+    if (maxsym) atomicMax(&s_mx, maxsym);
+    if (errs) atomicOr(&s_er, errs);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_nz) atomicAdd(&stats->nonzero_symbols, s_nz);
+    if (s_mx) atomicMax(&stats->max_symbol, s_mx);
+    if (s_er) atomicOr(&stats->error_flags, s_er);
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+__global__ void init_stats_kernel(AttrStats* st) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    for (int k = 0; k < 4; ++k) { st->vmin_bits[k] = 0; st->vmax_bits[k] = 0; }  // +0.0: min and max start at zero
+    st->range = 0.0f;
+    st->wrap_min = 0x7FFFFFFF;
+    st->wrap_max = (int32_t)0x80000000;
+    st->nonzero_symbols = 0; st->max_symbol = 0; st->error_flags = 0;
+    st->bit_length = 0; st->precision = 0; st->num_table_symbols = 0; st->table_bytes = 0; st->payload_bytes = 0;
+  }
+}
+void init_stats(AttrStats* stats, cudaStream_t s) { init_stats_kernel<<<1, 32, 0, s>>>(stats); }
+
+// ---------------------------------------------------------------------------------------
+// K1 — per-component min / max starting from 0 with strict comparisons
+// (quantization_coordinate_wise.rs:28-46). Results are +0.0 or strictly negative
+// (min) / strictly positive (max), so unsigned atomicMax on the bit pattern orders
+// both correctly and never produces -0.0.
+template <int N>
+__global__ void __launch_bounds__(kThreads) minmax_kernel(const float* __restrict__ values, uint64_t num_values, AttrStats* stats) {
+  float mn[N], mx[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) { mn[k] = 0.0f; mx[k] = 0.0f; }
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_values; i += stride) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float c = __ldcs(values + i * N + k);
+      if (c < mn[k]) mn[k] = c;
+      if (c > mx[k]) mx[k] = c;
+    }
+  }
+  __shared__ uint32_t s_mn[N], s_mx[N];
+  if (threadIdx.x < N) { s_mn[threadIdx.x] = 0; s_mx[threadIdx.x] = 0; }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const uint32_t a = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(mn[k]));
+    const uint32_t b = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(mx[k]));
+    if ((threadIdx.x & 31) == 0) { if (a) atomicMax(&s_mn[k], a); if (b) atomicMax(&s_mx[k], b); }
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    if (s_mn[threadIdx.x]) atomicMax(&stats->vmin_bits[threadIdx.x], s_mn[threadIdx.x]);
+    if (s_mx[threadIdx.x]) atomicMax(&stats->vmax_bits[threadIdx.x], s_mx[threadIdx.x]);
+  }
+}
+
+void launch_minmax(const float* values, uint64_t num_values, uint32_t ncomp, AttrStats* stats, cudaStream_t s) {
+  const int g = grid_for(num_values, kThreads * 4);
+  switch (ncomp) {
+    case 1: minmax_kernel<1><<<g, kThreads, 0, s>>>(values, num_values, stats); break;
+    case 2: minmax_kernel<2><<<g, kThreads, 0, s>>>(values, num_values, stats); break;
+    case 3: minmax_kernel<3><<<g, kThreads, 0, s>>>(values, num_values, stats); break;
+    default: minmax_kernel<4><<<g, kThreads, 0, s>>>(values, num_values, stats); break;
+  }
+}
+
+// K2 — q = (i32)(i64)(((v - min) / range) * (2^bits - 1) + 0.5), four separate f32
+// roundings (quantization_coordinate_wise.rs:70-91). One thread per component, flat.
+template <int N>
+__global__ void __launch_bounds__(kThreads) quantize_kernel(const float* __restrict__ values, uint64_t num_components_total, uint32_t bits,
+                                                            int32_t* __restrict__ out, AttrStats* stats) {
+  float mn[N];
+  float range = 0.0f;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    mn[k] = __uint_as_float(stats->vmin_bits[k]);
+    const float d = __uint_as_float(stats->vmax_bits[k]) - mn[k];
+    if (d > range) range = d;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) stats->range = range;
+  const float maxq = (float)(unsigned long long)((1ull << bits) - 1ull);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_components_total; i += stride) {
+    const int k = (int)(i % N);
+    float m = mn[0];
+#pragma unroll
+    for (int j = 1; j < N; ++j) if (k == j) m = mn[j];
+    const float v = __ldcs(values + i);
+    const float diff = v - m;
+    const float normalized = (range == 0.0f) ? diff : (diff / range);
+    const float quantized = normalized * maxq;
+    const float r = quantized + 0.5f;
+    const long long wide = (long long)r;  // cvt.rzi.s64.f32: truncates, saturates, NaN -> 0 (Rust `as i64`)
+    __stcs(out + i, (int32_t)wide);       // wrapping `as i32`
+  }
+}
+
+void launch_quantize(const float* values, uint64_t num_values, uint32_t ncomp, uint32_t bits, int32_t* out, AttrStats* stats, cudaStream_t s) {
+  const uint64_t total = num_values * ncomp;
+  const int g = grid_for(total, kThreads * 4);
+  switch (ncomp) {
+    case 1: quantize_kernel<1><<<g, kThreads, 0, s>>>(values, total, bits, out, stats); break;
+    case 2: quantize_kernel<2><<<g, kThreads, 0, s>>>(values, total, bits, out, stats); break;
+    case 3: quantize_kernel<3><<<g, kThreads, 0, s>>>(values, total, bits, out, stats); break;
+    default: quantize_kernel<4><<<g, kThreads, 0, s>>>(values, total, bits, out, stats); break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Octahedral map of a float vector (geom.rs:57-91) followed by (+1)*127, truncation and
+// the border fix-ups (octahedral_quantization.rs:49-64, geom.rs:137-157).
+__device__ __forceinline__ void oct_quantize_f32(float x, float y, float z, int32_t& qx, int32_t& qy) {
+  const float abs_sum = (fabsf(x) + fabsf(y)) + fabsf(z);
+  float u = y / abs_sum;
+  float v = z / abs_sum;
+  if (x < 0.0f) {
+    const float uo = (u < 0.0f) ? (fabsf(v) - 1.0f) : (1.0f - fabsf(v));
+    const float vo = (v < 0.0f) ? (fabsf(u) - 1.0f) : (1.0f - fabsf(u));
+    u = uo; v = vo;
+  }
+  const float a = (u + 1.0f) * 127.0f;
+  const float b = (v + 1.0f) * 127.0f;
+  int32_t qu = (int32_t)a, qv = (int32_t)b;  // cvt.rzi.s32.f32: truncate, saturate, NaN -> 0 (Rust `as i32`)
+  const int32_t mx = 255, half = 127;
+  if ((qu == 0 && qv == 0) || (qu == mx && qv == 0) || (qu == 0 && qv == mx)) { qx = mx; qy = mx; return; }
+  if (qu == 0 && qv > half) qv = half - (qv - half);
+  else if (qu == mx && qv < half) qv = half + (half - qv);
+  else if (qv == mx && qu < half) qu = half + (half - qu);
+  else if (qv == 0 && qu > half) qu = half - (qu - half);
+  qx = qu; qy = qv;
+}
+
+// K3 — octahedral normal quantization, one thread per unique normal.
+__global__ void __launch_bounds__(kThreads) oct_quantize_kernel(const float* __restrict__ normals, uint64_t n, int32_t* __restrict__ out, AttrStats* stats) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint32_t err = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float x = __ldcs(normals + 3 * i), y = __ldcs(normals + 3 * i + 1), z = __ldcs(normals + 3 * i + 2);
+    int32_t qx = 0, qy = 0;
+    if (x == 0.0f && y == 0.0f && z == 0.0f) err |= kErrZeroNormal;  // reference asserts (geom.rs:45)
+    else oct_quantize_f32(x, y, z, qx, qy);
+    reinterpret_cast<int2*>(out)[i] = make_int2(qx, qy);
+  }
+  if (__any_sync(0xFFFFFFFFu, err != 0) && (threadIdx.x & 31) == 0) atomicOr(&stats->error_flags, kErrZeroNormal);
+}
+
+void launch_oct_quantize(const float* normals, uint64_t num_values, int32_t* out, AttrStats* stats, cudaStream_t s) {
+  oct_quantize_kernel<<<grid_for(num_values, kThreads * 2), kThreads, 0, s>>>(normals, num_values, out, stats);
+}
+
+// ---------------------------------------------------------------------------------------
+// Sequence preparation. rank[v] = index of v in the sequence turns the reference's
+// `vertices_up_till_now.contains(v)` (O(V) scan per element) into `rank[v] < i`
+// (SURVEY Appendix C.1). Also reduces WrappedDifference's min / max over all
+// components of the visited originals (wrapped_difference.rs:41-49).
+__global__ void __launch_bounds__(kThreads) seq_prepare_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q,
+                                                               uint32_t* __restrict__ rank, int want_minmax, AttrStats* stats) {
+  int32_t mn = 0x7FFFFFFF, mx = (int32_t)0x80000000;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t c = ld_stream(seq + i);
+    rank[__ldg(t.corner_vertex + c)] = i;
+    if (want_minmax) {
+      const uint32_t vi = value_index(q, __ldg(t.corner_point + c));
+      for (uint32_t k = 0; k < q.num_components; ++k) {
+        const int32_t o = __ldg(q.values + (uint64_t)vi * q.num_components + k);
+        mn = min(mn, o); mx = max(mx, o);
+      }
+    }
+  }
+  if (want_minmax) {
+    mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&stats->wrap_min, mn); atomicMax(&stats->wrap_max, mx); }
+  }
+}
+
+void launch_seq_prepare(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, uint32_t* rank, bool want_minmax, AttrStats* stats, cudaStream_t s) {
+  seq_prepare_kernel<<<grid_for(n, kThreads * 2), kThreads, 0, s>>>(seq, n, t, q, rank, want_minmax ? 1 : 0, stats);
+}
+
+// ---------------------------------------------------------------------------------------
+// WrappedDifference::squeeze — wrapped_difference.rs:66-94
+struct WrapParams { int32_t mn, mx, max_diff, max_corr, min_corr; };
+__device__ __forceinline__ WrapParams wrap_params(const AttrStats* stats) {
+  WrapParams w;
+  w.mn = stats->wrap_min; w.mx = stats->wrap_max;
+  const int32_t diff = (int32_t)((uint32_t)w.mx - (uint32_t)w.mn);
+  w.max_diff = (int32_t)(1u + (uint32_t)diff);
+  w.max_corr = w.max_diff / 2;
+  w.min_corr = -w.max_corr;
+  if ((w.max_diff & 1) == 0) w.max_corr -= 1;
+  return w;
+}
+__device__ __forceinline__ uint32_t wrapped_symbol(int32_t orig, int32_t pred, const WrapParams& w) {
+  pred = pred < w.mn ? w.mn : (pred > w.mx ? w.mx : pred);
+  const int32_t val = (int32_t)((uint32_t)orig - (uint32_t)pred);
+  int32_t corr = val;
+  if (val > w.max_corr) corr = (int32_t)((uint32_t)val - (uint32_t)w.max_diff);
+  else if (val < w.min_corr) corr = (int32_t)((uint32_t)val + (uint32_t)w.max_diff);
+  return zigzag(corr);
+}
+
+// value of the vertex sequenced just before element i (left_most_corner(last_v)), or zero
+template <int N>
+__device__ __forceinline__ void previous_value(const uint32_t* seq, uint32_t i, const TableDev& t, const QuantDev& q, int32_t* pred) {
+  if (i == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) pred[k] = 0;
+    return;
+  }
+  const uint32_t last_v = __ldg(t.corner_vertex + __ldg(seq + i - 1));
+  const uint32_t lc = __ldg(t.left_most + last_v);
+  const uint32_t vi = value_index(q, __ldg(t.corner_point + lc));
+#pragma unroll
+  for (int k = 0; k < N; ++k) pred[k] = __ldg(q.values + (uint64_t)vi * N + k);
+}
+
+// K4 — MeshParallelogramPrediction::predict (mesh_parallelogram_prediction.rs:186-237)
+// fused with WrappedDifference and zig-zag. One thread per sequence element.
+template <int N>
+__global__ void __launch_bounds__(kThreads) predict_parallelogram_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q,
+                                                                         const uint32_t* __restrict__ rank, uint32_t* __restrict__ symbols, AttrStats* stats) {
+  const WrapParams w = wrap_params(stats);
+  uint32_t nz = 0, mxs = 0, err = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t c = ld_stream(seq + i);
+    int32_t pred[N];
+    bool have = false;
+    const uint32_t o = opp_of(t, c);
+    if (o != kNoneDev) {
+      const uint32_t nc = cnext(c), pc = cprev(c);
+      const uint32_t r0 = __ldg(rank + __ldg(t.corner_vertex + o));
+      const uint32_t r1 = __ldg(rank + __ldg(t.corner_vertex + nc));
+      const uint32_t r2 = __ldg(rank + __ldg(t.corner_vertex + pc));
+      if (r0 < i && r1 < i && r2 < i) {
+        const uint32_t a = value_index(q, __ldg(t.corner_point + nc));
+        const uint32_t b = value_index(q, __ldg(t.corner_point + pc));
+        const uint32_t d = value_index(q, __ldg(t.corner_point + o));
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          pred[k] = (int32_t)((uint32_t)__ldg(q.values + (uint64_t)a * N + k) + (uint32_t)__ldg(q.values + (uint64_t)b * N + k) -
+                              (uint32_t)__ldg(q.values + (uint64_t)d * N + k));
+        have = true;
+      }
+    }
+    if (!have) previous_value<N>(seq, i, t, q, pred);
+    const uint32_t vi = value_index(q, __ldg(t.corner_point + c));
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const uint32_t s = wrapped_symbol(__ldg(q.values + (uint64_t)vi * N + k), pred[k], w);
+      symbols[(uint64_t)i * N + k] = s;
+      nz += s != 0; mxs = max(mxs, s); err |= (s & 0x80000000u) ? kErrNegativeSymbol : 0u;
+    }
+  }
+  accumulate_symbol_stats(nz, mxs, err, stats);
+}
+
+void launch_predict_parallelogram(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, const uint32_t* rank, uint32_t* symbols, AttrStats* stats, cudaStream_t s) {
+  const int g = grid_for(n);
+  switch (q.num_components) {
+    case 1: predict_parallelogram_kernel<1><<<g, kThreads, 0, s>>>(seq, n, t, q, rank, symbols, stats); break;
+    case 2: predict_parallelogram_kernel<2><<<g, kThreads, 0, s>>>(seq, n, t, q, rank, symbols, stats); break;
+    case 3: predict_parallelogram_kernel<3><<<g, kThreads, 0, s>>>(seq, n, t, q, rank, symbols, stats); break;
+    default: predict_parallelogram_kernel<4><<<g, kThreads, 0, s>>>(seq, n, t, q, rank, symbols, stats); break;
+  }
+}
+
+// K7 — DeltaPrediction (delta_prediction.rs:56-71) + Difference (difference.rs:26-34)
+template <int N>
+__global__ void __launch_bounds__(kThreads) predict_delta_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q,
+                                                                 uint32_t* __restrict__ symbols, AttrStats* stats) {
+  uint32_t nz = 0, mxs = 0, err = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t c = ld_stream(seq + i);
+    int32_t pred[N];
+    previous_value<N>(seq, i, t, q, pred);
+    const uint32_t vi = value_index(q, __ldg(t.corner_point + c));
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const uint32_t s = zigzag((int32_t)((uint32_t)__ldg(q.values + (uint64_t)vi * N + k) - (uint32_t)pred[k]));
+      symbols[(uint64_t)i * N + k] = s;
+      nz += s != 0; mxs = max(mxs, s); err |= (s & 0x80000000u) ? kErrNegativeSymbol : 0u;
+    }
+  }
+  accumulate_symbol_stats(nz, mxs, err, stats);
+}
+
+void launch_predict_delta(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, uint32_t* symbols, AttrStats* stats, cudaStream_t s) {
+  const int g = grid_for(n);
+  switch (q.num_components) {
+    case 1: predict_delta_kernel<1><<<g, kThreads, 0, s>>>(seq, n, t, q, symbols, stats); break;
+    case 2: predict_delta_kernel<2><<<g, kThreads, 0, s>>>(seq, n, t, q, symbols, stats); break;
+    case 3: predict_delta_kernel<3><<<g, kThreads, 0, s>>>(seq, n, t, q, symbols, stats); break;
+    default: predict_delta_kernel<4><<<g, kThreads, 0, s>>>(seq, n, t, q, symbols, stats); break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K5 — MeshNormalPrediction::predict (mesh_normal_prediction.rs:77-144) fused with
+// OctahedronOrthogonalTransform (oct_orthogonal.rs:23-74).
+__device__ __forceinline__ void load_pos(const QuantDev& pos, const TableDev& t, uint32_t corner, int32_t* p) {
+  const uint32_t vi = value_index(pos, __ldg(t.corner_point + corner));
+  p[0] = __ldg(pos.values + (uint64_t)vi * 3); p[1] = __ldg(pos.values + (uint64_t)vi * 3 + 1); p[2] = __ldg(pos.values + (uint64_t)vi * 3 + 2);
+}
+// compute_normal_of_face (:22-44): cross product in wrapping i32, then widened.
+__device__ __forceinline__ void add_face_normal(const QuantDev& pos, const TableDev& t, uint32_t c, const int32_t* pc, long long* sum) {
+  int32_t pn[3], pp[3];
+  load_pos(pos, t, cnext(c), pn);
+  load_pos(pos, t, cprev(c), pp);
+  uint32_t dn[3], dp[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { dn[k] = (uint32_t)pn[k] - (uint32_t)pc[k]; dp[k] = (uint32_t)pp[k] - (uint32_t)pc[k]; }
+  sum[0] += (long long)(int32_t)(dn[1] * dp[2] - dn[2] * dp[1]);
+  sum[1] += (long long)(int32_t)(dn[2] * dp[0] - dn[0] * dp[2]);
+  sum[2] += (long long)(int32_t)(dn[0] * dp[1] - dn[1] * dp[0]);
+}
+__device__ __forceinline__ int32_t isign(int32_t a) { return (a > 0) - (a < 0); }
+__device__ __forceinline__ int32_t iabs_wrap(int32_t a) { return a < 0 ? (int32_t)(0u - (uint32_t)a) : a; }
+
+__global__ void __launch_bounds__(kThreads) predict_normal_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos,
+                                                                  uint32_t* __restrict__ symbols, uint8_t* __restrict__ flips, AttrStats* stats) {
+  uint32_t nz = 0, mxs = 0, err = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t c = ld_stream(seq + i);
+    int32_t pc[3];
+    load_pos(pos, t, c, pc);
+    // swing left to the start of the fan (:86-92), then right summing face normals (:94-101)
+    uint32_t cur = c;
+    uint32_t guard = t.num_corners;
+    for (;;) {
+      const uint32_t o = opp_of(t, cnext(cur));
+      if (o == kNoneDev) break;
+      cur = cnext(o);
+      if (cur == c) break;
+      if (--guard == 0) { err |= kErrFanWalk; break; }
+    }
+    const uint32_t start = cur;
+    long long sum[3] = {0, 0, 0};
+    add_face_normal(pos, t, cur, pc, sum);
+    guard = t.num_corners;
+    for (;;) {
+      const uint32_t o = opp_of(t, cprev(cur));
+      if (o == kNoneDev) break;
+      cur = cprev(o);
+      if (cur == start) break;
+      add_face_normal(pos, t, cur, pc, sum);
+      if (--guard == 0) { err |= kErrFanWalk; break; }
+    }
+    const long long upper = 1ll << 29;
+    const long long abs_sum = llabs(sum[0]) + llabs(sum[1]) + llabs(sum[2]);
+    if (abs_sum > upper) {
+      const long long quot = abs_sum / upper;
+      sum[0] /= quot; sum[1] /= quot; sum[2] /= quot;
+    }
+    const int32_t nx = (int32_t)sum[0], ny = (int32_t)sum[1], nzc = (int32_t)sum[2];
+    int32_t p0 = 0, p1 = 0;
+    if (!(nx == 0 && ny == 0 && nzc == 0)) {
+      // integer vector -> f32 through f64 (geom.rs:47-52); the normalize() result is discarded there
+      oct_quantize_f32((float)(double)nx, (float)(double)ny, (float)(double)nzc, p0, p1);
+    }
+    const uint32_t vi = value_index(q, __ldg(t.corner_point + c));
+    const int2 actual = __ldg(reinterpret_cast<const int2*>(q.values) + vi);
+    // choose the sign closer to the actual value, in wrapping i32 (:128-143)
+    const uint32_t d10 = (uint32_t)p0 - (uint32_t)actual.x, d11 = (uint32_t)p1 - (uint32_t)actual.y;
+    const uint32_t d20 = (uint32_t)(0u - (uint32_t)p0) - (uint32_t)actual.x, d21 = (uint32_t)(0u - (uint32_t)p1) - (uint32_t)actual.y;
+    const int32_t dot1 = (int32_t)(d10 * d10 + d11 * d11), dot2 = (int32_t)(d20 * d20 + d21 * d21);
+    const bool flip = dot1 > dot2;
+    if (flip) { p0 = (int32_t)(0u - (uint32_t)p0); p1 = (int32_t)(0u - (uint32_t)p1); }
+    flips[i] = flip ? 1 : 0;
+
+    // OctahedronOrthogonalTransform::map_with_tentative_metadata
+    const int32_t one = 127;
+    int32_t o0 = actual.x - one, o1 = actual.y - one;
+    p0 -= one; p1 -= one;
+    if (iabs_wrap(p0) + iabs_wrap(p1) > one) {
+      const int32_t pp0 = p0, qs = -isign(p0 * p1);
+      p0 = qs * p1 + isign(p0) * one;
+      p1 = qs * pp0 + isign(p1) * one;
+      const int32_t oo0 = o0, qs2 = -isign(o0 * o1);
+      o0 = qs2 * o1 + isign(o0) * one;
+      o1 = qs2 * oo0 + isign(o1) * one;
+    }
+    if (!(p0 == 0 && p1 == 0)) {
+#pragma unroll 1
+      for (int it = 0; it < 4 && (p0 >= 0 || p1 > 0); ++it) {  // at most 3 quarter turns are ever needed
+        int32_t tmp = p0; p0 = -p1; p1 = tmp;
+        tmp = o0; o0 = -o1; o1 = tmp;
+      }
+    }
+    int32_t c0 = o0 - p0, c1 = o1 - p1;
+    if (c0 < 0) c0 += 255;
+    if (c1 < 0) c1 += 255;
+    reinterpret_cast<uint2*>(symbols)[i] = make_uint2((uint32_t)c0, (uint32_t)c1);
+    nz += (c0 != 0) + (c1 != 0);
+    mxs = max(mxs, max((uint32_t)c0, (uint32_t)c1));
+    err |= ((c0 | c1) < 0) ? kErrNegativeSymbol : 0u;
+  }
+  accumulate_symbol_stats(nz, mxs, err, stats);
+}
+
+void launch_predict_normal(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos, uint32_t* symbols, uint8_t* flips, AttrStats* stats, cudaStream_t s) {
+  predict_normal_kernel<<<grid_for(n), kThreads, 0, s>>>(seq, n, t, q, pos, symbols, flips, stats);
+}
+
+// ---------------------------------------------------------------------------------------
+// K6 — MeshPredictionForTextureCoordinates::predict
+// (mesh_prediction_for_texture_coordinates.rs:107-219) fused with WrappedDifference.
+// All arithmetic is wrapping i64 / u64 as in release-mode Rust.
+__device__ __forceinline__ unsigned long long isqrt_ref(unsigned long long value) {  // int_sqrt :33-49
+  if (value == 0) return 0;
+  unsigned long long act = value, s = 1;
+  while (act >= 2) { s *= 2; act /= 4; }
+  s = (s + value / s) / 2;
+  while (s * s > value) s = (s + value / s) / 2;
+  return s;
+}
+__device__ __forceinline__ long long labs64(long long a) { return a < 0 ? (long long)(0ull - (unsigned long long)a) : a; }
+__device__ __forceinline__ long long mul64w(long long a, long long b) { return (long long)((unsigned long long)a * (unsigned long long)b); }
+__device__ __forceinline__ long long add64w(long long a, long long b) { return (long long)((unsigned long long)a + (unsigned long long)b); }
+__device__ __forceinline__ long long sub64w(long long a, long long b) { return (long long)((unsigned long long)a - (unsigned long long)b); }
+
+// fallback_predict (:52-82): next vertex's value if it is already sequenced, else the last sequenced value
+__device__ __forceinline__ void texcoord_fallback(const uint32_t* seq, uint32_t i, uint32_t c, const TableDev& t, const QuantDev& q,
+                                                  const uint32_t* rank, int32_t* pred) {
+  const uint32_t nc = cnext(c);
+  if (__ldg(rank + __ldg(t.corner_vertex + nc)) < i) {
+    const int2 v = __ldg(reinterpret_cast<const int2*>(q.values) + value_index(q, __ldg(t.corner_point + nc)));
+    pred[0] = v.x; pred[1] = v.y;
+    return;
+  }
+  previous_value<2>(seq, i, t, q, pred);
+}
+
+__global__ void __launch_bounds__(kThreads) predict_texcoord_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos,
+                                                                    uint32_t pos_num_points, const uint32_t* __restrict__ rank,
+                                                                    uint32_t* __restrict__ symbols, uint8_t* __restrict__ orient, AttrStats* stats) {
+  const WrapParams w = wrap_params(stats);
+  uint32_t nz = 0, mxs = 0, err = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const long long I64MAX = 0x7FFFFFFFFFFFFFFFll;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t c = ld_stream(seq + i);
+    const uint32_t nc = cnext(c), pc = cprev(c);
+    const uint32_t next_pt = __ldg(t.corner_point + nc), prev_pt = __ldg(t.corner_point + pc), curr_pt = __ldg(t.corner_point + c);
+    const int2 cur = __ldg(reinterpret_cast<const int2*>(q.values) + value_index(q, curr_pt));
+    int32_t pred[2];
+    uint8_t oflag = 0;  // 0: no orientation bit, 1: bit = false, 2: bit = true
+    bool done = false;
+    if (__ldg(rank + __ldg(t.corner_vertex + nc)) < i && __ldg(rank + __ldg(t.corner_vertex + pc)) < i) {
+      const int2 nu = __ldg(reinterpret_cast<const int2*>(q.values) + value_index(q, next_pt));
+      const int2 pu = __ldg(reinterpret_cast<const int2*>(q.values) + value_index(q, prev_pt));
+      if (nu.x == pu.x && nu.y == pu.y) { pred[0] = pu.x; pred[1] = pu.y; done = true; }
+      else {
+        long long cp[3] = {0, 0, 0}, np[3] = {0, 0, 0}, pp[3] = {0, 0, 0};
+        int32_t tmp[3];
+        if (curr_pt < pos_num_points) { const uint32_t vi = value_index(pos, curr_pt); tmp[0] = __ldg(pos.values + (uint64_t)vi * 3); tmp[1] = __ldg(pos.values + (uint64_t)vi * 3 + 1); tmp[2] = __ldg(pos.values + (uint64_t)vi * 3 + 2); cp[0] = tmp[0]; cp[1] = tmp[1]; cp[2] = tmp[2]; }
+        if (next_pt < pos_num_points) { const uint32_t vi = value_index(pos, next_pt); tmp[0] = __ldg(pos.values + (uint64_t)vi * 3); tmp[1] = __ldg(pos.values + (uint64_t)vi * 3 + 1); tmp[2] = __ldg(pos.values + (uint64_t)vi * 3 + 2); np[0] = tmp[0]; np[1] = tmp[1]; np[2] = tmp[2]; }
+        if (prev_pt < pos_num_points) { const uint32_t vi = value_index(pos, prev_pt); tmp[0] = __ldg(pos.values + (uint64_t)vi * 3); tmp[1] = __ldg(pos.values + (uint64_t)vi * 3 + 1); tmp[2] = __ldg(pos.values + (uint64_t)vi * 3 + 2); pp[0] = tmp[0]; pp[1] = tmp[1]; pp[2] = tmp[2]; }
+        const long long pn[3] = {sub64w(pp[0], np[0]), sub64w(pp[1], np[1]), sub64w(pp[2], np[2])};
+        const unsigned long long pn2 = (unsigned long long)add64w(add64w(mul64w(pn[0], pn[0]), mul64w(pn[1], pn[1])), mul64w(pn[2], pn[2]));
+        if (pn2 != 0) {
+          const long long cn[3] = {sub64w(cp[0], np[0]), sub64w(cp[1], np[1]), sub64w(cp[2], np[2])};
+          const long long cn_dot_pn = add64w(add64w(mul64w(pn[0], cn[0]), mul64w(pn[1], cn[1])), mul64w(pn[2], cn[2]));
+          const long long pn_uv[2] = {(long long)pu.x - (long long)nu.x, (long long)pu.y - (long long)nu.y};
+          const long long n_uv_absmax = max(labs64((long long)nu.x), labs64((long long)nu.y));
+          const long long pn_uv_absmax = max(labs64(pn_uv[0]), labs64(pn_uv[1]));
+          const long long pn_absmax = max(max(labs64(pn[0]), labs64(pn[1])), labs64(pn[2]));
+          // overflow guards (:139-160); a zero / -1 divisor would panic in the reference and cannot occur for
+          // quantized inputs (pn2 > 0 as i64 for < 2^31-bit coordinates, pn_uv != 0, pn != 0)
+          bool fallback = false;
+          if ((long long)pn2 == 0 || n_uv_absmax > I64MAX / (long long)pn2) fallback = true;
+          else if (pn_uv_absmax == 0 || labs64(cn_dot_pn) > I64MAX / pn_uv_absmax) fallback = true;
+          else if (pn_absmax == 0 || labs64(cn_dot_pn) > I64MAX / pn_absmax) fallback = true;
+          if (!fallback) {
+            const long long d = (long long)pn2;
+            const long long x_uv[2] = {add64w(mul64w((long long)nu.x, d), mul64w(pn_uv[0], cn_dot_pn)),
+                                       add64w(mul64w((long long)nu.y, d), mul64w(pn_uv[1], cn_dot_pn))};
+            long long cx[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const long long x_pos = add64w(np[k], mul64w(pn[k], cn_dot_pn) / d);
+              cx[k] = sub64w(cp[k], x_pos);
+            }
+            const unsigned long long cx2 = (unsigned long long)add64w(add64w(mul64w(cx[0], cx[0]), mul64w(cx[1], cx[1])), mul64w(cx[2], cx[2]));
+            const long long nrm = (long long)isqrt_ref(cx2 * pn2);
+            const long long cx_uv[2] = {mul64w(pn_uv[1], nrm), mul64w((long long)(0ull - (unsigned long long)pn_uv[0]), nrm)};
+            const long long a0 = add64w(x_uv[0], cx_uv[0]) / d, a1 = add64w(x_uv[1], cx_uv[1]) / d;
+            const long long b0 = sub64w(x_uv[0], cx_uv[0]) / d, b1 = sub64w(x_uv[1], cx_uv[1]) / d;
+            const long long ea0 = sub64w((long long)cur.x, a0), ea1 = sub64w((long long)cur.y, a1);
+            const long long eb0 = sub64w((long long)cur.x, b0), eb1 = sub64w((long long)cur.y, b1);
+            const long long da = add64w(mul64w(ea0, ea0), mul64w(ea1, ea1));
+            const long long db = add64w(mul64w(eb0, eb0), mul64w(eb1, eb1));
+            if (da < db) { oflag = 2; pred[0] = (int32_t)a0; pred[1] = (int32_t)a1; }
+            else { oflag = 1; pred[0] = (int32_t)b0; pred[1] = (int32_t)b1; }
+            done = true;
+          }
+        }
+      }
+    }
+    if (!done) texcoord_fallback(seq, i, c, t, q, rank, pred);
+    orient[i] = oflag;
+    const uint32_t s0 = wrapped_symbol(cur.x, pred[0], w), s1 = wrapped_symbol(cur.y, pred[1], w);
+    reinterpret_cast<uint2*>(symbols)[i] = make_uint2(s0, s1);
+    nz += (s0 != 0) + (s1 != 0);
+    mxs = max(mxs, max(s0, s1));
+    err |= ((s0 | s1) & 0x80000000u) ? kErrNegativeSymbol : 0u;
+  }
+  accumulate_symbol_stats(nz, mxs, err, stats);
+}
+
+void launch_predict_texcoord(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos, uint32_t pos_num_points, const uint32_t* rank,
+                             uint32_t* symbols, uint8_t* orient, AttrStats* stats, cudaStream_t s) {
+  predict_texcoord_kernel<<<grid_for(n), kThreads, 0, s>>>(seq, n, t, q, pos, pos_num_points, rank, symbols, orient, stats);
+}
+
+// ---------------------------------------------------------------------------------------
+// K8 — symbol histogram (symbol_coding.rs:149-157). Shared-memory bins when the
+// alphabet fits (always for the default 11/8/10 bits), warp-aggregated through
+// match_any so equal symbols inside a warp cost one atomic; global atomics otherwise.
+constexpr uint32_t kSmemBins = 8192;
+
+__global__ void __launch_bounds__(kThreads) histogram_smem_kernel(const uint32_t* __restrict__ symbols, uint64_t n, uint32_t* __restrict__ hist,
+                                                                  uint32_t capacity, AttrStats* stats) {
+  __shared__ uint32_t bins[kSmemBins];
+  const uint32_t nb = min(stats->max_symbol + 1u, capacity);
+  for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) bins[b] = 0;
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t s = ld_stream(symbols + i);
+    if (s < nb) atomicAdd(&bins[s], 1u);
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
+    const uint32_t v = bins[b];
+    if (v) atomicAdd(hist + b, v);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) histogram_global_kernel(const uint32_t* __restrict__ symbols, uint64_t n, uint32_t* __restrict__ hist,
+                                                                    uint32_t capacity, AttrStats* stats) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  bool over = false;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t s = ld_stream(symbols + i);
+    if (s < capacity) atomicAdd(hist + s, 1u); else over = true;
+  }
+  if (over) atomicOr(&stats->error_flags, kErrAlphabet);
+}
+
+void launch_histogram(const uint32_t* symbols, uint64_t num_symbols, uint32_t* hist, uint32_t hist_capacity, AttrStats* stats, cudaStream_t s) {
+  if (hist_capacity <= kSmemBins) {
+    int g = grid_for(num_symbols, kThreads * 16);
+    histogram_smem_kernel<<<g, kThreads, 0, s>>>(symbols, num_symbols, hist, hist_capacity, stats);
+  } else {
+    histogram_global_kernel<<<grid_for(num_symbols, kThreads * 4), kThreads, 0, s>>>(symbols, num_symbols, hist, hist_capacity, stats);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K9 — RansSymbolEncoder::new (rans.rs:146-230) as a single CTA:
+//   1. f64 normalisation of the histogram to 2^P with the min-1 rule,
+//   2. the sum correction with the reference's stable-sort semantics (deficit -> the
+//      largest entry, highest index among ties; excess -> minus one on the `err`
+//      largest entries walking down the stably sorted order),
+//   3. serialisation (leb128 count, 1-3 byte frequencies, zero-run tokens incl. the
+//      64-wrap quirk of :202-211),
+//   4. the per-symbol {freq, cumulative, reciprocal} table for K10.
+constexpr int kTableThreads = 1024;
+
+struct BlockScan {  // exclusive scans over a block of kTableThreads threads
+  uint32_t* warp_tmp;  // 32 entries of shared memory
+  __device__ uint32_t exclusive_sum(uint32_t v, uint32_t& total) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= (uint32_t)d) inc += o; }
+    __syncthreads();
+    if (lane == 31) warp_tmp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t w = warp_tmp[lane], winc = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, winc, d); if (lane >= (uint32_t)d) winc += o; }
+      warp_tmp[lane] = winc - w;
+      if (lane == 31) warp_tmp[32] = winc;
+    }
+    __syncthreads();
+    total = warp_tmp[32];
+    return warp_tmp[wid] + inc - v;
+  }
+  __device__ uint32_t reduce_max(uint32_t v) {
+    v = __reduce_max_sync(0xFFFFFFFFu, v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) warp_tmp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t r = warp_tmp[threadIdx.x & 31];
+    r = __reduce_max_sync(0xFFFFFFFFu, r);
+    return r;
+  }
+  __device__ unsigned long long reduce_sum64(unsigned long long v, unsigned long long* tmp64) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) tmp64[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long r = tmp64[threadIdx.x & 31];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) r += __shfl_xor_sync(0xFFFFFFFFu, r, d);
+    return r;
+  }
+};
+
+__device__ __forceinline__ uint32_t freq_token_bytes(uint32_t f) { return 1u + (f >= (1u << 6)) + (f >= (1u << 14)); }
+
+__global__ void __launch_bounds__(kTableThreads) build_table_kernel(const uint32_t* __restrict__ hist, uint32_t capacity, unsigned long long total_symbols,
+                                                                    uint32_t* __restrict__ work, uint4* __restrict__ rans_table,
+                                                                    uint8_t* __restrict__ table_bytes, uint32_t table_bytes_capacity, AttrStats* stats) {
+  __shared__ uint32_t s_warp[33];
+  __shared__ unsigned long long s_tmp64[32];
+  __shared__ uint32_t s_scalar[4];
+  BlockScan scan{s_warp};
+  const uint32_t tid = threadIdx.x;
+
+  // bit_length from the count of non-zero symbols (symbol_coding.rs:46-52,118) and the precision table (:120-140)
+  const uint32_t nonzero = stats->nonzero_symbols;
+  uint32_t bit_length = (nonzero == 0 ? 0u : (32u - (uint32_t)__clz(nonzero))) + 1u;
+  bit_length = min(max(bit_length, 1u), 18u);
+  const uint32_t P = bit_length <= 8 ? 12u : bit_length == 9 ? 13u : bit_length == 10 ? 15u : bit_length == 11 ? 16u
+                   : bit_length == 12 ? 18u : bit_length == 13 ? 19u : 20u;
+  const uint32_t target = 1u << P;
+  const uint32_t K = stats->max_symbol + 1u;  // histogram is sized max_symbol + 1 and its last bin is non-zero
+  if (K > capacity || total_symbols == 0) {
+    if (tid == 0) { atomicOr(&stats->error_flags, K > capacity ? kErrAlphabet : kErrRansFreq); stats->bit_length = bit_length; stats->precision = P; }
+    return;
+  }
+  uint32_t* dist = work;                 // normalised frequencies
+  uint32_t* prev_nz = work + capacity;   // index+1 of the last non-zero entry at or before i (0 = none)
+  uint32_t* next_nz = work + 2 * (size_t)capacity;  // index of the first non-zero entry after i
+  const uint32_t per = (K + kTableThreads - 1) / kTableThreads;  // contiguous entries per thread
+  const uint32_t lo = min(tid * per, K), hi = min(lo + per, K);
+
+  // 1. normalisation (rans.rs:156-168): prob = freq / total (f64); (prob * 2^P + 0.5) as usize; 0 -> 1 for present symbols
+  const double total_f = (double)total_symbols;
+  const double scale = (double)target;
+  unsigned long long local_sum = 0;
+  for (uint32_t i = lo; i < hi; ++i) {
+    const uint32_t f = hist[i];
+    const double prob = (double)f / total_f;
+    const double x = prob * scale;
+    const double y = x + 0.5;
+    uint32_t nf = (uint32_t)(unsigned long long)y;
+    if (nf == 0 && f > 0) nf = 1;
+    dist[i] = nf;
+    local_sum += nf;
+  }
+  const unsigned long long sum = scan.reduce_sum64(local_sum, s_tmp64);
+  __syncthreads();
+
+  // 2. correction
+  if (sum < target) {
+    // deficit goes to sorted.last(): the largest value, highest index among ties
+    uint32_t best = 0;
+    for (uint32_t i = lo; i < hi; ++i) best = max(best, dist[i]);
+    const uint32_t gmax = scan.reduce_max(best);
+    uint32_t idx = 0;
+    for (uint32_t i = lo; i < hi; ++i) if (dist[i] == gmax) idx = i + 1;
+    const uint32_t gidx = scan.reduce_max(idx);
+    __syncthreads();
+    if (tid == 0) dist[gidx - 1] += target - (uint32_t)sum;
+    __syncthreads();
+  } else if (sum > target) {
+    const unsigned long long err64 = sum - target;
+    if (err64 > K) {  // the reference walks past index 0 and panics
+      if (tid == 0) atomicOr(&stats->error_flags, kErrRansFreq);
+      return;
+    }
+    const uint32_t err = (uint32_t)err64;
+    // Find the value T such that all entries > T are decremented plus the highest-index
+    // entries == T: smallest T with count(dist > T) <= err.
+    uint32_t lo_t = 0, hi_t = target + K;  // count(dist > hi_t) == 0 <= err
+    while (lo_t < hi_t) {
+      const uint32_t mid = lo_t + (hi_t - lo_t) / 2;
+      uint32_t cnt = 0;
+      for (uint32_t i = lo; i < hi; ++i) cnt += dist[i] > mid;
+      uint32_t tot;
+      scan.exclusive_sum(cnt, tot);
+      if (tot <= err) hi_t = mid; else lo_t = mid + 1;
+      __syncthreads();
+    }
+    const uint32_t T = lo_t;
+    uint32_t above = 0, equal = 0;
+    for (uint32_t i = lo; i < hi; ++i) { above += dist[i] > T; equal += dist[i] == T; }
+    uint32_t tot_above, tot_equal;
+    scan.exclusive_sum(above, tot_above);
+    const uint32_t eq_before = scan.exclusive_sum(equal, tot_equal);
+    const uint32_t need_equal = err - tot_above;  // taken from the highest indices among dist == T
+    if (need_equal > tot_equal || (T == 0 && need_equal > 0)) {  // would decrement a zero entry: reference underflows
+      if (tid == 0) atomicOr(&stats->error_flags, kErrRansFreq);
+      return;
+    }
+    uint32_t eq_rank = eq_before;  // rank among equal entries in index order
+    for (uint32_t i = lo; i < hi; ++i) {
+      const uint32_t d = dist[i];
+      if (d > T) dist[i] = d - 1;
+      else if (d == T) { if (tot_equal - eq_rank <= need_equal) dist[i] = d - 1; ++eq_rank; }
+    }
+    __syncthreads();
+  }
+
+  // 3+4. cumulative frequencies, zero-run structure, serialisation
+  // prev_nz / next_nz by per-thread chunk + block-wide propagation
+  uint32_t chunk_sum = 0, last_nz_local = 0, first_nz_local = kNoneDev;
+  for (uint32_t i = lo; i < hi; ++i) {
+    const uint32_t d = dist[i];
+    chunk_sum += d;
+    if (d) { last_nz_local = i + 1; if (first_nz_local == kNoneDev) first_nz_local = i; }
+  }
+  uint32_t tot_freq;
+  uint32_t cum = scan.exclusive_sum(chunk_sum, tot_freq);
+  if (tot_freq != target) { if (tid == 0) atomicOr(&stats->error_flags, kErrRansFreq); return; }
+  // exclusive max-scan of last_nz over threads (values are increasing with tid when non-zero)
+  __shared__ uint32_t s_last[kTableThreads];
+  __shared__ uint32_t s_first[kTableThreads];
+  s_last[tid] = last_nz_local;
+  s_first[tid] = first_nz_local;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t run = 0;
+    for (int k = 0; k < kTableThreads; ++k) { const uint32_t v = s_last[k]; s_last[k] = run; if (v) run = v; }
+    uint32_t nxt = kNoneDev;
+    for (int k = kTableThreads - 1; k >= 0; --k) { const uint32_t v = s_first[k]; s_first[k] = nxt; if (v != kNoneDev) nxt = v; }
+  }
+  __syncthreads();
+  {
+    uint32_t run = s_last[tid];
+    for (uint32_t i = lo; i < hi; ++i) { if (dist[i]) run = i + 1; prev_nz[i] = run; }
+    uint32_t nxt = s_first[tid];
+    for (uint32_t i = hi; i-- > lo;) { next_nz[i] = nxt; if (dist[i]) nxt = i; }
+  }
+  __syncthreads();
+  // bytes emitted at each entry
+  auto entry_bytes = [&](uint32_t i, uint8_t* token) -> uint32_t {
+    const uint32_t d = dist[i];
+    if (d) return freq_token_bytes(d);
+    const uint32_t run_start = prev_nz[i];         // first index of this zero run
+    const uint32_t run_end = next_nz[i];           // index of the terminating non-zero entry (exists: last bin is non-zero)
+    const uint32_t R = run_end - run_start, j = i - run_start;
+    const uint32_t singles = R > 64 ? R - 64 : 0;  // entries emitted as lone zeros: offset counter wrapped to 0 (:202-211)
+    if (j < singles) { *token = 3; return 1; }
+    if (j == singles) { *token = (uint8_t)((((R - singles) - 1u) << 2) | 3u); return 1; }
+    return 0;
+  };
+  uint32_t nbytes = 0;
+  for (uint32_t i = lo; i < hi; ++i) { uint8_t tk; nbytes += entry_bytes(i, &tk); }
+  uint32_t tot_bytes;
+  uint32_t off = scan.exclusive_sum(nbytes, tot_bytes);
+  // leb128(num_symbols) header
+  uint32_t hdr = 0;
+  { uint32_t v = K; do { ++hdr; v >>= 7; } while (v); }
+  if (hdr + tot_bytes > table_bytes_capacity) { if (tid == 0) atomicOr(&stats->error_flags, kErrAlphabet); return; }
+  if (tid == 0) {
+    uint32_t v = K, p = 0;
+    do { uint8_t b = v & 0x7F; v >>= 7; table_bytes[p++] = v ? (b | 0x80) : b; } while (v);
+    stats->bit_length = bit_length; stats->precision = P; stats->num_table_symbols = K; stats->table_bytes = hdr + tot_bytes;
+    s_scalar[0] = hdr;
+  }
+  __syncthreads();
+  off += s_scalar[0];
+  for (uint32_t i = lo; i < hi; ++i) {
+    const uint32_t d = dist[i];
+    uint8_t tk = 0;
+    const uint32_t nb = entry_bytes(i, &tk);
+    if (d) {
+      const uint32_t extra = nb - 1;
+      table_bytes[off] = (uint8_t)((d << 2) | extra);
+      for (uint32_t b = 0; b < extra; ++b) table_bytes[off + 1 + b] = (uint8_t)(d >> (8 * (b + 1) - 2));
+      // K10 lookup: x / d for x < 2^30 as (x * magic) >> shift, exact (DESIGN.md "rANS division")
+      const uint32_t l = (d <= 1) ? 0u : (32u - (uint32_t)__clz(d - 1));  // ceil(log2 d)
+      const uint32_t shift = 30u + l;
+      const unsigned long long magic = ((1ull << shift) + d - 1) / d;
+      rans_table[i] = make_uint4(d, cum, (uint32_t)magic, shift);
+      cum += d;
+    } else {
+      if (nb) table_bytes[off] = tk;
+      rans_table[i] = make_uint4(0, cum, 0, 0);
+    }
+    off += nb;
+  }
+}
+
+void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t total_symbols, uint32_t* work, uint4* rans_table,
+                        uint8_t* table_bytes, uint32_t table_bytes_capacity, AttrStats* stats, cudaStream_t s) {
+  build_table_kernel<<<1, kTableThreads, 0, s>>>(hist, hist_capacity, total_symbols, work, rans_table, table_bytes, table_bytes_capacity, stats);
+}
+
+// ---------------------------------------------------------------------------------------
+// K10 — RansCoder::write / flush (rans.rs:33-68), symbols fed last-to-first
+// (symbol_coding.rs:161). The state recurrence is inherently serial, so one warp
+// owns the stream: lanes prefetch 32 symbols and their table rows with coalesced
+// loads, the state update runs warp-uniformly on values broadcast by shuffles.
+// x / f uses the exact reciprocal from K9: x < 2^30, f <= 2^20.
+__global__ void __launch_bounds__(32) rans_encode_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                         uint8_t* __restrict__ out, AttrStats* stats) {
+  const uint32_t lane = threadIdx.x;
+  const uint32_t P = stats->precision;
+  if (stats->error_flags) { if (lane == 0) stats->payload_bytes = 0; return; }
+  const uint32_t K = stats->num_table_symbols;
+  const uint32_t l_base = (1u << P) << 2;
+  const uint32_t full = 1u << P;
+  uint32_t x = l_base;
+  unsigned long long pos = 0;
+  uint32_t err = 0;
+  for (unsigned long long base = n; base > 0;) {
+    const uint32_t cnt = base >= 32 ? 32u : (uint32_t)base;
+    uint4 e = make_uint4(1, 0, 0, 0);
+    if (lane < cnt) {
+      const uint32_t sym = __ldcs(symbols + (base - 1 - lane));
+      if (sym < K) e = __ldg(table + sym); else err |= kErrRansFreq;
+      if (e.x == 0) { err |= kErrRansFreq; e.x = 1; }
+    }
+    for (uint32_t j = 0; j < cnt; ++j) {
+      const uint32_t f = __shfl_sync(0xFFFFFFFFu, e.x, j);
+      const uint32_t cum = __shfl_sync(0xFFFFFFFFu, e.y, j);
+      const uint32_t magic = __shfl_sync(0xFFFFFFFFu, e.z, j);
+      const uint32_t shift = __shfl_sync(0xFFFFFFFFu, e.w, j);
+      const uint32_t thr = f << 10;  // ((l_base >> P) * f) << 8
+      while (x >= thr) {
+        if (lane == 0) out[pos] = (uint8_t)x;
+        ++pos;
+        x >>= 8;
+      }
+      const uint32_t q = (uint32_t)(((unsigned long long)x * magic) >> shift);
+      x = x + q * (full - f) + cum;  // (q << P) + (x - q f) + cum
+    }
+    base -= cnt;
+  }
+  err = __reduce_or_sync(0xFFFFFFFFu, err);
+  if (lane == 0) {
+    uint32_t t = x - l_base;  // flush (:48-68)
+    if (t < (1u << 6)) { out[pos++] = (uint8_t)t; }
+    else if (t < (1u << 14)) { const uint32_t v = 0x4000u + t; out[pos++] = (uint8_t)v; out[pos++] = (uint8_t)(v >> 8); }
+    else if (t < (1u << 22)) { const uint32_t v = 0x800000u + t; out[pos++] = (uint8_t)v; out[pos++] = (uint8_t)(v >> 8); out[pos++] = (uint8_t)(v >> 16); }
+    else if (t < (1u << 30)) { const uint32_t v = 0xC0000000u + t; out[pos++] = (uint8_t)v; out[pos++] = (uint8_t)(v >> 8); out[pos++] = (uint8_t)(v >> 16); out[pos++] = (uint8_t)(v >> 24); }
+    else err |= kErrRansState;
+    stats->payload_bytes = (uint32_t)pos;
+    if (err) atomicOr(&stats->error_flags, err);
+  }
+}
+
+void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, uint8_t* payload, AttrStats* stats, cudaStream_t s) {
+  rans_encode_kernel<<<1, 32, 0, s>>>(symbols, num_symbols, rans_table, payload, stats);
+}
+
+// ---------------------------------------------------------------------------------------
+// K12 — CornerTable::compute_table (corner_table/mod.rs:252-340) for the manifold,
+// consistently oriented case: sort half edges by
+// (min(a,b), max(a,b)); an undirected edge with exactly two half edges of opposite
+// direction and different tips pairs them. Anything else (3+ half edges, equal
+// direction, equal tips, degenerate faces) raises not_exact: those results depend on
+// corner order and the caller must use the sequential matcher.
+__global__ void __launch_bounds__(kThreads) halfedge_keys_kernel(const uint32_t* __restrict__ cv, unsigned long long num_corners,
+                                                                 unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* not_exact) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < num_corners; c += stride) {
+    const uint32_t cc = (uint32_t)c;
+    const uint32_t tip = cv[cc], src = cv[cnext(cc)], snk = cv[cprev(cc)];
+    if (tip == src || tip == snk || src == snk) *not_exact = 1;  // degenerate face
+    const uint32_t a = min(src, snk), b = max(src, snk);
+    keys[c] = ((unsigned long long)a << 32) | b;
+    vals[c] = cc;
+  }
+}
+__global__ void __launch_bounds__(kThreads) halfedge_pair_kernel(const uint32_t* __restrict__ cv, unsigned long long num_corners,
+                                                                 const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                                 uint32_t* __restrict__ opposite, uint32_t* not_exact) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < num_corners; i += stride) {
+    const unsigned long long k = keys[i];
+    const bool same_prev = i > 0 && keys[i - 1] == k;
+    const bool same_next = i + 1 < num_corners && keys[i + 1] == k;
+    const uint32_t c = vals[i];
+    if (same_prev && same_next) { *not_exact = 1; continue; }  // 3+ half edges on one edge
+    if (!same_prev && !same_next) { opposite[c] = kNoneDev; continue; }
+    const uint32_t other = same_next ? vals[i + 1] : vals[i - 1];
+    if (same_next && i + 2 < num_corners && keys[i + 2] == k) { *not_exact = 1; continue; }
+    if (same_prev && i >= 2 && keys[i - 2] == k) { *not_exact = 1; continue; }
+    const uint32_t src = cv[cnext(c)], osrc = cv[cnext(other)];
+    if (src == osrc) { *not_exact = 1; continue; }               // same direction: inconsistent orientation
+    if (cv[c] == cv[other]) { *not_exact = 1; continue; }        // equal tips are skipped by the reference (:308-310)
+    opposite[c] = other;
+  }
+}
+
+size_t corner_table_scratch_bytes(uint64_t num_corners) {
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)num_corners);
+  const size_t a = ((num_corners * 8 + 255) / 256) * 256, b = ((num_corners * 4 + 255) / 256) * 256;
+  return 2 * a + 2 * b + cub_bytes + 256;
+}
+
+void launch_corner_table_opposites(const uint32_t* corner_vertex, uint64_t num_corners, uint32_t* opposite, uint32_t* not_exact_flag,
+                                   void* scratch, size_t scratch_bytes, cudaStream_t s) {
+  const size_t a = ((num_corners * 8 + 255) / 256) * 256, b = ((num_corners * 4 + 255) / 256) * 256;
+  uint8_t* p = (uint8_t*)scratch;
+  unsigned long long* keys_in = (unsigned long long*)p; p += a;
+  unsigned long long* keys_out = (unsigned long long*)p; p += a;
+  uint32_t* vals_in = (uint32_t*)p; p += b;
+  uint32_t* vals_out = (uint32_t*)p; p += b;
+  size_t cub_bytes = scratch_bytes - (2 * a + 2 * b);
+  const int g = grid_for(num_corners);
+  halfedge_keys_kernel<<<g, kThreads, 0, s>>>(corner_vertex, num_corners, keys_in, vals_in, not_exact_flag);
+  cub::DeviceRadixSort::SortPairs(p, cub_bytes, keys_in, keys_out, vals_in, vals_out, (int)num_corners, 0, 64, s);
+  halfedge_pair_kernel<<<g, kThreads, 0, s>>>(corner_vertex, num_corners, keys_out, vals_out, opposite, not_exact_flag);
+}
+
+}  // namespace gpu
+}  // namespace dxo

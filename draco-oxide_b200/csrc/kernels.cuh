@@ -1,0 +1,88 @@
+// Device-side interface of the attribute hot path (sm_100a). Host code includes this
+// header; kernels live in kernels.cu and are compiled with -fmad=false so that every
+// f32/f64 operation is a separately rounded IEEE operation (bit-exact integer outputs).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace dxo {
+namespace gpu {
+
+constexpr uint32_t kNoneDev = 0xFFFFFFFFu;
+
+// error bits accumulated on the device (AttrStats::error_flags)
+enum : uint32_t {
+  kErrZeroNormal = 1u << 0,      // geom.rs:45 assert
+  kErrFanWalk = 1u << 1,         // fan walk did not terminate (malformed table)
+  kErrNegativeSymbol = 1u << 2,  // residual that the reference would index out of range
+  kErrRansFreq = 1u << 3,        // normalised table does not sum to 2^P / zero frequency of a used symbol
+  kErrRansState = 1u << 4,       // rans.rs:64 StateTooLarge
+  kErrAlphabet = 1u << 5,        // alphabet larger than the histogram capacity
+};
+
+// Per-attribute scalars produced on the device and read back once by the host.
+struct AttrStats {
+  uint32_t vmin_bits[4];   // f32 bit patterns: per-component min (starts at +0.0)
+  uint32_t vmax_bits[4];   // per-component max (starts at +0.0)
+  float range;             // max_i(max_i - min_i)
+  int32_t wrap_min;        // WrappedDifference min/max over visited originals
+  int32_t wrap_max;
+  uint32_t nonzero_symbols;
+  uint32_t max_symbol;
+  uint32_t error_flags;
+  uint32_t bit_length;     // symbol_coding.rs:118
+  uint32_t precision;      // rANS precision bits
+  uint32_t num_table_symbols;
+  uint32_t table_bytes;    // serialized leb128 #symbols + frequency table
+  uint32_t payload_bytes;  // rANS payload
+  uint32_t pad[3];
+};
+
+// Immutable connectivity of one attribute as the predictors see it (GenericCornerTable).
+struct TableDev {
+  const uint32_t* corner_point;   // faces
+  const uint32_t* corner_vertex;  // attribute (or universal) vertex of each corner
+  const uint32_t* opposite;       // universal opposite corners
+  const uint8_t* seam;            // nullptr for the universal table
+  const uint32_t* left_most;      // per vertex
+  uint32_t num_corners;
+  uint32_t num_vertices;
+};
+
+// Quantized attribute: AoS int32 values + optional point map.
+struct QuantDev {
+  const int32_t* values;
+  const uint32_t* map;  // nullptr = identity
+  uint32_t num_components;
+};
+
+// ---- K1/K2: coordinate-wise quantization (quantization_coordinate_wise.rs:24-117) ----
+void launch_minmax(const float* values, uint64_t num_values, uint32_t ncomp, AttrStats* stats, cudaStream_t s);
+void launch_quantize(const float* values, uint64_t num_values, uint32_t ncomp, uint32_t bits, int32_t* out, AttrStats* stats, cudaStream_t s);
+// ---- K3: octahedral normal quantization (octahedral_quantization.rs:49-64) ----
+void launch_oct_quantize(const float* normals, uint64_t num_values, int32_t* out, AttrStats* stats, cudaStream_t s);
+// ---- sequence preparation: rank[vertex] = position in the sequence, WrappedDifference min/max ----
+void launch_seq_prepare(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, uint32_t* rank, bool want_minmax, AttrStats* stats, cudaStream_t s);
+// ---- K4-K7: prediction + transform + symbolization, one thread per sequence element ----
+void launch_predict_parallelogram(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, const uint32_t* rank, uint32_t* symbols, AttrStats* stats, cudaStream_t s);
+void launch_predict_normal(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos, uint32_t* symbols, uint8_t* flips, AttrStats* stats, cudaStream_t s);
+void launch_predict_texcoord(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos, uint32_t pos_num_points, const uint32_t* rank, uint32_t* symbols, uint8_t* orient, AttrStats* stats, cudaStream_t s);
+void launch_predict_delta(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, uint32_t* symbols, AttrStats* stats, cudaStream_t s);
+// ---- K8: symbol histogram (symbol_coding.rs:149-157) ----
+void launch_histogram(const uint32_t* symbols, uint64_t num_symbols, uint32_t* hist, uint32_t hist_capacity, AttrStats* stats, cudaStream_t s);
+// ---- K9: probability table normalisation + serialisation + rANS lookup table (rans.rs:146-230) ----
+// rans_table entries: {freq, cumulative, magic multiplier, shift}
+void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t total_symbols, uint32_t* work /*5*capacity*/, uint4* rans_table,
+                        uint8_t* table_bytes, uint32_t table_bytes_capacity, AttrStats* stats, cudaStream_t s);
+// ---- K10: rANS emission, serial within the stream (rans.rs:33-68) ----
+void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, uint8_t* payload, AttrStats* stats, cudaStream_t s);
+// ---- K12: half-edge matching by radix sort (corner_table/mod.rs:252-340, fast path) ----
+// keys/vals/tmp are caller-provided scratch (see corner_table_scratch_bytes).
+size_t corner_table_scratch_bytes(uint64_t num_corners);
+void launch_corner_table_opposites(const uint32_t* corner_vertex, uint64_t num_corners, uint32_t* opposite, uint32_t* not_exact_flag,
+                                   void* scratch, size_t scratch_bytes, cudaStream_t s);
+
+void init_stats(AttrStats* stats, cudaStream_t s);
+
+}  // namespace gpu
+}  // namespace dxo

@@ -152,6 +152,10 @@ int dxo_device_count(void);
 typedef struct dxo_session dxo_session;
 
 int dxo_session_create(const dxo_mesh* mesh, const dxo_config* cfg, dxo_session** out);
+/* Host-only part of encode(): header + Edgebreaker connectivity + attribute-section
+ * headers ("head_bytes") and the per-attribute traversal sequences, readable through
+ * dxo_session_trace_get. Needs no device; dxo_session_run on it returns DXO_ERR_NO_DEVICE. */
+int dxo_connectivity_create(const dxo_mesh* mesh, const dxo_config* cfg, dxo_session** out);
 /* Runs the device hot path once. out may be NULL (results are discarded after
  * the D2H completes). */
 int dxo_session_run(dxo_session* s, dxo_bytes* out);

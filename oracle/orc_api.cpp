@@ -244,6 +244,21 @@ int orc_mesh_view(void* handle, dxo_mesh* out) {
 }
 void orc_mesh_free(void* handle) { delete (MeshHandle*)handle; }
 
+// Attribute::from (dedup) followed by Attribute::remove of `removed` points, f32 x ncomp.
+// out_map receives the point->value map (identity when the attribute has none).
+int orc_dedup_and_remove(const float* values, uint64_t n, uint32_t ncomp, const uint32_t* removed, uint64_t nrem,
+                         uint32_t* out_map, uint64_t* out_len, uint64_t* out_num_unique, int* out_has_map) {
+  return guarded([&] {
+    Attribute a;
+    a.comp_type = CT_F32; a.num_components = ncomp;
+    a.buffer.assign((const uint8_t*)values, (const uint8_t*)values + n * ncomp * 4);
+    remove_duplicate_values(a);
+    for (uint64_t i = 0; i < nrem; ++i) remove_points(a, std::vector<uint32_t>{removed[i]});
+    *out_len = a.len(); *out_num_unique = a.num_unique(); *out_has_map = a.has_map ? 1 : 0;
+    for (size_t p = 0; p < a.len(); ++p) out_map[p] = a.unique_val_idx((uint32_t)p);
+  });
+}
+
 // ---- unit-level entry points for the known-answer tests --------------------------------
 int orc_leb128(uint64_t v, uint8_t* out, uint64_t* n) { Bytes b; leb128_write(v, b); memcpy(out, b.data(), b.size()); *n = b.size(); return ST_OK; }
 

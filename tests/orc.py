@@ -41,6 +41,8 @@ def lib():
         L.orc_mesh_build.restype = C.c_void_p
         L.orc_mesh_view.argtypes = [C.c_void_p, C.POINTER(_capi.dxo_mesh)]
         L.orc_mesh_free.argtypes = [C.c_void_p]
+        L.orc_dedup_and_remove.argtypes = [C.POINTER(C.c_float), C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint64,
+                                           C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
         L.orc_leb128.argtypes = [C.c_uint64, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]
         L.orc_bitwriter.argtypes = [C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]
         L.orc_rans_encode_raw.argtypes = [C.POINTER(C.c_uint64), C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint64, C.POINTER(_capi.dxo_bytes)]
@@ -169,6 +171,20 @@ def build_mesh(faces, atts):
     if st.value != 0:
         raise OracleError(st.value)
     return _mesh_from_handle(h)
+
+
+def dedup_and_remove(values, removed=()):
+    """Attribute::from + Attribute::remove; returns (map list, num_unique, has_map)."""
+    v = np.ascontiguousarray(values, dtype=np.float32)
+    r = np.ascontiguousarray(removed, dtype=np.uint32)
+    out = np.zeros(v.shape[0], np.uint32)
+    n, u, hm = C.c_uint64(), C.c_uint64(), C.c_int()
+    st = lib().orc_dedup_and_remove(v.ctypes.data_as(C.POINTER(C.c_float)), v.shape[0], v.shape[1],
+                                    r.ctypes.data_as(C.POINTER(C.c_uint32)), r.size,
+                                    out.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(n), C.byref(u), C.byref(hm))
+    if st != 0:
+        raise OracleError(st)
+    return out[: n.value].tolist(), u.value, bool(hm.value)
 
 
 def leb128(v):
