@@ -106,6 +106,12 @@ class Session:
         _check(_capi.lib().dxo_session_run(self._h, C.byref(out) if want_bytes else None))
         return _take(out) if want_bytes else None
 
+    def run_steps(self, steps):
+        """Bench loop: returns (CUDA-event milliseconds for all steps, kernels launched)."""
+        ms, n = C.c_float(), C.c_uint64()
+        _check(_capi.lib().dxo_session_run_steps(self._h, steps, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def set_trace(self, on=True):
         _capi.lib().dxo_session_set_trace(self._h, int(on))
 

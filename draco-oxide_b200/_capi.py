@@ -70,7 +70,7 @@ class dxo_timing(C.Structure):
 # every symbol include/dxo.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = [
     "dxo_config_default", "dxo_encode", "dxo_encode_batch", "dxo_free_bytes", "dxo_strerror",
-    "dxo_device_count", "dxo_session_create", "dxo_connectivity_create", "dxo_session_run", "dxo_session_destroy",
+    "dxo_device_count", "dxo_session_create", "dxo_connectivity_create", "dxo_session_run_steps", "dxo_session_run", "dxo_session_destroy",
     "dxo_set_profiling", "dxo_last_timing", "dxo_session_set_trace", "dxo_session_trace_get",
     "dxo_corner_table_opposites",
 ]
@@ -108,6 +108,8 @@ def lib():
     L.dxo_connectivity_create.restype = C.c_int
     L.dxo_session_run.argtypes = [C.c_void_p, C.POINTER(dxo_bytes)]
     L.dxo_session_run.restype = C.c_int
+    L.dxo_session_run_steps.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+    L.dxo_session_run_steps.restype = C.c_int
     L.dxo_session_destroy.argtypes = [C.c_void_p]
     L.dxo_session_destroy.restype = None
     L.dxo_set_profiling.argtypes = [C.c_int]

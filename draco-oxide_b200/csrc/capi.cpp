@@ -255,6 +255,31 @@ int dxo_session_run(dxo_session* s, dxo_bytes* out) {
   });
 }
 
+int dxo_session_run_steps(dxo_session* s, uint32_t steps, float* ms_total, uint64_t* launches_total) {
+  if (!s || !ms_total) return DXO_ERR_INVALID_ARGUMENT;
+  if (s->device < 0) return DXO_ERR_NO_DEVICE;
+  *ms_total = 0;
+  if (launches_total) *launches_total = 0;
+  return guarded([&] {
+    DeviceContext& ctx = DeviceContext::get(s->device);
+    static thread_local cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    if (!ev_a) { cuda_check(cudaEventCreate(&ev_a), "cudaEventCreate"); cuda_check(cudaEventCreate(&ev_b), "cudaEventCreate"); }
+    for (int k = 0; k < 3; ++k) cuda_check(cudaStreamSynchronize(ctx.stream[k]), "cudaStreamSynchronize");
+    cuda_check(cudaEventRecord(ev_a, ctx.stream[0]), "cudaEventRecord");
+    std::vector<uint8_t> bytes;
+    uint64_t launches = 0;
+    for (uint32_t k = 0; k < steps; ++k) {
+      s->job->d2h_bytes = 0;
+      run_device_phase(*s->job, ctx, g_profile, bytes, g_timing);
+      launches += g_timing.num_launches;
+    }
+    cuda_check(cudaEventRecord(ev_b, ctx.stream[0]), "cudaEventRecord");
+    cuda_check(cudaEventSynchronize(ev_b), "cudaEventSynchronize");
+    cuda_check(cudaEventElapsedTime(ms_total, ev_a, ev_b), "cudaEventElapsedTime");
+    if (launches_total) *launches_total = launches;
+  });
+}
+
 void dxo_session_destroy(dxo_session* s) {
   if (!s) return;
   if (s->device >= 0) guarded([&] {

@@ -159,6 +159,10 @@ int dxo_connectivity_create(const dxo_mesh* mesh, const dxo_config* cfg, dxo_ses
 /* Runs the device hot path once. out may be NULL (results are discarded after
  * the D2H completes). */
 int dxo_session_run(dxo_session* s, dxo_bytes* out);
+/* Runs the device hot path `steps` times back to back (bench loop). *ms_total is the
+ * CUDA-event time, on the launching stream, from before the first launch of the first
+ * step to after the last step's results reached the host. */
+int dxo_session_run_steps(dxo_session* s, uint32_t steps, float* ms_total, uint64_t* launches_total);
 void dxo_session_destroy(dxo_session* s);
 
 /* Timing of the last dxo_session_run / dxo_encode on this thread, measured with

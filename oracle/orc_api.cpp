@@ -303,7 +303,8 @@ int orc_rans_decode_raw(const uint64_t* freqs, uint64_t nfreq, uint32_t precisio
       state = q * freqs[s] + r - cum[s];
       out[i] = s;
     }
-    if (end != 0) throw EncodeError(ST_INVALID_ARGUMENT, "not fully consumed");
+    while (end > 0) state = state * 256 + buf[--end];
+    if (state != l_base) throw EncodeError(ST_INVALID_ARGUMENT, "rANS stream does not unwind to the initial state");
   });
 }
 int orc_rabs_encode(uint32_t zero_prob, const uint8_t* bits, uint64_t n, dxo_bytes* out) {

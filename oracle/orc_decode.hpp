@@ -80,7 +80,10 @@ inline std::vector<uint32_t> decode_symbols_direct(const uint8_t* b, size_t len,
     state = q * freq[s] + r - cum[s];
     out[i] = s;
   }
-  if (end != 0) throw EncodeError(ST_INVALID_ARGUMENT, "rANS payload not fully consumed");
+  // Bytes emitted while the encoder still held (part of) its initial state are not needed
+  // to decode the symbols; shifting them back in must reproduce the initial state exactly.
+  while (end > 0) state = state * 256 + pb[--end];
+  if (state != l_base) throw EncodeError(ST_INVALID_ARGUMENT, "rANS stream does not unwind to the initial state");
   pos += payload;
   return out;
 }
@@ -99,7 +102,8 @@ inline std::vector<uint8_t> rabs_decode(const uint8_t* pb, size_t payload, unsig
     if (r < f1) { state = xn + r; out[i] = 1; }
     else { state = x - xn - f1; out[i] = 0; }
   }
-  if (end != 0) throw EncodeError(ST_INVALID_ARGUMENT, "rABS payload not fully consumed");
+  while (end > 0) state = (state << 8) + pb[--end];
+  if (state != L) throw EncodeError(ST_INVALID_ARGUMENT, "rABS stream does not unwind to the initial state");
   return out;
 }
 

@@ -1,0 +1,68 @@
+"""CPU: the product's host-side connectivity (flat-array corner tables, seam tables,
+Edgebreaker, sequencer — draco-oxide_b200/csrc/connectivity.cpp) against the oracle's
+independent restatement: same bytes, same tables, same traversal sequences."""
+import numpy as np
+import pytest
+
+import draco_oxide_b200 as dxo
+import meshes
+from draco_oxide_b200 import synth
+
+
+def _compare(orc, mesh):
+    drc, tr = orc.encode(mesh, trace=True)
+    s = dxo.Session(mesh, host_only=True)
+    n = len(mesh.attributes)
+    end = int(tr.get("connectivity_end", np.uint64)[0])
+    head = s.trace("head_bytes", np.uint8).tobytes()
+    assert head == drc[: end + 1 + 10 * n]  # header + connectivity + attribute section headers
+    for key in ("opposite", "corner_to_vertex", "left_most", "corners_of_edgebreaker"):
+        assert np.array_equal(s.trace(key, np.uint32), tr.get(key, np.uint32)), key
+    assert s.trace("num_vertices", np.uint64)[0] == tr.get("num_vertices", np.uint64)[0]
+    for i in range(n):
+        assert np.array_equal(s.trace(f"att{i}.sequence", np.uint32), tr.get(f"att{i}.sequence", np.uint32)), i
+        if i > 0:
+            assert np.array_equal(s.trace(f"att{i}.c2v", np.uint32), tr.get(f"att{i}.c2v", np.uint32))
+            assert np.array_equal(s.trace(f"att{i}.left_most", np.uint32), tr.get(f"att{i}.left_most", np.uint32))
+            assert np.array_equal(s.trace(f"att{i}.seam", np.uint8), tr.get(f"att{i}.seam", np.uint8))
+    s.close()
+
+
+@pytest.mark.parametrize("name", sorted(meshes.zoo().keys()))
+def test_zoo(orc, name):
+    _compare(orc, meshes.drop_unused_points(meshes.zoo()[name]))
+
+
+@pytest.mark.parametrize("name", meshes.golden_names())
+def test_reference_fixtures(orc, name):
+    _compare(orc, meshes.load_golden(name)[0])
+
+
+def test_config1(orc):
+    _compare(orc, synth.config1_mesh())
+
+
+def test_random_face_soups(orc):
+    """Random index soups: non-manifold edges, flipped faces, shared vertices — the
+    order-dependent paths of compute_table / handle_no_manifold_edges."""
+    rng = np.random.default_rng(7)
+    done = 0
+    for trial in range(200):
+        nv = int(rng.integers(4, 12))
+        nf = int(rng.integers(2, 16))
+        faces = rng.integers(0, nv, (nf, 3)).astype(np.uint32)
+        faces = faces[(faces[:, 0] != faces[:, 1]) & (faces[:, 1] != faces[:, 2]) & (faces[:, 2] != faces[:, 0])]
+        if faces.shape[0] == 0:
+            continue
+        pos = rng.random((nv, 3)).astype(np.float32)
+        m = meshes.drop_unused_points(dxo.Mesh(faces, [dxo.Attribute.from_points(pos, 0, 0)]))
+        try:
+            orc.encode(m)
+        except orc.OracleError:
+            # inputs on which the reference panics: the product must refuse them too
+            with pytest.raises(dxo.Err):
+                dxo.Session(m, host_only=True)
+            continue
+        _compare(orc, m)
+        done += 1
+    assert done > 50
