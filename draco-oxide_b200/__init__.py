@@ -135,6 +135,16 @@ class Session:
             pass
 
 
+def encode_symbols(symbols, device=-1, timing=False):
+    """entropy::symbol_coding::encode_symbols(.., DirectCoded, ..) on the device."""
+    import numpy as np
+    sym = np.ascontiguousarray(symbols, dtype=np.uint32)
+    out, ms = _capi.dxo_bytes(), (C.c_float * 3)()
+    _check(_capi.lib().dxo_encode_symbols(sym.ctypes.data_as(C.POINTER(C.c_uint32)), sym.size, device, C.byref(out), ms))
+    data = _take(out)
+    return (data, {"histogram_ms": ms[0], "table_ms": ms[1], "rans_ms": ms[2]}) if timing else data
+
+
 def set_profiling(on):
     _capi.lib().dxo_set_profiling(int(on))
 

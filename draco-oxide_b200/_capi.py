@@ -72,7 +72,7 @@ EXPORTED = [
     "dxo_config_default", "dxo_encode", "dxo_encode_batch", "dxo_free_bytes", "dxo_strerror",
     "dxo_device_count", "dxo_session_create", "dxo_connectivity_create", "dxo_session_run_steps", "dxo_session_run", "dxo_session_destroy",
     "dxo_set_profiling", "dxo_last_timing", "dxo_session_set_trace", "dxo_session_trace_get",
-    "dxo_corner_table_opposites",
+    "dxo_corner_table_opposites", "dxo_encode_symbols",
 ]
 
 _lib = None
@@ -123,5 +123,7 @@ def lib():
     L.dxo_corner_table_opposites.argtypes = [C.POINTER(C.c_uint32), C.c_uint64, C.POINTER(C.c_uint32),
                                              C.POINTER(C.c_int), C.c_int]
     L.dxo_corner_table_opposites.restype = C.c_int
+    L.dxo_encode_symbols.argtypes = [C.POINTER(C.c_uint32), C.c_uint64, C.c_int, C.POINTER(dxo_bytes), C.POINTER(C.c_float)]
+    L.dxo_encode_symbols.restype = C.c_int
     _lib = L
     return L

@@ -309,6 +309,64 @@ int dxo_session_trace_get(dxo_session* s, const char* key, const void** data, ui
   return DXO_OK;
 }
 
+// encode_symbols(symbols, _, SymbolEncodingMethod::DirectCoded, writer) on the device:
+// histogram (K8) -> table (K9) -> rANS (K10). Output = method byte, bit_length byte,
+// leb128 #symbols + table, leb128 payload size, payload — what the reference writes.
+int dxo_encode_symbols(const uint32_t* symbols, uint64_t n, int device, dxo_bytes* out, float* kernel_ms /*[3] or NULL*/) {
+  if (!symbols || !out || n == 0 || n > 0xFFFFFFF0ull) return DXO_ERR_INVALID_ARGUMENT;
+  out->data = nullptr; out->len = 0;
+  return guarded([&] {
+    DeviceContext& ctx = DeviceContext::get(device);
+    cudaStream_t s = ctx.stream[0];
+    uint32_t mx = 0, nz = 0;
+    for (uint64_t i = 0; i < n; ++i) { mx = std::max(mx, symbols[i]); nz += symbols[i] != 0; }
+    if (mx >= (1u << 22)) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "alphabet too large");
+    const uint32_t cap = mx + 2;
+    uint32_t *d_sym, *d_hist, *d_work; uint4* d_tab; uint8_t *d_tb, *d_pay; gpu::AttrStats* d_st;
+    auto alloc = [&](void** p, size_t b) { cuda_check(cudaMallocAsync(p, b, s), "cudaMallocAsync"); };
+    alloc((void**)&d_sym, n * 4); alloc((void**)&d_hist, cap * 4ull); alloc((void**)&d_work, cap * 12ull); alloc((void**)&d_tab, cap * 16ull);
+    alloc((void**)&d_tb, cap * 3ull + 16); alloc((void**)&d_pay, n * 3 + 16); alloc((void**)&d_st, sizeof(gpu::AttrStats));
+    void* d_scr; alloc(&d_scr, gpu::rans_scratch_bytes(n));
+    cuda_check(cudaMemcpyAsync(d_sym, symbols, n * 4, cudaMemcpyHostToDevice, s), "H2D");
+    gpu::init_stats(d_st, s);
+    cuda_check(cudaMemsetAsync(d_hist, 0, cap * 4ull, s), "memset");
+    // the predict kernels normally produce these two scalars
+    cuda_check(cudaMemcpyAsync(&d_st->nonzero_symbols, &nz, 4, cudaMemcpyHostToDevice, s), "H2D");
+    cuda_check(cudaMemcpyAsync(&d_st->max_symbol, &mx, 4, cudaMemcpyHostToDevice, s), "H2D");
+    cudaEvent_t ev[4];
+    for (auto& e : ev) cuda_check(cudaEventCreate(&e), "cudaEventCreate");
+    cuda_check(cudaEventRecord(ev[0], s), "rec");
+    gpu::launch_histogram(d_sym, n, d_hist, cap, d_st, s);
+    cuda_check(cudaEventRecord(ev[1], s), "rec");
+    gpu::launch_build_table(d_hist, cap, n, d_work, d_tab, d_tb, cap * 3 + 16, d_st, s);
+    cuda_check(cudaEventRecord(ev[2], s), "rec");
+    gpu::launch_rans_encode(d_sym, n, d_tab, d_scr, d_pay, d_st, s);
+    cuda_check(cudaEventRecord(ev[3], s), "rec");
+    gpu::AttrStats st;
+    cuda_check(cudaMemcpyAsync(&st, d_st, sizeof st, cudaMemcpyDeviceToHost, s), "D2H");
+    cuda_check(cudaStreamSynchronize(s), "sync");
+    if (kernel_ms) for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&kernel_ms[k], ev[k], ev[k + 1]);
+    for (auto& e : ev) cudaEventDestroy(e);
+    std::vector<uint8_t> tb(st.table_bytes), pay(st.payload_bytes);
+    int status = DXO_OK;
+    if (st.error_flags) status = (st.error_flags & gpu::kErrRansFreq) ? DXO_ERR_RANS_FREQ_TABLE : DXO_ERR_UNSUPPORTED_INPUT;
+    else {
+      cuda_check(cudaMemcpyAsync(tb.data(), d_tb, tb.size(), cudaMemcpyDeviceToHost, s), "D2H");
+      cuda_check(cudaMemcpyAsync(pay.data(), d_pay, pay.size(), cudaMemcpyDeviceToHost, s), "D2H");
+    }
+    for (void* p : {(void*)d_sym, (void*)d_hist, (void*)d_work, (void*)d_tab, (void*)d_tb, (void*)d_pay, (void*)d_st, d_scr}) cudaFreeAsync(p, s);
+    cuda_check(cudaStreamSynchronize(s), "sync");
+    if (status != DXO_OK) throw Error(status, "device reported an entropy coding error");
+    ByteSink w;
+    w.u8(1);
+    w.u8((uint8_t)st.bit_length);
+    w.bytes(tb);
+    w.varint(pay.size());
+    w.bytes(pay);
+    if (int st2 = give(w.data, out)) throw Error(st2, "out of memory");
+  });
+}
+
 int dxo_corner_table_opposites(const uint32_t* vertex_of_corner, uint64_t num_faces, uint32_t* opposite_out, int* exact_out, int device) {
   if (!vertex_of_corner || !opposite_out || !exact_out || num_faces == 0 || num_faces > 0x2AAAAAAAull) return DXO_ERR_INVALID_ARGUMENT;
   return guarded([&] {

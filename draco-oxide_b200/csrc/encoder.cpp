@@ -252,6 +252,7 @@ void MeshJob::upload(DeviceContext& ctx) {
     d.table_bytes = dalloc<uint8_t>(d.table_capacity, s);
     d.payload_capacity = 3 * (uint64_t)M * p.ncomp_q + 16;  // <= P/8 <= 2.5 bytes per symbol + tail
     d.payload = dalloc<uint8_t>(d.payload_capacity, s);
+    d.rans_scratch = dalloc<uint8_t>(gpu::rans_scratch_bytes((uint64_t)M * p.ncomp_q), s);
     d.stats = dalloc<gpu::AttrStats>(1, s);
   }
   cuda_check(cudaEventRecord(ctx.ev_join[0], s), "cudaEventRecord");
@@ -345,7 +346,8 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     gpu::launch_build_table(d.hist, p.hist_capacity, S, d.work, d.rans_table, d.table_bytes, d.table_capacity, d.stats, s);
     prof.end(s);
     prof.begin("K10_rans_encode", 4 * S, s);
-    gpu::launch_rans_encode(d.symbols, S, d.rans_table, d.payload, d.stats, s);
+    gpu::launch_rans_encode(d.symbols, S, d.rans_table, d.rans_scratch, d.payload, d.stats, s);
+    prof.launches += 1 + (gpu::rans_num_chunks(S) > 1 ? 4 : 0);  // speculate + relax rounds + fix-up + gather
     prof.end(s);
   }
   cuda_check(cudaGetLastError(), "kernel launch");

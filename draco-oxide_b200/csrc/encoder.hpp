@@ -61,7 +61,7 @@ struct AttrDevice {
   uint32_t *corner_vertex = nullptr, *left_most = nullptr, *seq = nullptr; uint8_t* seam = nullptr;
   // intermediates / outputs
   int32_t* quant = nullptr; uint32_t *rank = nullptr, *symbols = nullptr, *hist = nullptr, *work = nullptr;
-  uint8_t *side = nullptr, *table_bytes = nullptr, *payload = nullptr; uint4* rans_table = nullptr;
+  uint8_t *side = nullptr, *table_bytes = nullptr, *payload = nullptr, *rans_scratch = nullptr; uint4* rans_table = nullptr;
   gpu::AttrStats* stats = nullptr;
   uint64_t payload_capacity = 0; uint32_t table_capacity = 0;
 };

@@ -838,11 +838,15 @@ __global__ void __launch_bounds__(kTableThreads) build_table_kernel(const uint32
       const uint32_t extra = nb - 1;
       table_bytes[off] = (uint8_t)((d << 2) | extra);
       for (uint32_t b = 0; b < extra; ++b) table_bytes[off + 1 + b] = (uint8_t)(d >> (8 * (b + 1) - 2));
-      // K10 lookup: x / d for x < 2^30 as (x * magic) >> shift, exact (DESIGN.md "rANS division")
-      const uint32_t l = (d <= 1) ? 0u : (32u - (uint32_t)__clz(d - 1));  // ceil(log2 d)
-      const uint32_t shift = 30u + l;
-      const unsigned long long magic = ((1ull << shift) + d - 1) / d;
-      rans_table[i] = make_uint4(d, cum, (uint32_t)magic, shift);
+      // K10 lookup: floor(x / d) for x < 2^30 as umulhi(x, M) >> lp with lp = ceil(log2 d) - 1,
+      // M = ceil(2^(32+lp) / d) < 2^32 (exact, DESIGN.md "rANS division"). d = 1 uses
+      // umulhi(x, 2^32 - 1) + 1 = x (x >= 1), signalled by lp = 0, M = 0xFFFFFFFF.
+      uint32_t lp = 0, magic = 0xFFFFFFFFu;
+      if (d >= 2) {
+        lp = 31u - (uint32_t)__clz(d - 1);  // ceil(log2 d) - 1
+        magic = (uint32_t)(((1ull << (32u + lp)) + d - 1) / d);
+      }
+      rans_table[i] = make_uint4(d, cum, magic, lp);
       cum += d;
     } else {
       if (nb) table_bytes[off] = tk;
@@ -859,60 +863,303 @@ void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t t
 
 // ---------------------------------------------------------------------------------------
 // K10 — RansCoder::write / flush (rans.rs:33-68), symbols fed last-to-first
-// (symbol_coding.rs:161). The state recurrence is inherently serial, so one warp
-// owns the stream: lanes prefetch 32 symbols and their table rows with coalesced
-// loads, the state update runs warp-uniformly on values broadcast by shuffles.
-// x / f uses the exact reciprocal from K9: x < 2^30, f <= 2^20.
-__global__ void __launch_bounds__(32) rans_encode_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                         uint8_t* __restrict__ out, AttrStats* stats) {
-  const uint32_t lane = threadIdx.x;
-  const uint32_t P = stats->precision;
-  if (stats->error_flags) { if (lane == 0) stats->payload_bytes = 0; return; }
-  const uint32_t K = stats->num_table_symbols;
-  const uint32_t l_base = (1u << P) << 2;
-  const uint32_t full = 1u << P;
-  uint32_t x = l_base;
-  unsigned long long pos = 0;
-  uint32_t err = 0;
-  for (unsigned long long base = n; base > 0;) {
-    const uint32_t cnt = base >= 32 ? 32u : (uint32_t)base;
-    uint4 e = make_uint4(1, 0, 0, 0);
-    if (lane < cnt) {
-      const uint32_t sym = __ldcs(symbols + (base - 1 - lane));
-      if (sym < K) e = __ldg(table + sym); else err |= kErrRansFreq;
-      if (e.x == 0) { err |= kErrRansFreq; e.x = 1; }
-    }
-    for (uint32_t j = 0; j < cnt; ++j) {
-      const uint32_t f = __shfl_sync(0xFFFFFFFFu, e.x, j);
-      const uint32_t cum = __shfl_sync(0xFFFFFFFFu, e.y, j);
-      const uint32_t magic = __shfl_sync(0xFFFFFFFFu, e.z, j);
-      const uint32_t shift = __shfl_sync(0xFFFFFFFFu, e.w, j);
-      const uint32_t thr = f << 10;  // ((l_base >> P) * f) << 8
-      while (x >= thr) {
-        if (lane == 0) out[pos] = (uint8_t)x;
-        ++pos;
-        x >>= 8;
+// (symbol_coding.rs:161).
+//
+// The state recurrence x -> x' is serial, but it FORGETS: two encoders that start from
+// different states and see the same symbols end up in exactly the same state after a
+// few hundred to a few thousand symbols (every renormalisation shifts the low state
+// bits — where small differences live — out into the byte stream). That makes an exact
+// speculative-parallel coder possible (DESIGN.md "Parallel rANS"):
+//   round 0   every chunk of kRansChunk steps is encoded by its own CTA, starting W
+//             steps early from an arbitrary state (warm-up); the state reached at the
+//             chunk start is the chunk's *claimed* entering state.
+//   round r   a chunk whose claimed entering state differs from the exit state of its
+//             predecessor is re-encoded from that exit state (Jacobi relaxation; after
+//             round r chunks 0..r are certainly right, typically 1-2 rounds fix all).
+//   fix-up    a single CTA walks the chunks in order and re-encodes any that is still
+//             inconsistent, so the result never depends on the speculation succeeding.
+//   gather    chunk byte strings are concatenated (prefix sum of their lengths) and the
+//             2-bit-tagged final state is appended.
+// The bytes are those of the sequential coder by construction: chunk 0 starts from
+// l_base and every other chunk is (re-)encoded from its predecessor's true exit state.
+//
+// Inside a chunk, one CTA of two warps works as producer / consumer:
+//   * PRODUCER warp: prefetches symbols several groups ahead (coalesced), gathers their
+//     table rows, derives the three renormalisation thresholds and fills a ring of
+//     32-row stages; it also turns the consumer's per-step record (x before the step,
+//     byte count) into output bytes with a warp scan, 32 steps at a time.
+//   * CONSUMER warp: the serial chain only. Per symbol: two broadcast LDS.128,
+//     q = ((umulhi(x, M) + c) >> lp) >> 8k with M = ceil(2^(32+lp)/f), lp = ceil(log2 f) - 1
+//     (exact for x < 2^30, DESIGN.md "rANS division"; the multiply does not wait for k),
+//     k from three independent compares and a two-level select,
+//     x' = (x >> 8k) + cum + q * (2^P - f), and one STS of (x, k) for the producer.
+// Stages are handed over with named barriers (bar.arrive / bar.sync), one pair per stage.
+constexpr int kRansStages = 4;
+constexpr int kRansLookahead = 3;      // groups of symbols in flight in the producer's registers
+constexpr uint32_t kRansChunk = 4096;  // steps per chunk (multiple of 32)
+constexpr uint32_t kRansWarmup = 8192; // speculative warm-up steps before a chunk (multiple of 32)
+constexpr int kRansRounds = 3;         // parallel relaxation rounds before the sequential fix-up
+
+// stage row: a = {thr1, thr2, thr3, cum}, b = {M, lp, g = 2^P - f, c = (f == 1)}
+
+__device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+struct RansShared {
+  uint4 rows_a[kRansStages][32];
+  uint4 rows_b[kRansStages][32];
+  uint32_t xk[kRansStages][32];
+  uint32_t x_main, x_exit, nbytes, err;
+};
+
+// Encodes steps [e_begin, e_end) of the stream (step e codes symbols[n - 1 - e]) starting
+// from state x_in; bytes are produced only for steps >= e_main (e_begin..e_main is the
+// warm-up). All three bounds except e_end are multiples of 32. Called by a 64-thread CTA.
+// Results in sh.x_main (state at e_main), sh.x_exit, sh.nbytes after the final barrier.
+__device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t* __restrict__ symbols, unsigned long long n,
+                                                  const uint4* __restrict__ table, uint32_t K, uint32_t P, unsigned long long e_begin,
+                                                  unsigned long long e_main, unsigned long long e_end, uint32_t x_in, uint8_t* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long steps = e_end - e_begin;
+  const unsigned long long ngroups = (steps + 31) / 32;
+  const unsigned long long g_main = (e_main - e_begin) / 32;  // first group that produces bytes
+  // barrier ids: 1..kRansStages = FULL, kRansStages+1..2*kRansStages = EMPTY
+  if (warp == 0) {
+    // ------------------------------- consumer: the serial chain -------------------------------
+    uint32_t x = x_in;
+    for (unsigned long long g = 0; g < ngroups; ++g) {
+      const int s = (int)(g % kRansStages);
+      const uint32_t cnt = (g + 1 == ngroups) ? (uint32_t)(steps - 32 * g) : 32u;
+      if (g == g_main && lane == 0) sh.x_main = x;
+      named_bar_sync(1 + s);
+      const uint32_t ra = (uint32_t)__cvta_generic_to_shared(&sh.rows_a[s][0]);
+      const uint32_t rb = (uint32_t)__cvta_generic_to_shared(&sh.rows_b[s][0]);
+      uint32_t* xk = sh.xk[s];
+      // Rows are fetched three steps ahead with volatile shared loads so that the ~30-cycle
+      // LDS latency never sits on the x -> x' chain.
+      auto load_row = [&](uint32_t j, uint4& a, uint4& b) {
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(ra + j * 16u));
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(rb + j * 16u));
+      };
+      auto step = [&](uint32_t j, const uint4& a, const uint4& b) {
+        const uint32_t hi = __umulhi(x, b.x) + b.w;                     // floor(x * M / 2^32) (+1 for f = 1), independent of k
+        const uint32_t q0 = hi >> b.y;                                  // floor(x / f): still independent of k
+        const bool p1 = x >= a.x, p2 = x >= a.y, p3 = x >= a.z;
+        const uint32_t k8 = p2 ? (p3 ? 24u : 16u) : (p1 ? 8u : 0u);
+        if (lane == 0) xk[j] = x + (k8 << 27);                          // x < 2^30; k8/8 in bits 30..31
+        x = (q0 >> k8) * b.z + ((x >> k8) + a.w);
+      };
+      if (cnt == 32) {
+        uint4 a0, a1, a2, a3; uint4 b0, b1, b2, b3;
+        load_row(0, a0, b0); load_row(1, a1, b1); load_row(2, a2, b2);
+#pragma unroll
+        for (uint32_t j = 0; j < 32; ++j) {
+          if (j + 3 < 32) load_row(j + 3, a3, b3);
+          step(j, a0, b0);
+          a0 = a1; b0 = b1; a1 = a2; b1 = b2; a2 = a3; b2 = b3;
+        }
+      } else {
+        for (uint32_t j = 0; j < cnt; ++j) { uint4 a, b; load_row(j, a, b); step(j, a, b); }
       }
-      const uint32_t q = (uint32_t)(((unsigned long long)x * magic) >> shift);
-      x = x + q * (full - f) + cum;  // (q << P) + (x - q f) + cum
+      named_bar_arrive(1 + kRansStages + s);
     }
-    base -= cnt;
+    if (lane == 0) { sh.x_exit = x; if (g_main >= ngroups) sh.x_main = x; }
+  } else {
+    // ------------------------------- producer / byte writer -----------------------------------
+    uint32_t err = 0;
+    uint32_t pos = 0;
+    uint32_t pre[kRansLookahead];
+    auto load_syms = [&](unsigned long long g) -> uint32_t {
+      if (g >= ngroups) return 0;
+      const unsigned long long e = e_begin + 32 * g + lane;  // this lane's step
+      return e < e_end ? __ldcs(symbols + (n - 1 - e)) : 0u;
+    };
+#pragma unroll
+    for (int d = 0; d < kRansLookahead; ++d) pre[d] = load_syms(d);
+    auto emit_bytes = [&](int s, uint32_t cnt) {
+      const uint32_t v = lane < cnt ? sh.xk[s][lane] : 0u;
+      const uint32_t k = v >> 30, xv = v & 0x3FFFFFFFu;
+      uint32_t inc = k;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= (uint32_t)d) inc += o; }
+      uint8_t* dst = out + pos + (inc - k);
+      if (k > 0) dst[0] = (uint8_t)xv;
+      if (k > 1) dst[1] = (uint8_t)(xv >> 8);
+      if (k > 2) dst[2] = (uint8_t)(xv >> 16);
+      pos += __shfl_sync(0xFFFFFFFFu, inc, 31);
+    };
+    for (unsigned long long g = 0; g < ngroups; ++g) {
+      const int s = (int)(g % kRansStages);
+      if (g >= kRansStages) {  // the stage is being reused: wait until the consumer is done with it, then write its bytes
+        named_bar_sync(1 + kRansStages + s);
+        if (g - kRansStages >= g_main) emit_bytes(s, 32);
+      }
+      const uint32_t sym = pre[0];
+#pragma unroll
+      for (int d = 0; d + 1 < kRansLookahead; ++d) pre[d] = pre[d + 1];
+      pre[kRansLookahead - 1] = load_syms(g + kRansLookahead);
+      const uint32_t cnt = (g + 1 == ngroups) ? (uint32_t)(steps - 32 * g) : 32u;
+      uint4 e = make_uint4(1, 0, 0xFFFFFFFFu, 0);
+      if (lane < cnt) {
+        if (sym < K) e = __ldg(table + sym); else err |= kErrRansFreq;
+        if (e.x == 0) { err |= kErrRansFreq; e = make_uint4(1, 0, 0xFFFFFFFFu, 0); }
+      }
+      const uint32_t thr1 = e.x << 10;  // f <= 2^20: fits; x < 2^30 never reaches the threshold of f = 2^20
+      uint4 a;
+      a.x = thr1;
+      a.y = thr1 >= (1u << 24) ? 0xFFFFFFFFu : (thr1 << 8);   // x >> 8 >= thr1  <=>  x >= thr1 << 8
+      a.z = thr1 >= (1u << 16) ? 0xFFFFFFFFu : (thr1 << 16);
+      a.w = e.y;
+      const uint4 b = make_uint4(e.z, e.w, (1u << P) - e.x, e.x == 1u ? 1u : 0u);  // {M, lp, g, c}
+      sh.rows_a[s][lane] = a;
+      sh.rows_b[s][lane] = b;
+      named_bar_arrive(1 + s);
+    }
+    // drain: bytes of the last min(ngroups, kRansStages) groups, in order
+    const unsigned long long first_pending = ngroups > (unsigned long long)kRansStages ? ngroups - kRansStages : 0;
+    for (unsigned long long g = first_pending; g < ngroups; ++g) {
+      const int s = (int)(g % kRansStages);
+      const uint32_t cnt = (g + 1 == ngroups) ? (uint32_t)(steps - 32 * g) : 32u;
+      named_bar_sync(1 + kRansStages + s);
+      if (g >= g_main) emit_bytes(s, cnt);
+    }
+    err = __reduce_or_sync(0xFFFFFFFFu, err);
+    if (lane == 0) { sh.nbytes = pos; sh.err = err; }
   }
-  err = __reduce_or_sync(0xFFFFFFFFu, err);
-  if (lane == 0) {
-    uint32_t t = x - l_base;  // flush (:48-68)
+  __syncthreads();
+}
+
+// chunk state arrays (device scratch): start[J] = entering state each chunk was last encoded from,
+// exit_a / exit_b[J] = exit states (double-buffered across rounds), nbytes[J].
+struct RansChunkState { uint32_t* start; uint32_t* exit_a; uint32_t* exit_b; uint32_t* nbytes; };
+
+__device__ __forceinline__ uint64_t rans_chunk_capacity() { return 3ull * kRansChunk + 8; }
+
+// round 0: speculative encode of every chunk (grid = number of chunks)
+__global__ void __launch_bounds__(64) rans_speculate_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                            uint8_t* __restrict__ scratch, RansChunkState cs, AttrStats* stats) {
+  __shared__ RansShared sh;
+  if (stats->error_flags) return;
+  const uint32_t P = stats->precision, K = stats->num_table_symbols;
+  const unsigned long long j = blockIdx.x;
+  const unsigned long long e_main = j * kRansChunk;
+  const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
+  const unsigned long long e_begin = e_main > kRansWarmup ? e_main - kRansWarmup : 0;  // warm-up from step 0 is exact
+  const uint32_t l_base = 4u << P;
+  rans_encode_range(sh, symbols, n, table, K, P, e_begin, e_main, e_end, l_base, scratch + j * rans_chunk_capacity());
+  if (threadIdx.x == 0) {
+    cs.start[j] = sh.x_main;
+    cs.exit_a[j] = sh.x_exit;
+    cs.nbytes[j] = sh.nbytes;
+    if (sh.err) atomicOr(&stats->error_flags, sh.err);
+  }
+}
+
+// round r >= 1: re-encode the chunks whose entering state does not match the predecessor's exit
+__global__ void __launch_bounds__(64) rans_relax_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                        uint8_t* __restrict__ scratch, RansChunkState cs, const uint32_t* __restrict__ exit_cur,
+                                                        uint32_t* __restrict__ exit_next, AttrStats* stats) {
+  __shared__ RansShared sh;
+  if (stats->error_flags) return;
+  const uint32_t P = stats->precision, K = stats->num_table_symbols;
+  const unsigned long long j = blockIdx.x;
+  const uint32_t l_base = 4u << P;
+  const uint32_t in = j == 0 ? l_base : exit_cur[j - 1];
+  if (in == cs.start[j]) { if (threadIdx.x == 0) exit_next[j] = exit_cur[j]; return; }
+  const unsigned long long e_main = j * kRansChunk;
+  const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
+  rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, in, scratch + j * rans_chunk_capacity());
+  if (threadIdx.x == 0) {
+    cs.start[j] = in;
+    exit_next[j] = sh.x_exit;
+    cs.nbytes[j] = sh.nbytes;
+    if (sh.err) atomicOr(&stats->error_flags, sh.err);
+  }
+}
+
+// sequential fix-up (one CTA): guarantees exactness whatever the speculation did
+__global__ void __launch_bounds__(64) rans_fixup_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                        uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t* __restrict__ exit_final,
+                                                        uint32_t num_chunks, AttrStats* stats) {
+  __shared__ RansShared sh;
+  __shared__ uint32_t s_in;
+  if (stats->error_flags) return;
+  const uint32_t P = stats->precision, K = stats->num_table_symbols;
+  const uint32_t l_base = 4u << P;
+  for (uint32_t j = 0; j < num_chunks; ++j) {
+    if (threadIdx.x == 0) s_in = j == 0 ? l_base : exit_final[j - 1];
+    __syncthreads();
+    const uint32_t in = s_in;
+    __syncthreads();                  // s_in is rewritten by thread 0 in the next iteration
+    if (in == cs.start[j]) continue;  // uniform: every thread reads the same values
+    const unsigned long long e_main = (unsigned long long)j * kRansChunk;
+    const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
+    rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, in, scratch + (unsigned long long)j * rans_chunk_capacity());
+    if (threadIdx.x == 0) {
+      cs.start[j] = in;
+      exit_final[j] = sh.x_exit;
+      cs.nbytes[j] = sh.nbytes;
+      if (sh.err) atomicOr(&stats->error_flags, sh.err);
+    }
+    __syncthreads();
+  }
+}
+
+// gather: chunk j's bytes go to payload[sum_{i<j} nbytes[i]]; the last CTA appends the flush bytes
+__global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restrict__ scratch, RansChunkState cs, const uint32_t* __restrict__ exit_final,
+                                                          uint32_t num_chunks, uint8_t* __restrict__ out, AttrStats* stats) {
+  __shared__ uint32_t s_part[8];
+  __shared__ uint32_t s_off;
+  if (stats->error_flags) { if (blockIdx.x == 0 && threadIdx.x == 0) stats->payload_bytes = 0; return; }
+  const uint32_t j = blockIdx.x;
+  uint32_t acc = 0;
+  for (uint32_t i = threadIdx.x; i < j; i += blockDim.x) acc += cs.nbytes[i];
+  acc = __reduce_add_sync(0xFFFFFFFFu, acc);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; ++w) t += s_part[w]; s_off = t; }
+  __syncthreads();
+  const uint32_t off = s_off, nb = cs.nbytes[j];
+  const uint8_t* src = scratch + (unsigned long long)j * rans_chunk_capacity();
+  for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) out[off + i] = src[i];
+  if (j + 1 == num_chunks && threadIdx.x == 0) {
+    uint32_t pos = off + nb, err = 0;
+    const uint32_t l_base = 4u << stats->precision;
+    const uint32_t t = exit_final[j] - l_base;  // flush (:48-68)
     if (t < (1u << 6)) { out[pos++] = (uint8_t)t; }
     else if (t < (1u << 14)) { const uint32_t v = 0x4000u + t; out[pos++] = (uint8_t)v; out[pos++] = (uint8_t)(v >> 8); }
     else if (t < (1u << 22)) { const uint32_t v = 0x800000u + t; out[pos++] = (uint8_t)v; out[pos++] = (uint8_t)(v >> 8); out[pos++] = (uint8_t)(v >> 16); }
     else if (t < (1u << 30)) { const uint32_t v = 0xC0000000u + t; out[pos++] = (uint8_t)v; out[pos++] = (uint8_t)(v >> 8); out[pos++] = (uint8_t)(v >> 16); out[pos++] = (uint8_t)(v >> 24); }
     else err |= kErrRansState;
-    stats->payload_bytes = (uint32_t)pos;
+    stats->payload_bytes = pos;
     if (err) atomicOr(&stats->error_flags, err);
   }
 }
 
-void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, uint8_t* payload, AttrStats* stats, cudaStream_t s) {
-  rans_encode_kernel<<<1, 32, 0, s>>>(symbols, num_symbols, rans_table, payload, stats);
+uint32_t rans_num_chunks(uint64_t num_symbols) { return (uint32_t)((num_symbols + kRansChunk - 1) / kRansChunk); }
+size_t rans_scratch_bytes(uint64_t num_symbols) {
+  const size_t J = rans_num_chunks(num_symbols);
+  return J * (3ull * kRansChunk + 8) + 256 + 4 * J * sizeof(uint32_t) + 64;
+}
+
+void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, void* scratch, uint8_t* payload,
+                        AttrStats* stats, cudaStream_t s) {
+  const uint32_t J = rans_num_chunks(num_symbols);
+  uint8_t* bytes = (uint8_t*)scratch;
+  size_t off = ((size_t)J * (3ull * kRansChunk + 8) + 255) / 256 * 256;
+  uint32_t* u = (uint32_t*)(bytes + off);
+  RansChunkState cs{u, u + J, u + 2 * (size_t)J, u + 3 * (size_t)J};
+  rans_speculate_kernel<<<J, 64, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, stats);
+  uint32_t* cur = cs.exit_a;
+  uint32_t* nxt = cs.exit_b;
+  if (J > 1) {
+    for (int r = 0; r < kRansRounds; ++r) {
+      rans_relax_kernel<<<J, 64, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, cur, nxt, stats);
+      uint32_t* t = cur; cur = nxt; nxt = t;
+    }
+    rans_fixup_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, cur, J, stats);
+  }
+  rans_gather_kernel<<<J, 256, 0, s>>>(bytes, cs, cur, J, payload, stats);
 }
 
 // ---------------------------------------------------------------------------------------

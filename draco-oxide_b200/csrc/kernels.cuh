@@ -72,10 +72,14 @@ void launch_predict_delta(const uint32_t* seq, uint32_t n, TableDev t, QuantDev 
 void launch_histogram(const uint32_t* symbols, uint64_t num_symbols, uint32_t* hist, uint32_t hist_capacity, AttrStats* stats, cudaStream_t s);
 // ---- K9: probability table normalisation + serialisation + rANS lookup table (rans.rs:146-230) ----
 // rans_table entries: {freq, cumulative, magic multiplier, shift}
-void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t total_symbols, uint32_t* work /*5*capacity*/, uint4* rans_table,
+void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t total_symbols, uint32_t* work /*3*capacity*/, uint4* rans_table,
                         uint8_t* table_bytes, uint32_t table_bytes_capacity, AttrStats* stats, cudaStream_t s);
 // ---- K10: rANS emission, serial within the stream (rans.rs:33-68) ----
-void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, uint8_t* payload, AttrStats* stats, cudaStream_t s);
+// scratch: rans_scratch_bytes(num_symbols) bytes of device memory (chunk byte strings + chunk states)
+size_t rans_scratch_bytes(uint64_t num_symbols);
+uint32_t rans_num_chunks(uint64_t num_symbols);
+void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, void* scratch, uint8_t* payload,
+                        AttrStats* stats, cudaStream_t s);
 // ---- K12: half-edge matching by radix sort (corner_table/mod.rs:252-340, fast path) ----
 // keys/vals/tmp are caller-provided scratch (see corner_table_scratch_bytes).
 size_t corner_table_scratch_bytes(uint64_t num_corners);

@@ -197,6 +197,12 @@ int dxo_last_timing(dxo_timing* out);
 void dxo_session_set_trace(dxo_session* s, int enabled);
 int dxo_session_trace_get(dxo_session* s, const char* key, const void** data, uint64_t* nbytes);
 
+/* encode_symbols(symbols, _, SymbolEncodingMethod::DirectCoded, writer)
+ * (encode/entropy/symbol_coding.rs:17-55) on the device: histogram, probability table,
+ * rANS. *out receives exactly the bytes the reference writes. kernel_ms (optional, 3
+ * floats) receives the device time of the histogram, table and rANS kernels. */
+int dxo_encode_symbols(const uint32_t* symbols, uint64_t n, int device, dxo_bytes* out, float* kernel_ms);
+
 /* Corner-table build on the device (half-edge matching by radix sort;
  * replaces CornerTable::compute_table, core/corner_table/mod.rs:252-340).
  * vertex_of_corner: 3*num_faces vertex ids. opposite_out: 3*num_faces entries,

@@ -183,3 +183,28 @@ def test_timing_record_counts_our_kernels():
     for k in ("K1_minmax", "K2_quantize", "K3_oct_quantize", "K4_predict_parallelogram", "K5_predict_normal",
               "K6_predict_texcoord", "K8_histogram", "K9_build_table", "K10_rans_encode"):
         assert k in names
+
+
+@pytest.mark.parametrize("case", ["uniform_small", "geometric", "sparse_large_alphabet", "single_symbol", "two_symbols", "all_zero_but_one"])
+def test_encode_symbols_entry(orc, case):
+    """Entropy stage alone (encode_symbols, symbol_coding.rs:17-55): bytes equal the oracle's,
+    covering the table-normalisation corner cases (deficit, excess, zero runs > 64)."""
+    rng = np.random.default_rng(11)
+    if case == "uniform_small":
+        sym = rng.integers(0, 23, 5000)
+    elif case == "geometric":
+        sym = np.minimum(rng.geometric(0.02, 200000) - 1, 4000)
+    elif case == "sparse_large_alphabet":
+        sym = rng.choice(np.array([0, 1, 70, 200, 201, 1000, 5000, 70000]), 30000, p=[.5, .2, .1, .05, .05, .05, .04, .01])
+    elif case == "single_symbol":
+        sym = np.full(1000, 7)
+    elif case == "two_symbols":
+        sym = np.array([0, 300] * 50 + [300])
+    else:
+        sym = np.zeros(100000, np.int64)
+        sym[777] = 9
+    sym = sym.astype(np.uint32)
+    got = dxo.encode_symbols(sym)
+    assert got == orc.encode_symbols(sym)
+    dec, used = orc.decode_symbols(got, sym.size)
+    assert used == len(got) and np.array_equal(dec, sym)
