@@ -1,6 +1,7 @@
 // extern "C" surface declared in include/dxo.h.
 #include <atomic>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <numeric>
 #include <thread>
@@ -346,6 +347,7 @@ int dxo_encode_symbols(const uint32_t* symbols, uint64_t n, int device, dxo_byte
     cuda_check(cudaMemcpyAsync(&st, d_st, sizeof st, cudaMemcpyDeviceToHost, s), "D2H");
     cuda_check(cudaStreamSynchronize(s), "sync");
     if (kernel_ms) for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&kernel_ms[k], ev[k], ev[k + 1]);
+    if (getenv("DXO_RANS_DEBUG")) fprintf(stderr, "[dxo] rANS chunks=%u relaxed=%u fixup=%u\n", gpu::rans_num_chunks(n), st.pad[0], st.pad[1]);
     for (auto& e : ev) cudaEventDestroy(e);
     std::vector<uint8_t> tb(st.table_bytes), pay(st.payload_bytes);
     int status = DXO_OK;

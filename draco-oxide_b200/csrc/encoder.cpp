@@ -347,7 +347,7 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     prof.end(s);
     prof.begin("K10_rans_encode", 4 * S, s);
     gpu::launch_rans_encode(d.symbols, S, d.rans_table, d.rans_scratch, d.payload, d.stats, s);
-    prof.launches += 1 + (gpu::rans_num_chunks(S) > 1 ? 4 : 0);  // speculate + relax rounds + fix-up + gather
+    prof.launches += gpu::rans_launch_count(S) - 1;  // speculate + relax rounds + fix-up + gather
     prof.end(s);
   }
   cuda_check(cudaGetLastError(), "kernel launch");

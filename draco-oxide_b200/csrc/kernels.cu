@@ -10,6 +10,8 @@
 
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace dxo {
 namespace gpu {
 
@@ -74,6 +76,7 @@ __global__ void init_stats_kernel(AttrStats* st) {
     st->wrap_max = (int32_t)0x80000000;
     st->nonzero_symbols = 0; st->max_symbol = 0; st->error_flags = 0;
     st->bit_length = 0; st->precision = 0; st->num_table_symbols = 0; st->table_bytes = 0; st->payload_bytes = 0;
+    st->pad[0] = st->pad[1] = st->pad[2] = 0;
   }
 }
 void init_stats(AttrStats* stats, cudaStream_t s) { init_stats_kernel<<<1, 32, 0, s>>>(stats); }
@@ -888,17 +891,34 @@ void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t t
 //     table rows, derives the three renormalisation thresholds and fills a ring of
 //     32-row stages; it also turns the consumer's per-step record (x before the step,
 //     byte count) into output bytes with a warp scan, 32 steps at a time.
+//     (Warps map to SM sub-partitions by warp index; a CTA carries two producer/consumer
+//     pairs and swaps the roles on odd CTAs so the consumers of an SM spread over all four
+//     schedulers.)
 //   * CONSUMER warp: the serial chain only. Per symbol: two broadcast LDS.128,
 //     q = ((umulhi(x, M) + c) >> lp) >> 8k with M = ceil(2^(32+lp)/f), lp = ceil(log2 f) - 1
 //     (exact for x < 2^30, DESIGN.md "rANS division"; the multiply does not wait for k),
 //     k from three independent compares and a two-level select,
 //     x' = (x >> 8k) + cum + q * (2^P - f), and one STS of (x, k) for the producer.
 // Stages are handed over with named barriers (bar.arrive / bar.sync), one pair per stage.
-constexpr int kRansStages = 4;
+constexpr int kRansStages = 3;        // 2 pairs x (3 FULL + 3 EMPTY + 1 END) named barriers = 14 of the 15 available
 constexpr int kRansLookahead = 3;      // groups of symbols in flight in the producer's registers
-constexpr uint32_t kRansChunk = 4096;  // steps per chunk (multiple of 32)
-constexpr uint32_t kRansWarmup = 8192; // speculative warm-up steps before a chunk (multiple of 32)
-constexpr int kRansRounds = 3;         // parallel relaxation rounds before the sequential fix-up
+// steps per chunk / speculative warm-up steps (multiples of 32) / parallel relaxation rounds before
+// the sequential fix-up. Defaults tuned on B200 (profiles/); DXO_RANS_CHUNK, DXO_RANS_WARMUP and
+// DXO_RANS_ROUNDS override them for experiments. Correctness never depends on these values.
+struct RansPlan { uint32_t chunk, warmup; int rounds; };
+static RansPlan rans_plan() {
+  static RansPlan plan = [] {
+    RansPlan p{8192, 16384, 3};
+    if (const char* e = getenv("DXO_RANS_CHUNK")) p.chunk = (uint32_t)atoi(e);
+    if (const char* e = getenv("DXO_RANS_WARMUP")) p.warmup = (uint32_t)atoi(e);
+    if (const char* e = getenv("DXO_RANS_ROUNDS")) p.rounds = atoi(e);
+    p.chunk = (p.chunk < 32 ? 32 : p.chunk) / 32 * 32;
+    p.warmup = p.warmup / 32 * 32;
+    if (p.rounds < 0) p.rounds = 0;
+    return p;
+  }();
+  return plan;
+}
 
 // stage row: a = {thr1, thr2, thr3, cum}, b = {M, lp, g = 2^P - f, c = (f == 1)}
 
@@ -918,20 +938,21 @@ struct RansShared {
 // Results in sh.x_main (state at e_main), sh.x_exit, sh.nbytes after the final barrier.
 __device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t* __restrict__ symbols, unsigned long long n,
                                                   const uint4* __restrict__ table, uint32_t K, uint32_t P, unsigned long long e_begin,
-                                                  unsigned long long e_main, unsigned long long e_end, uint32_t x_in, uint8_t* __restrict__ out) {
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                                                  unsigned long long e_main, unsigned long long e_end, uint32_t x_in, uint8_t* __restrict__ out,
+                                                  int bar_base, bool is_consumer) {
+  const uint32_t lane = threadIdx.x & 31;
   const unsigned long long steps = e_end - e_begin;
   const unsigned long long ngroups = (steps + 31) / 32;
   const unsigned long long g_main = (e_main - e_begin) / 32;  // first group that produces bytes
-  // barrier ids: 1..kRansStages = FULL, kRansStages+1..2*kRansStages = EMPTY
-  if (warp == 0) {
+  // barrier ids: bar_base + s = FULL[s], bar_base + kRansStages + s = EMPTY[s], bar_base + 2 * kRansStages = END
+  if (is_consumer) {
     // ------------------------------- consumer: the serial chain -------------------------------
     uint32_t x = x_in;
     for (unsigned long long g = 0; g < ngroups; ++g) {
       const int s = (int)(g % kRansStages);
       const uint32_t cnt = (g + 1 == ngroups) ? (uint32_t)(steps - 32 * g) : 32u;
       if (g == g_main && lane == 0) sh.x_main = x;
-      named_bar_sync(1 + s);
+      named_bar_sync(bar_base + s);
       const uint32_t ra = (uint32_t)__cvta_generic_to_shared(&sh.rows_a[s][0]);
       const uint32_t rb = (uint32_t)__cvta_generic_to_shared(&sh.rows_b[s][0]);
       uint32_t* xk = sh.xk[s];
@@ -961,7 +982,7 @@ __device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t
       } else {
         for (uint32_t j = 0; j < cnt; ++j) { uint4 a, b; load_row(j, a, b); step(j, a, b); }
       }
-      named_bar_arrive(1 + kRansStages + s);
+      named_bar_arrive(bar_base + kRansStages + s);
     }
     if (lane == 0) { sh.x_exit = x; if (g_main >= ngroups) sh.x_main = x; }
   } else {
@@ -991,7 +1012,7 @@ __device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t
     for (unsigned long long g = 0; g < ngroups; ++g) {
       const int s = (int)(g % kRansStages);
       if (g >= kRansStages) {  // the stage is being reused: wait until the consumer is done with it, then write its bytes
-        named_bar_sync(1 + kRansStages + s);
+        named_bar_sync(bar_base + kRansStages + s);
         if (g - kRansStages >= g_main) emit_bytes(s, 32);
       }
       const uint32_t sym = pre[0];
@@ -1013,41 +1034,55 @@ __device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t
       const uint4 b = make_uint4(e.z, e.w, (1u << P) - e.x, e.x == 1u ? 1u : 0u);  // {M, lp, g, c}
       sh.rows_a[s][lane] = a;
       sh.rows_b[s][lane] = b;
-      named_bar_arrive(1 + s);
+      named_bar_arrive(bar_base + s);
     }
     // drain: bytes of the last min(ngroups, kRansStages) groups, in order
     const unsigned long long first_pending = ngroups > (unsigned long long)kRansStages ? ngroups - kRansStages : 0;
     for (unsigned long long g = first_pending; g < ngroups; ++g) {
       const int s = (int)(g % kRansStages);
       const uint32_t cnt = (g + 1 == ngroups) ? (uint32_t)(steps - 32 * g) : 32u;
-      named_bar_sync(1 + kRansStages + s);
+      named_bar_sync(bar_base + kRansStages + s);
       if (g >= g_main) emit_bytes(s, cnt);
     }
     err = __reduce_or_sync(0xFFFFFFFFu, err);
     if (lane == 0) { sh.nbytes = pos; sh.err = err; }
   }
-  __syncthreads();
+  named_bar_sync(bar_base + 2 * kRansStages);  // both warps of the pair: results in sh are visible
+}
+
+// role / pair of the calling warp inside a 128-thread CTA (two pairs); odd CTAs swap roles
+struct RansRole { int pair; int bar_base; bool is_consumer; };
+__device__ __forceinline__ RansRole rans_role() {
+  const int warp = threadIdx.x >> 5;
+  RansRole r;
+  r.pair = warp >> 1;
+  r.bar_base = 1 + r.pair * (2 * kRansStages + 1);
+  r.is_consumer = (warp & 1) == (int)(blockIdx.x & 1);
+  return r;
 }
 
 // chunk state arrays (device scratch): start[J] = entering state each chunk was last encoded from,
 // exit_a / exit_b[J] = exit states (double-buffered across rounds), nbytes[J].
 struct RansChunkState { uint32_t* start; uint32_t* exit_a; uint32_t* exit_b; uint32_t* nbytes; };
 
-__device__ __forceinline__ uint64_t rans_chunk_capacity() { return 3ull * kRansChunk + 8; }
+__host__ __device__ __forceinline__ uint64_t rans_chunk_capacity(uint32_t chunk) { return 3ull * chunk + 8; }
 
-// round 0: speculative encode of every chunk (grid = number of chunks)
-__global__ void __launch_bounds__(64) rans_speculate_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                            uint8_t* __restrict__ scratch, RansChunkState cs, AttrStats* stats) {
-  __shared__ RansShared sh;
+// round 0: speculative encode of every chunk (two chunks per CTA)
+__global__ void __launch_bounds__(128) rans_speculate_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                             uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, uint32_t kRansWarmup, AttrStats* stats) {
+  __shared__ RansShared sh2[2];
   if (stats->error_flags) return;
+  const RansRole role = rans_role();
+  const unsigned long long j = 2ull * blockIdx.x + role.pair;
+  if (j >= num_chunks) return;  // both warps of the pair leave together
+  RansShared& sh = sh2[role.pair];
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
-  const unsigned long long j = blockIdx.x;
   const unsigned long long e_main = j * kRansChunk;
   const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
   const unsigned long long e_begin = e_main > kRansWarmup ? e_main - kRansWarmup : 0;  // warm-up from step 0 is exact
   const uint32_t l_base = 4u << P;
-  rans_encode_range(sh, symbols, n, table, K, P, e_begin, e_main, e_end, l_base, scratch + j * rans_chunk_capacity());
-  if (threadIdx.x == 0) {
+  rans_encode_range(sh, symbols, n, table, K, P, e_begin, e_main, e_end, l_base, scratch + j * rans_chunk_capacity(kRansChunk), role.bar_base, role.is_consumer);
+  if (role.is_consumer && (threadIdx.x & 31) == 0) {
     cs.start[j] = sh.x_main;
     cs.exit_a[j] = sh.x_exit;
     cs.nbytes[j] = sh.nbytes;
@@ -1056,36 +1091,41 @@ __global__ void __launch_bounds__(64) rans_speculate_kernel(const uint32_t* __re
 }
 
 // round r >= 1: re-encode the chunks whose entering state does not match the predecessor's exit
-__global__ void __launch_bounds__(64) rans_relax_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                        uint8_t* __restrict__ scratch, RansChunkState cs, const uint32_t* __restrict__ exit_cur,
-                                                        uint32_t* __restrict__ exit_next, AttrStats* stats) {
-  __shared__ RansShared sh;
+__global__ void __launch_bounds__(128) rans_relax_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                         uint8_t* __restrict__ scratch, RansChunkState cs, const uint32_t* __restrict__ exit_cur,
+                                                         uint32_t* __restrict__ exit_next, uint32_t num_chunks, uint32_t kRansChunk, AttrStats* stats) {
+  __shared__ RansShared sh2[2];
   if (stats->error_flags) return;
+  const RansRole role = rans_role();
+  const unsigned long long j = 2ull * blockIdx.x + role.pair;
+  if (j >= num_chunks) return;
+  RansShared& sh = sh2[role.pair];
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
-  const unsigned long long j = blockIdx.x;
   const uint32_t l_base = 4u << P;
   const uint32_t in = j == 0 ? l_base : exit_cur[j - 1];
-  if (in == cs.start[j]) { if (threadIdx.x == 0) exit_next[j] = exit_cur[j]; return; }
+  if (in == cs.start[j]) { if (role.is_consumer && (threadIdx.x & 31) == 0) exit_next[j] = exit_cur[j]; return; }  // pair-uniform
   const unsigned long long e_main = j * kRansChunk;
   const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
-  rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, in, scratch + j * rans_chunk_capacity());
-  if (threadIdx.x == 0) {
+  rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, in, scratch + j * rans_chunk_capacity(kRansChunk), role.bar_base, role.is_consumer);
+  if (role.is_consumer && (threadIdx.x & 31) == 0) {
     cs.start[j] = in;
     exit_next[j] = sh.x_exit;
     cs.nbytes[j] = sh.nbytes;
+    atomicAdd(&stats->pad[0], 1u);  // chunks re-encoded in relaxation rounds
     if (sh.err) atomicOr(&stats->error_flags, sh.err);
   }
 }
 
-// sequential fix-up (one CTA): guarantees exactness whatever the speculation did
+// sequential fix-up (one CTA of one pair): guarantees exactness whatever the speculation did
 __global__ void __launch_bounds__(64) rans_fixup_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
                                                         uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t* __restrict__ exit_final,
-                                                        uint32_t num_chunks, AttrStats* stats) {
+                                                        uint32_t num_chunks, uint32_t kRansChunk, AttrStats* stats) {
   __shared__ RansShared sh;
   __shared__ uint32_t s_in;
   if (stats->error_flags) return;
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
   const uint32_t l_base = 4u << P;
+  const bool is_consumer = threadIdx.x < 32;
   for (uint32_t j = 0; j < num_chunks; ++j) {
     if (threadIdx.x == 0) s_in = j == 0 ? l_base : exit_final[j - 1];
     __syncthreads();
@@ -1094,11 +1134,12 @@ __global__ void __launch_bounds__(64) rans_fixup_kernel(const uint32_t* __restri
     if (in == cs.start[j]) continue;  // uniform: every thread reads the same values
     const unsigned long long e_main = (unsigned long long)j * kRansChunk;
     const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
-    rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, in, scratch + (unsigned long long)j * rans_chunk_capacity());
+    rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, in, scratch + (unsigned long long)j * rans_chunk_capacity(kRansChunk), 1, is_consumer);
     if (threadIdx.x == 0) {
       cs.start[j] = in;
       exit_final[j] = sh.x_exit;
       cs.nbytes[j] = sh.nbytes;
+      stats->pad[1] += 1;  // chunks re-encoded by the sequential fix-up
       if (sh.err) atomicOr(&stats->error_flags, sh.err);
     }
     __syncthreads();
@@ -1107,7 +1148,7 @@ __global__ void __launch_bounds__(64) rans_fixup_kernel(const uint32_t* __restri
 
 // gather: chunk j's bytes go to payload[sum_{i<j} nbytes[i]]; the last CTA appends the flush bytes
 __global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restrict__ scratch, RansChunkState cs, const uint32_t* __restrict__ exit_final,
-                                                          uint32_t num_chunks, uint8_t* __restrict__ out, AttrStats* stats) {
+                                                          uint32_t num_chunks, uint32_t kRansChunk, uint8_t* __restrict__ out, AttrStats* stats) {
   __shared__ uint32_t s_part[8];
   __shared__ uint32_t s_off;
   if (stats->error_flags) { if (blockIdx.x == 0 && threadIdx.x == 0) stats->payload_bytes = 0; return; }
@@ -1120,7 +1161,7 @@ __global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restr
   if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; ++w) t += s_part[w]; s_off = t; }
   __syncthreads();
   const uint32_t off = s_off, nb = cs.nbytes[j];
-  const uint8_t* src = scratch + (unsigned long long)j * rans_chunk_capacity();
+  const uint8_t* src = scratch + (unsigned long long)j * rans_chunk_capacity(kRansChunk);
   for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) out[off + i] = src[i];
   if (j + 1 == num_chunks && threadIdx.x == 0) {
     uint32_t pos = off + nb, err = 0;
@@ -1136,31 +1177,33 @@ __global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restr
   }
 }
 
-uint32_t rans_num_chunks(uint64_t num_symbols) { return (uint32_t)((num_symbols + kRansChunk - 1) / kRansChunk); }
+uint32_t rans_num_chunks(uint64_t num_symbols) { const uint32_t c = rans_plan().chunk; return (uint32_t)((num_symbols + c - 1) / c); }
 size_t rans_scratch_bytes(uint64_t num_symbols) {
   const size_t J = rans_num_chunks(num_symbols);
-  return J * (3ull * kRansChunk + 8) + 256 + 4 * J * sizeof(uint32_t) + 64;
+  return J * rans_chunk_capacity(rans_plan().chunk) + 256 + 4 * J * sizeof(uint32_t) + 64;
 }
 
 void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, void* scratch, uint8_t* payload,
                         AttrStats* stats, cudaStream_t s) {
+  const RansPlan plan = rans_plan();
   const uint32_t J = rans_num_chunks(num_symbols);
   uint8_t* bytes = (uint8_t*)scratch;
-  size_t off = ((size_t)J * (3ull * kRansChunk + 8) + 255) / 256 * 256;
+  size_t off = ((size_t)J * rans_chunk_capacity(plan.chunk) + 255) / 256 * 256;
   uint32_t* u = (uint32_t*)(bytes + off);
   RansChunkState cs{u, u + J, u + 2 * (size_t)J, u + 3 * (size_t)J};
-  rans_speculate_kernel<<<J, 64, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, stats);
+  rans_speculate_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, plan.warmup, stats);
   uint32_t* cur = cs.exit_a;
   uint32_t* nxt = cs.exit_b;
   if (J > 1) {
-    for (int r = 0; r < kRansRounds; ++r) {
-      rans_relax_kernel<<<J, 64, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, cur, nxt, stats);
+    for (int r = 0; r < plan.rounds; ++r) {
+      rans_relax_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, cur, nxt, J, plan.chunk, stats);
       uint32_t* t = cur; cur = nxt; nxt = t;
     }
-    rans_fixup_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, cur, J, stats);
+    rans_fixup_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, cur, J, plan.chunk, stats);
   }
-  rans_gather_kernel<<<J, 256, 0, s>>>(bytes, cs, cur, J, payload, stats);
+  rans_gather_kernel<<<J, 256, 0, s>>>(bytes, cs, cur, J, plan.chunk, payload, stats);
 }
+int rans_launch_count(uint64_t num_symbols) { return rans_num_chunks(num_symbols) > 1 ? 3 + rans_plan().rounds : 2; }
 
 // ---------------------------------------------------------------------------------------
 // K12 — CornerTable::compute_table (corner_table/mod.rs:252-340) for the manifold,

@@ -78,6 +78,7 @@ void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t t
 // scratch: rans_scratch_bytes(num_symbols) bytes of device memory (chunk byte strings + chunk states)
 size_t rans_scratch_bytes(uint64_t num_symbols);
 uint32_t rans_num_chunks(uint64_t num_symbols);
+int rans_launch_count(uint64_t num_symbols);  // kernels launch_rans_encode issues
 void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, void* scratch, uint8_t* payload,
                         AttrStats* stats, cudaStream_t s);
 // ---- K12: half-edge matching by radix sort (corner_table/mod.rs:252-340, fast path) ----
