@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <future>
 
 namespace dxo {
 
@@ -34,6 +35,7 @@ DeviceContext& DeviceContext::get(int device) {
   auto c = std::make_unique<DeviceContext>();
   c->device = device;
   for (auto& s : c->stream) cuda_check(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
+  cuda_check(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
   cuda_check(cudaEventCreate(&c->ev_begin), "cudaEventCreate");
   cuda_check(cudaEventCreate(&c->ev_end), "cudaEventCreate");
   cuda_check(cudaEventCreateWithFlags(&c->ev_pos_ready, cudaEventDisableTiming), "cudaEventCreate");
@@ -47,6 +49,20 @@ DeviceContext& DeviceContext::get(int device) {
   DeviceContext& ref = *c;
   ctxs[device] = std::move(c);
   return ref;
+}
+
+uint8_t* DeviceContext::pinned_buffer(size_t slot, size_t bytes) {
+  if (pinned.size() <= slot) pinned.resize(slot + 1, {nullptr, 0});
+  auto& b = pinned[slot];
+  if (b.second < bytes) {
+    if (b.first) cudaFreeHost(b.first);
+    b = {nullptr, 0};
+    const size_t cap = bytes + bytes / 4 + 4096;
+    void* p = nullptr;
+    cuda_check(cudaHostAlloc(&p, cap, cudaHostAllocDefault), "cudaHostAlloc");
+    b = {(uint8_t*)p, cap};
+  }
+  return b.first;
 }
 
 cudaEvent_t Profile::take() {
@@ -158,7 +174,10 @@ MeshJob::MeshJob(const dxo_mesh* mesh, const dxo_config& cfg) : mesh_(mesh), cfg
   }
 }
 
-MeshJob::~MeshJob() {}
+MeshJob::~MeshJob() {
+  for (cudaEvent_t e : side_ready_) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : side_copied_) if (e) cudaEventDestroy(e);
+}
 
 // ---------------------------------------------------------------------------------------
 void MeshJob::build_connectivity() {
@@ -257,6 +276,14 @@ void MeshJob::upload(DeviceContext& ctx) {
   }
   cuda_check(cudaEventRecord(ctx.ev_join[0], s), "cudaEventRecord");
   for (int k = 1; k < 3; ++k) cuda_check(cudaStreamWaitEvent(ctx.stream[k], ctx.ev_join[0], 0), "cudaStreamWaitEvent");
+  cuda_check(cudaStreamWaitEvent(ctx.copy_stream, ctx.ev_join[0], 0), "cudaStreamWaitEvent");
+  side_ready_.assign(plans_.size(), nullptr);
+  side_copied_.assign(plans_.size(), nullptr);
+  for (size_t i = 0; i < plans_.size(); ++i) {
+    if (plans_[i].scheme != Scheme::Normal && plans_[i].scheme != Scheme::TexCoord) continue;
+    cuda_check(cudaEventCreateWithFlags(&side_ready_[i], cudaEventDisableTiming), "cudaEventCreate");
+    cuda_check(cudaEventCreateWithFlags(&side_copied_[i], cudaEventDisableTiming), "cudaEventCreate");
+  }
   uploaded_ = true;
 }
 
@@ -339,6 +366,14 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
         prof.end(s);
         break;
     }
+    if (side_ready_[i]) {  // flags leave for the host as soon as the predictor is done; the host codes them during K8-K10
+      uint8_t* host = ctx.pinned_buffer(2 * i + 1, M);
+      cuda_check(cudaEventRecord(side_ready_[i], s), "cudaEventRecord");
+      cuda_check(cudaStreamWaitEvent(ctx.copy_stream, side_ready_[i], 0), "cudaStreamWaitEvent");
+      cuda_check(cudaMemcpyAsync(host, d.side, M, cudaMemcpyDeviceToHost, ctx.copy_stream), "cudaMemcpyAsync D2H");
+      cuda_check(cudaEventRecord(side_copied_[i], ctx.copy_stream), "cudaEventRecord");
+      d2h_bytes += M;
+    }
     prof.begin("K8_histogram", 4 * S, s);
     gpu::launch_histogram(d.symbols, S, d.hist, p.hist_capacity, d.stats, s);
     prof.end(s);
@@ -353,32 +388,77 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
   cuda_check(cudaGetLastError(), "kernel launch");
 }
 
+// Binary side stream of attribute `att` (runs on a host worker thread):
+// normals — flips in sequence order, zero_prob from the zero count (mesh_normal_prediction.rs:147-163);
+// texcoords — order-preserving compaction of the orientation flags, zero_prob from the forward
+// transitions over len + 0.001, backward-delta bits written forward (mesh_prediction_for_texture_coordinates.rs:221-260).
+void MeshJob::encode_side_stream(size_t att) {
+  AttrResult& r = results_[att];
+  const uint8_t* flags = r.side;
+  const size_t n = r.side_len;
+  if (plans_[att].scheme == Scheme::Normal) {
+    uint64_t zeros = 0;
+    for (size_t i = 0; i < n; ++i) zeros += flags[i] ? 0 : 1;
+    r.side_count = (uint32_t)n;
+    r.side_zero_prob = side_stream_zero_prob(zeros, (float)n);
+    rabs_encode_forward(flags, n, r.side_zero_prob, r.side_payload);
+  } else {
+    std::vector<uint8_t> orient;
+    orient.reserve(n);
+    for (size_t i = 0; i < n; ++i) if (flags[i]) orient.push_back(flags[i] == 2 ? 1 : 0);
+    uint64_t transitions = 0;
+    { uint8_t last = 1; for (uint8_t o : orient) { transitions += o != last; last = o; } }
+    r.side_count = (uint32_t)orient.size();
+    r.side_zero_prob = side_stream_zero_prob(transitions, (float)orient.size() + 0.001f);
+    // bits[k] = (o[k] == o[k+1]) with o[len] = true, in place from the front
+    for (size_t k = 0; k < orient.size(); ++k) orient[k] = orient[k] == (k + 1 < orient.size() ? orient[k + 1] : 1) ? 1 : 0;
+    rabs_encode_forward(orient.data(), orient.size(), r.side_zero_prob, r.side_payload);
+  }
+}
+
 void MeshJob::download(DeviceContext& ctx) {
-  results_.assign(plans_.size(), AttrResult{});
+  results_.resize(plans_.size());
+  // side streams: start a host worker per stream as soon as its flags have landed
+  std::vector<std::future<void>> workers;
   for (size_t i = 0; i < plans_.size(); ++i) {
-    cudaStream_t s = ctx.stream[std::min<size_t>(i, 2)];
-    cuda_check(cudaMemcpyAsync(&results_[i].stats, dev_[i].stats, sizeof(gpu::AttrStats), cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
-    d2h_bytes += sizeof(gpu::AttrStats);
+    if (!side_copied_[i]) continue;
+    results_[i].side = ctx.pinned_buffer(2 * i + 1, plans_[i].sequence.size());
+    results_[i].side_len = plans_[i].sequence.size();
+    const int device = ctx.device;
+    cudaEvent_t ev = side_copied_[i];
+    workers.push_back(std::async(std::launch::async, [this, i, device, ev] {
+      cuda_check(cudaSetDevice(device), "cudaSetDevice");
+      cuda_check(cudaEventSynchronize(ev), "cudaEventSynchronize");
+      encode_side_stream(i);
+    }));
   }
-  for (size_t i = 0; i < plans_.size(); ++i) {
-    cudaStream_t s = ctx.stream[std::min<size_t>(i, 2)];
-    cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
-    AttrResult& r = results_[i];
-    if (int st = status_from_flags(r.stats.error_flags)) throw Error(st, "device reported an encoding error");
-    if (r.stats.table_bytes > dev_[i].table_capacity || r.stats.payload_bytes > dev_[i].payload_capacity)
-      throw Error(DXO_ERR_INTERNAL, "device output exceeds its buffer");
-    r.table_bytes.resize(r.stats.table_bytes);
-    r.payload.resize(r.stats.payload_bytes);
-    cuda_check(cudaMemcpyAsync(r.table_bytes.data(), dev_[i].table_bytes, r.table_bytes.size(), cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
-    cuda_check(cudaMemcpyAsync(r.payload.data(), dev_[i].payload, r.payload.size(), cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
-    d2h_bytes += r.table_bytes.size() + r.payload.size();
-    if (plans_[i].scheme == Scheme::Normal || plans_[i].scheme == Scheme::TexCoord) {
-      r.side.resize(plans_[i].sequence.size());
-      cuda_check(cudaMemcpyAsync(r.side.data(), dev_[i].side, r.side.size(), cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
-      d2h_bytes += r.side.size();
+  auto join_workers = [&] { for (auto& w : workers) w.get(); };
+  try {
+    for (size_t i = 0; i < plans_.size(); ++i) {
+      cudaStream_t s = ctx.stream[std::min<size_t>(i, 2)];
+      cuda_check(cudaMemcpyAsync(&results_[i].stats, dev_[i].stats, sizeof(gpu::AttrStats), cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+      d2h_bytes += sizeof(gpu::AttrStats);
     }
+    for (size_t i = 0; i < plans_.size(); ++i) {
+      cudaStream_t s = ctx.stream[std::min<size_t>(i, 2)];
+      cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+      AttrResult& r = results_[i];
+      if (int st = status_from_flags(r.stats.error_flags)) throw Error(st, "device reported an encoding error");
+      if (r.stats.table_bytes > dev_[i].table_capacity || r.stats.payload_bytes > dev_[i].payload_capacity)
+        throw Error(DXO_ERR_INTERNAL, "device output exceeds its buffer");
+      uint8_t* host = ctx.pinned_buffer(2 * i, (size_t)r.stats.table_bytes + r.stats.payload_bytes + 16);
+      r.table_bytes = host;
+      r.payload = host + r.stats.table_bytes;
+      cuda_check(cudaMemcpyAsync(host, dev_[i].table_bytes, r.stats.table_bytes, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+      cuda_check(cudaMemcpyAsync(host + r.stats.table_bytes, dev_[i].payload, r.stats.payload_bytes, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+      d2h_bytes += (size_t)r.stats.table_bytes + r.stats.payload_bytes;
+    }
+    for (int k = 0; k < 3; ++k) cuda_check(cudaStreamSynchronize(ctx.stream[k]), "cudaStreamSynchronize");
+  } catch (...) {
+    try { join_workers(); } catch (...) {}
+    throw;
   }
-  for (int k = 0; k < 3; ++k) cuda_check(cudaStreamSynchronize(ctx.stream[k]), "cudaStreamSynchronize");
+  join_workers();
   if (trace) capture_trace(ctx);
 }
 
@@ -386,7 +466,7 @@ void MeshJob::download(DeviceContext& ctx) {
 void MeshJob::assemble(std::vector<uint8_t>& out) {
   ByteSink w;
   size_t total = head_.size() + 64;
-  for (const AttrResult& r : results_) total += r.table_bytes.size() + r.payload.size() + r.side.size() / 4 + 64;
+  for (const AttrResult& r : results_) total += (size_t)r.stats.table_bytes + r.stats.payload_bytes + r.side_payload.size() + 64;
   w.data.reserve(total);
   w.bytes(head_.data);
   for (size_t i = 0; i < plans_.size(); ++i) {
@@ -397,34 +477,25 @@ void MeshJob::assemble(std::vector<uint8_t>& out) {
     w.u8(1);                     // rans_encoding (:344)
     w.u8(1);                     // SymbolEncodingMethod::DirectCoded (symbol_coding.rs:22)
     w.u8((uint8_t)r.stats.bit_length);
-    w.bytes(r.table_bytes);      // leb128 #symbols + frequency table (rans.rs:193-230)
-    w.varint(r.payload.size());  // RansSymbolEncoder::flush (rans.rs:248-255)
-    w.bytes(r.payload);
+    w.bytes(r.table_bytes, r.stats.table_bytes);  // leb128 #symbols + frequency table (rans.rs:193-230)
+    w.varint(r.stats.payload_bytes);              // RansSymbolEncoder::flush (rans.rs:248-255)
+    w.bytes(r.payload, r.stats.payload_bytes);
     // metadata: order depends on the scheme (:362-386)
     auto transform_info = [&] {
       if (p.transform == Transform::Wrapped) { w.i32(r.stats.wrap_min); w.i32(r.stats.wrap_max); }   // wrapped_difference.rs:95-96
       else if (p.transform == Transform::OctOrthogonal) { w.u32(255); w.u32(127); }                  // oct_orthogonal.rs:80-82
     };
+    auto side_stream = [&] {  // zero_prob byte, leb128 size, rABS bytes (coded by encode_side_stream)
+      w.u8(r.side_zero_prob);
+      w.varint(r.side_payload.size());
+      w.bytes(r.side_payload);
+    };
     if (p.scheme == Scheme::Normal) {
       transform_info();
-      // flips, in sequence order (mesh_normal_prediction.rs:147-163)
-      uint64_t zeros = 0;
-      for (uint8_t f : r.side) zeros += f ? 0 : 1;
-      const uint8_t p0 = side_stream_zero_prob(zeros, (float)r.side.size());
-      write_side_stream(r.side.data(), r.side.size(), false, p0, w);
+      side_stream();
     } else if (p.scheme == Scheme::TexCoord) {
-      // orientation bits exist only where the main branch ran: order-preserving compaction,
-      // then the forward-transition probability / backward-delta bits of :221-260
-      std::vector<uint8_t> orient;
-      orient.reserve(r.side.size());
-      for (uint8_t f : r.side) if (f) orient.push_back(f == 2 ? 1 : 0);
-      uint64_t transitions = 0;
-      { uint8_t last = 1; for (uint8_t o : orient) if (o != last) { last = o; ++transitions; } }
-      const uint8_t p0 = side_stream_zero_prob(transitions, (float)orient.size() + 0.001f);
-      std::vector<uint8_t> bits(orient.size());
-      { uint8_t next = 1; for (size_t k = orient.size(); k-- > 0;) { bits[k] = orient[k] == next ? 1 : 0; next = orient[k]; } }
-      w.u32((uint32_t)orient.size());
-      write_side_stream(bits.data(), bits.size(), false, p0, w);
+      w.u32(r.side_count);
+      side_stream();
       transform_info();
     } else {
       transform_info();
@@ -494,13 +565,13 @@ void MeshJob::capture_trace(DeviceContext& ctx) {
       std::vector<uint64_t> d64(d.begin(), d.end());
       put(k + "distribution", d64.data(), d64.size() * 8);
     }
-    put(k + "table_bytes", r.table_bytes.data(), r.table_bytes.size());
-    put(k + "payload", r.payload.data(), r.payload.size());
+    put(k + "table_bytes", r.table_bytes, r.stats.table_bytes);
+    put(k + "payload", r.payload, r.stats.payload_bytes);
     { int32_t mm[2] = {r.stats.wrap_min, r.stats.wrap_max}; put(k + "wrap_minmax", mm, 8); }
     { uint32_t bl[2] = {r.stats.bit_length, r.stats.precision}; put(k + "bit_length", bl, 8); }
     std::vector<uint8_t> side;
-    if (p.scheme == Scheme::Normal) side = r.side;
-    else if (p.scheme == Scheme::TexCoord) for (uint8_t f : r.side) if (f) side.push_back(f == 2 ? 1 : 0);
+    if (p.scheme == Scheme::Normal) side.assign(r.side, r.side + r.side_len);
+    else if (p.scheme == Scheme::TexCoord) for (size_t e = 0; e < r.side_len; ++e) if (r.side[e]) side.push_back(r.side[e] == 2 ? 1 : 0);
     put(k + "side_bits", side.data(), side.size());
   }
 }

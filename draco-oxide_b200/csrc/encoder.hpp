@@ -18,6 +18,10 @@ void cuda_check(cudaError_t e, const char* what);
 struct DeviceContext {
   int device = 0;
   cudaStream_t stream[3] = {nullptr, nullptr, nullptr};  // attribute i runs on stream[min(i,2)]
+  cudaStream_t copy_stream = nullptr;                    // early D2H of the side-stream flags
+  // pinned host staging, reused across calls (slot = attribute index * 2 + {0: results, 1: side flags})
+  std::vector<std::pair<uint8_t*, size_t>> pinned;
+  uint8_t* pinned_buffer(size_t slot, size_t bytes);
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_pos_ready = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   static DeviceContext& get(int device);  // thread-local; throws DXO_ERR_NO_DEVICE when there is no usable GPU
 };
@@ -68,7 +72,14 @@ struct AttrDevice {
 
 struct AttrResult {
   gpu::AttrStats stats;
-  std::vector<uint8_t> table_bytes, payload, side;
+  const uint8_t* table_bytes = nullptr;  // pinned staging (valid until the next run on this context)
+  const uint8_t* payload = nullptr;
+  const uint8_t* side = nullptr;         // per-element flip / orientation flags
+  size_t side_len = 0;
+  // binary side stream, coded on a host worker while the device runs K8-K10
+  uint32_t side_count = 0;
+  uint8_t side_zero_prob = 0;
+  std::vector<uint8_t> side_payload;
 };
 
 class MeshJob {
@@ -104,7 +115,9 @@ class MeshJob {
   std::vector<AttrDevice> dev_;
   std::vector<AttrResult> results_;
   std::vector<void*> allocations_;
+  std::vector<cudaEvent_t> side_ready_, side_copied_;
   bool uploaded_ = false;
+  void encode_side_stream(size_t att);
 
   template <class T> T* dalloc(size_t count, cudaStream_t s);
   template <class T> T* dupload(const T* host, size_t count, cudaStream_t s);
