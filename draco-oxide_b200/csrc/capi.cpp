@@ -79,10 +79,11 @@ void run_device_phase(MeshJob& job, DeviceContext& ctx, Profile& prof, std::vect
 
 thread_local Profile g_profile;
 
-void encode_one(const dxo_mesh* mesh, const dxo_config& cfg, std::vector<uint8_t>& bytes, dxo_timing& tm) {
+void encode_one(const dxo_mesh* mesh, const dxo_config& cfg, std::vector<uint8_t>& bytes, dxo_timing& tm, bool parallel_host = true) {
   tm = dxo_timing{};
   const auto t0 = Clock::now();
   MeshJob job(mesh, cfg);
+  job.parallel_host = parallel_host;
   job.build_connectivity();
   tm.host_connectivity_ms = (float)ms_since(t0);
   DeviceContext& ctx = DeviceContext::get(cfg.device);
@@ -160,7 +161,7 @@ int dxo_encode_batch(const dxo_mesh* meshes, size_t n, const dxo_config* cfg, dx
           const size_t i = order[k];
           sts[i] = guarded([&] {
             std::vector<uint8_t> bytes;
-            encode_one(&meshes[i], c, bytes, tm);
+            encode_one(&meshes[i], c, bytes, tm, workers == 1);
             if (int s2 = give(bytes, &outs[i])) throw Error(s2, "out of memory");
           });
         }

@@ -5,6 +5,10 @@
 // Reference paths are relative to /root/reference/draco-oxide/src/.
 #include "connectivity.hpp"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 namespace dxo {
 
 // ---------------------------------------------------------------------------------------
@@ -31,9 +35,22 @@ void UniversalTable::build(const uint32_t* faces, uint32_t nfaces, const AttrVie
     for (uint32_t v = 0; v < num_vertices; ++v)
       if (!used[v]) throw Error(DXO_ERR_UNUSED_VERTICES, "mesh contains unused vertices");
   }
+  const bool timing = getenv("DXO_TIMING") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[dxo]   %-26s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t0).count());
+    t0 = n;
+  };
+  lap("vertex ids + checks");
   match_half_edges();
-  if (has_non_manifold_edge()) break_non_manifold_edges();
+  lap("half-edge matching");
+  const bool nm = has_non_manifold_edge();
+  lap("non-manifold edge test");
+  if (nm) break_non_manifold_edges();
   assign_left_most_corners();
+  lap("left-most corners");
 }
 
 // compute_table — :252-340. Per-source-vertex buckets of open half edges; a corner
@@ -248,26 +265,23 @@ void SeamTable::build(const UniversalTable& ut, const AttrView& att) {
 
 // ---------------------------------------------------------------------------------------
 // Edgebreaker — encode/connectivity/edgebreaker.rs
-namespace {
-
 enum : uint8_t { kC = 0, kS = 1, kL = 2, kR = 3, kE = 4 };
 
 struct SplitEvent { uint64_t merge_symbol, split_symbol; uint8_t right; };
 
 class EdgebreakerRun {
  public:
-  EdgebreakerRun(const UniversalTable& ut, const std::vector<SeamTable>& seams) : ut_(ut), seams_(seams) {
+  explicit EdgebreakerRun(const UniversalTable& ut) : ut_(ut) {
     vertex_done_.assign(ut.num_vertices, 0);
     face_done_.assign(ut.num_faces, 0);
     split_symbol_of_face_.assign(ut.num_faces, kNoSymbol);
   }
 
-  std::vector<uint32_t> run(ByteSink& w) {
-    w.u8(0);  // EdgebreakerKind::Standard (:467)
+  // phase 1: the CLERS traversal of every connected component (needs only the universal table)
+  void traverse_all() {
     find_boundaries();
-    w.varint(ut_.num_vertices);
-    w.varint(ut_.num_faces);
-    w.u8((uint8_t)seams_.size());
+    symbols_.reserve(ut_.num_faces);
+    visit_order_.reserve(ut_.num_faces);
     for (uint32_t c = 0; c < ut_.num_corners; ++c) {  // one traversal per connected component (:478-511)
       const uint32_t face = c / 3u;
       if (face_done_[face]) continue;
@@ -286,21 +300,28 @@ class EdgebreakerRun {
         traverse(start);
       }
     }
+    corners_.assign(init_face_corners_.rbegin(), init_face_corners_.rend());
+    corners_.insert(corners_.end(), visit_order_.begin(), visit_order_.end());
+  }
+  const std::vector<uint32_t>& corners_of_edgebreaker() const { return corners_; }
+
+  // phase 2a: everything of the connectivity section up to and including the start-face stream
+  void write_head(ByteSink& w, size_t num_seam_tables) const {
+    w.u8(0);  // EdgebreakerKind::Standard (:467)
+    w.varint(ut_.num_vertices);
+    w.varint(ut_.num_faces);
+    w.u8((uint8_t)num_seam_tables);
     w.varint(symbols_.size());
     w.varint(num_splits_);
     write_split_events(w);
-    write_symbols_and_side_streams(w);
-    std::vector<uint32_t> out(init_face_corners_.rbegin(), init_face_corners_.rend());
-    out.insert(out.end(), visit_order_.begin(), visit_order_.end());
-    return out;
+    write_symbols_and_start_faces(w);
   }
 
  private:
   static constexpr uint64_t kNoSymbol = ~(uint64_t)0;
   const UniversalTable& ut_;
-  const std::vector<SeamTable>& seams_;
   std::vector<uint8_t> vertex_done_, face_done_, hole_done_, symbols_, start_face_interior_;
-  std::vector<uint32_t> hole_of_vertex_, stack_, visit_order_, init_face_corners_;
+  std::vector<uint32_t> hole_of_vertex_, stack_, visit_order_, init_face_corners_, corners_;
   std::vector<uint64_t> split_symbol_of_face_;
   std::vector<SplitEvent> split_events_;
   uint64_t symbol_index_ = ~(uint64_t)0;  // usize::MAX, incremented with wrap before use (:150,:276)
@@ -433,8 +454,8 @@ class EdgebreakerRun {
     bits.finish();
   }
 
-  // DefaultTraversal::encode — :575-656
-  void write_symbols_and_side_streams(ByteSink& w) const {
+  // DefaultTraversal::encode — :575-607
+  void write_symbols_and_start_faces(ByteSink& w) const {
     {  // CLERS codes, last symbol first, LSB-first bit packing (symbol_encoder.rs:50-58)
       static const uint8_t kBits[5] = {1, 3, 3, 3, 3};
       static const uint8_t kCode[5] = {0b0, 0b001, 0b011, 0b101, 0b111};
@@ -452,10 +473,15 @@ class EdgebreakerRun {
       const uint8_t p0 = side_stream_zero_prob(zeros, (float)start_face_interior_.size());
       write_side_stream(start_face_interior_.data(), start_face_interior_.size(), true, p0, w);
     }
-    // attribute seams, one stream per non-position attribute (:610-653)
+  }
+
+ public:
+  // phase 2b: the seam stream of one non-position attribute (:610-653); independent per attribute
+  void write_seam_stream(const SeamTable& st, ByteSink& w) const {
     std::vector<uint8_t> face_seen(ut_.num_faces, 0);
-    std::vector<std::vector<uint8_t>> flags(seams_.size());
-    for (auto& f : flags) f.reserve(ut_.num_corners / 2);
+    std::vector<uint8_t> flags;
+    flags.reserve(ut_.num_corners / 2 + 16);
+    uint64_t zeros = 0;
     for (size_t i = visit_order_.size(); i-- > 0;) {
       const uint32_t c = visit_order_[i];
       const uint32_t tri[3] = {c, corner_next(c), corner_prev(c)};
@@ -463,24 +489,38 @@ class EdgebreakerRun {
       for (uint32_t k : tri) {
         const uint32_t o = ut_.opposite[k];
         if (o == kNone || face_seen[o / 3u]) continue;
-        for (size_t a = 0; a < seams_.size(); ++a) flags[a].push_back(seams_[a].seam[k]);
+        const uint8_t f = st.seam[k];
+        flags.push_back(f);
+        zeros += f ? 0 : 1;
       }
     }
-    for (auto& f : flags) {
-      uint64_t zeros = 0;
-      for (uint8_t b : f) zeros += b ? 0 : 1;
-      const uint8_t p0 = side_stream_zero_prob(zeros, (float)f.size());
-      write_side_stream(f.data(), f.size(), true, p0, w);
-    }
+    const uint8_t p0 = side_stream_zero_prob(zeros, (float)flags.size());
+    // bits are fed last-to-first (:644): reverse once, then use the forward coder
+    std::reverse(flags.begin(), flags.end());
+    std::vector<uint8_t> bytes;
+    rabs_encode_forward(flags.data(), flags.size(), p0, bytes);
+    w.u8(p0);
+    w.varint(bytes.size());
+    w.bytes(bytes);
   }
 };
 
-}  // namespace
+EdgebreakerEncoder::EdgebreakerEncoder(const UniversalTable& ut) : run_(new EdgebreakerRun(ut)) {}
+EdgebreakerEncoder::~EdgebreakerEncoder() { delete run_; }
+void EdgebreakerEncoder::traverse() { run_->traverse_all(); }
+const std::vector<uint32_t>& EdgebreakerEncoder::corners_of_edgebreaker() const { return run_->corners_of_edgebreaker(); }
+void EdgebreakerEncoder::write_head(ByteSink& w, size_t num_seam_tables) const {
+  if (num_seam_tables > 255) throw Error(DXO_ERR_TOO_MANY_ATTRIBUTES, "too many connectivity attributes");
+  run_->write_head(w, num_seam_tables);
+}
+void EdgebreakerEncoder::write_seam_stream(const SeamTable& st, ByteSink& w) const { run_->write_seam_stream(st, w); }
 
 std::vector<uint32_t> encode_edgebreaker(const UniversalTable& ut, const std::vector<SeamTable>& seams, ByteSink& w) {
-  if (seams.size() > 255) throw Error(DXO_ERR_TOO_MANY_ATTRIBUTES, "too many connectivity attributes");
-  EdgebreakerRun r(ut, seams);
-  return r.run(w);
+  EdgebreakerEncoder eb(ut);
+  eb.traverse();
+  eb.write_head(w, seams.size());
+  for (const SeamTable& st : seams) eb.write_seam_stream(st, w);
+  return eb.corners_of_edgebreaker();
 }
 
 // ---------------------------------------------------------------------------------------

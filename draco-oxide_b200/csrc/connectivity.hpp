@@ -66,8 +66,26 @@ inline TableRef table_ref(const UniversalTable& u, const SeamTable& s) {
   return {u.num_faces, u.num_corners, s.num_vertices, s.corner_vertex.data(), u.opposite.data(), s.seam.data(), s.left_most.data()};
 }
 
-// Edgebreaker<DefaultTraversal>::encode_connectivity — encode/connectivity/edgebreaker.rs:458-657.
-// Appends the connectivity section to `w` and returns corners_of_edgebreaker.
+// Edgebreaker<DefaultTraversal>::encode_connectivity — encode/connectivity/edgebreaker.rs:458-657,
+// split into phases so independent parts can run on different host threads:
+//   traverse()            CLERS traversal (needs only the universal table)
+//   write_head()          traversal byte .. start-face stream
+//   write_seam_stream()   one rABS stream per non-position attribute (const, thread-safe)
+class EdgebreakerRun;
+class EdgebreakerEncoder {
+ public:
+  explicit EdgebreakerEncoder(const UniversalTable& ut);
+  ~EdgebreakerEncoder();
+  EdgebreakerEncoder(const EdgebreakerEncoder&) = delete;
+  EdgebreakerEncoder& operator=(const EdgebreakerEncoder&) = delete;
+  void traverse();
+  const std::vector<uint32_t>& corners_of_edgebreaker() const;
+  void write_head(ByteSink& w, size_t num_seam_tables) const;
+  void write_seam_stream(const SeamTable& st, ByteSink& w) const;
+ private:
+  EdgebreakerRun* run_;
+};
+// Serial convenience wrapper: appends the whole connectivity section, returns corners_of_edgebreaker.
 std::vector<uint32_t> encode_edgebreaker(const UniversalTable& ut, const std::vector<SeamTable>& seams, ByteSink& w);
 
 // Traverser::compute_seqeunce — shared/attribute/sequence.rs:48-151.

@@ -6,7 +6,10 @@
 #include "encoder.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <future>
 
 namespace dxo {
@@ -180,8 +183,22 @@ MeshJob::~MeshJob() {
 }
 
 // ---------------------------------------------------------------------------------------
+namespace {
+struct StageClock {
+  bool on = getenv("DXO_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[dxo] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+}  // namespace
+
 void MeshJob::build_connectivity() {
   const uint32_t nfaces = (uint32_t)mesh_->num_faces;
+  StageClock clk;
   // header (encode/header/mod.rs:26-54)
   for (char ch : std::string("DRACO")) head_.u8((uint8_t)ch);
   head_.u8(2); head_.u8(2);
@@ -190,9 +207,53 @@ void MeshJob::build_connectivity() {
   head_.u16(0);   // flags: no metadata
 
   ut_.build(mesh_->faces, nfaces, plans_[0].view);
-  seams_.resize(plans_.size() - 1);
-  for (size_t i = 1; i < plans_.size(); ++i) seams_[i - 1].build(ut_, plans_[i].view);
-  corners_of_edgebreaker_ = encode_edgebreaker(ut_, seams_, head_);
+  clk.lap("universal corner table");
+  const size_t natt = plans_.size();
+  seams_.resize(natt - 1);
+  table_refs_.assign(natt, TableRef{});
+  std::vector<ByteSink> seam_bytes(natt - 1);
+  EdgebreakerEncoder eb(ut_);
+  if (!parallel_host || natt == 1) {
+    for (size_t i = 1; i < natt; ++i) seams_[i - 1].build(ut_, plans_[i].view);
+    clk.lap("seam tables");
+    eb.traverse();
+    eb.write_head(head_, seams_.size());
+    for (size_t i = 1; i < natt; ++i) eb.write_seam_stream(seams_[i - 1], seam_bytes[i - 1]);
+    clk.lap("edgebreaker");
+    corners_of_edgebreaker_ = eb.corners_of_edgebreaker();
+    table_refs_[0] = table_ref(ut_);
+    for (size_t i = 1; i < natt; ++i) table_refs_[i] = table_ref(ut_, seams_[i - 1]);
+    for (size_t i = 0; i < natt; ++i) plans_[i].sequence = attribute_sequence(table_refs_[i], corners_of_edgebreaker_);
+    clk.lap("attribute sequences");
+  } else {
+    // Independent host passes on their own threads: seam tables (one per attribute) next to the
+    // CLERS traversal; then the per-attribute sequencers and seam streams next to the symbol packing.
+    std::vector<std::future<void>> tasks;
+    auto wait_all = [&] { std::exception_ptr first; for (auto& t : tasks) { try { if (t.valid()) t.get(); } catch (...) { if (!first) first = std::current_exception(); } } tasks.clear(); if (first) std::rethrow_exception(first); };
+    try {
+      for (size_t i = 1; i < natt; ++i)
+        tasks.push_back(std::async(std::launch::async, [this, i] { seams_[i - 1].build(ut_, plans_[i].view); }));
+      eb.traverse();
+      corners_of_edgebreaker_ = eb.corners_of_edgebreaker();
+      table_refs_[0] = table_ref(ut_);
+      auto seq0 = std::async(std::launch::async, [this] { plans_[0].sequence = attribute_sequence(table_refs_[0], corners_of_edgebreaker_); });
+      wait_all();  // seam tables
+      clk.lap("seam tables + traversal");
+      for (size_t i = 1; i < natt; ++i) {
+        table_refs_[i] = table_ref(ut_, seams_[i - 1]);
+        tasks.push_back(std::async(std::launch::async, [this, i] { plans_[i].sequence = attribute_sequence(table_refs_[i], corners_of_edgebreaker_); }));
+        tasks.push_back(std::async(std::launch::async, [this, i, &eb, &seam_bytes] { eb.write_seam_stream(seams_[i - 1], seam_bytes[i - 1]); }));
+      }
+      tasks.push_back(std::move(seq0));
+      eb.write_head(head_, seams_.size());
+      wait_all();
+      clk.lap("sequences + streams");
+    } catch (...) {
+      try { wait_all(); } catch (...) {}
+      throw;
+    }
+  }
+  for (const ByteSink& b : seam_bytes) head_.bytes(b.data);
 
   // attribute section headers (encode/attribute/mod.rs:26-57)
   head_.u8((uint8_t)plans_.size());
@@ -212,15 +273,7 @@ void MeshJob::build_connectivity() {
     head_.u8((uint8_t)p.port);
   }
 
-  // one table view + traversal sequence per attribute (attribute_encoder.rs:236-253)
-  table_refs_.clear();
-  table_refs_.reserve(plans_.size());
-  table_refs_.push_back(table_ref(ut_));
-  for (size_t i = 1; i < plans_.size(); ++i) table_refs_.push_back(table_ref(ut_, seams_[i - 1]));
-  for (size_t i = 0; i < plans_.size(); ++i) {
-    plans_[i].table = &table_refs_[i];
-    plans_[i].sequence = attribute_sequence(table_refs_[i], corners_of_edgebreaker_);
-  }
+  for (size_t i = 0; i < natt; ++i) plans_[i].table = &table_refs_[i];
 }
 
 // ---------------------------------------------------------------------------------------

@@ -97,6 +97,7 @@ class MeshJob {
   void release(DeviceContext& ctx);
 
   bool trace = false;
+  bool parallel_host = true;  // run independent host passes on their own threads (off inside batch workers)
   std::map<std::string, std::vector<uint8_t>> trace_items;
   uint64_t h2d_bytes = 0, d2h_bytes = 0;
   uint64_t num_position_vertices() const { return plans_.empty() ? 0 : plans_[0].sequence.size(); }
