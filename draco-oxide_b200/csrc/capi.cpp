@@ -64,7 +64,9 @@ void run_device_phase(MeshJob& job, DeviceContext& ctx, Profile& prof, std::vect
   tm.d2h_ms = (float)ms_since(t_d2h);
   cuda_check(cudaEventSynchronize(ctx.ev_end), "cudaEventSynchronize");
   cuda_check(cudaEventElapsedTime(&tm.device_ms, ctx.ev_begin, ctx.ev_end), "cudaEventElapsedTime");
+  const auto t_asm = Clock::now();
   job.assemble(bytes);
+  if (getenv("DXO_TIMING")) fprintf(stderr, "[dxo] device %.3f ms | download+side streams (wall) %.3f ms | assemble %.3f ms\n", tm.device_ms, tm.d2h_ms, ms_since(t_asm));
   tm.num_launches = prof.launches;
   tm.num_kernels = 0;
   for (const KernelRecord& r : prof.records) {
@@ -84,9 +86,9 @@ void encode_one(const dxo_mesh* mesh, const dxo_config& cfg, std::vector<uint8_t
   const auto t0 = Clock::now();
   MeshJob job(mesh, cfg);
   job.parallel_host = parallel_host;
-  job.build_connectivity();
-  tm.host_connectivity_ms = (float)ms_since(t0);
   DeviceContext& ctx = DeviceContext::get(cfg.device);
+  job.build_connectivity(&ctx);
+  tm.host_connectivity_ms = (float)ms_since(t0);
   const auto t1 = Clock::now();
   job.upload(ctx);
   if (g_profiling.load()) cuda_check(cudaStreamSynchronize(ctx.stream[0]), "cudaStreamSynchronize");
@@ -212,9 +214,9 @@ int dxo_session_create(const dxo_mesh* mesh, const dxo_config* cfg, dxo_session*
     g_timing = dxo_timing{};
     const auto t0 = Clock::now();
     s->job = std::make_unique<MeshJob>(mesh, s->cfg);
-    s->job->build_connectivity();
-    g_timing.host_connectivity_ms = (float)ms_since(t0);
     DeviceContext& ctx = DeviceContext::get(s->cfg.device);
+    s->job->build_connectivity(&ctx);
+    g_timing.host_connectivity_ms = (float)ms_since(t0);
     s->device = ctx.device;
     const auto t1 = Clock::now();
     s->job->upload(ctx);

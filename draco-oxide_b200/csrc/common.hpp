@@ -110,22 +110,25 @@ static inline void rabs_encode(const uint8_t* bits, size_t n, bool reversed, uin
 // m = ceil(2^32 / f) => x * (m * f - 2^32) < 2^28 < 2^32), bytes written through a raw pointer.
 static inline void rabs_encode_forward(const uint8_t* bits, size_t n, uint8_t zero_prob, std::vector<uint8_t>& out) {
   const uint32_t f0 = zero_prob, f1 = 256u - f0;
-  const uint32_t f[2] = {f0, f1}, cum[2] = {f1, 0u}, thr[2] = {f0 << 12, f1 << 12};
+  if ((f0 == 0 || f1 == 0) && n) {  // only reachable with a probability outside [1,255]
+    for (size_t i = 0; i < n; ++i) if ((bits[i] ? f1 : f0) == 0) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "rABS: zero frequency");
+  }
+  // x' = (q << 8) + (x - q f) + cum = x + q (256 - f) + cum, q = floor(x / f) = (x * m) >> 32
+  const uint32_t thr[2] = {f0 << 12, f1 << 12}, g[2] = {256u - f0, 256u - f1}, cum[2] = {f1, 0u};
   const uint64_t m[2] = {f0 ? ((1ull << 32) + f0 - 1) / f0 : 0, f1 ? ((1ull << 32) + f1 - 1) / f1 : 0};
-  out.resize(n + 8);  // at most one byte per bit, plus the tail
+  if (out.size() < n + 8) out.resize(n + 8);  // at most one byte per bit, plus the tail (capacity is kept across calls)
   uint8_t* p = out.data();
   uint32_t x = 4096u;
   for (size_t i = 0; i < n; ++i) {
-    const uint32_t b = bits[i] ? 1u : 0u;
-    if (f[b] == 0) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "rABS: zero frequency");
+    const uint32_t b = bits[i] != 0;
     if (x >= thr[b]) { *p++ = (uint8_t)x; x >>= 8; }
     const uint32_t q = (uint32_t)(((uint64_t)x * m[b]) >> 32);
-    x = (q << 8) + (x - q * f[b]) + cum[b];
+    x = x + q * g[b] + cum[b];
   }
-  out.resize((size_t)(p - out.data()));
   ByteSink tail;
   ans_write_tail(x - 4096u, tail);
-  out.insert(out.end(), tail.data.begin(), tail.data.end());
+  for (uint8_t b : tail.data) *p++ = b;
+  out.resize((size_t)(p - out.data()));
 }
 
 // zero_prob byte + leb128 length + rABS bytes: the framing every side stream uses.

@@ -13,7 +13,7 @@ namespace dxo {
 
 // ---------------------------------------------------------------------------------------
 // CornerTable::new — core/corner_table/mod.rs:84-118
-void UniversalTable::build(const uint32_t* faces, uint32_t nfaces, const AttrView& pos) {
+void UniversalTable::build(const uint32_t* faces, uint32_t nfaces, const AttrView& pos, DeviceMatcher matcher, void* matcher_user) {
   num_faces = nfaces;
   num_corners = nfaces * 3u;
   corner_point = faces;
@@ -44,10 +44,19 @@ void UniversalTable::build(const uint32_t* faces, uint32_t nfaces, const AttrVie
     t0 = n;
   };
   lap("vertex ids + checks");
-  match_half_edges();
-  lap("half-edge matching");
-  const bool nm = has_non_manifold_edge();
-  lap("non-manifold edge test");
+  bool nm = false;
+  matched_on_device = false;
+  if (matcher) {
+    opposite.resize(num_corners);
+    matched_on_device = matcher(matcher_user, corner_vertex.data(), num_faces, opposite.data());
+    lap(matched_on_device ? "half-edge matching (K12)" : "half-edge matching (K12, not exact)");
+  }
+  if (!matched_on_device) {
+    match_half_edges();
+    lap("half-edge matching");
+    nm = has_non_manifold_edge();  // an exact K12 result implies no edge with 3+ sides
+    lap("non-manifold edge test");
+  }
   if (nm) break_non_manifold_edges();
   assign_left_most_corners();
   lap("left-most corners");

@@ -31,7 +31,12 @@ struct UniversalTable {
   uint32_t swing_left(uint32_t c) const { uint32_t o = opposite[corner_next(c)]; return o == kNone ? kNone : corner_next(o); }
   uint32_t swing_right(uint32_t c) const { uint32_t o = opposite[corner_prev(c)]; return o == kNone ? kNone : corner_prev(o); }
 
-  void build(const uint32_t* faces, uint32_t nfaces, const AttrView& pos);
+  // Optional accelerator for the half-edge matching (K12 on the device): fills `opposite_out`
+  // and returns true only when its result provably equals the sequential matcher's
+  // (manifold, consistently oriented input); otherwise the sequential path runs.
+  using DeviceMatcher = bool (*)(void* user, const uint32_t* corner_vertex, uint32_t num_faces, uint32_t* opposite_out);
+  void build(const uint32_t* faces, uint32_t nfaces, const AttrView& pos, DeviceMatcher matcher = nullptr, void* matcher_user = nullptr);
+  bool matched_on_device = false;
 
  private:
   void match_half_edges();

@@ -178,6 +178,7 @@ MeshJob::MeshJob(const dxo_mesh* mesh, const dxo_config& cfg) : mesh_(mesh), cfg
 }
 
 MeshJob::~MeshJob() {
+  for (void* p : allocations_) cudaFreeAsync(p, alloc_stream_);  // normally released by release(); this covers error paths
   for (cudaEvent_t e : side_ready_) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : side_copied_) if (e) cudaEventDestroy(e);
 }
@@ -196,7 +197,36 @@ struct StageClock {
 };
 }  // namespace
 
-void MeshJob::build_connectivity() {
+// K12: half-edge matching on the device. Keeps the device copies of corner_vertex / opposite
+// for the attribute kernels when the result is exact.
+bool MeshJob::device_matcher(void* user, const uint32_t* corner_vertex, uint32_t num_faces, uint32_t* opposite_out) {
+  MeshJob* job = (MeshJob*)user;
+  DeviceContext& ctx = *job->match_ctx_;
+  cudaStream_t s = ctx.stream[0];
+  const size_t C = (size_t)num_faces * 3;
+  uint32_t* d_cv = job->dupload(corner_vertex, C, s);
+  uint32_t* d_opp = job->dalloc<uint32_t>(C, s);
+  uint32_t* d_flag = job->dalloc<uint32_t>(1, s);
+  const size_t sb = gpu::corner_table_scratch_bytes(C);
+  void* scratch = nullptr;
+  cuda_check(cudaMallocAsync(&scratch, sb, s), "cudaMallocAsync");
+  cuda_check(cudaMemsetAsync(d_flag, 0, 4, s), "cudaMemsetAsync");
+  cuda_check(cudaMemsetAsync(d_opp, 0xFF, C * 4, s), "cudaMemsetAsync");
+  gpu::launch_corner_table_opposites(d_cv, C, d_opp, d_flag, scratch, sb, s);
+  uint32_t flag = 1;
+  cuda_check(cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+  cuda_check(cudaFreeAsync(scratch, s), "cudaFreeAsync");
+  cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+  if (flag) return false;  // order-dependent case: the sequential matcher decides
+  cuda_check(cudaMemcpyAsync(opposite_out, d_opp, C * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+  cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+  job->d2h_bytes += C * 4;
+  job->d_corner_vertex_ = d_cv;
+  job->d_opposite_ = d_opp;
+  return true;
+}
+
+void MeshJob::build_connectivity(DeviceContext* ctx) {
   const uint32_t nfaces = (uint32_t)mesh_->num_faces;
   StageClock clk;
   // header (encode/header/mod.rs:26-54)
@@ -206,7 +236,9 @@ void MeshJob::build_connectivity() {
   head_.u8(1);    // EncoderMethod::Edgebreaker
   head_.u16(0);   // flags: no metadata
 
-  ut_.build(mesh_->faces, nfaces, plans_[0].view);
+  match_ctx_ = ctx;
+  const bool use_k12 = ctx != nullptr && nfaces >= 4096 && !getenv("DXO_NO_K12");  // tiny meshes: the launch + sync costs more than it saves
+  ut_.build(mesh_->faces, nfaces, plans_[0].view, use_k12 ? &MeshJob::device_matcher : nullptr, this);
   clk.lap("universal corner table");
   const size_t natt = plans_.size();
   seams_.resize(natt - 1);
@@ -281,6 +313,7 @@ template <class T> T* MeshJob::dalloc(size_t count, cudaStream_t s) {
   void* p = nullptr;
   cuda_check(cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T), s), "cudaMallocAsync");
   allocations_.push_back(p);
+  alloc_stream_ = s;
   return (T*)p;
 }
 template <class T> T* MeshJob::dupload(const T* host, size_t count, cudaStream_t s) {
@@ -294,8 +327,10 @@ void MeshJob::upload(DeviceContext& ctx) {
   cudaStream_t s = ctx.stream[0];
   const size_t C = ut_.num_corners;
   d_faces_ = dupload(mesh_->faces, C, s);
-  d_opposite_ = dupload(ut_.opposite.data(), C, s);
-  d_corner_vertex_ = dupload(ut_.corner_vertex.data(), C, s);
+  if (!d_opposite_) d_opposite_ = dupload(ut_.opposite.data(), C, s);
+  if (!d_corner_vertex_) d_corner_vertex_ = dupload(ut_.corner_vertex.data(), C, s);
+  else if (ut_.num_vertices != plans_[0].view.num_unique)  // non-manifold vertices were split after K12 ran: refresh the labels
+    cuda_check(cudaMemcpyAsync(d_corner_vertex_, ut_.corner_vertex.data(), C * 4, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D");
   d_left_most_ = dupload(ut_.left_most.data(), ut_.left_most.size(), s);
   dev_.assign(plans_.size(), AttrDevice{});
   for (size_t i = 0; i < plans_.size(); ++i) {
@@ -450,22 +485,24 @@ void MeshJob::encode_side_stream(size_t att) {
   const uint8_t* flags = r.side;
   const size_t n = r.side_len;
   if (plans_[att].scheme == Scheme::Normal) {
-    uint64_t zeros = 0;
-    for (size_t i = 0; i < n; ++i) zeros += flags[i] ? 0 : 1;
+    uint64_t ones = 0;
+    for (size_t i = 0; i < n; ++i) ones += flags[i];
     r.side_count = (uint32_t)n;
-    r.side_zero_prob = side_stream_zero_prob(zeros, (float)n);
+    r.side_zero_prob = side_stream_zero_prob(n - ones, (float)n);
     rabs_encode_forward(flags, n, r.side_zero_prob, r.side_payload);
   } else {
-    std::vector<uint8_t> orient;
-    orient.reserve(n);
-    for (size_t i = 0; i < n; ++i) if (flags[i]) orient.push_back(flags[i] == 2 ? 1 : 0);
+    // order-preserving compaction (branch-free), then the delta bits in place
+    std::vector<uint8_t>& o = r.side_scratch;
+    o.resize(n + 1);
+    size_t m = 0;
+    for (size_t i = 0; i < n; ++i) { const uint8_t f = flags[i]; o[m] = (uint8_t)(f >> 1); m += f != 0; }
     uint64_t transitions = 0;
-    { uint8_t last = 1; for (uint8_t o : orient) { transitions += o != last; last = o; } }
-    r.side_count = (uint32_t)orient.size();
-    r.side_zero_prob = side_stream_zero_prob(transitions, (float)orient.size() + 0.001f);
-    // bits[k] = (o[k] == o[k+1]) with o[len] = true, in place from the front
-    for (size_t k = 0; k < orient.size(); ++k) orient[k] = orient[k] == (k + 1 < orient.size() ? orient[k + 1] : 1) ? 1 : 0;
-    rabs_encode_forward(orient.data(), orient.size(), r.side_zero_prob, r.side_payload);
+    { uint8_t last = 1; for (size_t k = 0; k < m; ++k) { transitions += o[k] != last; last = o[k]; } }
+    r.side_count = (uint32_t)m;
+    r.side_zero_prob = side_stream_zero_prob(transitions, (float)m + 0.001f);
+    o[m] = 1;  // o[len] = true
+    for (size_t k = 0; k < m; ++k) o[k] = o[k] == o[k + 1] ? 1 : 0;  // bits[k] = (o[k] == o[k+1]); o[k+1] is still unmodified
+    rabs_encode_forward(o.data(), m, r.side_zero_prob, r.side_payload);
   }
 }
 
@@ -481,8 +518,13 @@ void MeshJob::download(DeviceContext& ctx) {
     cudaEvent_t ev = side_copied_[i];
     workers.push_back(std::async(std::launch::async, [this, i, device, ev] {
       cuda_check(cudaSetDevice(device), "cudaSetDevice");
+      const auto t0 = std::chrono::steady_clock::now();
       cuda_check(cudaEventSynchronize(ev), "cudaEventSynchronize");
+      const auto t1 = std::chrono::steady_clock::now();
       encode_side_stream(i);
+      if (getenv("DXO_TIMING"))
+        fprintf(stderr, "[dxo] side stream %zu: waited %.3f ms for flags, coded in %.3f ms\n", i, std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
     }));
   }
   auto join_workers = [&] { for (auto& w : workers) w.get(); };

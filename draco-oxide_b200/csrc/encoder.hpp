@@ -79,15 +79,16 @@ struct AttrResult {
   // binary side stream, coded on a host worker while the device runs K8-K10
   uint32_t side_count = 0;
   uint8_t side_zero_prob = 0;
-  std::vector<uint8_t> side_payload;
+  std::vector<uint8_t> side_payload, side_scratch;
 };
 
 class MeshJob {
  public:
   MeshJob(const dxo_mesh* mesh, const dxo_config& cfg);
   ~MeshJob();
-  // phase 1: host only — corner tables, Edgebreaker bytes, attribute sequences
-  void build_connectivity();
+  // phase 1: host — corner tables, Edgebreaker bytes, attribute sequences. With a device
+  // context the half-edge matching runs as K12 (radix sort) when that is provably exact.
+  void build_connectivity(DeviceContext* ctx = nullptr);
   // phase 2: device
   void upload(DeviceContext& ctx);
   void launch(DeviceContext& ctx, Profile& prof);
@@ -116,10 +117,13 @@ class MeshJob {
   std::vector<AttrDevice> dev_;
   std::vector<AttrResult> results_;
   std::vector<void*> allocations_;
+  cudaStream_t alloc_stream_ = nullptr;
   std::vector<cudaEvent_t> side_ready_, side_copied_;
   bool uploaded_ = false;
   void encode_side_stream(size_t att);
 
+  static bool device_matcher(void* user, const uint32_t* corner_vertex, uint32_t num_faces, uint32_t* opposite_out);
+  DeviceContext* match_ctx_ = nullptr;
   template <class T> T* dalloc(size_t count, cudaStream_t s);
   template <class T> T* dupload(const T* host, size_t count, cudaStream_t s);
   gpu::TableDev table_dev(size_t att) const;
