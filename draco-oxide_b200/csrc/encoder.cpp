@@ -332,6 +332,10 @@ void MeshJob::upload(DeviceContext& ctx) {
   else if (ut_.num_vertices != plans_[0].view.num_unique)  // non-manifold vertices were split after K12 ran: refresh the labels
     cuda_check(cudaMemcpyAsync(d_corner_vertex_, ut_.corner_vertex.data(), C * 4, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D");
   d_left_most_ = dupload(ut_.left_most.data(), ut_.left_most.size(), s);
+  d_faces4_ = dalloc<uint4>(ut_.num_faces, s);
+  gpu::launch_pad3(d_faces_, ut_.num_faces, d_faces4_, s);
+  vertex_is_point_ = plans_[0].view.map == nullptr && ut_.num_vertices == plans_[0].view.num_unique;
+  if (!vertex_is_point_) { d_corner_vertex4_ = dalloc<uint4>(ut_.num_faces, s); gpu::launch_pad3(d_corner_vertex_, ut_.num_faces, d_corner_vertex4_, s); }
   dev_.assign(plans_.size(), AttrDevice{});
   for (size_t i = 0; i < plans_.size(); ++i) {
     const AttrPlan& p = plans_[i];
@@ -348,7 +352,11 @@ void MeshJob::upload(DeviceContext& ctx) {
     }
     d.seq = dupload(p.sequence.data(), M, s);
     const uint32_t V = p.table->num_vertices;
-    d.quant = p.port == Portabilization::ToBits ? (int32_t*)d.values : dalloc<int32_t>(U * p.ncomp_q, s);
+    const size_t qstride = p.ncomp_q == 3 ? 4 : p.ncomp_q;  // one value = one vector load (kernels.cu load_q)
+    if (p.port == Portabilization::ToBits && p.ncomp_q != 3) d.quant = (int32_t*)d.values;
+    else d.quant = dalloc<int32_t>(U * qstride, s);
+    if (p.port == Portabilization::ToBits && p.ncomp_q == 3) gpu::launch_pad3((const uint32_t*)d.values, U, (uint4*)d.quant, s);
+    if (i > 0) { d.corner_vertex4 = dalloc<uint4>(ut_.num_faces, s); gpu::launch_pad3(d.corner_vertex, ut_.num_faces, d.corner_vertex4, s); }
     d.rank = dalloc<uint32_t>(V, s);
     d.symbols = dalloc<uint32_t>(M * p.ncomp_q, s);
     d.side = dalloc<uint8_t>(M, s);
@@ -378,10 +386,16 @@ void MeshJob::upload(DeviceContext& ctx) {
 gpu::TableDev MeshJob::table_dev(size_t att) const {
   gpu::TableDev t;
   t.corner_point = d_faces_;
+  t.corner_point4 = d_faces4_;
   t.opposite = d_opposite_;
   t.num_corners = ut_.num_corners;
-  if (att == 0) { t.corner_vertex = d_corner_vertex_; t.seam = nullptr; t.left_most = d_left_most_; t.num_vertices = ut_.num_vertices; }
-  else { t.corner_vertex = dev_[att].corner_vertex; t.seam = dev_[att].seam; t.left_most = dev_[att].left_most; t.num_vertices = seams_[att - 1].num_vertices; }
+  if (att == 0) {
+    t.corner_vertex = d_corner_vertex_; t.corner_vertex4 = vertex_is_point_ ? d_faces4_ : d_corner_vertex4_; t.vertex_is_point = vertex_is_point_ ? 1 : 0;
+    t.seam = nullptr; t.left_most = d_left_most_; t.num_vertices = ut_.num_vertices;
+  } else {
+    t.corner_vertex = dev_[att].corner_vertex; t.corner_vertex4 = dev_[att].corner_vertex4; t.vertex_is_point = 0;
+    t.seam = dev_[att].seam; t.left_most = dev_[att].left_most; t.num_vertices = seams_[att - 1].num_vertices;
+  }
   return t;
 }
 
@@ -648,7 +662,14 @@ void MeshJob::capture_trace(DeviceContext& ctx) {
     const AttrPlan& p = plans_[i];
     const AttrResult& r = results_[i];
     const std::string k = "att" + std::to_string(i) + ".";
-    fetch(k + "quantized", dev_[i].quant, (size_t)p.view.num_unique * p.ncomp_q * 4);
+    if (p.ncomp_q == 3) {  // stored with stride 4 on the device
+      std::vector<int32_t> padded((size_t)p.view.num_unique * 4), packed((size_t)p.view.num_unique * 3);
+      if (!padded.empty()) cuda_check(cudaMemcpy(padded.data(), dev_[i].quant, padded.size() * 4, cudaMemcpyDeviceToHost), "cudaMemcpy trace");
+      for (size_t v = 0; v < p.view.num_unique; ++v) for (int c = 0; c < 3; ++c) packed[v * 3 + c] = padded[v * 4 + c];
+      put(k + "quantized", packed.data(), packed.size() * 4);
+    } else {
+      fetch(k + "quantized", dev_[i].quant, (size_t)p.view.num_unique * p.ncomp_q * 4);
+    }
     fetch(k + "symbols", dev_[i].symbols, p.sequence.size() * p.ncomp_q * 4);
     {
       std::vector<uint32_t> h(r.stats.num_table_symbols);

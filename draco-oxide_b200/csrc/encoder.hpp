@@ -62,7 +62,7 @@ struct AttrPlan {
 struct AttrDevice {
   // inputs
   float* values = nullptr; uint32_t* map = nullptr;
-  uint32_t *corner_vertex = nullptr, *left_most = nullptr, *seq = nullptr; uint8_t* seam = nullptr;
+  uint32_t *corner_vertex = nullptr, *left_most = nullptr, *seq = nullptr; uint8_t* seam = nullptr; uint4* corner_vertex4 = nullptr;
   // intermediates / outputs
   int32_t* quant = nullptr; uint32_t *rank = nullptr, *symbols = nullptr, *hist = nullptr, *work = nullptr;
   uint8_t *side = nullptr, *table_bytes = nullptr, *payload = nullptr, *rans_scratch = nullptr; uint4* rans_table = nullptr;
@@ -114,6 +114,8 @@ class MeshJob {
   std::vector<uint32_t> corners_of_edgebreaker_;
   // device
   uint32_t *d_faces_ = nullptr, *d_opposite_ = nullptr, *d_corner_vertex_ = nullptr, *d_left_most_ = nullptr;
+  uint4 *d_faces4_ = nullptr, *d_corner_vertex4_ = nullptr;
+  bool vertex_is_point_ = false;
   std::vector<AttrDevice> dev_;
   std::vector<AttrResult> results_;
   std::vector<void*> allocations_;

@@ -39,6 +39,27 @@ __device__ __forceinline__ uint32_t opp_of(const TableDev& t, uint32_t c) {
 }
 __device__ __forceinline__ uint32_t value_index(const QuantDev& q, uint32_t point) { return q.map ? __ldg(q.map + point) : point; }
 
+// Quantized values are stored with a power-of-two stride so one value is one vector load:
+// N = 1 -> int, N = 2 -> int2, N = 3 -> int4 (w unused), N = 4 -> int4.
+template <int N> __device__ __forceinline__ void load_q(const QuantDev& q, uint32_t vi, int32_t* out) {
+  if (N == 1) { out[0] = __ldg(q.values + vi); }
+  else if (N == 2) { const int2 v = __ldg(reinterpret_cast<const int2*>(q.values) + vi); out[0] = v.x; out[1] = v.y; }
+  else { const int4 v = __ldg(reinterpret_cast<const int4*>(q.values) + vi); out[0] = v.x; out[1] = v.y; out[2] = v.z; if (N == 4) out[3] = v.w; }
+}
+
+// The three corners of a face are one 16-byte tuple {c0, c1, c2, -}: corner c = 3 f + k reads
+// its own entry and those of next(c) / prev(c) with a single LDG.128.
+struct Tri { uint32_t self, next, prev; };
+__device__ __forceinline__ Tri load_tri(const uint4* __restrict__ tuples, uint32_t c) {
+  const uint32_t f = c / 3u, k = c - 3u * f;
+  const uint4 t = __ldg(tuples + f);
+  Tri r;
+  r.self = k == 0 ? t.x : (k == 1 ? t.y : t.z);
+  r.next = k == 0 ? t.y : (k == 1 ? t.z : t.x);
+  r.prev = k == 0 ? t.z : (k == 1 ? t.x : t.y);
+  return r;
+}
+
 // to_positive_i32 — utils/mod.rs:152-158 (wrapping arithmetic)
 __device__ __forceinline__ uint32_t zigzag(int32_t v) {
   return v >= 0 ? ((uint32_t)v << 1) : ((((uint32_t)(-(v + 1))) << 1) + 1u);
@@ -127,9 +148,10 @@ void launch_minmax(const float* values, uint64_t num_values, uint32_t ncomp, Att
 }
 
 // K2 — q = (i32)(i64)(((v - min) / range) * (2^bits - 1) + 0.5), four separate f32
-// roundings (quantization_coordinate_wise.rs:70-91). One thread per component, flat.
+// roundings (quantization_coordinate_wise.rs:70-91). One thread per value; the result is
+// stored with the padded stride of load_q (N = 3 -> int4).
 template <int N>
-__global__ void __launch_bounds__(kThreads) quantize_kernel(const float* __restrict__ values, uint64_t num_components_total, uint32_t bits,
+__global__ void __launch_bounds__(kThreads) quantize_kernel(const float* __restrict__ values, uint64_t num_values, uint32_t bits,
                                                             int32_t* __restrict__ out, AttrStats* stats) {
   float mn[N];
   float range = 0.0f;
@@ -142,30 +164,42 @@ __global__ void __launch_bounds__(kThreads) quantize_kernel(const float* __restr
   if (blockIdx.x == 0 && threadIdx.x == 0) stats->range = range;
   const float maxq = (float)(unsigned long long)((1ull << bits) - 1ull);
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_components_total; i += stride) {
-    const int k = (int)(i % N);
-    float m = mn[0];
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_values; i += stride) {
+    int32_t q[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int j = 1; j < N; ++j) if (k == j) m = mn[j];
-    const float v = __ldcs(values + i);
-    const float diff = v - m;
-    const float normalized = (range == 0.0f) ? diff : (diff / range);
-    const float quantized = normalized * maxq;
-    const float r = quantized + 0.5f;
-    const long long wide = (long long)r;  // cvt.rzi.s64.f32: truncates, saturates, NaN -> 0 (Rust `as i64`)
-    __stcs(out + i, (int32_t)wide);       // wrapping `as i32`
+    for (int k = 0; k < N; ++k) {
+      const float v = __ldcs(values + i * N + k);
+      const float diff = v - mn[k];
+      const float normalized = (range == 0.0f) ? diff : (diff / range);
+      const float quantized = normalized * maxq;
+      const float r = quantized + 0.5f;
+      const long long wide = (long long)r;  // cvt.rzi.s64.f32: truncates, saturates, NaN -> 0 (Rust `as i64`)
+      q[k] = (int32_t)wide;                 // wrapping `as i32`
+    }
+    if (N == 1) out[i] = q[0];
+    else if (N == 2) reinterpret_cast<int2*>(out)[i] = make_int2(q[0], q[1]);
+    else reinterpret_cast<int4*>(out)[i] = make_int4(q[0], q[1], q[2], q[3]);
   }
 }
 
 void launch_quantize(const float* values, uint64_t num_values, uint32_t ncomp, uint32_t bits, int32_t* out, AttrStats* stats, cudaStream_t s) {
-  const uint64_t total = num_values * ncomp;
-  const int g = grid_for(total, kThreads * 4);
+  const int g = grid_for(num_values, kThreads * 2);
   switch (ncomp) {
-    case 1: quantize_kernel<1><<<g, kThreads, 0, s>>>(values, total, bits, out, stats); break;
-    case 2: quantize_kernel<2><<<g, kThreads, 0, s>>>(values, total, bits, out, stats); break;
-    case 3: quantize_kernel<3><<<g, kThreads, 0, s>>>(values, total, bits, out, stats); break;
-    default: quantize_kernel<4><<<g, kThreads, 0, s>>>(values, total, bits, out, stats); break;
+    case 1: quantize_kernel<1><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats); break;
+    case 2: quantize_kernel<2><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats); break;
+    case 3: quantize_kernel<3><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats); break;
+    default: quantize_kernel<4><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats); break;
   }
+}
+
+// 3-wide arrays -> 16-byte tuples: faces / corner_vertex (one tuple per face), ToBits values with 3 components.
+__global__ void __launch_bounds__(kThreads) pad3_kernel(const uint32_t* __restrict__ in, uint64_t n_tuples, uint4* __restrict__ out) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_tuples; i += stride)
+    out[i] = make_uint4(__ldcs(in + 3 * i), __ldcs(in + 3 * i + 1), __ldcs(in + 3 * i + 2), 0u);
+}
+void launch_pad3(const uint32_t* in, uint64_t n_tuples, uint4* out, cudaStream_t s) {
+  pad3_kernel<<<grid_for(n_tuples, kThreads * 2), kThreads, 0, s>>>(in, n_tuples, out);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -224,10 +258,10 @@ __global__ void __launch_bounds__(kThreads) seq_prepare_kernel(const uint32_t* _
     rank[__ldg(t.corner_vertex + c)] = i;
     if (want_minmax) {
       const uint32_t vi = value_index(q, __ldg(t.corner_point + c));
-      for (uint32_t k = 0; k < q.num_components; ++k) {
-        const int32_t o = __ldg(q.values + (uint64_t)vi * q.num_components + k);
-        mn = min(mn, o); mx = max(mx, o);
-      }
+      int32_t o[4];
+      const uint32_t nq = q.num_components;
+      if (nq == 1) load_q<1>(q, vi, o); else if (nq == 2) load_q<2>(q, vi, o); else if (nq == 3) load_q<3>(q, vi, o); else load_q<4>(q, vi, o);
+      for (uint32_t k = 0; k < nq; ++k) { mn = min(mn, o[k]); mx = max(mx, o[k]); }
     }
   }
   if (want_minmax) {
@@ -274,8 +308,7 @@ __device__ __forceinline__ void previous_value(const uint32_t* seq, uint32_t i, 
   const uint32_t last_v = __ldg(t.corner_vertex + __ldg(seq + i - 1));
   const uint32_t lc = __ldg(t.left_most + last_v);
   const uint32_t vi = value_index(q, __ldg(t.corner_point + lc));
-#pragma unroll
-  for (int k = 0; k < N; ++k) pred[k] = __ldg(q.values + (uint64_t)vi * N + k);
+  load_q<N>(q, vi, pred);
 }
 
 // K4 — MeshParallelogramPrediction::predict (mesh_parallelogram_prediction.rs:186-237)
@@ -291,27 +324,28 @@ __global__ void __launch_bounds__(kThreads) predict_parallelogram_kernel(const u
     int32_t pred[N];
     bool have = false;
     const uint32_t o = opp_of(t, c);
+    const Tri pts = load_tri(t.corner_point4, c);  // points of c, next(c), prev(c): one 128-bit load
     if (o != kNoneDev) {
-      const uint32_t nc = cnext(c), pc = cprev(c);
-      const uint32_t r0 = __ldg(rank + __ldg(t.corner_vertex + o));
-      const uint32_t r1 = __ldg(rank + __ldg(t.corner_vertex + nc));
-      const uint32_t r2 = __ldg(rank + __ldg(t.corner_vertex + pc));
+      // without non-manifold splits / seams / point maps a corner's vertex is its point: skip the vertex tuples
+      const Tri vts = t.vertex_is_point ? pts : load_tri(t.corner_vertex4, c);
+      const uint32_t ov = t.vertex_is_point ? __ldg(t.corner_point + o) : __ldg(t.corner_vertex + o);
+      const uint32_t r0 = __ldg(rank + ov), r1 = __ldg(rank + vts.next), r2 = __ldg(rank + vts.prev);
       if (r0 < i && r1 < i && r2 < i) {
-        const uint32_t a = value_index(q, __ldg(t.corner_point + nc));
-        const uint32_t b = value_index(q, __ldg(t.corner_point + pc));
-        const uint32_t d = value_index(q, __ldg(t.corner_point + o));
+        int32_t qa[N], qb[N], qd[N];
+        load_q<N>(q, value_index(q, pts.next), qa);
+        load_q<N>(q, value_index(q, pts.prev), qb);
+        load_q<N>(q, value_index(q, t.vertex_is_point ? ov : __ldg(t.corner_point + o)), qd);
 #pragma unroll
-        for (int k = 0; k < N; ++k)
-          pred[k] = (int32_t)((uint32_t)__ldg(q.values + (uint64_t)a * N + k) + (uint32_t)__ldg(q.values + (uint64_t)b * N + k) -
-                              (uint32_t)__ldg(q.values + (uint64_t)d * N + k));
+        for (int k = 0; k < N; ++k) pred[k] = (int32_t)((uint32_t)qa[k] + (uint32_t)qb[k] - (uint32_t)qd[k]);
         have = true;
       }
     }
     if (!have) previous_value<N>(seq, i, t, q, pred);
-    const uint32_t vi = value_index(q, __ldg(t.corner_point + c));
+    int32_t orig[N];
+    load_q<N>(q, value_index(q, pts.self), orig);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      const uint32_t s = wrapped_symbol(__ldg(q.values + (uint64_t)vi * N + k), pred[k], w);
+      const uint32_t s = wrapped_symbol(orig[k], pred[k], w);
       symbols[(uint64_t)i * N + k] = s;
       nz += s != 0; mxs = max(mxs, s); err |= (s & 0x80000000u) ? kErrNegativeSymbol : 0u;
     }
@@ -340,9 +374,11 @@ __global__ void __launch_bounds__(kThreads) predict_delta_kernel(const uint32_t*
     int32_t pred[N];
     previous_value<N>(seq, i, t, q, pred);
     const uint32_t vi = value_index(q, __ldg(t.corner_point + c));
+    int32_t orig[N];
+    load_q<N>(q, vi, orig);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      const uint32_t s = zigzag((int32_t)((uint32_t)__ldg(q.values + (uint64_t)vi * N + k) - (uint32_t)pred[k]));
+      const uint32_t s = zigzag((int32_t)((uint32_t)orig[k] - (uint32_t)pred[k]));
       symbols[(uint64_t)i * N + k] = s;
       nz += s != 0; mxs = max(mxs, s); err |= (s & 0x80000000u) ? kErrNegativeSymbol : 0u;
     }
@@ -363,15 +399,12 @@ void launch_predict_delta(const uint32_t* seq, uint32_t n, TableDev t, QuantDev 
 // ---------------------------------------------------------------------------------------
 // K5 — MeshNormalPrediction::predict (mesh_normal_prediction.rs:77-144) fused with
 // OctahedronOrthogonalTransform (oct_orthogonal.rs:23-74).
-__device__ __forceinline__ void load_pos(const QuantDev& pos, const TableDev& t, uint32_t corner, int32_t* p) {
-  const uint32_t vi = value_index(pos, __ldg(t.corner_point + corner));
-  p[0] = __ldg(pos.values + (uint64_t)vi * 3); p[1] = __ldg(pos.values + (uint64_t)vi * 3 + 1); p[2] = __ldg(pos.values + (uint64_t)vi * 3 + 2);
-}
 // compute_normal_of_face (:22-44): cross product in wrapping i32, then widened.
 __device__ __forceinline__ void add_face_normal(const QuantDev& pos, const TableDev& t, uint32_t c, const int32_t* pc, long long* sum) {
   int32_t pn[3], pp[3];
-  load_pos(pos, t, cnext(c), pn);
-  load_pos(pos, t, cprev(c), pp);
+  const Tri pts = load_tri(t.corner_point4, c);
+  load_q<3>(pos, value_index(pos, pts.next), pn);
+  load_q<3>(pos, value_index(pos, pts.prev), pp);
   uint32_t dn[3], dp[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) { dn[k] = (uint32_t)pn[k] - (uint32_t)pc[k]; dp[k] = (uint32_t)pp[k] - (uint32_t)pc[k]; }
@@ -389,7 +422,8 @@ __global__ void __launch_bounds__(kThreads) predict_normal_kernel(const uint32_t
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint32_t c = ld_stream(seq + i);
     int32_t pc[3];
-    load_pos(pos, t, c, pc);
+    const uint32_t point_c = __ldg(t.corner_point + c);
+    load_q<3>(pos, value_index(pos, point_c), pc);
     // swing left to the start of the fan (:86-92), then right summing face normals (:94-101)
     uint32_t cur = c;
     uint32_t guard = t.num_corners;
@@ -424,7 +458,7 @@ __global__ void __launch_bounds__(kThreads) predict_normal_kernel(const uint32_t
       // integer vector -> f32 through f64 (geom.rs:47-52); the normalize() result is discarded there
       oct_quantize_f32((float)(double)nx, (float)(double)ny, (float)(double)nzc, p0, p1);
     }
-    const uint32_t vi = value_index(q, __ldg(t.corner_point + c));
+    const uint32_t vi = value_index(q, point_c);
     const int2 actual = __ldg(reinterpret_cast<const int2*>(q.values) + vi);
     // choose the sign closer to the actual value, in wrapping i32 (:128-143)
     const uint32_t d10 = (uint32_t)p0 - (uint32_t)actual.x, d11 = (uint32_t)p1 - (uint32_t)actual.y;
@@ -486,11 +520,10 @@ __device__ __forceinline__ long long add64w(long long a, long long b) { return (
 __device__ __forceinline__ long long sub64w(long long a, long long b) { return (long long)((unsigned long long)a - (unsigned long long)b); }
 
 // fallback_predict (:52-82): next vertex's value if it is already sequenced, else the last sequenced value
-__device__ __forceinline__ void texcoord_fallback(const uint32_t* seq, uint32_t i, uint32_t c, const TableDev& t, const QuantDev& q,
-                                                  const uint32_t* rank, int32_t* pred) {
-  const uint32_t nc = cnext(c);
-  if (__ldg(rank + __ldg(t.corner_vertex + nc)) < i) {
-    const int2 v = __ldg(reinterpret_cast<const int2*>(q.values) + value_index(q, __ldg(t.corner_point + nc)));
+__device__ __forceinline__ void texcoord_fallback(const uint32_t* seq, uint32_t i, bool next_seen, uint32_t next_pt, const TableDev& t, const QuantDev& q,
+                                                  int32_t* pred) {
+  if (next_seen) {
+    const int2 v = __ldg(reinterpret_cast<const int2*>(q.values) + value_index(q, next_pt));
     pred[0] = v.x; pred[1] = v.y;
     return;
   }
@@ -506,22 +539,23 @@ __global__ void __launch_bounds__(kThreads) predict_texcoord_kernel(const uint32
   const long long I64MAX = 0x7FFFFFFFFFFFFFFFll;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint32_t c = ld_stream(seq + i);
-    const uint32_t nc = cnext(c), pc = cprev(c);
-    const uint32_t next_pt = __ldg(t.corner_point + nc), prev_pt = __ldg(t.corner_point + pc), curr_pt = __ldg(t.corner_point + c);
+    const Tri pts = load_tri(t.corner_point4, c), vts = load_tri(t.corner_vertex4, c);
+    const uint32_t next_pt = pts.next, prev_pt = pts.prev, curr_pt = pts.self;
     const int2 cur = __ldg(reinterpret_cast<const int2*>(q.values) + value_index(q, curr_pt));
     int32_t pred[2];
     uint8_t oflag = 0;  // 0: no orientation bit, 1: bit = false, 2: bit = true
     bool done = false;
-    if (__ldg(rank + __ldg(t.corner_vertex + nc)) < i && __ldg(rank + __ldg(t.corner_vertex + pc)) < i) {
+    const bool next_seen = __ldg(rank + vts.next) < i;
+    if (next_seen && __ldg(rank + vts.prev) < i) {
       const int2 nu = __ldg(reinterpret_cast<const int2*>(q.values) + value_index(q, next_pt));
       const int2 pu = __ldg(reinterpret_cast<const int2*>(q.values) + value_index(q, prev_pt));
       if (nu.x == pu.x && nu.y == pu.y) { pred[0] = pu.x; pred[1] = pu.y; done = true; }
       else {
         long long cp[3] = {0, 0, 0}, np[3] = {0, 0, 0}, pp[3] = {0, 0, 0};
         int32_t tmp[3];
-        if (curr_pt < pos_num_points) { const uint32_t vi = value_index(pos, curr_pt); tmp[0] = __ldg(pos.values + (uint64_t)vi * 3); tmp[1] = __ldg(pos.values + (uint64_t)vi * 3 + 1); tmp[2] = __ldg(pos.values + (uint64_t)vi * 3 + 2); cp[0] = tmp[0]; cp[1] = tmp[1]; cp[2] = tmp[2]; }
-        if (next_pt < pos_num_points) { const uint32_t vi = value_index(pos, next_pt); tmp[0] = __ldg(pos.values + (uint64_t)vi * 3); tmp[1] = __ldg(pos.values + (uint64_t)vi * 3 + 1); tmp[2] = __ldg(pos.values + (uint64_t)vi * 3 + 2); np[0] = tmp[0]; np[1] = tmp[1]; np[2] = tmp[2]; }
-        if (prev_pt < pos_num_points) { const uint32_t vi = value_index(pos, prev_pt); tmp[0] = __ldg(pos.values + (uint64_t)vi * 3); tmp[1] = __ldg(pos.values + (uint64_t)vi * 3 + 1); tmp[2] = __ldg(pos.values + (uint64_t)vi * 3 + 2); pp[0] = tmp[0]; pp[1] = tmp[1]; pp[2] = tmp[2]; }
+        if (curr_pt < pos_num_points) { load_q<3>(pos, value_index(pos, curr_pt), tmp); cp[0] = tmp[0]; cp[1] = tmp[1]; cp[2] = tmp[2]; }
+        if (next_pt < pos_num_points) { load_q<3>(pos, value_index(pos, next_pt), tmp); np[0] = tmp[0]; np[1] = tmp[1]; np[2] = tmp[2]; }
+        if (prev_pt < pos_num_points) { load_q<3>(pos, value_index(pos, prev_pt), tmp); pp[0] = tmp[0]; pp[1] = tmp[1]; pp[2] = tmp[2]; }
         const long long pn[3] = {sub64w(pp[0], np[0]), sub64w(pp[1], np[1]), sub64w(pp[2], np[2])};
         const unsigned long long pn2 = (unsigned long long)add64w(add64w(mul64w(pn[0], pn[0]), mul64w(pn[1], pn[1])), mul64w(pn[2], pn[2]));
         if (pn2 != 0) {
@@ -563,7 +597,7 @@ __global__ void __launch_bounds__(kThreads) predict_texcoord_kernel(const uint32
         }
       }
     }
-    if (!done) texcoord_fallback(seq, i, c, t, q, rank, pred);
+    if (!done) texcoord_fallback(seq, i, next_seen, next_pt, t, q, pred);
     orient[i] = oflag;
     const uint32_t s0 = wrapped_symbol(cur.x, pred[0], w), s1 = wrapped_symbol(cur.y, pred[1], w);
     reinterpret_cast<uint2*>(symbols)[i] = make_uint2(s0, s1);

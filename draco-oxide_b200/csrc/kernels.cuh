@@ -42,6 +42,9 @@ struct AttrStats {
 struct TableDev {
   const uint32_t* corner_point;   // faces
   const uint32_t* corner_vertex;  // attribute (or universal) vertex of each corner
+  const uint4* corner_point4;     // per face {p0, p1, p2, -}: one 128-bit load per corner triple
+  const uint4* corner_vertex4;    // per face {v0, v1, v2, -}
+  int vertex_is_point;            // corner_vertex == corner_point (no point map, seams or splits): vertex tuples are skipped
   const uint32_t* opposite;       // universal opposite corners
   const uint8_t* seam;            // nullptr for the universal table
   const uint32_t* left_most;      // per vertex
@@ -49,7 +52,8 @@ struct TableDev {
   uint32_t num_vertices;
 };
 
-// Quantized attribute: AoS int32 values + optional point map.
+// Quantized attribute: AoS int32 values with a power-of-two stride (1, 2, 4, 4 ints for 1..4
+// components, so one value is one vector load) + optional point map.
 struct QuantDev {
   const int32_t* values;
   const uint32_t* map;  // nullptr = identity
@@ -59,6 +63,7 @@ struct QuantDev {
 // ---- K1/K2: coordinate-wise quantization (quantization_coordinate_wise.rs:24-117) ----
 void launch_minmax(const float* values, uint64_t num_values, uint32_t ncomp, AttrStats* stats, cudaStream_t s);
 void launch_quantize(const float* values, uint64_t num_values, uint32_t ncomp, uint32_t bits, int32_t* out, AttrStats* stats, cudaStream_t s);
+void launch_pad3(const uint32_t* in, uint64_t n_tuples, uint4* out, cudaStream_t s);  // 3-wide -> 16-byte tuples
 // ---- K3: octahedral normal quantization (octahedral_quantization.rs:49-64) ----
 void launch_oct_quantize(const float* normals, uint64_t num_values, int32_t* out, AttrStats* stats, cudaStream_t s);
 // ---- sequence preparation: rank[vertex] = position in the sequence, WrappedDifference min/max ----
