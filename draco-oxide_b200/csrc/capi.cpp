@@ -328,7 +328,7 @@ int dxo_encode_symbols(const uint32_t* symbols, uint64_t n, int device, dxo_byte
     const uint32_t cap = mx + 2;
     uint32_t *d_sym, *d_hist, *d_work; uint4* d_tab; uint8_t *d_tb, *d_pay; gpu::AttrStats* d_st;
     auto alloc = [&](void** p, size_t b) { cuda_check(cudaMallocAsync(p, b, s), "cudaMallocAsync"); };
-    alloc((void**)&d_sym, n * 4); alloc((void**)&d_hist, cap * 4ull); alloc((void**)&d_work, cap * 12ull); alloc((void**)&d_tab, cap * 16ull);
+    alloc((void**)&d_sym, n * 4); alloc((void**)&d_hist, cap * 4ull); alloc((void**)&d_work, cap * 12ull); alloc((void**)&d_tab, (cap + 1) * 16ull);
     alloc((void**)&d_tb, cap * 3ull + 16); alloc((void**)&d_pay, n * 3 + 16); alloc((void**)&d_st, sizeof(gpu::AttrStats));
     void* d_scr; alloc(&d_scr, gpu::rans_scratch_bytes(n));
     cuda_check(cudaMemcpyAsync(d_sym, symbols, n * 4, cudaMemcpyHostToDevice, s), "H2D");
@@ -344,7 +344,7 @@ int dxo_encode_symbols(const uint32_t* symbols, uint64_t n, int device, dxo_byte
     cuda_check(cudaEventRecord(ev[1], s), "rec");
     gpu::launch_build_table(d_hist, cap, n, d_work, d_tab, d_tb, cap * 3 + 16, d_st, s);
     cuda_check(cudaEventRecord(ev[2], s), "rec");
-    gpu::launch_rans_encode(d_sym, n, d_tab, d_scr, d_pay, d_st, s);
+    gpu::launch_rans_encode(d_sym, n, d_tab, cap, d_scr, d_pay, d_st, s);
     cuda_check(cudaEventRecord(ev[3], s), "rec");
     gpu::AttrStats st;
     cuda_check(cudaMemcpyAsync(&st, d_st, sizeof st, cudaMemcpyDeviceToHost, s), "D2H");

@@ -42,6 +42,7 @@ DeviceContext& DeviceContext::get(int device) {
   cuda_check(cudaEventCreate(&c->ev_begin), "cudaEventCreate");
   cuda_check(cudaEventCreate(&c->ev_end), "cudaEventCreate");
   cuda_check(cudaEventCreateWithFlags(&c->ev_pos_ready, cudaEventDisableTiming), "cudaEventCreate");
+  cuda_check(cudaEventCreateWithFlags(&c->ev_layout, cudaEventDisableTiming), "cudaEventCreate");
   for (auto& ev : c->ev_join) cuda_check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate");
   // keep freed blocks in the stream-ordered pool: repeated encodes reuse them without cudaMalloc
   cudaMemPool_t pool;
@@ -332,10 +333,10 @@ void MeshJob::upload(DeviceContext& ctx) {
   else if (ut_.num_vertices != plans_[0].view.num_unique)  // non-manifold vertices were split after K12 ran: refresh the labels
     cuda_check(cudaMemcpyAsync(d_corner_vertex_, ut_.corner_vertex.data(), C * 4, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D");
   d_left_most_ = dupload(ut_.left_most.data(), ut_.left_most.size(), s);
+  // padded per-face layouts are derived on the device at the start of every launch() (part of the timed step)
   d_faces4_ = dalloc<uint4>(ut_.num_faces, s);
-  gpu::launch_pad3(d_faces_, ut_.num_faces, d_faces4_, s);
   vertex_is_point_ = plans_[0].view.map == nullptr && ut_.num_vertices == plans_[0].view.num_unique;
-  if (!vertex_is_point_) { d_corner_vertex4_ = dalloc<uint4>(ut_.num_faces, s); gpu::launch_pad3(d_corner_vertex_, ut_.num_faces, d_corner_vertex4_, s); }
+  if (!vertex_is_point_) d_corner_vertex4_ = dalloc<uint4>(ut_.num_faces, s);
   dev_.assign(plans_.size(), AttrDevice{});
   for (size_t i = 0; i < plans_.size(); ++i) {
     const AttrPlan& p = plans_[i];
@@ -355,14 +356,14 @@ void MeshJob::upload(DeviceContext& ctx) {
     const size_t qstride = p.ncomp_q == 3 ? 4 : p.ncomp_q;  // one value = one vector load (kernels.cu load_q)
     if (p.port == Portabilization::ToBits && p.ncomp_q != 3) d.quant = (int32_t*)d.values;
     else d.quant = dalloc<int32_t>(U * qstride, s);
-    if (p.port == Portabilization::ToBits && p.ncomp_q == 3) gpu::launch_pad3((const uint32_t*)d.values, U, (uint4*)d.quant, s);
-    if (i > 0) { d.corner_vertex4 = dalloc<uint4>(ut_.num_faces, s); gpu::launch_pad3(d.corner_vertex, ut_.num_faces, d.corner_vertex4, s); }
+    if (i > 0) d.corner_vertex4 = dalloc<uint4>(ut_.num_faces, s);
+    if (i > 0 && p.scheme == Scheme::Normal) d.opposite_masked = dalloc<uint32_t>(C, s);  // fan walks read one masked opposite per swing
     d.rank = dalloc<uint32_t>(V, s);
     d.symbols = dalloc<uint32_t>(M * p.ncomp_q, s);
     d.side = dalloc<uint8_t>(M, s);
     d.hist = dalloc<uint32_t>(p.hist_capacity, s);
     d.work = dalloc<uint32_t>(3 * (size_t)p.hist_capacity, s);
-    d.rans_table = dalloc<uint4>(p.hist_capacity, s);
+    d.rans_table = dalloc<uint4>(p.hist_capacity + 1, s);
     d.table_capacity = 3 * p.hist_capacity + 16;
     d.table_bytes = dalloc<uint8_t>(d.table_capacity, s);
     d.payload_capacity = 3 * (uint64_t)M * p.ncomp_q + 16;  // <= P/8 <= 2.5 bytes per symbol + tail
@@ -388,6 +389,7 @@ gpu::TableDev MeshJob::table_dev(size_t att) const {
   t.corner_point = d_faces_;
   t.corner_point4 = d_faces4_;
   t.opposite = d_opposite_;
+  t.opposite_masked = att == 0 ? d_opposite_ : dev_[att].opposite_masked;
   t.num_corners = ut_.num_corners;
   if (att == 0) {
     t.corner_vertex = d_corner_vertex_; t.corner_vertex4 = vertex_is_point_ ? d_faces4_ : d_corner_vertex4_; t.vertex_is_point = vertex_is_point_ ? 1 : 0;
@@ -404,6 +406,15 @@ gpu::TableDev MeshJob::table_dev(size_t att) const {
 void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
   const uint64_t C = ut_.num_corners;
   const uint64_t Upos = plans_[0].view.num_unique;
+  {  // shared per-face corner tuples (one 128-bit load per face in the predictors)
+    cudaStream_t s0 = ctx.stream[0];
+    prof.begin("layout_faces", 28ull * ut_.num_faces * (vertex_is_point_ ? 1 : 2), s0);
+    gpu::launch_pad3(d_faces_, ut_.num_faces, d_faces4_, s0);
+    if (!vertex_is_point_) { gpu::launch_pad3(d_corner_vertex_, ut_.num_faces, d_corner_vertex4_, s0); ++prof.launches; }
+    prof.end(s0);
+    cuda_check(cudaEventRecord(ctx.ev_layout, s0), "cudaEventRecord");
+    for (int k = 1; k < 3; ++k) cuda_check(cudaStreamWaitEvent(ctx.stream[k], ctx.ev_layout, 0), "cudaStreamWaitEvent");
+  }
   for (size_t i = 0; i < plans_.size(); ++i) {
     const AttrPlan& p = plans_[i];
     AttrDevice& d = dev_[i];
@@ -419,6 +430,16 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     cuda_check(cudaMemsetAsync(d.hist, 0, sizeof(uint32_t) * p.hist_capacity, s), "cudaMemsetAsync");
     cuda_check(cudaMemsetAsync(d.rank, 0xFF, sizeof(uint32_t) * V, s), "cudaMemsetAsync");
 
+    if (i > 0) {
+      prof.begin("layout_attribute", 28ull * ut_.num_faces + (d.opposite_masked ? 9 * C : 0), s);
+      gpu::launch_pad3(d.corner_vertex, ut_.num_faces, d.corner_vertex4, s);
+      if (d.opposite_masked) { gpu::launch_mask_opposite(d_opposite_, d.seam, C, d.opposite_masked, s); ++prof.launches; }
+      prof.end(s);
+    }
+    if (p.port == Portabilization::ToBits && p.ncomp_q == 3) {
+      gpu::launch_pad3((const uint32_t*)d.values, U, (uint4*)d.quant, s);
+      ++prof.launches;
+    }
     if (p.port == Portabilization::Quantize) {
       prof.begin("K1_minmax", 4 * p.ncomp_in * U, s);
       gpu::launch_minmax(d.values, U, p.ncomp_in, d.stats, s);
@@ -483,7 +504,7 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     gpu::launch_build_table(d.hist, p.hist_capacity, S, d.work, d.rans_table, d.table_bytes, d.table_capacity, d.stats, s);
     prof.end(s);
     prof.begin("K10_rans_encode", 4 * S, s);
-    gpu::launch_rans_encode(d.symbols, S, d.rans_table, d.rans_scratch, d.payload, d.stats, s);
+    gpu::launch_rans_encode(d.symbols, S, d.rans_table, p.hist_capacity, d.rans_scratch, d.payload, d.stats, s);
     prof.launches += gpu::rans_launch_count(S) - 1;  // speculate + relax rounds + fix-up + gather
     prof.end(s);
   }
@@ -553,6 +574,10 @@ void MeshJob::download(DeviceContext& ctx) {
       cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
       AttrResult& r = results_[i];
       if (int st = status_from_flags(r.stats.error_flags)) throw Error(st, "device reported an encoding error");
+      static const bool rans_debug = getenv("DXO_RANS_DEBUG") != nullptr;
+      if (rans_debug) fprintf(stderr, "[dxo] att %zu: rANS symbols=%llu P=%u K=%u chunks=%u relaxed=%u fixup=%u\n", i,
+                              (unsigned long long)plans_[i].sequence.size() * plans_[i].ncomp_q, r.stats.precision, r.stats.num_table_symbols,
+                              gpu::rans_num_chunks((uint64_t)plans_[i].sequence.size() * plans_[i].ncomp_q), r.stats.pad[0], r.stats.pad[1]);
       if (r.stats.table_bytes > dev_[i].table_capacity || r.stats.payload_bytes > dev_[i].payload_capacity)
         throw Error(DXO_ERR_INTERNAL, "device output exceeds its buffer");
       uint8_t* host = ctx.pinned_buffer(2 * i, (size_t)r.stats.table_bytes + r.stats.payload_bytes + 16);

@@ -22,7 +22,7 @@ struct DeviceContext {
   // pinned host staging, reused across calls (slot = attribute index * 2 + {0: results, 1: side flags})
   std::vector<std::pair<uint8_t*, size_t>> pinned;
   uint8_t* pinned_buffer(size_t slot, size_t bytes);
-  cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_pos_ready = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_pos_ready = nullptr, ev_layout = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   static DeviceContext& get(int device);  // thread-local; throws DXO_ERR_NO_DEVICE when there is no usable GPU
 };
 
@@ -62,7 +62,7 @@ struct AttrPlan {
 struct AttrDevice {
   // inputs
   float* values = nullptr; uint32_t* map = nullptr;
-  uint32_t *corner_vertex = nullptr, *left_most = nullptr, *seq = nullptr; uint8_t* seam = nullptr; uint4* corner_vertex4 = nullptr;
+  uint32_t *corner_vertex = nullptr, *left_most = nullptr, *seq = nullptr; uint8_t* seam = nullptr; uint4* corner_vertex4 = nullptr; uint32_t* opposite_masked = nullptr;
   // intermediates / outputs
   int32_t* quant = nullptr; uint32_t *rank = nullptr, *symbols = nullptr, *hist = nullptr, *work = nullptr;
   uint8_t *side = nullptr, *table_bytes = nullptr, *payload = nullptr, *rans_scratch = nullptr; uint4* rans_table = nullptr;

@@ -44,6 +44,7 @@ struct TableDev {
   const uint32_t* corner_vertex;  // attribute (or universal) vertex of each corner
   const uint4* corner_point4;     // per face {p0, p1, p2, -}: one 128-bit load per corner triple
   const uint4* corner_vertex4;    // per face {v0, v1, v2, -}
+  const uint32_t* opposite_masked;  // optional: opposite with seam edges set to none (fan walks of K5)
   int vertex_is_point;            // corner_vertex == corner_point (no point map, seams or splits): vertex tuples are skipped
   const uint32_t* opposite;       // universal opposite corners
   const uint8_t* seam;            // nullptr for the universal table
@@ -63,6 +64,7 @@ struct QuantDev {
 // ---- K1/K2: coordinate-wise quantization (quantization_coordinate_wise.rs:24-117) ----
 void launch_minmax(const float* values, uint64_t num_values, uint32_t ncomp, AttrStats* stats, cudaStream_t s);
 void launch_quantize(const float* values, uint64_t num_values, uint32_t ncomp, uint32_t bits, int32_t* out, AttrStats* stats, cudaStream_t s);
+void launch_mask_opposite(const uint32_t* opposite, const uint8_t* seam, uint64_t n, uint32_t* out, cudaStream_t s);
 void launch_pad3(const uint32_t* in, uint64_t n_tuples, uint4* out, cudaStream_t s);  // 3-wide -> 16-byte tuples
 // ---- K3: octahedral normal quantization (octahedral_quantization.rs:49-64) ----
 void launch_oct_quantize(const float* normals, uint64_t num_values, int32_t* out, AttrStats* stats, cudaStream_t s);
@@ -76,7 +78,7 @@ void launch_predict_delta(const uint32_t* seq, uint32_t n, TableDev t, QuantDev 
 // ---- K8: symbol histogram (symbol_coding.rs:149-157) ----
 void launch_histogram(const uint32_t* symbols, uint64_t num_symbols, uint32_t* hist, uint32_t hist_capacity, AttrStats* stats, cudaStream_t s);
 // ---- K9: probability table normalisation + serialisation + rANS lookup table (rans.rs:146-230) ----
-// rans_table entries: {freq, cumulative, magic multiplier, shift}
+// rans_table: hist_capacity + 1 entries {freq, cumulative, magic multiplier, shift}; entry [#symbols] is the identity row
 void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t total_symbols, uint32_t* work /*3*capacity*/, uint4* rans_table,
                         uint8_t* table_bytes, uint32_t table_bytes_capacity, AttrStats* stats, cudaStream_t s);
 // ---- K10: rANS emission, serial within the stream (rans.rs:33-68) ----
@@ -84,7 +86,7 @@ void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t t
 size_t rans_scratch_bytes(uint64_t num_symbols);
 uint32_t rans_num_chunks(uint64_t num_symbols);
 int rans_launch_count(uint64_t num_symbols);  // kernels launch_rans_encode issues
-void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, void* scratch, uint8_t* payload,
+void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, uint32_t table_capacity, void* scratch, uint8_t* payload,
                         AttrStats* stats, cudaStream_t s);
 // ---- K12: half-edge matching by radix sort (corner_table/mod.rs:252-340, fast path) ----
 // keys/vals/tmp are caller-provided scratch (see corner_table_scratch_bytes).
