@@ -4,6 +4,7 @@
 // visiting order while working on flat arrays.
 // Reference paths are relative to /root/reference/draco-oxide/src/.
 #include "connectivity.hpp"
+#include <future>
 
 #include <chrono>
 #include <cstdio>
@@ -17,24 +18,6 @@ void UniversalTable::build(const uint32_t* faces, uint32_t nfaces, const AttrVie
   num_faces = nfaces;
   num_corners = nfaces * 3u;
   corner_point = faces;
-  corner_vertex.resize(num_corners);
-  uint32_t max_v = 0;
-  for (uint32_t c = 0; c < num_corners; ++c) {
-    const uint32_t p = faces[c];
-    if (p >= pos.num_points) throw Error(DXO_ERR_INVALID_ARGUMENT, "face references a point outside the position attribute");
-    const uint32_t v = pos.value_of(p);
-    if (v >= pos.num_unique) throw Error(DXO_ERR_INVALID_ARGUMENT, "point_to_value entry out of range");
-    corner_vertex[c] = v;
-    max_v = std::max(max_v, v);
-  }
-  num_vertices = num_corners ? max_v + 1u : 0u;
-  // every vertex id up to the maximum must be used (get_unused_vertices, :236-250; panic :105-108)
-  {
-    std::vector<uint8_t> used(num_vertices, 0);
-    for (uint32_t c = 0; c < num_corners; ++c) used[corner_vertex[c]] = 1;
-    for (uint32_t v = 0; v < num_vertices; ++v)
-      if (!used[v]) throw Error(DXO_ERR_UNUSED_VERTICES, "mesh contains unused vertices");
-  }
   const bool timing = getenv("DXO_TIMING") != nullptr;
   auto t0 = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
@@ -43,14 +26,56 @@ void UniversalTable::build(const uint32_t* faces, uint32_t nfaces, const AttrVie
     fprintf(stderr, "[dxo]   %-26s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t0).count());
     t0 = n;
   };
+  corner_vertex.resize(num_corners);
+  // vertex ids of the corners, range checks and the largest id; large meshes split the pass over a few threads
+  auto fill_range = [&](uint32_t c0, uint32_t c1) -> uint32_t {
+    uint32_t mx = 0;
+    for (uint32_t c = c0; c < c1; ++c) {
+      const uint32_t p = faces[c];
+      if (p >= pos.num_points) throw Error(DXO_ERR_INVALID_ARGUMENT, "face references a point outside the position attribute");
+      const uint32_t v = pos.value_of(p);
+      if (v >= pos.num_unique) throw Error(DXO_ERR_INVALID_ARGUMENT, "point_to_value entry out of range");
+      corner_vertex[c] = v;
+      mx = std::max(mx, v);
+    }
+    return mx;
+  };
+  uint32_t max_v = 0;
+  if (num_corners >= (1u << 20)) {
+    constexpr uint32_t kParts = 4;
+    std::future<uint32_t> parts[kParts];
+    for (uint32_t k = 0; k < kParts; ++k) {
+      const uint32_t c0 = (uint32_t)((uint64_t)num_corners * k / kParts), c1 = (uint32_t)((uint64_t)num_corners * (k + 1) / kParts);
+      parts[k] = std::async(std::launch::async, fill_range, c0, c1);
+    }
+    std::exception_ptr first_error;
+    for (auto& f : parts) { try { max_v = std::max(max_v, f.get()); } catch (...) { if (!first_error) first_error = std::current_exception(); } }
+    if (first_error) std::rethrow_exception(first_error);
+  } else {
+    max_v = fill_range(0, num_corners);
+  }
+  num_vertices = num_corners ? max_v + 1u : 0u;
+  // every vertex id up to the maximum must be used (get_unused_vertices, :236-250; panic :105-108);
+  // the device pass (K13) reports this itself when it runs
+  auto check_all_used = [&] {
+    std::vector<uint8_t> used(num_vertices, 0);
+    for (uint32_t c = 0; c < num_corners; ++c) used[corner_vertex[c]] = 1;
+    for (uint32_t v = 0; v < num_vertices; ++v)
+      if (!used[v]) throw Error(DXO_ERR_UNUSED_VERTICES, "mesh contains unused vertices");
+  };
   lap("vertex ids + checks");
   bool nm = false;
   matched_on_device = false;
+  uint32_t device_done = 0;
   if (matcher) {
     opposite.resize(num_corners);
-    matched_on_device = matcher(matcher_user, corner_vertex.data(), num_faces, opposite.data());
-    lap(matched_on_device ? "half-edge matching (K12)" : "half-edge matching (K12, not exact)");
+    left_most.resize(num_vertices);
+    device_done = matcher(matcher_user, corner_vertex.data(), num_faces, num_vertices, opposite.data(), left_most.data());
+    if (device_done & kUnusedVertices) throw Error(DXO_ERR_UNUSED_VERTICES, "mesh contains unused vertices");
+    matched_on_device = (device_done & kMatchExact) != 0;
+    lap(matched_on_device ? ((device_done & kLeftMostDone) ? "half edges + left-most (K12, K13)" : "half-edge matching (K12)") : "half-edge matching (K12, not exact)");
   }
+  if (!(matched_on_device && (device_done & kLeftMostDone))) { check_all_used(); lap("unused-vertex check"); }
   if (!matched_on_device) {
     match_half_edges();
     lap("half-edge matching");
@@ -58,8 +83,10 @@ void UniversalTable::build(const uint32_t* faces, uint32_t nfaces, const AttrVie
     lap("non-manifold edge test");
   }
   if (nm) break_non_manifold_edges();
-  assign_left_most_corners();
-  lap("left-most corners");
+  if (!(matched_on_device && (device_done & kLeftMostDone))) {
+    assign_left_most_corners();
+    lap("left-most corners");
+  }
 }
 
 // compute_table — :252-340. Per-source-vertex buckets of open half edges; a corner
@@ -283,7 +310,7 @@ class EdgebreakerRun {
   explicit EdgebreakerRun(const UniversalTable& ut) : ut_(ut) {
     vertex_done_.assign(ut.num_vertices, 0);
     face_done_.assign(ut.num_faces, 0);
-    split_symbol_of_face_.assign(ut.num_faces, kNoSymbol);
+    split_symbol_of_face_.assign(ut.num_faces, kNone);
   }
 
   // phase 1: the CLERS traversal of every connected component (needs only the universal table)
@@ -313,6 +340,7 @@ class EdgebreakerRun {
     corners_.insert(corners_.end(), visit_order_.begin(), visit_order_.end());
   }
   const std::vector<uint32_t>& corners_of_edgebreaker() const { return corners_; }
+  std::vector<uint32_t> take_corners_of_edgebreaker() { return std::move(corners_); }
 
   // phase 2a: everything of the connectivity section up to and including the start-face stream
   void write_head(ByteSink& w, size_t num_seam_tables) const {
@@ -327,11 +355,10 @@ class EdgebreakerRun {
   }
 
  private:
-  static constexpr uint64_t kNoSymbol = ~(uint64_t)0;
   const UniversalTable& ut_;
   std::vector<uint8_t> vertex_done_, face_done_, hole_done_, symbols_, start_face_interior_;
   std::vector<uint32_t> hole_of_vertex_, stack_, visit_order_, init_face_corners_, corners_;
-  std::vector<uint64_t> split_symbol_of_face_;
+  std::vector<uint32_t> split_symbol_of_face_;  // symbol index of the S symbol a face got (< num_faces), kNone otherwise
   std::vector<SplitEvent> split_events_;
   uint64_t symbol_index_ = ~(uint64_t)0;  // usize::MAX, incremented with wrap before use (:150,:276)
   uint64_t num_splits_ = 0;
@@ -392,8 +419,8 @@ class EdgebreakerRun {
 
   void note_split_event(uint8_t right, uint32_t neighbour_corner) {  // check_and_store_topology_split_event — :434-448
     if (neighbour_corner == kNone) return;
-    const uint64_t s = split_symbol_of_face_[neighbour_corner / 3u];
-    if (s != kNoSymbol) split_events_.push_back({symbol_index_, s, right});
+    const uint32_t s = split_symbol_of_face_[neighbour_corner / 3u];
+    if (s != kNone) split_events_.push_back({symbol_index_, (uint64_t)s, right});
   }
 
   // edgebreaker_from — :261-350
@@ -441,7 +468,7 @@ class EdgebreakerRun {
           ++num_splits_;
           const uint32_t hole = hole_of_vertex_[v];
           if (hole != kNone && !hole_done_[hole]) walk_boundary(c, false);
-          split_symbol_of_face_[face] = symbol_index_;
+          split_symbol_of_face_[face] = (uint32_t)symbol_index_;
           stack_.back() = lc;
           stack_.push_back(rc);
           break;
@@ -518,6 +545,7 @@ EdgebreakerEncoder::EdgebreakerEncoder(const UniversalTable& ut) : run_(new Edge
 EdgebreakerEncoder::~EdgebreakerEncoder() { delete run_; }
 void EdgebreakerEncoder::traverse() { run_->traverse_all(); }
 const std::vector<uint32_t>& EdgebreakerEncoder::corners_of_edgebreaker() const { return run_->corners_of_edgebreaker(); }
+std::vector<uint32_t> EdgebreakerEncoder::take_corners_of_edgebreaker() { return run_->take_corners_of_edgebreaker(); }
 void EdgebreakerEncoder::write_head(ByteSink& w, size_t num_seam_tables) const {
   if (num_seam_tables > 255) throw Error(DXO_ERR_TOO_MANY_ATTRIBUTES, "too many connectivity attributes");
   run_->write_head(w, num_seam_tables);

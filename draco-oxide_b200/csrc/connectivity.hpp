@@ -31,10 +31,14 @@ struct UniversalTable {
   uint32_t swing_left(uint32_t c) const { uint32_t o = opposite[corner_next(c)]; return o == kNone ? kNone : corner_next(o); }
   uint32_t swing_right(uint32_t c) const { uint32_t o = opposite[corner_prev(c)]; return o == kNone ? kNone : corner_prev(o); }
 
-  // Optional accelerator for the half-edge matching (K12 on the device): fills `opposite_out`
-  // and returns true only when its result provably equals the sequential matcher's
-  // (manifold, consistently oriented input); otherwise the sequential path runs.
-  using DeviceMatcher = bool (*)(void* user, const uint32_t* corner_vertex, uint32_t num_faces, uint32_t* opposite_out);
+  // Optional accelerator (K12 + K13 on the device). Fills `opposite_out` and returns kMatchExact only when
+  // its result provably equals the sequential matcher's (manifold, consistently oriented input);
+  // with kLeftMostDone, `left_most_out[num_vertices]` also holds the left-most corners (every vertex has
+  // a single fan) and all vertex ids are used; kUnusedVertices reports the reference's unused-vertex
+  // panic. Whatever is not reported as done runs sequentially on the host.
+  enum : uint32_t { kMatchExact = 1u, kLeftMostDone = 2u, kUnusedVertices = 4u };
+  using DeviceMatcher = uint32_t (*)(void* user, const uint32_t* corner_vertex, uint32_t num_faces, uint32_t num_vertices,
+                                     uint32_t* opposite_out, uint32_t* left_most_out);
   void build(const uint32_t* faces, uint32_t nfaces, const AttrView& pos, DeviceMatcher matcher = nullptr, void* matcher_user = nullptr);
   bool matched_on_device = false;
 
@@ -85,6 +89,7 @@ class EdgebreakerEncoder {
   EdgebreakerEncoder& operator=(const EdgebreakerEncoder&) = delete;
   void traverse();
   const std::vector<uint32_t>& corners_of_edgebreaker() const;
+  std::vector<uint32_t> take_corners_of_edgebreaker();  // moves the list out (the seam streams do not need it)
   void write_head(ByteSink& w, size_t num_seam_tables) const;
   void write_seam_stream(const SeamTable& st, ByteSink& w) const;
  private:

@@ -39,6 +39,9 @@ DeviceContext& DeviceContext::get(int device) {
   c->device = device;
   for (auto& s : c->stream) cuda_check(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
   cuda_check(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  cuda_check(cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  cuda_check(cudaEventCreateWithFlags(&c->ev_uploaded, cudaEventDisableTiming), "cudaEventCreate");
+  cuda_check(cudaEventCreateWithFlags(&c->ev_inputs, cudaEventDisableTiming), "cudaEventCreate");
   cuda_check(cudaEventCreate(&c->ev_begin), "cudaEventCreate");
   cuda_check(cudaEventCreate(&c->ev_end), "cudaEventCreate");
   cuda_check(cudaEventCreateWithFlags(&c->ev_pos_ready, cudaEventDisableTiming), "cudaEventCreate");
@@ -179,6 +182,7 @@ MeshJob::MeshJob(const dxo_mesh* mesh, const dxo_config& cfg) : mesh_(mesh), cfg
 }
 
 MeshJob::~MeshJob() {
+  if (inputs_upload_.valid()) { try { inputs_upload_.wait(); } catch (...) {} }  // error paths: let the helper finish before freeing
   for (void* p : allocations_) cudaFreeAsync(p, alloc_stream_);  // normally released by release(); this covers error paths
   for (cudaEvent_t e : side_ready_) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : side_copied_) if (e) cudaEventDestroy(e);
@@ -198,33 +202,47 @@ struct StageClock {
 };
 }  // namespace
 
-// K12: half-edge matching on the device. Keeps the device copies of corner_vertex / opposite
-// for the attribute kernels when the result is exact.
-bool MeshJob::device_matcher(void* user, const uint32_t* corner_vertex, uint32_t num_faces, uint32_t* opposite_out) {
+// K12 + K13: half-edge matching and left-most corners on the device, one synchronisation. Keeps the device
+// copies of corner_vertex / opposite / left_most for the attribute kernels when the results are exact.
+uint32_t MeshJob::device_matcher(void* user, const uint32_t* corner_vertex, uint32_t num_faces, uint32_t num_vertices, uint32_t* opposite_out,
+                                 uint32_t* left_most_out) {
   MeshJob* job = (MeshJob*)user;
   DeviceContext& ctx = *job->match_ctx_;
   cudaStream_t s = ctx.stream[0];
   const size_t C = (size_t)num_faces * 3;
   uint32_t* d_cv = job->dupload(corner_vertex, C, s);
   uint32_t* d_opp = job->dalloc<uint32_t>(C, s);
-  uint32_t* d_flag = job->dalloc<uint32_t>(1, s);
-  const size_t sb = gpu::corner_table_scratch_bytes(C);
-  void* scratch = nullptr;
+  uint32_t* d_lm = job->dalloc<uint32_t>(num_vertices, s);
+  uint32_t* d_flag = job->dalloc<uint32_t>(2, s);  // [0] K12 not exact, [1] K13 fan flags
+  const size_t sb = gpu::corner_table_scratch_bytes(C), lb = gpu::left_most_scratch_bytes(num_vertices);
+  void *scratch = nullptr, *lscratch = nullptr;
   cuda_check(cudaMallocAsync(&scratch, sb, s), "cudaMallocAsync");
-  cuda_check(cudaMemsetAsync(d_flag, 0, 4, s), "cudaMemsetAsync");
+  cuda_check(cudaMallocAsync(&lscratch, lb, s), "cudaMallocAsync");
+  cuda_check(cudaMemsetAsync(d_flag, 0, 8, s), "cudaMemsetAsync");
   cuda_check(cudaMemsetAsync(d_opp, 0xFF, C * 4, s), "cudaMemsetAsync");
   gpu::launch_corner_table_opposites(d_cv, C, d_opp, d_flag, scratch, sb, s);
-  uint32_t flag = 1;
-  cuda_check(cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
-  cuda_check(cudaFreeAsync(scratch, s), "cudaFreeAsync");
-  cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
-  if (flag) return false;  // order-dependent case: the sequential matcher decides
+  gpu::launch_left_most(d_cv, d_opp, C, num_vertices, lscratch, d_lm, d_flag + 1, s);
+  uint32_t flag[2] = {1, 0};
+  cuda_check(cudaMemcpyAsync(flag, d_flag, 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+  // the results travel with the flags (one synchronisation); they are ignored when a flag is raised
   cuda_check(cudaMemcpyAsync(opposite_out, d_opp, C * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+  cuda_check(cudaMemcpyAsync(left_most_out, d_lm, (size_t)num_vertices * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+  cuda_check(cudaFreeAsync(scratch, s), "cudaFreeAsync");
+  cuda_check(cudaFreeAsync(lscratch, s), "cudaFreeAsync");
   cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+  uint32_t done = 0;
+  if (flag[1] & 1u) done |= UniversalTable::kUnusedVertices;
+  if (flag[0]) return done;  // order-dependent case: the sequential matcher decides
+  done |= UniversalTable::kMatchExact;
   job->d2h_bytes += C * 4;
   job->d_corner_vertex_ = d_cv;
   job->d_opposite_ = d_opp;
-  return true;
+  if (flag[1] == 0) {
+    done |= UniversalTable::kLeftMostDone;
+    job->d2h_bytes += (size_t)num_vertices * 4;
+    job->d_left_most_ = d_lm;
+  }
+  return done;
 }
 
 void MeshJob::build_connectivity(DeviceContext* ctx) {
@@ -238,6 +256,10 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
   head_.u16(0);   // flags: no metadata
 
   match_ctx_ = ctx;
+  dev_.assign(plans_.size(), AttrDevice{});
+  const bool early_uploads = ctx != nullptr && parallel_host && !getenv("DXO_NO_EARLY_UPLOAD");
+  if (early_uploads)
+    inputs_upload_ = std::async(std::launch::async, [this, ctx] { cuda_check(cudaSetDevice(ctx->device), "cudaSetDevice"); upload_inputs(*ctx); }).share();
   const bool use_k12 = ctx != nullptr && nfaces >= 4096 && !getenv("DXO_NO_K12");  // tiny meshes: the launch + sync costs more than it saves
   ut_.build(mesh_->faces, nfaces, plans_[0].view, use_k12 ? &MeshJob::device_matcher : nullptr, this);
   clk.lap("universal corner table");
@@ -253,7 +275,7 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
     eb.write_head(head_, seams_.size());
     for (size_t i = 1; i < natt; ++i) eb.write_seam_stream(seams_[i - 1], seam_bytes[i - 1]);
     clk.lap("edgebreaker");
-    corners_of_edgebreaker_ = eb.corners_of_edgebreaker();
+    corners_of_edgebreaker_ = eb.take_corners_of_edgebreaker();
     table_refs_[0] = table_ref(ut_);
     for (size_t i = 1; i < natt; ++i) table_refs_[i] = table_ref(ut_, seams_[i - 1]);
     for (size_t i = 0; i < natt; ++i) plans_[i].sequence = attribute_sequence(table_refs_[i], corners_of_edgebreaker_);
@@ -265,20 +287,26 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
     auto wait_all = [&] { std::exception_ptr first; for (auto& t : tasks) { try { if (t.valid()) t.get(); } catch (...) { if (!first) first = std::current_exception(); } } tasks.clear(); if (first) std::rethrow_exception(first); };
     try {
       for (size_t i = 1; i < natt; ++i)
-        tasks.push_back(std::async(std::launch::async, [this, i] { seams_[i - 1].build(ut_, plans_[i].view); }));
-      eb.traverse();
-      corners_of_edgebreaker_ = eb.corners_of_edgebreaker();
+        tasks.push_back(std::async(std::launch::async, [this, i, ctx, early_uploads] {
+          StageClock c;
+          if (early_uploads && !getenv("DXO_NO_K14") && device_seam_table(*ctx, i)) { c.lap("  (thread) seam table (K14)"); return; }
+          seams_[i - 1].build(ut_, plans_[i].view);
+          c.lap("  (thread) seam table");
+          if (early_uploads) { cuda_check(cudaSetDevice(ctx->device), "cudaSetDevice"); upload_seam_table(*ctx, i); c.lap("  (thread) seam table upload"); }
+        }));
+      { StageClock c; eb.traverse(); c.lap("  (main) CLERS traversal"); }
+      corners_of_edgebreaker_ = eb.take_corners_of_edgebreaker();
       table_refs_[0] = table_ref(ut_);
-      auto seq0 = std::async(std::launch::async, [this] { plans_[0].sequence = attribute_sequence(table_refs_[0], corners_of_edgebreaker_); });
+      auto seq0 = std::async(std::launch::async, [this] { StageClock c; plans_[0].sequence = attribute_sequence(table_refs_[0], corners_of_edgebreaker_); c.lap("  (thread) position sequence"); });
       wait_all();  // seam tables
       clk.lap("seam tables + traversal");
       for (size_t i = 1; i < natt; ++i) {
         table_refs_[i] = table_ref(ut_, seams_[i - 1]);
-        tasks.push_back(std::async(std::launch::async, [this, i] { plans_[i].sequence = attribute_sequence(table_refs_[i], corners_of_edgebreaker_); }));
-        tasks.push_back(std::async(std::launch::async, [this, i, &eb, &seam_bytes] { eb.write_seam_stream(seams_[i - 1], seam_bytes[i - 1]); }));
+        tasks.push_back(std::async(std::launch::async, [this, i] { StageClock c; plans_[i].sequence = attribute_sequence(table_refs_[i], corners_of_edgebreaker_); c.lap("  (thread) attribute sequence"); }));
+        tasks.push_back(std::async(std::launch::async, [this, i, &eb, &seam_bytes] { StageClock c; eb.write_seam_stream(seams_[i - 1], seam_bytes[i - 1]); c.lap("  (thread) seam stream"); }));
       }
       tasks.push_back(std::move(seq0));
-      eb.write_head(head_, seams_.size());
+      { StageClock c; eb.write_head(head_, seams_.size()); c.lap("  (main) connectivity head"); }
       wait_all();
       clk.lap("sequences + streams");
     } catch (...) {
@@ -313,6 +341,7 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
 template <class T> T* MeshJob::dalloc(size_t count, cudaStream_t s) {
   void* p = nullptr;
   cuda_check(cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T), s), "cudaMallocAsync");
+  std::lock_guard<std::mutex> lock(alloc_mu_);
   allocations_.push_back(p);
   alloc_stream_ = s;
   return (T*)p;
@@ -320,37 +349,97 @@ template <class T> T* MeshJob::dalloc(size_t count, cudaStream_t s) {
 template <class T> T* MeshJob::dupload(const T* host, size_t count, cudaStream_t s) {
   T* d = dalloc<T>(count, s);
   if (count) cuda_check(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D");
+  std::lock_guard<std::mutex> lock(alloc_mu_);
   h2d_bytes += count * sizeof(T);
   return d;
+}
+
+// Inputs that do not depend on the connectivity (called on a helper thread at the start of build_connectivity,
+// or from upload() when nothing was started early).
+void MeshJob::upload_inputs(DeviceContext& ctx) {
+  cudaStream_t s = ctx.upload_stream;
+  d_faces_ = dupload(mesh_->faces, (size_t)mesh_->num_faces * 3, s);
+  for (size_t i = 0; i < plans_.size(); ++i) {
+    const AttrPlan& p = plans_[i];
+    const dxo_attribute& a = *p.view.raw;
+    dev_[i].values = (float*)dupload((const uint32_t*)a.values, (size_t)p.view.num_unique * p.ncomp_in, s);
+    if (p.view.map) dev_[i].map = dupload(p.view.map, p.view.num_points, s);
+  }
+  cuda_check(cudaEventRecord(ctx.ev_inputs, s), "cudaEventRecord");
+}
+
+// K14: the seam table of attribute `att` from the device-resident universal table (K12 + K13 results).
+// Runs on the helper thread of that attribute; the host copies are needed by the sequencer and the seam stream.
+bool MeshJob::device_seam_table(DeviceContext& ctx, size_t att) {
+  if (!d_opposite_ || !d_corner_vertex_ || !d_left_most_ || !inputs_upload_.valid()) return false;
+  cuda_check(cudaSetDevice(ctx.device), "cudaSetDevice");
+  inputs_upload_.wait();
+  cudaStream_t s = ctx.stream[std::min<size_t>(att, 2)];
+  cuda_check(cudaStreamWaitEvent(s, ctx.ev_inputs, 0), "cudaStreamWaitEvent");
+  const size_t C = ut_.num_corners;
+  const uint32_t V = ut_.num_vertices;
+  AttrDevice& d = dev_[att];
+  if (!d_faces_) return false;  // the inputs upload failed; upload() reports it
+  uint8_t* d_seam = dalloc<uint8_t>(C, s);
+  uint32_t* d_cv = dalloc<uint32_t>(C, s);
+  uint32_t* d_lm = dalloc<uint32_t>(C, s);  // at most one attribute vertex per corner
+  uint32_t* d_scalars = dalloc<uint32_t>(2, s);  // [0] number of attribute vertices, [1] flags
+  const size_t sb = gpu::seam_table_scratch_bytes(V);
+  void* scratch = nullptr;
+  cuda_check(cudaMallocAsync(&scratch, sb, s), "cudaMallocAsync");
+  cuda_check(cudaMemsetAsync(d_scalars, 0, 8, s), "cudaMemsetAsync");
+  gpu::launch_seam_table(d_faces_, d.map, plans_[att].view.num_points, d_corner_vertex_, d_opposite_, d_left_most_, C, V, scratch, sb, d_seam, d_cv,
+                         d_lm, d_scalars, d_scalars + 1, s);
+  uint32_t scalars[2] = {0, 1};
+  cuda_check(cudaMemcpyAsync(scalars, d_scalars, 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+  cuda_check(cudaFreeAsync(scratch, s), "cudaFreeAsync");
+  cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+  if (scalars[1] != 0 || scalars[0] > C) return false;  // the sequential pass reports the error
+  SeamTable& st = seams_[att - 1];
+  st.num_vertices = scalars[0];
+  st.corner_vertex.resize(C);
+  st.seam.resize(C);
+  st.left_most.resize(st.num_vertices);
+  cuda_check(cudaMemcpyAsync(st.corner_vertex.data(), d_cv, C * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+  cuda_check(cudaMemcpyAsync(st.seam.data(), d_seam, C, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+  cuda_check(cudaMemcpyAsync(st.left_most.data(), d_lm, (size_t)st.num_vertices * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+  cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+  { std::lock_guard<std::mutex> lock(alloc_mu_); d2h_bytes += C * 5 + (size_t)st.num_vertices * 4; }
+  d.corner_vertex = d_cv; d.seam = d_seam; d.left_most = d_lm;
+  return true;
+}
+// Seam table of attribute `att` (called by the thread that has just built it).
+void MeshJob::upload_seam_table(DeviceContext& ctx, size_t att) {
+  cudaStream_t s = ctx.upload_stream;
+  const SeamTable& st = seams_[att - 1];
+  AttrDevice& d = dev_[att];
+  d.corner_vertex = dupload(st.corner_vertex.data(), st.corner_vertex.size(), s);
+  d.seam = dupload(st.seam.data(), st.seam.size(), s);
+  d.left_most = dupload(st.left_most.data(), st.left_most.size(), s);
 }
 
 void MeshJob::upload(DeviceContext& ctx) {
   cudaStream_t s = ctx.stream[0];
   const size_t C = ut_.num_corners;
-  d_faces_ = dupload(mesh_->faces, C, s);
+  if (dev_.size() != plans_.size()) dev_.assign(plans_.size(), AttrDevice{});
+  if (inputs_upload_.valid()) inputs_upload_.get();
+  else if (!d_faces_) upload_inputs(ctx);
+  for (size_t i = 1; i < plans_.size(); ++i) if (!dev_[i].corner_vertex) upload_seam_table(ctx, i);
+  cuda_check(cudaEventRecord(ctx.ev_uploaded, ctx.upload_stream), "cudaEventRecord");
+  cuda_check(cudaStreamWaitEvent(s, ctx.ev_uploaded, 0), "cudaStreamWaitEvent");
   if (!d_opposite_) d_opposite_ = dupload(ut_.opposite.data(), C, s);
   if (!d_corner_vertex_) d_corner_vertex_ = dupload(ut_.corner_vertex.data(), C, s);
   else if (ut_.num_vertices != plans_[0].view.num_unique)  // non-manifold vertices were split after K12 ran: refresh the labels
     cuda_check(cudaMemcpyAsync(d_corner_vertex_, ut_.corner_vertex.data(), C * 4, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D");
-  d_left_most_ = dupload(ut_.left_most.data(), ut_.left_most.size(), s);
+  if (!d_left_most_) d_left_most_ = dupload(ut_.left_most.data(), ut_.left_most.size(), s);
   // padded per-face layouts are derived on the device at the start of every launch() (part of the timed step)
   d_faces4_ = dalloc<uint4>(ut_.num_faces, s);
   vertex_is_point_ = plans_[0].view.map == nullptr && ut_.num_vertices == plans_[0].view.num_unique;
   if (!vertex_is_point_) d_corner_vertex4_ = dalloc<uint4>(ut_.num_faces, s);
-  dev_.assign(plans_.size(), AttrDevice{});
   for (size_t i = 0; i < plans_.size(); ++i) {
     const AttrPlan& p = plans_[i];
     AttrDevice& d = dev_[i];
-    const dxo_attribute& a = *p.view.raw;
     const size_t U = p.view.num_unique, M = p.sequence.size();
-    d.values = (float*)dupload((const uint32_t*)a.values, U * p.ncomp_in, s);
-    if (p.view.map) d.map = dupload(p.view.map, p.view.num_points, s);
-    if (i > 0) {
-      const SeamTable& st = seams_[i - 1];
-      d.corner_vertex = dupload(st.corner_vertex.data(), C, s);
-      d.seam = dupload(st.seam.data(), C, s);
-      d.left_most = dupload(st.left_most.data(), st.left_most.size(), s);
-    }
     d.seq = dupload(p.sequence.data(), M, s);
     const uint32_t V = p.table->num_vertices;
     const size_t qstride = p.ncomp_q == 3 ? 4 : p.ncomp_q;  // one value = one vector load (kernels.cu load_q)
@@ -504,7 +593,7 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     gpu::launch_build_table(d.hist, p.hist_capacity, S, d.work, d.rans_table, d.table_bytes, d.table_capacity, d.stats, s);
     prof.end(s);
     prof.begin("K10_rans_encode", 4 * S, s);
-    gpu::launch_rans_encode(d.symbols, S, d.rans_table, p.hist_capacity, d.rans_scratch, d.payload, d.stats, s);
+    gpu::launch_rans_encode(d.symbols, S, d.rans_table, d.rans_scratch, d.payload, d.stats, s);
     prof.launches += gpu::rans_launch_count(S) - 1;  // speculate + relax rounds + fix-up + gather
     prof.end(s);
   }

@@ -3,7 +3,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <future>
 #include <map>
+#include <mutex>
 #include <memory>
 #include <string>
 
@@ -19,6 +21,8 @@ struct DeviceContext {
   int device = 0;
   cudaStream_t stream[3] = {nullptr, nullptr, nullptr};  // attribute i runs on stream[min(i,2)]
   cudaStream_t copy_stream = nullptr;                    // early D2H of the side-stream flags
+  cudaStream_t upload_stream = nullptr;                  // H2D issued by helper threads while the host builds the connectivity
+  cudaEvent_t ev_uploaded = nullptr, ev_inputs = nullptr;
   // pinned host staging, reused across calls (slot = attribute index * 2 + {0: results, 1: side flags})
   std::vector<std::pair<uint8_t*, size_t>> pinned;
   uint8_t* pinned_buffer(size_t slot, size_t bytes);
@@ -119,12 +123,18 @@ class MeshJob {
   std::vector<AttrDevice> dev_;
   std::vector<AttrResult> results_;
   std::vector<void*> allocations_;
+  std::mutex alloc_mu_;              // dalloc / dupload are also called from the helper threads of build_connectivity
+  std::shared_future<void> inputs_upload_;  // faces, values and point maps travel while the host builds the tables
+  bool device_seam_table(DeviceContext& ctx, size_t att);  // K14; false = not applicable / flagged, use the host pass
+  void upload_inputs(DeviceContext& ctx);
+  void upload_seam_table(DeviceContext& ctx, size_t att);
   cudaStream_t alloc_stream_ = nullptr;
   std::vector<cudaEvent_t> side_ready_, side_copied_;
   bool uploaded_ = false;
   void encode_side_stream(size_t att);
 
-  static bool device_matcher(void* user, const uint32_t* corner_vertex, uint32_t num_faces, uint32_t* opposite_out);
+  static uint32_t device_matcher(void* user, const uint32_t* corner_vertex, uint32_t num_faces, uint32_t num_vertices, uint32_t* opposite_out,
+                                 uint32_t* left_most_out);
   DeviceContext* match_ctx_ = nullptr;
   template <class T> T* dalloc(size_t count, cudaStream_t s);
   template <class T> T* dupload(const T* host, size_t count, cudaStream_t s);

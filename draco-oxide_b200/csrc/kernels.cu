@@ -7,6 +7,7 @@
 // tensor cores are not used; the kernels are HBM-bound gathers/streams (K1-K8), one
 // small single-CTA table kernel (K9) and a latency-bound serial coder (K10).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "kernels.cuh"
 
@@ -918,7 +919,6 @@ __global__ void __launch_bounds__(kTableThreads) build_table_kernel(const uint32
     uint32_t v = K, p = 0;
     do { uint8_t b = v & 0x7F; v >>= 7; table_bytes[p++] = v ? (b | 0x80) : b; } while (v);
     stats->bit_length = bit_length; stats->precision = P; stats->num_table_symbols = K; stats->table_bytes = hdr + tot_bytes;
-    rans_table[K] = make_uint4(1u << 21, 0, 0, 0);  // identity row (K10); the table holds capacity + 1 rows
     s_scalar[0] = hdr;
   }
   __syncthreads();
@@ -931,15 +931,19 @@ __global__ void __launch_bounds__(kTableThreads) build_table_kernel(const uint32
       const uint32_t extra = nb - 1;
       table_bytes[off] = (uint8_t)((d << 2) | extra);
       for (uint32_t b = 0; b < extra; ++b) table_bytes[off + 1 + b] = (uint8_t)(d >> (8 * (b + 1) - 2));
-      // K10 lookup: floor(x / d) for x < 2^30 as umulhi(4x, M) >> lp with lp = ceil(log2 d),
-      // M = ceil(2^(30+lp) / d) <= 2^31 (exact, DESIGN.md "rANS division").
-      const uint32_t lp = d == 1 ? 0u : 32u - (uint32_t)__clz(d - 1);
-      const uint32_t magic = (uint32_t)(((1ull << (30u + lp)) + d - 1) / d);
+      // K10 lookup: floor(x / d) for x < 2^30 as umulhi(x, M) >> lp with lp = ceil(log2 d) - 1,
+      // M = ceil(2^(32+lp) / d) < 2^32 (exact, DESIGN.md "rANS division"). d = 1 uses
+      // umulhi(x, 2^32 - 1) + 1 = x (x >= 1), signalled by lp = 0, M = 0xFFFFFFFF.
+      uint32_t lp = 0, magic = 0xFFFFFFFFu;
+      if (d >= 2) {
+        lp = 31u - (uint32_t)__clz(d - 1);  // ceil(log2 d) - 1
+        magic = (uint32_t)(((1ull << (32u + lp)) + d - 1) / d);
+      }
       rans_table[i] = make_uint4(d, cum, magic, lp);
       cum += d;
     } else {
       if (nb) table_bytes[off] = tk;
-      rans_table[i] = make_uint4(1u << 21, 0, 0, 0);  // identity row: never referenced by a stream the table was built from
+      rans_table[i] = make_uint4(0, cum, 0, 0);
     }
     off += nb;
   }
@@ -959,44 +963,42 @@ void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t t
 // few hundred to a few thousand symbols (every renormalisation shifts the low state
 // bits — where small differences live — out into the byte stream). That makes an exact
 // speculative-parallel coder possible (DESIGN.md "Parallel rANS"):
-//   round 0   the stream is cut into chunks of C steps; every chunk is encoded by ONE
-//             THREAD, starting W steps early from an arbitrary state (warm-up); the state
-//             reached at the chunk start is the chunk's *claimed* entering state.
+//   round 0   every chunk of kRansChunk steps is encoded by its own CTA, starting W
+//             steps early from an arbitrary state (warm-up); the state reached at the
+//             chunk start is the chunk's *claimed* entering state.
 //   round r   a chunk whose claimed entering state differs from the exit state of its
-//             predecessor is re-encoded from that exit state (Jacobi relaxation; a round
-//             costs C steps, and a round that re-encodes nothing proves the whole chain).
-//   fix-up    if the last round still re-encoded something, a single CTA walks the
-//             remaining mismatches in order, so the result never depends on the
-//             speculation succeeding; it then prefix-sums the chunk byte counts.
-//   gather    chunk byte strings are concatenated and the 2-bit-tagged final state appended.
+//             predecessor is re-encoded from that exit state (Jacobi relaxation; after
+//             round r chunks 0..r are certainly right, typically 1-2 rounds fix all).
+//   fix-up    a single CTA walks the chunks in order and re-encodes any that is still
+//             inconsistent, so the result never depends on the speculation succeeding.
+//   gather    chunk byte strings are concatenated (prefix sum of their lengths) and the
+//             2-bit-tagged final state is appended.
 // The bytes are those of the sequential coder by construction: chunk 0 starts from
-// l_base and every other chunk was last encoded from its predecessor's final exit state.
+// l_base and every other chunk is (re-)encoded from its predecessor's true exit state.
 //
-// Thread-per-chunk keeps all 32 lanes of a warp busy on the serial chain (the previous
-// design spent a warp pair per chunk). What makes it work is keeping every memory access of
-// the inner loop either coalesced or in shared memory:
-//   * symbols: per 32 steps the warp loads, for each of its 32 chunks, one coalesced 128-byte
-//     row and parks it in shared memory with a 33-word pitch (conflict-free both ways); the
-//     loads of the next group are in flight in registers while the current group is coded;
-//   * table rows {f, cum, M, lp}: copied to shared memory once per CTA (alphabets up to
-//     kRansSmemRows), one LDS.128 per step, fetched two steps ahead;
-//   * bytes: collected in a 64-bit register and written as aligned 32-bit words.
-// Per step: q = umulhi(4x, M) >> lp with lp = ceil(log2 f), M = ceil(2^(30+lp)/f) (exact for
-// x < 2^30, DESIGN.md "rANS division"; independent of the renormalisation count k),
-// k from three independent compares, x' = (x >> 8k) + cum + (q >> 8k) * (2^P - f).
-// A row with f = 2^21, M = 0, cum = 0 is the identity step; it stands in for every step outside
-// a chunk's live range, so the loop has no per-lane control flow.
-constexpr int kRansThreads = 128;          // chunks per CTA (4 warps)
-constexpr uint32_t kRansSmemRows = 4096;   // 64 KB of table rows in shared memory
-constexpr uint32_t kRansPitch = 33;        // words per staged symbol row
-constexpr uint32_t kRansDeadSymbol = 0xFFFFFFFFu;
+// Inside a chunk, one CTA of two warps works as producer / consumer:
+//   * PRODUCER warp: prefetches symbols several groups ahead (coalesced), gathers their
+//     table rows, derives the three renormalisation thresholds and fills a ring of
+//     32-row stages; it also turns the consumer's per-step record (x before the step,
+//     byte count) into output bytes with a warp scan, 32 steps at a time.
+//     (Warps map to SM sub-partitions by warp index; a CTA carries two producer/consumer
+//     pairs and swaps the roles on odd CTAs so the consumers of an SM spread over all four
+//     schedulers.)
+//   * CONSUMER warp: the serial chain only. Per symbol: two broadcast LDS.128,
+//     q = ((umulhi(x, M) + c) >> lp) >> 8k with M = ceil(2^(32+lp)/f), lp = ceil(log2 f) - 1
+//     (exact for x < 2^30, DESIGN.md "rANS division"; the multiply does not wait for k),
+//     k from three independent compares and a two-level select,
+//     x' = (x >> 8k) + cum + q * (2^P - f), and one STS of (x, k) for the producer.
+// Stages are handed over with named barriers (bar.arrive / bar.sync), one pair per stage.
+constexpr int kRansStages = 3;        // 2 pairs x (3 FULL + 3 EMPTY + 1 END) named barriers = 14 of the 15 available
+constexpr int kRansLookahead = 3;      // groups of symbols in flight in the producer's registers
 // steps per chunk / speculative warm-up steps (multiples of 32) / parallel relaxation rounds before
-// the fix-up. Defaults tuned on B200 (profiles/); DXO_RANS_CHUNK, DXO_RANS_WARMUP and
+// the sequential fix-up. Defaults tuned on B200 (profiles/); DXO_RANS_CHUNK, DXO_RANS_WARMUP and
 // DXO_RANS_ROUNDS override them for experiments. Correctness never depends on these values.
 struct RansPlan { uint32_t chunk, warmup; int rounds; };
 static RansPlan rans_plan() {
   static RansPlan plan = [] {
-    RansPlan p{256, 2048, 4};
+    RansPlan p{8192, 16384, 3};
     if (const char* e = getenv("DXO_RANS_CHUNK")) p.chunk = (uint32_t)atoi(e);
     if (const char* e = getenv("DXO_RANS_WARMUP")) p.warmup = (uint32_t)atoi(e);
     if (const char* e = getenv("DXO_RANS_ROUNDS")) p.rounds = atoi(e);
@@ -1008,353 +1010,290 @@ static RansPlan rans_plan() {
   return plan;
 }
 
-// chunk state arrays (device scratch): start[J] = entering state each chunk was last encoded from,
-// exit_a / exit_b[J] = exit states (double-buffered across rounds), nbytes[J], offset[J].
-struct RansChunkState { uint32_t* start; uint32_t* exit_a; uint32_t* exit_b; uint32_t* nbytes; uint32_t* offset; };
+// stage row: a = {thr1, thr2, thr3, cum}, b = {M, lp, g = 2^P - f, c = (f == 1)}
 
-__host__ __device__ __forceinline__ uint64_t rans_chunk_capacity(uint32_t chunk) { return 3ull * chunk + 8; }  // multiple of 4
+__device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
-struct RansLane {
-  uint32_t x;               // coder state
-  unsigned long long acc;   // pending output bytes (little end first)
-  uint32_t fill8;           // bits in acc (< 32 between steps)
-  uint8_t* out;             // next aligned word of this chunk's byte string
+struct RansShared {
+  uint4 rows_a[kRansStages][32];
+  uint4 rows_b[kRansStages][32];
+  uint32_t xk[kRansStages][32];
+  uint32_t x_main, x_exit, nbytes, err;
 };
 
-template <bool EMIT>
-__device__ __forceinline__ void rans_step(RansLane& L, const uint4 r, uint32_t two_p) {
-  const uint32_t x = L.x;
-  const uint32_t thr = r.x << 10;
-  const uint32_t q0 = __umulhi(x << 2, r.z) >> r.w;  // floor(x / f)
-  const bool p1 = x >= thr, p2 = (x >> 8) >= thr, p3 = (x >> 16) >= thr;
-  const uint32_t k8 = p2 ? (p3 ? 24u : 16u) : (p1 ? 8u : 0u);
-  if (EMIT) {
-    L.acc |= (unsigned long long)(x & ((1u << k8) - 1u)) << L.fill8;
-    L.fill8 += k8;
-    if (L.fill8 >= 32) {
-      *reinterpret_cast<uint32_t*>(L.out) = (uint32_t)L.acc;
-      L.out += 4; L.acc >>= 32; L.fill8 -= 32;
-    }
-  }
-  L.x = (q0 >> k8) * (two_p - r.x) + ((x >> k8) + r.y);
-}
-
-// 32 steps of every lane; `mine` = this lane's staged symbols, rows = table (index K = identity row)
-template <bool EMIT, bool SMEM>
-__device__ __forceinline__ void rans_group(RansLane& L, const uint32_t* mine, const uint4* __restrict__ rows, uint32_t K, uint32_t two_p) {
-  uint32_t s[32];
-  uint4 r[32];
-  auto row = [&](uint32_t sym) -> uint4 { const uint32_t i = min(sym, K); return SMEM ? rows[i] : __ldg(rows + i); };
-#pragma unroll
-  for (int t = 0; t < 4; ++t) s[t] = mine[t];
-  r[0] = row(s[0]); r[1] = row(s[1]);
-#pragma unroll
-  for (int t = 0; t < 32; ++t) {
-    if (t + 4 < 32) s[t + 4] = mine[t + 4];
-    if (t + 2 < 32) r[t + 2] = row(s[t + 2]);
-    rans_step<EMIT>(L, r[t], two_p);
-  }
-}
-
-// Runs `groups` groups of 32 steps for the 32 chunks j0 .. j0+31 of the calling warp (lane l = chunk j0 + l).
-// Chunk j covers steps [j*C, (j+1)*C) of the stream (step e codes symbols[n - 1 - e]); the run starts
-// `warm` steps before the chunk and emits bytes from the chunk start on. Lanes outside `active`, steps
-// before 0 and steps >= n are identity steps. Returns the state at the chunk start in x_main.
-template <bool SMEM>
-__device__ __forceinline__ void rans_run_warp(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ rows, uint32_t K,
-                                              uint32_t P, unsigned long long j0, uint32_t C, uint32_t warm, uint32_t active, uint32_t* stage,
-                                              RansLane& L, uint32_t& x_main) {
+// Encodes steps [e_begin, e_end) of the stream (step e codes symbols[n - 1 - e]) starting
+// from state x_in; bytes are produced only for steps >= e_main (e_begin..e_main is the
+// warm-up). All three bounds except e_end are multiples of 32. Called by a 64-thread CTA.
+// Results in sh.x_main (state at e_main), sh.x_exit, sh.nbytes after the final barrier.
+__device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t* __restrict__ symbols, unsigned long long n,
+                                                  const uint4* __restrict__ table, uint32_t K, uint32_t P, unsigned long long e_begin,
+                                                  unsigned long long e_main, unsigned long long e_end, uint32_t x_in, uint8_t* __restrict__ out,
+                                                  int bar_base, bool is_consumer) {
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t two_p = 1u << P;
-  const uint32_t groups = (warm + C) / 32, g_main = warm / 32;
-  const long long e_first = (long long)(j0 * C) - (long long)warm + lane;  // lane's step inside chunk row 0, group 0
-  uint32_t nxt[32];
-  auto load_group = [&](uint32_t g) {
+  const unsigned long long steps = e_end - e_begin;
+  const unsigned long long ngroups = (steps + 31) / 32;
+  const unsigned long long g_main = (e_main - e_begin) / 32;  // first group that produces bytes
+  // barrier ids: bar_base + s = FULL[s], bar_base + kRansStages + s = EMPTY[s], bar_base + 2 * kRansStages = END
+  if (is_consumer) {
+    // ------------------------------- consumer: the serial chain -------------------------------
+    uint32_t x = x_in;
+    for (unsigned long long g = 0; g < ngroups; ++g) {
+      const int s = (int)(g % kRansStages);
+      const uint32_t cnt = (g + 1 == ngroups) ? (uint32_t)(steps - 32 * g) : 32u;
+      if (g == g_main && lane == 0) sh.x_main = x;
+      named_bar_sync(bar_base + s);
+      const uint32_t ra = (uint32_t)__cvta_generic_to_shared(&sh.rows_a[s][0]);
+      const uint32_t rb = (uint32_t)__cvta_generic_to_shared(&sh.rows_b[s][0]);
+      uint32_t* xk = sh.xk[s];
+      // Rows are fetched three steps ahead with volatile shared loads so that the ~30-cycle
+      // LDS latency never sits on the x -> x' chain.
+      auto load_row = [&](uint32_t j, uint4& a, uint4& b) {
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(ra + j * 16u));
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(rb + j * 16u));
+      };
+      auto step = [&](uint32_t j, const uint4& a, const uint4& b) {
+        const uint32_t hi = __umulhi(x, b.x) + b.w;                     // floor(x * M / 2^32) (+1 for f = 1), independent of k
+        const uint32_t q0 = hi >> b.y;                                  // floor(x / f): still independent of k
+        const bool p1 = x >= a.x, p2 = x >= a.y, p3 = x >= a.z;
+        const uint32_t k8 = p2 ? (p3 ? 24u : 16u) : (p1 ? 8u : 0u);
+        if (lane == 0) xk[j] = x + (k8 << 27);                          // x < 2^30; k8/8 in bits 30..31
+        x = (q0 >> k8) * b.z + ((x >> k8) + a.w);
+      };
+      if (cnt == 32) {
+        uint4 a0, a1, a2, a3; uint4 b0, b1, b2, b3;
+        load_row(0, a0, b0); load_row(1, a1, b1); load_row(2, a2, b2);
 #pragma unroll
-    for (int l = 0; l < 32; ++l) {
-      const unsigned long long e = (unsigned long long)(e_first + (long long)l * C + 32ll * g);  // negative -> huge -> not live
-      nxt[l] = ((active >> l) & 1u) && e < n ? __ldcs(symbols + (n - 1 - e)) : kRansDeadSymbol;
+        for (uint32_t j = 0; j < 32; ++j) {
+          if (j + 3 < 32) load_row(j + 3, a3, b3);
+          step(j, a0, b0);
+          a0 = a1; b0 = b1; a1 = a2; b1 = b2; a2 = a3; b2 = b3;
+        }
+      } else {
+        for (uint32_t j = 0; j < cnt; ++j) { uint4 a, b; load_row(j, a, b); step(j, a, b); }
+      }
+      named_bar_arrive(bar_base + kRansStages + s);
     }
-  };
-  auto park_group = [&]() {
+    if (lane == 0) { sh.x_exit = x; if (g_main >= ngroups) sh.x_main = x; }
+  } else {
+    // ------------------------------- producer / byte writer -----------------------------------
+    uint32_t err = 0;
+    uint32_t pos = 0;
+    uint32_t pre[kRansLookahead];
+    auto load_syms = [&](unsigned long long g) -> uint32_t {
+      if (g >= ngroups) return 0;
+      const unsigned long long e = e_begin + 32 * g + lane;  // this lane's step
+      return e < e_end ? __ldcs(symbols + (n - 1 - e)) : 0u;
+    };
 #pragma unroll
-    for (int l = 0; l < 32; ++l) stage[l * kRansPitch + lane] = nxt[l];
-  };
-  load_group(0);
-  park_group();
-  __syncwarp();
-  const uint32_t* mine = stage + lane * kRansPitch;
-  for (uint32_t g = 0; g < groups; ++g) {
-    if (g + 1 < groups) load_group(g + 1);
-    if (g == g_main) x_main = L.x;
-    if (g < g_main) rans_group<false, SMEM>(L, mine, rows, K, two_p);
-    else rans_group<true, SMEM>(L, mine, rows, K, two_p);
-    __syncwarp();
-    if (g + 1 < groups) { park_group(); __syncwarp(); }
+    for (int d = 0; d < kRansLookahead; ++d) pre[d] = load_syms(d);
+    auto emit_bytes = [&](int s, uint32_t cnt) {
+      const uint32_t v = lane < cnt ? sh.xk[s][lane] : 0u;
+      const uint32_t k = v >> 30, xv = v & 0x3FFFFFFFu;
+      uint32_t inc = k;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= (uint32_t)d) inc += o; }
+      uint8_t* dst = out + pos + (inc - k);
+      if (k > 0) dst[0] = (uint8_t)xv;
+      if (k > 1) dst[1] = (uint8_t)(xv >> 8);
+      if (k > 2) dst[2] = (uint8_t)(xv >> 16);
+      pos += __shfl_sync(0xFFFFFFFFu, inc, 31);
+    };
+    for (unsigned long long g = 0; g < ngroups; ++g) {
+      const int s = (int)(g % kRansStages);
+      if (g >= kRansStages) {  // the stage is being reused: wait until the consumer is done with it, then write its bytes
+        named_bar_sync(bar_base + kRansStages + s);
+        if (g - kRansStages >= g_main) emit_bytes(s, 32);
+      }
+      const uint32_t sym = pre[0];
+#pragma unroll
+      for (int d = 0; d + 1 < kRansLookahead; ++d) pre[d] = pre[d + 1];
+      pre[kRansLookahead - 1] = load_syms(g + kRansLookahead);
+      const uint32_t cnt = (g + 1 == ngroups) ? (uint32_t)(steps - 32 * g) : 32u;
+      uint4 e = make_uint4(1, 0, 0xFFFFFFFFu, 0);
+      if (lane < cnt) {
+        if (sym < K) e = __ldg(table + sym); else err |= kErrRansFreq;
+        if (e.x == 0) { err |= kErrRansFreq; e = make_uint4(1, 0, 0xFFFFFFFFu, 0); }
+      }
+      const uint32_t thr1 = e.x << 10;  // f <= 2^20: fits; x < 2^30 never reaches the threshold of f = 2^20
+      uint4 a;
+      a.x = thr1;
+      a.y = thr1 >= (1u << 24) ? 0xFFFFFFFFu : (thr1 << 8);   // x >> 8 >= thr1  <=>  x >= thr1 << 8
+      a.z = thr1 >= (1u << 16) ? 0xFFFFFFFFu : (thr1 << 16);
+      a.w = e.y;
+      const uint4 b = make_uint4(e.z, e.w, (1u << P) - e.x, e.x == 1u ? 1u : 0u);  // {M, lp, g, c}
+      sh.rows_a[s][lane] = a;
+      sh.rows_b[s][lane] = b;
+      named_bar_arrive(bar_base + s);
+    }
+    // drain: bytes of the last min(ngroups, kRansStages) groups, in order
+    const unsigned long long first_pending = ngroups > (unsigned long long)kRansStages ? ngroups - kRansStages : 0;
+    for (unsigned long long g = first_pending; g < ngroups; ++g) {
+      const int s = (int)(g % kRansStages);
+      const uint32_t cnt = (g + 1 == ngroups) ? (uint32_t)(steps - 32 * g) : 32u;
+      named_bar_sync(bar_base + kRansStages + s);
+      if (g >= g_main) emit_bytes(s, cnt);
+    }
+    err = __reduce_or_sync(0xFFFFFFFFu, err);
+    if (lane == 0) { sh.nbytes = pos; sh.err = err; }
   }
+  named_bar_sync(bar_base + 2 * kRansStages);  // both warps of the pair: results in sh are visible
 }
 
-// bytes still in the accumulator -> memory; returns the chunk's byte count
-__device__ __forceinline__ uint32_t rans_lane_finish(RansLane& L, const uint8_t* out_begin) {
-  uint32_t nb = (uint32_t)(L.out - out_begin);
-  for (uint32_t b = 0; b < L.fill8; b += 8) { L.out[b >> 3] = (uint8_t)(L.acc >> b); ++nb; }
-  return nb;
+// role / pair of the calling warp inside a 128-thread CTA (two pairs); odd CTAs swap roles
+struct RansRole { int pair; int bar_base; bool is_consumer; };
+__device__ __forceinline__ RansRole rans_role() {
+  const int warp = threadIdx.x >> 5;
+  RansRole r;
+  r.pair = warp >> 1;
+  r.bar_base = 1 + r.pair * (2 * kRansStages + 1);
+  r.is_consumer = (warp & 1) == (int)(blockIdx.x & 1);
+  return r;
 }
 
-// CTA prologue: table rows (plus the identity row at index K) into shared memory when they fit
-template <bool SMEM>
-__device__ __forceinline__ const uint4* rans_rows(const uint4* __restrict__ table, uint32_t K, uint4* smem_rows) {
-  if (!SMEM) return table;
-  for (uint32_t i = threadIdx.x; i <= K; i += blockDim.x) smem_rows[i] = __ldg(table + i);
-  __syncthreads();
-  return smem_rows;
-}
-template <bool SMEM>
-__device__ __forceinline__ uint32_t* rans_stage(uint4* smem, uint32_t K) {
-  uint32_t* base = reinterpret_cast<uint32_t*>(smem + (SMEM ? K + 1 : 0));
-  return base + (threadIdx.x >> 5) * (32 * kRansPitch);
-}
-static size_t rans_smem_bytes(uint32_t rows, int warps) { return (size_t)rows * 16 + (size_t)warps * 32 * kRansPitch * 4; }
+// chunk state arrays (device scratch): start[J] = entering state each chunk was last encoded from,
+// exit_a / exit_b[J] = exit states (double-buffered across rounds), nbytes[J].
+struct RansChunkState { uint32_t* start; uint32_t* exit_a; uint32_t* exit_b; uint32_t* nbytes; };
 
-// round 0: speculative encode of every chunk
-template <bool SMEM>
-__device__ __forceinline__ void rans_speculate_body(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                    uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t C, uint32_t W,
-                                                    uint32_t P, uint32_t K) {
-  extern __shared__ uint4 rans_smem[];
-  const uint4* rows = rans_rows<SMEM>(table, K, rans_smem);
-  uint32_t* stage = rans_stage<SMEM>(rans_smem, K);
-  const unsigned long long j = (unsigned long long)blockIdx.x * kRansThreads + threadIdx.x;
-  const unsigned long long j0 = j - (threadIdx.x & 31);
-  if (j0 >= num_chunks) return;
-  uint8_t* out = scratch + j * rans_chunk_capacity(C);
-  RansLane L{4u << P, 0ull, 0u, out};
-  uint32_t x_main = 4u << P;
-  rans_run_warp<SMEM>(symbols, n, rows, K, P, j0, C, W, 0xFFFFFFFFu, stage, L, x_main);
-  if (j < num_chunks) {
-    cs.start[j] = x_main;
-    cs.exit_a[j] = L.x;
-    cs.nbytes[j] = rans_lane_finish(L, out);
-  }
-}
-// smem_rows = table rows the launch reserved shared memory for; larger alphabets read the table through L1
-__global__ void __launch_bounds__(kRansThreads) rans_speculate_kernel(const uint32_t* __restrict__ symbols, unsigned long long n,
-                                                                      const uint4* __restrict__ table, uint8_t* __restrict__ scratch, RansChunkState cs,
-                                                                      uint32_t num_chunks, uint32_t C, uint32_t W, uint32_t smem_rows, AttrStats* stats) {
+__host__ __device__ __forceinline__ uint64_t rans_chunk_capacity(uint32_t chunk) { return 3ull * chunk + 8; }
+
+// round 0: speculative encode of every chunk (two chunks per CTA)
+__global__ void __launch_bounds__(128) rans_speculate_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                             uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, uint32_t kRansWarmup, AttrStats* stats) {
+  __shared__ RansShared sh2[2];
   if (stats->error_flags) return;
+  const RansRole role = rans_role();
+  const unsigned long long j = 2ull * blockIdx.x + role.pair;
+  if (j >= num_chunks) return;  // both warps of the pair leave together
+  RansShared& sh = sh2[role.pair];
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
-  if (K < smem_rows) rans_speculate_body<true>(symbols, n, table, scratch, cs, num_chunks, C, W, P, K);
-  else rans_speculate_body<false>(symbols, n, table, scratch, cs, num_chunks, C, W, P, K);
+  const unsigned long long e_main = j * kRansChunk;
+  const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
+  const unsigned long long e_begin = e_main > kRansWarmup ? e_main - kRansWarmup : 0;  // warm-up from step 0 is exact
+  const uint32_t l_base = 4u << P;
+  rans_encode_range(sh, symbols, n, table, K, P, e_begin, e_main, e_end, l_base, scratch + j * rans_chunk_capacity(kRansChunk), role.bar_base, role.is_consumer);
+  if (role.is_consumer && (threadIdx.x & 31) == 0) {
+    cs.start[j] = sh.x_main;
+    cs.exit_a[j] = sh.x_exit;
+    cs.nbytes[j] = sh.nbytes;
+    if (sh.err) atomicOr(&stats->error_flags, sh.err);
+  }
 }
 
 // round r >= 1: re-encode the chunks whose entering state does not match the predecessor's exit
-template <bool SMEM>
-__device__ __forceinline__ void rans_relax_body(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                uint8_t* __restrict__ scratch, RansChunkState cs, const uint32_t* __restrict__ exit_cur,
-                                                uint32_t* __restrict__ exit_next, uint32_t num_chunks, uint32_t C, int last_round, uint32_t P, uint32_t K,
-                                                AttrStats* stats) {
-  extern __shared__ uint4 rans_smem[];
-  const unsigned long long j = (unsigned long long)blockIdx.x * kRansThreads + threadIdx.x;
-  const uint32_t in = j == 0 ? (4u << P) : (j < num_chunks ? exit_cur[j - 1] : 0u);
-  const bool need = j < num_chunks && in != cs.start[j];
-  if (!__syncthreads_or(need)) {  // nothing to do in this CTA: carry the exit states over
-    if (j < num_chunks) exit_next[j] = exit_cur[j];
-    return;
-  }
-  const uint4* rows = rans_rows<SMEM>(table, K, rans_smem);
-  uint32_t* stage = rans_stage<SMEM>(rans_smem, K);
-  const uint32_t active = __ballot_sync(0xFFFFFFFFu, need);
-  if (active == 0) {
-    if (j < num_chunks) exit_next[j] = exit_cur[j];
-    return;
-  }
-  uint8_t* out = scratch + j * rans_chunk_capacity(C);
-  RansLane L{in, 0ull, 0u, out};
-  uint32_t x_main = in;
-  rans_run_warp<SMEM>(symbols, n, rows, K, P, j - (threadIdx.x & 31), C, 0, active, stage, L, x_main);
-  if (need) {
-    cs.start[j] = in;
-    exit_next[j] = L.x;
-    cs.nbytes[j] = rans_lane_finish(L, out);
-  } else if (j < num_chunks) {
-    exit_next[j] = exit_cur[j];
-  }
-  const uint32_t cnt = __popc(active);
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&stats->pad[0], cnt);               // chunks re-encoded in relaxation rounds
-    if (last_round) atomicAdd(&stats->pad[2], cnt);  // ... in the last one: zero proves the chain
-  }
-}
-__global__ void __launch_bounds__(kRansThreads) rans_relax_kernel(const uint32_t* __restrict__ symbols, unsigned long long n,
-                                                                  const uint4* __restrict__ table, uint8_t* __restrict__ scratch, RansChunkState cs,
-                                                                  const uint32_t* __restrict__ exit_cur, uint32_t* __restrict__ exit_next,
-                                                                  uint32_t num_chunks, uint32_t C, int last_round, uint32_t smem_rows, AttrStats* stats) {
+__global__ void __launch_bounds__(128) rans_relax_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                         uint8_t* __restrict__ scratch, RansChunkState cs, const uint32_t* __restrict__ exit_cur,
+                                                         uint32_t* __restrict__ exit_next, uint32_t num_chunks, uint32_t kRansChunk, AttrStats* stats) {
+  __shared__ RansShared sh2[2];
   if (stats->error_flags) return;
+  const RansRole role = rans_role();
+  const unsigned long long j = 2ull * blockIdx.x + role.pair;
+  if (j >= num_chunks) return;
+  RansShared& sh = sh2[role.pair];
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
-  if (K < smem_rows) rans_relax_body<true>(symbols, n, table, scratch, cs, exit_cur, exit_next, num_chunks, C, last_round, P, K, stats);
-  else rans_relax_body<false>(symbols, n, table, scratch, cs, exit_cur, exit_next, num_chunks, C, last_round, P, K, stats);
-}
-
-// Fix-up + offsets (one CTA). If the chain is not proven consistent, mismatching chunks are re-encoded
-// in stream order (first mismatch found by a parallel scan, its successors checked directly). Then the
-// exclusive prefix sum of the chunk byte counts.
-constexpr int kRansFixThreads = 1024;
-template <bool SMEM>
-__device__ __forceinline__ void rans_fixup_body(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t* __restrict__ exit_final, uint32_t num_chunks,
-                                                uint32_t C, uint32_t P, uint32_t K, AttrStats* stats) {
-  extern __shared__ uint4 rans_smem[];
-  __shared__ uint32_t s_first;
   const uint32_t l_base = 4u << P;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  {
-    const uint4* rows = rans_rows<SMEM>(table, K, rans_smem);
-    uint32_t* stage = rans_stage<SMEM>(rans_smem, K);  // warp 0's slot is the one used
-    uint32_t from = 0;
-    for (;;) {
-      // first chunk >= from whose entering state is not its predecessor's exit
-      if (threadIdx.x == 0) s_first = 0xFFFFFFFFu;
-      __syncthreads();
-      uint32_t first = 0xFFFFFFFFu;
-      for (uint32_t j = from + threadIdx.x; j < num_chunks && first == 0xFFFFFFFFu; j += kRansFixThreads) {
-        const uint32_t in = j == 0 ? l_base : exit_final[j - 1];
-        if (in != cs.start[j]) first = j;
-      }
-      if (first != 0xFFFFFFFFu) atomicMin(&s_first, first);
-      __syncthreads();
-      uint32_t j = s_first;
-      __syncthreads();
-      if (j == 0xFFFFFFFFu) break;
-      // re-encode j, then its successors for as long as they stop matching (warp 0, chunk in lane 0)
-      if (warp == 0) {
-        for (; j < num_chunks; ++j) {
-          const uint32_t in = j == 0 ? l_base : exit_final[j - 1];
-          if (in == cs.start[j]) break;
-          uint8_t* out = scratch + (unsigned long long)j * rans_chunk_capacity(C);
-          RansLane L{in, 0ull, 0u, out};
-          uint32_t x_main = in;
-          rans_run_warp<SMEM>(symbols, n, rows, K, P, j, C, 0, 1u, stage, L, x_main);
-          if (lane == 0) {
-            cs.start[j] = in;
-            exit_final[j] = L.x;
-            cs.nbytes[j] = rans_lane_finish(L, out);
-            stats->pad[1] += 1;  // chunks re-encoded by the sequential fix-up
-          }
-          __syncwarp();
-          __threadfence_block();
-        }
-        if (lane == 0) s_first = j;
-      }
-      __syncthreads();
-      from = s_first;
-      __syncthreads();
-      if (from >= num_chunks) break;
-    }
+  const uint32_t in = j == 0 ? l_base : exit_cur[j - 1];
+  if (in == cs.start[j]) { if (role.is_consumer && (threadIdx.x & 31) == 0) exit_next[j] = exit_cur[j]; return; }  // pair-uniform
+  const unsigned long long e_main = j * kRansChunk;
+  const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
+  rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, in, scratch + j * rans_chunk_capacity(kRansChunk), role.bar_base, role.is_consumer);
+  if (role.is_consumer && (threadIdx.x & 31) == 0) {
+    cs.start[j] = in;
+    exit_next[j] = sh.x_exit;
+    cs.nbytes[j] = sh.nbytes;
+    atomicAdd(&stats->pad[0], 1u);  // chunks re-encoded in relaxation rounds
+    if (sh.err) atomicOr(&stats->error_flags, sh.err);
   }
 }
-__global__ void __launch_bounds__(kRansFixThreads) rans_fixup_kernel(const uint32_t* __restrict__ symbols, unsigned long long n,
-                                                                     const uint4* __restrict__ table, uint8_t* __restrict__ scratch, RansChunkState cs,
-                                                                     uint32_t* __restrict__ exit_final, uint32_t num_chunks, uint32_t C, int must_scan,
-                                                                     uint32_t smem_rows, AttrStats* stats) {
-  __shared__ uint32_t s_total, s_warp[32];
+
+// sequential fix-up (one CTA of one pair): guarantees exactness whatever the speculation did
+__global__ void __launch_bounds__(64) rans_fixup_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                        uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t* __restrict__ exit_final,
+                                                        uint32_t num_chunks, uint32_t kRansChunk, AttrStats* stats) {
+  __shared__ RansShared sh;
+  __shared__ uint32_t s_in;
   if (stats->error_flags) return;
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (num_chunks > 1 && (must_scan || stats->pad[2] != 0)) {
-    if (K < smem_rows) rans_fixup_body<true>(symbols, n, table, scratch, cs, exit_final, num_chunks, C, P, K, stats);
-    else rans_fixup_body<false>(symbols, n, table, scratch, cs, exit_final, num_chunks, C, P, K, stats);
+  const uint32_t l_base = 4u << P;
+  const bool is_consumer = threadIdx.x < 32;
+  for (uint32_t j = 0; j < num_chunks; ++j) {
+    if (threadIdx.x == 0) s_in = j == 0 ? l_base : exit_final[j - 1];
     __syncthreads();
-  }
-  // exclusive prefix sum of nbytes -> offset (sequential over tiles of kRansFixThreads chunks)
-  uint32_t carry = 0;
-  for (uint32_t base = 0; base < num_chunks; base += kRansFixThreads) {
-    const uint32_t j = base + threadIdx.x;
-    const uint32_t v = j < num_chunks ? cs.nbytes[j] : 0u;
-    uint32_t inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= (uint32_t)d) inc += o; }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = s_warp[lane], winc = w;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, winc, d); if (lane >= (uint32_t)d) winc += o; }
-      s_warp[lane] = winc - w;  // exclusive
-      if (lane == 31) s_total = winc;  // tile total
+    const uint32_t in = s_in;
+    __syncthreads();                  // s_in is rewritten by thread 0 in the next iteration
+    if (in == cs.start[j]) continue;  // uniform: every thread reads the same values
+    const unsigned long long e_main = (unsigned long long)j * kRansChunk;
+    const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
+    rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, in, scratch + (unsigned long long)j * rans_chunk_capacity(kRansChunk), 1, is_consumer);
+    if (threadIdx.x == 0) {
+      cs.start[j] = in;
+      exit_final[j] = sh.x_exit;
+      cs.nbytes[j] = sh.nbytes;
+      stats->pad[1] += 1;  // chunks re-encoded by the sequential fix-up
+      if (sh.err) atomicOr(&stats->error_flags, sh.err);
     }
-    __syncthreads();
-    if (j < num_chunks) cs.offset[j] = carry + s_warp[warp] + inc - v;
-    carry += s_total;
     __syncthreads();
   }
 }
 
-// gather: chunk j's bytes go to payload[offset[j]]; the last chunk's warp appends the flush bytes
+// gather: chunk j's bytes go to payload[sum_{i<j} nbytes[i]]; the last CTA appends the flush bytes
 __global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restrict__ scratch, RansChunkState cs, const uint32_t* __restrict__ exit_final,
-                                                          uint32_t num_chunks, uint32_t C, uint8_t* __restrict__ out, AttrStats* stats) {
+                                                          uint32_t num_chunks, uint32_t kRansChunk, uint8_t* __restrict__ out, AttrStats* stats) {
+  __shared__ uint32_t s_part[8];
+  __shared__ uint32_t s_off;
   if (stats->error_flags) { if (blockIdx.x == 0 && threadIdx.x == 0) stats->payload_bytes = 0; return; }
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
-  for (uint32_t j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < num_chunks; j += warps) {
-    const uint32_t off = cs.offset[j], nb = cs.nbytes[j];
-    const uint8_t* src = scratch + (unsigned long long)j * rans_chunk_capacity(C);
-    // word copies on the destination's alignment: head bytes, aligned words (source words are aligned), tail bytes
-    for (uint32_t i = lane; i < nb; i += 32) out[off + i] = src[i];
-    if (j + 1 == num_chunks && lane == 0) {
-      uint32_t pos = off + nb, err = 0;
-      const uint32_t l_base = 4u << stats->precision;
-      const uint32_t t = exit_final[j] - l_base;  // flush (:48-68)
-      if (t < (1u << 6)) { out[pos++] = (uint8_t)t; }
-      else if (t < (1u << 14)) { const uint32_t v = 0x4000u + t; out[pos++] = (uint8_t)v; out[pos++] = (uint8_t)(v >> 8); }
-      else if (t < (1u << 22)) { const uint32_t v = 0x800000u + t; out[pos++] = (uint8_t)v; out[pos++] = (uint8_t)(v >> 8); out[pos++] = (uint8_t)(v >> 16); }
-      else if (t < (1u << 30)) { const uint32_t v = 0xC0000000u + t; out[pos++] = (uint8_t)v; out[pos++] = (uint8_t)(v >> 8); out[pos++] = (uint8_t)(v >> 16); out[pos++] = (uint8_t)(v >> 24); }
-      else err |= kErrRansState;
-      stats->payload_bytes = pos;
-      if (err) atomicOr(&stats->error_flags, err);
-    }
+  const uint32_t j = blockIdx.x;
+  uint32_t acc = 0;
+  for (uint32_t i = threadIdx.x; i < j; i += blockDim.x) acc += cs.nbytes[i];
+  acc = __reduce_add_sync(0xFFFFFFFFu, acc);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; ++w) t += s_part[w]; s_off = t; }
+  __syncthreads();
+  const uint32_t off = s_off, nb = cs.nbytes[j];
+  const uint8_t* src = scratch + (unsigned long long)j * rans_chunk_capacity(kRansChunk);
+  for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) out[off + i] = src[i];
+  if (j + 1 == num_chunks && threadIdx.x == 0) {
+    uint32_t pos = off + nb, err = 0;
+    const uint32_t l_base = 4u << stats->precision;
+    const uint32_t t = exit_final[j] - l_base;  // flush (:48-68)
+    if (t < (1u << 6)) { out[pos++] = (uint8_t)t; }
+    else if (t < (1u << 14)) { const uint32_t v = 0x4000u + t; out[pos++] = (uint8_t)v; out[pos++] = (uint8_t)(v >> 8); }
+    else if (t < (1u << 22)) { const uint32_t v = 0x800000u + t; out[pos++] = (uint8_t)v; out[pos++] = (uint8_t)(v >> 8); out[pos++] = (uint8_t)(v >> 16); }
+    else if (t < (1u << 30)) { const uint32_t v = 0xC0000000u + t; out[pos++] = (uint8_t)v; out[pos++] = (uint8_t)(v >> 8); out[pos++] = (uint8_t)(v >> 16); out[pos++] = (uint8_t)(v >> 24); }
+    else err |= kErrRansState;
+    stats->payload_bytes = pos;
+    if (err) atomicOr(&stats->error_flags, err);
   }
 }
 
 uint32_t rans_num_chunks(uint64_t num_symbols) { const uint32_t c = rans_plan().chunk; return (uint32_t)((num_symbols + c - 1) / c); }
 size_t rans_scratch_bytes(uint64_t num_symbols) {
   const size_t J = rans_num_chunks(num_symbols);
-  return J * rans_chunk_capacity(rans_plan().chunk) + 256 + 5 * J * sizeof(uint32_t) + 64;
+  return J * rans_chunk_capacity(rans_plan().chunk) + 256 + 4 * J * sizeof(uint32_t) + 64;
 }
 
-void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, uint32_t table_capacity, void* scratch, uint8_t* payload,
+void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, void* scratch, uint8_t* payload,
                         AttrStats* stats, cudaStream_t s) {
   const RansPlan plan = rans_plan();
   const uint32_t J = rans_num_chunks(num_symbols);
   uint8_t* bytes = (uint8_t*)scratch;
   size_t off = ((size_t)J * rans_chunk_capacity(plan.chunk) + 255) / 256 * 256;
   uint32_t* u = (uint32_t*)(bytes + off);
-  RansChunkState cs{u, u + J, u + 2 * (size_t)J, u + 3 * (size_t)J, u + 4 * (size_t)J};
-  // the alphabet size K is only known on the device; shared memory is reserved for what the capacity allows
-  // and the kernels fall back to reading rows through L1 when K does not fit
-  const uint32_t smem_rows = std::min(table_capacity + 1u, kRansSmemRows + 1u);  // rows incl. the identity row at K
-  const size_t sm_main = rans_smem_bytes(smem_rows, kRansThreads / 32), sm_fix = rans_smem_bytes(smem_rows, 1);
-  static bool attr_done = [] {
-    const int mx = (int)rans_smem_bytes(kRansSmemRows + 1u, kRansThreads / 32);
-    cudaFuncSetAttribute(rans_speculate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(rans_relax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(rans_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    return true;
-  }();
-  (void)attr_done;
-  const uint32_t grid = (J + kRansThreads - 1) / kRansThreads;
-  rans_speculate_kernel<<<grid, kRansThreads, sm_main, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, plan.warmup, smem_rows, stats);
+  RansChunkState cs{u, u + J, u + 2 * (size_t)J, u + 3 * (size_t)J};
+  rans_speculate_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, plan.warmup, stats);
   uint32_t* cur = cs.exit_a;
   uint32_t* nxt = cs.exit_b;
-  const int rounds = J > 1 ? plan.rounds : 0;
-  for (int r = 0; r < rounds; ++r) {
-    rans_relax_kernel<<<grid, kRansThreads, sm_main, s>>>(symbols, num_symbols, rans_table, bytes, cs, cur, nxt, J, plan.chunk, r + 1 == rounds, smem_rows, stats);
-    uint32_t* t = cur; cur = nxt; nxt = t;
+  if (J > 1) {
+    for (int r = 0; r < plan.rounds; ++r) {
+      rans_relax_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, cur, nxt, J, plan.chunk, stats);
+      uint32_t* t = cur; cur = nxt; nxt = t;
+    }
+    rans_fixup_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, cur, J, plan.chunk, stats);
   }
-  rans_fixup_kernel<<<1, kRansFixThreads, sm_fix, s>>>(symbols, num_symbols, rans_table, bytes, cs, cur, J, plan.chunk, rounds == 0, smem_rows, stats);
-  const uint32_t gather_grid = (uint32_t)std::min<uint64_t>((J + 7) / 8, 148u * 8u);
-  rans_gather_kernel<<<gather_grid, 256, 0, s>>>(bytes, cs, cur, J, plan.chunk, payload, stats);
+  rans_gather_kernel<<<J, 256, 0, s>>>(bytes, cs, cur, J, plan.chunk, payload, stats);
 }
-int rans_launch_count(uint64_t num_symbols) { return 3 + (rans_num_chunks(num_symbols) > 1 ? rans_plan().rounds : 0); }
+int rans_launch_count(uint64_t num_symbols) { return rans_num_chunks(num_symbols) > 1 ? 3 + rans_plan().rounds : 2; }
 
 // ---------------------------------------------------------------------------------------
 // K12 — CornerTable::compute_table (corner_table/mod.rs:252-340) for the manifold,
@@ -1417,6 +1356,175 @@ void launch_corner_table_opposites(const uint32_t* corner_vertex, uint64_t num_c
   halfedge_keys_kernel<<<g, kThreads, 0, s>>>(corner_vertex, num_corners, keys_in, vals_in, not_exact_flag);
   cub::DeviceRadixSort::SortPairs(p, cub_bytes, keys_in, keys_out, vals_in, vals_out, (int)num_corners, 0, 64, s);
   halfedge_pair_kernel<<<g, kThreads, 0, s>>>(corner_vertex, num_corners, keys_out, vals_out, opposite, not_exact_flag);
+}
+
+// ---------------------------------------------------------------------------------------
+// K13 — CornerTable::compute_left_most_corners (corner_table/mod.rs:342-416) for meshes whose vertices
+// all have a single fan. The reference walks the corners in order; the first corner of a vertex starts
+// its fan, and left_most[v] is the last corner reached by swinging left before the walk hits a boundary
+// or returns to the start. With one fan per vertex that first corner is the vertex's smallest corner
+// index, so the vertices are independent. A vertex whose fan does not contain all of its corners has a
+// second fan (the reference then splits it): flagged, and the caller runs the sequential pass instead.
+constexpr uint32_t kFanUnusedVertex = 1u, kFanSplitVertex = 2u;
+
+__global__ void __launch_bounds__(kThreads) vertex_first_corner_kernel(const uint32_t* __restrict__ cv, unsigned long long num_corners,
+                                                                       uint32_t* __restrict__ first_corner, uint32_t* __restrict__ valence) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < num_corners; c += stride) {
+    const uint32_t v = __ldcs(cv + c);
+    atomicMin(first_corner + v, (uint32_t)c);
+    atomicAdd(valence + v, 1u);
+  }
+}
+__global__ void __launch_bounds__(kThreads) left_most_kernel(const uint32_t* __restrict__ opposite, const uint32_t* __restrict__ first_corner,
+                                                             const uint32_t* __restrict__ valence, uint32_t num_vertices,
+                                                             uint32_t* __restrict__ left_most, uint32_t* flags) {
+  uint32_t bad = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < num_vertices; v += stride) {
+    const uint32_t n = valence[v], c = first_corner[v];
+    if (n == 0) { bad |= kFanUnusedVertex; left_most[v] = kNoneDev; continue; }
+    uint32_t last = c, count = 1, a = c;
+    bool open = false;
+    for (;;) {  // swing left: opposite(next(a)) -> next
+      const uint32_t o = __ldg(opposite + cnext(a));
+      if (o == kNoneDev) { open = true; break; }
+      a = cnext(o);
+      if (a == c || count > n) break;
+      last = a;
+      ++count;
+    }
+    if (open) {  // the corners to the right of the start belong to the fan as well
+      a = c;
+      for (;;) {
+        const uint32_t o = __ldg(opposite + cprev(a));
+        if (o == kNoneDev || count > n) break;
+        a = cprev(o);
+        ++count;
+      }
+    }
+    if (count != n) bad |= kFanSplitVertex;
+    left_most[v] = last;
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+size_t left_most_scratch_bytes(uint32_t num_vertices) { return 2 * (size_t)num_vertices * sizeof(uint32_t) + 256; }
+void launch_left_most(const uint32_t* corner_vertex, const uint32_t* opposite, uint64_t num_corners, uint32_t num_vertices, void* scratch,
+                      uint32_t* left_most, uint32_t* flags, cudaStream_t s) {
+  uint32_t* first_corner = (uint32_t*)scratch;
+  uint32_t* valence = first_corner + num_vertices;
+  cudaMemsetAsync(first_corner, 0xFF, sizeof(uint32_t) * num_vertices, s);
+  cudaMemsetAsync(valence, 0, sizeof(uint32_t) * num_vertices, s);
+  vertex_first_corner_kernel<<<grid_for(num_corners), kThreads, 0, s>>>(corner_vertex, num_corners, first_corner, valence);
+  left_most_kernel<<<grid_for(num_vertices), kThreads, 0, s>>>(opposite, first_corner, valence, num_vertices, left_most, flags);
+}
+
+// ---------------------------------------------------------------------------------------
+// K14 — AttributeCornerTable::new + recompute_vertices (attribute_corner_table.rs:16-137) on the device.
+// (a) per corner: the edge opposite to it is a seam when it is a mesh boundary or when the attribute values
+//     at its two end points differ between the two faces (symmetric, so each corner decides for itself);
+// (b) per universal vertex, in vertex order: the fan is walked to the right starting at the first corner after a
+//     seam, and every seam crossed opens a new attribute vertex. The ids are consecutive in (vertex, walk) order,
+//     i.e. an exclusive prefix sum of the per-vertex counts — so pass (b) runs twice around a scan.
+constexpr uint32_t kSeamBadPoint = 1u, kSeamClosedFan = 2u;
+
+__global__ void __launch_bounds__(kThreads) seam_flags_kernel(const uint32_t* __restrict__ corner_point, const uint32_t* __restrict__ map,
+                                                              uint32_t num_points, const uint32_t* __restrict__ cv,
+                                                              const uint32_t* __restrict__ opposite, unsigned long long num_corners,
+                                                              uint8_t* __restrict__ seam, uint8_t* __restrict__ vertex_on_seam, uint32_t* flags) {
+  uint32_t bad = 0;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  auto val = [&](uint32_t corner) -> uint32_t {
+    const uint32_t p = __ldg(corner_point + corner);
+    if (p >= num_points) { bad |= kSeamBadPoint; return 0u; }
+    return map ? __ldg(map + p) : p;
+  };
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < num_corners; i += stride) {
+    const uint32_t c = (uint32_t)i;
+    const uint32_t o = __ldg(opposite + c);
+    const uint32_t cn = cnext(c), cp = cprev(c);
+    bool is_seam;
+    if (o == kNoneDev) is_seam = true;  // mesh boundary counts as a seam
+    else {
+      const uint32_t on = cnext(o), op = cprev(o);
+      is_seam = val(cn) != val(op) || val(cp) != val(on);
+    }
+    seam[c] = is_seam ? 1 : 0;
+    if (is_seam) { vertex_on_seam[__ldg(cv + cn)] = 1; vertex_on_seam[__ldg(cv + cp)] = 1; }
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+// first corner of the attribute fan walk of universal vertex v (rotated to just after a seam)
+__device__ __forceinline__ uint32_t seam_walk_start(uint32_t v, const uint32_t* __restrict__ left_most_u, const uint32_t* __restrict__ opposite,
+                                                    const uint8_t* __restrict__ seam, const uint8_t* __restrict__ vertex_on_seam,
+                                                    uint32_t num_corners, uint32_t& bad) {
+  const uint32_t c = __ldg(left_most_u + v);
+  uint32_t first = c;
+  if (vertex_on_seam[v]) {
+    uint32_t guard = num_corners;
+    for (;;) {  // attribute swing left: stops at a seam
+      const uint32_t e = cnext(first);
+      const uint32_t o = seam[e] ? kNoneDev : __ldg(opposite + e);
+      if (o == kNoneDev) break;
+      first = cnext(o);
+      if (first == c || --guard == 0) { bad |= kSeamClosedFan; break; }
+    }
+  }
+  return first;
+}
+
+template <bool ASSIGN>
+__global__ void __launch_bounds__(kThreads) seam_vertices_kernel(const uint32_t* __restrict__ left_most_u, const uint32_t* __restrict__ opposite,
+                                                                 const uint8_t* __restrict__ seam, const uint8_t* __restrict__ vertex_on_seam,
+                                                                 uint32_t num_vertices, uint32_t num_corners, uint32_t* __restrict__ count_or_base,
+                                                                 uint32_t* __restrict__ corner_vertex, uint32_t* __restrict__ left_most_a,
+                                                                 uint32_t* total, uint32_t* flags) {
+  uint32_t bad = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < num_vertices; v += stride) {
+    const uint32_t first = seam_walk_start(v, left_most_u, opposite, seam, vertex_on_seam, num_corners, bad);
+    uint32_t id = ASSIGN ? count_or_base[v] : 0u, n = 1;
+    if (ASSIGN) { corner_vertex[first] = id; left_most_a[id] = first; }
+    uint32_t s = first, guard = num_corners;
+    for (;;) {  // universal swing right
+      const uint32_t o = __ldg(opposite + cprev(s));
+      if (o == kNoneDev) break;
+      s = cprev(o);
+      if (s == first || --guard == 0) break;
+      if (seam[cnext(s)]) {  // crossing a seam starts a new attribute vertex
+        ++n;
+        if (ASSIGN) { ++id; left_most_a[id] = s; }
+      }
+      if (ASSIGN) corner_vertex[s] = id;
+    }
+    if (!ASSIGN) count_or_base[v] = n;
+    else if (v + 1 == num_vertices) *total = count_or_base[v] + n;
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+size_t seam_table_scratch_bytes(uint32_t num_vertices) {
+  size_t cub_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)num_vertices);
+  return (((size_t)num_vertices + 255) / 256) * 256 + 2 * (((size_t)num_vertices * 4 + 255) / 256) * 256 + cub_bytes + 256;
+}
+void launch_seam_table(const uint32_t* corner_point, const uint32_t* map, uint32_t num_points, const uint32_t* cv, const uint32_t* opposite,
+                       const uint32_t* left_most_u, uint64_t num_corners, uint32_t num_vertices, void* scratch, size_t scratch_bytes,
+                       uint8_t* seam, uint32_t* corner_vertex, uint32_t* left_most_a, uint32_t* total, uint32_t* flags, cudaStream_t s) {
+  uint8_t* p = (uint8_t*)scratch;
+  const size_t a = (((size_t)num_vertices + 255) / 256) * 256, b = (((size_t)num_vertices * 4 + 255) / 256) * 256;
+  uint8_t* vertex_on_seam = p; p += a;
+  uint32_t* count = (uint32_t*)p; p += b;
+  uint32_t* base = (uint32_t*)p; p += b;
+  size_t cub_bytes = scratch_bytes - (a + 2 * b);
+  cudaMemsetAsync(vertex_on_seam, 0, num_vertices, s);
+  seam_flags_kernel<<<grid_for(num_corners), kThreads, 0, s>>>(corner_point, map, num_points, cv, opposite, num_corners, seam, vertex_on_seam, flags);
+  const int g = grid_for(num_vertices);
+  seam_vertices_kernel<false><<<g, kThreads, 0, s>>>(left_most_u, opposite, seam, vertex_on_seam, num_vertices, (uint32_t)num_corners, count, nullptr, nullptr, total, flags);
+  cub::DeviceScan::ExclusiveSum(p, cub_bytes, count, base, (int)num_vertices, s);
+  seam_vertices_kernel<true><<<g, kThreads, 0, s>>>(left_most_u, opposite, seam, vertex_on_seam, num_vertices, (uint32_t)num_corners, base, corner_vertex, left_most_a, total, flags);
 }
 
 }  // namespace gpu

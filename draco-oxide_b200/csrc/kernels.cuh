@@ -78,7 +78,7 @@ void launch_predict_delta(const uint32_t* seq, uint32_t n, TableDev t, QuantDev 
 // ---- K8: symbol histogram (symbol_coding.rs:149-157) ----
 void launch_histogram(const uint32_t* symbols, uint64_t num_symbols, uint32_t* hist, uint32_t hist_capacity, AttrStats* stats, cudaStream_t s);
 // ---- K9: probability table normalisation + serialisation + rANS lookup table (rans.rs:146-230) ----
-// rans_table: hist_capacity + 1 entries {freq, cumulative, magic multiplier, shift}; entry [#symbols] is the identity row
+// rans_table entries: {freq, cumulative, magic multiplier, shift}
 void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t total_symbols, uint32_t* work /*3*capacity*/, uint4* rans_table,
                         uint8_t* table_bytes, uint32_t table_bytes_capacity, AttrStats* stats, cudaStream_t s);
 // ---- K10: rANS emission, serial within the stream (rans.rs:33-68) ----
@@ -86,13 +86,29 @@ void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t t
 size_t rans_scratch_bytes(uint64_t num_symbols);
 uint32_t rans_num_chunks(uint64_t num_symbols);
 int rans_launch_count(uint64_t num_symbols);  // kernels launch_rans_encode issues
-void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, uint32_t table_capacity, void* scratch, uint8_t* payload,
+void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, void* scratch, uint8_t* payload,
                         AttrStats* stats, cudaStream_t s);
 // ---- K12: half-edge matching by radix sort (corner_table/mod.rs:252-340, fast path) ----
 // keys/vals/tmp are caller-provided scratch (see corner_table_scratch_bytes).
 size_t corner_table_scratch_bytes(uint64_t num_corners);
 void launch_corner_table_opposites(const uint32_t* corner_vertex, uint64_t num_corners, uint32_t* opposite, uint32_t* not_exact_flag,
                                    void* scratch, size_t scratch_bytes, cudaStream_t s);
+
+// ---- K13: left-most corners (corner_table/mod.rs:342-416, single-fan vertices) ----
+// flags (one word, zeroed by the caller): bit 0 = a vertex id below num_vertices is unused, bit 1 = a vertex has a
+// second fan (the reference splits it; the caller must run the sequential pass).
+size_t left_most_scratch_bytes(uint32_t num_vertices);
+void launch_left_most(const uint32_t* corner_vertex, const uint32_t* opposite, uint64_t num_corners, uint32_t num_vertices, void* scratch,
+                      uint32_t* left_most, uint32_t* flags, cudaStream_t s);
+
+// ---- K14: per-attribute seam table (attribute_corner_table.rs:16-137) from the device-resident universal table ----
+// Outputs: seam[C], corner_vertex[C], left_most_a[<= C] (attribute vertex -> corner), *total = number of attribute
+// vertices. flags (zeroed by the caller): bit 0 = a face references a point outside the attribute, bit 1 = a seam
+// vertex whose fan closes on itself; either sends the caller to the sequential pass (which reports the error).
+size_t seam_table_scratch_bytes(uint32_t num_vertices);
+void launch_seam_table(const uint32_t* corner_point, const uint32_t* map, uint32_t num_points, const uint32_t* cv, const uint32_t* opposite,
+                       const uint32_t* left_most_u, uint64_t num_corners, uint32_t num_vertices, void* scratch, size_t scratch_bytes,
+                       uint8_t* seam, uint32_t* corner_vertex, uint32_t* left_most_a, uint32_t* total, uint32_t* flags, cudaStream_t s);
 
 void init_stats(AttrStats* stats, cudaStream_t s);
 
