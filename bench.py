@@ -38,6 +38,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config2_small"])
+    ap.add_argument("--sessions", type=int, default=3,
+                    help="concurrent resident sessions per GPU for `value` (the batch entry dxo_encode_batch runs 3 workers per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -191,24 +193,68 @@ def main():
     cfg = dxo.Config(device=local_rank)
 
     # ---- device-resident arm ------------------------------------------------------------
-    sess = dxo.Session(mesh, cfg)
-    sess_timing = dxo.last_timing()
-    input_bytes = sess_timing["h2d_bytes"]
-    ref_bytes = sess.run()
-    sess.run_steps(max(args.warmup, 3))
+    # `value`: S sessions (one host thread each, own CUDA streams) encode the resident mesh concurrently, the way the
+    # batch entry keeps a GPU busy: the serial rANS chains and the host-coded side streams of one mesh overlap with
+    # the kernels of the others. A step = one pass of every session; every pass produces the complete Draco stream.
+    S = max(1, args.sessions)
+    sessions, results, errors = [None] * S, [None] * S, []
+    ready, go = threading.Barrier(S + 1), threading.Barrier(S + 1)
+
+    def worker(i):
+        try:
+            torch.cuda.set_device(local_rank)
+            sessions[i] = dxo.Session(mesh, cfg)
+            if i == 0:
+                results[i] = {"timing": dxo.last_timing(), "bytes": sessions[i].run()}
+            sessions[i].run_steps(max(args.warmup, 3))
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+        ready.wait()
+        go.wait()
+        try:
+            if not errors:
+                ms, n = sessions[i].run_steps(args.steps)
+                results[i] = dict(results[i] or {}, ms=ms, launches=n)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(S)]
+    for th in threads:
+        th.start()
+    ready.wait()
+    if errors:
+        go.wait()
+        raise errors[0]
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    ms_total, launches = sess.run_steps(args.steps)
+    go.wait()
+    for th in threads:
+        th.join()
     barrier()
+    if errors:
+        raise errors[0]
+    clocks_a = sampler.stop()
+    input_bytes = results[0]["timing"]["h2d_bytes"]
+    ref_bytes = results[0]["bytes"]
+    ms_total = max(r["ms"] for r in results)        # the sessions start together; the slowest one ends the step loop
+    launches = sum(r["launches"] for r in results)
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    n_launch = torch.tensor([launches], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n_launch, op=dist.ReduceOp.SUM)
     ms_total_max = float(t.item())
-    clocks_a = sampler.stop()
+    launches = int(n_launch.item())
+    for extra in sessions[1:]:
+        extra.close()
+    sess = sessions[0]
+    # one session alone (the latency of one mesh), for reference
+    ms_single, _ = sess.run_steps(args.steps)
 
-    # per-kernel timing (separate profiled steps, CUDA events between launches)
-    dxo.set_profiling(True)
+    # per-kernel timing: separate profiled steps, CUDA events around every launch on its own stream, the three
+    # attributes run one after the other (profiling mode 2) so that each kernel is timed alone
+    dxo.set_profiling(2)
     agg = {}
     prof_steps = 3
     for _ in range(prof_steps):
@@ -261,15 +307,18 @@ def main():
     barrier()
 
     if rank == 0:
-        value = V * world * args.steps / (ms_total_max * 1e-3) / 1e6
+        value = V * world * S * args.steps / (ms_total_max * 1e-3) / 1e6
         line = {
             "metric": METRIC, "value": value, "unit": "Mvertices/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32->i32/u32 (bit-exact integer pipeline)", "data": "synthetic",
-            "config": {"workload": desc, "units_per_step_per_gpu": "1 mesh", "parallelism": f"{world} independent replicas, no collective",
+            "config": {"workload": desc, "units_per_step_per_gpu": f"{S} meshes ({S} concurrent resident sessions of the workload mesh)",
+                       "parallelism": f"{world} independent replicas, no collective",
                        "l2": f"inputs larger than L2: {input_bytes / 1e6:.0f} MB resident per mesh vs 126 MB L2",
                        "stream_bytes": len(ref_bytes)},
             "gpu_launches": int(launches),
+            "single_session": {"value": V * args.steps / (ms_single * 1e-3) / 1e6, "unit": "Mvertices/s", "ms_per_step": ms_single / args.steps,
+                               "note": "one mesh at a time on rank 0: bounded by the serial rANS chains and the host-coded side streams"},
             "clocks": clocks_a,
             "e2e": {"value": V * world * e2e_steps / e2e_s / 1e6, "unit": "Mvertices/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "host_connectivity_ms_per_step": host_ms / e2e_steps, "steps": e2e_steps},

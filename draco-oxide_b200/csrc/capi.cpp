@@ -49,6 +49,7 @@ dxo_config effective_config(const dxo_config* cfg) {
 void run_device_phase(MeshJob& job, DeviceContext& ctx, Profile& prof, std::vector<uint8_t>& bytes, dxo_timing& tm) {
   prof.reset();
   prof.enabled = g_profiling.load() != 0;
+  prof.serial = g_profiling.load() == 2;
   cudaStream_t s0 = ctx.stream[0];
   cuda_check(cudaEventRecord(ctx.ev_begin, s0), "cudaEventRecord");
   for (int k = 1; k < 3; ++k) cuda_check(cudaStreamWaitEvent(ctx.stream[k], ctx.ev_begin, 0), "cudaStreamWaitEvent");
@@ -294,7 +295,7 @@ void dxo_session_destroy(dxo_session* s) {
   delete s;
 }
 
-void dxo_set_profiling(int enabled) { g_profiling.store(enabled ? 1 : 0); }
+void dxo_set_profiling(int mode) { g_profiling.store(mode == 2 ? 2 : (mode ? 1 : 0)); }
 
 int dxo_last_timing(dxo_timing* out) {
   if (!out) return DXO_ERR_INVALID_ARGUMENT;

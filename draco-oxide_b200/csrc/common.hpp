@@ -3,6 +3,8 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <memory>
+#include <utility>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -12,6 +14,20 @@
 namespace dxo {
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+// std::vector whose resize() leaves new elements uninitialised: the big connectivity arrays are
+// filled right after being sized (by a copy from the device or by a pass that writes every entry),
+// so the zero-fill of a plain vector would only add a memory pass.
+template <class T>
+struct NoInitAllocator : std::allocator<T> {
+  template <class U> struct rebind { using other = NoInitAllocator<U>; };
+  template <class U, class... Args> void construct(U* p, Args&&... args) {
+    if constexpr (sizeof...(Args) == 0) ::new ((void*)p) U;
+    else ::new ((void*)p) U(std::forward<Args>(args)...);
+  }
+};
+using U32Array = std::vector<uint32_t, NoInitAllocator<uint32_t>>;
+using U8Array = std::vector<uint8_t, NoInitAllocator<uint8_t>>;
 
 struct Error : std::runtime_error {
   int status;

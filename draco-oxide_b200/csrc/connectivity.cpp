@@ -26,34 +26,34 @@ void UniversalTable::build(const uint32_t* faces, uint32_t nfaces, const AttrVie
     fprintf(stderr, "[dxo]   %-26s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t0).count());
     t0 = n;
   };
-  corner_vertex.resize(num_corners);
-  // vertex ids of the corners, range checks and the largest id; large meshes split the pass over a few threads
-  auto fill_range = [&](uint32_t c0, uint32_t c1) -> uint32_t {
-    uint32_t mx = 0;
-    for (uint32_t c = c0; c < c1; ++c) {
-      const uint32_t p = faces[c];
-      if (p >= pos.num_points) throw Error(DXO_ERR_INVALID_ARGUMENT, "face references a point outside the position attribute");
-      const uint32_t v = pos.value_of(p);
-      if (v >= pos.num_unique) throw Error(DXO_ERR_INVALID_ARGUMENT, "point_to_value entry out of range");
-      corner_vertex[c] = v;
-      mx = std::max(mx, v);
-    }
-    return mx;
-  };
-  uint32_t max_v = 0;
-  if (num_corners >= (1u << 20)) {
+  // vertex ids of the corners with the reference's range checks; large meshes split the passes over a few threads
+  const uint32_t* map = pos.map;
+  auto over_parts = [&](auto&& fn) -> uint32_t {  // max of fn(c0, c1) over the parts
+    if (num_corners < (1u << 20)) return fn(0u, num_corners);
     constexpr uint32_t kParts = 4;
     std::future<uint32_t> parts[kParts];
-    for (uint32_t k = 0; k < kParts; ++k) {
-      const uint32_t c0 = (uint32_t)((uint64_t)num_corners * k / kParts), c1 = (uint32_t)((uint64_t)num_corners * (k + 1) / kParts);
-      parts[k] = std::async(std::launch::async, fill_range, c0, c1);
-    }
-    std::exception_ptr first_error;
-    for (auto& f : parts) { try { max_v = std::max(max_v, f.get()); } catch (...) { if (!first_error) first_error = std::current_exception(); } }
-    if (first_error) std::rethrow_exception(first_error);
-  } else {
-    max_v = fill_range(0, num_corners);
-  }
+    for (uint32_t k = 0; k < kParts; ++k)
+      parts[k] = std::async(std::launch::async, fn, (uint32_t)((uint64_t)num_corners * k / kParts), (uint32_t)((uint64_t)num_corners * (k + 1) / kParts));
+    uint32_t mx = 0;
+    for (auto& f : parts) mx = std::max(mx, f.get());
+    return mx;
+  };
+  corner_vertex.resize(num_corners);
+  uint32_t* cvw = corner_vertex.data();
+  const uint32_t max_p = over_parts([&](uint32_t c0, uint32_t c1) {
+    uint32_t mx = 0;
+    if (map) { for (uint32_t c = c0; c < c1; ++c) mx = std::max(mx, faces[c]); }
+    else { for (uint32_t c = c0; c < c1; ++c) { const uint32_t p = faces[c]; cvw[c] = p; mx = std::max(mx, p); } }
+    return mx;
+  });
+  if (num_corners && max_p >= pos.num_points) throw Error(DXO_ERR_INVALID_ARGUMENT, "face references a point outside the position attribute");
+  uint32_t max_v = max_p;
+  if (map) max_v = over_parts([&](uint32_t c0, uint32_t c1) {
+    uint32_t mx = 0;
+    for (uint32_t c = c0; c < c1; ++c) { const uint32_t v = map[faces[c]]; cvw[c] = v; mx = std::max(mx, v); }
+    return mx;
+  });
+  if (num_corners && max_v >= pos.num_unique) throw Error(DXO_ERR_INVALID_ARGUMENT, "point_to_value entry out of range");
   num_vertices = num_corners ? max_v + 1u : 0u;
   // every vertex id up to the maximum must be used (get_unused_vertices, :236-250; panic :105-108);
   // the device pass (K13) reports this itself when it runs
@@ -568,13 +568,18 @@ std::vector<uint32_t> encode_edgebreaker(const UniversalTable& ut, const std::ve
 // left on the stack here (lazy deletion, identical output).
 std::vector<uint32_t> attribute_sequence(const TableRef& t, const std::vector<uint32_t>& corners_of_edgebreaker) {
   std::vector<uint8_t> vertex_seen(t.num_vertices, 0), face_seen(t.num_faces, 0);
-  std::vector<uint32_t> stack(corners_of_edgebreaker), out;
+  // The reference's stack starts as a copy of the corner list and is popped from the back. Here the list
+  // itself is the (read-only) bottom of the stack, consumed from its end, and only pushed entries are stored.
+  size_t bottom = corners_of_edgebreaker.size();
+  std::vector<uint32_t> stack, out;
+  stack.reserve(1024);
   out.reserve(t.num_vertices);
   const uint32_t* cv = t.corner_vertex;
   auto emit = [&](uint32_t v, uint32_t c) { if (!vertex_seen[v]) { out.push_back(c); vertex_seen[v] = 1; } };
-  while (!stack.empty()) {
-    const uint32_t c = stack.back();
-    stack.pop_back();
+  while (!stack.empty() || bottom) {
+    uint32_t c;
+    if (!stack.empty()) { c = stack.back(); stack.pop_back(); }
+    else c = corners_of_edgebreaker[--bottom];
     const uint32_t face = c / 3u;
     if (face_seen[face]) continue;
     const uint32_t nc = corner_next(c), pc = corner_prev(c);

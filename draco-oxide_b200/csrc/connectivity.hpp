@@ -24,9 +24,9 @@ struct AttrView {
 struct UniversalTable {
   uint32_t num_faces = 0, num_corners = 0, num_vertices = 0;
   const uint32_t* corner_point = nullptr;  // faces, 3 per face (borrowed)
-  std::vector<uint32_t> corner_vertex;     // vertex_idx(c), non-manifold splits applied
-  std::vector<uint32_t> opposite;          // kNone = boundary
-  std::vector<uint32_t> left_most;         // per vertex
+  U32Array corner_vertex;     // vertex_idx(c), non-manifold splits applied
+  U32Array opposite;          // kNone = boundary
+  U32Array left_most;         // per vertex
 
   uint32_t swing_left(uint32_t c) const { uint32_t o = opposite[corner_next(c)]; return o == kNone ? kNone : corner_next(o); }
   uint32_t swing_right(uint32_t c) const { uint32_t o = opposite[corner_prev(c)]; return o == kNone ? kNone : corner_prev(o); }
@@ -52,9 +52,9 @@ struct UniversalTable {
 // Per-attribute seam table — AttributeCornerTable, core/corner_table/attribute_corner_table.rs:4-192.
 struct SeamTable {
   uint32_t num_vertices = 0;
-  std::vector<uint32_t> corner_vertex;  // attribute vertex of each corner
-  std::vector<uint8_t> seam;            // edge opposite to the corner is a seam (or boundary)
-  std::vector<uint32_t> left_most;      // per attribute vertex
+  U32Array corner_vertex;  // attribute vertex of each corner
+  U8Array seam;            // edge opposite to the corner is a seam (or boundary)
+  U32Array left_most;      // per attribute vertex
   void build(const UniversalTable& ut, const AttrView& att);
 };
 

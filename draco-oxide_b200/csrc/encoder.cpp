@@ -42,6 +42,7 @@ DeviceContext& DeviceContext::get(int device) {
   cuda_check(cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking), "cudaStreamCreate");
   cuda_check(cudaEventCreateWithFlags(&c->ev_uploaded, cudaEventDisableTiming), "cudaEventCreate");
   cuda_check(cudaEventCreateWithFlags(&c->ev_inputs, cudaEventDisableTiming), "cudaEventCreate");
+  cuda_check(cudaEventCreateWithFlags(&c->ev_serial, cudaEventDisableTiming), "cudaEventCreate");
   cuda_check(cudaEventCreate(&c->ev_begin), "cudaEventCreate");
   cuda_check(cudaEventCreate(&c->ev_end), "cudaEventCreate");
   cuda_check(cudaEventCreateWithFlags(&c->ev_pos_ready, cudaEventDisableTiming), "cudaEventCreate");
@@ -514,6 +515,7 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     const gpu::TableDev t = table_dev(i);
     const gpu::QuantDev q{d.quant, d.map, p.ncomp_q};
 
+    if (prof.serial && i > 0) cuda_check(cudaStreamWaitEvent(s, ctx.ev_serial, 0), "cudaStreamWaitEvent");
     gpu::init_stats(d.stats, s);
     ++prof.launches;
     cuda_check(cudaMemsetAsync(d.hist, 0, sizeof(uint32_t) * p.hist_capacity, s), "cudaMemsetAsync");
@@ -596,6 +598,7 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     gpu::launch_rans_encode(d.symbols, S, d.rans_table, d.rans_scratch, d.payload, d.stats, s);
     prof.launches += gpu::rans_launch_count(S) - 1;  // speculate + relax rounds + fix-up + gather
     prof.end(s);
+    if (prof.serial) cuda_check(cudaEventRecord(ctx.ev_serial, s), "cudaEventRecord");
   }
   cuda_check(cudaGetLastError(), "kernel launch");
 }

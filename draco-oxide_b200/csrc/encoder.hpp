@@ -22,7 +22,7 @@ struct DeviceContext {
   cudaStream_t stream[3] = {nullptr, nullptr, nullptr};  // attribute i runs on stream[min(i,2)]
   cudaStream_t copy_stream = nullptr;                    // early D2H of the side-stream flags
   cudaStream_t upload_stream = nullptr;                  // H2D issued by helper threads while the host builds the connectivity
-  cudaEvent_t ev_uploaded = nullptr, ev_inputs = nullptr;
+  cudaEvent_t ev_uploaded = nullptr, ev_inputs = nullptr, ev_serial = nullptr;
   // pinned host staging, reused across calls (slot = attribute index * 2 + {0: results, 1: side flags})
   std::vector<std::pair<uint8_t*, size_t>> pinned;
   uint8_t* pinned_buffer(size_t slot, size_t bytes);
@@ -34,6 +34,7 @@ struct KernelRecord { const char* name; uint64_t bytes; cudaEvent_t a, b; };
 
 struct Profile {
   bool enabled = false;
+  bool serial = false;  // profiling mode 2: attributes run one after the other, so each kernel is timed alone
   std::vector<KernelRecord> records;
   std::vector<cudaEvent_t> pool;
   size_t pool_used = 0;

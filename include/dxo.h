@@ -186,8 +186,9 @@ typedef struct dxo_timing {
   dxo_kernel_time kernels[64];
 } dxo_timing;
 
-/* Enables per-kernel event timing (adds event records between launches). */
-void dxo_set_profiling(int enabled);
+/* Per-kernel event timing: 0 = off, 1 = event records between launches (attributes still overlap on their
+ * streams), 2 = as 1 with the attributes run one after the other, so every kernel is timed alone. */
+void dxo_set_profiling(int mode);
 int dxo_last_timing(dxo_timing* out);
 
 /* ---- stage access for parity tests (GPU results, copied back) ----
