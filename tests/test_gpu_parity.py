@@ -208,3 +208,79 @@ def test_encode_symbols_entry(orc, case):
     assert got == orc.encode_symbols(sym)
     dec, used = orc.decode_symbols(got, sym.size)
     assert used == len(got) and np.array_equal(dec, sym)
+
+
+# ---- device connectivity passes (K12 half edges, K13 left-most corners, K14 seam tables): meshes above the
+# 4096-face threshold on which they must hand over to the sequential host passes ---------------------------
+def _points_of(mesh):
+    return [a.values if a.point_to_value is None else a.values[a.point_to_value] for a in mesh.attributes]
+
+
+def _rebuild(mesh, faces, points):
+    atts = [dxo.Attribute.from_points(p, a.att_type, a.domain, a.parents, a.unique_id) for a, p in zip(mesh.attributes, points)]
+    return dxo.Mesh(np.asarray(faces, np.uint32), atts)
+
+
+def test_large_bowtie_vertex_falls_back_to_host_left_most(orc):
+    """Two 50x50 grids welded at one point: that vertex has two fans, the reference splits it
+    (corner_table/mod.rs:342-416). K13 must flag it; left-most corners and seam tables then run on the host."""
+    g = synth.grid_mesh(50, 50, 31)
+    n = g.num_points()
+    pts = _points_of(g)
+    shifted = [p.copy() for p in pts]
+    shifted[0][:, 0] += 3.0
+    faces_b = g.faces.astype(np.int64) + n
+    faces_b[faces_b == n] = n - 1  # B's first point becomes A's last point
+    faces = np.concatenate([g.faces.astype(np.int64), faces_b])
+    m = meshes.drop_unused_points(_rebuild(g, faces, [np.concatenate([a, b]) for a, b in zip(pts, shifted)]))
+    assert m.faces.shape[0] >= 4096
+    assert_stage_parity(orc, m)
+
+
+def test_large_fin_edge_falls_back_to_host_matching(orc):
+    """A third triangle on an interior edge of a 60x60 grid: K12 reports 'not exact' and the sequential matcher,
+    the non-manifold edge split and the host left-most pass decide (corner_table/mod.rs:149-340)."""
+    g = synth.grid_mesh(60, 60, 32)
+    n = g.num_points()
+    pts = _points_of(g)
+    a, b = int(g.faces[2000, 0]), int(g.faces[2000, 1])
+    extra = [np.concatenate([p, p[a:a + 1] * 0.5 + p[b:b + 1] * 0.5 + (0.3 if i == 0 else 0.0)]).astype(p.dtype) for i, p in enumerate(pts)]
+    extra[1][-1] = extra[1][-1] / np.linalg.norm(extra[1][-1])
+    faces = np.concatenate([g.faces.astype(np.int64), [[b, a, n]]])
+    m = _rebuild(g, faces, extra)
+    assert m.faces.shape[0] >= 4096
+    assert gpu_encode(m) == orc.encode(m)
+
+
+def test_large_mesh_with_unused_vertex_is_reported():
+    """get_unused_vertices panics in the reference (corner_table/mod.rs:105-108); K13 reports it for large meshes."""
+    g = synth.grid_mesh(50, 50, 33, with_normals=False, with_uvs=False)
+    v = g.attributes[0].values
+    pos = np.concatenate([v[:100], [[9.0, 9.0, 9.0]], v[100:]]).astype(np.float32)  # point 100 is referenced by no face
+    faces = (g.faces + (g.faces >= 100)).astype(np.uint32)
+    bad = dxo.Mesh(faces, [dxo.Attribute(pos, 0, 0)])
+    with pytest.raises(dxo.Err) as e:
+        gpu_encode(bad)
+    assert e.value.status == -10  # DXO_ERR_UNUSED_VERTICES
+    assert gpu_encode(g)
+
+
+def test_large_grid_with_uv_seam_line(orc):
+    """80x80 grid whose texture coordinates jump along a column (an interior seam that ends inside the mesh on one
+    side): attribute vertices are split along the seam by K14 exactly as recompute_vertices does."""
+    g = synth.grid_mesh(80, 80, 34)
+    pts = _points_of(g)
+    ny = 80
+    corner_uv = pts[2][g.faces.ravel()].copy()            # per-corner uv
+    quad_col = (np.arange(g.faces.shape[0]) // 2) % (ny - 1)
+    quad_row = (np.arange(g.faces.shape[0]) // 2) // (ny - 1)
+    island = np.repeat((quad_col >= 40) & (quad_row < 60), 3)  # faces right of the cut, but only for the first 60 rows
+    corner_uv[island] += np.float32(0.25)
+    # de-index: one point per corner, then weld equal (position, normal, uv) tuples back through from_points
+    faces = np.arange(g.faces.size, dtype=np.uint32).reshape(-1, 3)
+    atts = [dxo.Attribute.from_points(pts[0][g.faces.ravel()], 0, 0),
+            dxo.Attribute.from_points(pts[1][g.faces.ravel()], g.attributes[1].att_type, g.attributes[1].domain, g.attributes[1].parents, g.attributes[1].unique_id),
+            dxo.Attribute.from_points(corner_uv, g.attributes[2].att_type, g.attributes[2].domain, g.attributes[2].parents, g.attributes[2].unique_id)]
+    m = dxo.Mesh(faces, atts)
+    assert m.faces.shape[0] >= 4096
+    assert_stage_parity(orc, m)
