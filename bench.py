@@ -29,6 +29,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "Mvertices/s encoded"
 PEAKS_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+# dram__bytes_read.sum + dram__bytes_write.sum per launch on config 2, from the `ncu --set full` capture summarised in
+# profiles/r1_ncu_full_final_summary.md (bytes)
+NCU_TRAFFIC_CONFIG2 = {"K4_predict_parallelogram": 110.7e6, "K5_predict_normal": 118.8e6, "K6_predict_texcoord": 102.7e6}
 
 
 def parse_args():
@@ -323,7 +326,8 @@ def main():
             "e2e": {"value": V * world * e2e_steps / e2e_s / 1e6, "unit": "Mvertices/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "host_connectivity_ms_per_step": host_ms / e2e_steps, "steps": e2e_steps},
             "roofline": {"bound": "hbm", "kernel": dom["name"], "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": dom["gbs"] / peak if dom["gbs"] else None, "traffic": None, "peak_source": peak_src,
+                         "frac": dom["gbs"] / peak if dom["gbs"] else None,
+                         "traffic": NCU_TRAFFIC_CONFIG2.get(dom["name"]) if args.workload == "config2" else None, "peak_source": peak_src,
                          "note": "dominant HBM-bound attribute kernel; K10 (rANS) is a serial latency-bound loop and is reported under 'rans' (SURVEY.md §8d)"},
             "attribute_kernels": {"algorithmic_bytes_per_step": attr_bytes, "ms_per_step": attr_ms, "gbs": attr_bytes / attr_ms / 1e6 if attr_ms else None,
                                   "frac_of_peak": attr_bytes / attr_ms / 1e6 / peak if attr_ms else None},
