@@ -29,6 +29,59 @@ struct NoInitAllocator : std::allocator<T> {
 using U32Array = std::vector<uint32_t, NoInitAllocator<uint32_t>>;
 using U8Array = std::vector<uint8_t, NoInitAllocator<uint8_t>>;
 
+// Array of the connectivity tables. Normally it owns a no-init vector; with a memory source set it lives in
+// caller-provided memory instead (pinned host blocks, so that the device copies of K12-K14 land in it by DMA
+// and no second host copy is needed). The source outlives the array; growing past the block copies into an
+// owned vector.
+template <class T>
+class HostArray {
+ public:
+  HostArray() = default;
+  HostArray(const HostArray&) = delete;
+  HostArray& operator=(const HostArray&) = delete;
+  HostArray(HostArray&&) = default;             // a moved vector keeps its buffer, so p_ stays valid
+  HostArray& operator=(HostArray&&) = default;
+  using Source = void* (*)(void* user, size_t bytes);  // returns memory for `bytes` bytes or nullptr
+  void set_source(Source fn, void* user) { source_ = fn; source_user_ = user; }
+  T* data() { return p_; }
+  const T* data() const { return p_; }
+  size_t size() const { return n_; }
+  bool empty() const { return n_ == 0; }
+  T& operator[](size_t i) { return p_[i]; }
+  const T& operator[](size_t i) const { return p_[i]; }
+  T* begin() { return p_; }
+  T* end() { return p_ + n_; }
+  const T* begin() const { return p_; }
+  const T* end() const { return p_ + n_; }
+  void resize(size_t n) {  // contents unspecified unless shrinking inside the current storage
+    if (n <= cap_) { n_ = n; return; }
+    if (source_) {
+      if (void* ext = source_(source_user_, n * sizeof(T))) { own_.clear(); p_ = (T*)ext; n_ = cap_ = n; return; }
+    }
+    own_.resize(n);
+    p_ = own_.data(); n_ = cap_ = n;
+  }
+  void assign(size_t n, T v) { resize(n); for (size_t i = 0; i < n; ++i) p_[i] = v; }
+  void clear() { n_ = 0; }
+  void reserve(size_t n) { if (n > cap_) { const size_t keep = n_; grow(n); n_ = keep; } }
+  void push_back(T v) {
+    if (n_ == cap_) grow(cap_ ? cap_ * 2 : 16);
+    p_[n_++] = v;
+  }
+ private:
+  void grow(size_t cap) {  // into an owned vector, keeping the contents
+    std::vector<T, NoInitAllocator<T>> bigger(cap);
+    if (n_) memcpy(bigger.data(), p_, n_ * sizeof(T));
+    own_.swap(bigger);
+    p_ = own_.data(); cap_ = cap;
+  }
+  T* p_ = nullptr;
+  size_t n_ = 0, cap_ = 0;
+  std::vector<T, NoInitAllocator<T>> own_;
+  Source source_ = nullptr;
+  void* source_user_ = nullptr;
+};
+
 struct Error : std::runtime_error {
   int status;
   Error(int st, const std::string& what) : std::runtime_error(what), status(st) {}

@@ -66,13 +66,15 @@ void UniversalTable::build(const uint32_t* faces, uint32_t nfaces, const AttrVie
   lap("vertex ids + checks");
   bool nm = false;
   matched_on_device = false;
+  has_boundary_list = false;
   uint32_t device_done = 0;
   if (matcher) {
     opposite.resize(num_corners);
     left_most.resize(num_vertices);
-    device_done = matcher(matcher_user, corner_vertex.data(), num_faces, num_vertices, opposite.data(), left_most.data());
+    device_done = matcher(matcher_user, corner_vertex.data(), num_faces, num_vertices, opposite.data(), left_most.data(), &boundary_corners);
     if (device_done & kUnusedVertices) throw Error(DXO_ERR_UNUSED_VERTICES, "mesh contains unused vertices");
     matched_on_device = (device_done & kMatchExact) != 0;
+    has_boundary_list = matched_on_device && (device_done & kBoundaryListDone);  // opposite[] is final: no non-manifold split follows
     lap(matched_on_device ? ((device_done & kLeftMostDone) ? "half edges + left-most (K12, K13)" : "half-edge matching (K12)") : "half-edge matching (K12, not exact)");
   }
   if (!(matched_on_device && (device_done & kLeftMostDone))) { check_all_used(); lap("unused-vertex check"); }
@@ -308,16 +310,26 @@ struct SplitEvent { uint64_t merge_symbol, split_symbol; uint8_t right; };
 class EdgebreakerRun {
  public:
   explicit EdgebreakerRun(const UniversalTable& ut) : ut_(ut) {
-    vertex_done_.assign(ut.num_vertices, 0);
+    vstate_.assign(ut.num_vertices, 0);
     face_done_.assign(ut.num_faces, 0);
     split_symbol_of_face_.assign(ut.num_faces, kNone);
   }
 
   // phase 1: the CLERS traversal of every connected component (needs only the universal table)
   void traverse_all() {
+    const bool timing = getenv("DXO_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+      if (!timing) return;
+      auto n = std::chrono::steady_clock::now();
+      fprintf(stderr, "[dxo]     %-24s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t0).count());
+      t0 = n;
+    };
     find_boundaries();
-    symbols_.reserve(ut_.num_faces);
-    visit_order_.reserve(ut_.num_faces);
+    lap("find boundaries");
+    symbols_.resize(ut_.num_faces);      // every face gets exactly one symbol / one visit-order entry
+    visit_order_.resize(ut_.num_faces);
+    num_visited_ = 0;
     for (uint32_t c = 0; c < ut_.num_corners; ++c) {  // one traversal per connected component (:478-511)
       const uint32_t face = c / 3u;
       if (face_done_[face]) continue;
@@ -325,7 +337,7 @@ class EdgebreakerRun {
       const uint32_t start = start_corner(face, interior);
       start_face_interior_.push_back(interior ? 1 : 0);
       if (interior) {
-        vertex_done_[vtx(start)] = vertex_done_[vtx(corner_next(start))] = vertex_done_[vtx(corner_prev(start))] = 1;
+        vstate_[vtx(start)] |= 1; vstate_[vtx(corner_next(start))] |= 1; vstate_[vtx(corner_prev(start))] |= 1;
         face_done_[face] = 1;
         init_face_corners_.push_back(corner_next(start));
         const uint32_t o = ut_.opposite[corner_next(start)];
@@ -336,8 +348,12 @@ class EdgebreakerRun {
         traverse(start);
       }
     }
+    lap("CLERS loop");
+    symbols_.resize(num_visited_);
+    visit_order_.resize(num_visited_);
     corners_.assign(init_face_corners_.rbegin(), init_face_corners_.rend());
     corners_.insert(corners_.end(), visit_order_.begin(), visit_order_.end());
+    lap("corner list");
   }
   const std::vector<uint32_t>& corners_of_edgebreaker() const { return corners_; }
   std::vector<uint32_t> take_corners_of_edgebreaker() { return std::move(corners_); }
@@ -356,11 +372,16 @@ class EdgebreakerRun {
 
  private:
   const UniversalTable& ut_;
-  std::vector<uint8_t> vertex_done_, face_done_, hole_done_, symbols_, start_face_interior_;
-  std::vector<uint32_t> hole_of_vertex_, stack_, visit_order_, init_face_corners_, corners_;
+  // vstate_: bit 0 = vertex visited, bit 1 = vertex lies on a hole (hole_of_vertex_ != kNone);
+  // face_done_: bit 0 = face visited, bit 1 = the face got an S symbol (split_symbol_of_face_ is set)
+  std::vector<uint8_t> vstate_, face_done_, hole_done_, start_face_interior_;
+  std::vector<uint32_t> hole_of_vertex_, stack_, init_face_corners_, corners_;
+  U8Array symbols_;        // sized once, every used entry written by the traversal (no zero-fill)
+  U32Array visit_order_;
   std::vector<uint32_t> split_symbol_of_face_;  // symbol index of the S symbol a face got (< num_faces), kNone otherwise
   std::vector<SplitEvent> split_events_;
   uint64_t symbol_index_ = ~(uint64_t)0;  // usize::MAX, incremented with wrap before use (:150,:276)
+  size_t num_visited_ = 0;                // entries of symbols_ / visit_order_ in use
   uint64_t num_splits_ = 0;
 
   uint32_t vtx(uint32_t c) const { return ut_.corner_vertex[c]; }
@@ -371,19 +392,25 @@ class EdgebreakerRun {
   // (not through the opposite corner), so in practice each boundary edge opens a new hole id.
   void find_boundaries() {
     hole_of_vertex_.assign(ut_.num_vertices, kNone);
-    for (uint32_t c0 = 0; c0 < ut_.num_corners; ++c0) {
-      if (ut_.opposite[c0] != kNone) continue;
+    auto open_hole = [&](uint32_t c0) {
       uint32_t v = vtx(corner_next(c0));
-      if (hole_of_vertex_[v] != kNone) continue;
+      if (hole_of_vertex_[v] != kNone) return;
       const uint32_t id = (uint32_t)hole_done_.size();
       hole_done_.push_back(0);
       uint32_t c = c0;
       while (hole_of_vertex_[v] == kNone) {
         hole_of_vertex_[v] = id;
+        vstate_[v] |= 2;
         c = corner_next(c);
         while (ut_.opposite[c] != kNone) c = corner_next(c);
         v = vtx(corner_next(c));
       }
+    };
+    if (ut_.has_boundary_list) {  // the corners without an opposite, ascending (K12 by-product): same visiting order
+      for (uint32_t c0 : ut_.boundary_corners) open_hole(c0);
+    } else {
+      for (uint32_t c0 = 0; c0 < ut_.num_corners; ++c0)
+        if (ut_.opposite[c0] == kNone) open_hole(c0);
     }
   }
 
@@ -392,11 +419,11 @@ class EdgebreakerRun {
     uint32_t c = corner_prev(start);
     for (uint32_t o; (o = ut_.opposite[c]) != kNone;) c = corner_next(o);
     const uint32_t v0 = vtx(start);
-    if (mark_first) vertex_done_[v0] = 1;
+    if (mark_first) vstate_[v0] |= 1;
     if (hole_of_vertex_[v0] == kNone) throw Error(DXO_ERR_INTERNAL, "boundary walk from a vertex that is not on a hole");
     hole_done_[hole_of_vertex_[v0]] = 1;
     for (uint32_t v = vtx(corner_prev(c)); v != v0; v = vtx(corner_prev(c))) {
-      vertex_done_[v] = 1;
+      vstate_[v] |= 1;
       c = corner_next(c);
       for (uint32_t o; (o = ut_.opposite[c]) != kNone;) c = corner_next(o);
     }
@@ -417,64 +444,94 @@ class EdgebreakerRun {
     return c;
   }
 
-  void note_split_event(uint8_t right, uint32_t neighbour_corner) {  // check_and_store_topology_split_event — :434-448
-    if (neighbour_corner == kNone) return;
-    const uint32_t s = split_symbol_of_face_[neighbour_corner / 3u];
-    if (s != kNone) split_events_.push_back({symbol_index_, (uint64_t)s, right});
-  }
-
   // edgebreaker_from — :261-350
   void traverse(uint32_t c) {
+    // Hot loop: every array is reached through a local pointer and the counters live in locals. The byte
+    // stores (face / vertex state, symbols) could alias the vectors' own bookkeeping, which would otherwise
+    // force the compiler to reload data pointers and sizes from `this` after each of them.
+    const uint32_t* const opp = ut_.opposite.data();
+    const uint32_t* const cv = ut_.corner_vertex.data();
+    uint8_t* const fdone = face_done_.data();
+    uint8_t* const vst = vstate_.data();
+    uint32_t* vo = visit_order_.data();
+    uint8_t* sym = symbols_.data();
+    size_t cap = visit_order_.size(), nv = num_visited_;
+    uint64_t si = symbol_index_;
+    auto split_event = [&](uint8_t right, uint32_t neighbour_corner, uint8_t neighbour_state) {  // check_and_store_topology_split_event — :434-448
+      if (neighbour_corner == kNone || !(neighbour_state & 2)) return;  // only faces that were given an S symbol carry a split symbol
+      split_events_.push_back({si, (uint64_t)split_symbol_of_face_[neighbour_corner / 3u], right});
+    };
     stack_.clear();
     stack_.push_back(c);
     const uint64_t face_budget = ut_.num_faces;
+    // The walk is a pointer chase (the next corner comes out of opposite[]), so a cache miss costs its full
+    // latency. On regularly indexed meshes the corner index advances by a constant amount every other step;
+    // the lines two and three such strides ahead are prefetched. A wrong guess only costs the prefetch.
+    const uint32_t num_corners = ut_.num_corners;
+    uint32_t c1 = c, c2 = c;  // corners of the previous two steps
     while (!stack_.empty()) {
       c = stack_.back();
-      if (face_done_[c / 3u]) { stack_.pop_back(); continue; }
+      if (fdone[c / 3u]) { stack_.pop_back(); continue; }
       for (uint64_t n = 0; n < face_budget; ++n) {
-        ++symbol_index_;
+        {
+          const uint32_t d2 = c - c2;  // wrapping: negative strides work the same way
+          const uint32_t a = c + 2u * d2, b = c + 3u * d2;
+          if (a < num_corners) { __builtin_prefetch(opp + a); __builtin_prefetch(cv + a); }
+          if (b < num_corners) { __builtin_prefetch(opp + b); __builtin_prefetch(cv + b); }
+          c2 = c1; c1 = c;
+        }
+        ++si;
         const uint32_t face = c / 3u;
-        face_done_[face] = 1;
-        visit_order_.push_back(c);
-        const uint32_t v = vtx(c);
-        if (!vertex_done_[v]) {
-          vertex_done_[v] = 1;
-          if (hole_of_vertex_[v] == kNone) {
-            symbols_.push_back(kC);
-            c = right_of(c);
+        if (nv >= cap) {  // cannot happen on a consistent table; keep the reference's unbounded growth
+          visit_order_.resize(cap + cap / 2 + 16);
+          symbols_.resize(visit_order_.size());
+          vo = visit_order_.data(); sym = symbols_.data(); cap = visit_order_.size();
+        }
+        fdone[face] |= 1;
+        vo[nv] = c;
+        const uint32_t cn = corner_next(c);
+        const uint32_t v = cv[c];
+        const uint8_t vs = vst[v];
+        if (!(vs & 1)) {
+          vst[v] = vs | 1;
+          if (!(vs & 2)) {
+            sym[nv++] = kC;
+            c = opp[cn];  // right neighbour
             if (c == kNone) throw Error(DXO_ERR_INTERNAL, "C symbol without a right neighbour");
             continue;
           }
         }
-        const uint32_t rc = right_of(c), lc = left_of(c);
-        const bool right_done = rc == kNone || face_done_[rc / 3u];
-        const bool left_done = lc == kNone || face_done_[lc / 3u];
+        const uint32_t rc = opp[cn], lc = opp[corner_prev(c)];
+        const uint8_t rs = rc == kNone ? 1 : fdone[rc / 3u], ls = lc == kNone ? 1 : fdone[lc / 3u];
+        const bool right_done = rs & 1, left_done = ls & 1;
         if (right_done) {
-          note_split_event(1, rc);
+          split_event(1, rc, rs);
           if (left_done) {
-            note_split_event(0, lc);
-            symbols_.push_back(kE);
+            split_event(0, lc, ls);
+            sym[nv++] = kE;
             stack_.pop_back();
             break;
           }
-          symbols_.push_back(kR);
+          sym[nv++] = kR;
           c = lc;
         } else if (left_done) {
-          note_split_event(0, lc);
-          symbols_.push_back(kL);
+          split_event(0, lc, ls);
+          sym[nv++] = kL;
           c = rc;
         } else {
-          symbols_.push_back(kS);
+          sym[nv++] = kS;
           ++num_splits_;
-          const uint32_t hole = hole_of_vertex_[v];
-          if (hole != kNone && !hole_done_[hole]) walk_boundary(c, false);
-          split_symbol_of_face_[face] = (uint32_t)symbol_index_;
+          if ((vs & 2) && !hole_done_[hole_of_vertex_[v]]) walk_boundary(c, false);
+          split_symbol_of_face_[face] = (uint32_t)si;
+          fdone[face] |= 2;
           stack_.back() = lc;
           stack_.push_back(rc);
           break;
         }
       }
     }
+    num_visited_ = nv;
+    symbol_index_ = si;
   }
 
   void write_split_events(ByteSink& w) const {  // encode_topology_splits — :375-403
@@ -566,56 +623,84 @@ std::vector<uint32_t> encode_edgebreaker(const UniversalTable& ut, const std::ve
 // (:98-131). Such entries can only be popped later, when the face is already marked
 // visited, and are dropped at :56-58 before they have any effect — so they are simply
 // left on the stack here (lazy deletion, identical output).
+std::vector<uint8_t> vertex_interior_flags(const TableRef& t) {
+  std::vector<uint8_t> f(t.num_vertices);
+  for (uint32_t v = 0; v < t.num_vertices; ++v) f[v] = t.opp(corner_next(t.left_most[v])) != kNone ? 1 : 0;
+  return f;
+}
+
 std::vector<uint32_t> attribute_sequence(const TableRef& t, const std::vector<uint32_t>& corners_of_edgebreaker) {
-  std::vector<uint8_t> vertex_seen(t.num_vertices, 0), face_seen(t.num_faces, 0);
+  std::vector<uint8_t> vertex_seen_v(t.num_vertices, 0), face_seen_v(t.num_faces, 0);
   // The reference's stack starts as a copy of the corner list and is popped from the back. Here the list
   // itself is the (read-only) bottom of the stack, consumed from its end, and only pushed entries are stored.
+  // As in the traversal, the hot loop works on local pointers and counters (see EdgebreakerRun::traverse).
+  const uint32_t* const bottom_list = corners_of_edgebreaker.data();
   size_t bottom = corners_of_edgebreaker.size();
-  std::vector<uint32_t> stack, out;
-  stack.reserve(1024);
-  out.reserve(t.num_vertices);
-  const uint32_t* cv = t.corner_vertex;
-  auto emit = [&](uint32_t v, uint32_t c) { if (!vertex_seen[v]) { out.push_back(c); vertex_seen[v] = 1; } };
-  while (!stack.empty() || bottom) {
-    uint32_t c;
-    if (!stack.empty()) { c = stack.back(); stack.pop_back(); }
-    else c = corners_of_edgebreaker[--bottom];
+  std::vector<uint32_t> stack_v(1024), out_v(t.num_vertices);
+  uint32_t* stack = stack_v.data();
+  size_t top = 0, stack_cap = stack_v.size();
+  uint32_t* const out = out_v.data();
+  size_t n_out = 0;
+  uint8_t* const vertex_seen = vertex_seen_v.data();
+  uint8_t* const face_seen = face_seen_v.data();
+  const uint32_t* const cv = t.corner_vertex;
+  const uint32_t* const opposite = t.opposite;
+  const uint8_t* const seam = t.seam;
+  const uint8_t* const interior = t.interior;
+  const uint32_t* const left_most = t.left_most;
+  auto opp = [&](uint32_t c) { return (seam && seam[c]) ? kNone : opposite[c]; };
+  auto push = [&](uint32_t c) {
+    if (top == stack_cap) { stack_v.resize(stack_cap * 2); stack = stack_v.data(); stack_cap = stack_v.size(); }
+    stack[top++] = c;
+  };
+  auto emit = [&](uint32_t v, uint32_t c) { if (!vertex_seen[v]) { out[n_out++] = c; vertex_seen[v] = 1; } };  // at most one entry per vertex
+  const uint32_t num_corners = t.num_corners;
+  uint32_t c1 = 0, c2 = 0;  // corners of the previous two visited faces (stride prefetch, see EdgebreakerRun::traverse)
+  while (top || bottom) {
+    const uint32_t c = top ? stack[--top] : bottom_list[--bottom];
     const uint32_t face = c / 3u;
     if (face_seen[face]) continue;
+    {
+      const uint32_t d2 = c - c2;
+      const uint32_t a = c + 2u * d2, b = c + 3u * d2;
+      if (a < num_corners) { __builtin_prefetch(opposite + a); __builtin_prefetch(cv + a); }
+      if (b < num_corners) { __builtin_prefetch(opposite + b); __builtin_prefetch(cv + b); }
+      c2 = c1; c1 = c;
+    }
     const uint32_t nc = corner_next(c), pc = corner_prev(c);
     const uint32_t v = cv[c], nv = cv[nc], pv = cv[pc];
     if (!vertex_seen[nv] || !vertex_seen[pv]) {  // first face of a component: next, prev, then the tip
       emit(nv, nc);
       emit(pv, pc);
-      stack.push_back(c);
+      push(c);
       continue;
     }
     face_seen[face] = 1;
     if (!vertex_seen[v]) {
       emit(v, c);
       // is_on_boundary(v): swing_left(left_most_corner(v)) is None (corner_table/mod.rs:36-38)
-      const uint32_t lm = t.left_most[v];
-      const uint32_t o = t.opp(corner_next(lm));
-      if (o != kNone) {  // interior vertex: keep going to the right
-        const uint32_t r = t.opp(nc);
+      const bool is_interior = interior ? interior[v] != 0 : opp(corner_next(left_most[v])) != kNone;
+      if (is_interior) {  // interior vertex: keep going to the right
+        const uint32_t r = opp(nc);
         if (r == kNone) throw Error(DXO_ERR_INTERNAL, "sequencer: interior vertex without right neighbour");
-        stack.push_back(r);
+        push(r);
         continue;
       }
     }
-    const uint32_t rc = t.opp(nc), lc = t.opp(pc);
+    const uint32_t rc = opp(nc), lc = opp(pc);
     const bool right_seen = rc != kNone && face_seen[rc / 3u];
     const bool left_seen = lc != kNone && face_seen[lc / 3u];
     if (right_seen) {
-      if (!left_seen && lc != kNone) stack.push_back(lc);
+      if (!left_seen && lc != kNone) push(lc);
     } else if (left_seen) {
-      if (rc != kNone) stack.push_back(rc);
+      if (rc != kNone) push(rc);
     } else {
-      if (lc != kNone) stack.push_back(lc);
-      if (rc != kNone) stack.push_back(rc);
+      if (lc != kNone) push(lc);
+      if (rc != kNone) push(rc);
     }
   }
-  return out;
+  out_v.resize(n_out);
+  return out_v;
 }
 
 }  // namespace dxo

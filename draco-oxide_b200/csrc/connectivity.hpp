@@ -24,9 +24,12 @@ struct AttrView {
 struct UniversalTable {
   uint32_t num_faces = 0, num_corners = 0, num_vertices = 0;
   const uint32_t* corner_point = nullptr;  // faces, 3 per face (borrowed)
-  U32Array corner_vertex;     // vertex_idx(c), non-manifold splits applied
-  U32Array opposite;          // kNone = boundary
-  U32Array left_most;         // per vertex
+  HostArray<uint32_t> corner_vertex;     // vertex_idx(c), non-manifold splits applied
+  HostArray<uint32_t> opposite;          // kNone = boundary
+  HostArray<uint32_t> left_most;         // per vertex
+  void set_memory_source(HostArray<uint32_t>::Source fn, void* user) {  // e.g. pinned blocks for the device passes
+    corner_vertex.set_source(fn, user); opposite.set_source(fn, user); left_most.set_source(fn, user);
+  }
 
   uint32_t swing_left(uint32_t c) const { uint32_t o = opposite[corner_next(c)]; return o == kNone ? kNone : corner_next(o); }
   uint32_t swing_right(uint32_t c) const { uint32_t o = opposite[corner_prev(c)]; return o == kNone ? kNone : corner_prev(o); }
@@ -36,9 +39,12 @@ struct UniversalTable {
   // with kLeftMostDone, `left_most_out[num_vertices]` also holds the left-most corners (every vertex has
   // a single fan) and all vertex ids are used; kUnusedVertices reports the reference's unused-vertex
   // panic. Whatever is not reported as done runs sequentially on the host.
-  enum : uint32_t { kMatchExact = 1u, kLeftMostDone = 2u, kUnusedVertices = 4u };
+  // With kBoundaryListDone, `boundary_corners` holds the corners without an opposite, ascending.
+  enum : uint32_t { kMatchExact = 1u, kLeftMostDone = 2u, kUnusedVertices = 4u, kBoundaryListDone = 8u };
   using DeviceMatcher = uint32_t (*)(void* user, const uint32_t* corner_vertex, uint32_t num_faces, uint32_t num_vertices,
-                                     uint32_t* opposite_out, uint32_t* left_most_out);
+                                     uint32_t* opposite_out, uint32_t* left_most_out, std::vector<uint32_t>* boundary_corners);
+  std::vector<uint32_t> boundary_corners;  // valid only when has_boundary_list
+  bool has_boundary_list = false;
   void build(const uint32_t* faces, uint32_t nfaces, const AttrView& pos, DeviceMatcher matcher = nullptr, void* matcher_user = nullptr);
   bool matched_on_device = false;
 
@@ -52,9 +58,12 @@ struct UniversalTable {
 // Per-attribute seam table — AttributeCornerTable, core/corner_table/attribute_corner_table.rs:4-192.
 struct SeamTable {
   uint32_t num_vertices = 0;
-  U32Array corner_vertex;  // attribute vertex of each corner
-  U8Array seam;            // edge opposite to the corner is a seam (or boundary)
-  U32Array left_most;      // per attribute vertex
+  HostArray<uint32_t> corner_vertex;  // attribute vertex of each corner
+  HostArray<uint8_t> seam;            // edge opposite to the corner is a seam (or boundary)
+  HostArray<uint32_t> left_most;      // per attribute vertex
+  void set_memory_source(HostArray<uint32_t>::Source fn, void* user) {
+    corner_vertex.set_source(fn, user); seam.set_source(fn, user); left_most.set_source(fn, user);
+  }
   void build(const UniversalTable& ut, const AttrView& att);
 };
 
@@ -66,8 +75,13 @@ struct TableRef {
   const uint32_t* opposite;   // universal opposites
   const uint8_t* seam;        // nullptr for the universal table
   const uint32_t* left_most;
+  const uint8_t* interior = nullptr;  // optional, per vertex: swing_left(left_most[v]) exists (see vertex_interior_flags)
   uint32_t opp(uint32_t c) const { return (seam && seam[c]) ? kNone : opposite[c]; }
+  bool is_interior(uint32_t v) const { return interior ? interior[v] != 0 : opp(corner_next(left_most[v])) != kNone; }
 };
+// !is_on_boundary(v) for every vertex of a table (corner_table/mod.rs:36-38); lets the sequencer replace two dependent
+// random reads per vertex by one byte. Independent of the traversal, so it is computed on a helper thread.
+std::vector<uint8_t> vertex_interior_flags(const TableRef& t);
 inline TableRef table_ref(const UniversalTable& u) {
   return {u.num_faces, u.num_corners, u.num_vertices, u.corner_vertex.data(), u.opposite.data(), nullptr, u.left_most.data()};
 }

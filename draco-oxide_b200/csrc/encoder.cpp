@@ -73,6 +73,51 @@ uint8_t* DeviceContext::pinned_buffer(size_t slot, size_t bytes) {
   return b.first;
 }
 
+// Process-wide pool of pinned host blocks (cudaHostAlloc is far too slow to call per mesh). Blocks are handed
+// out best-fit and kept for the life of the process.
+namespace {
+struct PinnedPool {
+  std::mutex mu;
+  std::vector<std::pair<void*, size_t>> free_blocks;
+  void* take(size_t bytes, size_t* cap) {
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      size_t best = free_blocks.size();
+      for (size_t i = 0; i < free_blocks.size(); ++i)
+        if (free_blocks[i].second >= bytes && free_blocks[i].second <= 2 * bytes + 4096 &&
+            (best == free_blocks.size() || free_blocks[i].second < free_blocks[best].second)) best = i;
+      if (best != free_blocks.size()) {
+        auto b = free_blocks[best];
+        free_blocks.erase(free_blocks.begin() + best);
+        *cap = b.second;
+        return b.first;
+      }
+    }
+    void* p = nullptr;
+    const size_t want = bytes + bytes / 8 + 4096;
+    if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *cap = want;
+    return p;
+  }
+  void give(void* p, size_t cap) {
+    std::lock_guard<std::mutex> lock(mu);
+    free_blocks.push_back({p, cap});
+  }
+};
+PinnedPool& pinned_pool() { static PinnedPool* pool = new PinnedPool; return *pool; }  // never destroyed: outlives every job
+}  // namespace
+
+void* MeshJob::pinned_source(void* user, size_t bytes) {
+  MeshJob* job = (MeshJob*)user;
+  if (bytes < (1u << 16)) return nullptr;  // small arrays stay in ordinary memory
+  size_t cap = 0;
+  void* p = pinned_pool().take(bytes, &cap);
+  if (!p) return nullptr;
+  std::lock_guard<std::mutex> lock(job->alloc_mu_);
+  job->pinned_blocks_.push_back({p, cap});
+  return p;
+}
+
 cudaEvent_t Profile::take() {
   if (pool_used == pool.size()) { cudaEvent_t e; cuda_check(cudaEventCreate(&e), "cudaEventCreate"); pool.push_back(e); }
   return pool[pool_used++];
@@ -185,6 +230,11 @@ MeshJob::MeshJob(const dxo_mesh* mesh, const dxo_config& cfg) : mesh_(mesh), cfg
 MeshJob::~MeshJob() {
   if (inputs_upload_.valid()) { try { inputs_upload_.wait(); } catch (...) {} }  // error paths: let the helper finish before freeing
   for (void* p : allocations_) cudaFreeAsync(p, alloc_stream_);  // normally released by release(); this covers error paths
+  if (!pinned_blocks_.empty()) {
+    // a copy into one of the blocks may still be in flight on an error path: the blocks go back only when the device is idle
+    if (alloc_stream_) cudaStreamSynchronize(alloc_stream_);
+    for (auto& b : pinned_blocks_) pinned_pool().give(b.first, b.second);
+  }
   for (cudaEvent_t e : side_ready_) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : side_copied_) if (e) cudaEventDestroy(e);
 }
@@ -206,33 +256,58 @@ struct StageClock {
 // K12 + K13: half-edge matching and left-most corners on the device, one synchronisation. Keeps the device
 // copies of corner_vertex / opposite / left_most for the attribute kernels when the results are exact.
 uint32_t MeshJob::device_matcher(void* user, const uint32_t* corner_vertex, uint32_t num_faces, uint32_t num_vertices, uint32_t* opposite_out,
-                                 uint32_t* left_most_out) {
+                                 uint32_t* left_most_out, std::vector<uint32_t>* boundary_corners) {
   MeshJob* job = (MeshJob*)user;
   DeviceContext& ctx = *job->match_ctx_;
   cudaStream_t s = ctx.stream[0];
   const size_t C = (size_t)num_faces * 3;
+  StageClock clk;
   uint32_t* d_cv = job->dupload(corner_vertex, C, s);
+  clk.lap("    K12 H2D corner_vertex");
   uint32_t* d_opp = job->dalloc<uint32_t>(C, s);
   uint32_t* d_lm = job->dalloc<uint32_t>(num_vertices, s);
-  uint32_t* d_flag = job->dalloc<uint32_t>(2, s);  // [0] K12 not exact, [1] K13 fan flags
+  uint32_t* d_flag = job->dalloc<uint32_t>(3, s);  // [0] K12 not exact, [1] K13 fan flags, [2] number of boundary corners
+  constexpr uint32_t kBoundaryPrefix = 1u << 18;   // boundary corners copied back together with the flags (1 MB)
+  const size_t bb = gpu::boundary_list_scratch_bytes(C);
+  uint32_t* d_blist = nullptr;
+  void* bscratch = nullptr;
+  cuda_check(cudaMallocAsync((void**)&d_blist, C * 4, s), "cudaMallocAsync");
+  cuda_check(cudaMallocAsync(&bscratch, bb, s), "cudaMallocAsync");
   const size_t sb = gpu::corner_table_scratch_bytes(C), lb = gpu::left_most_scratch_bytes(num_vertices);
   void *scratch = nullptr, *lscratch = nullptr;
   cuda_check(cudaMallocAsync(&scratch, sb, s), "cudaMallocAsync");
   cuda_check(cudaMallocAsync(&lscratch, lb, s), "cudaMallocAsync");
-  cuda_check(cudaMemsetAsync(d_flag, 0, 8, s), "cudaMemsetAsync");
+  cuda_check(cudaMemsetAsync(d_flag, 0, 12, s), "cudaMemsetAsync");
   cuda_check(cudaMemsetAsync(d_opp, 0xFF, C * 4, s), "cudaMemsetAsync");
   gpu::launch_corner_table_opposites(d_cv, C, d_opp, d_flag, scratch, sb, s);
   gpu::launch_left_most(d_cv, d_opp, C, num_vertices, lscratch, d_lm, d_flag + 1, s);
-  uint32_t flag[2] = {1, 0};
-  cuda_check(cudaMemcpyAsync(flag, d_flag, 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+  gpu::launch_boundary_list(d_opp, C, bscratch, bb, d_blist, d_flag + 2, s);
+  uint32_t flag[3] = {1, 0, 0};
+  if (clk.on) { cudaStreamSynchronize(s); clk.lap("    K12 + K13 kernels"); }
+  cuda_check(cudaMemcpyAsync(flag, d_flag, 12, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+  const uint32_t prefix = (uint32_t)std::min<size_t>(kBoundaryPrefix, C);
+  boundary_corners->resize(prefix);
+  cuda_check(cudaMemcpyAsync(boundary_corners->data(), d_blist, (size_t)prefix * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
   // the results travel with the flags (one synchronisation); they are ignored when a flag is raised
   cuda_check(cudaMemcpyAsync(opposite_out, d_opp, C * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
   cuda_check(cudaMemcpyAsync(left_most_out, d_lm, (size_t)num_vertices * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
   cuda_check(cudaFreeAsync(scratch, s), "cudaFreeAsync");
   cuda_check(cudaFreeAsync(lscratch, s), "cudaFreeAsync");
+  cuda_check(cudaFreeAsync(bscratch, s), "cudaFreeAsync");
   cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+  clk.lap("    K12 D2H opposite, left_most");
   uint32_t done = 0;
   if (flag[1] & 1u) done |= UniversalTable::kUnusedVertices;
+  if (flag[0] == 0 && flag[2] <= C) {  // boundary list: the part beyond the prefix needs a second copy (rare)
+    boundary_corners->resize(flag[2]);
+    if (flag[2] > prefix) {
+      cuda_check(cudaMemcpyAsync(boundary_corners->data() + prefix, d_blist + prefix, (size_t)(flag[2] - prefix) * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+      cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    }
+    done |= UniversalTable::kBoundaryListDone;
+    job->d2h_bytes += (size_t)flag[2] * 4;
+  }
+  cuda_check(cudaFreeAsync(d_blist, s), "cudaFreeAsync");
   if (flag[0]) return done;  // order-dependent case: the sequential matcher decides
   done |= UniversalTable::kMatchExact;
   job->d2h_bytes += C * 4;
@@ -261,12 +336,15 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
   const bool early_uploads = ctx != nullptr && parallel_host && !getenv("DXO_NO_EARLY_UPLOAD");
   if (early_uploads)
     inputs_upload_ = std::async(std::launch::async, [this, ctx] { cuda_check(cudaSetDevice(ctx->device), "cudaSetDevice"); upload_inputs(*ctx); }).share();
+  if (ctx != nullptr && !getenv("DXO_NO_PINNED_TABLES")) ut_.set_memory_source(&MeshJob::pinned_source, this);
   const bool use_k12 = ctx != nullptr && nfaces >= 4096 && !getenv("DXO_NO_K12");  // tiny meshes: the launch + sync costs more than it saves
   ut_.build(mesh_->faces, nfaces, plans_[0].view, use_k12 ? &MeshJob::device_matcher : nullptr, this);
   clk.lap("universal corner table");
   const size_t natt = plans_.size();
   seams_.resize(natt - 1);
+  if (ctx != nullptr && !getenv("DXO_NO_PINNED_TABLES")) for (SeamTable& st : seams_) st.set_memory_source(&MeshJob::pinned_source, this);
   table_refs_.assign(natt, TableRef{});
+  interior_.assign(natt, {});
   std::vector<ByteSink> seam_bytes(natt - 1);
   EdgebreakerEncoder eb(ut_);
   if (!parallel_host || natt == 1) {
@@ -290,19 +368,25 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
       for (size_t i = 1; i < natt; ++i)
         tasks.push_back(std::async(std::launch::async, [this, i, ctx, early_uploads] {
           StageClock c;
-          if (early_uploads && !getenv("DXO_NO_K14") && device_seam_table(*ctx, i)) { c.lap("  (thread) seam table (K14)"); return; }
-          seams_[i - 1].build(ut_, plans_[i].view);
-          c.lap("  (thread) seam table");
-          if (early_uploads) { cuda_check(cudaSetDevice(ctx->device), "cudaSetDevice"); upload_seam_table(*ctx, i); c.lap("  (thread) seam table upload"); }
+          if (early_uploads && !getenv("DXO_NO_K14") && device_seam_table(*ctx, i)) c.lap("  (thread) seam table (K14)");
+          else {
+            seams_[i - 1].build(ut_, plans_[i].view);
+            c.lap("  (thread) seam table");
+            if (early_uploads) { cuda_check(cudaSetDevice(ctx->device), "cudaSetDevice"); upload_seam_table(*ctx, i); c.lap("  (thread) seam table upload"); }
+          }
+          table_refs_[i] = table_ref(ut_, seams_[i - 1]);
+          interior_[i] = vertex_interior_flags(table_refs_[i]);
+          table_refs_[i].interior = interior_[i].data();
+          c.lap("  (thread) interior flags");
         }));
+      table_refs_[0] = table_ref(ut_);
+      tasks.push_back(std::async(std::launch::async, [this] { interior_[0] = vertex_interior_flags(table_refs_[0]); table_refs_[0].interior = interior_[0].data(); }));
       { StageClock c; eb.traverse(); c.lap("  (main) CLERS traversal"); }
       corners_of_edgebreaker_ = eb.take_corners_of_edgebreaker();
-      table_refs_[0] = table_ref(ut_);
-      auto seq0 = std::async(std::launch::async, [this] { StageClock c; plans_[0].sequence = attribute_sequence(table_refs_[0], corners_of_edgebreaker_); c.lap("  (thread) position sequence"); });
-      wait_all();  // seam tables
+      wait_all();  // seam tables, interior flags
       clk.lap("seam tables + traversal");
+      auto seq0 = std::async(std::launch::async, [this] { StageClock c; plans_[0].sequence = attribute_sequence(table_refs_[0], corners_of_edgebreaker_); c.lap("  (thread) position sequence"); });
       for (size_t i = 1; i < natt; ++i) {
-        table_refs_[i] = table_ref(ut_, seams_[i - 1]);
         tasks.push_back(std::async(std::launch::async, [this, i] { StageClock c; plans_[i].sequence = attribute_sequence(table_refs_[i], corners_of_edgebreaker_); c.lap("  (thread) attribute sequence"); }));
         tasks.push_back(std::async(std::launch::async, [this, i, &eb, &seam_bytes] { StageClock c; eb.write_seam_stream(seams_[i - 1], seam_bytes[i - 1]); c.lap("  (thread) seam stream"); }));
       }

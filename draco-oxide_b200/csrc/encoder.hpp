@@ -115,6 +115,7 @@ class MeshJob {
   UniversalTable ut_;
   std::vector<SeamTable> seams_;
   std::vector<TableRef> table_refs_;
+  std::vector<std::vector<uint8_t>> interior_;  // per table: vertex_interior_flags (helper threads, during the traversal)
   ByteSink head_;  // header + connectivity + attribute section headers
   std::vector<uint32_t> corners_of_edgebreaker_;
   // device
@@ -125,6 +126,10 @@ class MeshJob {
   std::vector<AttrResult> results_;
   std::vector<void*> allocations_;
   std::mutex alloc_mu_;              // dalloc / dupload are also called from the helper threads of build_connectivity
+  // pinned host blocks holding the connectivity tables that K12-K14 produce (borrowed from a process-wide pool,
+  // returned by the destructor)
+  std::vector<std::pair<void*, size_t>> pinned_blocks_;
+  static void* pinned_source(void* user, size_t bytes);
   std::shared_future<void> inputs_upload_;  // faces, values and point maps travel while the host builds the tables
   bool device_seam_table(DeviceContext& ctx, size_t att);  // K14; false = not applicable / flagged, use the host pass
   void upload_inputs(DeviceContext& ctx);
@@ -135,7 +140,7 @@ class MeshJob {
   void encode_side_stream(size_t att);
 
   static uint32_t device_matcher(void* user, const uint32_t* corner_vertex, uint32_t num_faces, uint32_t num_vertices, uint32_t* opposite_out,
-                                 uint32_t* left_most_out);
+                                 uint32_t* left_most_out, std::vector<uint32_t>* boundary_corners);
   DeviceContext* match_ctx_ = nullptr;
   template <class T> T* dalloc(size_t count, cudaStream_t s);
   template <class T> T* dupload(const T* host, size_t count, cudaStream_t s);

@@ -8,6 +8,8 @@
 // small single-CTA table kernel (K9) and a latency-bound serial coder (K10).
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include "kernels.cuh"
 
@@ -1407,6 +1409,24 @@ __global__ void __launch_bounds__(kThreads) left_most_kernel(const uint32_t* __r
     left_most[v] = last;
   }
   if (bad) atomicOr(flags, bad);
+}
+
+// corners without an opposite, ascending (ordered compaction): the outer loop of Edgebreaker::compute_boundaries
+// (edgebreaker.rs:195-224) visits exactly these
+struct IsBoundaryCorner {
+  const uint32_t* opposite;
+  __host__ __device__ bool operator()(uint32_t c) const { return opposite[c] == kNoneDev; }
+};
+size_t boundary_list_scratch_bytes(uint64_t num_corners) {
+  size_t b = 0;
+  thrust::counting_iterator<uint32_t> it(0);
+  cub::DeviceSelect::If(nullptr, b, it, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)num_corners, IsBoundaryCorner{nullptr});
+  return b + 256;
+}
+void launch_boundary_list(const uint32_t* opposite, uint64_t num_corners, void* scratch, size_t scratch_bytes, uint32_t* list, uint32_t* count,
+                          cudaStream_t s) {
+  thrust::counting_iterator<uint32_t> it(0);
+  cub::DeviceSelect::If(scratch, scratch_bytes, it, list, count, (int)num_corners, IsBoundaryCorner{opposite}, s);
 }
 
 size_t left_most_scratch_bytes(uint32_t num_vertices) { return 2 * (size_t)num_vertices * sizeof(uint32_t) + 256; }

@@ -98,6 +98,10 @@ void launch_corner_table_opposites(const uint32_t* corner_vertex, uint64_t num_c
 // flags (one word, zeroed by the caller): bit 0 = a vertex id below num_vertices is unused, bit 1 = a vertex has a
 // second fan (the reference splits it; the caller must run the sequential pass).
 size_t left_most_scratch_bytes(uint32_t num_vertices);
+// ordered list of the corners whose opposite is none (list: num_corners entries of capacity; *count = entries used)
+size_t boundary_list_scratch_bytes(uint64_t num_corners);
+void launch_boundary_list(const uint32_t* opposite, uint64_t num_corners, void* scratch, size_t scratch_bytes, uint32_t* list, uint32_t* count,
+                          cudaStream_t s);
 void launch_left_most(const uint32_t* corner_vertex, const uint32_t* opposite, uint64_t num_corners, uint32_t num_vertices, void* scratch,
                       uint32_t* left_most, uint32_t* flags, cudaStream_t s);
 
