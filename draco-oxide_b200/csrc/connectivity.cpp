@@ -245,6 +245,7 @@ void UniversalTable::assign_left_most_corners() {
 // AttributeCornerTable::new + recompute_vertices — attribute_corner_table.rs:16-137
 void SeamTable::build(const UniversalTable& ut, const AttrView& att) {
   const uint32_t C = ut.num_corners;
+  has_interior_seam = false;
   seam.assign(C, 0);
   std::vector<uint8_t> vertex_on_seam(ut.num_vertices, 0);
   const uint32_t* pt = ut.corner_point;
@@ -266,6 +267,7 @@ void SeamTable::build(const UniversalTable& ut, const AttrView& att) {
     // the two end points of the shared edge must carry the same values on both faces
     const uint32_t cn = corner_next(c), cp = corner_prev(c), on = corner_next(o), op = corner_prev(o);
     if (val(cn) != val(op) || val(cp) != val(on)) {
+      has_interior_seam = true;
       seam[c] = seam[o] = 1;
       vertex_on_seam[cv[cn]] = vertex_on_seam[cv[cp]] = 1;
       vertex_on_seam[cv[on]] = vertex_on_seam[cv[op]] = 1;
@@ -468,6 +470,7 @@ class EdgebreakerRun {
     // latency. On regularly indexed meshes the corner index advances by a constant amount every other step;
     // the lines two and three such strides ahead are prefetched. A wrong guess only costs the prefetch.
     const uint32_t num_corners = ut_.num_corners;
+    static const uint32_t pf_a = getenv("DXO_PF_A") ? (uint32_t)atoi(getenv("DXO_PF_A")) : 6u, pf_b = getenv("DXO_PF_B") ? (uint32_t)atoi(getenv("DXO_PF_B")) : 12u;
     uint32_t c1 = c, c2 = c;  // corners of the previous two steps
     while (!stack_.empty()) {
       c = stack_.back();
@@ -475,7 +478,7 @@ class EdgebreakerRun {
       for (uint64_t n = 0; n < face_budget; ++n) {
         {
           const uint32_t d2 = c - c2;  // wrapping: negative strides work the same way
-          const uint32_t a = c + 2u * d2, b = c + 3u * d2;
+          const uint32_t a = c + pf_a * d2, b = c + pf_b * d2;
           if (a < num_corners) { __builtin_prefetch(opp + a); __builtin_prefetch(cv + a); }
           if (b < num_corners) { __builtin_prefetch(opp + b); __builtin_prefetch(cv + b); }
           c2 = c1; c1 = c;
@@ -655,6 +658,7 @@ std::vector<uint32_t> attribute_sequence(const TableRef& t, const std::vector<ui
   };
   auto emit = [&](uint32_t v, uint32_t c) { if (!vertex_seen[v]) { out[n_out++] = c; vertex_seen[v] = 1; } };  // at most one entry per vertex
   const uint32_t num_corners = t.num_corners;
+  static const uint32_t pf_a = getenv("DXO_PF_A") ? (uint32_t)atoi(getenv("DXO_PF_A")) : 6u, pf_b = getenv("DXO_PF_B") ? (uint32_t)atoi(getenv("DXO_PF_B")) : 12u;
   uint32_t c1 = 0, c2 = 0;  // corners of the previous two visited faces (stride prefetch, see EdgebreakerRun::traverse)
   while (top || bottom) {
     const uint32_t c = top ? stack[--top] : bottom_list[--bottom];
@@ -662,7 +666,7 @@ std::vector<uint32_t> attribute_sequence(const TableRef& t, const std::vector<ui
     if (face_seen[face]) continue;
     {
       const uint32_t d2 = c - c2;
-      const uint32_t a = c + 2u * d2, b = c + 3u * d2;
+      const uint32_t a = c + pf_a * d2, b = c + pf_b * d2;
       if (a < num_corners) { __builtin_prefetch(opposite + a); __builtin_prefetch(cv + a); }
       if (b < num_corners) { __builtin_prefetch(opposite + b); __builtin_prefetch(cv + b); }
       c2 = c1; c1 = c;

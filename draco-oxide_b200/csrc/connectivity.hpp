@@ -58,6 +58,9 @@ struct UniversalTable {
 // Per-attribute seam table — AttributeCornerTable, core/corner_table/attribute_corner_table.rs:4-192.
 struct SeamTable {
   uint32_t num_vertices = 0;
+  // false: the only seams are mesh boundaries, every universal vertex maps to one attribute vertex. The table then
+  // equals the universal one (same vertex ids, opposites and left-most corners) and so does its sequence.
+  bool has_interior_seam = true;
   HostArray<uint32_t> corner_vertex;  // attribute vertex of each corner
   HostArray<uint8_t> seam;            // edge opposite to the corner is a seam (or boundary)
   HostArray<uint32_t> left_most;      // per attribute vertex

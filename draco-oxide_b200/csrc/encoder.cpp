@@ -386,13 +386,21 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
       wait_all();  // seam tables, interior flags
       clk.lap("seam tables + traversal");
       auto seq0 = std::async(std::launch::async, [this] { StageClock c; plans_[0].sequence = attribute_sequence(table_refs_[0], corners_of_edgebreaker_); c.lap("  (thread) position sequence"); });
+      // an attribute whose only seams are mesh boundaries has the universal table (same ids, opposites, left-most
+      // corners), hence the position sequence: it is copied instead of recomputed
+      auto shares_position_sequence = [this](size_t i) {
+        const SeamTable& st = seams_[i - 1];
+        return !st.has_interior_seam && st.num_vertices == ut_.num_vertices && !getenv("DXO_NO_SHARED_SEQUENCE");
+      };
       for (size_t i = 1; i < natt; ++i) {
-        tasks.push_back(std::async(std::launch::async, [this, i] { StageClock c; plans_[i].sequence = attribute_sequence(table_refs_[i], corners_of_edgebreaker_); c.lap("  (thread) attribute sequence"); }));
+        if (!shares_position_sequence(i))
+          tasks.push_back(std::async(std::launch::async, [this, i] { StageClock c; plans_[i].sequence = attribute_sequence(table_refs_[i], corners_of_edgebreaker_); c.lap("  (thread) attribute sequence"); }));
         tasks.push_back(std::async(std::launch::async, [this, i, &eb, &seam_bytes] { StageClock c; eb.write_seam_stream(seams_[i - 1], seam_bytes[i - 1]); c.lap("  (thread) seam stream"); }));
       }
       tasks.push_back(std::move(seq0));
       { StageClock c; eb.write_head(head_, seams_.size()); c.lap("  (main) connectivity head"); }
       wait_all();
+      for (size_t i = 1; i < natt; ++i) if (shares_position_sequence(i)) plans_[i].shares_sequence_of = 0;
       clk.lap("sequences + streams");
     } catch (...) {
       try { wait_all(); } catch (...) {}
@@ -479,9 +487,10 @@ bool MeshJob::device_seam_table(DeviceContext& ctx, size_t att) {
   cuda_check(cudaMemcpyAsync(scalars, d_scalars, 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
   cuda_check(cudaFreeAsync(scratch, s), "cudaFreeAsync");
   cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
-  if (scalars[1] != 0 || scalars[0] > C) return false;  // the sequential pass reports the error
+  if ((scalars[1] & 3u) != 0 || scalars[0] > C) return false;  // the sequential pass reports the error
   SeamTable& st = seams_[att - 1];
   st.num_vertices = scalars[0];
+  st.has_interior_seam = (scalars[1] & 4u) != 0;
   st.corner_vertex.resize(C);
   st.seam.resize(C);
   st.left_most.resize(st.num_vertices);
@@ -524,8 +533,8 @@ void MeshJob::upload(DeviceContext& ctx) {
   for (size_t i = 0; i < plans_.size(); ++i) {
     const AttrPlan& p = plans_[i];
     AttrDevice& d = dev_[i];
-    const size_t U = p.view.num_unique, M = p.sequence.size();
-    d.seq = dupload(p.sequence.data(), M, s);
+    const size_t U = p.view.num_unique, M = sequence_of(i).size();
+    d.seq = p.shares_sequence_of >= 0 ? dev_[p.shares_sequence_of].seq : dupload(p.sequence.data(), M, s);
     const uint32_t V = p.table->num_vertices;
     const size_t qstride = p.ncomp_q == 3 ? 4 : p.ncomp_q;  // one value = one vector load (kernels.cu load_q)
     if (p.port == Portabilization::ToBits && p.ncomp_q != 3) d.quant = (int32_t*)d.values;
@@ -594,7 +603,7 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     AttrDevice& d = dev_[i];
     cudaStream_t s = ctx.stream[std::min<size_t>(i, 2)];
     const uint64_t U = p.view.num_unique, V = p.table->num_vertices;
-    const uint32_t M = (uint32_t)p.sequence.size();
+    const uint32_t M = (uint32_t)sequence_of(i).size();
     const uint64_t S = (uint64_t)M * p.ncomp_q;
     const gpu::TableDev t = table_dev(i);
     const gpu::QuantDev q{d.quant, d.map, p.ncomp_q};
@@ -723,8 +732,8 @@ void MeshJob::download(DeviceContext& ctx) {
   std::vector<std::future<void>> workers;
   for (size_t i = 0; i < plans_.size(); ++i) {
     if (!side_copied_[i]) continue;
-    results_[i].side = ctx.pinned_buffer(2 * i + 1, plans_[i].sequence.size());
-    results_[i].side_len = plans_[i].sequence.size();
+    results_[i].side = ctx.pinned_buffer(2 * i + 1, sequence_of(i).size());
+    results_[i].side_len = sequence_of(i).size();
     const int device = ctx.device;
     cudaEvent_t ev = side_copied_[i];
     workers.push_back(std::async(std::launch::async, [this, i, device, ev] {
@@ -752,8 +761,8 @@ void MeshJob::download(DeviceContext& ctx) {
       if (int st = status_from_flags(r.stats.error_flags)) throw Error(st, "device reported an encoding error");
       static const bool rans_debug = getenv("DXO_RANS_DEBUG") != nullptr;
       if (rans_debug) fprintf(stderr, "[dxo] att %zu: rANS symbols=%llu P=%u K=%u chunks=%u relaxed=%u fixup=%u\n", i,
-                              (unsigned long long)plans_[i].sequence.size() * plans_[i].ncomp_q, r.stats.precision, r.stats.num_table_symbols,
-                              gpu::rans_num_chunks((uint64_t)plans_[i].sequence.size() * plans_[i].ncomp_q), r.stats.pad[0], r.stats.pad[1]);
+                              (unsigned long long)sequence_of(i).size() * plans_[i].ncomp_q, r.stats.precision, r.stats.num_table_symbols,
+                              gpu::rans_num_chunks((uint64_t)sequence_of(i).size() * plans_[i].ncomp_q), r.stats.pad[0], r.stats.pad[1]);
       if (r.stats.table_bytes > dev_[i].table_capacity || r.stats.payload_bytes > dev_[i].payload_capacity)
         throw Error(DXO_ERR_INTERNAL, "device output exceeds its buffer");
       uint8_t* host = ctx.pinned_buffer(2 * i, (size_t)r.stats.table_bytes + r.stats.payload_bytes + 16);
@@ -845,7 +854,7 @@ void MeshJob::capture_host_trace() {
       put(k + "left_most", seams_[i - 1].left_most.data(), seams_[i - 1].left_most.size() * 4);
       put(k + "seam", seams_[i - 1].seam.data(), seams_[i - 1].seam.size());
     }
-    put(k + "sequence", plans_[i].sequence.data(), plans_[i].sequence.size() * 4);
+    put(k + "sequence", sequence_of(i).data(), sequence_of(i).size() * 4);
   }
 }
 
@@ -871,7 +880,7 @@ void MeshJob::capture_trace(DeviceContext& ctx) {
     } else {
       fetch(k + "quantized", dev_[i].quant, (size_t)p.view.num_unique * p.ncomp_q * 4);
     }
-    fetch(k + "symbols", dev_[i].symbols, p.sequence.size() * p.ncomp_q * 4);
+    fetch(k + "symbols", dev_[i].symbols, sequence_of(i).size() * p.ncomp_q * 4);
     {
       std::vector<uint32_t> h(r.stats.num_table_symbols);
       if (!h.empty()) cuda_check(cudaMemcpy(h.data(), dev_[i].hist, h.size() * 4, cudaMemcpyDeviceToHost), "cudaMemcpy trace");

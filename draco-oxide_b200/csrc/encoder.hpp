@@ -61,7 +61,8 @@ struct AttrPlan {
   int parent = -1;            // index of the position attribute this one predicts from
   uint32_t hist_capacity = 0; // upper bound of the alphabet
   const TableRef* table = nullptr;
-  std::vector<uint32_t> sequence;
+  std::vector<uint32_t> sequence;  // empty when shared (see MeshJob::sequence_of)
+  int shares_sequence_of = -1;     // index of the attribute whose sequence (host and device copy) this one uses
 };
 
 struct AttrDevice {
@@ -107,6 +108,9 @@ class MeshJob {
   std::map<std::string, std::vector<uint8_t>> trace_items;
   uint64_t h2d_bytes = 0, d2h_bytes = 0;
   uint64_t num_position_vertices() const { return plans_.empty() ? 0 : plans_[0].sequence.size(); }
+  const std::vector<uint32_t>& sequence_of(size_t att) const {
+    return plans_[att].shares_sequence_of >= 0 ? plans_[plans_[att].shares_sequence_of].sequence : plans_[att].sequence;
+  }
 
  private:
   const dxo_mesh* mesh_;

@@ -1447,7 +1447,7 @@ void launch_left_most(const uint32_t* corner_vertex, const uint32_t* opposite, u
 // (b) per universal vertex, in vertex order: the fan is walked to the right starting at the first corner after a
 //     seam, and every seam crossed opens a new attribute vertex. The ids are consecutive in (vertex, walk) order,
 //     i.e. an exclusive prefix sum of the per-vertex counts — so pass (b) runs twice around a scan.
-constexpr uint32_t kSeamBadPoint = 1u, kSeamClosedFan = 2u;
+constexpr uint32_t kSeamBadPoint = 1u, kSeamClosedFan = 2u, kSeamInterior = 4u;  // kSeamInterior is informational: a seam that is not a mesh boundary exists
 
 __global__ void __launch_bounds__(kThreads) seam_flags_kernel(const uint32_t* __restrict__ corner_point, const uint32_t* __restrict__ map,
                                                               uint32_t num_points, const uint32_t* __restrict__ cv,
@@ -1472,6 +1472,7 @@ __global__ void __launch_bounds__(kThreads) seam_flags_kernel(const uint32_t* __
     }
     seam[c] = is_seam ? 1 : 0;
     if (is_seam) { vertex_on_seam[__ldg(cv + cn)] = 1; vertex_on_seam[__ldg(cv + cp)] = 1; }
+    if (is_seam && o != kNoneDev) bad |= kSeamInterior;
   }
   if (bad) atomicOr(flags, bad);
 }

@@ -109,6 +109,7 @@ void launch_left_most(const uint32_t* corner_vertex, const uint32_t* opposite, u
 // Outputs: seam[C], corner_vertex[C], left_most_a[<= C] (attribute vertex -> corner), *total = number of attribute
 // vertices. flags (zeroed by the caller): bit 0 = a face references a point outside the attribute, bit 1 = a seam
 // vertex whose fan closes on itself; either sends the caller to the sequential pass (which reports the error).
+// bit 2 is informational: the attribute has a seam that is not a mesh boundary.
 size_t seam_table_scratch_bytes(uint32_t num_vertices);
 void launch_seam_table(const uint32_t* corner_point, const uint32_t* map, uint32_t num_points, const uint32_t* cv, const uint32_t* opposite,
                        const uint32_t* left_most_u, uint64_t num_corners, uint32_t num_vertices, void* scratch, size_t scratch_bytes,
