@@ -353,12 +353,10 @@ class EdgebreakerRun {
     lap("CLERS loop");
     symbols_.resize(num_visited_);
     visit_order_.resize(num_visited_);
-    corners_.assign(init_face_corners_.rbegin(), init_face_corners_.rend());
-    corners_.insert(corners_.end(), visit_order_.begin(), visit_order_.end());
+    init_reversed_.assign(init_face_corners_.rbegin(), init_face_corners_.rend());
     lap("corner list");
   }
-  const std::vector<uint32_t>& corners_of_edgebreaker() const { return corners_; }
-  std::vector<uint32_t> take_corners_of_edgebreaker() { return std::move(corners_); }
+  EdgebreakerEncoder::CornerList corner_list() const { return {init_reversed_.data(), init_reversed_.size(), visit_order_.data(), visit_order_.size()}; }
 
   // phase 2a: everything of the connectivity section up to and including the start-face stream
   void write_head(ByteSink& w, size_t num_seam_tables) const {
@@ -377,7 +375,7 @@ class EdgebreakerRun {
   // vstate_: bit 0 = vertex visited, bit 1 = vertex lies on a hole (hole_of_vertex_ != kNone);
   // face_done_: bit 0 = face visited, bit 1 = the face got an S symbol (split_symbol_of_face_ is set)
   std::vector<uint8_t> vstate_, face_done_, hole_done_, start_face_interior_;
-  std::vector<uint32_t> hole_of_vertex_, stack_, init_face_corners_, corners_;
+  std::vector<uint32_t> hole_of_vertex_, stack_, init_face_corners_, init_reversed_;
   U8Array symbols_;        // sized once, every used entry written by the traversal (no zero-fill)
   U32Array visit_order_;
   std::vector<uint32_t> split_symbol_of_face_;  // symbol index of the S symbol a face got (< num_faces), kNone otherwise
@@ -574,27 +572,48 @@ class EdgebreakerRun {
  public:
   // phase 2b: the seam stream of one non-position attribute (:610-653); independent per attribute
   void write_seam_stream(const SeamTable& st, ByteSink& w) const {
-    std::vector<uint8_t> face_seen(ut_.num_faces, 0);
-    std::vector<uint8_t> flags;
-    flags.reserve(ut_.num_corners / 2 + 16);
+    // One flag per interior edge: faces are walked in reverse visiting order and an edge is reported by the first
+    // of its two faces met (the init face of an interior-start component is never walked, so its neighbours report
+    // its edges). The reference then feeds the flags to the coder last-to-first (:644); here they are written into
+    // the buffer back to front, so the buffer is already in coding order.
+    const size_t max_flags = ut_.num_corners / 2 + 1;
+    U8Array flags(max_flags);
+    uint8_t* const end = flags.data() + max_flags;
+    uint8_t* head = end;
     uint64_t zeros = 0;
-    for (size_t i = visit_order_.size(); i-- > 0;) {
-      const uint32_t c = visit_order_[i];
-      const uint32_t tri[3] = {c, corner_next(c), corner_prev(c)};
-      face_seen[c / 3u] = 1;
-      for (uint32_t k : tri) {
-        const uint32_t o = ut_.opposite[k];
-        if (o == kNone || face_seen[o / 3u]) continue;
-        const uint8_t f = st.seam[k];
-        flags.push_back(f);
-        zeros += f ? 0 : 1;
+    if (!st.has_interior_seam) {
+      // only mesh boundaries are seams: every reported flag is 0, and there are (corners - boundary corners) / 2 of them
+      size_t boundary = 0;
+      if (ut_.has_boundary_list) boundary = ut_.boundary_corners.size();
+      else for (uint32_t c = 0; c < ut_.num_corners; ++c) boundary += ut_.opposite[c] == kNone;
+      const size_t n = (ut_.num_corners - boundary) / 2;
+      head = end - n;
+      memset(head, 0, n);
+      zeros = n;
+    } else {
+      std::vector<uint8_t> face_seen_v(ut_.num_faces, 0);
+      uint8_t* const face_seen = face_seen_v.data();
+      const uint32_t* const opp = ut_.opposite.data();
+      const uint8_t* const seam = st.seam.data();
+      const uint32_t* const visit = visit_order_.data();
+      for (size_t i = visit_order_.size(); i-- > 0;) {
+        const uint32_t c = visit[i];
+        const uint32_t tri[3] = {c, corner_next(c), corner_prev(c)};
+        face_seen[c / 3u] = 1;
+        for (uint32_t k : tri) {
+          const uint32_t o = opp[k];
+          if (o == kNone || face_seen[o / 3u]) continue;
+          const uint8_t f = seam[k];
+          if (head == flags.data()) throw Error(DXO_ERR_INTERNAL, "seam stream: more flags than interior edges");
+          *--head = f;
+          zeros += f ? 0 : 1;
+        }
       }
     }
-    const uint8_t p0 = side_stream_zero_prob(zeros, (float)flags.size());
-    // bits are fed last-to-first (:644): reverse once, then use the forward coder
-    std::reverse(flags.begin(), flags.end());
+    const size_t n = (size_t)(end - head);
+    const uint8_t p0 = side_stream_zero_prob(zeros, (float)n);
     std::vector<uint8_t> bytes;
-    rabs_encode_forward(flags.data(), flags.size(), p0, bytes);
+    rabs_encode_forward(head, n, p0, bytes);
     w.u8(p0);
     w.varint(bytes.size());
     w.bytes(bytes);
@@ -604,8 +623,13 @@ class EdgebreakerRun {
 EdgebreakerEncoder::EdgebreakerEncoder(const UniversalTable& ut) : run_(new EdgebreakerRun(ut)) {}
 EdgebreakerEncoder::~EdgebreakerEncoder() { delete run_; }
 void EdgebreakerEncoder::traverse() { run_->traverse_all(); }
-const std::vector<uint32_t>& EdgebreakerEncoder::corners_of_edgebreaker() const { return run_->corners_of_edgebreaker(); }
-std::vector<uint32_t> EdgebreakerEncoder::take_corners_of_edgebreaker() { return run_->take_corners_of_edgebreaker(); }
+EdgebreakerEncoder::CornerList EdgebreakerEncoder::corner_list() const { return run_->corner_list(); }
+std::vector<uint32_t> EdgebreakerEncoder::corners_of_edgebreaker() const {
+  const CornerList l = corner_list();
+  std::vector<uint32_t> all(l.init_reversed, l.init_reversed + l.num_init);
+  all.insert(all.end(), l.visited, l.visited + l.num_visited);
+  return all;
+}
 void EdgebreakerEncoder::write_head(ByteSink& w, size_t num_seam_tables) const {
   if (num_seam_tables > 255) throw Error(DXO_ERR_TOO_MANY_ATTRIBUTES, "too many connectivity attributes");
   run_->write_head(w, num_seam_tables);
@@ -632,13 +656,13 @@ std::vector<uint8_t> vertex_interior_flags(const TableRef& t) {
   return f;
 }
 
-std::vector<uint32_t> attribute_sequence(const TableRef& t, const std::vector<uint32_t>& corners_of_edgebreaker) {
+std::vector<uint32_t> attribute_sequence(const TableRef& t, const EdgebreakerEncoder::CornerList& corners_of_edgebreaker) {
   std::vector<uint8_t> vertex_seen_v(t.num_vertices, 0), face_seen_v(t.num_faces, 0);
   // The reference's stack starts as a copy of the corner list and is popped from the back. Here the list
   // itself is the (read-only) bottom of the stack, consumed from its end, and only pushed entries are stored.
   // As in the traversal, the hot loop works on local pointers and counters (see EdgebreakerRun::traverse).
-  const uint32_t* const bottom_list = corners_of_edgebreaker.data();
-  size_t bottom = corners_of_edgebreaker.size();
+  const EdgebreakerEncoder::CornerList bottom_list = corners_of_edgebreaker;
+  size_t bottom = bottom_list.size();
   std::vector<uint32_t> stack_v(1024), out_v(t.num_vertices);
   uint32_t* stack = stack_v.data();
   size_t top = 0, stack_cap = stack_v.size();
@@ -647,8 +671,8 @@ std::vector<uint32_t> attribute_sequence(const TableRef& t, const std::vector<ui
   uint8_t* const vertex_seen = vertex_seen_v.data();
   uint8_t* const face_seen = face_seen_v.data();
   const uint32_t* const cv = t.corner_vertex;
-  const uint32_t* const opposite = t.opposite;
-  const uint8_t* const seam = t.seam;
+  const uint32_t* const opposite = t.opposite_masked ? t.opposite_masked : t.opposite;  // masked: seams already applied
+  const uint8_t* const seam = t.opposite_masked ? nullptr : t.seam;
   const uint8_t* const interior = t.interior;
   const uint32_t* const left_most = t.left_most;
   auto opp = [&](uint32_t c) { return (seam && seam[c]) ? kNone : opposite[c]; };

@@ -78,8 +78,9 @@ struct TableRef {
   const uint32_t* opposite;   // universal opposites
   const uint8_t* seam;        // nullptr for the universal table
   const uint32_t* left_most;
+  const uint32_t* opposite_masked = nullptr;  // optional: opposite with seam edges set to kNone (one read per opp())
   const uint8_t* interior = nullptr;  // optional, per vertex: swing_left(left_most[v]) exists (see vertex_interior_flags)
-  uint32_t opp(uint32_t c) const { return (seam && seam[c]) ? kNone : opposite[c]; }
+  uint32_t opp(uint32_t c) const { return opposite_masked ? opposite_masked[c] : (seam && seam[c]) ? kNone : opposite[c]; }
   bool is_interior(uint32_t v) const { return interior ? interior[v] != 0 : opp(corner_next(left_most[v])) != kNone; }
 };
 // !is_on_boundary(v) for every vertex of a table (corner_table/mod.rs:36-38); lets the sequencer replace two dependent
@@ -105,8 +106,16 @@ class EdgebreakerEncoder {
   EdgebreakerEncoder(const EdgebreakerEncoder&) = delete;
   EdgebreakerEncoder& operator=(const EdgebreakerEncoder&) = delete;
   void traverse();
-  const std::vector<uint32_t>& corners_of_edgebreaker() const;
-  std::vector<uint32_t> take_corners_of_edgebreaker();  // moves the list out (the seam streams do not need it)
+  // corners_of_edgebreaker = the init-face corners of interior-start components, last component first, followed by
+  // every visited corner in visiting order. Kept as its two parts (no concatenated copy).
+  struct CornerList {
+    const uint32_t* init_reversed; size_t num_init;
+    const uint32_t* visited; size_t num_visited;
+    size_t size() const { return num_init + num_visited; }
+    uint32_t operator[](size_t i) const { return i < num_init ? init_reversed[i] : visited[i - num_init]; }
+  };
+  CornerList corner_list() const;
+  std::vector<uint32_t> corners_of_edgebreaker() const;  // concatenated copy (tests, traces)
   void write_head(ByteSink& w, size_t num_seam_tables) const;
   void write_seam_stream(const SeamTable& st, ByteSink& w) const;
  private:
@@ -117,6 +126,6 @@ std::vector<uint32_t> encode_edgebreaker(const UniversalTable& ut, const std::ve
 
 // Traverser::compute_seqeunce — shared/attribute/sequence.rs:48-151.
 // One corner per attribute vertex, in the order the decoder will reconstruct them.
-std::vector<uint32_t> attribute_sequence(const TableRef& t, const std::vector<uint32_t>& corners_of_edgebreaker);
+std::vector<uint32_t> attribute_sequence(const TableRef& t, const EdgebreakerEncoder::CornerList& corners_of_edgebreaker);
 
 }  // namespace dxo

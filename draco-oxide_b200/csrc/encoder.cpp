@@ -346,7 +346,10 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
   table_refs_.assign(natt, TableRef{});
   interior_.assign(natt, {});
   std::vector<ByteSink> seam_bytes(natt - 1);
-  EdgebreakerEncoder eb(ut_);
+  eb_.reset(new EdgebreakerEncoder(ut_));
+  EdgebreakerEncoder& eb = *eb_;
+  masked_opposite_.clear();
+  masked_opposite_.resize(natt);
   if (!parallel_host || natt == 1) {
     for (size_t i = 1; i < natt; ++i) seams_[i - 1].build(ut_, plans_[i].view);
     clk.lap("seam tables");
@@ -354,10 +357,9 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
     eb.write_head(head_, seams_.size());
     for (size_t i = 1; i < natt; ++i) eb.write_seam_stream(seams_[i - 1], seam_bytes[i - 1]);
     clk.lap("edgebreaker");
-    corners_of_edgebreaker_ = eb.take_corners_of_edgebreaker();
     table_refs_[0] = table_ref(ut_);
     for (size_t i = 1; i < natt; ++i) table_refs_[i] = table_ref(ut_, seams_[i - 1]);
-    for (size_t i = 0; i < natt; ++i) plans_[i].sequence = attribute_sequence(table_refs_[i], corners_of_edgebreaker_);
+    for (size_t i = 0; i < natt; ++i) plans_[i].sequence = attribute_sequence(table_refs_[i], eb.corner_list());
     clk.lap("attribute sequences");
   } else {
     // Independent host passes on their own threads: seam tables (one per attribute) next to the
@@ -375,17 +377,25 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
             if (early_uploads) { cuda_check(cudaSetDevice(ctx->device), "cudaSetDevice"); upload_seam_table(*ctx, i); c.lap("  (thread) seam table upload"); }
           }
           table_refs_[i] = table_ref(ut_, seams_[i - 1]);
+          if (seams_[i - 1].has_interior_seam) {  // the sequencer of this table runs: give it one array for opp()
+            const uint32_t C = ut_.num_corners;
+            U32Array& mo = masked_opposite_[i];
+            mo.resize(C);
+            const uint32_t* opp = ut_.opposite.data();
+            const uint8_t* sm = seams_[i - 1].seam.data();
+            for (uint32_t k = 0; k < C; ++k) mo[k] = sm[k] ? kNone : opp[k];
+            table_refs_[i].opposite_masked = mo.data();
+          }
           interior_[i] = vertex_interior_flags(table_refs_[i]);
           table_refs_[i].interior = interior_[i].data();
-          c.lap("  (thread) interior flags");
+          c.lap("  (thread) masked opposites, interior flags");
         }));
       table_refs_[0] = table_ref(ut_);
       tasks.push_back(std::async(std::launch::async, [this] { interior_[0] = vertex_interior_flags(table_refs_[0]); table_refs_[0].interior = interior_[0].data(); }));
       { StageClock c; eb.traverse(); c.lap("  (main) CLERS traversal"); }
-      corners_of_edgebreaker_ = eb.take_corners_of_edgebreaker();
       wait_all();  // seam tables, interior flags
       clk.lap("seam tables + traversal");
-      auto seq0 = std::async(std::launch::async, [this] { StageClock c; plans_[0].sequence = attribute_sequence(table_refs_[0], corners_of_edgebreaker_); c.lap("  (thread) position sequence"); });
+      auto seq0 = std::async(std::launch::async, [this] { StageClock c; plans_[0].sequence = attribute_sequence(table_refs_[0], eb_->corner_list()); c.lap("  (thread) position sequence"); });
       // an attribute whose only seams are mesh boundaries has the universal table (same ids, opposites, left-most
       // corners), hence the position sequence: it is copied instead of recomputed
       auto shares_position_sequence = [this](size_t i) {
@@ -394,7 +404,7 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
       };
       for (size_t i = 1; i < natt; ++i) {
         if (!shares_position_sequence(i))
-          tasks.push_back(std::async(std::launch::async, [this, i] { StageClock c; plans_[i].sequence = attribute_sequence(table_refs_[i], corners_of_edgebreaker_); c.lap("  (thread) attribute sequence"); }));
+          tasks.push_back(std::async(std::launch::async, [this, i] { StageClock c; plans_[i].sequence = attribute_sequence(table_refs_[i], eb_->corner_list()); c.lap("  (thread) attribute sequence"); }));
         tasks.push_back(std::async(std::launch::async, [this, i, &eb, &seam_bytes] { StageClock c; eb.write_seam_stream(seams_[i - 1], seam_bytes[i - 1]); c.lap("  (thread) seam stream"); }));
       }
       tasks.push_back(std::move(seq0));
@@ -846,7 +856,7 @@ void MeshJob::capture_host_trace() {
   put("corner_to_vertex", ut_.corner_vertex.data(), ut_.corner_vertex.size() * 4);
   put("left_most", ut_.left_most.data(), ut_.left_most.size() * 4);
   { uint64_t nv = ut_.num_vertices; put("num_vertices", &nv, 8); }
-  put("corners_of_edgebreaker", corners_of_edgebreaker_.data(), corners_of_edgebreaker_.size() * 4);
+  { const std::vector<uint32_t> all = eb_->corners_of_edgebreaker(); put("corners_of_edgebreaker", all.data(), all.size() * 4); }
   for (size_t i = 0; i < plans_.size(); ++i) {
     const std::string k = "att" + std::to_string(i) + ".";
     if (i > 0) {

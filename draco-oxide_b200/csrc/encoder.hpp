@@ -121,7 +121,8 @@ class MeshJob {
   std::vector<TableRef> table_refs_;
   std::vector<std::vector<uint8_t>> interior_;  // per table: vertex_interior_flags (helper threads, during the traversal)
   ByteSink head_;  // header + connectivity + attribute section headers
-  std::vector<uint32_t> corners_of_edgebreaker_;
+  std::unique_ptr<EdgebreakerEncoder> eb_;  // kept: owns the corner list the sequencers (and traces) read
+  std::vector<U32Array> masked_opposite_;   // per attribute table: opposite with seam edges removed (host sequencer)
   // device
   uint32_t *d_faces_ = nullptr, *d_opposite_ = nullptr, *d_corner_vertex_ = nullptr, *d_left_most_ = nullptr;
   uint4 *d_faces4_ = nullptr, *d_corner_vertex4_ = nullptr;
