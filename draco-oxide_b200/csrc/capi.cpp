@@ -149,7 +149,10 @@ int dxo_encode_batch(const dxo_mesh* meshes, size_t n, const dxo_config* cfg, dx
     std::atomic<size_t> next{0};
     std::vector<int> sts(n, DXO_OK);
     const char* env = getenv("DXO_WORKERS_PER_GPU");
-    int per_gpu = env ? atoi(env) : 3;  // host connectivity of one mesh overlaps device work of another
+    // Inside a worker the host passes of a mesh run on one thread, so the batch is host-bound: one worker per host
+    // thread (at least 3, at most 16 per GPU); their device work overlaps on the GPU.
+    const int hw = (int)std::thread::hardware_concurrency();
+    int per_gpu = env ? atoi(env) : std::min(16, std::max(3, hw / std::max(1, num_gpus)));
     if (per_gpu < 1) per_gpu = 1;
     const int workers = (int)std::min<size_t>((size_t)num_gpus * per_gpu, std::max<size_t>(n, 1));
     std::vector<std::thread> pool;
@@ -351,7 +354,7 @@ int dxo_encode_symbols(const uint32_t* symbols, uint64_t n, int device, dxo_byte
     cuda_check(cudaMemcpyAsync(&st, d_st, sizeof st, cudaMemcpyDeviceToHost, s), "D2H");
     cuda_check(cudaStreamSynchronize(s), "sync");
     if (kernel_ms) for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&kernel_ms[k], ev[k], ev[k + 1]);
-    if (getenv("DXO_RANS_DEBUG")) fprintf(stderr, "[dxo] rANS chunks=%u relaxed=%u fixup=%u\n", gpu::rans_num_chunks(n), st.pad[0], st.pad[1]);
+    if (getenv("DXO_RANS_DEBUG")) fprintf(stderr, "[dxo] rANS chunks=%u chain misses=%u fixup=%u\n", gpu::rans_num_chunks(n), st.pad[0], st.pad[1]);
     for (auto& e : ev) cudaEventDestroy(e);
     std::vector<uint8_t> tb(st.table_bytes), pay(st.payload_bytes);
     int status = DXO_OK;

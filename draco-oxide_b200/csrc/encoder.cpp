@@ -770,7 +770,7 @@ void MeshJob::download(DeviceContext& ctx) {
       AttrResult& r = results_[i];
       if (int st = status_from_flags(r.stats.error_flags)) throw Error(st, "device reported an encoding error");
       static const bool rans_debug = getenv("DXO_RANS_DEBUG") != nullptr;
-      if (rans_debug) fprintf(stderr, "[dxo] att %zu: rANS symbols=%llu P=%u K=%u chunks=%u relaxed=%u fixup=%u\n", i,
+      if (rans_debug) fprintf(stderr, "[dxo] att %zu: rANS symbols=%llu P=%u K=%u chunks=%u chain misses=%u fixup=%u\n", i,
                               (unsigned long long)sequence_of(i).size() * plans_[i].ncomp_q, r.stats.precision, r.stats.num_table_symbols,
                               gpu::rans_num_chunks((uint64_t)sequence_of(i).size() * plans_[i].ncomp_q), r.stats.pad[0], r.stats.pad[1]);
       if (r.stats.table_bytes > dev_[i].table_capacity || r.stats.payload_bytes > dev_[i].payload_capacity)

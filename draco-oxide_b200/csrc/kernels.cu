@@ -1000,7 +1000,7 @@ constexpr int kRansLookahead = 3;      // groups of symbols in flight in the pro
 struct RansPlan { uint32_t chunk, warmup; int rounds; };
 static RansPlan rans_plan() {
   static RansPlan plan = [] {
-    RansPlan p{8192, 16384, 3};
+    RansPlan p{4096, 1024, 0};
     if (const char* e = getenv("DXO_RANS_CHUNK")) p.chunk = (uint32_t)atoi(e);
     if (const char* e = getenv("DXO_RANS_WARMUP")) p.warmup = (uint32_t)atoi(e);
     if (const char* e = getenv("DXO_RANS_ROUNDS")) p.rounds = atoi(e);
@@ -1021,17 +1021,19 @@ struct RansShared {
   uint4 rows_a[kRansStages][32];
   uint4 rows_b[kRansStages][32];
   uint32_t xk[kRansStages][32];
-  uint32_t x_main, x_exit, nbytes, err;
+  uint32_t x_main[32], x_exit[32];  // per consumer lane: state at e_main / after the last step
+  uint32_t nbytes, err;
 };
 
-// Encodes steps [e_begin, e_end) of the stream (step e codes symbols[n - 1 - e]) starting
-// from state x_in; bytes are produced only for steps >= e_main (e_begin..e_main is the
+// Encodes steps [e_begin, e_end) of the stream (step e codes symbols[n - 1 - e]). Every consumer lane
+// carries its own state, starting from its x_in (lanes given the same x_in stay identical); with `emit`
+// the bytes of LANE 0's trajectory are produced for the steps >= e_main (e_begin..e_main is the
 // warm-up). All three bounds except e_end are multiples of 32. Called by a 64-thread CTA.
-// Results in sh.x_main (state at e_main), sh.x_exit, sh.nbytes after the final barrier.
+// Results in sh.x_main[lane] (state at e_main), sh.x_exit[lane], sh.nbytes after the final barrier.
 __device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t* __restrict__ symbols, unsigned long long n,
                                                   const uint4* __restrict__ table, uint32_t K, uint32_t P, unsigned long long e_begin,
                                                   unsigned long long e_main, unsigned long long e_end, uint32_t x_in, uint8_t* __restrict__ out,
-                                                  int bar_base, bool is_consumer) {
+                                                  int bar_base, bool is_consumer, bool emit = true) {
   const uint32_t lane = threadIdx.x & 31;
   const unsigned long long steps = e_end - e_begin;
   const unsigned long long ngroups = (steps + 31) / 32;
@@ -1043,7 +1045,7 @@ __device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t
     for (unsigned long long g = 0; g < ngroups; ++g) {
       const int s = (int)(g % kRansStages);
       const uint32_t cnt = (g + 1 == ngroups) ? (uint32_t)(steps - 32 * g) : 32u;
-      if (g == g_main && lane == 0) sh.x_main = x;
+      if (g == g_main) sh.x_main[lane] = x;
       named_bar_sync(bar_base + s);
       const uint32_t ra = (uint32_t)__cvta_generic_to_shared(&sh.rows_a[s][0]);
       const uint32_t rb = (uint32_t)__cvta_generic_to_shared(&sh.rows_b[s][0]);
@@ -1076,7 +1078,8 @@ __device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t
       }
       named_bar_arrive(bar_base + kRansStages + s);
     }
-    if (lane == 0) { sh.x_exit = x; if (g_main >= ngroups) sh.x_main = x; }
+    sh.x_exit[lane] = x;
+    if (g_main >= ngroups) sh.x_main[lane] = x;
   } else {
     // ------------------------------- producer / byte writer -----------------------------------
     uint32_t err = 0;
@@ -1105,7 +1108,7 @@ __device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t
       const int s = (int)(g % kRansStages);
       if (g >= kRansStages) {  // the stage is being reused: wait until the consumer is done with it, then write its bytes
         named_bar_sync(bar_base + kRansStages + s);
-        if (g - kRansStages >= g_main) emit_bytes(s, 32);
+        if (emit && g - kRansStages >= g_main) emit_bytes(s, 32);
       }
       const uint32_t sym = pre[0];
 #pragma unroll
@@ -1134,7 +1137,7 @@ __device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t
       const int s = (int)(g % kRansStages);
       const uint32_t cnt = (g + 1 == ngroups) ? (uint32_t)(steps - 32 * g) : 32u;
       named_bar_sync(bar_base + kRansStages + s);
-      if (g >= g_main) emit_bytes(s, cnt);
+      if (emit && g >= g_main) emit_bytes(s, cnt);
     }
     err = __reduce_or_sync(0xFFFFFFFFu, err);
     if (lane == 0) { sh.nbytes = pos; sh.err = err; }
@@ -1153,15 +1156,21 @@ __device__ __forceinline__ RansRole rans_role() {
   return r;
 }
 
-// chunk state arrays (device scratch): start[J] = entering state each chunk was last encoded from,
-// exit_a / exit_b[J] = exit states (double-buffered across rounds), nbytes[J].
-struct RansChunkState { uint32_t* start; uint32_t* exit_a; uint32_t* exit_b; uint32_t* nbytes; };
+// chunk state arrays (device scratch): start[J] = entering state each chunk was last encoded from, exit[J] = its exit
+// state, nbytes[J]; cand_start / cand_exit[32 J] = the candidate entering / exit states found by the exploration.
+struct RansChunkState { uint32_t* start; uint32_t* exit; uint32_t* nbytes; uint32_t* cand_start; uint32_t* cand_exit; };
 
 __host__ __device__ __forceinline__ uint64_t rans_chunk_capacity(uint32_t chunk) { return 3ull * chunk + 8; }
 
-// round 0: speculative encode of every chunk (two chunks per CTA)
-__global__ void __launch_bounds__(128) rans_speculate_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                             uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, uint32_t kRansWarmup, AttrStats* stats) {
+// 32 start states spread geometrically over the state interval [l_base, 256 l_base): lane -> l_base * 2^(lane / 4)
+__device__ __forceinline__ uint32_t rans_guess_state(uint32_t lane, uint32_t l_base) {
+  const uint32_t frac = (lane & 3u) == 0 ? 65536u : (lane & 3u) == 1 ? 77936u : (lane & 3u) == 2 ? 92682u : 110218u;  // 2^(k/4) in Q16
+  return (uint32_t)(((unsigned long long)l_base * frac) >> 16) << (lane >> 2);
+}
+
+// phase A — exploration (two chunks per CTA): no bytes, 32 candidate (entering state -> exit state) pairs per chunk
+__global__ void __launch_bounds__(128) rans_explore_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                           RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, uint32_t kRansWarmup, AttrStats* stats) {
   __shared__ RansShared sh2[2];
   if (stats->error_flags) return;
   const RansRole role = rans_role();
@@ -1169,23 +1178,88 @@ __global__ void __launch_bounds__(128) rans_speculate_kernel(const uint32_t* __r
   if (j >= num_chunks) return;  // both warps of the pair leave together
   RansShared& sh = sh2[role.pair];
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
+  const uint32_t lane = threadIdx.x & 31;
   const unsigned long long e_main = j * kRansChunk;
   const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
-  const unsigned long long e_begin = e_main > kRansWarmup ? e_main - kRansWarmup : 0;  // warm-up from step 0 is exact
+  const unsigned long long e_begin = e_main > kRansWarmup ? e_main - kRansWarmup : 0;
   const uint32_t l_base = 4u << P;
-  rans_encode_range(sh, symbols, n, table, K, P, e_begin, e_main, e_end, l_base, scratch + j * rans_chunk_capacity(kRansChunk), role.bar_base, role.is_consumer);
-  if (role.is_consumer && (threadIdx.x & 31) == 0) {
-    cs.start[j] = sh.x_main;
-    cs.exit_a[j] = sh.x_exit;
-    cs.nbytes[j] = sh.nbytes;
-    if (sh.err) atomicOr(&stats->error_flags, sh.err);
+  const uint32_t x_in = e_begin == 0 ? l_base : rans_guess_state(lane, l_base);  // a warm-up from step 0 is the true trajectory
+  rans_encode_range(sh, symbols, n, table, K, P, e_begin, e_main, e_end, x_in, nullptr, role.bar_base, role.is_consumer, false);
+  if (role.is_consumer) {
+    cs.cand_start[j * 32 + lane] = sh.x_main[lane];
+    cs.cand_exit[j * 32 + lane] = sh.x_exit[lane];
+    if (lane == 0 && sh.err) atomicOr(&stats->error_flags, sh.err);
   }
 }
 
-// round r >= 1: re-encode the chunks whose entering state does not match the predecessor's exit
-__global__ void __launch_bounds__(128) rans_relax_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                         uint8_t* __restrict__ scratch, RansChunkState cs, const uint32_t* __restrict__ exit_cur,
-                                                         uint32_t* __restrict__ exit_next, uint32_t num_chunks, uint32_t kRansChunk, AttrStats* stats) {
+// phase B — the chain (one warp pair): walks the chunks in order carrying the TRUE state. A chunk whose candidates contain
+// it (one ballot) hands over the matching exit state; otherwise (rare: every trajectory of the exploration missed) the
+// chunk is run from the true state right here. The candidate rows go through shared memory in tiles of 32 chunks; the
+// next tile's global loads are in flight while the current tile is walked.
+constexpr int kChainTile = 32;
+__global__ void __launch_bounds__(64) rans_chain_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                        RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, AttrStats* stats) {
+  __shared__ RansShared sh;
+  __shared__ uint32_t tile_s[2][kChainTile][32], tile_e[2][kChainTile][32];
+  if (stats->error_flags) return;
+  const uint32_t P = stats->precision, K = stats->num_table_symbols;
+  const uint32_t lane = threadIdx.x & 31, half = threadIdx.x >> 5;
+  const bool is_consumer = threadIdx.x < 32;
+  uint32_t s = 4u << P;
+  uint32_t misses = 0;
+  constexpr int kRowsPerThread = kChainTile / 2;  // the two warps split the rows of a tile
+  uint32_t reg_s[kRowsPerThread], reg_e[kRowsPerThread];
+  auto fetch = [&](uint32_t tile) {
+#pragma unroll
+    for (int r = 0; r < kRowsPerThread; ++r) {
+      const size_t j = (size_t)tile * kChainTile + 2 * r + half;
+      const bool in = j < num_chunks;
+      reg_s[r] = in ? __ldcs(cs.cand_start + j * 32 + lane) : 0u;
+      reg_e[r] = in ? __ldcs(cs.cand_exit + j * 32 + lane) : 0u;
+    }
+  };
+  auto park = [&](int buf) {
+#pragma unroll
+    for (int r = 0; r < kRowsPerThread; ++r) { tile_s[buf][2 * r + half][lane] = reg_s[r]; tile_e[buf][2 * r + half][lane] = reg_e[r]; }
+  };
+  const uint32_t num_tiles = (num_chunks + kChainTile - 1) / kChainTile;
+  fetch(0);
+  park(0);
+  __syncthreads();
+  for (uint32_t t = 0; t < num_tiles; ++t) {
+    const int buf = (int)(t & 1);
+    if (t + 1 < num_tiles) fetch(t + 1);
+    const uint32_t j_end = min(num_chunks - t * kChainTile, (uint32_t)kChainTile);
+    uint32_t cand_s = tile_s[buf][0][lane], cand_e = tile_e[buf][0][lane];
+    for (uint32_t r = 0; r < j_end; ++r) {
+      const uint32_t j = t * kChainTile + r;
+      const uint32_t next_s = r + 1 < j_end ? tile_s[buf][r + 1][lane] : 0u, next_e = r + 1 < j_end ? tile_e[buf][r + 1][lane] : 0u;
+      if (threadIdx.x == 0) cs.start[j] = s;
+      // lanes whose candidate matches hold the same trajectory, hence the same exit state: one OR-reduction hands it
+      // over (states are >= l_base > 0, so 0 means that no lane matched)
+      const uint32_t hit = __reduce_or_sync(0xFFFFFFFFu, cand_s == s ? cand_e : 0u);
+      if (hit) {
+        s = hit;
+      } else {  // both warps see the same values and take this branch together
+        const unsigned long long e_main = (unsigned long long)j * kRansChunk;
+        const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
+        rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, s, nullptr, 1, is_consumer, false);
+        s = sh.x_exit[0];
+        ++misses;
+        __syncthreads();  // sh is rewritten by the next miss
+      }
+      cand_s = next_s; cand_e = next_e;
+    }
+    __syncthreads();  // everyone is done with buf^1's previous contents (tile t-1) ... and with this tile before it is overwritten
+    if (t + 1 < num_tiles) park(buf ^ 1);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) stats->pad[0] = misses;  // chunks whose true state matched no candidate
+}
+
+// phase C — every chunk is encoded once from its true entering state (two chunks per CTA)
+__global__ void __launch_bounds__(128) rans_encode_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                          uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, AttrStats* stats) {
   __shared__ RansShared sh2[2];
   if (stats->error_flags) return;
   const RansRole role = rans_role();
@@ -1193,33 +1267,38 @@ __global__ void __launch_bounds__(128) rans_relax_kernel(const uint32_t* __restr
   if (j >= num_chunks) return;
   RansShared& sh = sh2[role.pair];
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
-  const uint32_t l_base = 4u << P;
-  const uint32_t in = j == 0 ? l_base : exit_cur[j - 1];
-  if (in == cs.start[j]) { if (role.is_consumer && (threadIdx.x & 31) == 0) exit_next[j] = exit_cur[j]; return; }  // pair-uniform
+  const uint32_t in = j == 0 ? (4u << P) : cs.start[j];
   const unsigned long long e_main = j * kRansChunk;
   const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
   rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, in, scratch + j * rans_chunk_capacity(kRansChunk), role.bar_base, role.is_consumer);
   if (role.is_consumer && (threadIdx.x & 31) == 0) {
     cs.start[j] = in;
-    exit_next[j] = sh.x_exit;
+    cs.exit[j] = sh.x_exit[0];
     cs.nbytes[j] = sh.nbytes;
-    atomicAdd(&stats->pad[0], 1u);  // chunks re-encoded in relaxation rounds
     if (sh.err) atomicOr(&stats->error_flags, sh.err);
   }
 }
 
-// sequential fix-up (one CTA of one pair): guarantees exactness whatever the speculation did
+// phase D — verification and fix-up (one CTA of one pair). The stream is exact iff every chunk was encoded from the exit
+// state of its predecessor; that is checked in parallel, and only a violated link (which the chain makes impossible unless
+// something upstream went wrong) starts the sequential repair, so exactness never rests on the speculation.
 __global__ void __launch_bounds__(64) rans_fixup_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                        uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t* __restrict__ exit_final,
-                                                        uint32_t num_chunks, uint32_t kRansChunk, AttrStats* stats) {
+                                                        uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk,
+                                                        AttrStats* stats) {
   __shared__ RansShared sh;
-  __shared__ uint32_t s_in;
+  __shared__ uint32_t s_in, s_bad;
   if (stats->error_flags) return;
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
   const uint32_t l_base = 4u << P;
   const bool is_consumer = threadIdx.x < 32;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  for (uint32_t j = threadIdx.x; j < num_chunks; j += blockDim.x)
+    if ((j == 0 ? l_base : cs.exit[j - 1]) != cs.start[j]) s_bad = 1;
+  __syncthreads();
+  if (!s_bad) return;
   for (uint32_t j = 0; j < num_chunks; ++j) {
-    if (threadIdx.x == 0) s_in = j == 0 ? l_base : exit_final[j - 1];
+    if (threadIdx.x == 0) s_in = j == 0 ? l_base : cs.exit[j - 1];
     __syncthreads();
     const uint32_t in = s_in;
     __syncthreads();                  // s_in is rewritten by thread 0 in the next iteration
@@ -1229,7 +1308,7 @@ __global__ void __launch_bounds__(64) rans_fixup_kernel(const uint32_t* __restri
     rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, in, scratch + (unsigned long long)j * rans_chunk_capacity(kRansChunk), 1, is_consumer);
     if (threadIdx.x == 0) {
       cs.start[j] = in;
-      exit_final[j] = sh.x_exit;
+      cs.exit[j] = sh.x_exit[0];
       cs.nbytes[j] = sh.nbytes;
       stats->pad[1] += 1;  // chunks re-encoded by the sequential fix-up
       if (sh.err) atomicOr(&stats->error_flags, sh.err);
@@ -1239,8 +1318,8 @@ __global__ void __launch_bounds__(64) rans_fixup_kernel(const uint32_t* __restri
 }
 
 // gather: chunk j's bytes go to payload[sum_{i<j} nbytes[i]]; the last CTA appends the flush bytes
-__global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restrict__ scratch, RansChunkState cs, const uint32_t* __restrict__ exit_final,
-                                                          uint32_t num_chunks, uint32_t kRansChunk, uint8_t* __restrict__ out, AttrStats* stats) {
+__global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk,
+                                                          uint8_t* __restrict__ out, AttrStats* stats) {
   __shared__ uint32_t s_part[8];
   __shared__ uint32_t s_off;
   if (stats->error_flags) { if (blockIdx.x == 0 && threadIdx.x == 0) stats->payload_bytes = 0; return; }
@@ -1258,7 +1337,7 @@ __global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restr
   if (j + 1 == num_chunks && threadIdx.x == 0) {
     uint32_t pos = off + nb, err = 0;
     const uint32_t l_base = 4u << stats->precision;
-    const uint32_t t = exit_final[j] - l_base;  // flush (:48-68)
+    const uint32_t t = cs.exit[j] - l_base;  // flush (:48-68)
     if (t < (1u << 6)) { out[pos++] = (uint8_t)t; }
     else if (t < (1u << 14)) { const uint32_t v = 0x4000u + t; out[pos++] = (uint8_t)v; out[pos++] = (uint8_t)(v >> 8); }
     else if (t < (1u << 22)) { const uint32_t v = 0x800000u + t; out[pos++] = (uint8_t)v; out[pos++] = (uint8_t)(v >> 8); out[pos++] = (uint8_t)(v >> 16); }
@@ -1272,7 +1351,7 @@ __global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restr
 uint32_t rans_num_chunks(uint64_t num_symbols) { const uint32_t c = rans_plan().chunk; return (uint32_t)((num_symbols + c - 1) / c); }
 size_t rans_scratch_bytes(uint64_t num_symbols) {
   const size_t J = rans_num_chunks(num_symbols);
-  return J * rans_chunk_capacity(rans_plan().chunk) + 256 + 4 * J * sizeof(uint32_t) + 64;
+  return J * rans_chunk_capacity(rans_plan().chunk) + 256 + (3 + 64) * J * sizeof(uint32_t) + 64;
 }
 
 void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, void* scratch, uint8_t* payload,
@@ -1282,20 +1361,16 @@ void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uin
   uint8_t* bytes = (uint8_t*)scratch;
   size_t off = ((size_t)J * rans_chunk_capacity(plan.chunk) + 255) / 256 * 256;
   uint32_t* u = (uint32_t*)(bytes + off);
-  RansChunkState cs{u, u + J, u + 2 * (size_t)J, u + 3 * (size_t)J};
-  rans_speculate_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, plan.warmup, stats);
-  uint32_t* cur = cs.exit_a;
-  uint32_t* nxt = cs.exit_b;
+  RansChunkState cs{u, u + J, u + 2 * (size_t)J, u + 3 * (size_t)J, u + 35 * (size_t)J};
   if (J > 1) {
-    for (int r = 0; r < plan.rounds; ++r) {
-      rans_relax_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, cur, nxt, J, plan.chunk, stats);
-      uint32_t* t = cur; cur = nxt; nxt = t;
-    }
-    rans_fixup_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, cur, J, plan.chunk, stats);
+    rans_explore_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, plan.warmup, stats);
+    rans_chain_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, stats);
   }
-  rans_gather_kernel<<<J, 256, 0, s>>>(bytes, cs, cur, J, plan.chunk, payload, stats);
+  rans_encode_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, stats);
+  if (J > 1) rans_fixup_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, stats);
+  rans_gather_kernel<<<J, 256, 0, s>>>(bytes, cs, J, plan.chunk, payload, stats);
 }
-int rans_launch_count(uint64_t num_symbols) { return rans_num_chunks(num_symbols) > 1 ? 3 + rans_plan().rounds : 2; }
+int rans_launch_count(uint64_t num_symbols) { return rans_num_chunks(num_symbols) > 1 ? 5 : 2; }
 
 // ---------------------------------------------------------------------------------------
 // K12 — CornerTable::compute_table (corner_table/mod.rs:252-340) for the manifold,

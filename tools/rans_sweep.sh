@@ -1,10 +1,10 @@
 #!/bin/bash
-# sweeps the speculative rANS parameters on the GPU box: a synthetic geometric stream (tools/rans_bench.py)
-# and the three attribute streams of config 2 (tools/step_timing.py prints the device step time)
-for cfg in "256 2048 4" "256 4096 4" "256 8192 4" "512 4096 4" "512 8192 4" "1024 8192 4" "1024 16384 4" "256 4096 16" "512 8192 16" "2048 16384 4"; do
+# sweeps the chunk length / exploration warm-up of K10 on the GPU box: a synthetic geometric stream (tools/rans_bench.py)
+# and the three attribute streams of config 2 (tools/rans_config2.py prints K10 per attribute and the step time)
+for cfg in "4096 1024" "4096 512" "2048 1024" "2048 512" "1024 512" "8192 1024" "3072 768" "6144 1024"; do
   set -- $cfg
-  export DXO_RANS_DEBUG=1 DXO_RANS_CHUNK=$1 DXO_RANS_WARMUP=$2 DXO_RANS_ROUNDS=$3
-  echo "== chunk=$1 warmup=$2 rounds=$3"
+  export DXO_RANS_DEBUG=1 DXO_RANS_CHUNK=$1 DXO_RANS_WARMUP=$2
+  echo "== chunk=$1 warmup=$2"
   python tools/rans_bench.py 3000000 2 2>&1 | tail -2 | tr '\n' ' ' | sed 's/n=3000000 bytes=[0-9]* //'; echo
-  python tools/rans_config2.py 2>&1 | grep -E "att [0-9]|K10|step" | sort | uniq -c | sort -rn | head -8
+  python tools/rans_config2.py 2>&1 | grep -E "att [0-9]|K10|step" | sort | uniq -c | sort -rn | head -5
 done
