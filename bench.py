@@ -41,8 +41,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config2_small"])
-    ap.add_argument("--sessions", type=int, default=3,
-                    help="concurrent resident sessions per GPU for `value` (the batch entry dxo_encode_batch runs 3 workers per GPU)")
+    ap.add_argument("--sessions", type=int, default=0,
+                    help="concurrent resident sessions per GPU for `value`; 0 = one per three host threads available to this GPU, "
+                         "at most 6 (each session keeps a main thread and two side-stream coders busy)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -199,7 +200,7 @@ def main():
     # `value`: S sessions (one host thread each, own CUDA streams) encode the resident mesh concurrently, the way the
     # batch entry keeps a GPU busy: the serial rANS chains and the host-coded side streams of one mesh overlap with
     # the kernels of the others. A step = one pass of every session; every pass produces the complete Draco stream.
-    S = max(1, args.sessions)
+    S = args.sessions if args.sessions > 0 else max(1, min(6, (os.cpu_count() or 3) // (3 * max(1, world))))
     sessions, results, errors = [None] * S, [None] * S, []
     ready, go = threading.Barrier(S + 1), threading.Barrier(S + 1)
 

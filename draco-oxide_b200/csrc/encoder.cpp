@@ -683,6 +683,9 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
         prof.end(s);
         break;
     }
+    prof.begin("K8_histogram", 4 * S, s);
+    gpu::launch_histogram(d.symbols, S, d.hist, p.hist_capacity, d.stats, s);
+    prof.end(s);
     if (side_ready_[i]) {  // flags leave for the host as soon as the predictor is done; the host codes them during K8-K10
       uint8_t* host = ctx.pinned_buffer(2 * i + 1, M);
       cuda_check(cudaEventRecord(side_ready_[i], s), "cudaEventRecord");
@@ -691,9 +694,6 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
       cuda_check(cudaEventRecord(side_copied_[i], ctx.copy_stream), "cudaEventRecord");
       d2h_bytes += M;
     }
-    prof.begin("K8_histogram", 4 * S, s);
-    gpu::launch_histogram(d.symbols, S, d.hist, p.hist_capacity, d.stats, s);
-    prof.end(s);
     prof.begin("K9_build_table", 4ull * p.hist_capacity, s);
     gpu::launch_build_table(d.hist, p.hist_capacity, S, d.work, d.rans_table, d.table_bytes, d.table_capacity, d.stats, s);
     prof.end(s);
