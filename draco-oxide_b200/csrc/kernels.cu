@@ -996,11 +996,13 @@ constexpr int kRansStages = 3;        // 2 pairs x (3 FULL + 3 EMPTY + 1 END) na
 constexpr int kRansLookahead = 3;      // groups of symbols in flight in the producer's registers
 // steps per chunk / speculative warm-up steps (multiples of 32) / parallel relaxation rounds before
 // the sequential fix-up. Defaults tuned on B200 (profiles/); DXO_RANS_CHUNK, DXO_RANS_WARMUP and
-// DXO_RANS_ROUNDS override them for experiments. Correctness never depends on these values.
-struct RansPlan { uint32_t chunk, warmup; int rounds; };
+// DXO_RANS_ROUNDS override them for experiments. Correctness never depends on these values; DXO_RANS_FAULT=1 makes the
+// chain kernel deliberately record a wrong entering state for every fifth chunk (tests of the fix-up path).
+struct RansPlan { uint32_t chunk, warmup; int rounds; int fault; };
 static RansPlan rans_plan() {
   static RansPlan plan = [] {
-    RansPlan p{4096, 1024, 0};
+    RansPlan p{4096, 1024, 0, 0};
+    if (const char* e = getenv("DXO_RANS_FAULT")) p.fault = atoi(e);  // tests: the chain hands out wrong states, the fix-up must repair
     if (const char* e = getenv("DXO_RANS_CHUNK")) p.chunk = (uint32_t)atoi(e);
     if (const char* e = getenv("DXO_RANS_WARMUP")) p.warmup = (uint32_t)atoi(e);
     if (const char* e = getenv("DXO_RANS_ROUNDS")) p.rounds = atoi(e);
@@ -1198,7 +1200,7 @@ __global__ void __launch_bounds__(128) rans_explore_kernel(const uint32_t* __res
 // next tile's global loads are in flight while the current tile is walked.
 constexpr int kChainTile = 32;
 __global__ void __launch_bounds__(64) rans_chain_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                        RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, AttrStats* stats) {
+                                                        RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, int inject_fault, AttrStats* stats) {
   __shared__ RansShared sh;
   __shared__ uint32_t tile_s[2][kChainTile][32], tile_e[2][kChainTile][32];
   if (stats->error_flags) return;
@@ -1234,7 +1236,7 @@ __global__ void __launch_bounds__(64) rans_chain_kernel(const uint32_t* __restri
     for (uint32_t r = 0; r < j_end; ++r) {
       const uint32_t j = t * kChainTile + r;
       const uint32_t next_s = r + 1 < j_end ? tile_s[buf][r + 1][lane] : 0u, next_e = r + 1 < j_end ? tile_e[buf][r + 1][lane] : 0u;
-      if (threadIdx.x == 0) cs.start[j] = s;
+      if (threadIdx.x == 0) cs.start[j] = (inject_fault && j % 5 == 2) ? rans_guess_state(j & 31, 4u << P) : s;
       // lanes whose candidate matches hold the same trajectory, hence the same exit state: one OR-reduction hands it
       // over (states are >= l_base > 0, so 0 means that no lane matched)
       const uint32_t hit = __reduce_or_sync(0xFFFFFFFFu, cand_s == s ? cand_e : 0u);
@@ -1364,7 +1366,7 @@ void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uin
   RansChunkState cs{u, u + J, u + 2 * (size_t)J, u + 3 * (size_t)J, u + 35 * (size_t)J};
   if (J > 1) {
     rans_explore_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, plan.warmup, stats);
-    rans_chain_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, stats);
+    rans_chain_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, plan.fault, stats);
   }
   rans_encode_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, stats);
   if (J > 1) rans_fixup_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, stats);

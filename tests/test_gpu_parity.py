@@ -284,3 +284,43 @@ def test_large_grid_with_uv_seam_line(orc):
     m = dxo.Mesh(faces, atts)
     assert m.faces.shape[0] >= 4096
     assert_stage_parity(orc, m)
+
+
+# ---- K10 off its tuned operating point: the paths that the default parameters almost never take -------------------
+_K10_CHILD = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+import draco_oxide_b200 as dxo, orc
+from draco_oxide_b200 import synth
+orc.build()
+m = synth.grid_mesh(120, 130, 77)
+out = bytearray(); dxo.encode(m, out)
+assert bytes(out) == orc.encode(m), "mesh stream differs"
+rng = np.random.default_rng(5)
+for n, gen in [(200_000, lambda: np.minimum(rng.geometric(0.08, 200_000) - 1, 4000)), (50_001, lambda: rng.integers(0, 3, 50_001)),
+               (33, lambda: rng.integers(0, 900, 33)), (100_000, lambda: rng.integers(0, 70_000, 100_000))]:
+    sym = gen().astype(np.uint32)
+    assert dxo.encode_symbols(sym) == orc.encode_symbols(sym), n
+print("ok")
+"""
+
+
+@pytest.mark.parametrize("env", [
+    {"DXO_RANS_CHUNK": "64", "DXO_RANS_WARMUP": "0"},       # no warm-up: almost every chunk misses in the chain and is run there
+    {"DXO_RANS_CHUNK": "32", "DXO_RANS_WARMUP": "32"},      # smallest chunks, thousands of them
+    {"DXO_RANS_CHUNK": "256", "DXO_RANS_WARMUP": "64", "DXO_RANS_FAULT": "1"},  # wrong entering states: the fix-up must repair
+    {"DXO_RANS_CHUNK": "1048576", "DXO_RANS_WARMUP": "1024"},  # a single chunk: the sequential coder
+])
+def test_rans_paths_off_the_operating_point(env):
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ); e.update(env); e["DXO_RANS_DEBUG"] = "1"
+    r = subprocess.run([sys.executable, "-c", _K10_CHILD.format(root=root)], env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
+    import re
+    misses = sum(int(x) for x in re.findall(r"chain misses=(\d+)", r.stderr))
+    fixups = sum(int(x) for x in re.findall(r"fixup=(\d+)", r.stderr))
+    if env.get("DXO_RANS_WARMUP") == "0":
+        assert misses > 100, "the chain's run-from-the-true-state path was not exercised"
+    if "DXO_RANS_FAULT" in env:
+        assert fixups > 100, "the sequential fix-up was not exercised"
