@@ -59,6 +59,15 @@ DeviceContext& DeviceContext::get(int device) {
   return ref;
 }
 
+DeviceContext::~DeviceContext() {
+  // Errors are ignored: at process exit the CUDA runtime may already be gone when the main thread's context is destroyed.
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return; }
+  for (cudaStream_t s : {stream[0], stream[1], stream[2], copy_stream, upload_stream}) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+  for (cudaEvent_t e : {ev_begin, ev_end, ev_pos_ready, ev_layout, ev_join[0], ev_join[1], ev_join[2], ev_uploaded, ev_inputs, ev_serial}) if (e) cudaEventDestroy(e);
+  for (auto& b : pinned) if (b.first) cudaFreeHost(b.first);
+  cudaGetLastError();
+}
+
 uint8_t* DeviceContext::pinned_buffer(size_t slot, size_t bytes) {
   if (pinned.size() <= slot) pinned.resize(slot + 1, {nullptr, 0});
   auto& b = pinned[slot];

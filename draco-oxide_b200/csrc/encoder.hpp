@@ -28,6 +28,10 @@ struct DeviceContext {
   uint8_t* pinned_buffer(size_t slot, size_t bytes);
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_pos_ready = nullptr, ev_layout = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   static DeviceContext& get(int device);  // thread-local; throws DXO_ERR_NO_DEVICE when there is no usable GPU
+  DeviceContext() = default;
+  DeviceContext(const DeviceContext&) = delete;
+  DeviceContext& operator=(const DeviceContext&) = delete;
+  ~DeviceContext();  // runs when the owning thread exits (batch workers): streams, events and staging buffers are released
 };
 
 struct KernelRecord { const char* name; uint64_t bytes; cudaEvent_t a, b; };
