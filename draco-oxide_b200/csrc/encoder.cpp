@@ -708,7 +708,7 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     prof.end(s);
     prof.begin("K10_rans_encode", 4 * S, s);
     gpu::launch_rans_encode(d.symbols, S, d.rans_table, d.rans_scratch, d.payload, d.stats, s);
-    prof.launches += gpu::rans_launch_count(S) - 1;  // speculate + relax rounds + fix-up + gather
+    prof.launches += gpu::rans_launch_count(S) - 1;  // explore + chain + encode + fix-up + gather
     prof.end(s);
     if (prof.serial) cuda_check(cudaEventRecord(ctx.ev_serial, s), "cudaEventRecord");
   }

@@ -960,23 +960,26 @@ void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t t
 // K10 — RansCoder::write / flush (rans.rs:33-68), symbols fed last-to-first
 // (symbol_coding.rs:161).
 //
-// The state recurrence x -> x' is serial, but it FORGETS: two encoders that start from
-// different states and see the same symbols end up in exactly the same state after a
-// few hundred to a few thousand symbols (every renormalisation shifts the low state
-// bits — where small differences live — out into the byte stream). That makes an exact
-// speculative-parallel coder possible (DESIGN.md "Parallel rANS"):
-//   round 0   every chunk of kRansChunk steps is encoded by its own CTA, starting W
-//             steps early from an arbitrary state (warm-up); the state reached at the
-//             chunk start is the chunk's *claimed* entering state.
-//   round r   a chunk whose claimed entering state differs from the exit state of its
-//             predecessor is re-encoded from that exit state (Jacobi relaxation; after
-//             round r chunks 0..r are certainly right, typically 1-2 rounds fix all).
-//   fix-up    a single CTA walks the chunks in order and re-encodes any that is still
-//             inconsistent, so the result never depends on the speculation succeeding.
+// The state recurrence x -> x' is serial, but it FORGETS: two encoders that see the same
+// symbols from different states end up in exactly the same state — slowly from an arbitrary
+// state, within a few hundred steps from a NEARBY one (every renormalisation shifts the low
+// state bits, where small differences live, out into the byte stream). That makes an exact
+// speculative-parallel coder possible (DESIGN.md "Parallel rANS"; tools/rans_merge_sim.py):
+//   explore   the stream is cut into chunks of C steps. For every chunk a warp runs 32
+//             trajectories (one per lane, states spread geometrically over the whole state
+//             interval) through the same symbols, starting W steps before the chunk; each lane
+//             records its state at the chunk start and at the chunk end. No bytes.
+//   chain     one warp walks the chunks carrying the TRUE state (chunk 0: l_base): the lane
+//             whose recorded entering state equals it hands over its exit state; a chunk with
+//             no such lane (rare) is run from the true state on the spot.
+//   encode    every chunk is encoded once from its true entering state.
+//   fix-up    checks in parallel that every chunk was encoded from its predecessor's exit
+//             state and repairs sequentially otherwise, so the result never depends on the
+//             speculation succeeding.
 //   gather    chunk byte strings are concatenated (prefix sum of their lengths) and the
 //             2-bit-tagged final state is appended.
 // The bytes are those of the sequential coder by construction: chunk 0 starts from
-// l_base and every other chunk is (re-)encoded from its predecessor's true exit state.
+// l_base and every other chunk is encoded from its predecessor's true exit state.
 //
 // Inside a chunk, one CTA of two warps works as producer / consumer:
 //   * PRODUCER warp: prefetches symbols several groups ahead (coalesced), gathers their
@@ -994,21 +997,19 @@ void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t t
 // Stages are handed over with named barriers (bar.arrive / bar.sync), one pair per stage.
 constexpr int kRansStages = 3;        // 2 pairs x (3 FULL + 3 EMPTY + 1 END) named barriers = 14 of the 15 available
 constexpr int kRansLookahead = 3;      // groups of symbols in flight in the producer's registers
-// steps per chunk / speculative warm-up steps (multiples of 32) / parallel relaxation rounds before
-// the sequential fix-up. Defaults tuned on B200 (profiles/); DXO_RANS_CHUNK, DXO_RANS_WARMUP and
-// DXO_RANS_ROUNDS override them for experiments. Correctness never depends on these values; DXO_RANS_FAULT=1 makes the
-// chain kernel deliberately record a wrong entering state for every fifth chunk (tests of the fix-up path).
-struct RansPlan { uint32_t chunk, warmup; int rounds; int fault; };
+// steps per chunk / warm-up steps of the exploration (multiples of 32). Defaults tuned on B200 (profiles/);
+// DXO_RANS_CHUNK and DXO_RANS_WARMUP override them for experiments. Correctness never depends on these values;
+// DXO_RANS_FAULT=1 makes the chain kernel deliberately record a wrong entering state for every fifth chunk
+// (tests of the fix-up path).
+struct RansPlan { uint32_t chunk, warmup; int fault; };
 static RansPlan rans_plan() {
   static RansPlan plan = [] {
-    RansPlan p{4096, 1024, 0, 0};
+    RansPlan p{4096, 1024, 0};
     if (const char* e = getenv("DXO_RANS_FAULT")) p.fault = atoi(e);  // tests: the chain hands out wrong states, the fix-up must repair
     if (const char* e = getenv("DXO_RANS_CHUNK")) p.chunk = (uint32_t)atoi(e);
     if (const char* e = getenv("DXO_RANS_WARMUP")) p.warmup = (uint32_t)atoi(e);
-    if (const char* e = getenv("DXO_RANS_ROUNDS")) p.rounds = atoi(e);
     p.chunk = (p.chunk < 32 ? 32 : p.chunk) / 32 * 32;
     p.warmup = p.warmup / 32 * 32;
-    if (p.rounds < 0) p.rounds = 0;
     return p;
   }();
   return plan;
