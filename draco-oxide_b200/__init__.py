@@ -28,11 +28,14 @@ class Config:
     """encode::Config: only `default()` exists in the reference. Quantization bit
     counts are exposed for the qp sweep; only 11/10 is reference behaviour."""
 
-    def __init__(self, position_bits=11, texcoord_bits=10, generic_bits=11, device=-1):
+    GRAPH_REPLAY = 1  # DXO_FLAG_GRAPH_REPLAY
+
+    def __init__(self, position_bits=11, texcoord_bits=10, generic_bits=11, device=-1, flags=0):
         self.position_bits = position_bits
         self.texcoord_bits = texcoord_bits
         self.generic_bits = generic_bits
         self.device = device
+        self.flags = flags
 
     @classmethod
     def default(cls):
@@ -45,6 +48,7 @@ class Config:
         c.texcoord_bits = self.texcoord_bits
         c.generic_bits = self.generic_bits
         c.device = self.device
+        c.flags = self.flags
         return c
 
 

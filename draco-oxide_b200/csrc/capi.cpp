@@ -51,14 +51,15 @@ void run_device_phase(MeshJob& job, DeviceContext& ctx, Profile& prof, std::vect
   prof.enabled = g_profiling.load() != 0;
   prof.serial = g_profiling.load() == 2;
   cudaStream_t s0 = ctx.stream[0];
+  // opt-in (DXO_FLAG_GRAPH_REPLAY); one-shot encodes, traced and profiled runs launch directly
+  const bool replay = job.graph_replay && !prof.enabled && !job.trace && job.device_runs >= 1;
+  ++job.device_runs;
+  const auto t_launch = Clock::now();
   cuda_check(cudaEventRecord(ctx.ev_begin, s0), "cudaEventRecord");
-  for (int k = 1; k < 3; ++k) cuda_check(cudaStreamWaitEvent(ctx.stream[k], ctx.ev_begin, 0), "cudaStreamWaitEvent");
-  job.launch(ctx, prof);
-  for (int k = 1; k < 3; ++k) {
-    cuda_check(cudaEventRecord(ctx.ev_join[k], ctx.stream[k]), "cudaEventRecord");
-    cuda_check(cudaStreamWaitEvent(s0, ctx.ev_join[k], 0), "cudaStreamWaitEvent");
-  }
+  if (replay) job.launch_graph(ctx, prof);
+  else job.launch_all(ctx, prof);
   cuda_check(cudaEventRecord(ctx.ev_end, s0), "cudaEventRecord");
+  const double launch_cpu_ms = ms_since(t_launch);
   if (prof.enabled) cuda_check(cudaEventSynchronize(ctx.ev_end), "cudaEventSynchronize");
   const auto t_d2h = Clock::now();
   job.download(ctx);
@@ -67,7 +68,9 @@ void run_device_phase(MeshJob& job, DeviceContext& ctx, Profile& prof, std::vect
   cuda_check(cudaEventElapsedTime(&tm.device_ms, ctx.ev_begin, ctx.ev_end), "cudaEventElapsedTime");
   const auto t_asm = Clock::now();
   job.assemble(bytes);
-  if (getenv("DXO_TIMING")) fprintf(stderr, "[dxo] device %.3f ms | download+side streams (wall) %.3f ms | assemble %.3f ms\n", tm.device_ms, tm.d2h_ms, ms_since(t_asm));
+  if (getenv("DXO_TIMING"))
+    fprintf(stderr, "[dxo] thread %zx: launch (cpu) %.3f ms | device %.3f ms | download+side streams (wall) %.3f ms | assemble %.3f ms\n",
+            (size_t)std::hash<std::thread::id>()(std::this_thread::get_id()) & 0xFFFF, launch_cpu_ms, tm.device_ms, tm.d2h_ms, ms_since(t_asm));
   tm.num_launches = prof.launches;
   tm.num_kernels = 0;
   for (const KernelRecord& r : prof.records) {
@@ -272,7 +275,9 @@ int dxo_session_run_steps(dxo_session* s, uint32_t steps, float* ms_total, uint6
     DeviceContext& ctx = DeviceContext::get(s->device);
     static thread_local cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     if (!ev_a) { cuda_check(cudaEventCreate(&ev_a), "cudaEventCreate"); cuda_check(cudaEventCreate(&ev_b), "cudaEventCreate"); }
+    const auto t_enter = Clock::now();
     for (int k = 0; k < 3; ++k) cuda_check(cudaStreamSynchronize(ctx.stream[k]), "cudaStreamSynchronize");
+    const double enter_ms = ms_since(t_enter);
     cuda_check(cudaEventRecord(ev_a, ctx.stream[0]), "cudaEventRecord");
     std::vector<uint8_t> bytes;
     uint64_t launches = 0;
@@ -281,9 +286,12 @@ int dxo_session_run_steps(dxo_session* s, uint32_t steps, float* ms_total, uint6
       run_device_phase(*s->job, ctx, g_profile, bytes, g_timing);
       launches += g_timing.num_launches;
     }
+    const auto t_exit = Clock::now();
     cuda_check(cudaEventRecord(ev_b, ctx.stream[0]), "cudaEventRecord");
     cuda_check(cudaEventSynchronize(ev_b), "cudaEventSynchronize");
     cuda_check(cudaEventElapsedTime(ms_total, ev_a, ev_b), "cudaEventElapsedTime");
+    if (getenv("DXO_TIMING")) fprintf(stderr, "[dxo] run_steps(%u): entry sync %.3f ms, steps %.3f ms, exit sync %.3f ms, events %.3f ms\n", steps, enter_ms,
+                                      ms_since(t_enter) - enter_ms - ms_since(t_exit), ms_since(t_exit), *ms_total);
     if (launches_total) *launches_total = launches;
   });
 }

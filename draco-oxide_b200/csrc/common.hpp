@@ -188,11 +188,28 @@ static inline void rabs_encode_forward(const uint8_t* bits, size_t n, uint8_t ze
   if (out.size() < n + 8) out.resize(n + 8);  // at most one byte per bit, plus the tail (capacity is kept across calls)
   uint8_t* p = out.data();
   uint32_t x = 4096u;
-  for (size_t i = 0; i < n; ++i) {
-    const uint32_t b = bits[i] != 0;
-    if (x >= thr[b]) { *p++ = (uint8_t)x; x >>= 8; }
-    const uint32_t q = (uint32_t)(((uint64_t)x * m[b]) >> 32);
-    x = x + q * g[b] + cum[b];
+  if (g[0] == 1u || g[1] == 1u) {
+    // One value has probability 255/256 (flags of smooth meshes): the loop branches on the bit (predictable) and
+    // the common case needs no second multiply, x' = x + q + cum. The chain per bit drops from ~10 to ~6 cycles.
+    const uint32_t common = g[0] == 1u ? 0u : 1u, rare = common ^ 1u;
+    const uint32_t thr_c = thr[common], cum_c = cum[common], thr_r = thr[rare], g_r = g[rare], cum_r = cum[rare];
+    const uint64_t m_c = m[common], m_r = m[rare];
+    for (size_t i = 0; i < n; ++i) {
+      if (__builtin_expect((uint32_t)(bits[i] != 0) == common, 1)) {
+        if (x >= thr_c) { *p++ = (uint8_t)x; x >>= 8; }
+        x = x + (uint32_t)(((uint64_t)x * m_c) >> 32) + cum_c;
+      } else {
+        if (x >= thr_r) { *p++ = (uint8_t)x; x >>= 8; }
+        x = x + (uint32_t)(((uint64_t)x * m_r) >> 32) * g_r + cum_r;
+      }
+    }
+  } else {
+    for (size_t i = 0; i < n; ++i) {
+      const uint32_t b = bits[i] != 0;
+      if (x >= thr[b]) { *p++ = (uint8_t)x; x >>= 8; }
+      const uint32_t q = (uint32_t)(((uint64_t)x * m[b]) >> 32);
+      x = x + q * g[b] + cum[b];
+    }
   }
   ByteSink tail;
   ans_write_tail(x - 4096u, tail);

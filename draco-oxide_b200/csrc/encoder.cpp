@@ -43,6 +43,11 @@ DeviceContext& DeviceContext::get(int device) {
   cuda_check(cudaEventCreateWithFlags(&c->ev_uploaded, cudaEventDisableTiming), "cudaEventCreate");
   cuda_check(cudaEventCreateWithFlags(&c->ev_inputs, cudaEventDisableTiming), "cudaEventCreate");
   cuda_check(cudaEventCreateWithFlags(&c->ev_serial, cudaEventDisableTiming), "cudaEventCreate");
+  cuda_check(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
+  cuda_check(cudaEventCreateWithFlags(&c->ev_copy_join, cudaEventDisableTiming), "cudaEventCreate");
+  const unsigned wait_flags = cudaEventDisableTiming | (getenv("DXO_BLOCKING_WAIT") ? (unsigned)cudaEventBlockingSync : 0u);
+  for (auto& ev : c->ev_block) cuda_check(cudaEventCreateWithFlags(&ev, wait_flags), "cudaEventCreate");
+  c->helpers.reset(new HelperThreads(2));
   cuda_check(cudaEventCreate(&c->ev_begin), "cudaEventCreate");
   cuda_check(cudaEventCreate(&c->ev_end), "cudaEventCreate");
   cuda_check(cudaEventCreateWithFlags(&c->ev_pos_ready, cudaEventDisableTiming), "cudaEventCreate");
@@ -57,29 +62,6 @@ DeviceContext& DeviceContext::get(int device) {
   DeviceContext& ref = *c;
   ctxs[device] = std::move(c);
   return ref;
-}
-
-DeviceContext::~DeviceContext() {
-  // Errors are ignored: at process exit the CUDA runtime may already be gone when the main thread's context is destroyed.
-  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return; }
-  for (cudaStream_t s : {stream[0], stream[1], stream[2], copy_stream, upload_stream}) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
-  for (cudaEvent_t e : {ev_begin, ev_end, ev_pos_ready, ev_layout, ev_join[0], ev_join[1], ev_join[2], ev_uploaded, ev_inputs, ev_serial}) if (e) cudaEventDestroy(e);
-  for (auto& b : pinned) if (b.first) cudaFreeHost(b.first);
-  cudaGetLastError();
-}
-
-uint8_t* DeviceContext::pinned_buffer(size_t slot, size_t bytes) {
-  if (pinned.size() <= slot) pinned.resize(slot + 1, {nullptr, 0});
-  auto& b = pinned[slot];
-  if (b.second < bytes) {
-    if (b.first) cudaFreeHost(b.first);
-    b = {nullptr, 0};
-    const size_t cap = bytes + bytes / 4 + 4096;
-    void* p = nullptr;
-    cuda_check(cudaHostAlloc(&p, cap, cudaHostAllocDefault), "cudaHostAlloc");
-    b = {(uint8_t*)p, cap};
-  }
-  return b.first;
 }
 
 // Process-wide pool of pinned host blocks (cudaHostAlloc is far too slow to call per mesh). Blocks are handed
@@ -115,6 +97,64 @@ struct PinnedPool {
 };
 PinnedPool& pinned_pool() { static PinnedPool* pool = new PinnedPool; return *pool; }  // never destroyed: outlives every job
 }  // namespace
+
+HelperThreads::HelperThreads(int n) { for (int i = 0; i < n; ++i) threads_.emplace_back([this] { loop(); }); }
+HelperThreads::~HelperThreads() {
+  { std::lock_guard<std::mutex> lock(mu_); stop_ = true; }
+  cv_.notify_all();
+  for (std::thread& t : threads_) t.join();
+}
+std::future<void> HelperThreads::run(std::function<void()> fn) {
+  std::packaged_task<void()> task(std::move(fn));
+  std::future<void> f = task.get_future();
+  { std::lock_guard<std::mutex> lock(mu_); queue_.push_back(std::move(task)); }
+  cv_.notify_one();
+  return f;
+}
+void HelperThreads::loop() {
+  for (;;) {
+    std::packaged_task<void()> task;
+    {
+      std::unique_lock<std::mutex> lock(mu_);
+      cv_.wait(lock, [this] { return stop_ || !queue_.empty(); });
+      if (queue_.empty()) return;
+      task = std::move(queue_.front());
+      queue_.pop_front();
+    }
+    task();
+  }
+}
+
+void DeviceContext::wait_stream(int k) {
+  cuda_check(cudaEventRecord(ev_block[k], stream[k]), "cudaEventRecord");
+  cuda_check(cudaEventSynchronize(ev_block[k]), "cudaEventSynchronize");
+}
+
+DeviceContext::~DeviceContext() {
+  helpers.reset();
+  // Errors are ignored: at process exit the CUDA runtime may already be gone when the main thread's context is destroyed.
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return; }
+  for (cudaStream_t s : {stream[0], stream[1], stream[2], copy_stream, upload_stream}) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+  for (cudaEvent_t e : {ev_begin, ev_end, ev_pos_ready, ev_layout, ev_join[0], ev_join[1], ev_join[2], ev_uploaded, ev_inputs, ev_serial, ev_fork, ev_copy_join, ev_block[0], ev_block[1], ev_block[2]}) if (e) cudaEventDestroy(e);
+  // staging buffers go back to the process-wide pool: cudaFreeHost synchronises the whole device and stalled every other
+  // thread's launches for hundreds of milliseconds when a worker thread ended while others were still encoding
+  for (auto& b : pinned) if (b.first) pinned_pool().give(b.first, b.second);
+  cudaGetLastError();
+}
+
+uint8_t* DeviceContext::pinned_buffer(size_t slot, size_t bytes) {
+  if (pinned.size() <= slot) pinned.resize(slot + 1, {nullptr, 0});
+  auto& b = pinned[slot];
+  if (b.second < bytes) {
+    if (b.first) pinned_pool().give(b.first, b.second);
+    b = {nullptr, 0};
+    size_t cap = 0;
+    void* p = pinned_pool().take(bytes + bytes / 4 + 4096, &cap);
+    if (!p) throw Error(DXO_ERR_OUT_OF_MEMORY, "pinned host allocation failed");
+    b = {(uint8_t*)p, cap};
+  }
+  return b.first;
+}
 
 void* MeshJob::pinned_source(void* user, size_t bytes) {
   MeshJob* job = (MeshJob*)user;
@@ -169,6 +209,7 @@ int status_from_flags(uint32_t f) {
 }  // namespace
 
 MeshJob::MeshJob(const dxo_mesh* mesh, const dxo_config& cfg) : mesh_(mesh), cfg_(cfg) {
+  graph_replay = (cfg.flags & DXO_FLAG_GRAPH_REPLAY) != 0;
   if (!mesh || (mesh->num_faces && !mesh->faces) || (mesh->num_attributes && !mesh->attributes))
     throw Error(DXO_ERR_INVALID_ARGUMENT, "null mesh / faces / attributes");
   if (mesh->num_faces == 0 || mesh->num_faces > 0x55555554ull) throw Error(DXO_ERR_INVALID_ARGUMENT, "face count must be in [1, 2^32/3)");
@@ -237,11 +278,17 @@ MeshJob::MeshJob(const dxo_mesh* mesh, const dxo_config& cfg) : mesh_(mesh), cfg
 }
 
 MeshJob::~MeshJob() {
+  if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+  if (ev_graph_done_) cudaEventDestroy(ev_graph_done_);
   if (inputs_upload_.valid()) { try { inputs_upload_.wait(); } catch (...) {} }  // error paths: let the helper finish before freeing
-  for (void* p : allocations_) cudaFreeAsync(p, alloc_stream_);  // normally released by release(); this covers error paths
+  // normally released by release(); this covers error paths. cudaFree (synchronising) rather than cudaFreeAsync: the
+  // stream the blocks were allocated on may belong to a thread that has exited
+  for (void* p : allocations_) cudaFree(p);
   if (!pinned_blocks_.empty()) {
-    // a copy into one of the blocks may still be in flight on an error path: the blocks go back only when the device is idle
-    if (alloc_stream_) cudaStreamSynchronize(alloc_stream_);
+    // Every copy into the blocks is synchronised by the pass that issued it; only an exception between the enqueue and
+    // that synchronisation leaves one in flight. The stream it ran on may belong to a thread that is gone by now, so
+    // the whole device is drained in that case.
+    if (pinned_copy_in_flight_.load()) cudaDeviceSynchronize();
     for (auto& b : pinned_blocks_) pinned_pool().give(b.first, b.second);
   }
   for (cudaEvent_t e : side_ready_) if (e) cudaEventDestroy(e);
@@ -293,6 +340,7 @@ uint32_t MeshJob::device_matcher(void* user, const uint32_t* corner_vertex, uint
   gpu::launch_boundary_list(d_opp, C, bscratch, bb, d_blist, d_flag + 2, s);
   uint32_t flag[3] = {1, 0, 0};
   if (clk.on) { cudaStreamSynchronize(s); clk.lap("    K12 + K13 kernels"); }
+  job->pinned_copy_in_flight_.fetch_add(1);
   cuda_check(cudaMemcpyAsync(flag, d_flag, 12, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
   const uint32_t prefix = (uint32_t)std::min<size_t>(kBoundaryPrefix, C);
   boundary_corners->resize(prefix);
@@ -304,6 +352,7 @@ uint32_t MeshJob::device_matcher(void* user, const uint32_t* corner_vertex, uint
   cuda_check(cudaFreeAsync(lscratch, s), "cudaFreeAsync");
   cuda_check(cudaFreeAsync(bscratch, s), "cudaFreeAsync");
   cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+  job->pinned_copy_in_flight_.fetch_sub(1);
   clk.lap("    K12 D2H opposite, left_most");
   uint32_t done = 0;
   if (flag[1] & 1u) done |= UniversalTable::kUnusedVertices;
@@ -513,10 +562,12 @@ bool MeshJob::device_seam_table(DeviceContext& ctx, size_t att) {
   st.corner_vertex.resize(C);
   st.seam.resize(C);
   st.left_most.resize(st.num_vertices);
+  pinned_copy_in_flight_.fetch_add(1);
   cuda_check(cudaMemcpyAsync(st.corner_vertex.data(), d_cv, C * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
   cuda_check(cudaMemcpyAsync(st.seam.data(), d_seam, C, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
   cuda_check(cudaMemcpyAsync(st.left_most.data(), d_lm, (size_t)st.num_vertices * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
   cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+  pinned_copy_in_flight_.fetch_sub(1);
   { std::lock_guard<std::mutex> lock(alloc_mu_); d2h_bytes += C * 5 + (size_t)st.num_vertices * 4; }
   d.corner_vertex = d_cv; d.seam = d_seam; d.left_most = d_lm;
   return true;
@@ -581,7 +632,7 @@ void MeshJob::upload(DeviceContext& ctx) {
   for (size_t i = 0; i < plans_.size(); ++i) {
     if (plans_[i].scheme != Scheme::Normal && plans_[i].scheme != Scheme::TexCoord) continue;
     cuda_check(cudaEventCreateWithFlags(&side_ready_[i], cudaEventDisableTiming), "cudaEventCreate");
-    cuda_check(cudaEventCreateWithFlags(&side_copied_[i], cudaEventDisableTiming), "cudaEventCreate");
+    cuda_check(cudaEventCreateWithFlags(&side_copied_[i], cudaEventDisableTiming | (getenv("DXO_BLOCKING_WAIT") ? (unsigned)cudaEventBlockingSync : 0u)), "cudaEventCreate");
   }
   uploaded_ = true;
 }
@@ -605,6 +656,62 @@ gpu::TableDev MeshJob::table_dev(size_t att) const {
 
 // Algorithmic bytes per launch follow SURVEY.md §8(d): each distinct input array read
 // once, each output written once.
+void MeshJob::launch_all(DeviceContext& ctx, Profile& prof, bool capturing) {
+  cudaStream_t s0 = ctx.stream[0];
+  cuda_check(cudaEventRecord(ctx.ev_fork, s0), "cudaEventRecord");
+  for (int k = 1; k < 3; ++k) cuda_check(cudaStreamWaitEvent(ctx.stream[k], ctx.ev_fork, 0), "cudaStreamWaitEvent");
+  capturing_ = capturing;
+  launch(ctx, prof);
+  capturing_ = false;
+  for (int k = 1; k < 3; ++k) {
+    cuda_check(cudaEventRecord(ctx.ev_join[k], ctx.stream[k]), "cudaEventRecord");
+    cuda_check(cudaStreamWaitEvent(s0, ctx.ev_join[k], 0), "cudaStreamWaitEvent");
+  }
+  bool any_side = false;
+  for (cudaEvent_t e : side_copied_) any_side |= e != nullptr;
+  if (any_side) {  // the copy stream took part (flag copies): it joins the origin stream as well
+    cuda_check(cudaEventRecord(ctx.ev_copy_join, ctx.copy_stream), "cudaEventRecord");
+    cuda_check(cudaStreamWaitEvent(s0, ctx.ev_copy_join, 0), "cudaStreamWaitEvent");
+  }
+}
+
+void MeshJob::launch_graph(DeviceContext& ctx, Profile& prof) {
+  cudaStream_t s0 = ctx.stream[0];
+  if (!graph_exec_ || graph_ctx_ != &ctx) {
+    if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+    // everything the captured sequence would allocate lazily exists before the capture starts
+    for (size_t i = 0; i < plans_.size(); ++i) if (side_ready_[i]) ctx.pinned_buffer(2 * i + 1, sequence_of(i).size());
+    if (!ev_graph_done_) cuda_check(cudaEventCreateWithFlags(&ev_graph_done_, cudaEventDisableTiming), "cudaEventCreate");
+    for (int k = 0; k < 3; ++k) cuda_check(cudaStreamSynchronize(ctx.stream[k]), "cudaStreamSynchronize");
+    cuda_check(cudaStreamSynchronize(ctx.copy_stream), "cudaStreamSynchronize");
+    cudaGraph_t graph = nullptr;
+    cuda_check(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+    try {
+      const uint64_t d2h_before = d2h_bytes;
+      launch_all(ctx, prof, true);
+      graph_d2h_bytes_ = d2h_bytes - d2h_before;
+    } catch (...) {
+      cudaStreamEndCapture(s0, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      throw;
+    }
+    cuda_check(cudaStreamEndCapture(s0, &graph), "cudaStreamEndCapture");
+    graph_launches_ = prof.launches;
+    const cudaError_t e = cudaGraphInstantiate(&graph_exec_, graph, 0);
+    cudaGraphDestroy(graph);
+    cuda_check(e, "cudaGraphInstantiate");
+    graph_ctx_ = &ctx;
+  } else {
+    d2h_bytes += graph_d2h_bytes_;
+  }
+  prof.launches = graph_launches_;
+  cuda_check(cudaGraphLaunch(graph_exec_, s0), "cudaGraphLaunch");
+  // later work on the attribute streams (result copies) is ordered after the graph
+  cuda_check(cudaEventRecord(ev_graph_done_, s0), "cudaEventRecord");
+  for (int k = 1; k < 3; ++k) cuda_check(cudaStreamWaitEvent(ctx.stream[k], ev_graph_done_, 0), "cudaStreamWaitEvent");
+}
+
 void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
   const uint64_t C = ut_.num_corners;
   const uint64_t Upos = plans_[0].view.num_unique;
@@ -700,7 +807,8 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
       cuda_check(cudaEventRecord(side_ready_[i], s), "cudaEventRecord");
       cuda_check(cudaStreamWaitEvent(ctx.copy_stream, side_ready_[i], 0), "cudaStreamWaitEvent");
       cuda_check(cudaMemcpyAsync(host, d.side, M, cudaMemcpyDeviceToHost, ctx.copy_stream), "cudaMemcpyAsync D2H");
-      cuda_check(cudaEventRecord(side_copied_[i], ctx.copy_stream), "cudaEventRecord");
+      // inside a graph the event the host coder waits for has to be an external event-record node
+      cuda_check(cudaEventRecordWithFlags(side_copied_[i], ctx.copy_stream, capturing_ ? cudaEventRecordExternal : cudaEventRecordDefault), "cudaEventRecord");
       d2h_bytes += M;
     }
     prof.begin("K9_build_table", 4ull * p.hist_capacity, s);
@@ -745,6 +853,8 @@ void MeshJob::encode_side_stream(size_t att) {
   }
 }
 
+constexpr size_t kStatsSlot = 1024;  // pinned_buffer slot of the per-attribute scalars (attribute slots are 2i, 2i+1)
+
 void MeshJob::download(DeviceContext& ctx) {
   results_.resize(plans_.size());
   // side streams: start a host worker per stream as soon as its flags have landed
@@ -755,7 +865,7 @@ void MeshJob::download(DeviceContext& ctx) {
     results_[i].side_len = sequence_of(i).size();
     const int device = ctx.device;
     cudaEvent_t ev = side_copied_[i];
-    workers.push_back(std::async(std::launch::async, [this, i, device, ev] {
+    workers.push_back(ctx.helpers->run([this, i, device, ev] {
       cuda_check(cudaSetDevice(device), "cudaSetDevice");
       const auto t0 = std::chrono::steady_clock::now();
       cuda_check(cudaEventSynchronize(ev), "cudaEventSynchronize");
@@ -768,15 +878,19 @@ void MeshJob::download(DeviceContext& ctx) {
   }
   auto join_workers = [&] { for (auto& w : workers) w.get(); };
   try {
+    // the scalars land in pinned memory: a device-to-host copy into pageable memory blocks the calling thread inside the
+    // driver until the stream gets there, which stalls the launches of every other thread of the process
+    gpu::AttrStats* stats_host = (gpu::AttrStats*)ctx.pinned_buffer(kStatsSlot, plans_.size() * sizeof(gpu::AttrStats));
     for (size_t i = 0; i < plans_.size(); ++i) {
       cudaStream_t s = ctx.stream[std::min<size_t>(i, 2)];
-      cuda_check(cudaMemcpyAsync(&results_[i].stats, dev_[i].stats, sizeof(gpu::AttrStats), cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+      cuda_check(cudaMemcpyAsync(stats_host + i, dev_[i].stats, sizeof(gpu::AttrStats), cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
       d2h_bytes += sizeof(gpu::AttrStats);
     }
     for (size_t i = 0; i < plans_.size(); ++i) {
       cudaStream_t s = ctx.stream[std::min<size_t>(i, 2)];
-      cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+      if (i < 3) ctx.wait_stream((int)i);  // attributes 3.. share stream 2, already drained
       AttrResult& r = results_[i];
+      r.stats = stats_host[i];
       if (int st = status_from_flags(r.stats.error_flags)) throw Error(st, "device reported an encoding error");
       static const bool rans_debug = getenv("DXO_RANS_DEBUG") != nullptr;
       if (rans_debug) fprintf(stderr, "[dxo] att %zu: rANS symbols=%llu P=%u K=%u chunks=%u chain misses=%u fixup=%u\n", i,
@@ -791,7 +905,7 @@ void MeshJob::download(DeviceContext& ctx) {
       cuda_check(cudaMemcpyAsync(host + r.stats.table_bytes, dev_[i].payload, r.stats.payload_bytes, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
       d2h_bytes += (size_t)r.stats.table_bytes + r.stats.payload_bytes;
     }
-    for (int k = 0; k < 3; ++k) cuda_check(cudaStreamSynchronize(ctx.stream[k]), "cudaStreamSynchronize");
+    for (int k = 0; k < 3; ++k) ctx.wait_stream(k);
   } catch (...) {
     try { join_workers(); } catch (...) {}
     throw;

@@ -3,6 +3,11 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <thread>
 #include <future>
 #include <map>
 #include <mutex>
@@ -16,16 +21,37 @@ namespace dxo {
 
 void cuda_check(cudaError_t e, const char* what);
 
+// Two persistent helper threads per DeviceContext (i.e. per calling thread): the side-stream coders of every step run
+// on them, so a step neither creates threads nor leaves new threads at the mercy of the scheduler.
+class HelperThreads {
+ public:
+  explicit HelperThreads(int n);
+  ~HelperThreads();
+  std::future<void> run(std::function<void()> fn);
+ private:
+  void loop();
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::packaged_task<void()>> queue_;
+  std::vector<std::thread> threads_;
+  bool stop_ = false;
+};
+
 // One per (host thread, device): streams, events and the launch / timing log.
 struct DeviceContext {
   int device = 0;
   cudaStream_t stream[3] = {nullptr, nullptr, nullptr};  // attribute i runs on stream[min(i,2)]
   cudaStream_t copy_stream = nullptr;                    // early D2H of the side-stream flags
   cudaStream_t upload_stream = nullptr;                  // H2D issued by helper threads while the host builds the connectivity
-  cudaEvent_t ev_uploaded = nullptr, ev_inputs = nullptr, ev_serial = nullptr;
+  cudaEvent_t ev_uploaded = nullptr, ev_inputs = nullptr, ev_serial = nullptr, ev_fork = nullptr, ev_copy_join = nullptr;
   // pinned host staging, reused across calls (slot = attribute index * 2 + {0: results, 1: side flags})
   std::vector<std::pair<uint8_t*, size_t>> pinned;
   uint8_t* pinned_buffer(size_t slot, size_t bytes);
+  // Host waits go through these events. With DXO_BLOCKING_WAIT=1 they are created with cudaEventBlockingSync: the waiting
+  // thread sleeps instead of spinning, for hosts with fewer cores than encoder threads (spinning is ~10 % faster otherwise).
+  cudaEvent_t ev_block[3] = {nullptr, nullptr, nullptr};
+  void wait_stream(int k);
+  std::unique_ptr<HelperThreads> helpers;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_pos_ready = nullptr, ev_layout = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   static DeviceContext& get(int device);  // thread-local; throws DXO_ERR_NO_DEVICE when there is no usable GPU
   DeviceContext() = default;
@@ -102,6 +128,12 @@ class MeshJob {
   // phase 2: device
   void upload(DeviceContext& ctx);
   void launch(DeviceContext& ctx, Profile& prof);
+  // launch() with the fork onto / join from the attribute streams; every operation it issues can be stream-captured
+  void launch_all(DeviceContext& ctx, Profile& prof, bool capturing = false);
+  // Resident sessions replay the whole step (all streams, ~45 launches, memsets, flag copies, events) as ONE CUDA graph
+  // from their second run on: one driver call per step instead of ~80, which matters most when several sessions share
+  // the driver. Captured per (job, calling thread's context); re-captured when the session moves to another thread.
+  void launch_graph(DeviceContext& ctx, Profile& prof);
   void download(DeviceContext& ctx);  // D2H of stats, tables, payloads, side bits (synchronises)
   // phase 3: host — assemble the Draco stream
   void assemble(std::vector<uint8_t>& out);
@@ -138,6 +170,7 @@ class MeshJob {
   // pinned host blocks holding the connectivity tables that K12-K14 produce (borrowed from a process-wide pool,
   // returned by the destructor)
   std::vector<std::pair<void*, size_t>> pinned_blocks_;
+  std::atomic<int> pinned_copy_in_flight_{0};
   static void* pinned_source(void* user, size_t bytes);
   std::shared_future<void> inputs_upload_;  // faces, values and point maps travel while the host builds the tables
   bool device_seam_table(DeviceContext& ctx, size_t att);  // K14; false = not applicable / flagged, use the host pass
@@ -146,6 +179,16 @@ class MeshJob {
   cudaStream_t alloc_stream_ = nullptr;
   std::vector<cudaEvent_t> side_ready_, side_copied_;
   bool uploaded_ = false;
+  cudaGraphExec_t graph_exec_ = nullptr;
+  DeviceContext* graph_ctx_ = nullptr;
+  uint32_t graph_launches_ = 0;
+  cudaEvent_t ev_graph_done_ = nullptr;
+  uint64_t graph_d2h_bytes_ = 0;
+  bool capturing_ = false;
+ public:
+  int device_runs = 0;  // run_device_phase calls so far (the graph is built on the second)
+  bool graph_replay = false;  // DXO_FLAG_GRAPH_REPLAY
+ private:
   void encode_side_stream(size_t att);
 
   static uint32_t device_matcher(void* user, const uint32_t* corner_vertex, uint32_t num_faces, uint32_t num_vertices, uint32_t* opposite_out,

@@ -724,7 +724,10 @@ void launch_histogram(const uint32_t* symbols, uint64_t num_symbols, uint32_t* h
 //   3. serialisation (leb128 count, 1-3 byte frequencies, zero-run tokens incl. the
 //      64-wrap quirk of :202-211),
 //   4. the per-symbol {freq, cumulative, reciprocal} table for K10.
-constexpr int kTableThreads = 1024;
+// 256 threads, not 1024: a CTA that needs half an SM at once can starve for milliseconds when other sessions keep every
+// SM topped up with small CTAs (their rANS kernels queue thousands of them); a small CTA always finds room.
+constexpr int kTableThreads = 256;
+constexpr uint32_t kTableWarps = kTableThreads / 32;
 
 struct BlockScan {  // exclusive scans over a block of kTableThreads threads
   uint32_t* warp_tmp;  // 32 entries of shared memory
@@ -737,7 +740,7 @@ struct BlockScan {  // exclusive scans over a block of kTableThreads threads
     if (lane == 31) warp_tmp[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-      uint32_t w = warp_tmp[lane], winc = w;
+      uint32_t w = lane < kTableWarps ? warp_tmp[lane] : 0u, winc = w;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, winc, d); if (lane >= (uint32_t)d) winc += o; }
       warp_tmp[lane] = winc - w;
@@ -752,7 +755,7 @@ struct BlockScan {  // exclusive scans over a block of kTableThreads threads
     __syncthreads();
     if ((threadIdx.x & 31) == 0) warp_tmp[threadIdx.x >> 5] = v;
     __syncthreads();
-    uint32_t r = warp_tmp[threadIdx.x & 31];
+    uint32_t r = (threadIdx.x & 31) < kTableWarps ? warp_tmp[threadIdx.x & 31] : 0u;
     r = __reduce_max_sync(0xFFFFFFFFu, r);
     return r;
   }
@@ -762,7 +765,7 @@ struct BlockScan {  // exclusive scans over a block of kTableThreads threads
     __syncthreads();
     if ((threadIdx.x & 31) == 0) tmp64[threadIdx.x >> 5] = v;
     __syncthreads();
-    unsigned long long r = tmp64[threadIdx.x & 31];
+    unsigned long long r = (threadIdx.x & 31) < kTableWarps ? tmp64[threadIdx.x & 31] : 0ull;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) r += __shfl_xor_sync(0xFFFFFFFFu, r, d);
     return r;

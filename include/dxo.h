@@ -110,13 +110,17 @@ typedef struct dxo_mesh {
  * counts are constants in the reference (portabilization/mod.rs:116-142). They
  * are parameters here; only 11/10 is reference behaviour. Octahedral normal
  * quantization is fixed at 8 bits (the reference hard-codes 255/127). */
+/* Resident sessions replay the device step as one CUDA graph from their second run on (one driver call per step instead
+ * of ~80). Off by default: the flag copies for the host-coded side streams leave later from inside a graph. */
+#define DXO_FLAG_GRAPH_REPLAY 1u
+
 typedef struct dxo_config {
   uint32_t abi_version;       /* DXO_ABI_VERSION */
   uint32_t position_bits;     /* default 11 */
   uint32_t texcoord_bits;     /* default 10 */
   uint32_t generic_bits;      /* default 11: other quantized attribute types */
   int32_t  device;            /* CUDA device ordinal; -1 = current device */
-  uint32_t flags;             /* reserved, 0 */
+  uint32_t flags;             /* DXO_FLAG_* bits, 0 by default */
 } dxo_config;
 
 typedef struct dxo_bytes {

@@ -324,3 +324,23 @@ def test_rans_paths_off_the_operating_point(env):
         assert misses > 100, "the chain's run-from-the-true-state path was not exercised"
     if "DXO_RANS_FAULT" in env:
         assert fixups > 100, "the sequential fix-up was not exercised"
+
+
+def test_resident_session_graph_replay(orc):
+    """With DXO_FLAG_GRAPH_REPLAY a resident session replays the step as one CUDA graph from its second run on (all streams, flag copies, external
+    events for the host coders). Streams must stay byte-identical, also after run_steps and from another thread."""
+    import threading
+    for m in (synth.grid_mesh(90, 80, 41), synth.torus_mesh(50, 40, 42)):
+        ref = orc.encode(m)
+        s = dxo.Session(m, dxo.Config(flags=dxo.Config.GRAPH_REPLAY))
+        assert s.run() == ref          # direct launches
+        assert s.run() == ref          # capture + first replay
+        assert s.run() == ref          # replay
+        s.run_steps(3)
+        assert s.run() == ref
+        got = []
+        t = threading.Thread(target=lambda: got.append(s.run()))  # another thread: its own streams, the graph is re-captured
+        t.start(); t.join()
+        assert got == [ref]
+        assert s.run() == ref
+        s.close()
