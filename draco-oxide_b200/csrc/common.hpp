@@ -177,10 +177,12 @@ static inline void rabs_encode(const uint8_t* bits, size_t n, bool reversed, uin
 // Same coder, tuned for the long per-element side streams of the attribute path (flips,
 // orientations): reciprocal multiplication instead of division (exact: x < 2^20, f <= 255,
 // m = ceil(2^32 / f) => x * (m * f - 2^32) < 2^28 < 2^32), bytes written through a raw pointer.
-static inline void rabs_encode_forward(const uint8_t* bits, size_t n, uint8_t zero_prob, std::vector<uint8_t>& out) {
+// `bit(i)` yields the i-th bit to code (0 / 1), so a caller can derive the bits on the fly.
+template <class BitAt>
+static inline void rabs_encode_forward_fn(size_t n, uint8_t zero_prob, std::vector<uint8_t>& out, BitAt bit) {
   const uint32_t f0 = zero_prob, f1 = 256u - f0;
   if ((f0 == 0 || f1 == 0) && n) {  // only reachable with a probability outside [1,255]
-    for (size_t i = 0; i < n; ++i) if ((bits[i] ? f1 : f0) == 0) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "rABS: zero frequency");
+    for (size_t i = 0; i < n; ++i) if ((bit(i) ? f1 : f0) == 0) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "rABS: zero frequency");
   }
   // x' = (q << 8) + (x - q f) + cum = x + q (256 - f) + cum, q = floor(x / f) = (x * m) >> 32
   const uint32_t thr[2] = {f0 << 12, f1 << 12}, g[2] = {256u - f0, 256u - f1}, cum[2] = {f1, 0u};
@@ -195,7 +197,7 @@ static inline void rabs_encode_forward(const uint8_t* bits, size_t n, uint8_t ze
     const uint32_t thr_c = thr[common], cum_c = cum[common], thr_r = thr[rare], g_r = g[rare], cum_r = cum[rare];
     const uint64_t m_c = m[common], m_r = m[rare];
     for (size_t i = 0; i < n; ++i) {
-      if (__builtin_expect((uint32_t)(bits[i] != 0) == common, 1)) {
+      if (__builtin_expect((uint32_t)(bit(i) != 0) == common, 1)) {
         if (x >= thr_c) { *p++ = (uint8_t)x; x >>= 8; }
         x = x + (uint32_t)(((uint64_t)x * m_c) >> 32) + cum_c;
       } else {
@@ -205,7 +207,7 @@ static inline void rabs_encode_forward(const uint8_t* bits, size_t n, uint8_t ze
     }
   } else {
     for (size_t i = 0; i < n; ++i) {
-      const uint32_t b = bits[i] != 0;
+      const uint32_t b = bit(i) != 0;
       if (x >= thr[b]) { *p++ = (uint8_t)x; x >>= 8; }
       const uint32_t q = (uint32_t)(((uint64_t)x * m[b]) >> 32);
       x = x + q * g[b] + cum[b];
@@ -215,6 +217,9 @@ static inline void rabs_encode_forward(const uint8_t* bits, size_t n, uint8_t ze
   ans_write_tail(x - 4096u, tail);
   for (uint8_t b : tail.data) *p++ = b;
   out.resize((size_t)(p - out.data()));
+}
+static inline void rabs_encode_forward(const uint8_t* bits, size_t n, uint8_t zero_prob, std::vector<uint8_t>& out) {
+  rabs_encode_forward_fn(n, zero_prob, out, [bits](size_t i) { return bits[i]; });
 }
 
 // zero_prob byte + leb128 length + rABS bytes: the framing every side stream uses.

@@ -838,18 +838,25 @@ void MeshJob::encode_side_stream(size_t att) {
     r.side_zero_prob = side_stream_zero_prob(n - ones, (float)n);
     rabs_encode_forward(flags, n, r.side_zero_prob, r.side_payload);
   } else {
-    // order-preserving compaction (branch-free), then the delta bits in place
+    // one pass: order-preserving compaction (branch-free) and the transition count; the delta bits
+    // bits[k] = (o[k] == o[k+1]), o[len] = true, are formed inside the coder's loop
     std::vector<uint8_t>& o = r.side_scratch;
     o.resize(n + 1);
     size_t m = 0;
-    for (size_t i = 0; i < n; ++i) { const uint8_t f = flags[i]; o[m] = (uint8_t)(f >> 1); m += f != 0; }
     uint64_t transitions = 0;
-    { uint8_t last = 1; for (size_t k = 0; k < m; ++k) { transitions += o[k] != last; last = o[k]; } }
+    uint8_t last = 1;
+    for (size_t i = 0; i < n; ++i) {
+      const uint8_t f = flags[i], bit = (uint8_t)(f >> 1), present = f != 0;
+      o[m] = bit;
+      transitions += present & (uint8_t)(bit != last);
+      last = present ? bit : last;
+      m += present;
+    }
     r.side_count = (uint32_t)m;
     r.side_zero_prob = side_stream_zero_prob(transitions, (float)m + 0.001f);
-    o[m] = 1;  // o[len] = true
-    for (size_t k = 0; k < m; ++k) o[k] = o[k] == o[k + 1] ? 1 : 0;  // bits[k] = (o[k] == o[k+1]); o[k+1] is still unmodified
-    rabs_encode_forward(o.data(), m, r.side_zero_prob, r.side_payload);
+    o[m] = 1;
+    const uint8_t* ob = o.data();
+    rabs_encode_forward_fn(m, r.side_zero_prob, r.side_payload, [ob](size_t k) { return (uint8_t)(ob[k] == ob[k + 1]); });
   }
 }
 
