@@ -149,6 +149,61 @@ def encode_symbols(symbols, device=-1, timing=False):
     return (data, {"histogram_ms": ms[0], "table_ms": ms[1], "rans_ms": ms[2]}) if timing else data
 
 
+def dedup_values(values, device=-1):
+    """Attribute::remove_duplicate_values on the device: returns (point -> unique value map, first index of each
+    unique value), unique values numbered in first-occurrence order (core/attribute/mod.rs:394-452)."""
+    import numpy as np
+    from .mesh import _NP_TO_CT
+    v = np.ascontiguousarray(values)
+    if v.ndim == 1:
+        v = v.reshape(-1, 1)
+    n = v.shape[0]
+    out_map, first, nu = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.uint32), C.c_uint64()
+    _check(_capi.lib().dxo_dedup_values(v.ctypes.data, n, int(_NP_TO_CT[v.dtype]), v.shape[1], device,
+                                        out_map.ctypes.data_as(C.POINTER(C.c_uint32)), first.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(nu)))
+    return out_map[:n], first[: nu.value]
+
+
+def build_mesh(faces, atts, device=-1):
+    """MeshBuilder: atts = list of (per_point_values ndarray, AttributeType, AttributeDomain, parents). Value dedup per
+    attribute, position first, point merge, degenerate-face and unused-point removal (core/mesh/builder.rs:30-125);
+    the duplicate searches run on the device. Returns a Mesh ready for encode()."""
+    import numpy as np
+    from .mesh import _NP_TO_CT, Attribute, Mesh
+    faces = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1, 3)
+    arr = (_capi.dxo_attribute * max(len(atts), 1))()
+    keep = []
+    for i, (vals, ty, dom, parents) in enumerate(atts):
+        v = np.ascontiguousarray(vals)
+        if v.ndim == 1:
+            v = v.reshape(-1, 1)
+        par = np.asarray(parents, dtype=np.uint32)
+        keep += [v, par]
+        d = arr[i]
+        d.att_type, d.component_type, d.num_components, d.domain = int(ty), int(_NP_TO_CT[v.dtype]), v.shape[1], int(dom)
+        d.unique_id, d.num_parents, d.parent_ids = i, par.size, par.ctypes.data_as(C.POINTER(C.c_uint32))
+        d.num_unique_values, d.values, d.num_points = v.shape[0], v.ctypes.data, v.shape[0]
+    h = C.c_void_p()
+    _check(_capi.lib().dxo_mesh_build(faces.ctypes.data_as(C.POINTER(C.c_uint32)), faces.shape[0], arr, len(atts), device, C.byref(h)))
+    try:
+        view = _capi.dxo_mesh()
+        _check(_capi.lib().dxo_built_mesh_view(h, C.byref(view)))
+        out_faces = np.ctypeslib.as_array(view.faces, shape=(view.num_faces * 3,)).copy().reshape(-1, 3) if view.num_faces else np.zeros((0, 3), np.uint32)
+        out_atts = []
+        ct_to_np = {int(ct): dt for dt, ct in _NP_TO_CT.items()}
+        for i in range(view.num_attributes):
+            a = view.attributes[i]
+            dt = np.dtype(ct_to_np[a.component_type])
+            nbytes = a.num_unique_values * a.num_components * dt.itemsize
+            vals = np.frombuffer(C.string_at(a.values, nbytes), dtype=dt).reshape(-1, a.num_components).copy() if nbytes else np.zeros((0, a.num_components), dt)
+            pmap = np.ctypeslib.as_array(a.point_to_value, shape=(a.num_points,)).copy() if a.point_to_value and a.num_points else None
+            parents = tuple(a.parent_ids[k] for k in range(a.num_parents))
+            out_atts.append(Attribute(vals, a.att_type, a.domain, parents, pmap, a.unique_id))
+        return Mesh(out_faces, out_atts)
+    finally:
+        _capi.lib().dxo_built_mesh_free(h)
+
+
 def set_profiling(on):
     _capi.lib().dxo_set_profiling(int(on))
 

@@ -73,6 +73,7 @@ EXPORTED = [
     "dxo_device_count", "dxo_session_create", "dxo_connectivity_create", "dxo_session_run_steps", "dxo_session_run", "dxo_session_destroy",
     "dxo_set_profiling", "dxo_last_timing", "dxo_session_set_trace", "dxo_session_trace_get",
     "dxo_corner_table_opposites", "dxo_encode_symbols",
+    "dxo_mesh_build", "dxo_built_mesh_view", "dxo_built_mesh_free", "dxo_dedup_values",
 ]
 
 _lib = None
@@ -125,5 +126,14 @@ def lib():
     L.dxo_corner_table_opposites.restype = C.c_int
     L.dxo_encode_symbols.argtypes = [C.POINTER(C.c_uint32), C.c_uint64, C.c_int, C.POINTER(dxo_bytes), C.POINTER(C.c_float)]
     L.dxo_encode_symbols.restype = C.c_int
+    L.dxo_mesh_build.argtypes = [C.POINTER(C.c_uint32), C.c_uint64, C.POINTER(dxo_attribute), C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
+    L.dxo_mesh_build.restype = C.c_int
+    L.dxo_built_mesh_view.argtypes = [C.c_void_p, C.POINTER(dxo_mesh)]
+    L.dxo_built_mesh_view.restype = C.c_int
+    L.dxo_built_mesh_free.argtypes = [C.c_void_p]
+    L.dxo_built_mesh_free.restype = None
+    L.dxo_dedup_values.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                   C.POINTER(C.c_uint64)]
+    L.dxo_dedup_values.restype = C.c_int
     _lib = L
     return L

@@ -217,6 +217,26 @@ int dxo_encode_symbols(const uint32_t* symbols, uint64_t n, int device, dxo_byte
 int dxo_corner_table_opposites(const uint32_t* vertex_of_corner, uint64_t num_faces,
                                uint32_t* opposite_out, int* exact_out, int device);
 
+/* ---- mesh build: the step before the boundary ----
+ * dxo_mesh_build replaces MeshBuilder::add_attribute + MeshBuilder::build (core/mesh/builder.rs:30-125: value dedup
+ * per attribute = Attribute::from / remove_duplicate_values, core/attribute/mod.rs:87-103, 394-452; position attribute
+ * first; merge of points whose values agree in every attribute; removal of degenerate faces and unused points).
+ * per_point_attributes[i]: `values` holds `num_unique_values` per-POINT values (one per point, all attributes the same
+ * count); point_to_value and unique_id are ignored (ids are assigned in insertion order, parents refer to them).
+ * The duplicate searches (all-pairs / hashing in the reference) run on the device as radix sorts with first-occurrence
+ * numbering. Attributes of different lengths are reported as DXO_ERR_UNSUPPORTED_INPUT. */
+typedef struct dxo_built_mesh dxo_built_mesh;
+int dxo_mesh_build(const uint32_t* faces, uint64_t num_faces, const dxo_attribute* per_point_attributes,
+                   uint32_t num_attributes, int device, dxo_built_mesh** out);
+/* Borrowed view (valid until dxo_built_mesh_free), ready for dxo_encode. */
+int dxo_built_mesh_view(const dxo_built_mesh* mesh, dxo_mesh* out);
+void dxo_built_mesh_free(dxo_built_mesh* mesh);
+/* Attribute::remove_duplicate_values alone: out_map[n] = point -> unique value (first-occurrence order),
+ * out_first_index[u] = first point holding unique value u (u < *out_num_unique; the array needs n entries).
+ * Equality is the typed `==`: -0.0 equals +0.0, a NaN equals nothing. */
+int dxo_dedup_values(const void* values, uint64_t n, uint32_t component_type, uint32_t num_components, int device,
+                     uint32_t* out_map, uint32_t* out_first_index, uint64_t* out_num_unique);
+
 #ifdef __cplusplus
 }
 #endif
