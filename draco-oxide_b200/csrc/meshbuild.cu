@@ -17,7 +17,11 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <future>
 #include <memory>
 #include <string>
 #include <vector>
@@ -208,25 +212,28 @@ struct BuiltAttribute {
 // Attribute::remove for a set of points (core/attribute/mod.rs:454-482), batched: `gone[p]` marks removed points.
 void remove_points(BuiltAttribute& a, const std::vector<uint8_t>& gone) {
   const size_t vs = a.value_bytes(), L = a.len();
+  auto removed = [&](size_t p) { return p < gone.size() && gone[p]; };
   if (a.has_map) {
-    std::vector<uint32_t> kept_map;
-    kept_map.reserve(L);
+    std::vector<uint32_t> kept_map(L);
     std::vector<uint8_t> referenced(a.num_unique(), 0);
-    for (size_t p = 0; p < L; ++p) if (p >= gone.size() || !gone[p]) { kept_map.push_back(a.map[p]); referenced[a.map[p]] = 1; }
+    size_t kept = 0;
+    for (size_t p = 0; p < L; ++p) if (!removed(p)) { kept_map[kept++] = a.map[p]; referenced[a.map[p]] = 1; }
+    kept_map.resize(kept);
     std::vector<uint32_t> new_index(referenced.size(), kNone);
-    std::vector<uint8_t> kept_values;
-    kept_values.reserve(a.values.size());
     uint32_t next = 0;
-    for (size_t v = 0; v < referenced.size(); ++v)
-      if (referenced[v]) { new_index[v] = next++; kept_values.insert(kept_values.end(), a.values.begin() + v * vs, a.values.begin() + (v + 1) * vs); }
-    for (uint32_t& m : kept_map) m = new_index[m];
+    for (size_t v = 0; v < referenced.size(); ++v) if (referenced[v]) new_index[v] = next++;
+    if (next != referenced.size()) {  // values no remaining point refers to are dropped, larger indices shift down
+      std::vector<uint8_t> kept_values((size_t)next * vs);
+      for (size_t v = 0; v < referenced.size(); ++v) if (referenced[v]) memcpy(kept_values.data() + (size_t)new_index[v] * vs, a.values.data() + v * vs, vs);
+      a.values.swap(kept_values);
+      for (uint32_t& m : kept_map) m = new_index[m];
+    }
     a.map.swap(kept_map);
-    a.values.swap(kept_values);
   } else {
-    std::vector<uint8_t> kept_values;
-    kept_values.reserve(a.values.size());
-    for (size_t v = 0; v < L; ++v)
-      if (v >= gone.size() || !gone[v]) kept_values.insert(kept_values.end(), a.values.begin() + v * vs, a.values.begin() + (v + 1) * vs);
+    std::vector<uint8_t> kept_values(a.values.size());
+    size_t kept = 0;
+    for (size_t v = 0; v < L; ++v) if (!removed(v)) { memcpy(kept_values.data() + kept * vs, a.values.data() + v * vs, vs); ++kept; }
+    kept_values.resize(kept * vs);
     a.values.swap(kept_values);
   }
 }
@@ -251,6 +258,17 @@ template <class F> int guarded_build(F&& f) {
   catch (const std::exception& e) { g_build_error = e.what(); return DXO_ERR_INTERNAL; }
 }
 
+struct BuildClock {  // DXO_TIMING=1: stage times of dxo_mesh_build on stderr
+  bool on = getenv("DXO_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[dxo] mesh build: %-34s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+
 struct BuildStream {  // one stream per call; the default memory pool keeps its blocks between calls
   cudaStream_t s = nullptr;
   explicit BuildStream(int device) {
@@ -259,6 +277,12 @@ struct BuildStream {  // one stream per call; the default memory pool keeps its 
     if (device < 0) cuda_check(cudaGetDevice(&device), "cudaGetDevice");
     if (device >= count) throw Error(DXO_ERR_NO_DEVICE, "CUDA device ordinal out of range");
     cuda_check(cudaSetDevice(device), "cudaSetDevice");
+    // keep freed blocks in the stream-ordered pool (as DeviceContext does): a build allocates ~a dozen arrays per dedup
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     cuda_check(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
   }
   ~BuildStream() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
@@ -288,6 +312,7 @@ int dxo_mesh_build(const uint32_t* faces, uint64_t num_faces, const dxo_attribut
   const int st = guarded_build([&] {
     if (num_faces > 0x55555554ull) throw Error(DXO_ERR_INVALID_ARGUMENT, "too many faces");
     BuildStream bs(device);
+    BuildClock clk;
     std::vector<BuiltAttribute>& atts = mesh->attributes;
     // ---- add_attribute: Attribute::from with value dedup (builder.rs:30-39, attribute/mod.rs:87-103, 394-452) ----
     uint64_t L = 0;
@@ -304,6 +329,7 @@ int dxo_mesh_build(const uint32_t* faces, uint64_t num_faces, const dxo_attribut
       a.parents.assign(in.parent_ids, in.parent_ids + in.num_parents);
       bool has_nan = false;
       DedupResult r = dedup_values(in.values, in.num_unique_values, in.component_type, in.num_components, bs.s, &has_nan);
+      clk.lap("attribute value dedup (device)");
       att_has_nan[i] = has_nan ? 1 : 0;
       const size_t vs = a.value_bytes();
       const uint8_t* src = (const uint8_t*)in.values;
@@ -316,6 +342,7 @@ int dxo_mesh_build(const uint32_t* faces, uint64_t num_faces, const dxo_attribut
         for (size_t u = 0; u < r.first_index.size(); ++u) memcpy(a.values.data() + u * vs, src + (size_t)r.first_index[u] * vs, vs);
       }
       atts.push_back(std::move(a));
+      clk.lap("attribute unique values (host)");
     }
     // ---- build(): dependency_check (builder.rs:94-111) ----
     for (const BuiltAttribute& a : atts) {
@@ -338,36 +365,45 @@ int dxo_mesh_build(const uint32_t* faces, uint64_t num_faces, const dxo_attribut
       // value (the reference hashes value bytes here, so NaNs with equal bit patterns merge although they are distinct values)
       uint32_t num_words = 0;
       for (size_t a = 0; a < atts.size(); ++a) num_words += att_has_nan[a] ? (uint32_t)((atts[a].value_bytes() + 3) / 4) : 1u;
-      std::vector<uint32_t> words((size_t)num_words * num_vertices);
+      DeviceBuffer d_words(4ull * num_words * num_vertices, bs.s);
       uint32_t w0 = 0;
+      std::vector<uint32_t> tmp_words;
       for (size_t a = 0; a < atts.size(); ++a) {
         const BuiltAttribute& A = atts[a];
+        uint32_t* dst = d_words.as<uint32_t>() + (size_t)w0 * num_vertices;
         if (!att_has_nan[a]) {
-          for (uint32_t p = 0; p < num_vertices; ++p) words[(size_t)w0 * num_vertices + p] = A.value_of(p);
+          if (A.has_map) cuda_check(cudaMemcpyAsync(dst, A.map.data(), 4ull * num_vertices, cudaMemcpyHostToDevice, bs.s), "cudaMemcpyAsync H2D");
+          else iota_kernel<<<grid_for(num_vertices), kThreads, 0, bs.s>>>(dst, num_vertices);
           w0 += 1;
         } else {
           const size_t vs = A.value_bytes(), nw = (vs + 3) / 4;
+          tmp_words.assign(nw * num_vertices, 0);
           for (uint32_t p = 0; p < num_vertices; ++p) {
             uint32_t tmp[32] = {0};
             memcpy(tmp, A.values.data() + (size_t)A.value_of(p) * vs, vs);
-            for (size_t k = 0; k < nw; ++k) words[(size_t)(w0 + k) * num_vertices + p] = tmp[k];
+            for (size_t k = 0; k < nw; ++k) tmp_words[k * num_vertices + p] = tmp[k];
           }
+          cuda_check(cudaMemcpyAsync(dst, tmp_words.data(), 4ull * nw * num_vertices, cudaMemcpyHostToDevice, bs.s), "cudaMemcpyAsync H2D");
+          cuda_check(cudaStreamSynchronize(bs.s), "cudaStreamSynchronize");  // tmp_words is reused
           w0 += (uint32_t)nw;
         }
       }
-      DeviceBuffer d_words(4ull * words.size(), bs.s);
-      cuda_check(cudaMemcpyAsync(d_words.p, words.data(), 4ull * words.size(), cudaMemcpyHostToDevice, bs.s), "cudaMemcpyAsync H2D");
+      clk.lap("point keys (host)");
       DedupResult pm = dedup_on_device(d_words.as<uint32_t>(), num_words, num_vertices, bs.s);
+      clk.lap("point dedup (device)");
       const uint32_t unique_count = (uint32_t)pm.first_index.size();
       if (unique_count != num_vertices) {
         std::vector<uint8_t> gone(num_vertices, 0);
         for (uint32_t v = 0; v < num_vertices; ++v) gone[v] = pm.first_index[pm.uid[v]] != v;  // later duplicates
+        std::vector<std::future<void>> jobs;  // the attributes are independent
         for (BuiltAttribute& A : atts) {
           if (unique_count == A.len()) continue;  // remap_attribute's early return (:274-276)
-          remove_points(A, gone);
+          jobs.push_back(std::async(std::launch::async, [&A, &gone] { remove_points(A, gone); }));
         }
+        for (auto& j : jobs) j.get();
         for (uint32_t& p : f) p = pm.uid[p];
       }
+      clk.lap("point removal + face remap (host)");
     }
     // ---- degenerate faces (:76-79) ----
     {
@@ -382,7 +418,10 @@ int dxo_mesh_build(const uint32_t* faces, uint64_t num_faces, const dxo_attribut
       for (uint32_t p : f) max_idx = std::max(max_idx, p);
       std::vector<uint8_t> used((size_t)max_idx + 1, 0);
       for (uint32_t p : f) used[p] = 1;
+      bool all_used = true;
+      for (uint8_t u : used) all_used &= u != 0;
       for (BuiltAttribute& A : atts) {
+        if (all_used && A.len() == used.size()) continue;  // nothing to remove from this attribute
         std::vector<uint8_t> gone(A.len(), 0);
         for (size_t p = 0; p < gone.size(); ++p) gone[p] = p > max_idx || !used[p];
         remove_points(A, gone);
@@ -392,6 +431,7 @@ int dxo_mesh_build(const uint32_t* faces, uint64_t num_faces, const dxo_attribut
       for (size_t v = 0; v < used.size(); ++v) { offset[v] = removed; removed += !used[v]; }
       for (uint32_t& p : f) p -= offset[p];
     }
+    clk.lap("degenerate faces, unused points");
     // ---- views ----
     mesh->views.resize(atts.size());
     for (size_t i = 0; i < atts.size(); ++i) {
