@@ -75,3 +75,11 @@ def test_product_fails_loudly_without_gpu(built):
     with pytest.raises(dxo.Err) as e:
         s.run()
     assert e.value.status == -20
+    import numpy as np
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    with pytest.raises(dxo.Err) as e:  # the mesh build has no host path either
+        dxo.build_mesh(np.array([[0, 1, 2]], np.uint32), [(pos, 0, 0, ())])
+    assert e.value.status == -20
+    with pytest.raises(dxo.Err) as e:
+        dxo.dedup_values(pos)
+    assert e.value.status == -20
