@@ -48,6 +48,16 @@ def parse_args():
     return ap.parse_args()
 
 
+def default_sessions(world):
+    """(sessions per GPU, blocking waits?) from the host threads this GPU can count on. A session keeps two side-stream
+    coders busy; its main thread spins in the waits (fastest) when there are three threads per session to spare and
+    sleeps in them (DXO_BLOCKING_WAIT) when host threads are scarce, which then allows one session per two threads."""
+    per_gpu = max(1, (os.cpu_count() or 2) // max(1, world))
+    if per_gpu >= 15:
+        return max(1, min(6, per_gpu // 3)), False
+    return max(1, min(6, per_gpu // 2)), True
+
+
 def make_mesh(workload):
     from draco_oxide_b200 import synth
     if workload == "config1":
@@ -172,6 +182,8 @@ def main():
         run_reference(args, rank, world)
         return
 
+    if args.sessions <= 0 and default_sessions(world)[1]:
+        os.environ.setdefault("DXO_BLOCKING_WAIT", "1")  # read when a thread's device context is created
     import numpy as np
     import torch
     import draco_oxide_b200 as dxo
@@ -200,7 +212,7 @@ def main():
     # `value`: S sessions (one host thread each, own CUDA streams) encode the resident mesh concurrently, the way the
     # batch entry keeps a GPU busy: the serial rANS chains and the host-coded side streams of one mesh overlap with
     # the kernels of the others. A step = one pass of every session; every pass produces the complete Draco stream.
-    S = args.sessions if args.sessions > 0 else max(1, min(6, (os.cpu_count() or 3) // (3 * max(1, world))))
+    S = args.sessions if args.sessions > 0 else default_sessions(world)[0]
     sessions, results, errors = [None] * S, [None] * S, []
     ready, go = threading.Barrier(S + 1), threading.Barrier(S + 1)
 
@@ -321,6 +333,7 @@ def main():
             "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32->i32/u32 (bit-exact integer pipeline)", "data": "synthetic",
             "config": {"workload": desc, "units_per_step_per_gpu": f"{S} meshes ({S} concurrent resident sessions of the workload mesh)",
+                       "host_threads": os.cpu_count(), "host_waits": "blocking" if os.environ.get("DXO_BLOCKING_WAIT") else "spinning",
                        "parallelism": f"{world} independent replicas, no collective",
                        "l2": f"inputs larger than L2: {input_bytes / 1e6:.0f} MB resident per mesh vs 126 MB L2",
                        "stream_bytes": len(ref_bytes)},
