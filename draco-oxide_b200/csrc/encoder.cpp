@@ -610,7 +610,7 @@ void MeshJob::upload(DeviceContext& ctx) {
     if (p.port == Portabilization::ToBits && p.ncomp_q != 3) d.quant = (int32_t*)d.values;
     else d.quant = dalloc<int32_t>(U * qstride, s);
     if (i > 0) d.corner_vertex4 = dalloc<uint4>(ut_.num_faces, s);
-    if (i > 0 && p.scheme == Scheme::Normal) d.opposite_masked = dalloc<uint32_t>(C, s);  // fan walks read one masked opposite per swing
+    if (i > 0 && p.scheme == Scheme::Normal) d.fan_link = dalloc<uint2>(C, s);  // fan walks read one link per swing
     d.rank = dalloc<uint32_t>(V, s);
     d.symbols = dalloc<uint32_t>(M * p.ncomp_q, s);
     d.side = dalloc<uint8_t>(M, s);
@@ -642,7 +642,7 @@ gpu::TableDev MeshJob::table_dev(size_t att) const {
   t.corner_point = d_faces_;
   t.corner_point4 = d_faces4_;
   t.opposite = d_opposite_;
-  t.opposite_masked = att == 0 ? d_opposite_ : dev_[att].opposite_masked;
+  t.fan_link = att == 0 ? nullptr : dev_[att].fan_link;
   t.num_corners = ut_.num_corners;
   if (att == 0) {
     t.corner_vertex = d_corner_vertex_; t.corner_vertex4 = vertex_is_point_ ? d_faces4_ : d_corner_vertex4_; t.vertex_is_point = vertex_is_point_ ? 1 : 0;
@@ -741,9 +741,9 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     cuda_check(cudaMemsetAsync(d.rank, 0xFF, sizeof(uint32_t) * V, s), "cudaMemsetAsync");
 
     if (i > 0) {
-      prof.begin("layout_attribute", 28ull * ut_.num_faces + (d.opposite_masked ? 9 * C : 0), s);
+      prof.begin("layout_attribute", 28ull * ut_.num_faces + (d.fan_link ? 17 * C : 0), s);
       gpu::launch_pad3(d.corner_vertex, ut_.num_faces, d.corner_vertex4, s);
-      if (d.opposite_masked) { gpu::launch_mask_opposite(d_opposite_, d.seam, C, d.opposite_masked, s); ++prof.launches; }
+      if (d.fan_link) { gpu::launch_fan_link(d_opposite_, d.seam, d_faces_, C, d.fan_link, s); ++prof.launches; }
       prof.end(s);
     }
     if (p.port == Portabilization::ToBits && p.ncomp_q == 3) {

@@ -98,7 +98,7 @@ struct AttrPlan {
 struct AttrDevice {
   // inputs
   float* values = nullptr; uint32_t* map = nullptr;
-  uint32_t *corner_vertex = nullptr, *left_most = nullptr, *seq = nullptr; uint8_t* seam = nullptr; uint4* corner_vertex4 = nullptr; uint32_t* opposite_masked = nullptr;
+  uint32_t *corner_vertex = nullptr, *left_most = nullptr, *seq = nullptr; uint8_t* seam = nullptr; uint4* corner_vertex4 = nullptr; uint2* fan_link = nullptr;
   // intermediates / outputs
   int32_t* quant = nullptr; uint32_t *rank = nullptr, *symbols = nullptr, *hist = nullptr, *work = nullptr;
   uint8_t *side = nullptr, *table_bytes = nullptr, *payload = nullptr, *rans_scratch = nullptr; uint4* rans_table = nullptr;

@@ -400,27 +400,30 @@ void launch_predict_delta(const uint32_t* seq, uint32_t n, TableDev t, QuantDev 
 }
 
 // ---------------------------------------------------------------------------------------
-// opposite corner with seam edges already masked out (one load per swing in the fan walks)
-__device__ __forceinline__ uint32_t masked_opp(const TableDev& t, uint32_t c) {
-  return t.opposite_masked ? __ldg(t.opposite_masked + c) : opp_of(t, c);
+// Fan walks of K5: one 8-byte load per swing. link[c] = {opposite corner of c with seam edges masked out, point of
+// that opposite corner}. Swinging from a corner of vertex v across an edge lands in the neighbouring face, whose only
+// vertex not on the shared edge is the tip of that opposite corner — so its point comes with the link.
+__device__ __forceinline__ uint2 fan_link(const TableDev& t, uint32_t c) {
+  if (t.fan_link) return __ldg(t.fan_link + c);
+  const uint32_t o = opp_of(t, c);
+  return make_uint2(o, o == kNoneDev ? 0u : __ldg(t.corner_point + o));
 }
-__global__ void __launch_bounds__(kThreads) mask_opposite_kernel(const uint32_t* __restrict__ opposite, const uint8_t* __restrict__ seam, uint64_t n,
-                                                                 uint32_t* __restrict__ out) {
+__global__ void __launch_bounds__(kThreads) fan_link_kernel(const uint32_t* __restrict__ opposite, const uint8_t* __restrict__ seam,
+                                                            const uint32_t* __restrict__ corner_point, uint64_t n, uint2* __restrict__ out) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) out[c] = __ldcs(seam + c) ? kNoneDev : __ldcs(opposite + c);
+  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
+    const uint32_t o = __ldcs(seam + c) ? kNoneDev : __ldcs(opposite + c);
+    out[c] = make_uint2(o, o == kNoneDev ? 0u : __ldg(corner_point + o));
+  }
 }
-void launch_mask_opposite(const uint32_t* opposite, const uint8_t* seam, uint64_t n, uint32_t* out, cudaStream_t s) {
-  mask_opposite_kernel<<<grid_for(n, kThreads * 4), kThreads, 0, s>>>(opposite, seam, n, out);
+void launch_fan_link(const uint32_t* opposite, const uint8_t* seam, const uint32_t* corner_point, uint64_t n, uint2* out, cudaStream_t s) {
+  fan_link_kernel<<<grid_for(n, kThreads * 4), kThreads, 0, s>>>(opposite, seam, corner_point, n, out);
 }
 
 // K5 — MeshNormalPrediction::predict (mesh_normal_prediction.rs:77-144) fused with
 // OctahedronOrthogonalTransform (oct_orthogonal.rs:23-74).
 // compute_normal_of_face (:22-44): cross product in wrapping i32, then widened.
-__device__ __forceinline__ void add_face_normal(const QuantDev& pos, const TableDev& t, uint32_t c, const int32_t* pc, long long* sum) {
-  int32_t pn[3], pp[3];
-  const Tri pts = load_tri(t.corner_point4, c);
-  load_q<3>(pos, value_index(pos, pts.next), pn);
-  load_q<3>(pos, value_index(pos, pts.prev), pp);
+__device__ __forceinline__ void add_cross(const int32_t* pn, const int32_t* pp, const int32_t* pc, long long* sum) {
   uint32_t dn[3], dp[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) { dn[k] = (uint32_t)pn[k] - (uint32_t)pc[k]; dp[k] = (uint32_t)pp[k] - (uint32_t)pc[k]; }
@@ -443,28 +446,47 @@ __global__ void __launch_bounds__(kThreads) predict_normal_kernel(const uint32_t
     // The reference swings left to the start of the fan (:86-92) and then right, summing the face
     // normals (:94-101). The sum is a wrapping i64 sum (order-independent), so one pass suffices:
     // accumulate while swinging left; only an open fan needs the walk to the right of c as well.
+    // Neighbouring faces of the fan share an edge, i.e. one of the two outer vertices: its position is carried
+    // over (equal vertex => equal position value), so a swing costs one link and one position load.
     long long sum[3] = {0, 0, 0};
-    add_face_normal(pos, t, c, pc, sum);
+    const Tri pts = load_tri(t.corner_point4, c);
+    int32_t first_next[3], shared[3], tip[3];
+    load_q<3>(pos, value_index(pos, pts.next), first_next);
+    load_q<3>(pos, value_index(pos, pts.prev), shared);
+    add_cross(first_next, shared, pc, sum);  // face of c: (next - c) x (prev - c)
     uint32_t cur = c;
     uint32_t guard = t.num_corners;
     bool closed = false;
-    for (;;) {
-      const uint32_t o = masked_opp(t, cnext(cur));
-      if (o == kNoneDev) break;
-      cur = cnext(o);
+    // swing left: across the edge (c, prev); the new face has next = shared vertex, prev = the link's tip.
+    // The link of the following swing is requested before the tip's position is consumed (two loads in flight).
+    uint2 l = fan_link(t, cnext(cur));
+    while (l.x != kNoneDev) {
+      cur = cnext(l.x);
       if (cur == c) { closed = true; break; }
-      add_face_normal(pos, t, cur, pc, sum);
+      const uint2 l_next = fan_link(t, cnext(cur));
+      load_q<3>(pos, value_index(pos, l.y), tip);
+      add_cross(shared, tip, pc, sum);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) shared[k] = tip[k];
+      l = l_next;
       if (--guard == 0) { err |= kErrFanWalk; break; }
     }
     if (!closed) {
       cur = c;
       guard = t.num_corners;
-      for (;;) {
-        const uint32_t o = masked_opp(t, cprev(cur));
-        if (o == kNoneDev) break;
-        cur = cprev(o);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) shared[k] = first_next[k];
+      // swing right: across the edge (c, next); the new face has prev = shared vertex, next = the link's tip
+      l = fan_link(t, cprev(cur));
+      while (l.x != kNoneDev) {
+        cur = cprev(l.x);
         if (cur == c) break;  // cannot happen for an open fan; kept as a guard
-        add_face_normal(pos, t, cur, pc, sum);
+        const uint2 l_next = fan_link(t, cprev(cur));
+        load_q<3>(pos, value_index(pos, l.y), tip);
+        add_cross(tip, shared, pc, sum);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) shared[k] = tip[k];
+        l = l_next;
         if (--guard == 0) { err |= kErrFanWalk; break; }
       }
     }
