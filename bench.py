@@ -31,7 +31,7 @@ METRIC = "Mvertices/s encoded"
 PEAKS_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 # dram__bytes_read.sum + dram__bytes_write.sum per launch on config 2, from the `ncu --set full` capture summarised in
 # profiles/r1_ncu_full_final_summary.md (bytes)
-NCU_TRAFFIC_CONFIG2 = {"K4_predict_parallelogram": 110.7e6, "K5_predict_normal": 118.8e6, "K6_predict_texcoord": 102.7e6}
+NCU_TRAFFIC_CONFIG2 = {"K4_predict_parallelogram": 110.7e6, "K5_predict_normal": 145.9e6, "K6_predict_texcoord": 102.7e6}
 
 
 def parse_args():
