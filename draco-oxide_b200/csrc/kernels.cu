@@ -434,7 +434,7 @@ __device__ __forceinline__ void add_cross(const int32_t* pn, const int32_t* pp, 
 __device__ __forceinline__ int32_t isign(int32_t a) { return (a > 0) - (a < 0); }
 __device__ __forceinline__ int32_t iabs_wrap(int32_t a) { return a < 0 ? (int32_t)(0u - (uint32_t)a) : a; }
 
-__global__ void __launch_bounds__(kThreads) predict_normal_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos,
+__global__ void __launch_bounds__(kThreads, 8) predict_normal_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos,
                                                                   uint32_t* __restrict__ symbols, uint8_t* __restrict__ flips, AttrStats* stats) {
   uint32_t nz = 0, mxs = 0, err = 0;
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -604,7 +604,7 @@ __device__ __forceinline__ void texcoord_fallback(const uint32_t* seq, uint32_t 
   previous_value<2>(seq, i, t, q, pred);
 }
 
-__global__ void __launch_bounds__(kThreads) predict_texcoord_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos,
+__global__ void __launch_bounds__(kThreads, 4) predict_texcoord_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos,
                                                                     uint32_t pos_num_points, const uint32_t* __restrict__ rank,
                                                                     uint32_t* __restrict__ symbols, uint8_t* __restrict__ orient, AttrStats* stats) {
   const WrapParams w = wrap_params(stats);
