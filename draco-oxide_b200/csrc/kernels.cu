@@ -267,10 +267,15 @@ __global__ void __launch_bounds__(kThreads) seq_prepare_kernel(const uint32_t* _
       for (uint32_t k = 0; k < nq; ++k) { mn = min(mn, o[k]); mx = max(mx, o[k]); }
     }
   }
-  if (want_minmax) {
+  if (want_minmax) {  // warp -> CTA -> one global atomic pair per CTA (thousands of warps on one address serialise in L2)
+    __shared__ int32_t s_mn, s_mx;
+    if (threadIdx.x == 0) { s_mn = 0x7FFFFFFF; s_mx = (int32_t)0x80000000; }
+    __syncthreads();
     mn = __reduce_min_sync(0xFFFFFFFFu, mn);
     mx = __reduce_max_sync(0xFFFFFFFFu, mx);
-    if ((threadIdx.x & 31) == 0) { atomicMin(&stats->wrap_min, mn); atomicMax(&stats->wrap_max, mx); }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&s_mn, mn); atomicMax(&s_mx, mx); }
+    __syncthreads();
+    if (threadIdx.x == 0) { atomicMin(&stats->wrap_min, s_mn); atomicMax(&stats->wrap_max, s_mx); }
   }
 }
 
