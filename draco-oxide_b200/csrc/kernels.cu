@@ -1231,7 +1231,7 @@ __global__ void __launch_bounds__(128) rans_explore_kernel(const uint32_t* __res
 // next tile's global loads are in flight while the current tile is walked.
 constexpr int kChainTile = 32;
 __global__ void __launch_bounds__(64) rans_chain_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                        RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, int inject_fault, AttrStats* stats) {
+                                                        RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, AttrStats* stats) {
   __shared__ RansShared sh;
   __shared__ uint32_t tile_s[2][kChainTile][32], tile_e[2][kChainTile][32];
   if (stats->error_flags) return;
@@ -1267,7 +1267,7 @@ __global__ void __launch_bounds__(64) rans_chain_kernel(const uint32_t* __restri
     for (uint32_t r = 0; r < j_end; ++r) {
       const uint32_t j = t * kChainTile + r;
       const uint32_t next_s = r + 1 < j_end ? tile_s[buf][r + 1][lane] : 0u, next_e = r + 1 < j_end ? tile_e[buf][r + 1][lane] : 0u;
-      if (threadIdx.x == 0) cs.start[j] = (inject_fault && j % 5 == 2) ? rans_guess_state(j & 31, 4u << P) : s;
+      if (threadIdx.x == 0) cs.start[j] = s;
       // lanes whose candidate matches hold the same trajectory, hence the same exit state: one OR-reduction hands it
       // over (states are >= l_base > 0, so 0 means that no lane matched)
       const uint32_t hit = __reduce_or_sync(0xFFFFFFFFu, cand_s == s ? cand_e : 0u);
@@ -1288,6 +1288,12 @@ __global__ void __launch_bounds__(64) rans_chain_kernel(const uint32_t* __restri
     __syncthreads();
   }
   if (threadIdx.x == 0) stats->pad[0] = misses;  // chunks whose true state matched no candidate
+}
+
+// tests only (DXO_RANS_FAULT): every fifth chunk gets a wrong entering state, which the fix-up has to repair
+__global__ void rans_fault_kernel(RansChunkState cs, uint32_t num_chunks, AttrStats* stats) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < num_chunks && j % 5 == 2) cs.start[j] = rans_guess_state(j & 31, 4u << stats->precision);
 }
 
 // phase C — every chunk is encoded once from its true entering state (two chunks per CTA)
@@ -1397,7 +1403,8 @@ void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uin
   RansChunkState cs{u, u + J, u + 2 * (size_t)J, u + 3 * (size_t)J, u + 35 * (size_t)J};
   if (J > 1) {
     rans_explore_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, plan.warmup, stats);
-    rans_chain_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, plan.fault, stats);
+    rans_chain_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, stats);
+    if (plan.fault) rans_fault_kernel<<<(J + 255) / 256, 256, 0, s>>>(cs, J, stats);
   }
   rans_encode_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, stats);
   if (J > 1) rans_fixup_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, stats);
