@@ -127,6 +127,21 @@ def test_batch_entry_matches_per_mesh_streams(orc):
         assert g == orc.encode(m)
 
 
+def test_batch_entry_over_all_visible_gpus(orc):
+    """The batch entry shards independent meshes over every visible GPU (one on the default test box, N under
+    `gpurun --gpus N`); results come back in input order and equal the per-mesh streams, large meshes included."""
+    n_gpus = dxo.device_count()
+    counts = list(synth.batch_vertex_counts(20, 500, 30000, seed=9)) + [60000, 90000]
+    ms = [synth.batch_mesh(k, int(c)) for k, c in enumerate(counts)]
+    got = dxo.encode_batch(ms, first_gpu=0, num_gpus=n_gpus)
+    assert len(got) == len(ms)
+    for m, g in zip(ms, got):
+        out = bytearray(); dxo.encode(m, out)
+        assert g == bytes(out)
+    for k in (0, 7, len(ms) - 1):
+        assert got[k] == orc.encode(ms[k])
+
+
 def test_zero_normal_error_code():
     m = synth.grid_mesh(6, 6, 3)
     n = m.attributes[1]
