@@ -95,9 +95,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        """Start of the timed region: nvidia-smi was launched earlier so that it is already sampling."""
+        self.t_begin = time.perf_counter()
 
     def stop(self):
+        t_end = time.perf_counter()
+        t_begin = getattr(self, "t_begin", 0.0)
+        inside = [r for t, r in self.rows if t_begin <= t <= t_end + 0.05]
+        if not inside:  # region shorter than the sampling period: the samples that bracket it
+            inside = [r for t, r in self.rows if t_begin - 0.15 <= t <= t_end + 0.15]
+        self.rows = inside
         if self.proc:
             self.proc.terminate()
             try:
@@ -234,6 +244,8 @@ def main():
         except Exception as e:  # noqa: BLE001
             errors.append(e)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # before the warm-up: nvidia-smi needs a moment to start, the timed region may be short
     threads = [threading.Thread(target=worker, args=(i,)) for i in range(S)]
     for th in threads:
         th.start()
@@ -241,9 +253,8 @@ def main():
     if errors:
         go.wait()
         raise errors[0]
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    sampler.mark_begin()
     go.wait()
     for th in threads:
         th.join()
@@ -308,6 +319,7 @@ def main():
     sampler2 = ClockSampler(local_rank)
     sampler2.start()
     barrier()
+    sampler2.mark_begin()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 5))
     h2d = d2h = 0
@@ -323,7 +335,7 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
-    sampler2.stop()
+    clocks_e2e = sampler2.stop()
     barrier()
 
     if rank == 0:
@@ -342,7 +354,7 @@ def main():
                                "note": "one mesh at a time on rank 0: bounded by the serial rANS chains and the host-coded side streams"},
             "clocks": clocks_a,
             "e2e": {"value": V * world * e2e_steps / e2e_s / 1e6, "unit": "Mvertices/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "host_connectivity_ms_per_step": host_ms / e2e_steps, "steps": e2e_steps},
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "host_connectivity_ms_per_step": host_ms / e2e_steps, "steps": e2e_steps, "clocks": clocks_e2e},
             "roofline": {"bound": "hbm", "kernel": dom["name"], "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
                          "frac": dom["gbs"] / peak if dom["gbs"] else None,
                          "traffic": NCU_TRAFFIC_CONFIG2.get(dom["name"]) if args.workload == "config2" else None, "peak_source": peak_src,
