@@ -359,3 +359,39 @@ def test_resident_session_graph_replay(orc):
         assert got == [ref]
         assert s.run() == ref
         s.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_large_irregular_meshes(orc, seed):
+    """Meshes above the device-connectivity threshold that are far from the manifold fast path: random triangle soups
+    (non-manifold edges and vertices everywhere), grids with randomly flipped faces (inconsistent orientation), welded
+    points, duplicated attribute values. Whatever K12-K14 flag must come out byte-identical through the host passes."""
+    rng = np.random.default_rng(1000 + seed)
+    if seed % 2 == 0:  # random soup
+        n_pts, n_faces = 2500, 5200
+        faces = rng.integers(0, n_pts, (n_faces, 3))
+        faces = faces[(faces[:, 0] != faces[:, 1]) & (faces[:, 1] != faces[:, 2]) & (faces[:, 0] != faces[:, 2])].astype(np.uint32)
+        pos = rng.integers(0, 40, (n_pts, 3)).astype(np.float32) * 0.25       # many coinciding positions
+        nrm = rng.normal(size=(n_pts, 3)).astype(np.float32)
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        uv = rng.integers(0, 30, (n_pts, 2)).astype(np.float32) / 30
+    else:  # grid with flipped faces and welded columns
+        g = synth.grid_mesh(60, 50, 200 + seed)
+        faces = g.faces.copy()
+        flip = rng.random(faces.shape[0]) < 0.03
+        faces[flip] = faces[flip][:, ::-1]
+        pts = [a.values if a.point_to_value is None else a.values[a.point_to_value] for a in g.attributes]
+        pos, nrm, uv = (p.copy() for p in pts)
+        weld = rng.integers(0, pos.shape[0], 40)
+        pos[weld] = pos[(weld + 1) % pos.shape[0]]                              # pairs of points share a position
+    m = dxo.Mesh(faces, [dxo.Attribute.from_points(pos, 0, 0), dxo.Attribute.from_points(nrm, 1, 1, (0,), 1), dxo.Attribute.from_points(uv, 3, 1, (0,), 2)])
+    m = meshes.drop_unused_points(m)
+    assert m.faces.shape[0] >= 4096
+    try:
+        ref = orc.encode(m)
+    except Exception as e:  # inputs the reference rejects must be rejected with the same status
+        with pytest.raises(dxo.Err) as ge:
+            gpu_encode(m)
+        assert ge.value.status == getattr(e, "status", ge.value.status)
+        return
+    assert gpu_encode(m) == ref
