@@ -1094,7 +1094,7 @@ __device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t
         const uint32_t q0 = hi >> b.y;                                  // floor(x / f): still independent of k
         const bool p1 = x >= a.x, p2 = x >= a.y, p3 = x >= a.z;
         const uint32_t k8 = p2 ? (p3 ? 24u : 16u) : (p1 ? 8u : 0u);
-        if (lane == 0) xk[j] = x + (k8 << 27);                          // x < 2^30; k8/8 in bits 30..31
+        if (emit && lane == 0) xk[j] = x + (k8 << 27);                  // x < 2^30; k8/8 in bits 30..31 (only the byte writer reads it)
         x = (q0 >> k8) * b.z + ((x >> k8) + a.w);
       };
       if (cnt == 32) {
