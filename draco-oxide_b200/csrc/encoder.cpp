@@ -614,6 +614,10 @@ void MeshJob::upload(DeviceContext& ctx) {
     d.rank = dalloc<uint32_t>(V, s);
     d.symbols = dalloc<uint32_t>(M * p.ncomp_q, s);
     d.side = dalloc<uint8_t>(M, s);
+    if (p.scheme == Scheme::Normal || p.scheme == Scheme::TexCoord) {
+      d.side_out = dalloc<uint8_t>(M + 16, s);
+      if (p.scheme == Scheme::TexCoord) { d.side_scratch_bytes = gpu::side_prepare_scratch_bytes((uint32_t)M); d.side_scratch = dalloc<uint8_t>(d.side_scratch_bytes, s); }
+    }
     d.hist = dalloc<uint32_t>(p.hist_capacity, s);
     d.work = dalloc<uint32_t>(3 * (size_t)p.hist_capacity, s);
     d.rans_table = dalloc<uint4>(p.hist_capacity + 1, s);
@@ -680,7 +684,7 @@ void MeshJob::launch_graph(DeviceContext& ctx, Profile& prof) {
   if (!graph_exec_ || graph_ctx_ != &ctx) {
     if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
     // everything the captured sequence would allocate lazily exists before the capture starts
-    for (size_t i = 0; i < plans_.size(); ++i) if (side_ready_[i]) ctx.pinned_buffer(2 * i + 1, sequence_of(i).size());
+    for (size_t i = 0; i < plans_.size(); ++i) if (side_ready_[i]) ctx.pinned_buffer(2 * i + 1, sequence_of(i).size() + 16);
     if (!ev_graph_done_) cuda_check(cudaEventCreateWithFlags(&ev_graph_done_, cudaEventDisableTiming), "cudaEventCreate");
     for (int k = 0; k < 3; ++k) cuda_check(cudaStreamSynchronize(ctx.stream[k]), "cudaStreamSynchronize");
     cuda_check(cudaStreamSynchronize(ctx.copy_stream), "cudaStreamSynchronize");
@@ -781,7 +785,7 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
         const AttrDevice& pd = dev_[p.parent];
         const gpu::QuantDev pos{pd.quant, pd.map, 3};
         prof.begin("K5_predict_normal", 4ull * M + 4 * C + C + 4 * C + 4 * C + 12 * Upos + 8 * U + 4 * S + M, s);
-        gpu::launch_predict_normal(d.seq, M, t, q, pos, d.symbols, d.side, d.stats, s);
+        gpu::launch_predict_normal(d.seq, M, t, q, pos, d.symbols, d.side_out + 8, d.stats, s);  // flips go straight behind the scalars
         prof.end(s);
         break;
       }
@@ -802,14 +806,24 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     prof.begin("K8_histogram", 4 * S, s);
     gpu::launch_histogram(d.symbols, S, d.hist, p.hist_capacity, d.stats, s);
     prof.end(s);
-    if (side_ready_[i]) {  // flags leave for the host as soon as the predictor is done; the host codes them during K8-K10
-      uint8_t* host = ctx.pinned_buffer(2 * i + 1, M);
+    if (side_ready_[i]) {
+      // The side stream input leaves for the host as soon as it is ready; the host codes it during K9-K10. What is
+      // data-parallel about it is done here: flips are counted, orientation flags compacted and their transitions counted.
+      uint8_t* host = ctx.pinned_buffer(2 * i + 1, M + 16);
+      uint32_t* scalars = (uint32_t*)d.side_out;
+      if (p.scheme == Scheme::Normal) {
+        gpu::launch_count_flips(d.side_out + 8, M, scalars, s);
+        prof.launches += 1;
+      } else {
+        gpu::launch_compact_orientations(d.side, M, d.side_out + 8, scalars, d.side_scratch, d.side_scratch_bytes, s);
+        prof.launches += 2;  // select + transition count (cub's own init kernel not counted)
+      }
       cuda_check(cudaEventRecord(side_ready_[i], s), "cudaEventRecord");
       cuda_check(cudaStreamWaitEvent(ctx.copy_stream, side_ready_[i], 0), "cudaStreamWaitEvent");
-      cuda_check(cudaMemcpyAsync(host, d.side, M, cudaMemcpyDeviceToHost, ctx.copy_stream), "cudaMemcpyAsync D2H");
+      cuda_check(cudaMemcpyAsync(host, d.side_out, M + 8, cudaMemcpyDeviceToHost, ctx.copy_stream), "cudaMemcpyAsync D2H");
       // inside a graph the event the host coder waits for has to be an external event-record node
       cuda_check(cudaEventRecordWithFlags(side_copied_[i], ctx.copy_stream, capturing_ ? cudaEventRecordExternal : cudaEventRecordDefault), "cudaEventRecord");
-      d2h_bytes += M;
+      d2h_bytes += M + 8;
     }
     prof.begin("K9_build_table", 4ull * p.hist_capacity, s);
     gpu::launch_build_table(d.hist, p.hist_capacity, S, d.work, d.rans_table, d.table_bytes, d.table_capacity, d.stats, s);
@@ -829,34 +843,21 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
 // transitions over len + 0.001, backward-delta bits written forward (mesh_prediction_for_texture_coordinates.rs:221-260).
 void MeshJob::encode_side_stream(size_t att) {
   AttrResult& r = results_[att];
-  const uint8_t* flags = r.side;
-  const size_t n = r.side_len;
+  uint32_t scalars[2];
+  memcpy(scalars, r.side, 8);
+  const uint8_t* flags = r.side + 8;
+  const size_t n = scalars[0];
+  if (n > r.side_len) throw Error(DXO_ERR_INTERNAL, "side stream longer than its attribute");
+  r.side_count = (uint32_t)n;
   if (plans_[att].scheme == Scheme::Normal) {
-    uint64_t ones = 0;
-    for (size_t i = 0; i < n; ++i) ones += flags[i];
-    r.side_count = (uint32_t)n;
-    r.side_zero_prob = side_stream_zero_prob(n - ones, (float)n);
+    r.side_zero_prob = side_stream_zero_prob(n - scalars[1], (float)n);  // scalars[1] = flips set
     rabs_encode_forward(flags, n, r.side_zero_prob, r.side_payload);
   } else {
-    // one pass: order-preserving compaction (branch-free) and the transition count; the delta bits
+    // flags[0..n) = orientation values (1 = false, 2 = true) in order, scalars[1] = forward transitions; the delta bits
     // bits[k] = (o[k] == o[k+1]), o[len] = true, are formed inside the coder's loop
-    std::vector<uint8_t>& o = r.side_scratch;
-    o.resize(n + 1);
-    size_t m = 0;
-    uint64_t transitions = 0;
-    uint8_t last = 1;
-    for (size_t i = 0; i < n; ++i) {
-      const uint8_t f = flags[i], bit = (uint8_t)(f >> 1), present = f != 0;
-      o[m] = bit;
-      transitions += present & (uint8_t)(bit != last);
-      last = present ? bit : last;
-      m += present;
-    }
-    r.side_count = (uint32_t)m;
-    r.side_zero_prob = side_stream_zero_prob(transitions, (float)m + 0.001f);
-    o[m] = 1;
-    const uint8_t* ob = o.data();
-    rabs_encode_forward_fn(m, r.side_zero_prob, r.side_payload, [ob](size_t k) { return (uint8_t)(ob[k] == ob[k + 1]); });
+    r.side_zero_prob = side_stream_zero_prob(scalars[1], (float)n + 0.001f);
+    rabs_encode_forward_fn(n, r.side_zero_prob, r.side_payload,
+                           [flags, n](size_t k) { return (uint8_t)(flags[k] == (k + 1 < n ? flags[k + 1] : (uint8_t)2)); });
   }
 }
 
@@ -868,7 +869,7 @@ void MeshJob::download(DeviceContext& ctx) {
   std::vector<std::future<void>> workers;
   for (size_t i = 0; i < plans_.size(); ++i) {
     if (!side_copied_[i]) continue;
-    results_[i].side = ctx.pinned_buffer(2 * i + 1, sequence_of(i).size());
+    results_[i].side = ctx.pinned_buffer(2 * i + 1, sequence_of(i).size() + 16);
     results_[i].side_len = sequence_of(i).size();
     const int device = ctx.device;
     cudaEvent_t ev = side_copied_[i];
@@ -1036,8 +1037,8 @@ void MeshJob::capture_trace(DeviceContext& ctx) {
     { int32_t mm[2] = {r.stats.wrap_min, r.stats.wrap_max}; put(k + "wrap_minmax", mm, 8); }
     { uint32_t bl[2] = {r.stats.bit_length, r.stats.precision}; put(k + "bit_length", bl, 8); }
     std::vector<uint8_t> side;
-    if (p.scheme == Scheme::Normal) side.assign(r.side, r.side + r.side_len);
-    else if (p.scheme == Scheme::TexCoord) for (size_t e = 0; e < r.side_len; ++e) if (r.side[e]) side.push_back(r.side[e] == 2 ? 1 : 0);
+    if (p.scheme == Scheme::Normal) side.assign(r.side + 8, r.side + 8 + r.side_count);
+    else if (p.scheme == Scheme::TexCoord) for (size_t e = 0; e < r.side_count; ++e) side.push_back(r.side[8 + e] == 2 ? 1 : 0);
     put(k + "side_bits", side.data(), side.size());
   }
 }

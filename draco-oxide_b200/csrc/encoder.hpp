@@ -99,6 +99,7 @@ struct AttrDevice {
   // inputs
   float* values = nullptr; uint32_t* map = nullptr;
   uint32_t *corner_vertex = nullptr, *left_most = nullptr, *seq = nullptr; uint8_t* seam = nullptr; uint4* corner_vertex4 = nullptr; uint2* fan_link = nullptr;
+  uint8_t* side_out = nullptr; void* side_scratch = nullptr; size_t side_scratch_bytes = 0;  // [8-byte scalars][flags (+1)] for the host coder
   // intermediates / outputs
   int32_t* quant = nullptr; uint32_t *rank = nullptr, *symbols = nullptr, *hist = nullptr, *work = nullptr;
   uint8_t *side = nullptr, *table_bytes = nullptr, *payload = nullptr, *rans_scratch = nullptr; uint4* rans_table = nullptr;
@@ -110,8 +111,10 @@ struct AttrResult {
   gpu::AttrStats stats;
   const uint8_t* table_bytes = nullptr;  // pinned staging (valid until the next run on this context)
   const uint8_t* payload = nullptr;
-  const uint8_t* side = nullptr;         // per-element flip / orientation flags
-  size_t side_len = 0;
+  // pinned staging of the side stream input: [8 bytes: entries, ones | transitions][flags]; normals: one flip flag per
+  // element, texcoords: the orientation values (1 = false, 2 = true) of the elements that have one, in order
+  const uint8_t* side = nullptr;
+  size_t side_len = 0;                   // elements of the attribute (capacity of the flag area)
   // binary side stream, coded on a host worker while the device runs K8-K10
   uint32_t side_count = 0;
   uint8_t side_zero_prob = 0;

@@ -1413,6 +1413,51 @@ void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uin
 int rans_launch_count(uint64_t num_symbols) { return rans_num_chunks(num_symbols) > 1 ? 5 : 2; }
 
 // ---------------------------------------------------------------------------------------
+// Side-stream preparation for the host coders (mesh_normal_prediction.rs:147-163,
+// mesh_prediction_for_texture_coordinates.rs:221-260). The coding itself is a serial binary rANS on the host; what is
+// data-parallel moves here: K5's flips are counted; K6's per-element flags (0 none / 1 false / 2 true) are compacted in
+// order (cub::DeviceSelect) and the forward transitions (first compared with `true`) are counted.
+// scalars[0] = number of entries, scalars[1] = ones (normals) / transitions (texcoords).
+struct NonZeroFlag {
+  __host__ __device__ bool operator()(uint8_t v) const { return v != 0; }
+};
+__global__ void __launch_bounds__(kThreads) count_ones_kernel(const uint8_t* __restrict__ flags, uint32_t n, uint32_t* scalars) {
+  uint32_t ones = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) ones += __ldcs(flags + i) != 0;
+  ones = __reduce_add_sync(0xFFFFFFFFu, ones);
+  if ((threadIdx.x & 31) == 0 && ones) atomicAdd(scalars + 1, ones);
+  if (blockIdx.x == 0 && threadIdx.x == 0) scalars[0] = n;
+}
+__global__ void __launch_bounds__(kThreads) count_transitions_kernel(const uint8_t* __restrict__ compact, const uint32_t* __restrict__ scalars_in,
+                                                                     uint32_t* scalars) {
+  const uint32_t m = scalars_in[0];
+  uint32_t t = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < m; k += stride) {
+    const uint8_t cur = compact[k], last = k ? compact[k - 1] : (uint8_t)2;  // the scan starts from `true`
+    t += cur != last;
+  }
+  t = __reduce_add_sync(0xFFFFFFFFu, t);
+  if ((threadIdx.x & 31) == 0 && t) atomicAdd(scalars + 1, t);
+}
+size_t side_prepare_scratch_bytes(uint32_t n) {
+  size_t b = 0;
+  cub::DeviceSelect::If(nullptr, b, (const uint8_t*)nullptr, (uint8_t*)nullptr, (uint32_t*)nullptr, (int)n, NonZeroFlag{});
+  return b + 256;
+}
+void launch_count_flips(const uint8_t* flips, uint32_t n, uint32_t* scalars, cudaStream_t s) {
+  cudaMemsetAsync(scalars, 0, 8, s);
+  count_ones_kernel<<<grid_for(n, kThreads * 8), kThreads, 0, s>>>(flips, n, scalars);
+}
+void launch_compact_orientations(const uint8_t* flags, uint32_t n, uint8_t* compact, uint32_t* scalars, void* scratch, size_t scratch_bytes,
+                                 cudaStream_t s) {
+  cudaMemsetAsync(scalars, 0, 8, s);
+  cub::DeviceSelect::If(scratch, scratch_bytes, flags, compact, scalars, (int)n, NonZeroFlag{}, s);
+  count_transitions_kernel<<<grid_for(n, kThreads * 8), kThreads, 0, s>>>(compact, scalars, scalars);
+}
+
+// ---------------------------------------------------------------------------------------
 // K12 — CornerTable::compute_table (corner_table/mod.rs:252-340) for the manifold,
 // consistently oriented case: sort half edges by
 // (min(a,b), max(a,b)); an undirected edge with exactly two half edges of opposite

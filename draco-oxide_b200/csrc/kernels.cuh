@@ -88,6 +88,12 @@ uint32_t rans_num_chunks(uint64_t num_symbols);
 int rans_launch_count(uint64_t num_symbols);  // kernels launch_rans_encode issues
 void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, void* scratch, uint8_t* payload,
                         AttrStats* stats, cudaStream_t s);
+// ---- side-stream preparation (counts / ordered compaction of the K5 / K6 flags; the binary coding stays on the host) ----
+// scalars: two words, [0] = entries, [1] = ones (flips) or transitions (orientations).
+size_t side_prepare_scratch_bytes(uint32_t n);
+void launch_count_flips(const uint8_t* flips, uint32_t n, uint32_t* scalars, cudaStream_t s);
+void launch_compact_orientations(const uint8_t* flags, uint32_t n, uint8_t* compact /*n + 1*/, uint32_t* scalars, void* scratch, size_t scratch_bytes,
+                                 cudaStream_t s);
 // ---- K12: half-edge matching by radix sort (corner_table/mod.rs:252-340, fast path) ----
 // keys/vals/tmp are caller-provided scratch (see corner_table_scratch_bytes).
 size_t corner_table_scratch_bytes(uint64_t num_corners);
