@@ -356,7 +356,7 @@ int dxo_encode_symbols(const uint32_t* symbols, uint64_t n, int device, dxo_byte
     cuda_check(cudaEventRecord(ev[1], s), "rec");
     gpu::launch_build_table(d_hist, cap, n, d_work, d_tab, d_tb, cap * 3 + 16, d_st, s);
     cuda_check(cudaEventRecord(ev[2], s), "rec");
-    gpu::launch_rans_encode(d_sym, n, d_tab, d_scr, d_pay, d_st, s);
+    gpu::launch_rans_encode(d_sym, n, d_tab, cap, d_scr, d_pay, d_st, s);
     cuda_check(cudaEventRecord(ev[3], s), "rec");
     gpu::AttrStats st;
     cuda_check(cudaMemcpyAsync(&st, d_st, sizeof st, cudaMemcpyDeviceToHost, s), "D2H");

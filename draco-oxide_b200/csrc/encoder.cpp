@@ -829,7 +829,7 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     gpu::launch_build_table(d.hist, p.hist_capacity, S, d.work, d.rans_table, d.table_bytes, d.table_capacity, d.stats, s);
     prof.end(s);
     prof.begin("K10_rans_encode", 4 * S, s);
-    gpu::launch_rans_encode(d.symbols, S, d.rans_table, d.rans_scratch, d.payload, d.stats, s);
+    gpu::launch_rans_encode(d.symbols, S, d.rans_table, p.hist_capacity, d.rans_scratch, d.payload, d.stats, s);
     prof.launches += gpu::rans_launch_count(S) - 1;  // explore + chain + encode + fix-up + gather
     prof.end(s);
     if (prof.serial) cuda_check(cudaEventRecord(ctx.ev_serial, s), "cudaEventRecord");

@@ -1031,10 +1031,11 @@ constexpr int kRansLookahead = 3;      // groups of symbols in flight in the pro
 // DXO_RANS_CHUNK and DXO_RANS_WARMUP override them for experiments. Correctness never depends on these values;
 // DXO_RANS_FAULT=1 makes the chain kernel deliberately record a wrong entering state for every fifth chunk
 // (tests of the fix-up path).
-struct RansPlan { uint32_t chunk, warmup; int fault; };
+struct RansPlan { uint32_t chunk, warmup; int fault; int lanes; };
 static RansPlan rans_plan() {
   static RansPlan plan = [] {
-    RansPlan p{4096, 1024, 0};
+    RansPlan p{4096, 1024, 0, 1};
+    if (const char* e = getenv("DXO_RANS_LANES")) p.lanes = atoi(e);  // phase C: 1 = one thread per chunk (default), 0 = one warp pair per chunk
     if (const char* e = getenv("DXO_RANS_FAULT")) p.fault = atoi(e);  // tests: the chain hands out wrong states, the fix-up must repair
     if (const char* e = getenv("DXO_RANS_CHUNK")) p.chunk = (uint32_t)atoi(e);
     if (const char* e = getenv("DXO_RANS_WARMUP")) p.warmup = (uint32_t)atoi(e);
@@ -1318,6 +1319,130 @@ __global__ void __launch_bounds__(128) rans_encode_kernel(const uint32_t* __rest
   }
 }
 
+// phase C, lane-parallel variant — one THREAD per chunk (32 chunks per warp) instead of one warp pair per chunk. All that the
+// serial chain of a chunk needs is one lane, so this spends ~1/20 of the instruction slots of the warp-pair kernel; a lone
+// warp issues its ~40 instructions per step more slowly than the specialised consumer (≈ 50 ns against 32 ns per step), which
+// a single stream pays as latency and concurrent sessions win back several times over as throughput. To keep the inner loop's
+// memory accesses coalesced or in shared memory: per 32 steps the warp loads, for each of its 32 chunks, one coalesced
+// 128-byte row of symbols and parks it in shared memory with a 33-word pitch (conflict-free both ways), the next group's
+// loads are in flight meanwhile; table rows live in shared memory (alphabets up to kLaneSmemRows, else read through L1);
+// bytes are collected in a 64-bit register and written as aligned 32-bit words. A row with f = 2^21, M = 0, cum = 0 is the
+// identity step and stands in for every step outside a chunk, so the loop has no per-lane control flow.
+constexpr int kLaneThreads = 128;          // chunks per CTA (4 warps)
+constexpr uint32_t kLaneSmemRows = 4096;   // 64 KB of table rows in shared memory
+constexpr uint32_t kLanePitch = 33;        // words per staged symbol row
+constexpr uint32_t kLaneDeadSymbol = 0xFFFFFFFFu;
+
+struct RansLane {
+  uint32_t x;               // coder state
+  unsigned long long acc;   // pending output bytes (little end first)
+  uint32_t fill8;           // bits in acc (< 32 between steps)
+  uint8_t* out;             // next aligned word of this chunk's byte string
+};
+
+__device__ __forceinline__ void rans_lane_step(RansLane& L, const uint4 r, uint32_t two_p) {
+  const uint32_t x = L.x;
+  const uint32_t thr = r.x << 10;
+  const uint32_t q0 = (__umulhi(x, r.z) + (r.x == 1u ? 1u : 0u)) >> r.w;  // floor(x / f), see "rANS division"
+  const bool p1 = x >= thr, p2 = (x >> 8) >= thr, p3 = (x >> 16) >= thr;
+  const uint32_t k8 = p2 ? (p3 ? 24u : 16u) : (p1 ? 8u : 0u);
+  L.acc |= (unsigned long long)(x & ((1u << k8) - 1u)) << L.fill8;
+  L.fill8 += k8;
+  if (L.fill8 >= 32) {
+    *reinterpret_cast<uint32_t*>(L.out) = (uint32_t)L.acc;
+    L.out += 4; L.acc >>= 32; L.fill8 -= 32;
+  }
+  L.x = (q0 >> k8) * (two_p - r.x) + ((x >> k8) + r.y);
+}
+
+// 32 steps of every lane; `mine` = this lane's staged symbols, rows[K] = identity row
+template <bool SMEM>
+__device__ __forceinline__ void rans_lane_group(RansLane& L, const uint32_t* mine, const uint4* __restrict__ rows, uint32_t K, uint32_t two_p) {
+  uint32_t s[32];
+  uint4 r[32];
+  const uint4 dead = make_uint4(1u << 21, 0u, 0u, 0u);
+  auto row = [&](uint32_t sym) -> uint4 {
+    if (SMEM) return rows[min(sym, K)];
+    return sym < K ? __ldg(rows + sym) : dead;
+  };
+#pragma unroll
+  for (int t = 0; t < 4; ++t) s[t] = mine[t];
+  r[0] = row(s[0]); r[1] = row(s[1]);
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    if (t + 4 < 32) s[t + 4] = mine[t + 4];
+    if (t + 2 < 32) r[t + 2] = row(s[t + 2]);
+    rans_lane_step(L, r[t], two_p);
+  }
+}
+
+template <bool SMEM>
+__device__ __forceinline__ void rans_encode_lanes_body(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                       uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t C, uint32_t P,
+                                                       uint32_t K, AttrStats* stats) {
+  extern __shared__ uint4 lane_smem[];
+  const uint4* rows = table;
+  if (SMEM) {
+    for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) {
+      uint4 e = __ldg(table + i);
+      if (e.x == 0) e = make_uint4(1u << 21, 0u, 0u, 0u);  // zero-frequency symbols cannot occur in a stream the table was built from
+      lane_smem[i] = e;
+    }
+    if (threadIdx.x == 0) lane_smem[K] = make_uint4(1u << 21, 0u, 0u, 0u);
+    __syncthreads();
+    rows = lane_smem;
+  }
+  uint32_t* stage = reinterpret_cast<uint32_t*>(lane_smem + (SMEM ? K + 1 : 0)) + (threadIdx.x >> 5) * (32 * kLanePitch);
+  const uint32_t lane = threadIdx.x & 31;
+  const unsigned long long j = (unsigned long long)blockIdx.x * kLaneThreads + threadIdx.x;
+  const unsigned long long j0 = j - lane;
+  if (j0 >= num_chunks) return;
+  const uint32_t two_p = 1u << P;
+  uint8_t* out = scratch + j * rans_chunk_capacity(C);
+  const uint32_t in = j == 0 ? (4u << P) : (j < num_chunks ? cs.start[j] : 0u);
+  RansLane L{in, 0ull, 0u, out};
+  const uint32_t groups = C / 32;
+  const unsigned long long e_first = j0 * C + lane;  // lane's step inside chunk row 0, group 0
+  uint32_t nxt[32];
+  auto load_group = [&](uint32_t g) {
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      const unsigned long long e = e_first + (unsigned long long)l * C + 32ull * g;
+      nxt[l] = e < n ? __ldcs(symbols + (n - 1 - e)) : kLaneDeadSymbol;  // steps past the end are identity steps
+    }
+  };
+  auto park_group = [&]() {
+#pragma unroll
+    for (int l = 0; l < 32; ++l) stage[l * kLanePitch + lane] = nxt[l];
+  };
+  load_group(0);
+  park_group();
+  __syncwarp();
+  const uint32_t* mine = stage + lane * kLanePitch;
+  for (uint32_t g = 0; g < groups; ++g) {
+    if (g + 1 < groups) load_group(g + 1);
+    rans_lane_group<SMEM>(L, mine, rows, K, two_p);
+    __syncwarp();
+    if (g + 1 < groups) { park_group(); __syncwarp(); }
+  }
+  if (j < num_chunks) {
+    uint32_t nb = (uint32_t)(L.out - out);
+    for (uint32_t b = 0; b < L.fill8; b += 8) { L.out[b >> 3] = (uint8_t)(L.acc >> b); ++nb; }
+    cs.start[j] = in;
+    cs.exit[j] = L.x;
+    cs.nbytes[j] = nb;
+  }
+}
+__global__ void __launch_bounds__(kLaneThreads) rans_encode_lanes_kernel(const uint32_t* __restrict__ symbols, unsigned long long n,
+                                                                         const uint4* __restrict__ table, uint8_t* __restrict__ scratch,
+                                                                         RansChunkState cs, uint32_t num_chunks, uint32_t C, uint32_t smem_rows,
+                                                                         AttrStats* stats) {
+  if (stats->error_flags) return;
+  const uint32_t P = stats->precision, K = stats->num_table_symbols;
+  if (K < smem_rows) rans_encode_lanes_body<true>(symbols, n, table, scratch, cs, num_chunks, C, P, K, stats);
+  else rans_encode_lanes_body<false>(symbols, n, table, scratch, cs, num_chunks, C, P, K, stats);
+}
+
 // phase D — verification and fix-up (one CTA of one pair). The stream is exact iff every chunk was encoded from the exit
 // state of its predecessor; that is checked in parallel, and only a violated link (which the chain makes impossible unless
 // something upstream went wrong) starts the sequential repair, so exactness never rests on the speculation.
@@ -1393,8 +1518,8 @@ size_t rans_scratch_bytes(uint64_t num_symbols) {
   return J * rans_chunk_capacity(rans_plan().chunk) + 256 + (3 + 64) * J * sizeof(uint32_t) + 64;
 }
 
-void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, void* scratch, uint8_t* payload,
-                        AttrStats* stats, cudaStream_t s) {
+void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, uint32_t table_capacity, void* scratch,
+                        uint8_t* payload, AttrStats* stats, cudaStream_t s) {
   const RansPlan plan = rans_plan();
   const uint32_t J = rans_num_chunks(num_symbols);
   uint8_t* bytes = (uint8_t*)scratch;
@@ -1406,7 +1531,21 @@ void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uin
     rans_chain_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, stats);
     if (plan.fault) rans_fault_kernel<<<(J + 255) / 256, 256, 0, s>>>(cs, J, stats);
   }
-  rans_encode_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, stats);
+  if (plan.lanes) {
+    // shared memory is reserved for what the alphabet bound allows; the kernel reads rows through L1 when K does not fit
+    const uint32_t smem_rows = std::min(table_capacity + 1u, kLaneSmemRows + 1u);
+    const size_t sm = (size_t)smem_rows * 16 + (size_t)(kLaneThreads / 32) * 32 * kLanePitch * 4;
+    static const bool attr_done = [] {
+      cudaFuncSetAttribute(rans_encode_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)((size_t)(kLaneSmemRows + 1) * 16 + (size_t)(kLaneThreads / 32) * 32 * kLanePitch * 4));
+      return true;
+    }();
+    (void)attr_done;
+    rans_encode_lanes_kernel<<<(J + kLaneThreads - 1) / kLaneThreads, kLaneThreads, sm, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk,
+                                                                                               smem_rows, stats);
+  } else {
+    rans_encode_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, stats);
+  }
   if (J > 1) rans_fixup_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, stats);
   rans_gather_kernel<<<J, 256, 0, s>>>(bytes, cs, J, plan.chunk, payload, stats);
 }

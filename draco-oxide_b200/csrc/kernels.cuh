@@ -86,8 +86,8 @@ void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t t
 size_t rans_scratch_bytes(uint64_t num_symbols);
 uint32_t rans_num_chunks(uint64_t num_symbols);
 int rans_launch_count(uint64_t num_symbols);  // kernels launch_rans_encode issues
-void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, void* scratch, uint8_t* payload,
-                        AttrStats* stats, cudaStream_t s);
+void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, uint32_t table_capacity, void* scratch,
+                        uint8_t* payload, AttrStats* stats, cudaStream_t s);
 // ---- side-stream preparation (counts / ordered compaction of the K5 / K6 flags; the binary coding stays on the host) ----
 // scalars: two words, [0] = entries, [1] = ones (flips) or transitions (orientations).
 size_t side_prepare_scratch_bytes(uint32_t n);
