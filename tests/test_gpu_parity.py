@@ -325,6 +325,8 @@ print("ok")
     {"DXO_RANS_CHUNK": "32", "DXO_RANS_WARMUP": "32"},      # smallest chunks, thousands of them
     {"DXO_RANS_CHUNK": "256", "DXO_RANS_WARMUP": "64", "DXO_RANS_FAULT": "1"},  # wrong entering states: the fix-up must repair
     {"DXO_RANS_CHUNK": "1048576", "DXO_RANS_WARMUP": "1024"},  # a single chunk: the sequential coder
+    {"DXO_RANS_LANES": "0"},                                 # encode pass by warp pairs instead of one thread per chunk
+    {"DXO_RANS_LANES": "0", "DXO_RANS_CHUNK": "256", "DXO_RANS_WARMUP": "64", "DXO_RANS_FAULT": "1"},
 ])
 def test_rans_paths_off_the_operating_point(env):
     import os, subprocess, sys
