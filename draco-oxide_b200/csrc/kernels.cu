@@ -1025,6 +1025,7 @@ void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t t
 //     k from three independent compares and a two-level select,
 //     x' = (x >> 8k) + cum + q * (2^P - f), and one STS of (x, k) for the producer.
 // Stages are handed over with named barriers (bar.arrive / bar.sync), one pair per stage.
+constexpr int kRansSub = 4;           // the encode pass works on quarters of an exploration chunk (see phase C)
 constexpr int kRansStages = 3;        // 2 pairs x (3 FULL + 3 EMPTY + 1 END) named barriers = 14 of the 15 available
 constexpr int kRansLookahead = 3;      // groups of symbols in flight in the producer's registers
 // steps per chunk / warm-up steps of the exploration (multiples of 32). Defaults tuned on B200 (profiles/);
@@ -1039,7 +1040,8 @@ static RansPlan rans_plan() {
     if (const char* e = getenv("DXO_RANS_FAULT")) p.fault = atoi(e);  // tests: the chain hands out wrong states, the fix-up must repair
     if (const char* e = getenv("DXO_RANS_CHUNK")) p.chunk = (uint32_t)atoi(e);
     if (const char* e = getenv("DXO_RANS_WARMUP")) p.warmup = (uint32_t)atoi(e);
-    p.chunk = (p.chunk < 32 ? 32 : p.chunk) / 32 * 32;
+    const uint32_t unit = 32u * kRansSub;  // the sub-chunks of the encode pass are whole groups of 32 steps
+    p.chunk = (p.chunk < unit ? unit : p.chunk) / unit * unit;
     p.warmup = p.warmup / 32 * 32;
     return p;
   }();
@@ -1056,6 +1058,7 @@ struct RansShared {
   uint4 rows_b[kRansStages][32];
   uint32_t xk[kRansStages][32];
   uint32_t x_main[32], x_exit[32];  // per consumer lane: state at e_main / after the last step
+  uint32_t x_mid[kRansSub - 1][32]; // ... and at the inner sub-chunk boundaries (e_main + k * sub_groups * 32 steps)
   uint32_t nbytes, err;
 };
 
@@ -1067,7 +1070,7 @@ struct RansShared {
 __device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t* __restrict__ symbols, unsigned long long n,
                                                   const uint4* __restrict__ table, uint32_t K, uint32_t P, unsigned long long e_begin,
                                                   unsigned long long e_main, unsigned long long e_end, uint32_t x_in, uint8_t* __restrict__ out,
-                                                  int bar_base, bool is_consumer, bool emit = true) {
+                                                  int bar_base, bool is_consumer, bool emit = true, uint32_t sub_groups = 0) {
   const uint32_t lane = threadIdx.x & 31;
   const unsigned long long steps = e_end - e_begin;
   const unsigned long long ngroups = (steps + 31) / 32;
@@ -1080,6 +1083,8 @@ __device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t
       const int s = (int)(g % kRansStages);
       const uint32_t cnt = (g + 1 == ngroups) ? (uint32_t)(steps - 32 * g) : 32u;
       if (g == g_main) sh.x_main[lane] = x;
+      if (sub_groups && g > g_main && (g - g_main) % sub_groups == 0 && (g - g_main) / sub_groups < (unsigned long long)kRansSub)
+        sh.x_mid[(g - g_main) / sub_groups - 1][lane] = x;  // state at an inner sub-chunk boundary
       named_bar_sync(bar_base + s);
       const uint32_t ra = (uint32_t)__cvta_generic_to_shared(&sh.rows_a[s][0]);
       const uint32_t rb = (uint32_t)__cvta_generic_to_shared(&sh.rows_b[s][0]);
@@ -1190,9 +1195,15 @@ __device__ __forceinline__ RansRole rans_role() {
   return r;
 }
 
-// chunk state arrays (device scratch): start[J] = entering state each chunk was last encoded from, exit[J] = its exit
-// state, nbytes[J]; cand_start / cand_exit[32 J] = the candidate entering / exit states found by the exploration.
-struct RansChunkState { uint32_t* start; uint32_t* exit; uint32_t* nbytes; uint32_t* cand_start; uint32_t* cand_exit; };
+// chunk state arrays (device scratch): start[] = entering state each piece was last encoded from, exit[] = its exit
+// state, nbytes[]; cand_start / cand_exit[32 J] = the candidate entering / exit states found by the exploration,
+// cand_mid = the candidates' states at the inner sub-chunk boundaries.
+struct RansChunkState {
+  uint32_t* start; uint32_t* exit; uint32_t* nbytes;  // per encoded piece (a chunk, or a sub-chunk in the lane-parallel encode pass)
+  uint32_t* chain_start;                               // per exploration chunk: its true entering state (phase B)
+  uint32_t* cand_start; uint32_t* cand_exit;           // per chunk x 32 lanes
+  uint32_t* cand_mid;                                  // per chunk x (kRansSub - 1) inner boundaries x 32 lanes
+};
 
 __host__ __device__ __forceinline__ uint64_t rans_chunk_capacity(uint32_t chunk) { return 3ull * chunk + 8; }
 
@@ -1218,10 +1229,13 @@ __global__ void __launch_bounds__(128) rans_explore_kernel(const uint32_t* __res
   const unsigned long long e_begin = e_main > kRansWarmup ? e_main - kRansWarmup : 0;
   const uint32_t l_base = 4u << P;
   const uint32_t x_in = e_begin == 0 ? l_base : rans_guess_state(lane, l_base);  // a warm-up from step 0 is the true trajectory
-  rans_encode_range(sh, symbols, n, table, K, P, e_begin, e_main, e_end, x_in, nullptr, role.bar_base, role.is_consumer, false);
+  rans_encode_range(sh, symbols, n, table, K, P, e_begin, e_main, e_end, x_in, nullptr, role.bar_base, role.is_consumer, false,
+                    kRansChunk / kRansSub / 32);
   if (role.is_consumer) {
     cs.cand_start[j * 32 + lane] = sh.x_main[lane];
     cs.cand_exit[j * 32 + lane] = sh.x_exit[lane];
+#pragma unroll
+    for (int k = 0; k < kRansSub - 1; ++k) cs.cand_mid[(j * (kRansSub - 1) + k) * 32 + lane] = sh.x_mid[k][lane];  // unreached boundaries lie past the end
     if (lane == 0 && sh.err) atomicOr(&stats->error_flags, sh.err);
   }
 }
@@ -1268,19 +1282,28 @@ __global__ void __launch_bounds__(64) rans_chain_kernel(const uint32_t* __restri
     for (uint32_t r = 0; r < j_end; ++r) {
       const uint32_t j = t * kChainTile + r;
       const uint32_t next_s = r + 1 < j_end ? tile_s[buf][r + 1][lane] : 0u, next_e = r + 1 < j_end ? tile_e[buf][r + 1][lane] : 0u;
-      if (threadIdx.x == 0) cs.start[j] = s;
+      if (threadIdx.x == 0) cs.chain_start[j] = s;
       // lanes whose candidate matches hold the same trajectory, hence the same exit state: one OR-reduction hands it
       // over (states are >= l_base > 0, so 0 means that no lane matched)
       const uint32_t hit = __reduce_or_sync(0xFFFFFFFFu, cand_s == s ? cand_e : 0u);
       if (hit) {
         s = hit;
       } else {  // both warps see the same values and take this branch together
+        // The chunk is run from the true state here, one sub-chunk at a time, and lane 0's candidate slots are overwritten
+        // with the true states so that the encode pass finds them like any other match.
         const unsigned long long e_main = (unsigned long long)j * kRansChunk;
         const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
-        rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, s, nullptr, 1, is_consumer, false);
-        s = sh.x_exit[0];
+        const uint32_t sub = kRansChunk / kRansSub;
+        if (threadIdx.x == 0) cs.cand_start[(size_t)j * 32] = s;
+        for (int k = 0; k < kRansSub; ++k) {
+          const unsigned long long e0 = e_main + (unsigned long long)k * sub;
+          if (e0 >= e_end) break;
+          rans_encode_range(sh, symbols, n, table, K, P, e0, e0, min(e0 + sub, e_end), s, nullptr, 1, is_consumer, false);
+          s = sh.x_exit[0];
+          if (threadIdx.x == 0 && k + 1 < kRansSub) cs.cand_mid[((size_t)j * (kRansSub - 1) + k) * 32] = s;
+          __syncthreads();  // sh is rewritten by the next piece
+        }
         ++misses;
-        __syncthreads();  // sh is rewritten by the next miss
       }
       cand_s = next_s; cand_e = next_e;
     }
@@ -1294,7 +1317,7 @@ __global__ void __launch_bounds__(64) rans_chain_kernel(const uint32_t* __restri
 // tests only (DXO_RANS_FAULT): every fifth chunk gets a wrong entering state, which the fix-up has to repair
 __global__ void rans_fault_kernel(RansChunkState cs, uint32_t num_chunks, AttrStats* stats) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < num_chunks && j % 5 == 2) cs.start[j] = rans_guess_state(j & 31, 4u << stats->precision);
+  if (j < num_chunks && j % 5 == 2) cs.chain_start[j] = rans_guess_state(j & 31, 4u << stats->precision);
 }
 
 // phase C — every chunk is encoded once from its true entering state (two chunks per CTA)
@@ -1307,7 +1330,7 @@ __global__ void __launch_bounds__(128) rans_encode_kernel(const uint32_t* __rest
   if (j >= num_chunks) return;
   RansShared& sh = sh2[role.pair];
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
-  const uint32_t in = j == 0 ? (4u << P) : cs.start[j];
+  const uint32_t in = j == 0 ? (4u << P) : cs.chain_start[j];
   const unsigned long long e_main = j * kRansChunk;
   const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
   rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, in, scratch + j * rans_chunk_capacity(kRansChunk), role.bar_base, role.is_consumer);
@@ -1378,8 +1401,8 @@ __device__ __forceinline__ void rans_lane_group(RansLane& L, const uint32_t* min
 
 template <bool SMEM>
 __device__ __forceinline__ void rans_encode_lanes_body(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                       uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t C, uint32_t P,
-                                                       uint32_t K, AttrStats* stats) {
+                                                       uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t num_pieces,
+                                                       uint32_t Cs, uint32_t P, uint32_t K, AttrStats* stats) {
   extern __shared__ uint4 lane_smem[];
   const uint4* rows = table;
   if (SMEM) {
@@ -1394,20 +1417,41 @@ __device__ __forceinline__ void rans_encode_lanes_body(const uint32_t* __restric
   }
   uint32_t* stage = reinterpret_cast<uint32_t*>(lane_smem + (SMEM ? K + 1 : 0)) + (threadIdx.x >> 5) * (32 * kLanePitch);
   const uint32_t lane = threadIdx.x & 31;
-  const unsigned long long j = (unsigned long long)blockIdx.x * kLaneThreads + threadIdx.x;
-  const unsigned long long j0 = j - lane;
-  if (j0 >= num_chunks) return;
+  // piece q = sub-chunk (q % kRansSub) of exploration chunk (q / kRansSub); Cs steps each
+  const unsigned long long q = (unsigned long long)blockIdx.x * kLaneThreads + threadIdx.x;
+  const unsigned long long q0 = q - lane;
+  if (q0 >= num_pieces) return;
   const uint32_t two_p = 1u << P;
-  uint8_t* out = scratch + j * rans_chunk_capacity(C);
-  const uint32_t in = j == 0 ? (4u << P) : (j < num_chunks ? cs.start[j] : 0u);
+  // Entering states: a chunk's first piece enters with the chain's state; the inner pieces with the checkpoints of the
+  // exploration lane that the chain matched (it IS the true trajectory from the chunk start on). The warp looks that lane
+  // up for the 32 / kRansSub chunks it covers with one ballot each. No match (never observed) leaves state 0, whose bytes
+  // the verification of phase D rejects and repairs.
+  uint32_t in = 0;
+  {
+    const unsigned long long my_chunk = q / kRansSub;
+    const uint32_t my_sub = (uint32_t)(q % kRansSub);
+#pragma unroll
+    for (int c = 0; c < 32 / kRansSub; ++c) {
+      const unsigned long long jj = q0 / kRansSub + c;
+      if (jj >= num_chunks) break;
+      const uint32_t s_j = jj == 0 ? (4u << P) : __ldg(cs.chain_start + jj);
+      const uint32_t cand = num_chunks > 1 ? cs.cand_start[jj * 32 + lane] : s_j;
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, cand == s_j);
+      if (jj == my_chunk && q < num_pieces) {
+        if (my_sub == 0) in = s_j;
+        else if (m) in = cs.cand_mid[(jj * (kRansSub - 1) + (my_sub - 1)) * 32 + (__ffs(m) - 1)];
+      }
+    }
+  }
+  uint8_t* out = scratch + q * rans_chunk_capacity(Cs);
   RansLane L{in, 0ull, 0u, out};
-  const uint32_t groups = C / 32;
-  const unsigned long long e_first = j0 * C + lane;  // lane's step inside chunk row 0, group 0
+  const uint32_t groups = Cs / 32;
+  const unsigned long long e_first = q0 * Cs + lane;  // lane's step inside piece row 0, group 0
   uint32_t nxt[32];
   auto load_group = [&](uint32_t g) {
 #pragma unroll
     for (int l = 0; l < 32; ++l) {
-      const unsigned long long e = e_first + (unsigned long long)l * C + 32ull * g;
+      const unsigned long long e = e_first + (unsigned long long)l * Cs + 32ull * g;
       nxt[l] = e < n ? __ldcs(symbols + (n - 1 - e)) : kLaneDeadSymbol;  // steps past the end are identity steps
     }
   };
@@ -1425,22 +1469,22 @@ __device__ __forceinline__ void rans_encode_lanes_body(const uint32_t* __restric
     __syncwarp();
     if (g + 1 < groups) { park_group(); __syncwarp(); }
   }
-  if (j < num_chunks) {
+  if (q < num_pieces) {
     uint32_t nb = (uint32_t)(L.out - out);
     for (uint32_t b = 0; b < L.fill8; b += 8) { L.out[b >> 3] = (uint8_t)(L.acc >> b); ++nb; }
-    cs.start[j] = in;
-    cs.exit[j] = L.x;
-    cs.nbytes[j] = nb;
+    cs.start[q] = in;
+    cs.exit[q] = L.x;
+    cs.nbytes[q] = nb;
   }
 }
 __global__ void __launch_bounds__(kLaneThreads) rans_encode_lanes_kernel(const uint32_t* __restrict__ symbols, unsigned long long n,
                                                                          const uint4* __restrict__ table, uint8_t* __restrict__ scratch,
-                                                                         RansChunkState cs, uint32_t num_chunks, uint32_t C, uint32_t smem_rows,
-                                                                         AttrStats* stats) {
+                                                                         RansChunkState cs, uint32_t num_chunks, uint32_t num_pieces, uint32_t Cs,
+                                                                         uint32_t smem_rows, AttrStats* stats) {
   if (stats->error_flags) return;
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
-  if (K < smem_rows) rans_encode_lanes_body<true>(symbols, n, table, scratch, cs, num_chunks, C, P, K, stats);
-  else rans_encode_lanes_body<false>(symbols, n, table, scratch, cs, num_chunks, C, P, K, stats);
+  if (K < smem_rows) rans_encode_lanes_body<true>(symbols, n, table, scratch, cs, num_chunks, num_pieces, Cs, P, K, stats);
+  else rans_encode_lanes_body<false>(symbols, n, table, scratch, cs, num_chunks, num_pieces, Cs, P, K, stats);
 }
 
 // phase D — verification and fix-up (one CTA of one pair). The stream is exact iff every chunk was encoded from the exit
@@ -1513,25 +1557,35 @@ __global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restr
 }
 
 uint32_t rans_num_chunks(uint64_t num_symbols) { const uint32_t c = rans_plan().chunk; return (uint32_t)((num_symbols + c - 1) / c); }
+// pieces of the encode pass: sub-chunks with the lane-parallel kernel, whole chunks with the warp-pair kernel
+static uint32_t rans_piece_steps() { const RansPlan p = rans_plan(); return p.lanes ? p.chunk / kRansSub : p.chunk; }
+static uint32_t rans_num_pieces(uint64_t num_symbols) { const uint32_t c = rans_piece_steps(); return (uint32_t)((num_symbols + c - 1) / c); }
 size_t rans_scratch_bytes(uint64_t num_symbols) {
-  const size_t J = rans_num_chunks(num_symbols);
-  return J * rans_chunk_capacity(rans_plan().chunk) + 256 + (3 + 64) * J * sizeof(uint32_t) + 64;
+  // either layout of launch_rans_encode must fit: pieces = sub-chunks (lane-parallel encode) or whole chunks (warp pairs)
+  const size_t J = rans_num_chunks(num_symbols), Q = std::max<size_t>(rans_num_pieces(num_symbols), J);
+  const size_t area = std::max(Q * rans_chunk_capacity(rans_piece_steps()), J * rans_chunk_capacity(rans_plan().chunk));
+  return area + 512 + (3 * Q + J + 64 * J + 32 * (kRansSub - 1) * J) * sizeof(uint32_t) + 64;
 }
 
 void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, uint32_t table_capacity, void* scratch,
                         uint8_t* payload, AttrStats* stats, cudaStream_t s) {
   const RansPlan plan = rans_plan();
   const uint32_t J = rans_num_chunks(num_symbols);
+  const bool lanes = plan.lanes && J > 1;  // a single chunk has no exploration, hence no checkpoints: one warp pair codes it
+  const uint32_t Q = lanes ? rans_num_pieces(num_symbols) : J, piece = lanes ? rans_piece_steps() : plan.chunk;
   uint8_t* bytes = (uint8_t*)scratch;
-  size_t off = ((size_t)J * rans_chunk_capacity(plan.chunk) + 255) / 256 * 256;
+  size_t off = ((size_t)Q * rans_chunk_capacity(piece) + 255) / 256 * 256;
   uint32_t* u = (uint32_t*)(bytes + off);
-  RansChunkState cs{u, u + J, u + 2 * (size_t)J, u + 3 * (size_t)J, u + 35 * (size_t)J};
+  RansChunkState cs;
+  cs.start = u; cs.exit = u + Q; cs.nbytes = u + 2 * (size_t)Q;
+  cs.chain_start = u + 3 * (size_t)Q;
+  cs.cand_start = cs.chain_start + J; cs.cand_exit = cs.cand_start + 32 * (size_t)J; cs.cand_mid = cs.cand_exit + 32 * (size_t)J;
   if (J > 1) {
     rans_explore_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, plan.warmup, stats);
     rans_chain_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, stats);
     if (plan.fault) rans_fault_kernel<<<(J + 255) / 256, 256, 0, s>>>(cs, J, stats);
   }
-  if (plan.lanes) {
+  if (lanes) {
     // shared memory is reserved for what the alphabet bound allows; the kernel reads rows through L1 when K does not fit
     const uint32_t smem_rows = std::min(table_capacity + 1u, kLaneSmemRows + 1u);
     const size_t sm = (size_t)smem_rows * 16 + (size_t)(kLaneThreads / 32) * 32 * kLanePitch * 4;
@@ -1541,13 +1595,13 @@ void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uin
       return true;
     }();
     (void)attr_done;
-    rans_encode_lanes_kernel<<<(J + kLaneThreads - 1) / kLaneThreads, kLaneThreads, sm, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk,
+    rans_encode_lanes_kernel<<<(Q + kLaneThreads - 1) / kLaneThreads, kLaneThreads, sm, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, Q, piece,
                                                                                                smem_rows, stats);
   } else {
     rans_encode_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, stats);
   }
-  if (J > 1) rans_fixup_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, stats);
-  rans_gather_kernel<<<J, 256, 0, s>>>(bytes, cs, J, plan.chunk, payload, stats);
+  if (Q > 1) rans_fixup_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, Q, piece, stats);
+  rans_gather_kernel<<<Q, 256, 0, s>>>(bytes, cs, Q, piece, payload, stats);
 }
 int rans_launch_count(uint64_t num_symbols) { return rans_num_chunks(num_symbols) > 1 ? 5 : 2; }
 
