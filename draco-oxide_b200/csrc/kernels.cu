@@ -1025,24 +1025,28 @@ void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t t
 //     k from three independent compares and a two-level select,
 //     x' = (x >> 8k) + cum + q * (2^P - f), and one STS of (x, k) for the producer.
 // Stages are handed over with named barriers (bar.arrive / bar.sync), one pair per stage.
-constexpr int kRansSub = 4;           // the encode pass works on quarters of an exploration chunk (see phase C)
+constexpr int kRansSubMax = 16;       // the encode pass works on up to 16 sub-chunks of an exploration chunk (see phase C)
 constexpr int kRansStages = 3;        // 2 pairs x (3 FULL + 3 EMPTY + 1 END) named barriers = 14 of the 15 available
 constexpr int kRansLookahead = 3;      // groups of symbols in flight in the producer's registers
 // steps per chunk / warm-up steps of the exploration (multiples of 32). Defaults tuned on B200 (profiles/);
 // DXO_RANS_CHUNK and DXO_RANS_WARMUP override them for experiments. Correctness never depends on these values;
 // DXO_RANS_FAULT=1 makes the chain kernel deliberately record a wrong entering state for every fifth chunk
 // (tests of the fix-up path).
-struct RansPlan { uint32_t chunk, warmup; int fault; int lanes; };
+struct RansPlan { uint32_t chunk, warmup; int fault; int lanes; uint32_t sub; };
 static RansPlan rans_plan() {
   static RansPlan plan = [] {
-    RansPlan p{4096, 1024, 0, 1};
+    RansPlan p{4096, 1024, 0, 1, (uint32_t)kRansSubMax};
     if (const char* e = getenv("DXO_RANS_LANES")) p.lanes = atoi(e);  // phase C: 1 = one thread per chunk (default), 0 = one warp pair per chunk
     if (const char* e = getenv("DXO_RANS_FAULT")) p.fault = atoi(e);  // tests: the chain hands out wrong states, the fix-up must repair
     if (const char* e = getenv("DXO_RANS_CHUNK")) p.chunk = (uint32_t)atoi(e);
     if (const char* e = getenv("DXO_RANS_WARMUP")) p.warmup = (uint32_t)atoi(e);
-    const uint32_t unit = 32u * kRansSub;  // the sub-chunks of the encode pass are whole groups of 32 steps
-    p.chunk = (p.chunk < unit ? unit : p.chunk) / unit * unit;
+    if (const char* e = getenv("DXO_RANS_SUB")) p.sub = (uint32_t)atoi(e);
+    p.chunk = (p.chunk < 32u ? 32u : p.chunk) / 32u * 32u;
     p.warmup = p.warmup / 32 * 32;
+    // sub-chunks are whole groups of 32 steps and a warp of the encode pass covers whole chunks: a power of two <= 16
+    uint32_t sub = 1;
+    while (sub * 2 <= p.sub && sub * 2 <= (uint32_t)kRansSubMax && p.chunk % (64u * sub) == 0) sub *= 2;
+    p.sub = sub;
     return p;
   }();
   return plan;
@@ -1058,7 +1062,7 @@ struct RansShared {
   uint4 rows_b[kRansStages][32];
   uint32_t xk[kRansStages][32];
   uint32_t x_main[32], x_exit[32];  // per consumer lane: state at e_main / after the last step
-  uint32_t x_mid[kRansSub - 1][32]; // ... and at the inner sub-chunk boundaries (e_main + k * sub_groups * 32 steps)
+  uint32_t x_mid[kRansSubMax - 1][32]; // ... and at the inner sub-chunk boundaries (e_main + k * sub_groups * 32 steps)
   uint32_t nbytes, err;
 };
 
@@ -1083,7 +1087,7 @@ __device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t
       const int s = (int)(g % kRansStages);
       const uint32_t cnt = (g + 1 == ngroups) ? (uint32_t)(steps - 32 * g) : 32u;
       if (g == g_main) sh.x_main[lane] = x;
-      if (sub_groups && g > g_main && (g - g_main) % sub_groups == 0 && (g - g_main) / sub_groups < (unsigned long long)kRansSub)
+      if (sub_groups && g > g_main && (g - g_main) % sub_groups == 0 && (g - g_main) / sub_groups < (unsigned long long)kRansSubMax)
         sh.x_mid[(g - g_main) / sub_groups - 1][lane] = x;  // state at an inner sub-chunk boundary
       named_bar_sync(bar_base + s);
       const uint32_t ra = (uint32_t)__cvta_generic_to_shared(&sh.rows_a[s][0]);
@@ -1185,13 +1189,15 @@ __device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t
 }
 
 // role / pair of the calling warp inside a 128-thread CTA (two pairs); odd CTAs swap roles
+// (CTAs are handed to the SMs wave by wave, CTA b, b + num_sms, b + 2 num_sms ... landing on one SM: the swap follows
+// b + b / num_sms so that the consumers of successive waves alternate between the schedulers {0, 2} and {1, 3}.)
 struct RansRole { int pair; int bar_base; bool is_consumer; };
-__device__ __forceinline__ RansRole rans_role() {
+__device__ __forceinline__ RansRole rans_role(uint32_t num_sms) {
   const int warp = threadIdx.x >> 5;
   RansRole r;
   r.pair = warp >> 1;
   r.bar_base = 1 + r.pair * (2 * kRansStages + 1);
-  r.is_consumer = (warp & 1) == (int)(blockIdx.x & 1);
+  r.is_consumer = (warp & 1) == (int)((blockIdx.x + blockIdx.x / num_sms) & 1);
   return r;
 }
 
@@ -1202,7 +1208,8 @@ struct RansChunkState {
   uint32_t* start; uint32_t* exit; uint32_t* nbytes;  // per encoded piece (a chunk, or a sub-chunk in the lane-parallel encode pass)
   uint32_t* chain_start;                               // per exploration chunk: its true entering state (phase B)
   uint32_t* cand_start; uint32_t* cand_exit;           // per chunk x 32 lanes
-  uint32_t* cand_mid;                                  // per chunk x (kRansSub - 1) inner boundaries x 32 lanes
+  uint32_t* cand_mid;                                  // per chunk x (sub - 1) inner boundaries x 32 lanes
+  uint32_t* offset;                                    // per piece: where its bytes go in the payload (phase D)
 };
 
 __host__ __device__ __forceinline__ uint64_t rans_chunk_capacity(uint32_t chunk) { return 3ull * chunk + 8; }
@@ -1215,10 +1222,11 @@ __device__ __forceinline__ uint32_t rans_guess_state(uint32_t lane, uint32_t l_b
 
 // phase A — exploration (two chunks per CTA): no bytes, 32 candidate (entering state -> exit state) pairs per chunk
 __global__ void __launch_bounds__(128) rans_explore_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                           RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, uint32_t kRansWarmup, AttrStats* stats) {
+                                                           RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, uint32_t kRansWarmup, uint32_t sub,
+                                                           uint32_t num_sms, AttrStats* stats) {
   __shared__ RansShared sh2[2];
   if (stats->error_flags) return;
-  const RansRole role = rans_role();
+  const RansRole role = rans_role(num_sms);
   const unsigned long long j = 2ull * blockIdx.x + role.pair;
   if (j >= num_chunks) return;  // both warps of the pair leave together
   RansShared& sh = sh2[role.pair];
@@ -1230,12 +1238,11 @@ __global__ void __launch_bounds__(128) rans_explore_kernel(const uint32_t* __res
   const uint32_t l_base = 4u << P;
   const uint32_t x_in = e_begin == 0 ? l_base : rans_guess_state(lane, l_base);  // a warm-up from step 0 is the true trajectory
   rans_encode_range(sh, symbols, n, table, K, P, e_begin, e_main, e_end, x_in, nullptr, role.bar_base, role.is_consumer, false,
-                    kRansChunk / kRansSub / 32);
+                    kRansChunk / sub / 32);
   if (role.is_consumer) {
     cs.cand_start[j * 32 + lane] = sh.x_main[lane];
     cs.cand_exit[j * 32 + lane] = sh.x_exit[lane];
-#pragma unroll
-    for (int k = 0; k < kRansSub - 1; ++k) cs.cand_mid[(j * (kRansSub - 1) + k) * 32 + lane] = sh.x_mid[k][lane];  // unreached boundaries lie past the end
+    for (uint32_t k = 0; k + 1 < sub; ++k) cs.cand_mid[(j * (sub - 1) + k) * 32 + lane] = sh.x_mid[k][lane];  // unreached boundaries lie past the end
     if (lane == 0 && sh.err) atomicOr(&stats->error_flags, sh.err);
   }
 }
@@ -1246,7 +1253,7 @@ __global__ void __launch_bounds__(128) rans_explore_kernel(const uint32_t* __res
 // next tile's global loads are in flight while the current tile is walked.
 constexpr int kChainTile = 32;
 __global__ void __launch_bounds__(64) rans_chain_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                        RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, AttrStats* stats) {
+                                                        RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, uint32_t nsub, AttrStats* stats) {
   __shared__ RansShared sh;
   __shared__ uint32_t tile_s[2][kChainTile][32], tile_e[2][kChainTile][32];
   if (stats->error_flags) return;
@@ -1293,14 +1300,14 @@ __global__ void __launch_bounds__(64) rans_chain_kernel(const uint32_t* __restri
         // with the true states so that the encode pass finds them like any other match.
         const unsigned long long e_main = (unsigned long long)j * kRansChunk;
         const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
-        const uint32_t sub = kRansChunk / kRansSub;
+        const uint32_t sub = kRansChunk / nsub;
         if (threadIdx.x == 0) cs.cand_start[(size_t)j * 32] = s;
-        for (int k = 0; k < kRansSub; ++k) {
+        for (uint32_t k = 0; k < nsub; ++k) {
           const unsigned long long e0 = e_main + (unsigned long long)k * sub;
           if (e0 >= e_end) break;
           rans_encode_range(sh, symbols, n, table, K, P, e0, e0, min(e0 + sub, e_end), s, nullptr, 1, is_consumer, false);
           s = sh.x_exit[0];
-          if (threadIdx.x == 0 && k + 1 < kRansSub) cs.cand_mid[((size_t)j * (kRansSub - 1) + k) * 32] = s;
+          if (threadIdx.x == 0 && k + 1 < nsub) cs.cand_mid[((size_t)j * (nsub - 1) + k) * 32] = s;
           __syncthreads();  // sh is rewritten by the next piece
         }
         ++misses;
@@ -1322,10 +1329,11 @@ __global__ void rans_fault_kernel(RansChunkState cs, uint32_t num_chunks, AttrSt
 
 // phase C — every chunk is encoded once from its true entering state (two chunks per CTA)
 __global__ void __launch_bounds__(128) rans_encode_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                          uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, AttrStats* stats) {
+                                                          uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, uint32_t num_sms,
+                                                          AttrStats* stats) {
   __shared__ RansShared sh2[2];
   if (stats->error_flags) return;
-  const RansRole role = rans_role();
+  const RansRole role = rans_role(num_sms);
   const unsigned long long j = 2ull * blockIdx.x + role.pair;
   if (j >= num_chunks) return;
   RansShared& sh = sh2[role.pair];
@@ -1402,7 +1410,7 @@ __device__ __forceinline__ void rans_lane_group(RansLane& L, const uint32_t* min
 template <bool SMEM>
 __device__ __forceinline__ void rans_encode_lanes_body(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
                                                        uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t num_pieces,
-                                                       uint32_t Cs, uint32_t P, uint32_t K, AttrStats* stats) {
+                                                       uint32_t Cs, uint32_t sub, uint32_t P, uint32_t K, AttrStats* stats) {
   extern __shared__ uint4 lane_smem[];
   const uint4* rows = table;
   if (SMEM) {
@@ -1417,29 +1425,28 @@ __device__ __forceinline__ void rans_encode_lanes_body(const uint32_t* __restric
   }
   uint32_t* stage = reinterpret_cast<uint32_t*>(lane_smem + (SMEM ? K + 1 : 0)) + (threadIdx.x >> 5) * (32 * kLanePitch);
   const uint32_t lane = threadIdx.x & 31;
-  // piece q = sub-chunk (q % kRansSub) of exploration chunk (q / kRansSub); Cs steps each
+  // piece q = sub-chunk (q % sub) of exploration chunk (q / sub); Cs steps each
   const unsigned long long q = (unsigned long long)blockIdx.x * kLaneThreads + threadIdx.x;
   const unsigned long long q0 = q - lane;
   if (q0 >= num_pieces) return;
   const uint32_t two_p = 1u << P;
   // Entering states: a chunk's first piece enters with the chain's state; the inner pieces with the checkpoints of the
   // exploration lane that the chain matched (it IS the true trajectory from the chunk start on). The warp looks that lane
-  // up for the 32 / kRansSub chunks it covers with one ballot each. No match (never observed) leaves state 0, whose bytes
+  // up for the 32 / sub chunks it covers with one ballot each. No match (never observed) leaves state 0, whose bytes
   // the verification of phase D rejects and repairs.
   uint32_t in = 0;
   {
-    const unsigned long long my_chunk = q / kRansSub;
-    const uint32_t my_sub = (uint32_t)(q % kRansSub);
-#pragma unroll
-    for (int c = 0; c < 32 / kRansSub; ++c) {
-      const unsigned long long jj = q0 / kRansSub + c;
+    const unsigned long long my_chunk = q / sub;
+    const uint32_t my_sub = (uint32_t)(q % sub);
+    for (uint32_t c = 0; c < 32u / sub; ++c) {
+      const unsigned long long jj = q0 / sub + c;
       if (jj >= num_chunks) break;
       const uint32_t s_j = jj == 0 ? (4u << P) : __ldg(cs.chain_start + jj);
       const uint32_t cand = num_chunks > 1 ? cs.cand_start[jj * 32 + lane] : s_j;
       const uint32_t m = __ballot_sync(0xFFFFFFFFu, cand == s_j);
       if (jj == my_chunk && q < num_pieces) {
         if (my_sub == 0) in = s_j;
-        else if (m) in = cs.cand_mid[(jj * (kRansSub - 1) + (my_sub - 1)) * 32 + (__ffs(m) - 1)];
+        else if (m) in = cs.cand_mid[(jj * (sub - 1) + (my_sub - 1)) * 32 + (__ffs(m) - 1)];
       }
     }
   }
@@ -1480,69 +1487,92 @@ __device__ __forceinline__ void rans_encode_lanes_body(const uint32_t* __restric
 __global__ void __launch_bounds__(kLaneThreads) rans_encode_lanes_kernel(const uint32_t* __restrict__ symbols, unsigned long long n,
                                                                          const uint4* __restrict__ table, uint8_t* __restrict__ scratch,
                                                                          RansChunkState cs, uint32_t num_chunks, uint32_t num_pieces, uint32_t Cs,
-                                                                         uint32_t smem_rows, AttrStats* stats) {
+                                                                         uint32_t sub, uint32_t smem_rows, AttrStats* stats) {
   if (stats->error_flags) return;
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
-  if (K < smem_rows) rans_encode_lanes_body<true>(symbols, n, table, scratch, cs, num_chunks, num_pieces, Cs, P, K, stats);
-  else rans_encode_lanes_body<false>(symbols, n, table, scratch, cs, num_chunks, num_pieces, Cs, P, K, stats);
+  if (K < smem_rows) rans_encode_lanes_body<true>(symbols, n, table, scratch, cs, num_chunks, num_pieces, Cs, sub, P, K, stats);
+  else rans_encode_lanes_body<false>(symbols, n, table, scratch, cs, num_chunks, num_pieces, Cs, sub, P, K, stats);
 }
 
-// phase D — verification and fix-up (one CTA of one pair). The stream is exact iff every chunk was encoded from the exit
-// state of its predecessor; that is checked in parallel, and only a violated link (which the chain makes impossible unless
-// something upstream went wrong) starts the sequential repair, so exactness never rests on the speculation.
-__global__ void __launch_bounds__(64) rans_fixup_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                        uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk,
-                                                        AttrStats* stats) {
+// phase D — verification, fix-up and payload offsets (one CTA). The stream is exact iff every piece was encoded from the exit
+// state of its predecessor; that is checked in parallel by the whole CTA, and only a violated link (which the chain makes
+// impossible unless something upstream went wrong) starts the sequential repair by the CTA's first warp pair, so exactness
+// never rests on the speculation. Then the exclusive prefix sum of the pieces' byte counts is left in cs.offset.
+constexpr int kFixupThreads = 1024;
+constexpr int kFixupPairBarrier = 2 * kRansStages + 2;  // named barrier of the repairing pair (rans_encode_range with bar_base 1 uses 1..7)
+__global__ void __launch_bounds__(kFixupThreads) rans_fixup_kernel(const uint32_t* __restrict__ symbols, unsigned long long n,
+                                                                   const uint4* __restrict__ table, uint8_t* __restrict__ scratch, RansChunkState cs,
+                                                                   uint32_t num_chunks, uint32_t kRansChunk, AttrStats* stats) {
   __shared__ RansShared sh;
-  __shared__ uint32_t s_in, s_bad;
+  __shared__ uint32_t s_in, s_bad, s_warp[kFixupThreads / 32];
   if (stats->error_flags) return;
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
   const uint32_t l_base = 4u << P;
-  const bool is_consumer = threadIdx.x < 32;
   if (threadIdx.x == 0) s_bad = 0;
   __syncthreads();
-  for (uint32_t j = threadIdx.x; j < num_chunks; j += blockDim.x)
-    if ((j == 0 ? l_base : cs.exit[j - 1]) != cs.start[j]) s_bad = 1;
+  {
+    uint32_t bad = 0;
+    for (uint32_t j = threadIdx.x; j < num_chunks; j += kFixupThreads) bad |= (j == 0 ? l_base : __ldcg(cs.exit + j - 1)) != __ldcg(cs.start + j);
+    if (bad) s_bad = 1;
+  }
   __syncthreads();
-  if (!s_bad) return;
-  for (uint32_t j = 0; j < num_chunks; ++j) {
-    if (threadIdx.x == 0) s_in = j == 0 ? l_base : cs.exit[j - 1];
-    __syncthreads();
-    const uint32_t in = s_in;
-    __syncthreads();                  // s_in is rewritten by thread 0 in the next iteration
-    if (in == cs.start[j]) continue;  // uniform: every thread reads the same values
-    const unsigned long long e_main = (unsigned long long)j * kRansChunk;
-    const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
-    rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, in, scratch + (unsigned long long)j * rans_chunk_capacity(kRansChunk), 1, is_consumer);
-    if (threadIdx.x == 0) {
-      cs.start[j] = in;
-      cs.exit[j] = sh.x_exit[0];
-      cs.nbytes[j] = sh.nbytes;
-      stats->pad[1] += 1;  // chunks re-encoded by the sequential fix-up
-      if (sh.err) atomicOr(&stats->error_flags, sh.err);
+  if (s_bad && threadIdx.x < 64) {
+    const bool is_consumer = threadIdx.x < 32;
+    for (uint32_t j = 0; j < num_chunks; ++j) {
+      if (threadIdx.x == 0) s_in = j == 0 ? l_base : cs.exit[j - 1];
+      named_bar_sync(kFixupPairBarrier);
+      const uint32_t in = s_in;
+      named_bar_sync(kFixupPairBarrier);  // s_in is rewritten by thread 0 in the next iteration
+      if (in == cs.start[j]) continue;    // uniform: both warps read the same values
+      const unsigned long long e_main = (unsigned long long)j * kRansChunk;
+      const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
+      rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, in, scratch + (unsigned long long)j * rans_chunk_capacity(kRansChunk), 1, is_consumer);
+      if (threadIdx.x == 0) {
+        cs.start[j] = in;
+        cs.exit[j] = sh.x_exit[0];
+        cs.nbytes[j] = sh.nbytes;
+        stats->pad[1] += 1;  // pieces re-encoded by the sequential fix-up
+        if (sh.err) atomicOr(&stats->error_flags, sh.err);
+      }
+      named_bar_sync(kFixupPairBarrier);
     }
+  }
+  __syncthreads();
+  // exclusive scan of nbytes, a tile of kFixupThreads pieces at a time
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < num_chunks; base += kFixupThreads) {
+    const uint32_t j = base + threadIdx.x;
+    const uint32_t v = j < num_chunks ? cs.nbytes[j] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= (uint32_t)d) inc += o; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t w = s_warp[lane];  // kFixupThreads / 32 == 32 partial sums
+    uint32_t winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, winc, d); if (lane >= (uint32_t)d) winc += o; }
+    const uint32_t before = __shfl_sync(0xFFFFFFFFu, winc - w, warp);
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, winc, 31);
+    if (j < num_chunks) cs.offset[j] = carry + before + (inc - v);
+    carry += total;
     __syncthreads();
   }
 }
 
-// gather: chunk j's bytes go to payload[sum_{i<j} nbytes[i]]; the last CTA appends the flush bytes
+// gather: piece j's bytes go to payload[offset[j]]; the last piece's threads append the flush bytes. A CTA copies
+// `pieces_per_cta` pieces (a power of two <= 8), 256 / pieces_per_cta threads each.
 __global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk,
-                                                          uint8_t* __restrict__ out, AttrStats* stats) {
-  __shared__ uint32_t s_part[8];
-  __shared__ uint32_t s_off;
+                                                          uint32_t pieces_per_cta, uint8_t* __restrict__ out, AttrStats* stats) {
   if (stats->error_flags) { if (blockIdx.x == 0 && threadIdx.x == 0) stats->payload_bytes = 0; return; }
-  const uint32_t j = blockIdx.x;
-  uint32_t acc = 0;
-  for (uint32_t i = threadIdx.x; i < j; i += blockDim.x) acc += cs.nbytes[i];
-  acc = __reduce_add_sync(0xFFFFFFFFu, acc);
-  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; ++w) t += s_part[w]; s_off = t; }
-  __syncthreads();
-  const uint32_t off = s_off, nb = cs.nbytes[j];
+  const uint32_t tpp = 256u / pieces_per_cta;  // threads per piece
+  const uint32_t j = blockIdx.x * pieces_per_cta + threadIdx.x / tpp, t = threadIdx.x % tpp;
+  if (j >= num_chunks) return;
+  const uint32_t off = num_chunks > 1 ? cs.offset[j] : 0u, nb = cs.nbytes[j];
   const uint8_t* src = scratch + (unsigned long long)j * rans_chunk_capacity(kRansChunk);
-  for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) out[off + i] = src[i];
-  if (j + 1 == num_chunks && threadIdx.x == 0) {
+  for (uint32_t i = t; i < nb; i += tpp) out[off + i] = src[i];
+  if (j + 1 == num_chunks && t == 0) {
     uint32_t pos = off + nb, err = 0;
     const uint32_t l_base = 4u << stats->precision;
     const uint32_t t = cs.exit[j] - l_base;  // flush (:48-68)
@@ -1558,18 +1588,24 @@ __global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restr
 
 uint32_t rans_num_chunks(uint64_t num_symbols) { const uint32_t c = rans_plan().chunk; return (uint32_t)((num_symbols + c - 1) / c); }
 // pieces of the encode pass: sub-chunks with the lane-parallel kernel, whole chunks with the warp-pair kernel
-static uint32_t rans_piece_steps() { const RansPlan p = rans_plan(); return p.lanes ? p.chunk / kRansSub : p.chunk; }
+static uint32_t rans_piece_steps() { const RansPlan p = rans_plan(); return p.lanes ? p.chunk / p.sub : p.chunk; }
 static uint32_t rans_num_pieces(uint64_t num_symbols) { const uint32_t c = rans_piece_steps(); return (uint32_t)((num_symbols + c - 1) / c); }
 size_t rans_scratch_bytes(uint64_t num_symbols) {
   // either layout of launch_rans_encode must fit: pieces = sub-chunks (lane-parallel encode) or whole chunks (warp pairs)
   const size_t J = rans_num_chunks(num_symbols), Q = std::max<size_t>(rans_num_pieces(num_symbols), J);
   const size_t area = std::max(Q * rans_chunk_capacity(rans_piece_steps()), J * rans_chunk_capacity(rans_plan().chunk));
-  return area + 512 + (3 * Q + J + 64 * J + 32 * (kRansSub - 1) * J) * sizeof(uint32_t) + 64;
+  return area + 512 + (4 * Q + J + 64 * J + 32 * (kRansSubMax - 1) * J) * sizeof(uint32_t) + 64;
 }
 
 void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, uint32_t table_capacity, void* scratch,
                         uint8_t* payload, AttrStats* stats, cudaStream_t s) {
   const RansPlan plan = rans_plan();
+  static const uint32_t num_sms = [] {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return (uint32_t)(v > 0 ? v : 148);
+  }();
   const uint32_t J = rans_num_chunks(num_symbols);
   const bool lanes = plan.lanes && J > 1;  // a single chunk has no exploration, hence no checkpoints: one warp pair codes it
   const uint32_t Q = lanes ? rans_num_pieces(num_symbols) : J, piece = lanes ? rans_piece_steps() : plan.chunk;
@@ -1578,11 +1614,12 @@ void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uin
   uint32_t* u = (uint32_t*)(bytes + off);
   RansChunkState cs;
   cs.start = u; cs.exit = u + Q; cs.nbytes = u + 2 * (size_t)Q;
-  cs.chain_start = u + 3 * (size_t)Q;
+  cs.offset = u + 3 * (size_t)Q;
+  cs.chain_start = u + 4 * (size_t)Q;
   cs.cand_start = cs.chain_start + J; cs.cand_exit = cs.cand_start + 32 * (size_t)J; cs.cand_mid = cs.cand_exit + 32 * (size_t)J;
   if (J > 1) {
-    rans_explore_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, plan.warmup, stats);
-    rans_chain_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, stats);
+    rans_explore_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, plan.warmup, plan.sub, num_sms, stats);
+    rans_chain_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, plan.sub, stats);
     if (plan.fault) rans_fault_kernel<<<(J + 255) / 256, 256, 0, s>>>(cs, J, stats);
   }
   if (lanes) {
@@ -1596,12 +1633,13 @@ void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uin
     }();
     (void)attr_done;
     rans_encode_lanes_kernel<<<(Q + kLaneThreads - 1) / kLaneThreads, kLaneThreads, sm, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, Q, piece,
-                                                                                               smem_rows, stats);
+                                                                                               plan.sub, smem_rows, stats);
   } else {
-    rans_encode_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, stats);
+    rans_encode_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, num_sms, stats);
   }
-  if (Q > 1) rans_fixup_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, Q, piece, stats);
-  rans_gather_kernel<<<Q, 256, 0, s>>>(bytes, cs, Q, piece, payload, stats);
+  if (Q > 1) rans_fixup_kernel<<<1, kFixupThreads, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, Q, piece, stats);
+  const uint32_t ppc = piece <= 256 ? 8u : piece <= 512 ? 4u : piece <= 1024 ? 2u : 1u;
+  rans_gather_kernel<<<(Q + ppc - 1) / ppc, 256, 0, s>>>(bytes, cs, Q, piece, ppc, payload, stats);
 }
 int rans_launch_count(uint64_t num_symbols) { return rans_num_chunks(num_symbols) > 1 ? 5 : 2; }
 
