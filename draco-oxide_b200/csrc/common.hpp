@@ -18,9 +18,27 @@ constexpr uint32_t kNone = 0xFFFFFFFFu;
 // std::vector whose resize() leaves new elements uninitialised: the big connectivity arrays are
 // filled right after being sized (by a copy from the device or by a pass that writes every entry),
 // so the zero-fill of a plain vector would only add a memory pass.
+// Large blocks (>= kHostBlockMin bytes) come from a process-wide pool of 2 MB-aligned, huge-page-advised blocks that are
+// kept for reuse (connectivity.cpp): the per-mesh tables are tens of megabytes, and taking them from the C library means a
+// fresh mmap, a page fault per 4 KB and a munmap with its TLB shoot-down on every call — which serialises concurrent
+// encoder threads — while the order-dependent walks over them miss the TLB at every step unless the pages are large.
+constexpr size_t kHostBlockMin = 256u << 10;
+void* host_block_take(size_t bytes);
+void host_block_give(void* p) noexcept;
+
 template <class T>
 struct NoInitAllocator : std::allocator<T> {
   template <class U> struct rebind { using other = NoInitAllocator<U>; };
+  NoInitAllocator() = default;
+  template <class U> NoInitAllocator(const NoInitAllocator<U>&) {}
+  T* allocate(size_t n) {
+    if (n * sizeof(T) >= kHostBlockMin) return static_cast<T*>(host_block_take(n * sizeof(T)));
+    return static_cast<T*>(::operator new(n * sizeof(T)));
+  }
+  void deallocate(T* p, size_t n) noexcept {
+    if (n * sizeof(T) >= kHostBlockMin) host_block_give(p);
+    else ::operator delete(p);
+  }
   template <class U, class... Args> void construct(U* p, Args&&... args) {
     if constexpr (sizeof...(Args) == 0) ::new ((void*)p) U;
     else ::new ((void*)p) U(std::forward<Args>(args)...);

@@ -10,7 +10,67 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <mutex>
+#include <unordered_map>
+#include <sys/mman.h>
+
 namespace dxo {
+
+// ---------------------------------------------------------------------------------------
+// Pool behind NoInitAllocator (common.hpp). Best fit among the cached blocks; a block is reused for requests down to
+// half its size. Blocks of 2 MB and more are 2 MB-aligned and advised as transparent huge pages (DXO_NO_HUGEPAGES=1
+// turns the advice off). At most kHostPoolCacheBytes stay cached, the rest goes back to the C library.
+namespace {
+constexpr size_t kHugePage = 2u << 20;
+constexpr size_t kHostPoolCacheBytes = 6ull << 30;
+struct HostBlockPool {
+  std::mutex mu;
+  std::vector<std::pair<void*, size_t>> free_blocks;
+  std::unordered_map<void*, size_t> live;
+  size_t cached = 0;
+  void* take(size_t bytes) {
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      size_t best = free_blocks.size();
+      for (size_t k = 0; k < free_blocks.size(); ++k)
+        if (free_blocks[k].second >= bytes && free_blocks[k].second <= 2 * bytes + kHugePage &&
+            (best == free_blocks.size() || free_blocks[k].second < free_blocks[best].second)) best = k;
+      if (best != free_blocks.size()) {
+        const auto b = free_blocks[best];
+        free_blocks[best] = free_blocks.back();
+        free_blocks.pop_back();
+        cached -= b.second;
+        live.emplace(b.first, b.second);
+        return b.first;
+      }
+    }
+    const bool huge = bytes >= kHugePage;
+    const size_t align = huge ? kHugePage : 4096;
+    const size_t cap = (bytes + align - 1) / align * align;
+    void* p = aligned_alloc(align, cap);
+    if (!p) throw std::bad_alloc();
+    static const bool advise = getenv("DXO_NO_HUGEPAGES") == nullptr;
+    if (huge && advise) madvise(p, cap, MADV_HUGEPAGE);  // best effort
+    std::lock_guard<std::mutex> lock(mu);
+    live.emplace(p, cap);
+    return p;
+  }
+  void give(void* p) noexcept {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = live.find(p);
+    if (it == live.end()) return;  // not ours (cannot happen)
+    const size_t cap = it->second;
+    live.erase(it);
+    if (cached + cap > kHostPoolCacheBytes) { free(p); return; }
+    cached += cap;
+    free_blocks.push_back({p, cap});
+  }
+};
+HostBlockPool& host_pool() { static HostBlockPool* pool = new HostBlockPool; return *pool; }  // never destroyed
+}  // namespace
+void* host_block_take(size_t bytes) { return host_pool().take(bytes); }
+void host_block_give(void* p) noexcept { host_pool().give(p); }
+
 
 // ---------------------------------------------------------------------------------------
 // CornerTable::new — core/corner_table/mod.rs:84-118
@@ -374,11 +434,13 @@ class EdgebreakerRun {
   const UniversalTable& ut_;
   // vstate_: bit 0 = vertex visited, bit 1 = vertex lies on a hole (hole_of_vertex_ != kNone);
   // face_done_: bit 0 = face visited, bit 1 = the face got an S symbol (split_symbol_of_face_ is set)
-  std::vector<uint8_t> vstate_, face_done_, hole_done_, start_face_interior_;
-  std::vector<uint32_t> hole_of_vertex_, stack_, init_face_corners_, init_reversed_;
+  U8Array vstate_, face_done_;  // pooled blocks (common.hpp)
+  std::vector<uint8_t> hole_done_, start_face_interior_;
+  U32Array hole_of_vertex_;
+  std::vector<uint32_t> stack_, init_face_corners_, init_reversed_;
   U8Array symbols_;        // sized once, every used entry written by the traversal (no zero-fill)
   U32Array visit_order_;
-  std::vector<uint32_t> split_symbol_of_face_;  // symbol index of the S symbol a face got (< num_faces), kNone otherwise
+  U32Array split_symbol_of_face_;  // symbol index of the S symbol a face got (< num_faces), kNone otherwise
   std::vector<SplitEvent> split_events_;
   uint64_t symbol_index_ = ~(uint64_t)0;  // usize::MAX, incremented with wrap before use (:150,:276)
   size_t num_visited_ = 0;                // entries of symbols_ / visit_order_ in use
@@ -650,20 +712,23 @@ std::vector<uint32_t> encode_edgebreaker(const UniversalTable& ut, const std::ve
 // (:98-131). Such entries can only be popped later, when the face is already marked
 // visited, and are dropped at :56-58 before they have any effect — so they are simply
 // left on the stack here (lazy deletion, identical output).
-std::vector<uint8_t> vertex_interior_flags(const TableRef& t) {
-  std::vector<uint8_t> f(t.num_vertices);
+U8Array vertex_interior_flags(const TableRef& t) {
+  U8Array f(t.num_vertices);
   for (uint32_t v = 0; v < t.num_vertices; ++v) f[v] = t.opp(corner_next(t.left_most[v])) != kNone ? 1 : 0;
   return f;
 }
 
-std::vector<uint32_t> attribute_sequence(const TableRef& t, const EdgebreakerEncoder::CornerList& corners_of_edgebreaker) {
-  std::vector<uint8_t> vertex_seen_v(t.num_vertices, 0), face_seen_v(t.num_faces, 0);
+U32Array attribute_sequence(const TableRef& t, const EdgebreakerEncoder::CornerList& corners_of_edgebreaker) {
+  U8Array vertex_seen_v(t.num_vertices), face_seen_v(t.num_faces);
+  memset(vertex_seen_v.data(), 0, vertex_seen_v.size());
+  memset(face_seen_v.data(), 0, face_seen_v.size());
   // The reference's stack starts as a copy of the corner list and is popped from the back. Here the list
   // itself is the (read-only) bottom of the stack, consumed from its end, and only pushed entries are stored.
   // As in the traversal, the hot loop works on local pointers and counters (see EdgebreakerRun::traverse).
   const EdgebreakerEncoder::CornerList bottom_list = corners_of_edgebreaker;
   size_t bottom = bottom_list.size();
-  std::vector<uint32_t> stack_v(1024), out_v(t.num_vertices);
+  std::vector<uint32_t> stack_v(1024);
+  U32Array out_v(t.num_vertices);
   uint32_t* stack = stack_v.data();
   size_t top = 0, stack_cap = stack_v.size();
   uint32_t* const out = out_v.data();

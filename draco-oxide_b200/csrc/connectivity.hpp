@@ -85,7 +85,7 @@ struct TableRef {
 };
 // !is_on_boundary(v) for every vertex of a table (corner_table/mod.rs:36-38); lets the sequencer replace two dependent
 // random reads per vertex by one byte. Independent of the traversal, so it is computed on a helper thread.
-std::vector<uint8_t> vertex_interior_flags(const TableRef& t);
+U8Array vertex_interior_flags(const TableRef& t);
 inline TableRef table_ref(const UniversalTable& u) {
   return {u.num_faces, u.num_corners, u.num_vertices, u.corner_vertex.data(), u.opposite.data(), nullptr, u.left_most.data()};
 }
@@ -126,6 +126,6 @@ std::vector<uint32_t> encode_edgebreaker(const UniversalTable& ut, const std::ve
 
 // Traverser::compute_seqeunce — shared/attribute/sequence.rs:48-151.
 // One corner per attribute vertex, in the order the decoder will reconstruct them.
-std::vector<uint32_t> attribute_sequence(const TableRef& t, const EdgebreakerEncoder::CornerList& corners_of_edgebreaker);
+U32Array attribute_sequence(const TableRef& t, const EdgebreakerEncoder::CornerList& corners_of_edgebreaker);
 
 }  // namespace dxo

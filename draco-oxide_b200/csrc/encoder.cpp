@@ -4,6 +4,7 @@
 // loops of the latter run as CUDA kernels (kernels.cu). No CPU implementation of those
 // loops exists in this library: without a device the job fails.
 #include "encoder.hpp"
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <chrono>
@@ -84,7 +85,24 @@ struct PinnedPool {
         return b.first;
       }
     }
+    // New block: 2 MB-aligned memory advised as transparent huge pages, touched, then pinned with cudaHostRegister — the
+    // host walks over the tables in these blocks (CLERS traversal, sequencer) are random accesses over ~100 MB and miss the
+    // TLB at every step with 4 KB pages. cudaHostAlloc is the fallback (and the choice with DXO_NO_HUGEPAGES=1).
     void* p = nullptr;
+    static const bool huge = getenv("DXO_NO_HUGEPAGES") == nullptr;
+    if (huge) {
+      constexpr size_t kHuge = 2u << 20;
+      const size_t want = (bytes + bytes / 8 + kHuge - 1) / kHuge * kHuge;
+      p = aligned_alloc(kHuge, want);
+      if (p) {
+        madvise(p, want, MADV_HUGEPAGE);
+        for (size_t o = 0; o < want; o += 4096) static_cast<volatile uint8_t*>(p)[o] = 0;
+        if (cudaHostRegister(p, want, cudaHostRegisterPortable) == cudaSuccess) { *cap = want; return p; }
+        cudaGetLastError();
+        free(p);
+        p = nullptr;
+      }
+    }
     const size_t want = bytes + bytes / 8 + 4096;
     if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     *cap = want;

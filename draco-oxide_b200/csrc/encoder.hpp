@@ -91,7 +91,7 @@ struct AttrPlan {
   int parent = -1;            // index of the position attribute this one predicts from
   uint32_t hist_capacity = 0; // upper bound of the alphabet
   const TableRef* table = nullptr;
-  std::vector<uint32_t> sequence;  // empty when shared (see MeshJob::sequence_of)
+  U32Array sequence;  // empty when shared (see MeshJob::sequence_of)
   int shares_sequence_of = -1;     // index of the attribute whose sequence (host and device copy) this one uses
 };
 
@@ -147,7 +147,7 @@ class MeshJob {
   std::map<std::string, std::vector<uint8_t>> trace_items;
   uint64_t h2d_bytes = 0, d2h_bytes = 0;
   uint64_t num_position_vertices() const { return plans_.empty() ? 0 : plans_[0].sequence.size(); }
-  const std::vector<uint32_t>& sequence_of(size_t att) const {
+  const U32Array& sequence_of(size_t att) const {
     return plans_[att].shares_sequence_of >= 0 ? plans_[plans_[att].shares_sequence_of].sequence : plans_[att].sequence;
   }
 
@@ -158,7 +158,7 @@ class MeshJob {
   UniversalTable ut_;
   std::vector<SeamTable> seams_;
   std::vector<TableRef> table_refs_;
-  std::vector<std::vector<uint8_t>> interior_;  // per table: vertex_interior_flags (helper threads, during the traversal)
+  std::vector<U8Array> interior_;  // per table: vertex_interior_flags (helper threads, during the traversal)
   ByteSink head_;  // header + connectivity + attribute section headers
   std::unique_ptr<EdgebreakerEncoder> eb_;  // kept: owns the corner list the sequencers (and traces) read
   std::vector<U32Array> masked_opposite_;   // per attribute table: opposite with seam edges removed (host sequencer)

@@ -998,16 +998,18 @@ void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t t
 //   explore   the stream is cut into chunks of C steps. For every chunk a warp runs 32
 //             trajectories (one per lane, states spread geometrically over the whole state
 //             interval) through the same symbols, starting W steps before the chunk; each lane
-//             records its state at the chunk start and at the chunk end. No bytes.
+//             records its state at the chunk start, at up to 15 evenly spaced checkpoints
+//             inside the chunk and at the chunk end. No bytes.
 //   chain     one warp walks the chunks carrying the TRUE state (chunk 0: l_base): the lane
 //             whose recorded entering state equals it hands over its exit state; a chunk with
 //             no such lane (rare) is run from the true state on the spot.
-//   encode    every chunk is encoded once from its true entering state.
-//   fix-up    checks in parallel that every chunk was encoded from its predecessor's exit
+//   encode    every piece (a sixteenth of a chunk; its true entering state is the chain's state
+//             or a checkpoint of the matched lane) is encoded once, one thread per piece.
+//   fix-up    checks in parallel that every piece was encoded from its predecessor's exit
 //             state and repairs sequentially otherwise, so the result never depends on the
-//             speculation succeeding.
-//   gather    chunk byte strings are concatenated (prefix sum of their lengths) and the
-//             2-bit-tagged final state is appended.
+//             speculation succeeding; leaves the prefix sum of the pieces' byte counts.
+//   gather    the pieces' byte strings are concatenated and the 2-bit-tagged final state is
+//             appended.
 // The bytes are those of the sequential coder by construction: chunk 0 starts from
 // l_base and every other chunk is encoded from its predecessor's true exit state.
 //
@@ -1016,9 +1018,9 @@ void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t t
 //     table rows, derives the three renormalisation thresholds and fills a ring of
 //     32-row stages; it also turns the consumer's per-step record (x before the step,
 //     byte count) into output bytes with a warp scan, 32 steps at a time.
-//     (Warps map to SM sub-partitions by warp index; a CTA carries two producer/consumer
-//     pairs and swaps the roles on odd CTAs so the consumers of an SM spread over all four
-//     schedulers.)
+//     (A CTA carries two producer/consumer pairs; which warp of a pair takes which role is
+//     drawn when the pair starts so that the consumers of an SM spread over all four
+//     schedulers, see rans_role.)
 //   * CONSUMER warp: the serial chain only. Per symbol: two broadcast LDS.128,
 //     q = ((umulhi(x, M) + c) >> lp) >> 8k with M = ceil(2^(32+lp)/f), lp = ceil(log2 f) - 1
 //     (exact for x < 2^30, DESIGN.md "rANS division"; the multiply does not wait for k),
@@ -1032,13 +1034,13 @@ constexpr int kRansLookahead = 3;      // groups of symbols in flight in the pro
 // DXO_RANS_CHUNK and DXO_RANS_WARMUP override them for experiments. Correctness never depends on these values;
 // DXO_RANS_FAULT=1 makes the chain kernel deliberately record a wrong entering state for every fifth chunk
 // (tests of the fix-up path).
-struct RansPlan { uint32_t chunk, warmup; int fault; int lanes; uint32_t sub; };
+struct RansPlan { uint32_t chunk, warmup; int fault; int lanes; uint32_t sub; bool fixed_chunk; };
 static RansPlan rans_plan() {
   static RansPlan plan = [] {
-    RansPlan p{4096, 1024, 0, 1, (uint32_t)kRansSubMax};
+    RansPlan p{4096, 1024, 0, 1, (uint32_t)kRansSubMax, false};
     if (const char* e = getenv("DXO_RANS_LANES")) p.lanes = atoi(e);  // phase C: 1 = one thread per chunk (default), 0 = one warp pair per chunk
     if (const char* e = getenv("DXO_RANS_FAULT")) p.fault = atoi(e);  // tests: the chain hands out wrong states, the fix-up must repair
-    if (const char* e = getenv("DXO_RANS_CHUNK")) p.chunk = (uint32_t)atoi(e);
+    if (const char* e = getenv("DXO_RANS_CHUNK")) { p.chunk = (uint32_t)atoi(e); p.fixed_chunk = true; }
     if (const char* e = getenv("DXO_RANS_WARMUP")) p.warmup = (uint32_t)atoi(e);
     if (const char* e = getenv("DXO_RANS_SUB")) p.sub = (uint32_t)atoi(e);
     p.chunk = (p.chunk < 32u ? 32u : p.chunk) / 32u * 32u;
@@ -1188,16 +1190,26 @@ __device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t
   named_bar_sync(bar_base + 2 * kRansStages);  // both warps of the pair: results in sh are visible
 }
 
-// role / pair of the calling warp inside a 128-thread CTA (two pairs); odd CTAs swap roles
-// (CTAs are handed to the SMs wave by wave, CTA b, b + num_sms, b + 2 num_sms ... landing on one SM: the swap follows
-// b + b / num_sms so that the consumers of successive waves alternate between the schedulers {0, 2} and {1, 3}.)
+// role / pair of the calling warp inside a 128-thread CTA (two pairs)
+// Which warp of a pair runs the serial chain is decided when the pair starts: the consumer's ~16 instructions per step
+// keep the integer pipe of its scheduler busy for most of a step, so two consumers on one scheduler halve each other's
+// speed. Pairs draw a ticket per (SM, scheduler pair) and alternate, which spreads the consumers of all resident CTAs
+// (of every stream that is running K10) evenly over the four schedulers wherever the CTAs happen to land.
+__device__ uint32_t g_rans_ticket[2048];
 struct RansRole { int pair; int bar_base; bool is_consumer; };
-__device__ __forceinline__ RansRole rans_role(uint32_t num_sms) {
+__device__ __forceinline__ RansRole rans_role(int* role_slot /* shared, one per pair */) {
   const int warp = threadIdx.x >> 5;
   RansRole r;
   r.pair = warp >> 1;
   r.bar_base = 1 + r.pair * (2 * kRansStages + 1);
-  r.is_consumer = (warp & 1) == (int)((blockIdx.x + blockIdx.x / num_sms) & 1);
+  if ((warp & 1) == 0 && (threadIdx.x & 31) == 0) {
+    uint32_t smid, wid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+    role_slot[r.pair] = (int)(atomicAdd(&g_rans_ticket[(smid & 1023u) * 2u + ((wid >> 1) & 1u)], 1u) & 1u);
+  }
+  named_bar_sync(r.bar_base + 2 * kRansStages);
+  r.is_consumer = (warp & 1) == role_slot[r.pair];
   return r;
 }
 
@@ -1223,12 +1235,13 @@ __device__ __forceinline__ uint32_t rans_guess_state(uint32_t lane, uint32_t l_b
 // phase A — exploration (two chunks per CTA): no bytes, 32 candidate (entering state -> exit state) pairs per chunk
 __global__ void __launch_bounds__(128) rans_explore_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
                                                            RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, uint32_t kRansWarmup, uint32_t sub,
-                                                           uint32_t num_sms, AttrStats* stats) {
+                                                           AttrStats* stats) {
   __shared__ RansShared sh2[2];
+  __shared__ int role_slot[2];
   if (stats->error_flags) return;
-  const RansRole role = rans_role(num_sms);
+  if (2ull * blockIdx.x + (threadIdx.x >> 6) >= num_chunks) return;  // both warps of the pair leave together
+  const RansRole role = rans_role(role_slot);
   const unsigned long long j = 2ull * blockIdx.x + role.pair;
-  if (j >= num_chunks) return;  // both warps of the pair leave together
   RansShared& sh = sh2[role.pair];
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
   const uint32_t lane = threadIdx.x & 31;
@@ -1329,13 +1342,13 @@ __global__ void rans_fault_kernel(RansChunkState cs, uint32_t num_chunks, AttrSt
 
 // phase C — every chunk is encoded once from its true entering state (two chunks per CTA)
 __global__ void __launch_bounds__(128) rans_encode_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                          uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, uint32_t num_sms,
-                                                          AttrStats* stats) {
+                                                          uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, AttrStats* stats) {
   __shared__ RansShared sh2[2];
+  __shared__ int role_slot[2];
   if (stats->error_flags) return;
-  const RansRole role = rans_role(num_sms);
+  if (2ull * blockIdx.x + (threadIdx.x >> 6) >= num_chunks) return;
+  const RansRole role = rans_role(role_slot);
   const unsigned long long j = 2ull * blockIdx.x + role.pair;
-  if (j >= num_chunks) return;
   RansShared& sh = sh2[role.pair];
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
   const uint32_t in = j == 0 ? (4u << P) : cs.chain_start[j];
@@ -1498,7 +1511,7 @@ __global__ void __launch_bounds__(kLaneThreads) rans_encode_lanes_kernel(const u
 // state of its predecessor; that is checked in parallel by the whole CTA, and only a violated link (which the chain makes
 // impossible unless something upstream went wrong) starts the sequential repair by the CTA's first warp pair, so exactness
 // never rests on the speculation. Then the exclusive prefix sum of the pieces' byte counts is left in cs.offset.
-constexpr int kFixupThreads = 1024;
+constexpr int kFixupThreads = 1024, kFixupItems = 8;
 constexpr int kFixupPairBarrier = 2 * kRansStages + 2;  // named barrier of the repairing pair (rans_encode_range with bar_base 1 uses 1..7)
 __global__ void __launch_bounds__(kFixupThreads) rans_fixup_kernel(const uint32_t* __restrict__ symbols, unsigned long long n,
                                                                    const uint4* __restrict__ table, uint8_t* __restrict__ scratch, RansChunkState cs,
@@ -1510,9 +1523,17 @@ __global__ void __launch_bounds__(kFixupThreads) rans_fixup_kernel(const uint32_
   const uint32_t l_base = 4u << P;
   if (threadIdx.x == 0) s_bad = 0;
   __syncthreads();
-  {
+  for (uint32_t base = 0; base < num_chunks; base += kFixupThreads * kFixupItems) {  // all loads of a tile are in flight together
+    uint32_t e[kFixupItems], st[kFixupItems];
+#pragma unroll
+    for (int i = 0; i < kFixupItems; ++i) {
+      const uint32_t j = base + i * kFixupThreads + threadIdx.x;
+      e[i] = j < num_chunks && j > 0 ? __ldcg(cs.exit + j - 1) : l_base;
+      st[i] = j < num_chunks ? __ldcg(cs.start + j) : l_base;
+    }
     uint32_t bad = 0;
-    for (uint32_t j = threadIdx.x; j < num_chunks; j += kFixupThreads) bad |= (j == 0 ? l_base : __ldcg(cs.exit + j - 1)) != __ldcg(cs.start + j);
+#pragma unroll
+    for (int i = 0; i < kFixupItems; ++i) bad |= e[i] != st[i];
     if (bad) s_bad = 1;
   }
   __syncthreads();
@@ -1538,26 +1559,35 @@ __global__ void __launch_bounds__(kFixupThreads) rans_fixup_kernel(const uint32_
     }
   }
   __syncthreads();
-  // exclusive scan of nbytes, a tile of kFixupThreads pieces at a time
+  // exclusive scan of nbytes: kFixupItems rows of kFixupThreads pieces are loaded together, then scanned row by row
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t carry = 0;
-  for (uint32_t base = 0; base < num_chunks; base += kFixupThreads) {
-    const uint32_t j = base + threadIdx.x;
-    const uint32_t v = j < num_chunks ? cs.nbytes[j] : 0u;
-    uint32_t inc = v;
+  for (uint32_t base = 0; base < num_chunks; base += kFixupThreads * kFixupItems) {
+    uint32_t v[kFixupItems];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= (uint32_t)d) inc += o; }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    uint32_t w = s_warp[lane];  // kFixupThreads / 32 == 32 partial sums
-    uint32_t winc = w;
+    for (int i = 0; i < kFixupItems; ++i) {
+      const uint32_t j = base + i * kFixupThreads + threadIdx.x;
+      v[i] = j < num_chunks ? cs.nbytes[j] : 0u;
+    }
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, winc, d); if (lane >= (uint32_t)d) winc += o; }
-    const uint32_t before = __shfl_sync(0xFFFFFFFFu, winc - w, warp);
-    const uint32_t total = __shfl_sync(0xFFFFFFFFu, winc, 31);
-    if (j < num_chunks) cs.offset[j] = carry + before + (inc - v);
-    carry += total;
-    __syncthreads();
+    for (int i = 0; i < kFixupItems; ++i) {
+      if (base + i * kFixupThreads >= num_chunks) break;  // uniform
+      const uint32_t j = base + i * kFixupThreads + threadIdx.x;
+      uint32_t inc = v[i];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= (uint32_t)d) inc += o; }
+      if (lane == 31) s_warp[warp] = inc;
+      __syncthreads();
+      const uint32_t w = s_warp[lane];  // kFixupThreads / 32 == 32 partial sums
+      uint32_t winc = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, winc, d); if (lane >= (uint32_t)d) winc += o; }
+      const uint32_t before = __shfl_sync(0xFFFFFFFFu, winc - w, warp);
+      const uint32_t total = __shfl_sync(0xFFFFFFFFu, winc, 31);
+      if (j < num_chunks) cs.offset[j] = carry + before + (inc - v[i]);
+      carry += total;
+      __syncthreads();
+    }
   }
 }
 
@@ -1586,29 +1616,47 @@ __global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restr
   }
 }
 
-uint32_t rans_num_chunks(uint64_t num_symbols) { const uint32_t c = rans_plan().chunk; return (uint32_t)((num_symbols + c - 1) / c); }
-// pieces of the encode pass: sub-chunks with the lane-parallel kernel, whole chunks with the warp-pair kernel
-static uint32_t rans_piece_steps() { const RansPlan p = rans_plan(); return p.lanes ? p.chunk / p.sub : p.chunk; }
-static uint32_t rans_num_pieces(uint64_t num_symbols) { const uint32_t c = rans_piece_steps(); return (uint32_t)((num_symbols + c - 1) / c); }
-size_t rans_scratch_bytes(uint64_t num_symbols) {
-  // either layout of launch_rans_encode must fit: pieces = sub-chunks (lane-parallel encode) or whole chunks (warp pairs)
-  const size_t J = rans_num_chunks(num_symbols), Q = std::max<size_t>(rans_num_pieces(num_symbols), J);
-  const size_t area = std::max(Q * rans_chunk_capacity(rans_piece_steps()), J * rans_chunk_capacity(rans_plan().chunk));
-  return area + 512 + (4 * Q + J + 64 * J + 32 * (kRansSubMax - 1) * J) * sizeof(uint32_t) + 64;
-}
-
-void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, uint32_t table_capacity, void* scratch,
-                        uint8_t* payload, AttrStats* stats, cudaStream_t s) {
-  const RansPlan plan = rans_plan();
+// Chunk size for a stream of n symbols. The exploration is fastest with at most one consumer warp per scheduler, i.e. up to
+// 4 pairs per SM, so longer streams get longer chunks (up to 16384 steps; beyond that the SMs are full either way and
+// the chain kernel would gain nothing). DXO_RANS_CHUNK pins the size.
+constexpr uint32_t kRansChunkMin = 4096, kRansChunkMax = 16384;
+static uint32_t rans_sm_count() {
   static const uint32_t num_sms = [] {
     int dev = 0, v = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
     return (uint32_t)(v > 0 ? v : 148);
   }();
-  const uint32_t J = rans_num_chunks(num_symbols);
+  return num_sms;
+}
+static RansPlan rans_plan_for(uint64_t n) {
+  RansPlan p = rans_plan();
+  if (!p.fixed_chunk) {
+    const uint64_t unit = 32ull * p.sub, pairs = 4ull * rans_sm_count();
+    const uint64_t c = ((n + pairs - 1) / pairs + unit - 1) / unit * unit;
+    p.chunk = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(c, kRansChunkMin), kRansChunkMax);
+  }
+  return p;
+}
+uint32_t rans_num_chunks(uint64_t num_symbols) { const uint32_t c = rans_plan_for(num_symbols).chunk; return (uint32_t)((num_symbols + c - 1) / c); }
+size_t rans_scratch_bytes(uint64_t num_symbols) {
+  // Valid for every stream of at most num_symbols symbols and for both layouts of launch_rans_encode (pieces = sub-chunks
+  // for the lane-parallel encode, whole chunks for the warp pairs): Q pieces of c steps hold Q (3 c + 8) <= 3 (n + c) + 8 Q bytes.
+  const RansPlan p = rans_plan();
+  const uint64_t c_min = p.fixed_chunk ? p.chunk : kRansChunkMin, c_max = p.fixed_chunk ? p.chunk : kRansChunkMax;
+  const uint64_t piece_min = p.lanes ? c_min / p.sub : c_min;
+  const size_t J = (size_t)(num_symbols / c_min + 1), Q = (size_t)(num_symbols / piece_min + 1);
+  const size_t area = 3 * ((size_t)num_symbols + c_max) + 8 * Q;
+  return area + 512 + (4 * Q + J + 64 * J + 32 * (kRansSubMax - 1) * J) * sizeof(uint32_t) + 64;
+}
+
+void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, uint32_t table_capacity, void* scratch,
+                        uint8_t* payload, AttrStats* stats, cudaStream_t s) {
+  const RansPlan plan = rans_plan_for(num_symbols);
+  const uint32_t J = (uint32_t)((num_symbols + plan.chunk - 1) / plan.chunk);
   const bool lanes = plan.lanes && J > 1;  // a single chunk has no exploration, hence no checkpoints: one warp pair codes it
-  const uint32_t Q = lanes ? rans_num_pieces(num_symbols) : J, piece = lanes ? rans_piece_steps() : plan.chunk;
+  const uint32_t piece = lanes ? plan.chunk / plan.sub : plan.chunk;
+  const uint32_t Q = (uint32_t)((num_symbols + piece - 1) / piece);
   uint8_t* bytes = (uint8_t*)scratch;
   size_t off = ((size_t)Q * rans_chunk_capacity(piece) + 255) / 256 * 256;
   uint32_t* u = (uint32_t*)(bytes + off);
@@ -1618,7 +1666,7 @@ void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uin
   cs.chain_start = u + 4 * (size_t)Q;
   cs.cand_start = cs.chain_start + J; cs.cand_exit = cs.cand_start + 32 * (size_t)J; cs.cand_mid = cs.cand_exit + 32 * (size_t)J;
   if (J > 1) {
-    rans_explore_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, plan.warmup, plan.sub, num_sms, stats);
+    rans_explore_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, plan.warmup, plan.sub, stats);
     rans_chain_kernel<<<1, 64, 0, s>>>(symbols, num_symbols, rans_table, cs, J, plan.chunk, plan.sub, stats);
     if (plan.fault) rans_fault_kernel<<<(J + 255) / 256, 256, 0, s>>>(cs, J, stats);
   }
@@ -1635,7 +1683,7 @@ void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uin
     rans_encode_lanes_kernel<<<(Q + kLaneThreads - 1) / kLaneThreads, kLaneThreads, sm, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, Q, piece,
                                                                                                plan.sub, smem_rows, stats);
   } else {
-    rans_encode_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, num_sms, stats);
+    rans_encode_kernel<<<(J + 1) / 2, 128, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, plan.chunk, stats);
   }
   if (Q > 1) rans_fixup_kernel<<<1, kFixupThreads, 0, s>>>(symbols, num_symbols, rans_table, bytes, cs, Q, piece, stats);
   const uint32_t ppc = piece <= 256 ? 8u : piece <= 512 ? 4u : piece <= 1024 ? 2u : 1u;
