@@ -1191,26 +1191,43 @@ __device__ __forceinline__ void rans_encode_range(RansShared& sh, const uint32_t
 }
 
 // role / pair of the calling warp inside a 128-thread CTA (two pairs)
-// Which warp of a pair runs the serial chain is decided when the pair starts: the consumer's ~16 instructions per step
-// keep the integer pipe of its scheduler busy for most of a step, so two consumers on one scheduler halve each other's
-// speed. Pairs draw a ticket per (SM, scheduler pair) and alternate, which spreads the consumers of all resident CTAs
-// (of every stream that is running K10) evenly over the four schedulers wherever the CTAs happen to land.
-__device__ uint32_t g_rans_ticket[2048];
-struct RansRole { int pair; int bar_base; bool is_consumer; };
-__device__ __forceinline__ RansRole rans_role(int* role_slot /* shared, one per pair */) {
+// Which warp of a pair runs the serial chain is decided when the pair starts: the consumer's ~16 instructions per step keep
+// the integer pipe of its scheduler busy for a good part of a step, so consumers sharing a scheduler slow each other down
+// (ncu: issue rate 0.54 on the busiest scheduler against 0.04 on the idlest with fixed roles). A warp's scheduler is its
+// hardware warp slot modulo 4 (tools/probe/smsp_map.cu); the pair puts its consumer on the one of its two schedulers that
+// currently runs fewer consumers of any K10 kernel on this SM (live counters, updated under a per-SM lock, released when
+// the consumer is done).
+__device__ uint32_t g_rans_consumers[1024 * 4];
+__device__ uint32_t g_rans_lock[1024];
+struct RansRole { int pair; int bar_base; bool is_consumer; uint32_t counter; };
+__device__ __forceinline__ RansRole rans_role(int* role_slot /* shared, one per pair */, uint32_t* sched_slot /* shared, one per warp */) {
   const int warp = threadIdx.x >> 5;
   RansRole r;
   r.pair = warp >> 1;
   r.bar_base = 1 + r.pair * (2 * kRansStages + 1);
+  uint32_t smid, wid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+  smid &= 1023u;
+  if ((threadIdx.x & 31) == 0) sched_slot[warp] = wid & 3u;
+  named_bar_sync(r.bar_base + 2 * kRansStages);
   if ((warp & 1) == 0 && (threadIdx.x & 31) == 0) {
-    uint32_t smid, wid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-    role_slot[r.pair] = (int)(atomicAdd(&g_rans_ticket[(smid & 1023u) * 2u + ((wid >> 1) & 1u)], 1u) & 1u);
+    uint32_t* cnt = g_rans_consumers + smid * 4u;
+    const uint32_t a = sched_slot[warp], b = sched_slot[warp + 1];
+    while (atomicCAS(&g_rans_lock[smid], 0u, 1u) != 0u) {}
+    const int pick = atomicAdd(&cnt[a], 0u) <= atomicAdd(&cnt[b], 0u) ? 0 : 1;  // 0: the even warp is the consumer
+    atomicAdd(&cnt[pick ? b : a], 1u);
+    __threadfence();
+    atomicExch(&g_rans_lock[smid], 0u);
+    role_slot[r.pair] = pick;
   }
   named_bar_sync(r.bar_base + 2 * kRansStages);
   r.is_consumer = (warp & 1) == role_slot[r.pair];
+  r.counter = smid * 4u + sched_slot[warp];
   return r;
+}
+__device__ __forceinline__ void rans_role_release(const RansRole& r) {
+  if (r.is_consumer && (threadIdx.x & 31) == 0) atomicSub(&g_rans_consumers[r.counter], 1u);
 }
 
 // chunk state arrays (device scratch): start[] = entering state each piece was last encoded from, exit[] = its exit
@@ -1238,9 +1255,10 @@ __global__ void __launch_bounds__(128) rans_explore_kernel(const uint32_t* __res
                                                            AttrStats* stats) {
   __shared__ RansShared sh2[2];
   __shared__ int role_slot[2];
+  __shared__ uint32_t sched_slot[4];
   if (stats->error_flags) return;
   if (2ull * blockIdx.x + (threadIdx.x >> 6) >= num_chunks) return;  // both warps of the pair leave together
-  const RansRole role = rans_role(role_slot);
+  const RansRole role = rans_role(role_slot, sched_slot);
   const unsigned long long j = 2ull * blockIdx.x + role.pair;
   RansShared& sh = sh2[role.pair];
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
@@ -1258,6 +1276,7 @@ __global__ void __launch_bounds__(128) rans_explore_kernel(const uint32_t* __res
     for (uint32_t k = 0; k + 1 < sub; ++k) cs.cand_mid[(j * (sub - 1) + k) * 32 + lane] = sh.x_mid[k][lane];  // unreached boundaries lie past the end
     if (lane == 0 && sh.err) atomicOr(&stats->error_flags, sh.err);
   }
+  rans_role_release(role);
 }
 
 // phase B — the chain (one warp pair): walks the chunks in order carrying the TRUE state. A chunk whose candidates contain
@@ -1345,9 +1364,10 @@ __global__ void __launch_bounds__(128) rans_encode_kernel(const uint32_t* __rest
                                                           uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, AttrStats* stats) {
   __shared__ RansShared sh2[2];
   __shared__ int role_slot[2];
+  __shared__ uint32_t sched_slot[4];
   if (stats->error_flags) return;
   if (2ull * blockIdx.x + (threadIdx.x >> 6) >= num_chunks) return;
-  const RansRole role = rans_role(role_slot);
+  const RansRole role = rans_role(role_slot, sched_slot);
   const unsigned long long j = 2ull * blockIdx.x + role.pair;
   RansShared& sh = sh2[role.pair];
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
@@ -1361,6 +1381,7 @@ __global__ void __launch_bounds__(128) rans_encode_kernel(const uint32_t* __rest
     cs.nbytes[j] = sh.nbytes;
     if (sh.err) atomicOr(&stats->error_flags, sh.err);
   }
+  rans_role_release(role);
 }
 
 // phase C, lane-parallel variant — one THREAD per chunk (32 chunks per warp) instead of one warp pair per chunk. All that the
