@@ -824,6 +824,9 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     prof.begin("K8_histogram", 4 * S, s);
     gpu::launch_histogram(d.symbols, S, d.hist, p.hist_capacity, d.stats, s);
     prof.end(s);
+    prof.begin("K9_build_table", 4ull * p.hist_capacity, s);
+    gpu::launch_build_table(d.hist, p.hist_capacity, S, d.work, d.rans_table, d.table_bytes, d.table_capacity, d.stats, s);
+    prof.end(s);
     if (side_ready_[i]) {
       // The side stream input leaves for the host as soon as it is ready; the host codes it during K9-K10. What is
       // data-parallel about it is done here: flips are counted, orientation flags compacted and their transitions counted.
@@ -843,9 +846,6 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
       cuda_check(cudaEventRecordWithFlags(side_copied_[i], ctx.copy_stream, capturing_ ? cudaEventRecordExternal : cudaEventRecordDefault), "cudaEventRecord");
       d2h_bytes += M + 8;
     }
-    prof.begin("K9_build_table", 4ull * p.hist_capacity, s);
-    gpu::launch_build_table(d.hist, p.hist_capacity, S, d.work, d.rans_table, d.table_bytes, d.table_capacity, d.stats, s);
-    prof.end(s);
     prof.begin("K10_rans_encode", 4 * S, s);
     gpu::launch_rans_encode(d.symbols, S, d.rans_table, p.hist_capacity, d.rans_scratch, d.payload, d.stats, s);
     prof.launches += gpu::rans_launch_count(S) - 1;  // explore + chain + encode + fix-up + gather
