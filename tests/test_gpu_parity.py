@@ -313,7 +313,8 @@ out = bytearray(); dxo.encode(m, out)
 assert bytes(out) == orc.encode(m), "mesh stream differs"
 rng = np.random.default_rng(5)
 for n, gen in [(200_000, lambda: np.minimum(rng.geometric(0.08, 200_000) - 1, 4000)), (50_001, lambda: rng.integers(0, 3, 50_001)),
-               (33, lambda: rng.integers(0, 900, 33)), (100_000, lambda: rng.integers(0, 70_000, 100_000))]:
+               (33, lambda: rng.integers(0, 900, 33)), (100_000, lambda: rng.integers(0, 70_000, 100_000)),
+               (2_700_001, lambda: np.minimum(rng.geometric(0.05, 2_700_001) - 1, 2000))]:  # long enough for the chunk size to adapt
     sym = gen().astype(np.uint32)
     assert dxo.encode_symbols(sym) == orc.encode_symbols(sym), n
 print("ok")
@@ -325,6 +326,11 @@ print("ok")
     {"DXO_RANS_CHUNK": "32", "DXO_RANS_WARMUP": "32"},      # smallest chunks, thousands of them
     {"DXO_RANS_CHUNK": "256", "DXO_RANS_WARMUP": "64", "DXO_RANS_FAULT": "1"},  # wrong entering states: the fix-up must repair
     {"DXO_RANS_CHUNK": "1048576", "DXO_RANS_WARMUP": "1024"},  # a single chunk: the sequential coder
+    {"DXO_RANS_CHUNK": "512", "DXO_RANS_WARMUP": "0"},      # misses with 16 pieces per chunk: the chain publishes the checkpoints itself
+    {"DXO_RANS_CHUNK": "512", "DXO_RANS_WARMUP": "64", "DXO_RANS_FAULT": "1"},  # wrong entering states with 16 pieces per chunk
+    {"DXO_RANS_SUB": "1"},                                   # one piece per chunk (no checkpoints), adaptive chunk size
+    {"DXO_RANS_CHUNK": "4096", "DXO_RANS_WARMUP": "512", "DXO_RANS_SUB": "4"},
+    {"DXO_NO_HUGEPAGES": "1"},                               # plain pinned / pageable blocks
     {"DXO_RANS_LANES": "0"},                                 # encode pass by warp pairs instead of one thread per chunk
     {"DXO_RANS_LANES": "0", "DXO_RANS_CHUNK": "256", "DXO_RANS_WARMUP": "64", "DXO_RANS_FAULT": "1"},
 ])

@@ -42,6 +42,25 @@ def test_config1(orc):
     _compare(orc, synth.config1_mesh())
 
 
+def test_large_mesh_twice_through_the_host_block_pool(orc):
+    """Tables of a 400x300 grid (239k faces) are large enough to come from the pooled host blocks (common.hpp); the
+    second pass reuses the blocks of the first and must not see stale contents. Two threads run at once as well."""
+    import threading
+    m = synth.grid_mesh(400, 300, 5)
+    _compare(orc, m)
+    _compare(orc, m)
+    errs = []
+    def run():
+        try:
+            _compare(orc, synth.torus_mesh(300, 200, 6))
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    ts = [threading.Thread(target=run) for _ in range(2)]
+    for t in ts: t.start()
+    for t in ts: t.join()
+    assert not errs, errs
+
+
 def test_random_face_soups(orc):
     """Random index soups: non-manifold edges, flipped faces, shared vertices — the
     order-dependent paths of compute_table / handle_no_manifold_edges."""
