@@ -182,11 +182,20 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "Mvertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "C++ oracle (oracle/): the Rust reference cannot be compiled in this image; the oracle replaces its O(V^2) membership scans by rank lookups, so it is faster than the reference would be",
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT or sys.stdout, flush=True)
+
+
+RESULT_OUT = None  # the process's real stdout, see main()
 
 
 def main():
+    global RESULT_OUT
     args = parse_args()
+    # The JSON line is the only thing that may reach stdout: libraries that write to fd 1 on their own (NCCL prints its
+    # version banner there on the first collective) are sent to stderr for the rest of the run.
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -418,7 +427,7 @@ def main():
                                               "encoder is single-threaded per mesh; compare with e2e.value); one thread alone: single_thread_value "
                                               "(compare with e2e.single_call_mvertices_per_s)",
                                     "single_thread_value": V * reps / secs / 1e6}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=RESULT_OUT or sys.stdout, flush=True)
     sess.close()
     if dist is not None:
         dist.destroy_process_group()
