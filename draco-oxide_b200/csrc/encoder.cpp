@@ -76,7 +76,7 @@ struct PinnedPool {
       std::lock_guard<std::mutex> lock(mu);
       size_t best = free_blocks.size();
       for (size_t i = 0; i < free_blocks.size(); ++i)
-        if (free_blocks[i].second >= bytes && free_blocks[i].second <= 2 * bytes + 4096 &&
+        if (free_blocks[i].second >= bytes && free_blocks[i].second <= std::max<size_t>(2 * bytes + 4096, 2u << 20) &&  // blocks are >= 2 MB
             (best == free_blocks.size() || free_blocks[i].second < free_blocks[best].second)) best = i;
       if (best != free_blocks.size()) {
         auto b = free_blocks[best];
