@@ -349,6 +349,16 @@ def test_rans_paths_off_the_operating_point(env):
         assert fixups > 100, "the sequential fix-up was not exercised"
 
 
+def test_rans_stream_of_config3_size(orc):
+    """12M symbols (a 10M-triangle mesh's position stream is 15M): more chunks than the GPU holds warp pairs, chunk size at
+    its upper bound, ~47k encode pieces. Bit-exact against the sequential oracle coder, and deterministic."""
+    rng = np.random.default_rng(11)
+    sym = np.minimum(rng.geometric(0.03, 12_000_001) - 1, 3000).astype(np.uint32)
+    ref = orc.encode_symbols(sym)
+    assert dxo.encode_symbols(sym) == ref
+    assert dxo.encode_symbols(sym) == ref
+
+
 def test_resident_session_graph_replay(orc):
     """With DXO_FLAG_GRAPH_REPLAY a resident session replays the step as one CUDA graph from its second run on (all streams, flag copies, external
     events for the host coders). Streams must stay byte-identical, also after run_steps and from another thread."""
