@@ -56,7 +56,7 @@ def default_sessions(world):
     sleeps in them (DXO_BLOCKING_WAIT) when host threads are scarce, which then allows one session per two threads."""
     per_gpu = max(1, (os.cpu_count() or 2) // max(1, world))
     if per_gpu >= 15:
-        return max(1, min(6, per_gpu // 3)), False
+        return max(1, min(8, per_gpu // 2)), False  # measured on 16 threads: 5 sessions 1290, 8 sessions 1420, 16 sessions 1460 Mvertices/s
     return max(1, min(6, per_gpu // 2)), True
 
 
