@@ -164,6 +164,23 @@ def dedup_values(values, device=-1):
     return out_map[:n], first[: nu.value]
 
 
+def attribute_bounds(values, point_to_value=None, device=-1):
+    """Accessor min / max of the glTF writer (compute_vec3_bounds / compute_vec4_bounds, io/gltf/encode.rs:815-899) on the
+    device: per-component bounds over the values of all points, NaNs skipped. Returns (min, max) float32 arrays, or
+    (None, None) for an attribute without points (the reference returns empty vectors)."""
+    import numpy as np
+    v = np.ascontiguousarray(values, dtype=np.float32)
+    if v.ndim == 1:
+        v = v.reshape(-1, 1)
+    pm = None if point_to_value is None else np.ascontiguousarray(point_to_value, dtype=np.uint32)
+    npoints = v.shape[0] if pm is None else pm.shape[0]
+    mn, mx = (C.c_float * 4)(), (C.c_float * 4)()
+    _check(_capi.lib().dxo_attribute_bounds(v.ctypes.data, v.shape[0], v.shape[1], None if pm is None else pm.ctypes.data, npoints, device, mn, mx))
+    if npoints == 0:
+        return None, None
+    return np.array(mn[: v.shape[1]], np.float32), np.array(mx[: v.shape[1]], np.float32)
+
+
 def build_mesh(faces, atts, device=-1):
     """MeshBuilder: atts = list of (per_point_values ndarray, AttributeType, AttributeDomain, parents). Value dedup per
     attribute, position first, point merge, degenerate-face and unused-point removal (core/mesh/builder.rs:30-125);

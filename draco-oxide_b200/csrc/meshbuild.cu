@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <future>
+#include <limits>
 #include <memory>
 #include <string>
 #include <vector>
@@ -238,6 +239,39 @@ void remove_points(BuiltAttribute& a, const std::vector<uint8_t>& gone) {
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Accessor bounds — compute_vec3_bounds / compute_vec4_bounds (io/gltf/encode.rs:815-899): running f32::min / f32::max over
+// the values of all points, starting from point 0's value. f32::min / max return the other operand when one is NaN, so NaNs
+// are skipped unless every value is NaN. The order of the points matters only for that and for a mix of -0.0 and +0.0,
+// where the reference's result depends on how LLVM lowers minnum (unpinned): here -0.0 orders below +0.0.
+// Floats are compared through an order-preserving unsigned key; key 0 (below every real key) marks "no value yet".
+__device__ __forceinline__ uint32_t bounds_key(float v) {
+  const uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__global__ void __launch_bounds__(256) bounds_kernel(const float* __restrict__ values, const uint32_t* __restrict__ point_to_value, uint64_t num_points,
+                                                     uint32_t ncomp, uint32_t* __restrict__ keys /* [0..4) min, [4..8) max, [8..12) non-NaN seen */) {
+  uint32_t mn[4], mx[4], any[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { mn[k] = 0xFFFFFFFFu; mx[k] = 0u; any[k] = 0u; }
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < num_points; p += stride) {
+    const uint64_t v = point_to_value ? (uint64_t)__ldg(point_to_value + p) : p;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if ((uint32_t)k >= ncomp) break;
+      const float c = __ldg(values + v * ncomp + k);
+      if (c == c) { const uint32_t key = bounds_key(c); mn[k] = min(mn[k], key); mx[k] = max(mx[k], key); any[k] = 1u; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if ((uint32_t)k >= ncomp) break;
+    const uint32_t a = __reduce_min_sync(0xFFFFFFFFu, mn[k]), b = __reduce_max_sync(0xFFFFFFFFu, mx[k]), c = __reduce_or_sync(0xFFFFFFFFu, any[k]);
+    if ((threadIdx.x & 31) == 0 && c) { atomicMin(&keys[k], a); atomicMax(&keys[4 + k], b); atomicOr(&keys[8 + k], 1u); }
+  }
+}
+
 }  // namespace
 }  // namespace dxo
 
@@ -300,6 +334,45 @@ int dxo_dedup_values(const void* values, uint64_t n, uint32_t component_type, ui
     if (n) memcpy(out_map, r.uid.data(), 4 * (size_t)n);
     if (!r.first_index.empty()) memcpy(out_first_index, r.first_index.data(), 4 * r.first_index.size());
     *out_num_unique = r.first_index.size();
+  });
+}
+
+int dxo_attribute_bounds(const float* values, uint64_t num_values, uint32_t num_components, const uint32_t* point_to_value, uint64_t num_points,
+                         int device, float* out_min, float* out_max) {
+  if (!out_min || !out_max || num_components == 0 || num_components > 4 || (!values && num_values)) return DXO_ERR_INVALID_ARGUMENT;
+  if (!point_to_value) num_points = num_values;
+  if (num_points == 0) return DXO_OK;  // the reference returns empty vectors: outputs untouched
+  if (num_values == 0) return DXO_ERR_INVALID_ARGUMENT;
+  return guarded_build([&] {
+    if (point_to_value)
+      for (uint64_t p = 0; p < num_points; ++p)
+        if (point_to_value[p] >= num_values) throw Error(DXO_ERR_INVALID_ARGUMENT, "point_to_value entry out of range");
+    BuildStream bs(device);
+    float* d_values = nullptr; uint32_t *d_map = nullptr, *d_keys = nullptr;
+    const size_t vb = (size_t)num_values * num_components * sizeof(float);
+    cuda_check(cudaMallocAsync((void**)&d_values, vb, bs.s), "cudaMallocAsync");
+    cuda_check(cudaMemcpyAsync(d_values, values, vb, cudaMemcpyHostToDevice, bs.s), "cudaMemcpyAsync H2D");
+    if (point_to_value) {
+      cuda_check(cudaMallocAsync((void**)&d_map, (size_t)num_points * 4, bs.s), "cudaMallocAsync");
+      cuda_check(cudaMemcpyAsync(d_map, point_to_value, (size_t)num_points * 4, cudaMemcpyHostToDevice, bs.s), "cudaMemcpyAsync H2D");
+    }
+    uint32_t init[12];
+    for (int k = 0; k < 4; ++k) { init[k] = 0xFFFFFFFFu; init[4 + k] = 0u; init[8 + k] = 0u; }
+    cuda_check(cudaMallocAsync((void**)&d_keys, sizeof(init), bs.s), "cudaMallocAsync");
+    cuda_check(cudaMemcpyAsync(d_keys, init, sizeof(init), cudaMemcpyHostToDevice, bs.s), "cudaMemcpyAsync H2D");
+    const uint64_t want = (num_points + 256ull * 4 - 1) / (256ull * 4);
+    const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(want, 1), 148ull * 8);
+    bounds_kernel<<<grid, 256, 0, bs.s>>>(d_values, d_map, num_points, num_components, d_keys);
+    cuda_check(cudaGetLastError(), "bounds_kernel");
+    uint32_t keys[12];
+    cuda_check(cudaMemcpyAsync(keys, d_keys, sizeof(keys), cudaMemcpyDeviceToHost, bs.s), "cudaMemcpyAsync D2H");
+    cuda_check(cudaStreamSynchronize(bs.s), "cudaStreamSynchronize");
+    cudaFreeAsync(d_values, bs.s); if (d_map) cudaFreeAsync(d_map, bs.s); cudaFreeAsync(d_keys, bs.s);
+    auto unkey = [](uint32_t k) { const uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k; float f; memcpy(&f, &b, 4); return f; };
+    for (uint32_t k = 0; k < num_components; ++k) {
+      if (keys[8 + k]) { out_min[k] = unkey(keys[k]); out_max[k] = unkey(keys[4 + k]); }
+      else out_min[k] = out_max[k] = std::numeric_limits<float>::quiet_NaN();  // every value of the component is NaN
+    }
   });
 }
 

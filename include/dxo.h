@@ -237,6 +237,15 @@ void dxo_built_mesh_free(dxo_built_mesh* mesh);
 int dxo_dedup_values(const void* values, uint64_t n, uint32_t component_type, uint32_t num_components, int device,
                      uint32_t* out_map, uint32_t* out_first_index, uint64_t* out_num_unique);
 
+/* Accessor bounds of the glTF writer around encode(): compute_vec3_bounds / compute_vec4_bounds,
+ * io/gltf/encode.rs:815-899 — per-component minimum and maximum over the values of all points (values[point_to_value[p]],
+ * or values[p] when point_to_value is NULL and num_points is ignored), f32::min / f32::max semantics: NaNs are skipped, a
+ * component that holds only NaNs yields NaN. num_components <= 4. With zero points the outputs are left untouched (the
+ * reference returns empty vectors). A mix of -0.0 and +0.0 at a bound is unpinned in the reference (LLVM minnum); here
+ * -0.0 < +0.0. Runs on the device (no CPU fallback). */
+int dxo_attribute_bounds(const float* values, uint64_t num_values, uint32_t num_components, const uint32_t* point_to_value,
+                         uint64_t num_points, int device, float* out_min, float* out_max);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,7 @@ struct MeshHandle {
 
 }  // namespace
 
+#include <cmath>
 extern "C" {
 
 const char* orc_last_error() { return g_last_error.c_str(); }
@@ -331,5 +332,36 @@ void orc_oct_quantize(float x, float y, float z, int32_t* out, int* status) {
   if (status) *status = st;
 }
 void orc_oct_transform(float x, float y, float z, float* out) { octahedral_transform_f32(x, y, z, out[0], out[1]); }
+
+// compute_vec3_bounds / compute_vec4_bounds — io/gltf/encode.rs:815-899: the bounds start from point 0's value and fold
+// f32::min / f32::max over points 1.. in order (Attribute::get maps the point through point_to_att_val_map,
+// core/attribute/mod.rs:122-128, 216-230). f32::min / max return the other operand when one is NaN. For -0.0 against
+// +0.0 the reference's result depends on LLVM's lowering of minnum / maxnum (unpinned); this restatement orders
+// -0.0 below +0.0. Returns the number of points folded (0: the reference returns empty vectors, outputs untouched).
+uint64_t orc_attribute_bounds(const float* values, uint64_t num_values, uint32_t ncomp, const uint32_t* point_to_value, uint64_t num_points,
+                              float* out_min, float* out_max) {
+  if (!point_to_value) num_points = num_values;
+  if (num_points == 0) return 0;
+  auto value_of = [&](uint64_t p, uint32_t k) { return values[(point_to_value ? point_to_value[p] : p) * ncomp + k]; };
+  auto rust_min = [](float a, float b) {
+    if (a != a) return b;
+    if (b != b) return a;
+    if (a == b) return std::signbit(a) ? a : b;  // -0.0 before +0.0
+    return a < b ? a : b;
+  };
+  auto rust_max = [](float a, float b) {
+    if (a != a) return b;
+    if (b != b) return a;
+    if (a == b) return std::signbit(a) ? b : a;
+    return a > b ? a : b;
+  };
+  for (uint32_t k = 0; k < ncomp; ++k) { out_min[k] = value_of(0, k); out_max[k] = value_of(0, k); }
+  for (uint64_t p = 1; p < num_points; ++p)
+    for (uint32_t k = 0; k < ncomp; ++k) {
+      out_min[k] = rust_min(out_min[k], value_of(p, k));
+      out_max[k] = rust_max(out_max[k], value_of(p, k));
+    }
+  return num_points;
+}
 
 }  // extern "C"

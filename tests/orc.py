@@ -43,6 +43,8 @@ def lib():
         L.orc_mesh_free.argtypes = [C.c_void_p]
         L.orc_dedup_and_remove.argtypes = [C.POINTER(C.c_float), C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint64,
                                            C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+        L.orc_attribute_bounds.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.orc_attribute_bounds.restype = C.c_uint64
         L.orc_leb128.argtypes = [C.c_uint64, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]
         L.orc_bitwriter.argtypes = [C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]
         L.orc_rans_encode_raw.argtypes = [C.POINTER(C.c_uint64), C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint64, C.POINTER(_capi.dxo_bytes)]
@@ -261,3 +263,17 @@ def decode_symbols(buf, n):
     if st != 0:
         raise OracleError(st)
     return out, used.value
+
+
+def attribute_bounds(values, point_to_value=None):
+    """compute_vec3_bounds / compute_vec4_bounds of the reference's glTF writer: (min, max) or (None, None) without points."""
+    v = np.ascontiguousarray(values, dtype=np.float32)
+    if v.ndim == 1:
+        v = v.reshape(-1, 1)
+    pm = None if point_to_value is None else np.ascontiguousarray(point_to_value, dtype=np.uint32)
+    mn, mx = (C.c_float * 4)(), (C.c_float * 4)()
+    n = lib().orc_attribute_bounds(v.ctypes.data, v.shape[0], v.shape[1], None if pm is None else pm.ctypes.data,
+                                   0 if pm is None else pm.shape[0], mn, mx)
+    if n == 0:
+        return None, None
+    return np.array(mn[: v.shape[1]], np.float32), np.array(mx[: v.shape[1]], np.float32)

@@ -83,3 +83,6 @@ def test_product_fails_loudly_without_gpu(built):
     with pytest.raises(dxo.Err) as e:
         dxo.dedup_values(pos)
     assert e.value.status == -20
+    with pytest.raises(dxo.Err) as e:
+        dxo.attribute_bounds(pos)
+    assert e.value.status == -20

@@ -108,3 +108,33 @@ def test_build_errors():
     with pytest.raises(dxo.Err) as e:
         dxo.build_mesh(np.array([[0, 1, 7]], np.uint32), [(pos, Ty.Position, Dom.Position, ())])
     assert e.value.status == -1
+
+
+def test_accessor_bounds_match_oracle(orc):
+    """dxo_attribute_bounds (io/gltf/encode.rs:815-899) against the oracle: bit-exact floats, with and
+    without a point map, NaNs, signed zeros, one point, no points, 1-4 components, config-2-sized input."""
+    rng = np.random.default_rng(9)
+    def same(values, pm=None):
+        a, b = dxo.attribute_bounds(values, pm), orc.attribute_bounds(values, pm)
+        if b[0] is None:
+            assert a == (None, None)
+            return
+        assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes(), (a, b)
+    for ncomp in (1, 2, 3, 4):
+        v = (rng.normal(size=(5000, ncomp)) * 100).astype(np.float32)
+        same(v)
+        same(v, rng.integers(0, 5000, 12345).astype(np.uint32))
+        same(v, rng.integers(10, 20, 7).astype(np.uint32))
+        v[rng.integers(0, 5000, 300), rng.integers(0, ncomp, 300)] = np.nan
+        same(v)
+    same(np.array([[3.5, -1.25, 7.0]], np.float32))
+    same(np.zeros((0, 3), np.float32))
+    same(np.array([[0.0], [-0.0], [0.0]], np.float32))
+    same(np.array([[-0.0], [0.0]], np.float32))
+    same(np.full((9, 2), np.nan, np.float32))
+    same(np.array([[5.0, 6.0], [1.0, 2.0]], np.float32), np.array([0, 0, 0], np.uint32))
+    m = synth.config2_mesh(600)
+    pos = m.attributes[0]
+    same(pos.values, pos.point_to_value)
+    with pytest.raises(dxo.Err):
+        dxo.attribute_bounds(np.zeros((3, 3), np.float32), np.array([0, 3], np.uint32))  # map entry out of range

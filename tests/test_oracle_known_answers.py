@@ -266,3 +266,24 @@ def test_octahedral_transform_inverse(orc):
         r = np.asarray([x, y, z])
         r /= np.sqrt((r * r).sum())
         assert ((n - r) ** 2).sum() < 1e-10
+
+
+def test_accessor_bounds_restatement(orc):
+    """compute_vec3_bounds (io/gltf/encode.rs:815-856): true per-point bounds starting from point 0 — unlike the
+    quantizer's zero-initialised bounds (Appendix B.3) an all-positive attribute keeps a positive minimum; NaNs are
+    skipped by f32::min / max; the point map selects which values count; no points -> empty."""
+    v = np.array([[1, 2, 3], [4, 5, 6], [2, 9, 3.5]], np.float32)
+    mn, mx = orc.attribute_bounds(v)
+    assert mn.tolist() == [1, 2, 3] and mx.tolist() == [4, 9, 6]
+    mn, mx = orc.attribute_bounds(v, [2, 2, 0])          # value 1 is referenced by no point
+    assert mn.tolist() == [1, 2, 3] and mx.tolist() == [2, 9, 3.5]
+    w = np.array([[np.nan, 1], [3, np.nan], [-2, np.nan]], np.float32)
+    mn, mx = orc.attribute_bounds(w)
+    assert mn.tolist() == [-2, 1] and mx.tolist() == [3, 1]
+    mn, mx = orc.attribute_bounds(np.full((4, 1), np.nan, np.float32))
+    assert np.isnan(mn[0]) and np.isnan(mx[0])
+    assert orc.attribute_bounds(np.zeros((0, 3), np.float32)) == (None, None)
+    rng = np.random.default_rng(3)
+    r = rng.normal(size=(1000, 4)).astype(np.float32)
+    mn, mx = orc.attribute_bounds(r)
+    assert np.array_equal(mn, r.min(axis=0)) and np.array_equal(mx, r.max(axis=0))
