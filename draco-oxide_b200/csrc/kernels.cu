@@ -1251,7 +1251,7 @@ __device__ __forceinline__ uint32_t rans_guess_state(uint32_t lane, uint32_t l_b
 
 // phase A — exploration (two chunks per CTA): no bytes, 32 candidate (entering state -> exit state) pairs per chunk
 __global__ void __launch_bounds__(128) rans_explore_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                           RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, uint32_t kRansWarmup, uint32_t sub,
+                                                           RansChunkState cs, uint32_t num_chunks, uint32_t chunk_steps, uint32_t warmup_steps, uint32_t sub,
                                                            AttrStats* stats) {
   __shared__ RansShared sh2[2];
   __shared__ int role_slot[2];
@@ -1263,13 +1263,13 @@ __global__ void __launch_bounds__(128) rans_explore_kernel(const uint32_t* __res
   RansShared& sh = sh2[role.pair];
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
   const uint32_t lane = threadIdx.x & 31;
-  const unsigned long long e_main = j * kRansChunk;
-  const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
-  const unsigned long long e_begin = e_main > kRansWarmup ? e_main - kRansWarmup : 0;
+  const unsigned long long e_main = j * chunk_steps;
+  const unsigned long long e_end = min(e_main + (unsigned long long)chunk_steps, n);
+  const unsigned long long e_begin = e_main > warmup_steps ? e_main - warmup_steps : 0;
   const uint32_t l_base = 4u << P;
   const uint32_t x_in = e_begin == 0 ? l_base : rans_guess_state(lane, l_base);  // a warm-up from step 0 is the true trajectory
   rans_encode_range(sh, symbols, n, table, K, P, e_begin, e_main, e_end, x_in, nullptr, role.bar_base, role.is_consumer, false,
-                    kRansChunk / sub / 32);
+                    chunk_steps / sub / 32);
   if (role.is_consumer) {
     cs.cand_start[j * 32 + lane] = sh.x_main[lane];
     cs.cand_exit[j * 32 + lane] = sh.x_exit[lane];
@@ -1285,7 +1285,7 @@ __global__ void __launch_bounds__(128) rans_explore_kernel(const uint32_t* __res
 // next tile's global loads are in flight while the current tile is walked.
 constexpr int kChainTile = 32;
 __global__ void __launch_bounds__(64) rans_chain_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                        RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, uint32_t nsub, AttrStats* stats) {
+                                                        RansChunkState cs, uint32_t num_chunks, uint32_t chunk_steps, uint32_t nsub, AttrStats* stats) {
   __shared__ RansShared sh;
   __shared__ uint32_t tile_s[2][kChainTile][32], tile_e[2][kChainTile][32];
   if (stats->error_flags) return;
@@ -1330,9 +1330,9 @@ __global__ void __launch_bounds__(64) rans_chain_kernel(const uint32_t* __restri
       } else {  // both warps see the same values and take this branch together
         // The chunk is run from the true state here, one sub-chunk at a time, and lane 0's candidate slots are overwritten
         // with the true states so that the encode pass finds them like any other match.
-        const unsigned long long e_main = (unsigned long long)j * kRansChunk;
-        const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
-        const uint32_t sub = kRansChunk / nsub;
+        const unsigned long long e_main = (unsigned long long)j * chunk_steps;
+        const unsigned long long e_end = min(e_main + (unsigned long long)chunk_steps, n);
+        const uint32_t sub = chunk_steps / nsub;
         if (threadIdx.x == 0) cs.cand_start[(size_t)j * 32] = s;
         for (uint32_t k = 0; k < nsub; ++k) {
           const unsigned long long e0 = e_main + (unsigned long long)k * sub;
@@ -1361,7 +1361,7 @@ __global__ void rans_fault_kernel(RansChunkState cs, uint32_t num_chunks, AttrSt
 
 // phase C — every chunk is encoded once from its true entering state (two chunks per CTA)
 __global__ void __launch_bounds__(128) rans_encode_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                          uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk, AttrStats* stats) {
+                                                          uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t chunk_steps, AttrStats* stats) {
   __shared__ RansShared sh2[2];
   __shared__ int role_slot[2];
   __shared__ uint32_t sched_slot[4];
@@ -1372,9 +1372,9 @@ __global__ void __launch_bounds__(128) rans_encode_kernel(const uint32_t* __rest
   RansShared& sh = sh2[role.pair];
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
   const uint32_t in = j == 0 ? (4u << P) : cs.chain_start[j];
-  const unsigned long long e_main = j * kRansChunk;
-  const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
-  rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, in, scratch + j * rans_chunk_capacity(kRansChunk), role.bar_base, role.is_consumer);
+  const unsigned long long e_main = j * chunk_steps;
+  const unsigned long long e_end = min(e_main + (unsigned long long)chunk_steps, n);
+  rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, in, scratch + j * rans_chunk_capacity(chunk_steps), role.bar_base, role.is_consumer);
   if (role.is_consumer && (threadIdx.x & 31) == 0) {
     cs.start[j] = in;
     cs.exit[j] = sh.x_exit[0];
@@ -1536,7 +1536,7 @@ constexpr int kFixupThreads = 1024, kFixupItems = 8;
 constexpr int kFixupPairBarrier = 2 * kRansStages + 2;  // named barrier of the repairing pair (rans_encode_range with bar_base 1 uses 1..7)
 __global__ void __launch_bounds__(kFixupThreads) rans_fixup_kernel(const uint32_t* __restrict__ symbols, unsigned long long n,
                                                                    const uint4* __restrict__ table, uint8_t* __restrict__ scratch, RansChunkState cs,
-                                                                   uint32_t num_chunks, uint32_t kRansChunk, AttrStats* stats) {
+                                                                   uint32_t num_chunks, uint32_t chunk_steps, AttrStats* stats) {
   __shared__ RansShared sh;
   __shared__ uint32_t s_in, s_bad, s_warp[kFixupThreads / 32];
   if (stats->error_flags) return;
@@ -1566,9 +1566,9 @@ __global__ void __launch_bounds__(kFixupThreads) rans_fixup_kernel(const uint32_
       const uint32_t in = s_in;
       named_bar_sync(kFixupPairBarrier);  // s_in is rewritten by thread 0 in the next iteration
       if (in == cs.start[j]) continue;    // uniform: both warps read the same values
-      const unsigned long long e_main = (unsigned long long)j * kRansChunk;
-      const unsigned long long e_end = min(e_main + (unsigned long long)kRansChunk, n);
-      rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, in, scratch + (unsigned long long)j * rans_chunk_capacity(kRansChunk), 1, is_consumer);
+      const unsigned long long e_main = (unsigned long long)j * chunk_steps;
+      const unsigned long long e_end = min(e_main + (unsigned long long)chunk_steps, n);
+      rans_encode_range(sh, symbols, n, table, K, P, e_main, e_main, e_end, in, scratch + (unsigned long long)j * rans_chunk_capacity(chunk_steps), 1, is_consumer);
       if (threadIdx.x == 0) {
         cs.start[j] = in;
         cs.exit[j] = sh.x_exit[0];
@@ -1614,14 +1614,14 @@ __global__ void __launch_bounds__(kFixupThreads) rans_fixup_kernel(const uint32_
 
 // gather: piece j's bytes go to payload[offset[j]]; the last piece's threads append the flush bytes. A CTA copies
 // `pieces_per_cta` pieces (a power of two <= 8), 256 / pieces_per_cta threads each.
-__global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t kRansChunk,
+__global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t chunk_steps,
                                                           uint32_t pieces_per_cta, uint8_t* __restrict__ out, AttrStats* stats) {
   if (stats->error_flags) { if (blockIdx.x == 0 && threadIdx.x == 0) stats->payload_bytes = 0; return; }
   const uint32_t tpp = 256u / pieces_per_cta;  // threads per piece
   const uint32_t j = blockIdx.x * pieces_per_cta + threadIdx.x / tpp, t = threadIdx.x % tpp;
   if (j >= num_chunks) return;
   const uint32_t off = num_chunks > 1 ? cs.offset[j] : 0u, nb = cs.nbytes[j];
-  const uint8_t* src = scratch + (unsigned long long)j * rans_chunk_capacity(kRansChunk);
+  const uint8_t* src = scratch + (unsigned long long)j * rans_chunk_capacity(chunk_steps);
   for (uint32_t i = t; i < nb; i += tpp) out[off + i] = src[i];
   if (j + 1 == num_chunks && t == 0) {
     uint32_t pos = off + nb, err = 0;
