@@ -1384,16 +1384,17 @@ __global__ void __launch_bounds__(128) rans_encode_kernel(const uint32_t* __rest
   rans_role_release(role);
 }
 
-// phase C, lane-parallel variant — one THREAD per chunk (32 chunks per warp) instead of one warp pair per chunk. All that the
-// serial chain of a chunk needs is one lane, so this spends ~1/20 of the instruction slots of the warp-pair kernel; a lone
-// warp issues its ~40 instructions per step more slowly than the specialised consumer (≈ 50 ns against 32 ns per step), which
-// a single stream pays as latency and concurrent sessions win back several times over as throughput. To keep the inner loop's
-// memory accesses coalesced or in shared memory: per 32 steps the warp loads, for each of its 32 chunks, one coalesced
-// 128-byte row of symbols and parks it in shared memory with a 33-word pitch (conflict-free both ways), the next group's
-// loads are in flight meanwhile; table rows live in shared memory (alphabets up to kLaneSmemRows, else read through L1);
-// bytes are collected in a 64-bit register and written as aligned 32-bit words. A row with f = 2^21, M = 0, cum = 0 is the
-// identity step and stands in for every step outside a chunk, so the loop has no per-lane control flow.
-constexpr int kLaneThreads = 128;          // chunks per CTA (4 warps)
+// phase C, lane-parallel variant — one THREAD per piece (a chunk's sub-chunk; 32 pieces per warp) instead of one warp pair
+// per chunk. All that the serial chain needs is one lane, so this spends ~1/20 of the instruction slots of the warp-pair
+// kernel; a lone warp issues its ~40 instructions per step more slowly than the specialised consumer (≈ 85 ns against
+// 28 ns per step), which is why the pieces are short: the exploration's checkpoints give the true entering state of up to 16
+// pieces per chunk, so a stream makes 16x more pieces than chunks and the pass takes ~30 us instead of ~200. To keep the
+// inner loop's memory accesses coalesced or in shared memory: per 32 steps the warp loads, for each of its 32 pieces, one
+// coalesced 128-byte row of symbols and parks it in shared memory with a 33-word pitch (conflict-free both ways), the next
+// group's loads are in flight meanwhile; table rows live in shared memory (alphabets up to kLaneSmemRows, else read through
+// L1); bytes are collected in a 64-bit register and written as aligned 32-bit words. A row with f = 2^21, M = 0, cum = 0 is
+// the identity step and stands in for every step outside a piece, so the loop has no per-lane control flow.
+constexpr int kLaneThreads = 128;          // pieces per CTA (4 warps)
 constexpr uint32_t kLaneSmemRows = 4096;   // 64 KB of table rows in shared memory
 constexpr uint32_t kLanePitch = 33;        // words per staged symbol row
 constexpr uint32_t kLaneDeadSymbol = 0xFFFFFFFFu;
