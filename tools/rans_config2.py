@@ -1,5 +1,5 @@
 """Device step time of config 2 plus the speculative-rANS counters (DXO_RANS_DEBUG=1) for the current
-DXO_RANS_CHUNK / DXO_RANS_WARMUP / DXO_RANS_ROUNDS."""
+DXO_RANS_CHUNK / DXO_RANS_WARMUP / DXO_RANS_SUB (unset: the adaptive chunk size)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import draco_oxide_b200 as dxo
