@@ -341,7 +341,7 @@ def main():
     single_call_ms = 1e3 * (time.perf_counter() - t0) / lone_calls
     tm = dxo.last_timing()
     h2d, d2h = tm["h2d_bytes"], tm["d2h_bytes"]
-    T = args.e2e_callers if args.e2e_callers > 0 else max(1, (os.cpu_count() or 1) // max(1, world))
+    T = args.e2e_callers if args.e2e_callers > 0 else max(1, min(32, (os.cpu_count() or 1) // max(1, world)))  # ~250 MB of pinned tables per caller
     e2e_steps = max(1, min(args.steps, 10))
     e_ready, e_go = threading.Barrier(T + 1), threading.Barrier(T + 1)
     e_errors = []
