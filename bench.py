@@ -167,7 +167,7 @@ def run_reference(args, rank, world):
     orc.build()
     mesh, desc = make_mesh(args.workload)
     V = mesh.num_points()
-    threads = max(1, os.cpu_count() or 1)  # every host thread encodes the workload mesh: the reference is single-threaded per mesh
+    threads = max(1, min(64, os.cpu_count() or 1))  # every host thread (at most 64: ~250 MB each) encodes the workload mesh; the reference is single-threaded per mesh
     for _ in range(max(0, min(args.warmup, 1))):
         orc.encode_timed(mesh, 1, threads)
     t = 0.0
@@ -422,7 +422,7 @@ def main():
             import orc
             reps = 3
             secs = orc.encode_timed(mesh, reps, 1)
-            cores = max(1, os.cpu_count() or 1)
+            cores = max(1, min(64, os.cpu_count() or 1))
             secs_all = orc.encode_timed(mesh, 2, cores)
             line["cpu_baseline"] = {"value": V * 2 * cores / secs_all / 1e6, "unit": "Mvertices/s", "cores": cores, "kind": "port",
                                     "sample": f"2 full encode() calls of the same mesh per thread by the C++ oracle on {cores} threads at once (the reference "
