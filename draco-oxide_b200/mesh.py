@@ -81,8 +81,23 @@ class Attribute:
         key = v + 0 if v.dtype.kind == "f" else v  # -0.0 + 0 == +0.0: float == semantics
         if v.dtype.kind == "f" and np.isnan(key).any():
             raise ValueError("NaN attribute values are not supported by from_points")
-        kb = np.ascontiguousarray(key).view(np.dtype((np.void, key.dtype.itemsize * key.shape[1]))).ravel()
-        _, first, inv = np.unique(kb, return_index=True, return_inverse=True)
+        key = np.ascontiguousarray(key)
+        # Group rows by a 64-bit mix of their bytes (integer sort), then check that every row equals the first row of
+        # its group: if so the hash groups ARE the value groups. Otherwise (a collision) compare the raw bytes.
+        words = key.view(np.uint8).reshape(key.shape[0], -1).astype(np.uint64) if key.dtype.itemsize < 4 else \
+            key.view(np.uint32).reshape(key.shape[0], -1).astype(np.uint64)
+        h = np.full(key.shape[0], 0x9E3779B97F4A7C15, np.uint64)
+        with np.errstate(over="ignore"):
+            for c in range(words.shape[1]):
+                h = (h ^ words[:, c]) * np.uint64(0xFF51AFD7ED558CCD)
+                h ^= h >> np.uint64(29)
+        hs = np.sort(h)
+        if not (hs[1:] == hs[:-1]).any():  # distinct hashes: distinct rows
+            return cls(v, att_type, domain, parents, None, unique_id)
+        _, first, inv = np.unique(h, return_index=True, return_inverse=True)
+        if not np.array_equal(key[first[inv]], key):
+            kb = key.view(np.dtype((np.void, key.dtype.itemsize * key.shape[1]))).ravel()
+            _, first, inv = np.unique(kb, return_index=True, return_inverse=True)
         order = np.argsort(first, kind="stable")            # unique ids sorted by first occurrence
         rank = np.empty_like(order)
         rank[order] = np.arange(order.size)

@@ -86,6 +86,14 @@ def test_config3_quarter_size_torus_with_seams(orc):
     assert gpu_encode(m) == orc.encode(m)
 
 
+def test_config3_full_size_byte_parity(orc):
+    """BASELINE config 3 at full size (2000 x 2500-quad torus, 10 000 000 triangles, uv seams on both cuts):
+    the stream is byte-identical to the oracle's."""
+    m = synth.config3_mesh()
+    assert m.faces.shape[0] == 10_000_000 and m.attributes[0].num_unique_values == 5_000_000
+    assert gpu_encode(m) == orc.encode(m)
+
+
 def test_config3_full_size_properties(orc):
     """BASELINE config 3 (10M triangles): size-independent properties — the stream parses,
     every rANS / rABS section decodes back to the symbols and bits the GPU produced, and
@@ -117,6 +125,50 @@ def test_quantization_bit_sweep(orc, bits):
     m = synth.grid_mesh(120, 90, 5)
     cfg = dxo.Config(position_bits=bits, texcoord_bits=min(bits, 12))
     assert_stage_parity(orc, m, cfg)
+
+
+@pytest.fixture(scope="module")
+def config2_mesh():
+    return synth.config2_mesh()
+
+
+@pytest.mark.parametrize("bits", [8, 10, 11, 12, 14, 16])
+def test_config5_qp_sweep_on_the_1m_vertex_mesh(orc, config2_mesh, bits):
+    """BASELINE config 5 at its stated size: qp in {8,10,11,12,14,16} on config 2's 1M-vertex mesh, Edgebreaker
+    (the reference has no sequential-connectivity attribute path). Byte parity against the oracle."""
+    cfg = dxo.Config(position_bits=bits)
+    assert gpu_encode(config2_mesh, cfg) == orc.encode(config2_mesh, cfg)
+
+
+def _config4_full_batch(num_gpus):
+    """All 4096 primitives of BASELINE config 4 (87.9M vertices) through dxo_encode_batch, in slabs of 512 to bound
+    host memory; every stream's sha256 against tests/golden/config4_hashes.txt (oracle bytes,
+    tests/golden/make_config4_hashes.py) and the checksum of checksums."""
+    lines = open(meshes.GOLDEN + "/config4_hashes.txt").read().split()
+    counts = synth.batch_vertex_counts()
+    assert counts.size == 4096 and len(lines) == 4097
+    digests = []
+    for lo in range(0, counts.size, 512):
+        ms = synth.batch_meshes(counts[lo:lo + 512], first=lo)
+        got = dxo.encode_batch(ms, first_gpu=0, num_gpus=num_gpus)
+        assert len(got) == len(ms)
+        for k, g in enumerate(got):
+            d = hashlib.sha256(g).hexdigest()
+            assert d[:16] == lines[lo + k], f"primitive {lo + k} ({ms[k].num_points()} points) differs from the oracle's stream"
+            digests.append(d)
+    assert hashlib.sha256("".join(digests).encode()).hexdigest() == lines[4096]
+
+
+def test_config4_full_batch_one_gpu():
+    _config4_full_batch(1)
+
+
+def test_config4_full_batch_over_all_gpus():
+    """Runs when the lease has more than one GPU (`gpurun --gpus N`): the batch is sharded over all of them."""
+    n = dxo.device_count()
+    if n < 2:
+        pytest.skip("single-GPU lease: covered by test_config4_full_batch_one_gpu")
+    _config4_full_batch(n)
 
 
 def test_batch_entry_matches_per_mesh_streams(orc):

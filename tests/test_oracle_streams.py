@@ -68,3 +68,15 @@ def test_quantization_bit_sweep(orc):
     m = synth.grid_mesh(20, 20, 4)
     sizes = [len(orc.encode(m, dxo.Config(position_bits=b))) for b in (8, 10, 11, 12, 14, 16)]
     assert sizes == sorted(sizes)  # more bits never shrinks the stream on this mesh
+
+
+def test_config4_sample_matches_golden_hashes(orc):
+    """A sample of BASELINE config 4's 4096 primitives (the smallest 24 of the first 256 plus two larger ones)
+    against tests/golden/config4_hashes.txt; the GPU suite checks all 4096 at full size."""
+    lines = open(meshes.GOLDEN + "/config4_hashes.txt").read().split()
+    counts = synth.batch_vertex_counts()
+    assert len(lines) == counts.size + 1
+    pick = sorted(np.argsort(counts[:256])[:24].tolist() + [2, 255])
+    for k in pick:
+        m = synth.batch_mesh(k, int(counts[k]))
+        assert hashlib.sha256(orc.encode(m)).hexdigest()[:16] == lines[k], k
