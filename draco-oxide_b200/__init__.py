@@ -77,8 +77,9 @@ def encode(mesh, writer, cfg=None):
         writer.write(data)
 
 
-def encode_batch(meshes, cfg=None, first_gpu=0, num_gpus=1):
-    """The transcoder loop (io/gltf/encode.rs:941-953): one stream per mesh."""
+def encode_batch(meshes, cfg=None, first_gpu=0, num_gpus=1, return_statuses=False):
+    """The transcoder loop (io/gltf/encode.rs:941-953): one stream per mesh. With return_statuses the call does not
+    raise for per-mesh failures and returns (streams, statuses) instead (a failed mesh has an empty stream)."""
     cfg = cfg or Config.default()
     L = _capi.lib()
     n = len(meshes)
@@ -89,6 +90,8 @@ def encode_batch(meshes, cfg=None, first_gpu=0, num_gpus=1):
     cc = cfg.as_c()
     st = L.dxo_encode_batch(arr, n, C.byref(cc), outs, sts, first_gpu, num_gpus)
     res = [_take(outs[i]) for i in range(n)]
+    if return_statuses:
+        return res, [int(sts[i]) for i in range(n)]
     _check(st)
     return res
 

@@ -86,6 +86,12 @@ void run_device_phase(MeshJob& job, DeviceContext& ctx, Profile& prof, std::vect
 thread_local Profile g_profile;
 
 void encode_one(const dxo_mesh* mesh, const dxo_config& cfg, std::vector<uint8_t>& bytes, dxo_timing& tm, bool parallel_host = true) {
+  dxo::encode_one_mesh(mesh, cfg, bytes, tm, parallel_host);
+}
+
+}  // namespace
+
+void dxo::encode_one_mesh(const dxo_mesh* mesh, const dxo_config& cfg, std::vector<uint8_t>& bytes, dxo_timing& tm, bool parallel_host) {
   tm = dxo_timing{};
   const auto t0 = Clock::now();
   MeshJob job(mesh, cfg);
@@ -103,8 +109,6 @@ void encode_one(const dxo_mesh* mesh, const dxo_config& cfg, std::vector<uint8_t
   job.release(ctx);
   tm.total_ms = (float)ms_since(t0);
 }
-
-}  // namespace
 
 struct dxo_session {
   std::unique_ptr<MeshJob> job;
@@ -145,7 +149,13 @@ int dxo_encode_batch(const dxo_mesh* meshes, size_t n, const dxo_config* cfg, dx
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { cudaGetLastError(); throw Error(DXO_ERR_NO_DEVICE, "no CUDA device available (this path has no CPU fallback)"); }
     if (num_gpus <= 0) num_gpus = 1;
     if (first_gpu < 0 || first_gpu + num_gpus > count) throw Error(DXO_ERR_NO_DEVICE, "GPU range out of bounds");
-    // longest-processing-time-first order over a shared queue
+    if (!getenv("DXO_BATCH_PER_MESH")) {  // groups of meshes through segmented launches (batch.cpp)
+      std::vector<int> sts(n, DXO_OK);
+      encode_batch_grouped(meshes, n, base, outs, sts.data(), first_gpu, num_gpus);
+      for (size_t i = 0; i < n; ++i) { if (statuses) statuses[i] = sts[i]; if (sts[i] != DXO_OK && first_error == DXO_OK) first_error = sts[i]; }
+      return;
+    }
+    // DXO_BATCH_PER_MESH=1: the per-mesh path for every mesh, longest-processing-time-first order over a shared queue
     std::vector<size_t> order(n);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return meshes[a].num_faces > meshes[b].num_faces; });
@@ -400,7 +410,7 @@ int dxo_corner_table_opposites(const uint32_t* vertex_of_corner, uint64_t num_fa
     cuda_check(cudaMemcpyAsync(d_cv, vertex_of_corner, C * 4, cudaMemcpyHostToDevice, s), "H2D");
     cuda_check(cudaMemsetAsync(d_flag, 0, 4, s), "memset");
     cuda_check(cudaMemsetAsync(d_opp, 0xFF, C * 4, s), "memset");
-    gpu::launch_corner_table_opposites(d_cv, C, d_opp, d_flag, scratch, sb, s);
+    gpu::launch_corner_table_opposites(d_cv, C, 0, d_opp, d_flag, scratch, sb, s);
     uint32_t flag = 0;
     cuda_check(cudaMemcpyAsync(opposite_out, d_opp, C * 4, cudaMemcpyDeviceToHost, s), "D2H");
     cuda_check(cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, s), "D2H");

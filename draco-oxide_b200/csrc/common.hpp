@@ -61,6 +61,8 @@ class HostArray {
   HostArray& operator=(HostArray&&) = default;
   using Source = void* (*)(void* user, size_t bytes);  // returns memory for `bytes` bytes or nullptr
   void set_source(Source fn, void* user) { source_ = fn; source_user_ = user; }
+  // lives in caller-owned memory from now on (contents kept as they are); the memory outlives the array
+  void adopt(T* p, size_t n) { own_.clear(); p_ = p; n_ = cap_ = n; }
   T* data() { return p_; }
   const T* data() const { return p_; }
   size_t size() const { return n_; }

@@ -107,6 +107,7 @@ void UniversalTable::build(const uint32_t* faces, uint32_t nfaces, const AttrVie
     return mx;
   });
   if (num_corners && max_p >= pos.num_points) throw Error(DXO_ERR_INVALID_ARGUMENT, "face references a point outside the position attribute");
+  max_point = max_p;
   uint32_t max_v = max_p;
   if (map) max_v = over_parts([&](uint32_t c0, uint32_t c1) {
     uint32_t mx = 0;

@@ -23,6 +23,7 @@ struct AttrView {
 // Universal (position) corner table — CornerTable, core/corner_table/mod.rs:54-529.
 struct UniversalTable {
   uint32_t num_faces = 0, num_corners = 0, num_vertices = 0;
+  uint32_t max_point = 0;                  // largest point index used by a face (build)
   const uint32_t* corner_point = nullptr;  // faces, 3 per face (borrowed)
   HostArray<uint32_t> corner_vertex;     // vertex_idx(c), non-manifold splits applied
   HostArray<uint32_t> opposite;          // kNone = boundary

@@ -115,6 +115,8 @@ struct PinnedPool {
 };
 PinnedPool& pinned_pool() { static PinnedPool* pool = new PinnedPool; return *pool; }  // never destroyed: outlives every job
 }  // namespace
+void* pinned_block_take(size_t bytes, size_t* capacity) { return pinned_pool().take(bytes, capacity); }
+void pinned_block_give(void* p, size_t capacity) { pinned_pool().give(p, capacity); }
 
 HelperThreads::HelperThreads(int n) { for (int i = 0; i < n; ++i) threads_.emplace_back([this] { loop(); }); }
 HelperThreads::~HelperThreads() {
@@ -353,7 +355,7 @@ uint32_t MeshJob::device_matcher(void* user, const uint32_t* corner_vertex, uint
   cuda_check(cudaMallocAsync(&lscratch, lb, s), "cudaMallocAsync");
   cuda_check(cudaMemsetAsync(d_flag, 0, 12, s), "cudaMemsetAsync");
   cuda_check(cudaMemsetAsync(d_opp, 0xFF, C * 4, s), "cudaMemsetAsync");
-  gpu::launch_corner_table_opposites(d_cv, C, d_opp, d_flag, scratch, sb, s);
+  gpu::launch_corner_table_opposites(d_cv, C, num_vertices, d_opp, d_flag, scratch, sb, s);
   gpu::launch_left_most(d_cv, d_opp, C, num_vertices, lscratch, d_lm, d_flag + 1, s);
   gpu::launch_boundary_list(d_opp, C, bscratch, bb, d_blist, d_flag + 2, s);
   uint32_t flag[3] = {1, 0, 0};
@@ -400,12 +402,7 @@ uint32_t MeshJob::device_matcher(void* user, const uint32_t* corner_vertex, uint
 void MeshJob::build_connectivity(DeviceContext* ctx) {
   const uint32_t nfaces = (uint32_t)mesh_->num_faces;
   StageClock clk;
-  // header (encode/header/mod.rs:26-54)
-  for (char ch : std::string("DRACO")) head_.u8((uint8_t)ch);
-  head_.u8(2); head_.u8(2);
-  head_.u8(1);    // EncodedGeometryType::TrianglarMesh
-  head_.u8(1);    // EncoderMethod::Edgebreaker
-  head_.u16(0);   // flags: no metadata
+  write_stream_header();
 
   match_ctx_ = ctx;
   dev_.assign(plans_.size(), AttrDevice{});
@@ -415,6 +412,7 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
   if (ctx != nullptr && !getenv("DXO_NO_PINNED_TABLES")) ut_.set_memory_source(&MeshJob::pinned_source, this);
   const bool use_k12 = ctx != nullptr && nfaces >= 4096 && !getenv("DXO_NO_K12");  // tiny meshes: the launch + sync costs more than it saves
   ut_.build(mesh_->faces, nfaces, plans_[0].view, use_k12 ? &MeshJob::device_matcher : nullptr, this);
+  validate_attribute_indices(ut_.max_point);
   clk.lap("universal corner table");
   const size_t natt = plans_.size();
   seams_.resize(natt - 1);
@@ -494,8 +492,34 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
     }
   }
   for (const ByteSink& b : seam_bytes) head_.bytes(b.data);
+  write_attribute_section_headers();
+  for (size_t i = 0; i < natt; ++i) plans_[i].table = &table_refs_[i];
+}
 
-  // attribute section headers (encode/attribute/mod.rs:26-57)
+// header (encode/header/mod.rs:26-54)
+void MeshJob::write_stream_header() {
+  for (char ch : std::string("DRACO")) head_.u8((uint8_t)ch);
+  head_.u8(2); head_.u8(2);
+  head_.u8(1);    // EncodedGeometryType::TrianglarMesh
+  head_.u8(1);    // EncoderMethod::Edgebreaker
+  head_.u16(0);   // flags: no metadata
+}
+
+// Every attribute must cover the points the faces use, and every point -> value entry must name an existing value:
+// the predict kernels gather quant[map[point]] without further checks (the reference would panic on the slice index).
+void MeshJob::validate_attribute_indices(uint32_t max_face_point) const {
+  for (size_t i = 0; i < plans_.size(); ++i) {
+    const AttrView& v = plans_[i].view;
+    if (v.num_points <= max_face_point) throw Error(DXO_ERR_INVALID_ARGUMENT, "face references a point outside an attribute");
+    if (i == 0 || !v.map) continue;  // the position map is checked by the corner-table build
+    uint32_t mx = 0;
+    for (uint32_t p = 0; p < v.num_points; ++p) mx = std::max(mx, v.map[p]);
+    if (v.num_points && mx >= v.num_unique) throw Error(DXO_ERR_INVALID_ARGUMENT, "point_to_value entry out of range");
+  }
+}
+
+// attribute section headers (encode/attribute/mod.rs:26-57)
+void MeshJob::write_attribute_section_headers() {
   head_.u8((uint8_t)plans_.size());
   for (size_t i = 0; i < plans_.size(); ++i) {
     head_.u8((uint8_t)((uint8_t)i - 1u));
@@ -512,8 +536,6 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
     head_.u8((uint8_t)a.unique_id);
     head_.u8((uint8_t)p.port);
   }
-
-  for (size_t i = 0; i < natt; ++i) plans_[i].table = &table_refs_[i];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -944,7 +966,7 @@ void MeshJob::download(DeviceContext& ctx) {
 void MeshJob::assemble(std::vector<uint8_t>& out) {
   ByteSink w;
   size_t total = head_.size() + 64;
-  for (const AttrResult& r : results_) total += (size_t)r.stats.table_bytes + r.stats.payload_bytes + r.side_payload.size() + 64;
+  for (const AttrResult& r : results_) total += (size_t)r.stats.table_bytes + r.stats.payload_bytes + r.side_payload.size() + r.side_bytes_len + 64;
   w.data.reserve(total);
   w.bytes(head_.data);
   for (size_t i = 0; i < plans_.size(); ++i) {
@@ -963,10 +985,10 @@ void MeshJob::assemble(std::vector<uint8_t>& out) {
       if (p.transform == Transform::Wrapped) { w.i32(r.stats.wrap_min); w.i32(r.stats.wrap_max); }   // wrapped_difference.rs:95-96
       else if (p.transform == Transform::OctOrthogonal) { w.u32(255); w.u32(127); }                  // oct_orthogonal.rs:80-82
     };
-    auto side_stream = [&] {  // zero_prob byte, leb128 size, rABS bytes (coded by encode_side_stream)
+    auto side_stream = [&] {  // zero_prob byte, leb128 size, rABS bytes (coded by encode_side_stream, or on the device in the group path)
       w.u8(r.side_zero_prob);
-      w.varint(r.side_payload.size());
-      w.bytes(r.side_payload);
+      if (r.side_bytes) { w.varint(r.side_bytes_len); w.bytes(r.side_bytes, r.side_bytes_len); }
+      else { w.varint(r.side_payload.size()); w.bytes(r.side_payload); }
     };
     if (p.scheme == Scheme::Normal) {
       transform_info();

@@ -20,6 +20,13 @@
 namespace dxo {
 
 void cuda_check(cudaError_t e, const char* what);
+// process-wide pool of pinned host blocks (2 MB-aligned, huge-page advised, never freed)
+void* pinned_block_take(size_t bytes, size_t* capacity);
+void pinned_block_give(void* p, size_t capacity);
+// one mesh through the per-mesh path (capi.cpp)
+void encode_one_mesh(const dxo_mesh* mesh, const dxo_config& cfg, std::vector<uint8_t>& bytes, dxo_timing& tm, bool parallel_host);
+// the batch entry (batch.cpp): groups of meshes through segmented launches, sharded over GPUs
+void encode_batch_grouped(const dxo_mesh* meshes, size_t n, const dxo_config& cfg, dxo_bytes* outs, int* statuses, int first_gpu, int num_gpus);
 
 // Two persistent helper threads per DeviceContext (i.e. per calling thread): the side-stream coders of every step run
 // on them, so a step neither creates threads nor leaves new threads at the mercy of the scheduler.
@@ -119,9 +126,14 @@ struct AttrResult {
   uint32_t side_count = 0;
   uint8_t side_zero_prob = 0;
   std::vector<uint8_t> side_payload, side_scratch;
+  // group path: the side stream was coded on the device, its bytes live in the group's output block
+  const uint8_t* side_bytes = nullptr;
+  size_t side_bytes_len = 0;
 };
 
+class GroupRunner;
 class MeshJob {
+  friend class GroupRunner;  // batch.cpp: the same job driven through segmented launches over a group of meshes
  public:
   MeshJob(const dxo_mesh* mesh, const dxo_config& cfg);
   ~MeshJob();
@@ -203,6 +215,11 @@ class MeshJob {
   void capture_trace(DeviceContext& ctx);
  public:
   void capture_host_trace();  // host-side results only (no device needed)
+ private:
+  void write_stream_header();                // "DRACO", version, geometry type, method, flags
+  void write_attribute_section_headers();    // encode_attributes' header part
+  void validate_attribute_indices(uint32_t max_face_point) const;  // every attribute covers the faces' points, every map entry is a valid value
+ public:
   bool has_device_buffers() const { return uploaded_; }
 };
 

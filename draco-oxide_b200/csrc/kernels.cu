@@ -111,12 +111,11 @@ void init_stats(AttrStats* stats, cudaStream_t s) { init_stats_kernel<<<1, 32, 0
 // (min) / strictly positive (max), so unsigned atomicMax on the bit pattern orders
 // both correctly and never produces -0.0.
 template <int N>
-__global__ void __launch_bounds__(kThreads) minmax_kernel(const float* __restrict__ values, uint64_t num_values, AttrStats* stats) {
+__device__ __forceinline__ void minmax_body(const float* __restrict__ values, AttrStats* stats, uint64_t i0, uint64_t i1, uint64_t istep) {
   float mn[N], mx[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) { mn[k] = 0.0f; mx[k] = 0.0f; }
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_values; i += stride) {
+  for (uint64_t i = i0; i < i1; i += istep) {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       const float c = __ldcs(values + i * N + k);
@@ -139,6 +138,10 @@ __global__ void __launch_bounds__(kThreads) minmax_kernel(const float* __restric
     if (s_mx[threadIdx.x]) atomicMax(&stats->vmax_bits[threadIdx.x], s_mx[threadIdx.x]);
   }
 }
+template <int N>
+__global__ void __launch_bounds__(kThreads) minmax_kernel(const float* __restrict__ values, uint64_t num_values, AttrStats* stats) {
+  minmax_body<N>(values, stats, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, num_values, (uint64_t)gridDim.x * blockDim.x);
+}
 
 void launch_minmax(const float* values, uint64_t num_values, uint32_t ncomp, AttrStats* stats, cudaStream_t s) {
   const int g = grid_for(num_values, kThreads * 4);
@@ -154,8 +157,8 @@ void launch_minmax(const float* values, uint64_t num_values, uint32_t ncomp, Att
 // roundings (quantization_coordinate_wise.rs:70-91). One thread per value; the result is
 // stored with the padded stride of load_q (N = 3 -> int4).
 template <int N>
-__global__ void __launch_bounds__(kThreads) quantize_kernel(const float* __restrict__ values, uint64_t num_values, uint32_t bits,
-                                                            int32_t* __restrict__ out, AttrStats* stats) {
+__device__ __forceinline__ void quantize_body(const float* __restrict__ values, uint32_t bits, int32_t* __restrict__ out, AttrStats* stats,
+                                              bool writes_range, uint64_t i0, uint64_t i1, uint64_t istep) {
   float mn[N];
   float range = 0.0f;
 #pragma unroll
@@ -164,10 +167,9 @@ __global__ void __launch_bounds__(kThreads) quantize_kernel(const float* __restr
     const float d = __uint_as_float(stats->vmax_bits[k]) - mn[k];
     if (d > range) range = d;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) stats->range = range;
+  if (writes_range && threadIdx.x == 0) stats->range = range;
   const float maxq = (float)(unsigned long long)((1ull << bits) - 1ull);
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_values; i += stride) {
+  for (uint64_t i = i0; i < i1; i += istep) {
     int32_t q[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int k = 0; k < N; ++k) {
@@ -183,6 +185,11 @@ __global__ void __launch_bounds__(kThreads) quantize_kernel(const float* __restr
     else if (N == 2) reinterpret_cast<int2*>(out)[i] = make_int2(q[0], q[1]);
     else reinterpret_cast<int4*>(out)[i] = make_int4(q[0], q[1], q[2], q[3]);
   }
+}
+template <int N>
+__global__ void __launch_bounds__(kThreads) quantize_kernel(const float* __restrict__ values, uint64_t num_values, uint32_t bits,
+                                                            int32_t* __restrict__ out, AttrStats* stats) {
+  quantize_body<N>(values, bits, out, stats, blockIdx.x == 0, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, num_values, (uint64_t)gridDim.x * blockDim.x);
 }
 
 void launch_quantize(const float* values, uint64_t num_values, uint32_t ncomp, uint32_t bits, int32_t* out, AttrStats* stats, cudaStream_t s) {
@@ -230,10 +237,10 @@ __device__ __forceinline__ void oct_quantize_f32(float x, float y, float z, int3
 }
 
 // K3 — octahedral normal quantization, one thread per unique normal.
-__global__ void __launch_bounds__(kThreads) oct_quantize_kernel(const float* __restrict__ normals, uint64_t n, int32_t* __restrict__ out, AttrStats* stats) {
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+__device__ __forceinline__ void oct_quantize_body(const float* __restrict__ normals, int32_t* __restrict__ out, AttrStats* stats, uint64_t i0, uint64_t i1,
+                                                  uint64_t istep) {
   uint32_t err = 0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (uint64_t i = i0; i < i1; i += istep) {
     const float x = __ldcs(normals + 3 * i), y = __ldcs(normals + 3 * i + 1), z = __ldcs(normals + 3 * i + 2);
     int32_t qx = 0, qy = 0;
     if (x == 0.0f && y == 0.0f && z == 0.0f) err |= kErrZeroNormal;  // reference asserts (geom.rs:45)
@@ -241,6 +248,9 @@ __global__ void __launch_bounds__(kThreads) oct_quantize_kernel(const float* __r
     reinterpret_cast<int2*>(out)[i] = make_int2(qx, qy);
   }
   if (__any_sync(0xFFFFFFFFu, err != 0) && (threadIdx.x & 31) == 0) atomicOr(&stats->error_flags, kErrZeroNormal);
+}
+__global__ void __launch_bounds__(kThreads) oct_quantize_kernel(const float* __restrict__ normals, uint64_t n, int32_t* __restrict__ out, AttrStats* stats) {
+  oct_quantize_body(normals, out, stats, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, n, (uint64_t)gridDim.x * blockDim.x);
 }
 
 void launch_oct_quantize(const float* normals, uint64_t num_values, int32_t* out, AttrStats* stats, cudaStream_t s) {
@@ -252,11 +262,10 @@ void launch_oct_quantize(const float* normals, uint64_t num_values, int32_t* out
 // `vertices_up_till_now.contains(v)` (O(V) scan per element) into `rank[v] < i`
 // (SURVEY Appendix C.1). Also reduces WrappedDifference's min / max over all
 // components of the visited originals (wrapped_difference.rs:41-49).
-__global__ void __launch_bounds__(kThreads) seq_prepare_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q,
-                                                               uint32_t* __restrict__ rank, int want_minmax, AttrStats* stats) {
+__device__ __forceinline__ void seq_prepare_body(const uint32_t* __restrict__ seq, const TableDev& t, const QuantDev& q, uint32_t* __restrict__ rank,
+                                                 int want_minmax, AttrStats* stats, uint32_t i0, uint32_t i1, uint32_t istep) {
   int32_t mn = 0x7FFFFFFF, mx = (int32_t)0x80000000;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (uint32_t i = i0; i < i1; i += istep) {
     const uint32_t c = ld_stream(seq + i);
     rank[__ldg(t.corner_vertex + c)] = i;
     if (want_minmax) {
@@ -277,6 +286,10 @@ __global__ void __launch_bounds__(kThreads) seq_prepare_kernel(const uint32_t* _
     __syncthreads();
     if (threadIdx.x == 0) { atomicMin(&stats->wrap_min, s_mn); atomicMax(&stats->wrap_max, s_mx); }
   }
+}
+__global__ void __launch_bounds__(kThreads) seq_prepare_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q,
+                                                               uint32_t* __restrict__ rank, int want_minmax, AttrStats* stats) {
+  seq_prepare_body(seq, t, q, rank, want_minmax, stats, blockIdx.x * blockDim.x + threadIdx.x, n, gridDim.x * blockDim.x);
 }
 
 void launch_seq_prepare(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, uint32_t* rank, bool want_minmax, AttrStats* stats, cudaStream_t s) {
@@ -322,12 +335,12 @@ __device__ __forceinline__ void previous_value(const uint32_t* seq, uint32_t i, 
 // K4 — MeshParallelogramPrediction::predict (mesh_parallelogram_prediction.rs:186-237)
 // fused with WrappedDifference and zig-zag. One thread per sequence element.
 template <int N>
-__global__ void __launch_bounds__(kThreads) predict_parallelogram_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q,
-                                                                         const uint32_t* __restrict__ rank, uint32_t* __restrict__ symbols, AttrStats* stats) {
+__device__ __forceinline__ void predict_parallelogram_body(const uint32_t* __restrict__ seq, const TableDev& t, const QuantDev& q,
+                                                           const uint32_t* __restrict__ rank, uint32_t* __restrict__ symbols, AttrStats* stats,
+                                                           uint32_t i0, uint32_t i1, uint32_t istep) {
   const WrapParams w = wrap_params(stats);
   uint32_t nz = 0, mxs = 0, err = 0;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (uint32_t i = i0; i < i1; i += istep) {
     const uint32_t c = ld_stream(seq + i);
     int32_t pred[N];
     bool have = false;
@@ -360,6 +373,11 @@ __global__ void __launch_bounds__(kThreads) predict_parallelogram_kernel(const u
   }
   accumulate_symbol_stats(nz, mxs, err, stats);
 }
+template <int N>
+__global__ void __launch_bounds__(kThreads) predict_parallelogram_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q,
+                                                                         const uint32_t* __restrict__ rank, uint32_t* __restrict__ symbols, AttrStats* stats) {
+  predict_parallelogram_body<N>(seq, t, q, rank, symbols, stats, blockIdx.x * blockDim.x + threadIdx.x, n, gridDim.x * blockDim.x);
+}
 
 void launch_predict_parallelogram(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, const uint32_t* rank, uint32_t* symbols, AttrStats* stats, cudaStream_t s) {
   const int g = grid_for(n);
@@ -373,11 +391,10 @@ void launch_predict_parallelogram(const uint32_t* seq, uint32_t n, TableDev t, Q
 
 // K7 — DeltaPrediction (delta_prediction.rs:56-71) + Difference (difference.rs:26-34)
 template <int N>
-__global__ void __launch_bounds__(kThreads) predict_delta_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q,
-                                                                 uint32_t* __restrict__ symbols, AttrStats* stats) {
+__device__ __forceinline__ void predict_delta_body(const uint32_t* __restrict__ seq, const TableDev& t, const QuantDev& q, uint32_t* __restrict__ symbols,
+                                                   AttrStats* stats, uint32_t i0, uint32_t i1, uint32_t istep) {
   uint32_t nz = 0, mxs = 0, err = 0;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (uint32_t i = i0; i < i1; i += istep) {
     const uint32_t c = ld_stream(seq + i);
     int32_t pred[N];
     previous_value<N>(seq, i, t, q, pred);
@@ -392,6 +409,11 @@ __global__ void __launch_bounds__(kThreads) predict_delta_kernel(const uint32_t*
     }
   }
   accumulate_symbol_stats(nz, mxs, err, stats);
+}
+template <int N>
+__global__ void __launch_bounds__(kThreads) predict_delta_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q,
+                                                                 uint32_t* __restrict__ symbols, AttrStats* stats) {
+  predict_delta_body<N>(seq, t, q, symbols, stats, blockIdx.x * blockDim.x + threadIdx.x, n, gridDim.x * blockDim.x);
 }
 
 void launch_predict_delta(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, uint32_t* symbols, AttrStats* stats, cudaStream_t s) {
@@ -439,11 +461,11 @@ __device__ __forceinline__ void add_cross(const int32_t* pn, const int32_t* pp, 
 __device__ __forceinline__ int32_t isign(int32_t a) { return (a > 0) - (a < 0); }
 __device__ __forceinline__ int32_t iabs_wrap(int32_t a) { return a < 0 ? (int32_t)(0u - (uint32_t)a) : a; }
 
-__global__ void __launch_bounds__(kThreads, 8) predict_normal_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos,
-                                                                  uint32_t* __restrict__ symbols, uint8_t* __restrict__ flips, AttrStats* stats) {
+__device__ __forceinline__ void predict_normal_body(const uint32_t* __restrict__ seq, const TableDev& t, const QuantDev& q, const QuantDev& pos,
+                                                    uint32_t* __restrict__ symbols, uint8_t* __restrict__ flips, AttrStats* stats, uint32_t i0, uint32_t i1,
+                                                    uint32_t istep) {
   uint32_t nz = 0, mxs = 0, err = 0;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (uint32_t i = i0; i < i1; i += istep) {
     const uint32_t c = ld_stream(seq + i);
     int32_t pc[3];
     const uint32_t point_c = __ldg(t.corner_point + c);
@@ -546,6 +568,10 @@ __global__ void __launch_bounds__(kThreads, 8) predict_normal_kernel(const uint3
   }
   accumulate_symbol_stats(nz, mxs, err, stats);
 }
+__global__ void __launch_bounds__(kThreads, 8) predict_normal_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos,
+                                                                  uint32_t* __restrict__ symbols, uint8_t* __restrict__ flips, AttrStats* stats) {
+  predict_normal_body(seq, t, q, pos, symbols, flips, stats, blockIdx.x * blockDim.x + threadIdx.x, n, gridDim.x * blockDim.x);
+}
 
 void launch_predict_normal(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos, uint32_t* symbols, uint8_t* flips, AttrStats* stats, cudaStream_t s) {
   predict_normal_kernel<<<grid_for(n), kThreads, 0, s>>>(seq, n, t, q, pos, symbols, flips, stats);
@@ -609,14 +635,13 @@ __device__ __forceinline__ void texcoord_fallback(const uint32_t* seq, uint32_t 
   previous_value<2>(seq, i, t, q, pred);
 }
 
-__global__ void __launch_bounds__(kThreads, 4) predict_texcoord_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos,
-                                                                    uint32_t pos_num_points, const uint32_t* __restrict__ rank,
-                                                                    uint32_t* __restrict__ symbols, uint8_t* __restrict__ orient, AttrStats* stats) {
+__device__ __forceinline__ void predict_texcoord_body(const uint32_t* __restrict__ seq, const TableDev& t, const QuantDev& q, const QuantDev& pos,
+                                                      uint32_t pos_num_points, const uint32_t* __restrict__ rank, uint32_t* __restrict__ symbols,
+                                                      uint8_t* __restrict__ orient, AttrStats* stats, uint32_t i0, uint32_t i1, uint32_t istep) {
   const WrapParams w = wrap_params(stats);
   uint32_t nz = 0, mxs = 0, err = 0;
-  const uint32_t stride = gridDim.x * blockDim.x;
   const long long I64MAX = 0x7FFFFFFFFFFFFFFFll;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (uint32_t i = i0; i < i1; i += istep) {
     const uint32_t c = ld_stream(seq + i);
     const Tri pts = load_tri(t.corner_point4, c), vts = load_tri(t.corner_vertex4, c);
     const uint32_t next_pt = pts.next, prev_pt = pts.prev, curr_pt = pts.self;
@@ -692,6 +717,11 @@ __global__ void __launch_bounds__(kThreads, 4) predict_texcoord_kernel(const uin
   }
   accumulate_symbol_stats(nz, mxs, err, stats);
 }
+__global__ void __launch_bounds__(kThreads, 4) predict_texcoord_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos,
+                                                                    uint32_t pos_num_points, const uint32_t* __restrict__ rank,
+                                                                    uint32_t* __restrict__ symbols, uint8_t* __restrict__ orient, AttrStats* stats) {
+  predict_texcoord_body(seq, t, q, pos, pos_num_points, rank, symbols, orient, stats, blockIdx.x * blockDim.x + threadIdx.x, n, gridDim.x * blockDim.x);
+}
 
 void launch_predict_texcoord(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos, uint32_t pos_num_points, const uint32_t* rank,
                              uint32_t* symbols, uint8_t* orient, AttrStats* stats, cudaStream_t s) {
@@ -704,14 +734,13 @@ void launch_predict_texcoord(const uint32_t* seq, uint32_t n, TableDev t, QuantD
 // match_any so equal symbols inside a warp cost one atomic; global atomics otherwise.
 constexpr uint32_t kSmemBins = 8192;
 
-__global__ void __launch_bounds__(kThreads) histogram_smem_kernel(const uint32_t* __restrict__ symbols, uint64_t n, uint32_t* __restrict__ hist,
-                                                                  uint32_t capacity, AttrStats* stats) {
+__device__ __forceinline__ void histogram_smem_body(const uint32_t* __restrict__ symbols, uint32_t* __restrict__ hist, uint32_t capacity, AttrStats* stats,
+                                                    uint64_t i0, uint64_t i1, uint64_t istep) {
   __shared__ uint32_t bins[kSmemBins];
   const uint32_t nb = min(stats->max_symbol + 1u, capacity);
   for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) bins[b] = 0;
   __syncthreads();
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (uint64_t i = i0; i < i1; i += istep) {
     const uint32_t s = ld_stream(symbols + i);
     if (s < nb) atomicAdd(&bins[s], 1u);
   }
@@ -721,16 +750,23 @@ __global__ void __launch_bounds__(kThreads) histogram_smem_kernel(const uint32_t
     if (v) atomicAdd(hist + b, v);
   }
 }
+__global__ void __launch_bounds__(kThreads) histogram_smem_kernel(const uint32_t* __restrict__ symbols, uint64_t n, uint32_t* __restrict__ hist,
+                                                                  uint32_t capacity, AttrStats* stats) {
+  histogram_smem_body(symbols, hist, capacity, stats, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, n, (uint64_t)gridDim.x * blockDim.x);
+}
 
-__global__ void __launch_bounds__(kThreads) histogram_global_kernel(const uint32_t* __restrict__ symbols, uint64_t n, uint32_t* __restrict__ hist,
-                                                                    uint32_t capacity, AttrStats* stats) {
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+__device__ __forceinline__ void histogram_global_body(const uint32_t* __restrict__ symbols, uint32_t* __restrict__ hist, uint32_t capacity, AttrStats* stats,
+                                                      uint64_t i0, uint64_t i1, uint64_t istep) {
   bool over = false;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (uint64_t i = i0; i < i1; i += istep) {
     const uint32_t s = ld_stream(symbols + i);
     if (s < capacity) atomicAdd(hist + s, 1u); else over = true;
   }
   if (over) atomicOr(&stats->error_flags, kErrAlphabet);
+}
+__global__ void __launch_bounds__(kThreads) histogram_global_kernel(const uint32_t* __restrict__ symbols, uint64_t n, uint32_t* __restrict__ hist,
+                                                                    uint32_t capacity, AttrStats* stats) {
+  histogram_global_body(symbols, hist, capacity, stats, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, n, (uint64_t)gridDim.x * blockDim.x);
 }
 
 void launch_histogram(const uint32_t* symbols, uint64_t num_symbols, uint32_t* hist, uint32_t hist_capacity, AttrStats* stats, cudaStream_t s) {
@@ -801,9 +837,9 @@ struct BlockScan {  // exclusive scans over a block of kTableThreads threads
 
 __device__ __forceinline__ uint32_t freq_token_bytes(uint32_t f) { return 1u + (f >= (1u << 6)) + (f >= (1u << 14)); }
 
-__global__ void __launch_bounds__(kTableThreads) build_table_kernel(const uint32_t* __restrict__ hist, uint32_t capacity, unsigned long long total_symbols,
-                                                                    uint32_t* __restrict__ work, uint4* __restrict__ rans_table,
-                                                                    uint8_t* __restrict__ table_bytes, uint32_t table_bytes_capacity, AttrStats* stats) {
+__device__ __forceinline__ void build_table_body(const uint32_t* __restrict__ hist, uint32_t capacity, unsigned long long total_symbols,
+                                                 uint32_t* __restrict__ work, uint4* __restrict__ rans_table,
+                                                 uint8_t* __restrict__ table_bytes, uint32_t table_bytes_capacity, AttrStats* stats) {
   __shared__ uint32_t s_warp[33];
   __shared__ unsigned long long s_tmp64[32];
   __shared__ uint32_t s_scalar[4];
@@ -979,6 +1015,11 @@ __global__ void __launch_bounds__(kTableThreads) build_table_kernel(const uint32
     }
     off += nb;
   }
+}
+__global__ void __launch_bounds__(kTableThreads) build_table_kernel(const uint32_t* __restrict__ hist, uint32_t capacity, unsigned long long total_symbols,
+                                                                    uint32_t* __restrict__ work, uint4* __restrict__ rans_table,
+                                                                    uint8_t* __restrict__ table_bytes, uint32_t table_bytes_capacity, AttrStats* stats) {
+  build_table_body(hist, capacity, total_symbols, work, rans_table, table_bytes, table_bytes_capacity, stats);
 }
 
 void launch_build_table(const uint32_t* hist, uint32_t hist_capacity, uint64_t total_symbols, uint32_t* work, uint4* rans_table,
@@ -1250,16 +1291,19 @@ __device__ __forceinline__ uint32_t rans_guess_state(uint32_t lane, uint32_t l_b
 }
 
 // phase A — exploration (two chunks per CTA): no bytes, 32 candidate (entering state -> exit state) pairs per chunk
-__global__ void __launch_bounds__(128) rans_explore_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                           RansChunkState cs, uint32_t num_chunks, uint32_t chunk_steps, uint32_t warmup_steps, uint32_t sub,
-                                                           AttrStats* stats) {
+__device__ __forceinline__ void rans_explore_body(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                  const RansChunkState& cs, uint32_t num_chunks, uint32_t chunk_steps, uint32_t warmup_steps, uint32_t sub,
+                                                  AttrStats* stats, uint32_t blk) {
   __shared__ RansShared sh2[2];
   __shared__ int role_slot[2];
   __shared__ uint32_t sched_slot[4];
-  if (stats->error_flags) return;
-  if (2ull * blockIdx.x + (threadIdx.x >> 6) >= num_chunks) return;  // both warps of the pair leave together
+  __shared__ uint32_t s_abort;  // one read for the whole CTA: warps that saw different values would part ways before a named barrier
+  if (threadIdx.x == 0) s_abort = *(volatile uint32_t*)&stats->error_flags;
+  __syncthreads();
+  if (s_abort) return;
+  if (2ull * blk + (threadIdx.x >> 6) >= num_chunks) return;  // both warps of the pair leave together
   const RansRole role = rans_role(role_slot, sched_slot);
-  const unsigned long long j = 2ull * blockIdx.x + role.pair;
+  const unsigned long long j = 2ull * blk + role.pair;
   RansShared& sh = sh2[role.pair];
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
   const uint32_t lane = threadIdx.x & 31;
@@ -1278,17 +1322,26 @@ __global__ void __launch_bounds__(128) rans_explore_kernel(const uint32_t* __res
   }
   rans_role_release(role);
 }
+__global__ void __launch_bounds__(128) rans_explore_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                           RansChunkState cs, uint32_t num_chunks, uint32_t chunk_steps, uint32_t warmup_steps, uint32_t sub,
+                                                           AttrStats* stats) {
+  rans_explore_body(symbols, n, table, cs, num_chunks, chunk_steps, warmup_steps, sub, stats, blockIdx.x);
+}
 
 // phase B — the chain (one warp pair): walks the chunks in order carrying the TRUE state. A chunk whose candidates contain
 // it (one ballot) hands over the matching exit state; otherwise (rare: every trajectory of the exploration missed) the
 // chunk is run from the true state right here. The candidate rows go through shared memory in tiles of 32 chunks; the
 // next tile's global loads are in flight while the current tile is walked.
 constexpr int kChainTile = 32;
-__global__ void __launch_bounds__(64) rans_chain_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                        RansChunkState cs, uint32_t num_chunks, uint32_t chunk_steps, uint32_t nsub, AttrStats* stats) {
+__device__ __forceinline__ void rans_chain_body(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                const RansChunkState& cs, uint32_t num_chunks, uint32_t chunk_steps, uint32_t nsub, AttrStats* stats) {
   __shared__ RansShared sh;
   __shared__ uint32_t tile_s[2][kChainTile][32], tile_e[2][kChainTile][32];
-  if (stats->error_flags) return;
+  __shared__ uint32_t s_abort;  // one read for the whole CTA: warps that saw different values would part ways before a named barrier
+  if (threadIdx.x == 0) s_abort = *(volatile uint32_t*)&stats->error_flags;
+  __syncthreads();
+  if (s_abort) return;
+
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
   const uint32_t lane = threadIdx.x & 31, half = threadIdx.x >> 5;
   const bool is_consumer = threadIdx.x < 32;
@@ -1352,6 +1405,10 @@ __global__ void __launch_bounds__(64) rans_chain_kernel(const uint32_t* __restri
   }
   if (threadIdx.x == 0) stats->pad[0] = misses;  // chunks whose true state matched no candidate
 }
+__global__ void __launch_bounds__(64) rans_chain_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                        RansChunkState cs, uint32_t num_chunks, uint32_t chunk_steps, uint32_t nsub, AttrStats* stats) {
+  rans_chain_body(symbols, n, table, cs, num_chunks, chunk_steps, nsub, stats);
+}
 
 // tests only (DXO_RANS_FAULT): every fifth chunk gets a wrong entering state, which the fix-up has to repair
 __global__ void rans_fault_kernel(RansChunkState cs, uint32_t num_chunks, AttrStats* stats) {
@@ -1360,15 +1417,19 @@ __global__ void rans_fault_kernel(RansChunkState cs, uint32_t num_chunks, AttrSt
 }
 
 // phase C — every chunk is encoded once from its true entering state (two chunks per CTA)
-__global__ void __launch_bounds__(128) rans_encode_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                          uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t chunk_steps, AttrStats* stats) {
+__device__ __forceinline__ void rans_encode_body(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                 uint8_t* __restrict__ scratch, const RansChunkState& cs, uint32_t num_chunks, uint32_t chunk_steps,
+                                                 AttrStats* stats, uint32_t blk) {
   __shared__ RansShared sh2[2];
   __shared__ int role_slot[2];
   __shared__ uint32_t sched_slot[4];
-  if (stats->error_flags) return;
-  if (2ull * blockIdx.x + (threadIdx.x >> 6) >= num_chunks) return;
+  __shared__ uint32_t s_abort;  // one read for the whole CTA: warps that saw different values would part ways before a named barrier
+  if (threadIdx.x == 0) s_abort = *(volatile uint32_t*)&stats->error_flags;
+  __syncthreads();
+  if (s_abort) return;
+  if (2ull * blk + (threadIdx.x >> 6) >= num_chunks) return;
   const RansRole role = rans_role(role_slot, sched_slot);
-  const unsigned long long j = 2ull * blockIdx.x + role.pair;
+  const unsigned long long j = 2ull * blk + role.pair;
   RansShared& sh = sh2[role.pair];
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
   const uint32_t in = j == 0 ? (4u << P) : cs.chain_start[j];
@@ -1382,6 +1443,10 @@ __global__ void __launch_bounds__(128) rans_encode_kernel(const uint32_t* __rest
     if (sh.err) atomicOr(&stats->error_flags, sh.err);
   }
   rans_role_release(role);
+}
+__global__ void __launch_bounds__(128) rans_encode_kernel(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
+                                                          uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t chunk_steps, AttrStats* stats) {
+  rans_encode_body(symbols, n, table, scratch, cs, num_chunks, chunk_steps, stats, blockIdx.x);
 }
 
 // phase C, lane-parallel variant — one THREAD per piece (a chunk's sub-chunk; 32 pieces per warp) instead of one warp pair
@@ -1444,8 +1509,8 @@ __device__ __forceinline__ void rans_lane_group(RansLane& L, const uint32_t* min
 
 template <bool SMEM>
 __device__ __forceinline__ void rans_encode_lanes_body(const uint32_t* __restrict__ symbols, unsigned long long n, const uint4* __restrict__ table,
-                                                       uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t num_pieces,
-                                                       uint32_t Cs, uint32_t sub, uint32_t P, uint32_t K, AttrStats* stats) {
+                                                       uint8_t* __restrict__ scratch, const RansChunkState& cs, uint32_t num_chunks, uint32_t num_pieces,
+                                                       uint32_t Cs, uint32_t sub, uint32_t P, uint32_t K, AttrStats* stats, uint32_t blk) {
   extern __shared__ uint4 lane_smem[];
   const uint4* rows = table;
   if (SMEM) {
@@ -1461,7 +1526,7 @@ __device__ __forceinline__ void rans_encode_lanes_body(const uint32_t* __restric
   uint32_t* stage = reinterpret_cast<uint32_t*>(lane_smem + (SMEM ? K + 1 : 0)) + (threadIdx.x >> 5) * (32 * kLanePitch);
   const uint32_t lane = threadIdx.x & 31;
   // piece q = sub-chunk (q % sub) of exploration chunk (q / sub); Cs steps each
-  const unsigned long long q = (unsigned long long)blockIdx.x * kLaneThreads + threadIdx.x;
+  const unsigned long long q = (unsigned long long)blk * kLaneThreads + threadIdx.x;
   const unsigned long long q0 = q - lane;
   if (q0 >= num_pieces) return;
   const uint32_t two_p = 1u << P;
@@ -1525,8 +1590,8 @@ __global__ void __launch_bounds__(kLaneThreads) rans_encode_lanes_kernel(const u
                                                                          uint32_t sub, uint32_t smem_rows, AttrStats* stats) {
   if (stats->error_flags) return;
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
-  if (K < smem_rows) rans_encode_lanes_body<true>(symbols, n, table, scratch, cs, num_chunks, num_pieces, Cs, sub, P, K, stats);
-  else rans_encode_lanes_body<false>(symbols, n, table, scratch, cs, num_chunks, num_pieces, Cs, sub, P, K, stats);
+  if (K < smem_rows) rans_encode_lanes_body<true>(symbols, n, table, scratch, cs, num_chunks, num_pieces, Cs, sub, P, K, stats, blockIdx.x);
+  else rans_encode_lanes_body<false>(symbols, n, table, scratch, cs, num_chunks, num_pieces, Cs, sub, P, K, stats, blockIdx.x);
 }
 
 // phase D — verification, fix-up and payload offsets (one CTA). The stream is exact iff every piece was encoded from the exit
@@ -1535,12 +1600,16 @@ __global__ void __launch_bounds__(kLaneThreads) rans_encode_lanes_kernel(const u
 // never rests on the speculation. Then the exclusive prefix sum of the pieces' byte counts is left in cs.offset.
 constexpr int kFixupThreads = 1024, kFixupItems = 8;
 constexpr int kFixupPairBarrier = 2 * kRansStages + 2;  // named barrier of the repairing pair (rans_encode_range with bar_base 1 uses 1..7)
-__global__ void __launch_bounds__(kFixupThreads) rans_fixup_kernel(const uint32_t* __restrict__ symbols, unsigned long long n,
-                                                                   const uint4* __restrict__ table, uint8_t* __restrict__ scratch, RansChunkState cs,
-                                                                   uint32_t num_chunks, uint32_t chunk_steps, AttrStats* stats) {
+__device__ __forceinline__ void rans_fixup_body(const uint32_t* __restrict__ symbols, unsigned long long n,
+                                                const uint4* __restrict__ table, uint8_t* __restrict__ scratch, const RansChunkState& cs,
+                                                uint32_t num_chunks, uint32_t chunk_steps, AttrStats* stats) {
   __shared__ RansShared sh;
   __shared__ uint32_t s_in, s_bad, s_warp[kFixupThreads / 32];
-  if (stats->error_flags) return;
+  __shared__ uint32_t s_abort;  // one read for the whole CTA: warps that saw different values would part ways before a named barrier
+  if (threadIdx.x == 0) s_abort = *(volatile uint32_t*)&stats->error_flags;
+  __syncthreads();
+  if (s_abort) return;
+
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
   const uint32_t l_base = 4u << P;
   if (threadIdx.x == 0) s_bad = 0;
@@ -1612,14 +1681,19 @@ __global__ void __launch_bounds__(kFixupThreads) rans_fixup_kernel(const uint32_
     }
   }
 }
+__global__ void __launch_bounds__(kFixupThreads) rans_fixup_kernel(const uint32_t* __restrict__ symbols, unsigned long long n,
+                                                                   const uint4* __restrict__ table, uint8_t* __restrict__ scratch, RansChunkState cs,
+                                                                   uint32_t num_chunks, uint32_t chunk_steps, AttrStats* stats) {
+  rans_fixup_body(symbols, n, table, scratch, cs, num_chunks, chunk_steps, stats);
+}
 
 // gather: piece j's bytes go to payload[offset[j]]; the last piece's threads append the flush bytes. A CTA copies
 // `pieces_per_cta` pieces (a power of two <= 8), 256 / pieces_per_cta threads each.
-__global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t chunk_steps,
-                                                          uint32_t pieces_per_cta, uint8_t* __restrict__ out, AttrStats* stats) {
-  if (stats->error_flags) { if (blockIdx.x == 0 && threadIdx.x == 0) stats->payload_bytes = 0; return; }
+__device__ __forceinline__ void rans_gather_body(const uint8_t* __restrict__ scratch, const RansChunkState& cs, uint32_t num_chunks, uint32_t chunk_steps,
+                                                 uint32_t pieces_per_cta, uint8_t* __restrict__ out, AttrStats* stats, uint32_t blk) {
+  if (stats->error_flags) { if (blk == 0 && threadIdx.x == 0) stats->payload_bytes = 0; return; }
   const uint32_t tpp = 256u / pieces_per_cta;  // threads per piece
-  const uint32_t j = blockIdx.x * pieces_per_cta + threadIdx.x / tpp, t = threadIdx.x % tpp;
+  const uint32_t j = blk * pieces_per_cta + threadIdx.x / tpp, t = threadIdx.x % tpp;
   if (j >= num_chunks) return;
   const uint32_t off = num_chunks > 1 ? cs.offset[j] : 0u, nb = cs.nbytes[j];
   const uint8_t* src = scratch + (unsigned long long)j * rans_chunk_capacity(chunk_steps);
@@ -1636,6 +1710,10 @@ __global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restr
     stats->payload_bytes = pos;
     if (err) atomicOr(&stats->error_flags, err);
   }
+}
+__global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restrict__ scratch, RansChunkState cs, uint32_t num_chunks, uint32_t chunk_steps,
+                                                          uint32_t pieces_per_cta, uint8_t* __restrict__ out, AttrStats* stats) {
+  rans_gather_body(scratch, cs, num_chunks, chunk_steps, pieces_per_cta, out, stats, blockIdx.x);
 }
 
 // Chunk size for a stream of n symbols. The exploration is fastest with at most one consumer warp per scheduler, i.e. up to
@@ -1765,7 +1843,7 @@ void launch_compact_orientations(const uint8_t* flags, uint32_t n, uint8_t* comp
 // direction and different tips pairs them. Anything else (3+ half edges, equal
 // direction, equal tips, degenerate faces) raises not_exact: those results depend on
 // corner order and the caller must use the sequential matcher.
-__global__ void __launch_bounds__(kThreads) halfedge_keys_kernel(const uint32_t* __restrict__ cv, unsigned long long num_corners,
+__global__ void __launch_bounds__(kThreads) halfedge_keys_kernel(const uint32_t* __restrict__ cv, unsigned long long num_corners, uint32_t vertex_bits,
                                                                  unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* not_exact) {
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < num_corners; c += stride) {
@@ -1773,7 +1851,7 @@ __global__ void __launch_bounds__(kThreads) halfedge_keys_kernel(const uint32_t*
     const uint32_t tip = cv[cc], src = cv[cnext(cc)], snk = cv[cprev(cc)];
     if (tip == src || tip == snk || src == snk) *not_exact = 1;  // degenerate face
     const uint32_t a = min(src, snk), b = max(src, snk);
-    keys[c] = ((unsigned long long)a << 32) | b;
+    keys[c] = ((unsigned long long)a << vertex_bits) | b;  // only 2 * vertex_bits key bits are sorted
     vals[c] = cc;
   }
 }
@@ -1806,8 +1884,11 @@ size_t corner_table_scratch_bytes(uint64_t num_corners) {
   return 2 * a + 2 * b + cub_bytes + 256;
 }
 
-void launch_corner_table_opposites(const uint32_t* corner_vertex, uint64_t num_corners, uint32_t* opposite, uint32_t* not_exact_flag,
+void launch_corner_table_opposites(const uint32_t* corner_vertex, uint64_t num_corners, uint32_t num_vertices, uint32_t* opposite, uint32_t* not_exact_flag,
                                    void* scratch, size_t scratch_bytes, cudaStream_t s) {
+  // vertex ids below num_vertices (0 = unknown: all 32 bits): the radix sort runs over 2 * vertex_bits key bits only
+  uint32_t vertex_bits = 32;
+  if (num_vertices) { vertex_bits = 1; while (vertex_bits < 32 && ((uint64_t)(num_vertices - 1) >> vertex_bits) != 0) ++vertex_bits; }
   const size_t a = ((num_corners * 8 + 255) / 256) * 256, b = ((num_corners * 4 + 255) / 256) * 256;
   uint8_t* p = (uint8_t*)scratch;
   unsigned long long* keys_in = (unsigned long long*)p; p += a;
@@ -1816,8 +1897,8 @@ void launch_corner_table_opposites(const uint32_t* corner_vertex, uint64_t num_c
   uint32_t* vals_out = (uint32_t*)p; p += b;
   size_t cub_bytes = scratch_bytes - (2 * a + 2 * b);
   const int g = grid_for(num_corners);
-  halfedge_keys_kernel<<<g, kThreads, 0, s>>>(corner_vertex, num_corners, keys_in, vals_in, not_exact_flag);
-  cub::DeviceRadixSort::SortPairs(p, cub_bytes, keys_in, keys_out, vals_in, vals_out, (int)num_corners, 0, 64, s);
+  halfedge_keys_kernel<<<g, kThreads, 0, s>>>(corner_vertex, num_corners, vertex_bits, keys_in, vals_in, not_exact_flag);
+  cub::DeviceRadixSort::SortPairs(p, cub_bytes, keys_in, keys_out, vals_in, vals_out, (int)num_corners, 0, (int)(2 * vertex_bits), s);
   halfedge_pair_kernel<<<g, kThreads, 0, s>>>(corner_vertex, num_corners, keys_out, vals_out, opposite, not_exact_flag);
 }
 
@@ -2008,6 +2089,8 @@ void launch_seam_table(const uint32_t* corner_point, const uint32_t* map, uint32
   cub::DeviceScan::ExclusiveSum(p, cub_bytes, count, base, (int)num_vertices, s);
   seam_vertices_kernel<true><<<g, kThreads, 0, s>>>(left_most_u, opposite, seam, vertex_on_seam, num_vertices, (uint32_t)num_corners, base, corner_vertex, left_most_a, total, flags);
 }
+
+#include "segmented.inl"
 
 }  // namespace gpu
 }  // namespace dxo

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <vector>
 
 namespace dxo {
 namespace gpu {
@@ -97,7 +98,8 @@ void launch_compact_orientations(const uint8_t* flags, uint32_t n, uint8_t* comp
 // ---- K12: half-edge matching by radix sort (corner_table/mod.rs:252-340, fast path) ----
 // keys/vals/tmp are caller-provided scratch (see corner_table_scratch_bytes).
 size_t corner_table_scratch_bytes(uint64_t num_corners);
-void launch_corner_table_opposites(const uint32_t* corner_vertex, uint64_t num_corners, uint32_t* opposite, uint32_t* not_exact_flag,
+// num_vertices (0 = unknown) bounds the vertex ids, so that only 2 * ceil(log2 num_vertices) key bits are sorted
+void launch_corner_table_opposites(const uint32_t* corner_vertex, uint64_t num_corners, uint32_t num_vertices, uint32_t* opposite, uint32_t* not_exact_flag,
                                    void* scratch, size_t scratch_bytes, cudaStream_t s);
 
 // ---- K13: left-most corners (corner_table/mod.rs:342-416, single-fan vertices) ----
@@ -122,6 +124,106 @@ void launch_seam_table(const uint32_t* corner_point, const uint32_t* map, uint32
                        uint8_t* seam, uint32_t* corner_vertex, uint32_t* left_most_a, uint32_t* total, uint32_t* flags, cudaStream_t s);
 
 void init_stats(AttrStats* stats, cudaStream_t s);
+
+// =======================================================================================
+// Segmented launches over a GROUP of meshes (the batch entry, SURVEY §7 step 8 / north_star "across every attribute
+// stream of a mesh batch"): one launch set per group instead of one per mesh. Every kernel takes an array of segment
+// descriptors in device memory plus a tile list: CTA b works on elements [tile.first, tile.first + kSegTile) of segment
+// tile.seg. All indices stay local to their mesh; descriptors carry the base pointers.
+struct Tile { uint32_t seg, first; };
+constexpr uint32_t kSegTile = 1024;  // elements per CTA
+
+// per-mesh flags raised by the connectivity kernels (any of them sends the mesh to the sequential host passes)
+enum : uint32_t {
+  kMeshNotExact = 1u,       // K12: non-manifold edge, inconsistent orientation, degenerate face, equal tips
+  kMeshUnusedVertex = 2u,   // K13: a vertex id below num_vertices is used by no corner
+  kMeshSplitVertex = 4u,    // K13: a vertex with a second fan
+  kMeshBadIndex = 8u,       // a face references a point / value outside the position attribute
+};
+struct MeshSeg {  // K12 + K13 of one mesh (CornerTable, core/corner_table/mod.rs:84-460)
+  const uint32_t* faces;     // corner -> point, 3 per face
+  const uint32_t* pos_map;   // point -> position value (nullptr = identity)
+  uint32_t num_corners, num_points, num_vertices;
+  uint32_t corner_base;      // first slot of this mesh in the group-wide sort arrays
+  uint32_t* cv;              // out: corner -> vertex
+  uint32_t* opposite;        // out (pre-set to 0xFF by the caller)
+  uint32_t* left_most;       // out [num_vertices]
+  uint8_t* interior;         // out [num_vertices]: swing_left(left_most[v]) exists
+  uint32_t* first_corner;    // scratch [num_vertices], pre-set to 0xFF
+  uint32_t* valence;         // scratch [num_vertices], pre-set to 0
+  uint32_t* flags;           // out: one word, pre-set to 0
+};
+size_t seg_corner_tables_scratch_bytes(uint64_t total_corners);
+// vertex_bits: bits that hold the largest num_vertices of the group; keys are mesh << 2 vertex_bits | min << vertex_bits | max
+void launch_seg_corner_tables(const MeshSeg* segs, uint32_t num_meshes, const Tile* corner_tiles, uint32_t num_corner_tiles, const Tile* vertex_tiles,
+                              uint32_t num_vertex_tiles, uint64_t total_corners, uint32_t vertex_bits, void* scratch, size_t scratch_bytes, cudaStream_t s);
+
+struct SeamSeg {  // K14 of one non-position attribute (AttributeCornerTable, attribute_corner_table.rs:16-137)
+  const uint32_t* faces; const uint32_t* map; uint32_t num_points;
+  const uint32_t* cv_u; const uint32_t* opposite; const uint32_t* left_most_u;
+  uint32_t num_corners, num_vertices_u;
+  uint32_t count_base;       // first slot of this segment in the group-wide count / base arrays (num_vertices_u slots)
+  uint32_t capacity;         // slots of left_most_a / interior_a
+  uint8_t* seam;             // out [num_corners]
+  uint8_t* vertex_on_seam;   // scratch [num_vertices_u], pre-set to 0
+  uint32_t* cv_a;            // out [num_corners]
+  uint32_t* left_most_a;     // out [capacity]
+  uint8_t* interior_a;       // out [capacity]
+  uint32_t* scalars;         // out: [0] attribute vertices, [1] flags (kSeam* bits of launch_seam_table + 8 = capacity exceeded), pre-set to 0
+  const uint32_t* mesh_flags;  // the mesh's MeshSeg::flags: a flagged mesh is skipped
+};
+size_t seg_seam_tables_scratch_bytes(uint64_t total_count_slots);
+void launch_seg_seam_tables(const SeamSeg* segs, uint32_t num_segs, const Tile* corner_tiles, uint32_t num_corner_tiles, const Tile* vertex_tiles,
+                            uint32_t num_vertex_tiles, const Tile* attr_vertex_tiles, uint32_t num_attr_vertex_tiles, uint32_t* counts, uint32_t* bases,
+                            uint64_t total_count_slots, void* scratch, size_t scratch_bytes, cudaStream_t s);
+
+// One attribute stream of one mesh for K1-K10.
+struct SideStats { uint32_t count, zero_prob, nbytes, pad; };
+struct AttrSeg {
+  TableDev t; QuantDev q; QuantDev pos; uint32_t pos_num_points;
+  const float* values; uint32_t num_unique, ncomp_in, bits;
+  uint32_t scheme, wrapped;          // Scheme enum value; transform is WrappedDifference
+  const uint32_t* seq; uint32_t n;   // sequence (corners), elements
+  uint32_t num_symbols;              // n * q.num_components
+  uint32_t* rank; uint32_t* symbols; uint8_t* side_flags /* K5 flips / K6 orientation flags, [n] */;
+  uint32_t* hist; uint32_t hist_capacity; uint32_t* work; uint4* rans_table; uint8_t* table_bytes; uint32_t table_capacity;
+  AttrStats* stats;
+  // fan links of K5 (normals): out [num_corners]
+  uint2* fan_link_out; const uint8_t* seam_for_links;
+  // binary side stream (device rABS): out
+  uint8_t* side_payload; uint32_t side_capacity; SideStats* side_stats;
+};
+void launch_seg_init_stats(const AttrSeg* segs, uint32_t num_segs, cudaStream_t s);
+struct Pad3Seg { const uint32_t* in; uint4* out; uint32_t n; };  // 3-wide rows -> 16-byte tuples (faces, corner -> vertex tables, 3-component ToBits values)
+void launch_seg_pad3(const Pad3Seg* segs, const Tile* tiles, uint32_t num_tiles, cudaStream_t s);
+void launch_seg_fan_links(const AttrSeg* segs, const Tile* tiles, uint32_t num_tiles, cudaStream_t s);       // tiles over corners of normal streams
+void launch_seg_minmax(const AttrSeg* segs, const Tile* tiles, uint32_t num_tiles, uint32_t ncomp, cudaStream_t s);      // tiles over unique values
+void launch_seg_quantize(const AttrSeg* segs, const Tile* tiles, uint32_t num_tiles, uint32_t ncomp, cudaStream_t s);
+void launch_seg_oct_quantize(const AttrSeg* segs, const Tile* tiles, uint32_t num_tiles, cudaStream_t s);
+void launch_seg_seq_prepare(const AttrSeg* segs, const Tile* tiles, uint32_t num_tiles, cudaStream_t s);                 // tiles over sequence elements
+void launch_seg_predict(const AttrSeg* segs, const Tile* tiles, uint32_t num_tiles, uint32_t scheme, uint32_t ncomp, cudaStream_t s);
+void launch_seg_histogram(const AttrSeg* segs, const Tile* tiles, uint32_t num_tiles, bool smem, cudaStream_t s);        // tiles over symbols
+void launch_seg_build_tables(const AttrSeg* segs, uint32_t num_segs, cudaStream_t s);
+void launch_seg_side_streams(const AttrSeg* segs, const uint32_t* seg_ids, uint32_t num_side_streams, cudaStream_t s);   // one warp per stream
+
+// K10 over every stream of the group
+struct RansJob {
+  const uint32_t* symbols; unsigned long long n; const uint4* table; uint8_t* scratch; uint8_t* payload; AttrStats* stats;
+  uint32_t *start, *exit, *nbytes, *chain_start, *cand_start, *cand_exit, *cand_mid, *offset;
+  uint32_t num_chunks, chunk_steps, warmup_steps, sub, num_pieces, piece_steps, pieces_per_cta, lanes;
+};
+RansJob rans_make_job(const uint32_t* symbols, uint64_t num_symbols, const uint4* rans_table, void* scratch, uint8_t* payload, AttrStats* stats);
+struct RansTiles {  // built by the host from the jobs (rans_plan_tiles), uploaded with them
+  std::vector<Tile> explore, chain, lanes, pairs, fixup, gather;
+};
+void rans_plan_tiles(const RansJob* jobs, uint32_t num_jobs, RansTiles& out);
+struct RansTilesDev { const Tile *explore, *chain, *lanes, *pairs, *fixup, *gather; uint32_t n_explore, n_chain, n_lanes, n_pairs, n_fixup, n_gather; };
+void launch_seg_rans(const RansJob* jobs, const RansTilesDev& tiles, uint32_t max_table_capacity, cudaStream_t s);
+
+// Packs every stream's table bytes, rANS payload and side-stream bytes into one buffer (each part 4-byte aligned, in
+// stream order) and leaves the layout in `index`: per stream {offset, table_bytes, payload_bytes, side_bytes}; index[num_segs].x = total.
+void launch_seg_pack(const AttrSeg* segs, const RansJob* jobs, uint32_t num_segs, uint4* index, uint8_t* out, uint64_t out_capacity, const Tile* tiles,
+                     uint32_t num_tiles, cudaStream_t s);
 
 }  // namespace gpu
 }  // namespace dxo

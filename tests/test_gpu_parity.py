@@ -179,6 +179,31 @@ def test_batch_entry_matches_per_mesh_streams(orc):
         assert g == orc.encode(m)
 
 
+def test_batch_entry_mixed_zoo_with_fallbacks_and_errors(orc):
+    """One batch holding every zoo mesh (non-manifold edges and vertices, holes, several components, custom and colour
+    attributes, a single triangle), a mesh with a zero normal and one whose face points outside its attributes: the
+    meshes the group kernels flag take the per-mesh path, failures are reported per mesh, everything else is unaffected."""
+    zoo = meshes.zoo()
+    names = sorted(zoo.keys())
+    ms = [meshes.drop_unused_points(zoo[k]) for k in names]
+    g = synth.grid_mesh(12, 12, 3)
+    n = g.attributes[1]
+    vals = n.values.copy()
+    vals[5] = 0
+    ms.append(dxo.Mesh(g.faces, [g.attributes[0], dxo.Attribute(vals, n.att_type, n.domain, n.parents, n.point_to_value, n.unique_id), g.attributes[2]]))
+    bad_faces = g.faces.copy()
+    bad_faces[3, 1] = g.num_points() + 7
+    ms.append(dxo.Mesh(bad_faces, g.attributes))
+    ms.append(synth.torus_mesh(30, 20, 8))
+    got, sts = dxo.encode_batch(ms, first_gpu=0, num_gpus=1, return_statuses=True)
+    for k, name in enumerate(names):
+        assert sts[k] == 0, name
+        assert got[k] == orc.encode(ms[k]), name
+    assert sts[len(names)] == -9 and got[len(names)] == b""       # DXO_ERR_ZERO_NORMAL
+    assert sts[len(names) + 1] == -1 and got[len(names) + 1] == b""  # DXO_ERR_INVALID_ARGUMENT
+    assert sts[-1] == 0 and got[-1] == orc.encode(ms[-1])
+
+
 def test_batch_entry_over_all_visible_gpus(orc):
     """The batch entry shards independent meshes over every visible GPU (one on the default test box, N under
     `gpurun --gpus N`); results come back in input order and equal the per-mesh streams, large meshes included."""
