@@ -271,7 +271,14 @@ void GroupRunner::stage2_host_connectivity(GroupMesh& m) {
     const uint32_t* sc = hp<uint32_t>(m.atts[i].scalars);
     if ((sc[1] & (1u | 2u | 8u)) || sc[0] > m.atts[i].capacity || sc[0] < m.V) flagged = true;
   }
-  if (flagged) { m.fallback = true; encode_fallback(m); return; }
+  if (flagged) {
+    if (getenv("DXO_DEBUG")) {
+      fprintf(stderr, "[dxo] batch mesh %zu falls back to the per-mesh path: mesh flags %u", m.index, flags);
+      for (size_t i = 1; i < natt; ++i) fprintf(stderr, ", att %zu: vertices %u (capacity %u, V %u) flags %u", i, hp<uint32_t>(m.atts[i].scalars)[0], m.atts[i].capacity, m.V, hp<uint32_t>(m.atts[i].scalars)[1]);
+      fprintf(stderr, "\n");
+    }
+    m.fallback = true; encode_fallback(m); return;
+  }
   guarded(m, [&] {
     UniversalTable& ut = job.ut_;
     ut.num_faces = m.F; ut.num_corners = m.C; ut.num_vertices = m.V;
@@ -341,7 +348,6 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
   cuda_check(cudaSetDevice(slot_.device), "cudaSetDevice");
   const size_t G = meshes.size();
   if (G == 0) return;
-  cudaStream_t s = slot_.stream;
 
   // ---------------------------------------------------------------- sizes
   uint64_t sumC = 0, sumV = 0, sumF = 0, sum_values = 0, sum_maps = 0, sum_cap = 0, sum_seamC = 0, sum_seamV = 0, sum_symbols = 0, sum_hist = 0;
@@ -400,6 +406,7 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
       + (size_t)sum_symbols * 3 + num_streams * 16 + rans_scratch
       + (num_streams * 12 + G * 3 + 16) * per_array;
   slot_.ensure(pair_bytes, std::max(only_stage1, only_stage3));
+  cudaStream_t s = slot_.stream;  // exists from here on (created by the slot's first ensure())
   pair_ = Slab{slot_.h_pair, slot_.pair_cap, 0};
   only_ = Slab{slot_.d_only, slot_.only_cap, 0};
 
@@ -508,7 +515,8 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
     cuda_check(cudaMemsetAsync(slot_.d_only + fc_begin, 0xFF, fc_end - fc_begin, s), "cudaMemsetAsync");
     cuda_check(cudaMemsetAsync(slot_.d_only + zero_begin, 0, zero_end - zero_begin, s), "cudaMemsetAsync");
     gpu::launch_seg_corner_tables(dp<gpu::MeshSeg>(o_mesh_segs), (uint32_t)live.size(), dp<gpu::Tile>(o_t_corner), (uint32_t)t_corner.size(),
-                                  dp<gpu::Tile>(o_t_vertex), (uint32_t)t_vertex.size(), sumC, vertex_bits, dn<uint8_t>(sort_off), sort_bytes, s);
+                                  dp<gpu::Tile>(o_t_vertex), (uint32_t)t_vertex.size(), corner_base /* corners of the live meshes */, vertex_bits,
+                                  dn<uint8_t>(sort_off), sort_bytes, s);
     gpu::launch_seg_seam_tables(dp<gpu::SeamSeg>(o_seam_segs), (uint32_t)seam_segs.size(), dp<gpu::Tile>(o_t_sc), (uint32_t)t_seam_corner.size(),
                                 dp<gpu::Tile>(o_t_sv), (uint32_t)t_seam_vertex.size(), dp<gpu::Tile>(o_t_sa), (uint32_t)t_seam_attr.size(),
                                 dn<uint32_t>(counts_off), dn<uint32_t>(bases_off), sum_seamV, dn<uint8_t>(scan_off), scan_bytes, s);
@@ -694,6 +702,10 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
   const size_t in3_end = pair_.used;
   const size_t o_packed = pair_.take(packed_capacity);
   lap("stage 3 (descriptors)");
+  if (getenv("DXO_DEBUG"))
+    fprintf(stderr, "[dxo] group: %zu meshes, %zu live, %zu active, %zu streams; tiles pad %zu explore %zu chain %zu lanes %zu pairs %zu fixup %zu gather %zu; packed capacity %llu\n", G,
+            live.size(), act.size(), n_streams, t_pad.size(), rt.explore.size(), rt.chain.size(), rt.lanes.size(), rt.pairs.size(), rt.fixup.size(), rt.gather.size(),
+            (unsigned long long)packed_capacity);
 
   const gpu::AttrSeg* d_segs = dp<gpu::AttrSeg>(o_segs);
   h2d(in3_begin, out3_begin);
@@ -750,7 +762,10 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
           throw Error(st, "device reported an encoding error");
         }
         const uint4 ix = index[k];
-        if (ix.y == 0xFFFFFFFFu || ix.y != r.stats.table_bytes || ix.z != r.stats.payload_bytes) throw Error(DXO_ERR_INTERNAL, "packed output index is inconsistent");
+        if (ix.y == 0xFFFFFFFFu || ix.y != r.stats.table_bytes || ix.z != r.stats.payload_bytes)
+          throw Error(DXO_ERR_INTERNAL, "packed output index is inconsistent: stream " + std::to_string(k) + " of " + std::to_string(n_streams) + " index {" + std::to_string(ix.x) + "," +
+                                            std::to_string(ix.y) + "," + std::to_string(ix.z) + "," + std::to_string(ix.w) + "} stats table " + std::to_string(r.stats.table_bytes) +
+                                            " payload " + std::to_string(r.stats.payload_bytes) + " symbols " + std::to_string(job.sequence_of(i).size() * job.plans_[i].ncomp_q));
         const uint8_t* base = packed + ix.x;
         r.table_bytes = base;
         r.payload = base + align_up(ix.y, 4);
@@ -844,6 +859,7 @@ void encode_batch_grouped(const dxo_mesh* meshes, size_t n, const dxo_config& cf
     // a mesh that is still marked alive was never finished (its group died before stage 4)
     if (all[i].alive && all[i].status == DXO_OK && outs[i].data == nullptr) all[i].status = DXO_ERR_INTERNAL;
     if (statuses) statuses[i] = all[i].status;
+    if (all[i].status != DXO_OK && getenv("DXO_DEBUG")) fprintf(stderr, "[dxo] batch mesh %zu: status %d (%s)\n", i, all[i].status, all[i].error.c_str());
   }
 }
 

@@ -14,6 +14,8 @@
 #include "kernels.cuh"
 
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 
 namespace dxo {
 namespace gpu {
@@ -1588,7 +1590,10 @@ __global__ void __launch_bounds__(kLaneThreads) rans_encode_lanes_kernel(const u
                                                                          const uint4* __restrict__ table, uint8_t* __restrict__ scratch,
                                                                          RansChunkState cs, uint32_t num_chunks, uint32_t num_pieces, uint32_t Cs,
                                                                          uint32_t sub, uint32_t smem_rows, AttrStats* stats) {
-  if (stats->error_flags) return;
+  __shared__ uint32_t s_abort;  // one read for the whole CTA (the body synchronises the CTA; other CTAs may raise the flag meanwhile)
+  if (threadIdx.x == 0) s_abort = *(volatile uint32_t*)&stats->error_flags;
+  __syncthreads();
+  if (s_abort) return;
   const uint32_t P = stats->precision, K = stats->num_table_symbols;
   if (K < smem_rows) rans_encode_lanes_body<true>(symbols, n, table, scratch, cs, num_chunks, num_pieces, Cs, sub, P, K, stats, blockIdx.x);
   else rans_encode_lanes_body<false>(symbols, n, table, scratch, cs, num_chunks, num_pieces, Cs, sub, P, K, stats, blockIdx.x);
@@ -1716,6 +1721,19 @@ __global__ void __launch_bounds__(256) rans_gather_kernel(const uint8_t* __restr
   rans_gather_body(scratch, cs, num_chunks, chunk_steps, pieces_per_cta, out, stats, blockIdx.x);
 }
 
+// The lane-parallel encode kernels use more than 48 KB of dynamic shared memory: opted in once per (kernel, device).
+static void allow_lane_smem(const void* kernel) {
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& d : done) if (d.first == kernel && d.second == dev) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)((size_t)(kLaneSmemRows + 1) * 16 + (size_t)(kLaneThreads / 32) * 32 * kLanePitch * 4));
+  done.push_back({kernel, dev});
+}
+
 // Chunk size for a stream of n symbols. The exploration is fastest with at most one consumer warp per scheduler, i.e. up to
 // 4 pairs per SM, so longer streams get longer chunks (up to 16384 steps; beyond that the SMs are full either way and
 // the chain kernel would gain nothing). DXO_RANS_CHUNK pins the size.
@@ -1774,12 +1792,7 @@ void launch_rans_encode(const uint32_t* symbols, uint64_t num_symbols, const uin
     // shared memory is reserved for what the alphabet bound allows; the kernel reads rows through L1 when K does not fit
     const uint32_t smem_rows = std::min(table_capacity + 1u, kLaneSmemRows + 1u);
     const size_t sm = (size_t)smem_rows * 16 + (size_t)(kLaneThreads / 32) * 32 * kLanePitch * 4;
-    static const bool attr_done = [] {
-      cudaFuncSetAttribute(rans_encode_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)((size_t)(kLaneSmemRows + 1) * 16 + (size_t)(kLaneThreads / 32) * 32 * kLanePitch * 4));
-      return true;
-    }();
-    (void)attr_done;
+    allow_lane_smem((const void*)rans_encode_lanes_kernel);
     rans_encode_lanes_kernel<<<(Q + kLaneThreads - 1) / kLaneThreads, kLaneThreads, sm, s>>>(symbols, num_symbols, rans_table, bytes, cs, J, Q, piece,
                                                                                                plan.sub, smem_rows, stats);
   } else {

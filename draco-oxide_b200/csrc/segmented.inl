@@ -550,7 +550,10 @@ __global__ void __launch_bounds__(128) seg_rans_encode_kernel(const RansJob* __r
 __global__ void __launch_bounds__(kLaneThreads) seg_rans_lanes_kernel(const RansJob* __restrict__ jobs, const Tile* __restrict__ tiles, uint32_t smem_rows) {
   const Tile tl = load_tile(tiles);
   const RansJob& j = jobs[tl.seg];
-  if (j.stats->error_flags) return;
+  __shared__ uint32_t s_abort;
+  if (threadIdx.x == 0) s_abort = *(volatile uint32_t*)&j.stats->error_flags;
+  __syncthreads();
+  if (s_abort) return;
   const uint32_t P = j.stats->precision, K = j.stats->num_table_symbols;
   if (K < smem_rows) rans_encode_lanes_body<true>(j.symbols, j.n, j.table, j.scratch, chunk_state_of(j), j.num_chunks, j.num_pieces, j.piece_steps, j.sub, P, K, j.stats, tl.first);
   else rans_encode_lanes_body<false>(j.symbols, j.n, j.table, j.scratch, chunk_state_of(j), j.num_chunks, j.num_pieces, j.piece_steps, j.sub, P, K, j.stats, tl.first);
@@ -608,12 +611,7 @@ void launch_seg_rans(const RansJob* jobs, const RansTilesDev& t, uint32_t max_ta
   if (t.n_lanes) {
     const uint32_t smem_rows = std::min(max_table_capacity + 1u, kLaneSmemRows + 1u);
     const size_t sm = (size_t)smem_rows * 16 + (size_t)(kLaneThreads / 32) * 32 * kLanePitch * 4;
-    static const bool attr_done = [] {
-      cudaFuncSetAttribute(seg_rans_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)((size_t)(kLaneSmemRows + 1) * 16 + (size_t)(kLaneThreads / 32) * 32 * kLanePitch * 4));
-      return true;
-    }();
-    (void)attr_done;
+    allow_lane_smem((const void*)seg_rans_lanes_kernel);
     seg_rans_lanes_kernel<<<t.n_lanes, kLaneThreads, sm, s>>>(jobs, t.lanes, smem_rows);
   }
   if (t.n_pairs) seg_rans_encode_kernel<<<t.n_pairs, 128, 0, s>>>(jobs, t.pairs);
