@@ -143,6 +143,57 @@ struct Slot {
   }
 };
 
+// Slots outlive the call that created them: a slot's slabs are a gigabyte of device memory and hundreds of megabytes of
+// pinned memory, and cudaMalloc / cudaFree of that size cost milliseconds and synchronise the device. Idle slots wait here
+// (process lifetime, like the pinned pool).
+struct SlotPool {
+  std::mutex mu;
+  std::vector<Slot*> idle;
+  Slot* acquire(int device) {
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      for (size_t k = 0; k < idle.size(); ++k)
+        if (idle[k]->device == device) { Slot* s = idle[k]; idle.erase(idle.begin() + k); return s; }
+    }
+    Slot* s = new Slot;
+    s->device = device;
+    return s;
+  }
+  void release(Slot* s) { std::lock_guard<std::mutex> lock(mu); idle.push_back(s); }
+};
+SlotPool& slot_pool() { static SlotPool* p = new SlotPool; return *p; }
+
+// DXO_TIMING: CPU time of the host stages, summed over all workers of a batch call
+struct HostClock {
+  std::atomic<uint64_t> ns[8];
+  const char* name[8] = {"stage 0 copy inputs", "stage 2 setup (tables, masks)", "stage 2 Edgebreaker traversal", "stage 2 connectivity bytes",
+                         "stage 2 seam streams", "stage 2 sequencers", "stage 4 side streams (host)", "stage 4 assembly"};
+  void reset() { for (auto& v : ns) v.store(0); }
+  void report(uint64_t vertices) {
+    uint64_t total = 0;
+    for (auto& v : ns) total += v.load();
+    for (int k = 0; k < 8; ++k) fprintf(stderr, "[dxo] host cpu  %-34s %9.3f ms  %6.1f ns/vertex\n", name[k], ns[k].load() * 1e-6, (double)ns[k].load() / (double)std::max<uint64_t>(vertices, 1));
+    fprintf(stderr, "[dxo] host cpu  %-34s %9.3f ms  %6.1f ns/vertex\n", "total", total * 1e-6, (double)total / (double)std::max<uint64_t>(vertices, 1));
+  }
+};
+HostClock g_host_clock;
+struct HostLap {
+  Clock::time_point t = Clock::now();
+  void lap(int k) { const auto n = Clock::now(); g_host_clock.ns[k].fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(n - t).count(), std::memory_order_relaxed); t = n; }
+};
+
+// copy + maximum in one pass; eight independent lanes so that the compiler keeps the loop in vector registers
+uint32_t copy_max_u32(uint32_t* dst, const uint32_t* src, size_t n) {
+  uint32_t m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8)
+    for (int k = 0; k < 8; ++k) { const uint32_t v = src[i + k]; dst[i + k] = v; m[k] = v > m[k] ? v : m[k]; }
+  uint32_t mx = 0;
+  for (; i < n; ++i) { dst[i] = src[i]; mx = std::max(mx, src[i]); }
+  for (int k = 0; k < 8; ++k) mx = std::max(mx, m[k]);
+  return mx;
+}
+
 void add_tiles(std::vector<gpu::Tile>& v, uint32_t seg, uint64_t count, uint32_t tile = gpu::kSegTile) {
   for (uint64_t f = 0; f < count; f += tile) v.push_back({seg, (uint32_t)f});
 }
@@ -173,22 +224,31 @@ struct GroupMesh {
     // stage 3
     int stream = -1;        // index of this attribute's AttrSeg / RansJob
     size_t seq = 0;         // pair slab (when the attribute has its own sequence)
+    size_t host_flags = 0;  // pair slab: K5 / K6 flags of a side stream that the host codes (long streams)
+    bool host_side = false;
   };
   std::vector<Att> atts;
   // device-only offsets of stage 1
   size_t first_corner = 0, valence = 0;
+  uint32_t corner_base = 0;   // first slot in the group-wide corner order (sort slots, opposite array, boundary list)
 };
+
+struct GroupSizes { uint64_t sumC = 0, sum_seamV = 0; uint32_t vertex_bits = 1; size_t sort_bytes = 0, scan_bytes = 0, pair_bytes = 0, only_bytes = 0; };
 
 class GroupRunner {
  public:
-  GroupRunner(Slot& slot, Workers& workers, const dxo_config& cfg, dxo_bytes* outs) : slot_(slot), workers_(workers), cfg_(cfg), outs_(outs) {}
+  GroupRunner(Slot& slot, Workers& workers, const dxo_config& cfg, dxo_bytes* outs, size_t min_pair = 0, size_t min_only = 0)
+      : slot_(slot), workers_(workers), cfg_(cfg), outs_(outs), min_pair_(min_pair), min_only_(min_only) {}
   void run(std::vector<GroupMesh*>& meshes);
+  // also fills the per-mesh sizes (C, F, V, attribute capacities)
+  static GroupSizes measure(std::vector<GroupMesh*>& meshes);
 
  private:
   Slot& slot_;
   Workers& workers_;
   dxo_config cfg_;
   dxo_bytes* outs_;
+  size_t min_pair_, min_only_;  // the largest group of the batch: slabs are sized once, not regrown group by group
   Slab pair_, only_;
   template <class T> T* dp(size_t off) const { return (T*)(slot_.d_pair + off); }
   template <class T> T* hp(size_t off) const { return (T*)(slot_.h_pair + off); }
@@ -240,24 +300,22 @@ void GroupRunner::encode_fallback(GroupMesh& m) {
 
 // faces, values and maps into the pinned slab, with the range checks the kernels rely on
 void GroupRunner::stage0_copy_inputs(GroupMesh& m) {
+  HostLap hl;
   guarded(m, [&] {
     const uint32_t* faces = m.mesh->faces;
-    uint32_t* dst = hp<uint32_t>(m.faces);
-    uint32_t max_p = 0;
-    for (uint32_t c = 0; c < m.C; ++c) { const uint32_t p = faces[c]; dst[c] = p; max_p = std::max(max_p, p); }
+    const uint32_t max_p = copy_max_u32(hp<uint32_t>(m.faces), faces, m.C);
     MeshJob& job = *m.job;
     for (size_t i = 0; i < job.plans_.size(); ++i) {
       const AttrView& v = job.plans_[i].view;
       if (v.num_points <= max_p) throw Error(DXO_ERR_INVALID_ARGUMENT, i == 0 ? "face references a point outside the position attribute" : "face references a point outside an attribute");
       memcpy(hp<uint8_t>(m.atts[i].values), v.raw->values, m.atts[i].value_bytes);
       if (v.map) {
-        uint32_t* md = hp<uint32_t>(m.atts[i].map);
-        uint32_t mx = 0;
-        for (uint32_t p = 0; p < v.num_points; ++p) { const uint32_t x = v.map[p]; md[p] = x; mx = std::max(mx, x); }
+        const uint32_t mx = copy_max_u32(hp<uint32_t>(m.atts[i].map), v.map, v.num_points);
         if (v.num_points && mx >= v.num_unique) throw Error(DXO_ERR_INVALID_ARGUMENT, "point_to_value entry out of range");
       }
     }
   });
+  hl.lap(0);
 }
 
 // The tables of K12-K14 have landed in the pinned slab: wrap them as the job's universal / seam tables and run what
@@ -279,15 +337,17 @@ void GroupRunner::stage2_host_connectivity(GroupMesh& m) {
     }
     m.fallback = true; encode_fallback(m); return;
   }
+  HostLap hl;
   guarded(m, [&] {
     UniversalTable& ut = job.ut_;
     ut.num_faces = m.F; ut.num_corners = m.C; ut.num_vertices = m.V;
     ut.corner_point = m.mesh->faces;
-    ut.corner_vertex.adopt(hp<uint32_t>(m.cv), m.C);
+    // corner -> vertex: the faces themselves without a position map (never written on this path), else map[faces] from stage 0
+    if (!m.atts[0].has_map) ut.corner_vertex.adopt(const_cast<uint32_t*>(m.mesh->faces), m.C);
+    else ut.corner_vertex.adopt(hp<uint32_t>(m.cv), m.C);
     ut.opposite.adopt(hp<uint32_t>(m.opposite), m.C);
     ut.left_most.adopt(hp<uint32_t>(m.left_most), m.V);
     ut.matched_on_device = true;
-    ut.has_boundary_list = false;
     job.write_stream_header();
     job.seams_.resize(natt - 1);
     job.table_refs_.assign(natt, TableRef{});
@@ -302,6 +362,7 @@ void GroupRunner::stage2_host_connectivity(GroupMesh& m) {
       SeamTable& st = job.seams_[i - 1];
       st.num_vertices = sc[0];
       st.has_interior_seam = (sc[1] & 4u) != 0;
+      if (!st.has_interior_seam && st.num_vertices == m.V) continue;  // same table as the universal one: nothing was fetched, nothing is needed
       st.corner_vertex.adopt(hp<uint32_t>(a.cv_a), m.C);
       st.seam.adopt(hp<uint8_t>(a.seam), m.C);
       st.left_most.adopt(hp<uint32_t>(a.left_most_a), st.num_vertices);
@@ -316,15 +377,19 @@ void GroupRunner::stage2_host_connectivity(GroupMesh& m) {
         job.table_refs_[i].opposite_masked = mo.data();
       }
     }
+    hl.lap(1);
     job.eb_.reset(new EdgebreakerEncoder(ut));
     EdgebreakerEncoder& eb = *job.eb_;
     eb.traverse();
+    hl.lap(2);
     eb.write_head(job.head_, job.seams_.size());
+    hl.lap(3);
     for (size_t i = 1; i < natt; ++i) {
       ByteSink sb;
       eb.write_seam_stream(job.seams_[i - 1], sb);
       job.head_.bytes(sb.data);
     }
+    hl.lap(4);
     job.plans_[0].sequence = attribute_sequence(job.table_refs_[0], eb.corner_list());
     for (size_t i = 1; i < natt; ++i) {
       const SeamTable& st = job.seams_[i - 1];
@@ -334,22 +399,13 @@ void GroupRunner::stage2_host_connectivity(GroupMesh& m) {
     }
     job.write_attribute_section_headers();
     for (size_t i = 0; i < natt; ++i) job.plans_[i].table = &job.table_refs_[i];
+    hl.lap(5);
   });
 }
 
-void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
-  const bool timing = getenv("DXO_TIMING") != nullptr;
-  auto t0 = Clock::now();
-  auto lap = [&](const char* what) {
-    if (!timing) return;
-    fprintf(stderr, "[dxo] group(%zu meshes) %-28s %9.3f ms\n", meshes.size(), what, ms_since(t0));
-    t0 = Clock::now();
-  };
-  cuda_check(cudaSetDevice(slot_.device), "cudaSetDevice");
+// Sizes of a group and upper bounds of its two slabs (every array is padded to 256 bytes: + 256 per array).
+GroupSizes GroupRunner::measure(std::vector<GroupMesh*>& meshes) {
   const size_t G = meshes.size();
-  if (G == 0) return;
-
-  // ---------------------------------------------------------------- sizes
   uint64_t sumC = 0, sumV = 0, sumF = 0, sum_values = 0, sum_maps = 0, sum_cap = 0, sum_seamC = 0, sum_seamV = 0, sum_symbols = 0, sum_hist = 0;
   uint32_t maxV = 1;
   size_t num_streams = 0, num_seams = 0;
@@ -405,7 +461,30 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
       + (size_t)sum_hist * (4 + 12 + 16 + 3) + num_streams * 64
       + (size_t)sum_symbols * 3 + num_streams * 16 + rans_scratch
       + (num_streams * 12 + G * 3 + 16) * per_array;
-  slot_.ensure(pair_bytes, std::max(only_stage1, only_stage3));
+  GroupSizes gs;
+  gs.sumC = sumC; gs.sum_seamV = sum_seamV; gs.vertex_bits = vertex_bits; gs.sort_bytes = sort_bytes; gs.scan_bytes = scan_bytes;
+  gs.pair_bytes = pair_bytes + (size_t)sumC / 4 + 16384 + 64;                                                        // boundary list
+  gs.only_bytes = std::max(only_stage1 + (size_t)sumC * 4 + gpu::boundary_list_scratch_bytes(sumC) + 512, only_stage3);
+  return gs;
+}
+
+void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
+  const bool timing = getenv("DXO_TIMING") != nullptr;
+  auto t0 = Clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    fprintf(stderr, "[dxo] group(%zu meshes) %-28s %9.3f ms\n", meshes.size(), what, ms_since(t0));
+    t0 = Clock::now();
+  };
+  cuda_check(cudaSetDevice(slot_.device), "cudaSetDevice");
+  const size_t G = meshes.size();
+  if (G == 0) return;
+
+  const GroupSizes gs = measure(meshes);
+  const uint64_t sum_seamV = gs.sum_seamV;
+  const uint32_t vertex_bits = gs.vertex_bits;
+  const size_t sort_bytes = gs.sort_bytes, scan_bytes = gs.scan_bytes;
+  slot_.ensure(std::max(gs.pair_bytes, min_pair_), std::max(gs.only_bytes, min_only_));
   cudaStream_t s = slot_.stream;  // exists from here on (created by the slot's first ensure())
   pair_ = Slab{slot_.h_pair, slot_.pair_cap, 0};
   only_ = Slab{slot_.d_only, slot_.only_cap, 0};
@@ -425,26 +504,38 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
   // tables that go back to the host (one contiguous range), by kind so that each kind is initialised by one memset
   std::vector<GroupMesh*> live;
   for (GroupMesh* gm : meshes) if (gm->alive) live.push_back(gm);
+  // What every mesh's host walks need goes back in one contiguous range: opposite (one gap-free array in the group-wide
+  // corner order, so that the boundary list can be selected from it in one pass), left-most corners, interior flags,
+  // the flag words and the ordered list of boundary corners. corner -> vertex stays on the device (the host has the
+  // faces / computes map[faces] itself), and the seam tables are fetched afterwards only for the attributes that turn
+  // out to have interior seams — for the others the attribute's table IS the universal one.
+  uint64_t liveC = 0;
+  for (GroupMesh* gm : live) { gm->corner_base = (uint32_t)liveC; liveC += gm->C; }
   const size_t out1_begin = pair_.take(0);
-  const size_t opp_begin = pair_.take(0);
-  for (GroupMesh* gm : live) gm->opposite = pair_.take((size_t)gm->C * 4);
+  const size_t opp_begin = pair_.take((size_t)liveC * 4);
+  for (GroupMesh* gm : live) gm->opposite = opp_begin + (size_t)gm->corner_base * 4;
   const size_t opp_end = pair_.used;
-  for (GroupMesh* gm : live) gm->cv = pair_.take((size_t)gm->C * 4);
-  for (GroupMesh* gm : live) gm->left_most = pair_.take((size_t)gm->V * 4);
-  for (GroupMesh* gm : live) gm->interior = pair_.take(gm->V);
+  for (GroupMesh* gm : live) gm->left_most = pair_.take((size_t)gm->V * 4, 4);
+  for (GroupMesh* gm : live) gm->interior = pair_.take(gm->V, 1);
+  const size_t scalars_begin = pair_.take(0, 4);
+  for (GroupMesh* gm : live) gm->flags = pair_.take(4, 4);
+  for (GroupMesh* gm : live) for (size_t i = 1; i < gm->atts.size(); ++i) gm->atts[i].scalars = pair_.take(8, 4);
+  const size_t boundary_count = pair_.take(4, 4);
+  const size_t scalars_end = pair_.used;
+  const uint32_t boundary_cap = (uint32_t)std::min<uint64_t>(liveC, liveC / 16 + 4096);  // list entries copied back (more: the host scans instead)
+  const size_t boundary_list = pair_.take((size_t)boundary_cap * 4, 4);
+  // corner -> vertex of the meshes whose position attribute has a point map follows directly (same copy); the others' is their faces
+  for (GroupMesh* gm : live) if (gm->atts[0].has_map) gm->cv = pair_.take((size_t)gm->C * 4, 4);
+  const size_t out1_end = pair_.used;
+  for (GroupMesh* gm : live) if (!gm->atts[0].has_map) gm->cv = pair_.take((size_t)gm->C * 4);
   for (GroupMesh* gm : live)
     for (size_t i = 1; i < gm->atts.size(); ++i) {
       GroupMesh::Att& a = gm->atts[i];
-      a.seam = pair_.take(gm->C);
-      a.cv_a = pair_.take((size_t)gm->C * 4);
-      a.left_most_a = pair_.take((size_t)a.capacity * 4);
-      a.interior_a = pair_.take(a.capacity);
+      a.cv_a = pair_.take((size_t)gm->C * 4);       // the four arrays of an attribute are one contiguous range (one copy when fetched)
+      a.left_most_a = pair_.take((size_t)a.capacity * 4, 4);
+      a.seam = pair_.take(gm->C, 1);
+      a.interior_a = pair_.take(a.capacity, 1);
     }
-  const size_t scalars_begin = pair_.take(0);
-  for (GroupMesh* gm : live) gm->flags = pair_.take(4, 4);
-  for (GroupMesh* gm : live) for (size_t i = 1; i < gm->atts.size(); ++i) gm->atts[i].scalars = pair_.take(8, 4);
-  const size_t scalars_end = pair_.used;
-  const size_t out1_end = pair_.used;
 
   // device-only scratch of stage 1
   const size_t fc_begin = only_.take(0);
@@ -458,12 +549,15 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
   const size_t bases_off = only_.take((size_t)std::max<uint64_t>(sum_seamV, 1) * 4);
   const size_t sort_off = only_.take(sort_bytes);
   const size_t scan_off = only_.take(scan_bytes);
+  const size_t blist_bytes = gpu::boundary_list_scratch_bytes(liveC);
+  const size_t blist_scratch = only_.take(blist_bytes);
+  const size_t blist_full = only_.take((size_t)std::max<uint64_t>(liveC, 1) * 4);  // the select writes every boundary corner; a prefix goes back
 
   // descriptors and tiles (part of the input range)
   std::vector<gpu::MeshSeg> mesh_segs(live.size());
   std::vector<gpu::SeamSeg> seam_segs;
   std::vector<gpu::Tile> t_corner, t_vertex, t_seam_corner, t_seam_vertex, t_seam_attr;
-  uint32_t corner_base = 0, count_base = 0;
+  uint32_t count_base = 0;
   for (size_t k = 0; k < live.size(); ++k) {
     GroupMesh& m = *live[k];
     const MeshJob& job = *m.job;
@@ -471,8 +565,7 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
     g.faces = dp<uint32_t>(m.faces);
     g.pos_map = m.atts[0].has_map ? dp<uint32_t>(m.atts[0].map) : nullptr;
     g.num_corners = m.C; g.num_points = job.plans_[0].view.num_points; g.num_vertices = m.V;
-    g.corner_base = corner_base;
-    corner_base += m.C;
+    g.corner_base = m.corner_base;
     g.cv = dp<uint32_t>(m.cv); g.opposite = dp<uint32_t>(m.opposite); g.left_most = dp<uint32_t>(m.left_most); g.interior = dp<uint8_t>(m.interior);
     g.first_corner = dn<uint32_t>(m.first_corner); g.valence = dn<uint32_t>(m.valence);
     g.flags = dp<uint32_t>(m.flags);
@@ -515,19 +608,50 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
     cuda_check(cudaMemsetAsync(slot_.d_only + fc_begin, 0xFF, fc_end - fc_begin, s), "cudaMemsetAsync");
     cuda_check(cudaMemsetAsync(slot_.d_only + zero_begin, 0, zero_end - zero_begin, s), "cudaMemsetAsync");
     gpu::launch_seg_corner_tables(dp<gpu::MeshSeg>(o_mesh_segs), (uint32_t)live.size(), dp<gpu::Tile>(o_t_corner), (uint32_t)t_corner.size(),
-                                  dp<gpu::Tile>(o_t_vertex), (uint32_t)t_vertex.size(), corner_base /* corners of the live meshes */, vertex_bits,
-                                  dn<uint8_t>(sort_off), sort_bytes, s);
+                                  dp<gpu::Tile>(o_t_vertex), (uint32_t)t_vertex.size(), liveC, vertex_bits, dn<uint8_t>(sort_off), sort_bytes, s);
+    // corners without an opposite, ascending in the group-wide corner order (flagged meshes contribute garbage that nobody reads)
+    gpu::launch_boundary_list(dp<uint32_t>(opp_begin), liveC, dn<uint8_t>(blist_scratch), blist_bytes, dn<uint32_t>(blist_full), dp<uint32_t>(boundary_count), s);
+    cuda_check(cudaMemcpyAsync(slot_.d_pair + boundary_list, slot_.d_only + blist_full, (size_t)boundary_cap * 4, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync D2D");
     gpu::launch_seg_seam_tables(dp<gpu::SeamSeg>(o_seam_segs), (uint32_t)seam_segs.size(), dp<gpu::Tile>(o_t_sc), (uint32_t)t_seam_corner.size(),
                                 dp<gpu::Tile>(o_t_sv), (uint32_t)t_seam_vertex.size(), dp<gpu::Tile>(o_t_sa), (uint32_t)t_seam_attr.size(),
                                 dn<uint32_t>(counts_off), dn<uint32_t>(bases_off), sum_seamV, dn<uint8_t>(scan_off), scan_bytes, s);
     cuda_check(cudaGetLastError(), "kernel launch (group stage 1)");
     d2h(out1_begin, out1_end);
     slot_.wait();
+    // second step: the seam tables of the attributes that have interior seams (or more vertices than the universal table)
+    bool any = false;
+    for (GroupMesh* gm : live) {
+      if (*hp<uint32_t>(gm->flags)) continue;
+      for (size_t i = 1; i < gm->atts.size(); ++i) {
+        const GroupMesh::Att& a = gm->atts[i];
+        const uint32_t* sc = hp<uint32_t>(a.scalars);
+        if ((sc[1] & (1u | 2u | 8u)) || sc[0] > a.capacity || sc[0] < gm->V) continue;  // the mesh falls back
+        if (!(sc[1] & 4u) && sc[0] == gm->V) continue;                                    // the universal table serves
+        d2h(a.cv_a, a.interior_a + a.capacity);
+        any = true;
+      }
+    }
+    if (any) slot_.wait();
   }
   lap("stage 1 (K12-K14)");
+  // boundary corners per mesh: the list is ascending in the group-wide corner order
+  const uint32_t num_boundary = live.empty() ? 0u : *hp<uint32_t>(boundary_count);
+  const bool have_boundary_list = !live.empty() && num_boundary <= boundary_cap;
+  const uint32_t* blist = hp<uint32_t>(boundary_list);
 
   // ---------------------------------------------------------------- stage 2: host connectivity per mesh
-  workers_.parallel_for(live.size(), [&](size_t k) { stage2_host_connectivity(*live[k]); });
+  workers_.parallel_for(live.size(), [&](size_t k) {
+    GroupMesh& m = *live[k];
+    if (have_boundary_list && *hp<uint32_t>(m.flags) == 0) {
+      const uint32_t* lo = std::lower_bound(blist, blist + num_boundary, m.corner_base);
+      const uint32_t* hi = std::lower_bound(lo, blist + num_boundary, m.corner_base + m.C);
+      std::vector<uint32_t>& bc = m.job->ut_.boundary_corners;
+      bc.resize((size_t)(hi - lo));
+      for (size_t j = 0; j < bc.size(); ++j) bc[j] = lo[j] - m.corner_base;
+      m.job->ut_.has_boundary_list = true;
+    }
+    stage2_host_connectivity(m);
+  });
   lap("stage 2 (traversal, sequences)");
 
   // ---------------------------------------------------------------- stage 3: K1-K10 over the group
@@ -572,8 +696,20 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
     faces4[mi] = only_.take((size_t)act[mi]->F * 16);
     if (act[mi]->atts[0].has_map) cv4_u[mi] = only_.take((size_t)act[mi]->F * 16);
   }
-  // results that go back to the host: stats | side stats | index, then the packed bytes
+  // results that go back to the host: flags of the long side streams | stats | side stats | index, then the packed bytes.
+  // A binary side stream is a serial chain of ~15 ns per bit on the device (one warp per stream): fine for the many short
+  // streams of a group, which then never touch the host, but a 100k-vertex mesh's stream would take longer than all
+  // other kernels of the group together — those are coded by the host workers during assembly (~1.5 ns per bit).
+  static const uint32_t device_rabs_max = getenv("DXO_DEVICE_RABS_MAX") ? (uint32_t)atoi(getenv("DXO_DEVICE_RABS_MAX")) : 16384u;
   const size_t out3_begin = pair_.take(0);
+  for (GroupMesh* gm : act)
+    for (size_t i = 0; i < gm->atts.size(); ++i) {
+      const AttrPlan& p = gm->job->plans_[i];
+      GroupMesh::Att& a = gm->atts[i];
+      const size_t M = gm->job->sequence_of(i).size();
+      a.host_side = (p.scheme == Scheme::Normal || p.scheme == Scheme::TexCoord) && M > device_rabs_max;
+      if (a.host_side) a.host_flags = pair_.take(M);
+    }
   const size_t o_stats = pair_.take(n_streams * sizeof(gpu::AttrStats));
   const size_t o_side_stats = pair_.take(n_streams * sizeof(gpu::SideStats));
   const size_t o_index = pair_.take((n_streams + 1) * sizeof(uint4));
@@ -598,7 +734,7 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
     const bool to_bits = p.port == Portabilization::ToBits;
     sm.quant = (to_bits && p.ncomp_q != 3) ? 0 : only_.take((size_t)U * qstride * 4);
     sm.symbols = only_.take((size_t)std::max<uint32_t>(S, 1) * 4);
-    sm.side_flags = only_.take(std::max<uint32_t>(M, 1));
+    sm.side_flags = a.host_side ? 0 : only_.take(std::max<uint32_t>(M, 1));
     sm.work = only_.take((size_t)p.hist_capacity * 12);
     sm.rans_table = only_.take(((size_t)p.hist_capacity + 1) * 16);
     const uint32_t table_capacity = 3 * p.hist_capacity + 16;
@@ -607,7 +743,7 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
     sm.payload = only_.take(payload_capacity);
     sm.rans_scratch = only_.take(gpu::rans_scratch_bytes(S));
     const bool has_side = p.scheme == Scheme::Normal || p.scheme == Scheme::TexCoord;
-    sm.side_payload = has_side ? only_.take((size_t)M + 16) : 0;
+    sm.side_payload = (has_side && !a.host_side) ? only_.take((size_t)M + 16) : 0;
     sm.fan_link = (i > 0 && p.scheme == Scheme::Normal) ? only_.take((size_t)m.C * 8) : 0;
     sm.cv4 = i > 0 ? only_.take((size_t)m.F * 16) : 0;
     max_table_capacity = std::max(max_table_capacity, p.hist_capacity);
@@ -646,18 +782,19 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
     const size_t seq_att = p.shares_sequence_of >= 0 ? (size_t)p.shares_sequence_of : i;
     g.seq = dp<uint32_t>(m.atts[seq_att].seq);
     g.n = M; g.num_symbols = S;
-    g.rank = dn<uint32_t>(sm.rank); g.symbols = dn<uint32_t>(sm.symbols); g.side_flags = dn<uint8_t>(sm.side_flags);
+    g.rank = dn<uint32_t>(sm.rank); g.symbols = dn<uint32_t>(sm.symbols);
+    g.side_flags = a.host_side ? dp<uint8_t>(a.host_flags) : dn<uint8_t>(sm.side_flags);
     g.hist = dn<uint32_t>(sm.hist); g.hist_capacity = p.hist_capacity; g.work = dn<uint32_t>(sm.work);
     g.rans_table = dn<uint4>(sm.rans_table); g.table_bytes = dn<uint8_t>(sm.table_bytes); g.table_capacity = table_capacity;
     g.stats = dp<gpu::AttrStats>(o_stats) + k;
     g.fan_link_out = sm.fan_link ? dn<uint2>(sm.fan_link) : nullptr;
     g.seam_for_links = i > 0 ? dp<uint8_t>(a.seam) : nullptr;
-    if (has_side) {
+    if (has_side && !a.host_side) {
       g.side_payload = dn<uint8_t>(sm.side_payload); g.side_capacity = M + 16; g.side_stats = dp<gpu::SideStats>(o_side_stats) + k;
       side_ids.push_back((uint32_t)k);
     }
     jobs[k] = gpu::rans_make_job(g.symbols, S, g.rans_table, dn<uint8_t>(sm.rans_scratch), dn<uint8_t>(sm.payload), g.stats);
-    packed_capacity += align_up(table_capacity, 4) + align_up(payload_capacity, 4) + (has_side ? align_up((size_t)M + 16, 4) : 0);
+    packed_capacity += align_up(table_capacity, 4) + align_up(payload_capacity, 4) + ((has_side && !a.host_side) ? align_up((size_t)M + 16, 4) : 0);
   }
   // tile lists per kernel class
   std::vector<gpu::Tile> t_fan, t_mm[5], t_oct, t_prep, t_par[5], t_delta[5], t_nrm, t_uv, t_hs, t_hg;
@@ -748,6 +885,7 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
   const uint8_t* packed = hp<uint8_t>(o_packed);
   workers_.parallel_for(act.size(), [&](size_t mi) {
     GroupMesh& m = *act[mi];
+    HostLap hl;
     guarded(m, [&] {
       MeshJob& job = *m.job;
       job.results_.assign(job.plans_.size(), AttrResult{});
@@ -769,7 +907,12 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
         const uint8_t* base = packed + ix.x;
         r.table_bytes = base;
         r.payload = base + align_up(ix.y, 4);
-        if (side_stats[k].nbytes || job.plans_[i].scheme == Scheme::Normal || job.plans_[i].scheme == Scheme::TexCoord) {
+        if (m.atts[i].host_side) {
+          HostLap side;
+          job.encode_side_stream_from_flags(i, hp<uint8_t>(m.atts[i].host_flags), job.sequence_of(i).size());
+          side.lap(6);
+          hl.t = side.t;
+        } else if (job.plans_[i].scheme == Scheme::Normal || job.plans_[i].scheme == Scheme::TexCoord) {
           r.side_bytes = base + align_up(ix.y, 4) + align_up(ix.z, 4);
           r.side_bytes_len = ix.w;
           r.side_count = side_stats[k].count;
@@ -782,6 +925,7 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
       m.status = DXO_OK;
     });
     m.job.reset();
+    hl.lap(7);
   });
   lap("stage 4 (assembly)");
 }
@@ -797,9 +941,9 @@ void encode_batch_grouped(const dxo_mesh* meshes, size_t n, const dxo_config& cf
   const char* env_w = getenv("DXO_BATCH_WORKERS");
   const int num_workers = env_w ? std::max(1, atoi(env_w)) : std::max(2, hw);
   const char* env_s = getenv("DXO_BATCH_SLOTS");
-  const int slots_per_gpu = env_s ? std::max(1, atoi(env_s)) : 3;
+  const int slots_per_gpu = env_s ? std::max(1, atoi(env_s)) : 4;
   const char* env_c = getenv("DXO_GROUP_CORNERS");
-  const uint64_t group_corners = env_c ? std::max<uint64_t>(3, strtoull(env_c, nullptr, 10)) : (6ull << 20);
+  uint64_t group_corners = env_c ? std::max<uint64_t>(3, strtoull(env_c, nullptr, 10)) : (12ull << 20);
   const size_t group_meshes = 512;
 
   std::vector<GroupMesh> all(n);
@@ -815,7 +959,10 @@ void encode_batch_grouped(const dxo_mesh* meshes, size_t n, const dxo_config& cf
   });
   // longest first, cut into groups
   std::vector<size_t> order;
-  for (size_t i = 0; i < n; ++i) if (all[i].alive) order.push_back(i);
+  uint64_t total_corners = 0;
+  for (size_t i = 0; i < n; ++i) if (all[i].alive) { order.push_back(i); total_corners += 3ull * meshes[i].num_faces; }
+  // groups large enough to amortise a launch set, small enough that every slot of every GPU gets a few of them
+  if (!env_c) group_corners = std::max<uint64_t>(1ull << 20, std::min<uint64_t>(group_corners, total_corners / ((uint64_t)num_gpus * slots_per_gpu * 2) + 1));
   std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return meshes[a].num_faces > meshes[b].num_faces; });
   std::vector<std::vector<GroupMesh*>> groups;
   {
@@ -827,12 +974,18 @@ void encode_batch_grouped(const dxo_mesh* meshes, size_t n, const dxo_config& cf
       corners += c;
     }
   }
+  size_t max_pair = 0, max_only = 0;
+  for (auto& g : groups) { const GroupSizes gs = GroupRunner::measure(g); max_pair = std::max(max_pair, gs.pair_bytes); max_only = std::max(max_only, gs.only_bytes); }
   std::atomic<size_t> next{0};
   std::mutex err_mu;
   std::exception_ptr first_error;
   const int num_slots = (int)std::min<size_t>((size_t)num_gpus * slots_per_gpu, std::max<size_t>(groups.size(), 1));
-  std::vector<std::unique_ptr<Slot>> slots;
-  for (int k = 0; k < num_slots; ++k) { slots.emplace_back(new Slot); slots.back()->device = first_gpu + k % num_gpus; }
+  struct SlotLease {
+    std::vector<Slot*> v;
+    ~SlotLease() { for (Slot* s : v) slot_pool().release(s); }
+    Slot* operator[](size_t k) const { return v[k]; }
+  } slots;
+  for (int k = 0; k < num_slots; ++k) slots.v.push_back(slot_pool().acquire(first_gpu + k % num_gpus));
   std::vector<std::thread> drivers;
   for (int k = 0; k < num_slots; ++k)
     drivers.emplace_back([&, k] {
@@ -840,7 +993,7 @@ void encode_batch_grouped(const dxo_mesh* meshes, size_t n, const dxo_config& cf
         const size_t gi = next.fetch_add(1);
         if (gi >= groups.size()) break;
         try {
-          GroupRunner runner(*slots[k], workers, cfg, outs);
+          GroupRunner runner(*slots[k], workers, cfg, outs, max_pair, max_only);
           runner.run(groups[gi]);
         } catch (...) {
           // a failure of the group as a whole (CUDA error, slab overflow): its unfinished meshes report it
@@ -854,7 +1007,13 @@ void encode_batch_grouped(const dxo_mesh* meshes, size_t n, const dxo_config& cf
         }
       }
     });
+  if (getenv("DXO_TIMING")) g_host_clock.reset();
   for (std::thread& t : drivers) t.join();
+  if (getenv("DXO_TIMING")) {
+    uint64_t verts = 0;
+    for (size_t i = 0; i < n; ++i) if (all[i].status == DXO_OK && meshes[i].num_attributes) verts += meshes[i].attributes[0].num_unique_values;
+    g_host_clock.report(verts);
+  }
   for (size_t i = 0; i < n; ++i) {
     // a mesh that is still marked alive was never finished (its group died before stage 4)
     if (all[i].alive && all[i].status == DXO_OK && outs[i].data == nullptr) all[i].status = DXO_ERR_INTERNAL;

@@ -242,6 +242,48 @@ static inline void rabs_encode_forward(const uint8_t* bits, size_t n, uint8_t ze
   rabs_encode_forward_fn(n, zero_prob, out, [bits](size_t i) { return bits[i]; });
 }
 
+// A stream of n zero bits (the seam flags of an attribute without interior seams, edgebreaker.rs:610-653): the coder's
+// state walks the same cycle over and over — it grows by f0-th parts until the renormalisation threshold, emits one byte
+// and drops back to one of at most 16 states x >> 8 — so the cycles are tabulated per start state (steps until the next
+// renormalisation, byte emitted, state after it) by running the coder's own update rule once, and the run is then
+// coded by table jumps plus a tail of single steps. Bytes are those of rabs_encode by construction.
+static inline void rabs_encode_zero_run(size_t n, uint8_t zero_prob, std::vector<uint8_t>& out) {
+  const uint32_t f0 = zero_prob, f1 = 256u - f0;
+  if (f0 == 0) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "rABS: zero frequency");
+  const uint32_t thr = f0 << 12;
+  auto step = [&](uint32_t x) { const uint32_t q = x / f0; return (q << 8) + (x - q * f0) + f1; };  // after the renormalisation check
+  out.clear();
+  uint32_t x = 4096u;
+  size_t left = n;
+  struct Cycle { uint32_t steps = 0, next = 0; uint8_t byte = 0; };
+  // states right after a renormalisation lie in [thr >> 8, (2^20 - 1) >> 8]
+  const uint32_t lo = thr >> 8, hi = ((1u << 20) - 1u) >> 8;
+  std::vector<Cycle> table(hi - lo + 1);
+  while (left) {
+    if (x >= thr) {  // renormalise, then look the cycle of the new state up (or measure it)
+      out.push_back((uint8_t)x);
+      x >>= 8;
+      for (;;) {
+        Cycle& cy = table[x - lo];
+        if (cy.steps == 0) {  // from x (just renormalised): steps taken before the next renormalisation is due
+          uint32_t y = x, k = 0;
+          while (y < thr) { y = step(y); ++k; }
+          cy.steps = k; cy.byte = (uint8_t)y; cy.next = y >> 8;
+        }
+        if (left <= cy.steps) break;  // the run ends inside this cycle (a renormalisation happens only when another bit follows)
+        left -= cy.steps;
+        out.push_back(cy.byte);
+        x = cy.next;
+      }
+    }
+    x = step(x);
+    --left;
+  }
+  ByteSink tail;
+  ans_write_tail(x - 4096u, tail);
+  out.insert(out.end(), tail.data.begin(), tail.data.end());
+}
+
 // zero_prob byte + leb128 length + rABS bytes: the framing every side stream uses.
 static inline void write_side_stream(const uint8_t* bits, size_t n, bool reversed, uint8_t zero_prob, ByteSink& w) {
   w.u8(zero_prob);

@@ -650,9 +650,13 @@ class EdgebreakerRun {
       if (ut_.has_boundary_list) boundary = ut_.boundary_corners.size();
       else for (uint32_t c = 0; c < ut_.num_corners; ++c) boundary += ut_.opposite[c] == kNone;
       const size_t n = (ut_.num_corners - boundary) / 2;
-      head = end - n;
-      memset(head, 0, n);
-      zeros = n;
+      const uint8_t p0 = side_stream_zero_prob(n, (float)n);
+      std::vector<uint8_t> bytes;
+      rabs_encode_zero_run(n, p0, bytes);  // n zero flags: coded by cycle jumps, same bytes as the bit-by-bit coder
+      w.u8(p0);
+      w.varint(bytes.size());
+      w.bytes(bytes);
+      return;
     } else {
       std::vector<uint8_t> face_seen_v(ut_.num_faces, 0);
       uint8_t* const face_seen = face_seen_v.data();

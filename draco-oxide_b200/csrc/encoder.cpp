@@ -901,6 +901,32 @@ void MeshJob::encode_side_stream(size_t att) {
   }
 }
 
+void MeshJob::encode_side_stream_from_flags(size_t att, const uint8_t* flags, size_t n) {
+  AttrResult& r = results_[att];
+  if (plans_[att].scheme == Scheme::Normal) {
+    size_t ones = 0;
+    for (size_t k = 0; k < n; ++k) ones += flags[k] != 0;
+    r.side_count = (uint32_t)n;
+    r.side_zero_prob = side_stream_zero_prob(n - ones, (float)n);
+    rabs_encode_forward(flags, n, r.side_zero_prob, r.side_payload);
+    return;
+  }
+  U8Array o(n);  // the orientation values that exist, in order
+  size_t m = 0, transitions = 0;
+  uint8_t last = 2;  // the transition scan starts from `true`
+  for (size_t k = 0; k < n; ++k) {
+    const uint8_t f = flags[k];
+    if (!f) continue;
+    o[m++] = f;
+    transitions += f != last;
+    last = f;
+  }
+  r.side_count = (uint32_t)m;
+  r.side_zero_prob = side_stream_zero_prob(transitions, (float)m + 0.001f);
+  const uint8_t* v = o.data();
+  rabs_encode_forward_fn(m, r.side_zero_prob, r.side_payload, [v, m](size_t k) { return (uint8_t)(v[k] == (k + 1 < m ? v[k + 1] : (uint8_t)2)); });
+}
+
 constexpr size_t kStatsSlot = 1024;  // pinned_buffer slot of the per-attribute scalars (attribute slots are 2i, 2i+1)
 
 void MeshJob::download(DeviceContext& ctx) {

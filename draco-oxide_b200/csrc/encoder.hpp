@@ -205,6 +205,8 @@ class MeshJob {
   bool graph_replay = false;  // DXO_FLAG_GRAPH_REPLAY
  private:
   void encode_side_stream(size_t att);
+  // the same from K5 / K6's raw per-element flags (flips, or 0 = none / 1 = false / 2 = true orientations): group path, long streams
+  void encode_side_stream_from_flags(size_t att, const uint8_t* flags, size_t n);
 
   static uint32_t device_matcher(void* user, const uint32_t* corner_vertex, uint32_t num_faces, uint32_t num_vertices, uint32_t* opposite_out,
                                  uint32_t* left_most_out, std::vector<uint32_t>* boundary_corners);

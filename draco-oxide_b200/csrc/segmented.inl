@@ -434,24 +434,28 @@ __device__ __forceinline__ uint32_t device_zero_prob(uint32_t zeros, float len) 
 
 struct RabsDev {
   uint32_t x, pos;
-  uint32_t thr[2], g[2], cum[2];
-  unsigned long long m[2];  // ceil(2^32 / f): 2^32 itself for f = 1
+  // per bit value, in registers (selected, never indexed): renormalisation threshold f << 12, g = 256 - f, cum,
+  // m = ceil(2^32 / f) (f = 1 has m = 2^32: its quotient is x itself, flagged by one[])
+  uint32_t thr0, thr1, g0, g1, cum0, m0, m1, one0, one1;
   uint8_t* out; uint32_t cap; bool lane0; bool overflow;
   __device__ __forceinline__ void init(uint32_t zero_prob, uint8_t* o, uint32_t capacity, bool l0) {
     const uint32_t f0 = zero_prob, f1 = 256u - zero_prob;
-    thr[0] = f0 << 12; thr[1] = f1 << 12;
-    g[0] = 256u - f0; g[1] = 256u - f1;
-    cum[0] = f1; cum[1] = 0u;
-    // q = floor(x / f) = umulhi(x, ceil(2^32 / f)) for x < 2^20, f <= 255 (common.hpp rabs_encode_forward_fn)
-    m[0] = ((1ull << 32) + f0 - 1) / f0; m[1] = ((1ull << 32) + f1 - 1) / f1;
+    thr0 = f0 << 12; thr1 = f1 << 12;
+    g0 = 256u - f0; g1 = 256u - f1;
+    cum0 = f1;
+    // q = floor(x / f) = umulhi(x, ceil(2^32 / f)) for x < 2^20, 2 <= f <= 255 (common.hpp rabs_encode_forward_fn)
+    one0 = f0 == 1u; one1 = f1 == 1u;
+    m0 = one0 ? 0u : (uint32_t)(((1ull << 32) + f0 - 1) / f0); m1 = one1 ? 0u : (uint32_t)(((1ull << 32) + f1 - 1) / f1);
     x = 4096u; pos = 0; out = o; cap = capacity; lane0 = l0; overflow = false;
   }
   __device__ __forceinline__ void put(uint32_t b) {
-    if (x >= thr[b]) {
+    const uint32_t thr = b ? thr1 : thr0, g = b ? g1 : g0, cum = b ? 0u : cum0, m = b ? m1 : m0, one = b ? one1 : one0;
+    if (x >= thr) {
       if (pos < cap) { if (lane0) out[pos] = (uint8_t)x; } else overflow = true;
       ++pos; x >>= 8;
     }
-    x = x + (uint32_t)(((unsigned long long)x * m[b]) >> 32) * g[b] + cum[b];
+    const uint32_t q = one ? x : __umulhi(x, m);
+    x = x + q * g + cum;
   }
   __device__ __forceinline__ void finish() {  // ans_write_tail
     const uint32_t t = x - 4096u;
