@@ -1,7 +1,12 @@
 #!/usr/bin/env python
-"""bench.py — Mvertices/s of the attribute-encoding hot path on BASELINE.json's config 2.
+"""bench.py — Mvertices/s of the attribute-encoding hot path on BASELINE.json's configs (default: config 2).
 
-  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload config2]
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload config2|config3|config4|config5]
+
+Workloads: config2 = the headline (1M-vertex grid; also what the driver runs), config3 = 10M-triangle torus
+with uv seams, config4 = 4096 primitives (1k-100k vertices) through the batch entry dxo_encode_batch, sharded over the
+ranks (strong scaling, meshes/s), config5 = qp sweep on config 2's mesh. The default run also appends a `config4` block
+(the batch entry on this job's GPUs) to the config-2 line, so every driver run measures the sharded batch as well.
 
 A "step" = one pass of the hot path over one synthetic mesh (config 2: 1000x1000 grid,
 1 000 000 vertices, 1 996 002 triangles, positions + normals + texcoords, qp/qn/qt
@@ -40,7 +45,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config2_small"])
+    ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config2_small", "config3", "config4", "config5"])
+    ap.add_argument("--batch-meshes", type=int, default=4096, help="primitives of config 4 used by the config4 workload / block (4096 = all)")
+    ap.add_argument("--no-config4", action="store_true", help="skip the config4 block of the default run")
     ap.add_argument("--sessions", type=int, default=0,
                     help="concurrent resident sessions per GPU for `value`; 0 = one per three host threads available to this GPU, "
                          "at most 6 (each session keeps a main thread and two side-stream coders busy)")
@@ -68,6 +75,8 @@ def make_mesh(workload):
         return synth.config1_mesh(), "config1: 101x251 grid, 25 351 vertices, 50 000 triangles, pos+normal+uv, 11/8/10 bits"
     if workload == "config2_small":
         return synth.config2_mesh(300), "config2_small: 300x300 grid (debug)"
+    if workload == "config3":
+        return synth.config3_mesh(), "config3: 2000x2500-quad torus, 5 000 000 position vertices (5 004 501 points), 10 000 000 triangles, uv seams on both cuts, pos+normal+uv, 11/8/10 bits"
     return synth.config2_mesh(), "config2: 1000x1000 grid, 1 000 000 vertices, 1 996 002 triangles, pos+normal+uv, Edgebreaker, qp/qn/qt=11/8/10"
 
 
@@ -79,6 +88,130 @@ def hbm_peak():
         except Exception:
             pass
     return PEAKS_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
+    (profiles/ncu_traffic.json: {workload: {kernel: bytes}}, written by tools/ncu_traffic.py); the round-1 constants otherwise."""
+    try:
+        return {k: float(v) for k, v in json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(workload, {}).items()}
+    except Exception:
+        return dict(NCU_TRAFFIC_CONFIG2) if workload == "config2" else {}
+
+
+def oracle_stage_split(orc, mesh):
+    """One single-thread oracle encode with ORC_TIMING=1: wall clock of the host-only stages (corner tables, Edgebreaker,
+    sequencer) and of the attribute stages (quantize, predict, transform, entropy, side streams) — BASELINE.md §3."""
+    import re
+    import tempfile
+    os.environ["ORC_TIMING"] = "1"
+    sys.stderr.flush()
+    saved = os.dup(2)
+    with tempfile.TemporaryFile(mode="w+b") as tmp:
+        os.dup2(tmp.fileno(), 2)
+        try:
+            orc.encode(mesh)
+        finally:
+            os.dup2(saved, 2)
+            os.close(saved)
+            os.environ.pop("ORC_TIMING", None)
+        tmp.seek(0)
+        text = tmp.read().decode(errors="replace")
+    host = attr = 0.0
+    for name, ms in re.findall(r"\[orc\]\s+(.+?)\s+([0-9.]+) ms", text):
+        name = name.strip()
+        if name in ("corner table", "attribute corner tables", "edgebreaker", "sequencer"):
+            host += float(ms)
+        elif name in ("portabilize", "predict", "transform", "entropy (hist+table+rANS)", "metadata (rABS)"):
+            attr += float(ms)
+    return {"host_ms": host, "attribute_ms": attr, "note": "one oracle encode on one thread: host = corner tables + Edgebreaker + sequencers, attribute = quantize + predict + transform + entropy + side streams"}
+
+
+def config4_shard(n_meshes, rank, world):
+    """This rank's primitives of config 4: longest first, dealt round-robin over the ranks."""
+    import numpy as np
+    from draco_oxide_b200 import synth
+    counts = synth.batch_vertex_counts()[:n_meshes]
+    order = np.argsort(-counts, kind="stable")
+    mine = order[rank::world]
+    procs = max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
+    # a shard is not a consecutive range of primitives: generate by index
+    import multiprocessing as mp
+    jobs = [(int(k), int(counts[k])) for k in mine]
+    if procs > 1 and len(jobs) >= 8:
+        with mp.get_context("fork").Pool(procs) as pool:
+            meshes = pool.map(synth._batch_mesh_job, jobs, chunksize=4)
+    else:
+        meshes = [synth._batch_mesh_job(j) for j in jobs]
+    return meshes, int(counts.sum()), int(counts.size)
+
+
+def measure_config4(meshes, local_rank, reps, dist, torch, dxo):
+    """The batch entry on this rank's shard: wall clock of dxo_encode_batch (host buffers in, streams out), max over ranks."""
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    out = dxo.encode_batch(meshes, first_gpu=local_rank, num_gpus=1)  # warm-up: slabs, pinned blocks, contexts
+    out = dxo.encode_batch(meshes, first_gpu=local_rank, num_gpus=1)
+    times = []
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.mark_begin()
+    for _ in range(reps):
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        out = dxo.encode_batch(meshes, first_gpu=local_rank, num_gpus=1)
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+    clocks = sampler.stop()
+    in_bytes = sum(m.faces.nbytes + sum(a.values.nbytes + (a.point_to_value.nbytes if a.point_to_value is not None else 0) for a in m.attributes) for m in meshes)
+    out_bytes = sum(len(o) for o in out)
+    tot = torch.tensor([float(in_bytes), float(out_bytes), float(sum(m.num_points() for m in meshes)), float(len(meshes))], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    return times, [float(x) for x in tot.tolist()], clocks, out
+
+
+def config4_cpu_baseline(orc, meshes, sample_every=16):
+    """The oracle on every host thread over a bounded sample of the shard (every 16th primitive of the size-sorted list)."""
+    from concurrent.futures import ThreadPoolExecutor
+    sample = meshes[::sample_every] if len(meshes) >= 4 * sample_every else meshes
+    cores = max(1, min(64, os.cpu_count() or 1))
+    verts = sum(m.num_points() for m in sample)
+    with ThreadPoolExecutor(cores) as ex:
+        list(ex.map(orc.encode, sample[: cores]))  # warm-up
+        t0 = time.perf_counter()
+        list(ex.map(orc.encode, sample))
+        dt = time.perf_counter() - t0
+    return {"value": verts / dt / 1e6, "unit": "Mvertices/s", "meshes_per_s": len(sample) / dt, "cores": cores, "kind": "port",
+            "sample": f"{len(sample)} of the {len(meshes)} primitives (every {sample_every}th of the size-sorted list, {verts} vertices), one oracle encode() per primitive, {cores} threads pulling from one queue"}
+
+
+def config4_block(args, shard, rank, world, local_rank, dist, torch, dxo, with_cpu=True):
+    meshes, total_vertices, total_meshes = shard
+    reps = max(1, min(args.steps, 3))
+    times, tot, clocks, out = measure_config4(meshes, local_rank, reps, dist, torch, dxo)
+    best = min(times)
+    mean = sum(times) / len(times)
+    block = {
+        "workload": f"config4: {int(tot[3])} synthetic glTF primitives (vertex counts log-uniform in [1k, 100k], alternating grid patches / tori with uv seams), "
+                    f"{int(tot[2])} vertices, through dxo_encode_batch; primitives dealt longest-first round-robin over {world} rank(s), one GPU each",
+        "scaling": "strong", "n_gpus": world, "reps": reps,
+        "e2e": {"value": tot[2] / mean / 1e6, "unit": "Mvertices/s", "best": tot[2] / best / 1e6, "meshes_per_s": tot[3] / mean, "ms_per_batch": 1e3 * mean,
+                "h2d_bytes_per_batch": int(tot[0]), "d2h_bytes_per_batch": int(tot[1]), "times_s": times,
+                "note": "wall clock of the call (max over ranks): host buffers in, Draco streams out; connectivity walks on the host workers, everything else in one segmented launch set per group of meshes"},
+        "host_threads": os.cpu_count(), "clocks": clocks,
+    }
+    if with_cpu and rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import orc
+        orc.build()
+        block["cpu_baseline"] = config4_cpu_baseline(orc, meshes)
+    return block
 
 
 class ClockSampler:
@@ -187,6 +320,65 @@ def run_reference(args, rank, world):
     print(json.dumps(line), file=RESULT_OUT or sys.stdout, flush=True)
 
 
+def run_config4(args, shard, rank, world, local_rank, dist, torch, dxo):
+    """--workload config4: the sharded batch as the line itself (strong scaling). The batch entry has no resident mode —
+    host connectivity of a group overlaps with the device work of the others — so value is the end-to-end figure."""
+    block = config4_block(args, shard, rank, world, local_rank, dist, torch, dxo, with_cpu=not args.no_cpu_baseline)
+    if rank != 0:
+        return
+    e = block["e2e"]
+    line = {"metric": METRIC, "value": e["value"], "unit": "Mvertices/s", "n_gpus": world, "steps": block["reps"], "warmup": 2,
+            "ms_per_step": e["ms_per_batch"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32->i32/u32 (bit-exact integer pipeline)", "data": "synthetic", "config": {"workload": block["workload"], "host_threads": os.cpu_count()},
+            "meshes_per_s": e["meshes_per_s"], "gpu_launches": None,
+            "e2e": {"value": e["value"], "unit": "Mvertices/s", "h2d_bytes_per_step": e["h2d_bytes_per_batch"], "d2h_bytes_per_step": e["d2h_bytes_per_batch"],
+                    "meshes_per_s": e["meshes_per_s"], "note": e["note"]},
+            "value_scope": "the batch entry has no resident mode: value == e2e (host buffers in, streams out)",
+            "roofline": {"bound": "hbm", "kernel": None, "achieved": None, "peak": hbm_peak()[0], "unit": "GB/s", "frac": None, "traffic": None,
+                         "note": "per-kernel figures are taken on config 2 (same kernel bodies); the batch is bound by the host connectivity walks"},
+            "clocks": block["clocks"], "cpu_baseline": block.get("cpu_baseline")}
+    print(json.dumps(line), file=RESULT_OUT or sys.stdout, flush=True)
+
+
+def run_config5(args, rank, world, local_rank, dist, torch, dxo):
+    """--workload config5: qp in {8,10,11,12,14,16} on config 2's mesh (Edgebreaker; the reference has no sequential-connectivity
+    attribute path). Per qp: a lone dxo_encode call from pinned host buffers, and the oracle on one thread."""
+    from draco_oxide_b200 import synth
+    mesh = synth.config2_mesh()
+    V = mesh.num_points()
+    pmesh = pinned_copy(mesh)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    orc.build()
+    rows = []
+    for qp in (8, 10, 11, 12, 14, 16):
+        cfg = dxo.Config(position_bits=qp, device=local_rank)
+        for _ in range(2):
+            out = bytearray(); dxo.encode(pmesh, out, cfg)
+        t0 = time.perf_counter()
+        n = max(1, min(args.steps, 5))
+        for _ in range(n):
+            out = bytearray(); dxo.encode(pmesh, out, cfg)
+        ms = 1e3 * (time.perf_counter() - t0) / n
+        tm = dxo.last_timing()
+        row = {"qp": qp, "stream_bytes": len(out), "e2e_single_call_ms": ms, "e2e_mvertices_per_s": V / ms / 1e3, "device_ms": tm["device_ms"],
+               "host_connectivity_ms": tm["host_connectivity_ms"]}
+        if not args.no_cpu_baseline and rank == 0:
+            secs = orc.encode_timed(mesh, 1, 1, cfg)
+            row["oracle_single_thread_mvertices_per_s"] = V / secs / 1e6
+        rows.append(row)
+    if rank != 0:
+        return
+    main_row = [r for r in rows if r["qp"] == 11][0]
+    line = {"metric": METRIC, "value": main_row["e2e_mvertices_per_s"], "unit": "Mvertices/s", "n_gpus": world, "steps": max(1, min(args.steps, 5)), "warmup": 2,
+            "ms_per_step": main_row["e2e_single_call_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32->i32/u32 (bit-exact integer pipeline)", "data": "synthetic",
+            "config": {"workload": "config5: qp sweep {8,10,11,12,14,16} on config 2's 1M-vertex mesh, Edgebreaker; 'sequential' is not applicable (unimplemented in the reference)"},
+            "value_scope": "lone dxo_encode calls from pinned host buffers (latency figure); value is the qp = 11 row", "sweep": rows,
+            "e2e": {"value": main_row["e2e_mvertices_per_s"], "unit": "Mvertices/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None}}
+    print(json.dumps(line), file=RESULT_OUT or sys.stdout, flush=True)
+
+
 RESULT_OUT = None  # the process's real stdout, see main()
 
 
@@ -207,6 +399,10 @@ def main():
 
     if args.sessions <= 0 and default_sessions(world)[1]:
         os.environ.setdefault("DXO_BLOCKING_WAIT", "1")  # read when a thread's device context is created
+    # config 4's primitives are generated by forked numpy workers: before this process holds a CUDA context
+    c4_shard = None
+    if args.workload == "config4" or (args.workload == "config2" and not args.no_config4):
+        c4_shard = config4_shard(args.batch_meshes, rank, world)
     import numpy as np
     import torch
     import draco_oxide_b200 as dxo
@@ -227,9 +423,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.workload == "config4":
+        run_config4(args, c4_shard, rank, world, local_rank, dist, torch, dxo)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    if args.workload == "config5":
+        run_config5(args, rank, world, local_rank, dist, torch, dxo)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     mesh, desc = make_mesh(args.workload)
     V = mesh.num_points()
     cfg = dxo.Config(device=local_rank)
+    if args.workload == "config3" and args.sessions <= 0:
+        args.sessions = 2       # ~0.9 GB resident per session
+    if args.workload == "config3" and args.e2e_callers <= 0:
+        args.e2e_callers = 4
 
     # ---- device-resident arm ------------------------------------------------------------
     # `value`: S sessions (one host thread each, own CUDA streams) encode the resident mesh concurrently, the way the
@@ -385,6 +595,12 @@ def main():
     e2e_s = float(t.item())
     clocks_e2e = sampler2.stop()
     barrier()
+    sess.close()
+    # the sharded batch (config 4) on the same GPUs, before rank 0 spends its host threads on the CPU baseline
+    c4 = None
+    if args.workload == "config2" and not args.no_config4:
+        c4 = config4_block(args, c4_shard, rank, world, local_rank, dist, torch, dxo, with_cpu=not args.no_cpu_baseline)
+        c4_shard = None
 
     if rank == 0:
         value = V * world * S * args.steps / (ms_total_max * 1e-3) / 1e6
@@ -407,7 +623,7 @@ def main():
                     "host_connectivity_ms_per_call": host_ms / lone_calls, "steps": e2e_steps, "clocks": clocks_e2e},
             "roofline": {"bound": "hbm", "kernel": dom["name"], "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
                          "frac": dom["gbs"] / peak if dom["gbs"] else None,
-                         "traffic": NCU_TRAFFIC_CONFIG2.get(dom["name"]) if args.workload == "config2" else None, "peak_source": peak_src,
+                         "traffic": ncu_traffic(args.workload).get(dom["name"]), "peak_source": peak_src,
                          "note": "dominant HBM-bound attribute kernel; K10 (rANS) is a serial latency-bound loop and is reported under 'rans' (SURVEY.md §8d)"},
             "attribute_kernels": {"algorithmic_bytes_per_step": attr_bytes, "ms_per_step": attr_ms, "gbs": attr_bytes / attr_ms / 1e6 if attr_ms else None,
                                   "frac_of_peak": attr_bytes / attr_ms / 1e6 / peak if attr_ms else None},
@@ -417,20 +633,30 @@ def main():
                                                    / max((k["ms_per_launch"] for k in rans), default=1) / 1e3) if rans else None},
             "kernels": kernels,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import orc
-            reps = 3
+            orc.build()
+            reps = 1 if args.workload == "config3" else 3
             secs = orc.encode_timed(mesh, reps, 1)
             cores = max(1, min(64, os.cpu_count() or 1))
+            if args.workload == "config3":
+                cores = min(cores, 16)  # ~1.3 GB per oracle thread
             secs_all = orc.encode_timed(mesh, 2, cores)
             line["cpu_baseline"] = {"value": V * 2 * cores / secs_all / 1e6, "unit": "Mvertices/s", "cores": cores, "kind": "port",
                                     "sample": f"2 full encode() calls of the same mesh per thread by the C++ oracle on {cores} threads at once (the reference "
                                               "encoder is single-threaded per mesh; compare with e2e.value); one thread alone: single_thread_value "
                                               "(compare with e2e.single_call_mvertices_per_s)",
-                                    "single_thread_value": V * reps / secs / 1e6}
+                                    "single_thread_value": V * reps / secs / 1e6,
+                                    "split": oracle_stage_split(orc, mesh)}
+            line["cpu_baseline"]["split"]["repo_host_connectivity_ms"] = host_ms / lone_calls
+            line["cpu_baseline"]["split"]["repo_device_ms"] = tm["device_ms"]
+        line["value_scope"] = ("value = resident device step (K1-K10, result D2H, side streams, assembly); corner tables, Edgebreaker, sequencer and H2D are "
+                               "outside it, so compare the reference arm with e2e, not with value")
+        if c4 is not None:
+            line["config4"] = c4
+            line["meshes_per_s"] = c4["e2e"]["meshes_per_s"]
         print(json.dumps(line), file=RESULT_OUT or sys.stdout, flush=True)
-    sess.close()
     if dist is not None:
         dist.destroy_process_group()
 
