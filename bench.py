@@ -57,16 +57,24 @@ def parse_args():
     return ap.parse_args()
 
 
+def host_threads():
+    """Host threads this process may use (the affinity mask, so that `taskset` runs emulate a box with fewer threads)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def default_sessions(world):
-    """(sessions per GPU, blocking waits?) from the host threads this GPU can count on. A session keeps two side-stream
-    coders busy; its main thread spins in the waits (fastest) when there are three threads per session to spare and
-    sleeps in them (DXO_BLOCKING_WAIT) when host threads are scarce."""
-    per_gpu = max(1, (os.cpu_count() or 2) // max(1, world))
+    """(sessions per GPU, scarce host threads?) from the host threads this GPU can count on. With threads to spare a session
+    keeps two side-stream coder threads busy and its main thread spins in the waits (fastest); when host threads are scarce
+    (e.g. 32 threads for 8 GPUs) a session is ONE thread that sleeps in its waits (DXO_BLOCKING_WAIT) and codes both side
+    streams itself in one interleaved loop (DXO_SIDE_INLINE), with a few more sessions than threads so that the device
+    always has a step queued."""
+    per_gpu = max(1, host_threads() // max(1, world))
     if per_gpu >= 15:
         return max(1, min(8, per_gpu // 2)), False  # measured on 16 threads: 5 sessions 1290, 8 sessions 1420, 16 sessions 1460 Mvertices/s
-    # few host threads (e.g. 32 threads for 8 GPUs): sleeping waits, and more sessions than threads still help because a
-    # session's host work comes in bursts (measured with 4 threads: 2 / 4 / 6 sessions give 617 / 751 / 811 Mvertices/s)
-    return max(2, min(8, per_gpu * 3 // 2)), True
+    return max(2, min(8, per_gpu + 2)), True
 
 
 def make_mesh(workload):
@@ -134,7 +142,7 @@ def config4_shard(n_meshes, rank, world):
     counts = synth.batch_vertex_counts()[:n_meshes]
     order = np.argsort(-counts, kind="stable")
     mine = order[rank::world]
-    procs = max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
+    procs = max(1, min(16, host_threads() // max(1, world)))
     # a shard is not a consecutive range of primitives: generate by index
     import multiprocessing as mp
     jobs = [(int(k), int(counts[k])) for k in mine]
@@ -180,7 +188,7 @@ def config4_cpu_baseline(orc, meshes, sample_every=16):
     """The oracle on every host thread over a bounded sample of the shard (every 16th primitive of the size-sorted list)."""
     from concurrent.futures import ThreadPoolExecutor
     sample = meshes[::sample_every] if len(meshes) >= 4 * sample_every else meshes
-    cores = max(1, min(64, os.cpu_count() or 1))
+    cores = max(1, min(64, host_threads()))
     verts = sum(m.num_points() for m in sample)
     with ThreadPoolExecutor(cores) as ex:
         list(ex.map(orc.encode, sample[: cores]))  # warm-up
@@ -204,7 +212,7 @@ def config4_block(args, shard, rank, world, local_rank, dist, torch, dxo, with_c
         "e2e": {"value": tot[2] / mean / 1e6, "unit": "Mvertices/s", "best": tot[2] / best / 1e6, "meshes_per_s": tot[3] / mean, "ms_per_batch": 1e3 * mean,
                 "h2d_bytes_per_batch": int(tot[0]), "d2h_bytes_per_batch": int(tot[1]), "times_s": times,
                 "note": "wall clock of the call (max over ranks): host buffers in, Draco streams out; connectivity walks on the host workers, everything else in one segmented launch set per group of meshes"},
-        "host_threads": os.cpu_count(), "clocks": clocks,
+        "host_threads": host_threads(), "clocks": clocks,
     }
     if with_cpu and rank == 0:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -300,7 +308,7 @@ def run_reference(args, rank, world):
     orc.build()
     mesh, desc = make_mesh(args.workload)
     V = mesh.num_points()
-    threads = max(1, min(64, os.cpu_count() or 1))  # every host thread (at most 64: ~250 MB each) encodes the workload mesh; the reference is single-threaded per mesh
+    threads = max(1, min(64, host_threads()))  # every host thread (at most 64: ~250 MB each) encodes the workload mesh; the reference is single-threaded per mesh
     for _ in range(max(0, min(args.warmup, 1))):
         orc.encode_timed(mesh, 1, threads)
     t = 0.0
@@ -329,7 +337,7 @@ def run_config4(args, shard, rank, world, local_rank, dist, torch, dxo):
     e = block["e2e"]
     line = {"metric": METRIC, "value": e["value"], "unit": "Mvertices/s", "n_gpus": world, "steps": block["reps"], "warmup": 2,
             "ms_per_step": e["ms_per_batch"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32->i32/u32 (bit-exact integer pipeline)", "data": "synthetic", "config": {"workload": block["workload"], "host_threads": os.cpu_count()},
+            "dtype": "f32->i32/u32 (bit-exact integer pipeline)", "data": "synthetic", "config": {"workload": block["workload"], "host_threads": host_threads()},
             "meshes_per_s": e["meshes_per_s"], "gpu_launches": None,
             "e2e": {"value": e["value"], "unit": "Mvertices/s", "h2d_bytes_per_step": e["h2d_bytes_per_batch"], "d2h_bytes_per_step": e["d2h_bytes_per_batch"],
                     "meshes_per_s": e["meshes_per_s"], "note": e["note"]},
@@ -399,6 +407,7 @@ def main():
 
     if args.sessions <= 0 and default_sessions(world)[1]:
         os.environ.setdefault("DXO_BLOCKING_WAIT", "1")  # read when a thread's device context is created
+        os.environ.setdefault("DXO_SIDE_INLINE", "1")
     # config 4's primitives are generated by forked numpy workers: before this process holds a CUDA context
     c4_shard = None
     if args.workload == "config4" or (args.workload == "config2" and not args.no_config4):
@@ -551,7 +560,7 @@ def main():
     single_call_ms = 1e3 * (time.perf_counter() - t0) / lone_calls
     tm = dxo.last_timing()
     h2d, d2h = tm["h2d_bytes"], tm["d2h_bytes"]
-    T = args.e2e_callers if args.e2e_callers > 0 else max(1, min(32, (os.cpu_count() or 1) // max(1, world)))  # ~250 MB of pinned tables per caller
+    T = args.e2e_callers if args.e2e_callers > 0 else max(1, min(32, host_threads() // max(1, world)))  # ~250 MB of pinned tables per caller
     e2e_steps = max(1, min(args.steps, 10))
     e_ready, e_go = threading.Barrier(T + 1), threading.Barrier(T + 1)
     e_errors = []
@@ -609,7 +618,7 @@ def main():
             "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32->i32/u32 (bit-exact integer pipeline)", "data": "synthetic",
             "config": {"workload": desc, "units_per_step_per_gpu": f"{S} meshes ({S} concurrent resident sessions of the workload mesh)",
-                       "host_threads": os.cpu_count(), "host_waits": "blocking" if os.environ.get("DXO_BLOCKING_WAIT") else "spinning",
+                       "host_threads": host_threads(), "host_waits": "blocking" if os.environ.get("DXO_BLOCKING_WAIT") else "spinning", "side_streams": "inline, interleaved" if os.environ.get("DXO_SIDE_INLINE") else "two helper threads per session",
                        "parallelism": f"{world} independent replicas, no collective",
                        "l2": f"inputs larger than L2: {input_bytes / 1e6:.0f} MB resident per mesh vs 126 MB L2",
                        "stream_bytes": len(ref_bytes)},
@@ -639,7 +648,7 @@ def main():
             orc.build()
             reps = 1 if args.workload == "config3" else 3
             secs = orc.encode_timed(mesh, reps, 1)
-            cores = max(1, min(64, os.cpu_count() or 1))
+            cores = max(1, min(64, host_threads()))
             if args.workload == "config3":
                 cores = min(cores, 16)  # ~1.3 GB per oracle thread
             secs_all = orc.encode_timed(mesh, 2, cores)

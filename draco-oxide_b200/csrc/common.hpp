@@ -242,6 +242,49 @@ static inline void rabs_encode_forward(const uint8_t* bits, size_t n, uint8_t ze
   rabs_encode_forward_fn(n, zero_prob, out, [bits](size_t i) { return bits[i]; });
 }
 
+// Two independent streams coded in ONE loop: the coder is a serial chain of ~6 cycles per bit, two chains interleave in
+// the pipeline and finish in little more than the time of one. Used when host threads are scarce (one thread per resident
+// session instead of three). Same bytes as rabs_encode_forward_fn on each stream.
+struct RabsChain {
+  uint32_t x = 4096u;
+  uint32_t thr[2], g[2], cum[2];
+  uint64_t m[2];
+  uint8_t* p = nullptr;
+  void init(uint8_t zero_prob, uint8_t* out) {
+    const uint32_t f0 = zero_prob, f1 = 256u - f0;
+    thr[0] = f0 << 12; thr[1] = f1 << 12;
+    g[0] = 256u - f0; g[1] = 256u - f1;
+    cum[0] = f1; cum[1] = 0u;
+    m[0] = f0 ? ((1ull << 32) + f0 - 1) / f0 : 0; m[1] = f1 ? ((1ull << 32) + f1 - 1) / f1 : 0;
+    p = out;
+  }
+  inline void put(uint32_t b) {
+    if (x >= thr[b]) { *p++ = (uint8_t)x; x >>= 8; }
+    x = x + (uint32_t)(((uint64_t)x * m[b]) >> 32) * g[b] + cum[b];
+  }
+  void finish(std::vector<uint8_t>& out) {
+    ByteSink tail;
+    ans_write_tail(x - 4096u, tail);
+    for (uint8_t b : tail.data) *p++ = b;
+    out.resize((size_t)(p - out.data()));
+  }
+};
+template <class BitA, class BitB>
+static inline void rabs_encode_forward_pair(size_t na, uint8_t pa, std::vector<uint8_t>& outa, BitA bita, size_t nb, uint8_t pb, std::vector<uint8_t>& outb, BitB bitb) {
+  if (pa == 0 || pb == 0) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "rABS: zero frequency");  // zero_prob is clamped to [1, 255] by its callers
+  if (outa.size() < na + 8) outa.resize(na + 8);
+  if (outb.size() < nb + 8) outb.resize(nb + 8);
+  RabsChain a, b;
+  a.init(pa, outa.data());
+  b.init(pb, outb.data());
+  const size_t both = na < nb ? na : nb;
+  for (size_t i = 0; i < both; ++i) { a.put(bita(i) != 0); b.put(bitb(i) != 0); }
+  for (size_t i = both; i < na; ++i) a.put(bita(i) != 0);
+  for (size_t i = both; i < nb; ++i) b.put(bitb(i) != 0);
+  a.finish(outa);
+  b.finish(outb);
+}
+
 // A stream of n zero bits (the seam flags of an attribute without interior seams, edgebreaker.rs:610-653): the coder's
 // state walks the same cycle over and over — it grows by f0-th parts until the renormalisation threshold, emits one byte
 // and drops back to one of at most 16 states x >> 8 — so the cycles are tabulated per start state (steps until the next

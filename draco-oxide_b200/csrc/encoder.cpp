@@ -311,6 +311,7 @@ MeshJob::~MeshJob() {
     if (pinned_copy_in_flight_.load()) cudaDeviceSynchronize();
     for (auto& b : pinned_blocks_) pinned_pool().give(b.first, b.second);
   }
+  for (size_t i = 0; i < side_host_.size(); ++i) if (side_host_[i]) pinned_pool().give(side_host_[i], side_host_cap_[i]);
   for (cudaEvent_t e : side_ready_) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : side_copied_) if (e) cudaEventDestroy(e);
 }
@@ -673,8 +674,12 @@ void MeshJob::upload(DeviceContext& ctx) {
   cuda_check(cudaStreamWaitEvent(ctx.copy_stream, ctx.ev_join[0], 0), "cudaStreamWaitEvent");
   side_ready_.assign(plans_.size(), nullptr);
   side_copied_.assign(plans_.size(), nullptr);
+  side_host_.assign(plans_.size(), nullptr);
+  side_host_cap_.assign(plans_.size(), 0);
   for (size_t i = 0; i < plans_.size(); ++i) {
     if (plans_[i].scheme != Scheme::Normal && plans_[i].scheme != Scheme::TexCoord) continue;
+    side_host_[i] = (uint8_t*)pinned_pool().take(sequence_of(i).size() + 16, &side_host_cap_[i]);
+    if (!side_host_[i]) throw Error(DXO_ERR_OUT_OF_MEMORY, "pinned host allocation failed");
     cuda_check(cudaEventCreateWithFlags(&side_ready_[i], cudaEventDisableTiming), "cudaEventCreate");
     cuda_check(cudaEventCreateWithFlags(&side_copied_[i], cudaEventDisableTiming | (getenv("DXO_BLOCKING_WAIT") ? (unsigned)cudaEventBlockingSync : 0u)), "cudaEventCreate");
   }
@@ -723,8 +728,6 @@ void MeshJob::launch_graph(DeviceContext& ctx, Profile& prof) {
   cudaStream_t s0 = ctx.stream[0];
   if (!graph_exec_ || graph_ctx_ != &ctx) {
     if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
-    // everything the captured sequence would allocate lazily exists before the capture starts
-    for (size_t i = 0; i < plans_.size(); ++i) if (side_ready_[i]) ctx.pinned_buffer(2 * i + 1, sequence_of(i).size() + 16);
     if (!ev_graph_done_) cuda_check(cudaEventCreateWithFlags(&ev_graph_done_, cudaEventDisableTiming), "cudaEventCreate");
     for (int k = 0; k < 3; ++k) cuda_check(cudaStreamSynchronize(ctx.stream[k]), "cudaStreamSynchronize");
     cuda_check(cudaStreamSynchronize(ctx.copy_stream), "cudaStreamSynchronize");
@@ -852,7 +855,7 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     if (side_ready_[i]) {
       // The side stream input leaves for the host as soon as it is ready; the host codes it during K9-K10. What is
       // data-parallel about it is done here: flips are counted, orientation flags compacted and their transitions counted.
-      uint8_t* host = ctx.pinned_buffer(2 * i + 1, M + 16);
+      uint8_t* host = side_host_[i];
       uint32_t* scalars = (uint32_t*)d.side_out;
       if (p.scheme == Scheme::Normal) {
         gpu::launch_count_flips(d.side_out + 8, M, scalars, s);
@@ -901,6 +904,30 @@ void MeshJob::encode_side_stream(size_t att) {
   }
 }
 
+// Two side streams (a normal attribute's flips and a texcoord attribute's orientations, or two of a kind) in one loop.
+void MeshJob::encode_side_stream_pair(size_t ia, size_t ib) {
+  struct View { const uint8_t* flags; size_t n; uint8_t p0; bool normal; };
+  auto view = [&](size_t att) {
+    AttrResult& r = results_[att];
+    uint32_t scalars[2];
+    memcpy(scalars, r.side, 8);
+    const size_t n = scalars[0];
+    if (n > r.side_len) throw Error(DXO_ERR_INTERNAL, "side stream longer than its attribute");
+    r.side_count = (uint32_t)n;
+    const bool normal = plans_[att].scheme == Scheme::Normal;
+    r.side_zero_prob = normal ? side_stream_zero_prob(n - scalars[1], (float)n) : side_stream_zero_prob(scalars[1], (float)n + 0.001f);
+    return View{r.side + 8, n, r.side_zero_prob, normal};
+  };
+  const View a = view(ia), b = view(ib);
+  auto bit = [](const View& v) {
+    const uint8_t* f = v.flags;
+    const size_t n = v.n;
+    const bool normal = v.normal;
+    return [f, n, normal](size_t k) -> uint8_t { return normal ? f[k] : (uint8_t)(f[k] == (k + 1 < n ? f[k + 1] : (uint8_t)2)); };
+  };
+  rabs_encode_forward_pair(a.n, a.p0, results_[ia].side_payload, bit(a), b.n, b.p0, results_[ib].side_payload, bit(b));
+}
+
 void MeshJob::encode_side_stream_from_flags(size_t att, const uint8_t* flags, size_t n) {
   AttrResult& r = results_[att];
   if (plans_[att].scheme == Scheme::Normal) {
@@ -931,12 +958,16 @@ constexpr size_t kStatsSlot = 1024;  // pinned_buffer slot of the per-attribute 
 
 void MeshJob::download(DeviceContext& ctx) {
   results_.resize(plans_.size());
-  // side streams: start a host worker per stream as soon as its flags have landed
+  // side streams: start a host worker per stream as soon as its flags have landed — or, with DXO_SIDE_INLINE=1 (hosts with
+  // few threads per GPU), code them on this thread, two at a time in one interleaved loop, while the device runs K8-K10
+  static const bool side_inline = getenv("DXO_SIDE_INLINE") != nullptr;
   std::vector<std::future<void>> workers;
+  std::vector<size_t> inline_streams;
   for (size_t i = 0; i < plans_.size(); ++i) {
     if (!side_copied_[i]) continue;
-    results_[i].side = ctx.pinned_buffer(2 * i + 1, sequence_of(i).size() + 16);
+    results_[i].side = side_host_[i];
     results_[i].side_len = sequence_of(i).size();
+    if (side_inline) { inline_streams.push_back(i); continue; }
     const int device = ctx.device;
     cudaEvent_t ev = side_copied_[i];
     workers.push_back(ctx.helpers->run([this, i, device, ev] {
@@ -952,6 +983,15 @@ void MeshJob::download(DeviceContext& ctx) {
   }
   auto join_workers = [&] { for (auto& w : workers) w.get(); };
   try {
+    for (size_t k = 0; k < inline_streams.size(); k += 2) {
+      cuda_check(cudaEventSynchronize(side_copied_[inline_streams[k]]), "cudaEventSynchronize");
+      if (k + 1 < inline_streams.size()) {
+        cuda_check(cudaEventSynchronize(side_copied_[inline_streams[k + 1]]), "cudaEventSynchronize");
+        encode_side_stream_pair(inline_streams[k], inline_streams[k + 1]);
+      } else {
+        encode_side_stream(inline_streams[k]);
+      }
+    }
     // the scalars land in pinned memory: a device-to-host copy into pageable memory blocks the calling thread inside the
     // driver until the stream gets there, which stalls the launches of every other thread of the process
     gpu::AttrStats* stats_host = (gpu::AttrStats*)ctx.pinned_buffer(kStatsSlot, plans_.size() * sizeof(gpu::AttrStats));

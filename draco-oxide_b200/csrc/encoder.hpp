@@ -193,6 +193,10 @@ class MeshJob {
   void upload_seam_table(DeviceContext& ctx, size_t att);
   cudaStream_t alloc_stream_ = nullptr;
   std::vector<cudaEvent_t> side_ready_, side_copied_;
+  // pinned staging of the side-stream flags, owned by the job (a captured graph bakes the destination address in, so it
+  // must not belong to a thread's context, whose buffers move when another job on that thread needs larger ones)
+  std::vector<uint8_t*> side_host_;
+  std::vector<size_t> side_host_cap_;
   bool uploaded_ = false;
   cudaGraphExec_t graph_exec_ = nullptr;
   DeviceContext* graph_ctx_ = nullptr;
@@ -205,6 +209,7 @@ class MeshJob {
   bool graph_replay = false;  // DXO_FLAG_GRAPH_REPLAY
  private:
   void encode_side_stream(size_t att);
+  void encode_side_stream_pair(size_t a, size_t b);  // both in one interleaved loop (DXO_SIDE_INLINE: no helper threads)
   // the same from K5 / K6's raw per-element flags (flips, or 0 = none / 1 = false / 2 = true orientations): group path, long streams
   void encode_side_stream_from_flags(size_t att, const uint8_t* flags, size_t n);
 
