@@ -52,6 +52,8 @@ def parse_args():
                     help="concurrent resident sessions per GPU for `value`; 0 = one per three host threads available to this GPU, "
                          "at most 6 (each session keeps a main thread and two side-stream coders busy)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph-replay", default="auto", choices=["auto", "on", "off"],
+                    help="resident sessions replay their step as one CUDA graph (auto: when host threads are scarce)")
     ap.add_argument("--e2e-callers", type=int, default=0,
                     help="host threads calling dxo_encode() concurrently in the end-to-end arm (0 = the host threads this GPU can count on)")
     return ap.parse_args()
@@ -445,6 +447,8 @@ def main():
     mesh, desc = make_mesh(args.workload)
     V = mesh.num_points()
     cfg = dxo.Config(device=local_rank)
+    graph = args.graph_replay == "on" or (args.graph_replay == "auto" and default_sessions(world)[1])
+    session_cfg = dxo.Config(device=local_rank, flags=dxo.Config.GRAPH_REPLAY if graph else 0)
     if args.workload == "config3" and args.sessions <= 0:
         args.sessions = 2       # ~0.9 GB resident per session
     if args.workload == "config3" and args.e2e_callers <= 0:
@@ -461,7 +465,7 @@ def main():
     def worker(i):
         try:
             torch.cuda.set_device(local_rank)
-            sessions[i] = dxo.Session(mesh, cfg)
+            sessions[i] = dxo.Session(mesh, session_cfg)
             if i == 0:
                 results[i] = {"timing": dxo.last_timing(), "bytes": sessions[i].run()}
             sessions[i].run_steps(max(args.warmup, 3))
@@ -618,7 +622,7 @@ def main():
             "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32->i32/u32 (bit-exact integer pipeline)", "data": "synthetic",
             "config": {"workload": desc, "units_per_step_per_gpu": f"{S} meshes ({S} concurrent resident sessions of the workload mesh)",
-                       "host_threads": host_threads(), "host_waits": "blocking" if os.environ.get("DXO_BLOCKING_WAIT") else "spinning", "side_streams": "inline, interleaved" if os.environ.get("DXO_SIDE_INLINE") else "two helper threads per session",
+                       "host_threads": host_threads(), "host_waits": "blocking" if os.environ.get("DXO_BLOCKING_WAIT") else "spinning", "graph_replay": bool(graph), "side_streams": "inline, interleaved" if os.environ.get("DXO_SIDE_INLINE") else "two helper threads per session",
                        "parallelism": f"{world} independent replicas, no collective",
                        "l2": f"inputs larger than L2: {input_bytes / 1e6:.0f} MB resident per mesh vs 126 MB L2",
                        "stream_bytes": len(ref_bytes)},

@@ -894,7 +894,8 @@ void MeshJob::encode_side_stream(size_t att) {
   r.side_count = (uint32_t)n;
   if (plans_[att].scheme == Scheme::Normal) {
     r.side_zero_prob = side_stream_zero_prob(n - scalars[1], (float)n);  // scalars[1] = flips set
-    rabs_encode_forward(flags, n, r.side_zero_prob, r.side_payload);
+    if (scalars[1] == 0) rabs_encode_zero_run(n, r.side_zero_prob, r.side_payload);  // no flip at all (smooth normals): cycle jumps
+    else rabs_encode_forward(flags, n, r.side_zero_prob, r.side_payload);
   } else {
     // flags[0..n) = orientation values (1 = false, 2 = true) in order, scalars[1] = forward transitions; the delta bits
     // bits[k] = (o[k] == o[k+1]), o[len] = true, are formed inside the coder's loop
@@ -919,6 +920,17 @@ void MeshJob::encode_side_stream_pair(size_t ia, size_t ib) {
     return View{r.side + 8, n, r.side_zero_prob, normal};
   };
   const View a = view(ia), b = view(ib);
+  {  // a flip stream without a single flip is coded by cycle jumps; the other stream then has the loop to itself
+    uint32_t sa[2], sb[2];
+    memcpy(sa, results_[ia].side, 8);
+    memcpy(sb, results_[ib].side, 8);
+    const bool za = a.normal && sa[1] == 0, zb = b.normal && sb[1] == 0;
+    if (za || zb) {
+      if (za) rabs_encode_zero_run(a.n, a.p0, results_[ia].side_payload); else encode_side_stream(ia);
+      if (zb) rabs_encode_zero_run(b.n, b.p0, results_[ib].side_payload); else encode_side_stream(ib);
+      return;
+    }
+  }
   auto bit = [](const View& v) {
     const uint8_t* f = v.flags;
     const size_t n = v.n;
@@ -935,7 +947,8 @@ void MeshJob::encode_side_stream_from_flags(size_t att, const uint8_t* flags, si
     for (size_t k = 0; k < n; ++k) ones += flags[k] != 0;
     r.side_count = (uint32_t)n;
     r.side_zero_prob = side_stream_zero_prob(n - ones, (float)n);
-    rabs_encode_forward(flags, n, r.side_zero_prob, r.side_payload);
+    if (ones == 0) rabs_encode_zero_run(n, r.side_zero_prob, r.side_payload);
+    else rabs_encode_forward(flags, n, r.side_zero_prob, r.side_payload);
     return;
   }
   U8Array o(n);  // the orientation values that exist, in order
@@ -1031,6 +1044,8 @@ void MeshJob::download(DeviceContext& ctx) {
 // ---------------------------------------------------------------------------------------
 void MeshJob::assemble(std::vector<uint8_t>& out) {
   ByteSink w;
+  w.data.swap(out);  // a caller that keeps its vector across steps (resident sessions) keeps the storage too
+  w.data.clear();
   size_t total = head_.size() + 64;
   for (const AttrResult& r : results_) total += (size_t)r.stats.table_bytes + r.stats.payload_bytes + r.side_payload.size() + r.side_bytes_len + 64;
   w.data.reserve(total);
