@@ -9,6 +9,7 @@
 #include "../include/dxo.h"
 #include "orc_attribute.hpp"
 #include "orc_decode.hpp"
+#include "orc_inverse.hpp"
 #include "orc_mesh.hpp"
 
 using namespace orc;
@@ -322,6 +323,24 @@ int orc_decode_symbols(const uint8_t* buf, uint64_t len, uint64_t n, uint32_t* o
   return guarded([&] { size_t pos = 0; auto v = decode_symbols_direct(buf, len, n, pos); memcpy(out, v.data(), n * 4); *consumed = pos; });
 }
 // Traverser on the universal / attribute tables with literal stack removal toggled
+// The inverse of the attribute path (orc_inverse.hpp): decodes `drc` against `mesh`. counts: 3 + 5 per attribute
+// ([0] attributes, [1] first differing byte of header + connectivity or ~0, [2] bytes consumed; per attribute: values
+// checked, mismatches, inconsistent writes, not invertible, unreferenced values); errors: per attribute max |dequantised -
+// original| and its bound (0, 0 where the attribute is not coordinate-quantised).
+int orc_decode_check(const dxo_mesh* mesh, const dxo_config* cfg, const uint8_t* drc, uint64_t len, uint64_t* counts, double* errors, uint32_t max_attributes) {
+  return guarded([&] {
+    Mesh m = mesh_from_c(mesh);
+    OracleConfig oc = cfg_from_c(cfg, 0);
+    InverseReport rep = decode_and_check(m, oc, drc, (size_t)len);
+    counts[0] = rep.num_attributes; counts[1] = rep.prefix_mismatch_at; counts[2] = rep.consumed;
+    for (size_t i = 0; i < rep.atts.size() && i < max_attributes; ++i) {
+      const auto& a = rep.atts[i];
+      uint64_t* c = counts + 3 + 5 * i;
+      c[0] = a.values_checked; c[1] = a.mismatches; c[2] = a.inconsistent_writes; c[3] = a.not_invertible; c[4] = a.unreferenced;
+      errors[2 * i] = a.max_abs_error; errors[2 * i + 1] = a.error_bound;
+    }
+  });
+}
 int orc_zero_prob(uint64_t n0, uint64_t len, int texcoord_variant) {
   float lf = texcoord_variant ? (float)len + 0.001f : (float)len;
   return zero_prob_f32(n0, lf);

@@ -54,6 +54,8 @@ def lib():
         L.orc_encode_symbols.argtypes = [C.POINTER(C.c_uint32), C.c_uint64, C.POINTER(_capi.dxo_bytes)]
         L.orc_decode_symbols.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         L.orc_zero_prob.argtypes = [C.c_uint64, C.c_uint64, C.c_int]
+        L.orc_decode_check.argtypes = [C.POINTER(_capi.dxo_mesh), C.POINTER(_capi.dxo_config), C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint64),
+                                       C.POINTER(C.c_double), C.c_uint32]
         L.orc_to_positive_i32.argtypes = [C.c_int32]
         L.orc_to_positive_i32.restype = C.c_int32
         L.orc_oct_quantize.argtypes = [C.c_float, C.c_float, C.c_float, C.POINTER(C.c_int32), C.POINTER(C.c_int)]
@@ -277,3 +279,35 @@ def attribute_bounds(values, point_to_value=None):
     if n == 0:
         return None, None
     return np.array(mn[: v.shape[1]], np.float32), np.array(mx[: v.shape[1]], np.float32)
+
+
+def decode_check(mesh, drc, cfg=None):
+    """The inverse of the attribute path (oracle/orc_inverse.hpp): decodes `drc` causally against `mesh` and reports, per
+    attribute, how many decoded values were compared with the quantised attribute and how many differ."""
+    cm, cc = mesh.as_c(), _cfg(cfg)
+    buf = np.frombuffer(drc, dtype=np.uint8).copy()
+    counts = (C.c_uint64 * (3 + 5 * 16))()
+    errors = (C.c_double * 32)()
+    st = lib().orc_decode_check(C.byref(cm), C.byref(cc), buf.ctypes.data_as(C.POINTER(C.c_uint8)), buf.size, counts, errors, 16)
+    if st != 0:
+        raise OracleError(st)
+    n = int(counts[0])
+    rep = {"num_attributes": n, "prefix_mismatch_at": None if counts[1] == 2**64 - 1 else int(counts[1]), "consumed": int(counts[2]), "length": buf.size, "attributes": []}
+    for i in range(min(n, 16)):
+        c = counts[3 + 5 * i: 8 + 5 * i]
+        rep["attributes"].append({"values_checked": int(c[0]), "mismatches": int(c[1]), "inconsistent_writes": int(c[2]), "not_invertible": int(c[3]),
+                                  "unreferenced": int(c[4]), "max_abs_error": errors[2 * i], "error_bound": errors[2 * i + 1]})
+    return rep
+
+
+def assert_decodes(mesh, drc, cfg=None):
+    """decode(drc) reproduces every quantised attribute value of `mesh` (and the dequantised floats within half a step)."""
+    rep = decode_check(mesh, drc, cfg)
+    assert rep["prefix_mismatch_at"] is None, f"header / connectivity bytes differ at {rep['prefix_mismatch_at']}"
+    assert rep["consumed"] == rep["length"], (rep["consumed"], rep["length"])
+    assert rep["num_attributes"] == len(mesh.attributes)
+    for i, a in enumerate(rep["attributes"]):
+        assert a["values_checked"] + a["unreferenced"] == mesh.attributes[i].num_unique_values, (i, a)
+        assert a["mismatches"] == 0 and a["inconsistent_writes"] == 0, (i, a)
+        assert a["max_abs_error"] <= a["error_bound"] or a["error_bound"] == 0, (i, a)
+    return rep
