@@ -652,6 +652,12 @@ void MeshJob::upload(DeviceContext& ctx) {
     else d.quant = dalloc<int32_t>(U * qstride, s);
     if (i > 0) d.corner_vertex4 = dalloc<uint4>(ut_.num_faces, s);
     if (i > 0 && p.scheme == Scheme::Normal) d.fan_link = dalloc<uint2>(C, s);  // fan walks read one link per swing
+    // K4's fast path: {opposite, its point} links and ranks carried in the values' padding component
+    if (i == 0) rank_in_w_ = false;
+    if (i == 0 && vertex_is_point_ && p.scheme == Scheme::Parallelogram && p.port == Portabilization::Quantize && p.ncomp_q == 3 && !getenv("DXO_NO_K4_FAST")) {
+      d.fan_link = dalloc<uint2>(C, s);
+      rank_in_w_ = true;
+    }
     d.rank = dalloc<uint32_t>(V, s);
     d.symbols = dalloc<uint32_t>(M * p.ncomp_q, s);
     d.side = dalloc<uint8_t>(M, s);
@@ -669,6 +675,20 @@ void MeshJob::upload(DeviceContext& ctx) {
     d.rans_scratch = dalloc<uint8_t>(gpu::rans_scratch_bytes((uint64_t)M * p.ncomp_q), s);
     d.stats = dalloc<gpu::AttrStats>(1, s);
   }
+  // Layouts derived from the tables alone — per-face corner tuples (one 128-bit load per face in the predictors), the fan
+  // links of K5, 3-component ToBits values padded to 4 — are built here, once per mesh, not in every step.
+  gpu::launch_pad3(d_faces_, ut_.num_faces, d_faces4_, s);
+  if (!vertex_is_point_) gpu::launch_pad3(d_corner_vertex_, ut_.num_faces, d_corner_vertex4_, s);
+  for (size_t i = 0; i < plans_.size(); ++i) {
+    const AttrPlan& p = plans_[i];
+    AttrDevice& d = dev_[i];
+    if (i > 0) gpu::launch_pad3(d.corner_vertex, ut_.num_faces, d.corner_vertex4, s);
+    if (d.fan_link) gpu::launch_fan_link(d_opposite_, i == 0 ? nullptr : d.seam, d_faces_, C, d.fan_link, s);
+    if (p.port == Portabilization::ToBits && p.ncomp_q == 3) gpu::launch_pad3((const uint32_t*)d.values, p.view.num_unique, (uint4*)d.quant, s);
+  }
+  layout_launches_ = 1 + (vertex_is_point_ ? 0 : 1);
+  for (size_t i = 0; i < plans_.size(); ++i)
+    layout_launches_ += (i > 0 ? 1 : 0) + (dev_[i].fan_link ? 1 : 0) + ((plans_[i].port == Portabilization::ToBits && plans_[i].ncomp_q == 3) ? 1 : 0);
   cuda_check(cudaEventRecord(ctx.ev_join[0], s), "cudaEventRecord");
   for (int k = 1; k < 3; ++k) cuda_check(cudaStreamWaitEvent(ctx.stream[k], ctx.ev_join[0], 0), "cudaStreamWaitEvent");
   cuda_check(cudaStreamWaitEvent(ctx.copy_stream, ctx.ev_join[0], 0), "cudaStreamWaitEvent");
@@ -691,7 +711,7 @@ gpu::TableDev MeshJob::table_dev(size_t att) const {
   t.corner_point = d_faces_;
   t.corner_point4 = d_faces4_;
   t.opposite = d_opposite_;
-  t.fan_link = att == 0 ? nullptr : dev_[att].fan_link;
+  t.fan_link = dev_[att].fan_link;
   t.num_corners = ut_.num_corners;
   if (att == 0) {
     t.corner_vertex = d_corner_vertex_; t.corner_vertex4 = vertex_is_point_ ? d_faces4_ : d_corner_vertex4_; t.vertex_is_point = vertex_is_point_ ? 1 : 0;
@@ -762,15 +782,7 @@ void MeshJob::launch_graph(DeviceContext& ctx, Profile& prof) {
 void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
   const uint64_t C = ut_.num_corners;
   const uint64_t Upos = plans_[0].view.num_unique;
-  {  // shared per-face corner tuples (one 128-bit load per face in the predictors)
-    cudaStream_t s0 = ctx.stream[0];
-    prof.begin("layout_faces", 28ull * ut_.num_faces * (vertex_is_point_ ? 1 : 2), s0);
-    gpu::launch_pad3(d_faces_, ut_.num_faces, d_faces4_, s0);
-    if (!vertex_is_point_) { gpu::launch_pad3(d_corner_vertex_, ut_.num_faces, d_corner_vertex4_, s0); ++prof.launches; }
-    prof.end(s0);
-    cuda_check(cudaEventRecord(ctx.ev_layout, s0), "cudaEventRecord");
-    for (int k = 1; k < 3; ++k) cuda_check(cudaStreamWaitEvent(ctx.stream[k], ctx.ev_layout, 0), "cudaStreamWaitEvent");
-  }
+  if (device_runs <= 1) prof.launches += layout_launches_;  // issued by upload(): counted with the first step
   for (size_t i = 0; i < plans_.size(); ++i) {
     const AttrPlan& p = plans_[i];
     AttrDevice& d = dev_[i];
@@ -779,7 +791,8 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     const uint32_t M = (uint32_t)sequence_of(i).size();
     const uint64_t S = (uint64_t)M * p.ncomp_q;
     const gpu::TableDev t = table_dev(i);
-    const gpu::QuantDev q{d.quant, d.map, p.ncomp_q};
+    gpu::QuantDev q{d.quant, d.map, p.ncomp_q};
+    q.rank_in_w = (i == 0 && rank_in_w_) ? 1u : 0u;
 
     if (prof.serial && i > 0) cuda_check(cudaStreamWaitEvent(s, ctx.ev_serial, 0), "cudaStreamWaitEvent");
     gpu::init_stats(d.stats, s);
@@ -787,22 +800,12 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     cuda_check(cudaMemsetAsync(d.hist, 0, sizeof(uint32_t) * p.hist_capacity, s), "cudaMemsetAsync");
     cuda_check(cudaMemsetAsync(d.rank, 0xFF, sizeof(uint32_t) * V, s), "cudaMemsetAsync");
 
-    if (i > 0) {
-      prof.begin("layout_attribute", 28ull * ut_.num_faces + (d.fan_link ? 17 * C : 0), s);
-      gpu::launch_pad3(d.corner_vertex, ut_.num_faces, d.corner_vertex4, s);
-      if (d.fan_link) { gpu::launch_fan_link(d_opposite_, d.seam, d_faces_, C, d.fan_link, s); ++prof.launches; }
-      prof.end(s);
-    }
-    if (p.port == Portabilization::ToBits && p.ncomp_q == 3) {
-      gpu::launch_pad3((const uint32_t*)d.values, U, (uint4*)d.quant, s);
-      ++prof.launches;
-    }
     if (p.port == Portabilization::Quantize) {
       prof.begin("K1_minmax", 4 * p.ncomp_in * U, s);
       gpu::launch_minmax(d.values, U, p.ncomp_in, d.stats, s);
       prof.end(s);
       prof.begin("K2_quantize", 8 * p.ncomp_in * U, s);
-      gpu::launch_quantize(d.values, U, p.ncomp_in, p.bits, d.quant, d.stats, s);
+      gpu::launch_quantize(d.values, U, p.ncomp_in, p.bits, d.quant, d.stats, s, q.rank_in_w ? -1 : 0);
       prof.end(s);
     } else if (p.port == Portabilization::Octahedral) {
       prof.begin("K3_oct_quantize", 20 * U, s);

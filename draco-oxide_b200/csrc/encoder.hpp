@@ -201,6 +201,8 @@ class MeshJob {
   cudaGraphExec_t graph_exec_ = nullptr;
   DeviceContext* graph_ctx_ = nullptr;
   uint32_t graph_launches_ = 0;
+  uint32_t layout_launches_ = 0;  // pad3 / fan-link kernels issued by upload()
+  bool rank_in_w_ = false;        // position attribute: K4's fast path (see gpu::QuantDev::rank_in_w)
   cudaEvent_t ev_graph_done_ = nullptr;
   uint64_t graph_d2h_bytes_ = 0;
   bool capturing_ = false;

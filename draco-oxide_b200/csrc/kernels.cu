@@ -160,7 +160,7 @@ void launch_minmax(const float* values, uint64_t num_values, uint32_t ncomp, Att
 // stored with the padded stride of load_q (N = 3 -> int4).
 template <int N>
 __device__ __forceinline__ void quantize_body(const float* __restrict__ values, uint32_t bits, int32_t* __restrict__ out, AttrStats* stats,
-                                              bool writes_range, uint64_t i0, uint64_t i1, uint64_t istep) {
+                                              bool writes_range, uint64_t i0, uint64_t i1, uint64_t istep, int32_t w_init = 0) {
   float mn[N];
   float range = 0.0f;
 #pragma unroll
@@ -172,7 +172,7 @@ __device__ __forceinline__ void quantize_body(const float* __restrict__ values, 
   if (writes_range && threadIdx.x == 0) stats->range = range;
   const float maxq = (float)(unsigned long long)((1ull << bits) - 1ull);
   for (uint64_t i = i0; i < i1; i += istep) {
-    int32_t q[4] = {0, 0, 0, 0};
+    int32_t q[4] = {0, 0, 0, N == 3 ? w_init : 0};
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       const float v = __ldcs(values + i * N + k);
@@ -190,17 +190,17 @@ __device__ __forceinline__ void quantize_body(const float* __restrict__ values, 
 }
 template <int N>
 __global__ void __launch_bounds__(kThreads) quantize_kernel(const float* __restrict__ values, uint64_t num_values, uint32_t bits,
-                                                            int32_t* __restrict__ out, AttrStats* stats) {
-  quantize_body<N>(values, bits, out, stats, blockIdx.x == 0, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, num_values, (uint64_t)gridDim.x * blockDim.x);
+                                                            int32_t* __restrict__ out, AttrStats* stats, int32_t w_init) {
+  quantize_body<N>(values, bits, out, stats, blockIdx.x == 0, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, num_values, (uint64_t)gridDim.x * blockDim.x, w_init);
 }
 
-void launch_quantize(const float* values, uint64_t num_values, uint32_t ncomp, uint32_t bits, int32_t* out, AttrStats* stats, cudaStream_t s) {
+void launch_quantize(const float* values, uint64_t num_values, uint32_t ncomp, uint32_t bits, int32_t* out, AttrStats* stats, cudaStream_t s, int32_t w_init) {
   const int g = grid_for(num_values, kThreads * 2);
   switch (ncomp) {
-    case 1: quantize_kernel<1><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats); break;
-    case 2: quantize_kernel<2><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats); break;
-    case 3: quantize_kernel<3><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats); break;
-    default: quantize_kernel<4><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats); break;
+    case 1: quantize_kernel<1><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats, 0); break;
+    case 2: quantize_kernel<2><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats, 0); break;
+    case 3: quantize_kernel<3><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats, w_init); break;
+    default: quantize_kernel<4><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats, 0); break;
   }
 }
 
@@ -269,7 +269,9 @@ __device__ __forceinline__ void seq_prepare_body(const uint32_t* __restrict__ se
   int32_t mn = 0x7FFFFFFF, mx = (int32_t)0x80000000;
   for (uint32_t i = i0; i < i1; i += istep) {
     const uint32_t c = ld_stream(seq + i);
-    rank[__ldg(t.corner_vertex + c)] = i;
+    const uint32_t vtx = __ldg(t.corner_vertex + c);
+    if (q.rank_in_w) const_cast<int32_t*>(q.values)[4 * (size_t)vtx + 3] = (int32_t)i;  // vertex == value index on this path
+    else rank[vtx] = i;
     if (want_minmax) {
       const uint32_t vi = value_index(q, __ldg(t.corner_point + c));
       int32_t o[4];
@@ -345,27 +347,60 @@ __device__ __forceinline__ void predict_parallelogram_body(const uint32_t* __res
   for (uint32_t i = i0; i < i1; i += istep) {
     const uint32_t c = ld_stream(seq + i);
     int32_t pred[N];
-    bool have = false;
+    if (N == 3 && q.rank_in_w && t.fan_link) {
+      // Fast path (no point map, seams or splits: point == vertex == value index). The kernel is bound by L1 wavefronts —
+      // every scattered gather of a warp costs up to 32 of them — so the number of gathers per element is what counts:
+      // the link array delivers the opposite corner together with its point, and the int4 value entries carry their
+      // vertex's rank in w. Six gathers instead of ten.
+      const uint2 l = __ldg(t.fan_link + c);
+      const Tri pts = load_tri(t.corner_point4, c);
+      const int4* vals = reinterpret_cast<const int4*>(q.values);
+      const int4 a = __ldg(vals + pts.next), b = __ldg(vals + pts.prev), self = __ldg(vals + pts.self);
+      const int4 d = __ldg(vals + (l.x != kNoneDev ? l.y : pts.self));
+      if (l.x != kNoneDev && (uint32_t)d.w < i && (uint32_t)a.w < i && (uint32_t)b.w < i) {
+        pred[0] = (int32_t)((uint32_t)a.x + (uint32_t)b.x - (uint32_t)d.x);
+        pred[1] = (int32_t)((uint32_t)a.y + (uint32_t)b.y - (uint32_t)d.y);
+        pred[2] = (int32_t)((uint32_t)a.z + (uint32_t)b.z - (uint32_t)d.z);
+      } else if (i == 0) {
+        pred[0] = pred[1] = pred[2] = 0;
+      } else {  // value of the vertex sequenced just before (left_most_corner(last_v))
+        const uint32_t last_v = __ldg(t.corner_vertex + __ldg(seq + i - 1));
+        const int4 p = __ldg(vals + __ldg(t.corner_point + __ldg(t.left_most + last_v)));
+        pred[0] = p.x; pred[1] = p.y; pred[2] = p.z;
+      }
+      const int32_t orig3[3] = {self.x, self.y, self.z};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const uint32_t s = wrapped_symbol(orig3[k], pred[k], w);
+        symbols[(uint64_t)i * 3 + k] = s;
+        nz += s != 0; mxs = max(mxs, s); err |= (s & 0x80000000u) ? kErrNegativeSymbol : 0u;
+      }
+      continue;
+    }
     const uint32_t o = opp_of(t, c);
     const Tri pts = load_tri(t.corner_point4, c);  // points of c, next(c), prev(c): one 128-bit load
-    if (o != kNoneDev) {
-      // without non-manifold splits / seams / point maps a corner's vertex is its point: skip the vertex tuples
-      const Tri vts = t.vertex_is_point ? pts : load_tri(t.corner_vertex4, c);
-      const uint32_t ov = t.vertex_is_point ? __ldg(t.corner_point + o) : __ldg(t.corner_vertex + o);
-      const uint32_t r0 = __ldg(rank + ov), r1 = __ldg(rank + vts.next), r2 = __ldg(rank + vts.prev);
-      if (r0 < i && r1 < i && r2 < i) {
-        int32_t qa[N], qb[N], qd[N];
-        load_q<N>(q, value_index(q, pts.next), qa);
-        load_q<N>(q, value_index(q, pts.prev), qb);
-        load_q<N>(q, value_index(q, t.vertex_is_point ? ov : __ldg(t.corner_point + o)), qd);
-#pragma unroll
-        for (int k = 0; k < N; ++k) pred[k] = (int32_t)((uint32_t)qa[k] + (uint32_t)qb[k] - (uint32_t)qd[k]);
-        have = true;
-      }
-    }
-    if (!have) previous_value<N>(seq, i, t, q, pred);
-    int32_t orig[N];
+    // The gathers are latency-bound, so nothing waits for the rank test: the three values of the parallelogram are
+    // requested together with the ranks (a corner without an opposite reads its own entries instead; the result is then
+    // discarded). Dependent levels per element: seq -> {opposite, tuples} -> {ranks, values of next / prev / self, the
+    // opposite's vertex} -> {its rank, its value}.
+    const uint32_t os = o != kNoneDev ? o : c;
+    // without non-manifold splits / seams / point maps a corner's vertex is its point: skip the vertex tuples
+    const Tri vts = t.vertex_is_point ? pts : load_tri(t.corner_vertex4, c);
+    const uint32_t op = __ldg(t.corner_point + os);
+    const uint32_t ov = t.vertex_is_point ? op : __ldg(t.corner_vertex + os);
+    const uint32_t r1 = __ldg(rank + vts.next), r2 = __ldg(rank + vts.prev);
+    int32_t qa[N], qb[N], qd[N], orig[N];
+    load_q<N>(q, value_index(q, pts.next), qa);
+    load_q<N>(q, value_index(q, pts.prev), qb);
     load_q<N>(q, value_index(q, pts.self), orig);
+    const uint32_t r0 = __ldg(rank + ov);
+    load_q<N>(q, value_index(q, op), qd);
+    if (o != kNoneDev && r0 < i && r1 < i && r2 < i) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) pred[k] = (int32_t)((uint32_t)qa[k] + (uint32_t)qb[k] - (uint32_t)qd[k]);
+    } else {
+      previous_value<N>(seq, i, t, q, pred);
+    }
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       const uint32_t s = wrapped_symbol(orig[k], pred[k], w);
@@ -441,7 +476,7 @@ __global__ void __launch_bounds__(kThreads) fan_link_kernel(const uint32_t* __re
                                                             const uint32_t* __restrict__ corner_point, uint64_t n, uint2* __restrict__ out) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
-    const uint32_t o = __ldcs(seam + c) ? kNoneDev : __ldcs(opposite + c);
+    const uint32_t o = (seam && __ldcs(seam + c)) ? kNoneDev : __ldcs(opposite + c);
     out[c] = make_uint2(o, o == kNoneDev ? 0u : __ldg(corner_point + o));
   }
 }

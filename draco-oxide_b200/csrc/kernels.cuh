@@ -45,7 +45,7 @@ struct TableDev {
   const uint32_t* corner_vertex;  // attribute (or universal) vertex of each corner
   const uint4* corner_point4;     // per face {p0, p1, p2, -}: one 128-bit load per corner triple
   const uint4* corner_vertex4;    // per face {v0, v1, v2, -}
-  const uint2* fan_link;  // optional: per corner {opposite with seam edges set to none, point of that corner} (fan walks of K5)
+  const uint2* fan_link;  // optional: per corner {opposite with seam edges set to none, point of that corner} (fan walks of K5, K4's fast path)
   int vertex_is_point;            // corner_vertex == corner_point (no point map, seams or splits): vertex tuples are skipped
   const uint32_t* opposite;       // universal opposite corners
   const uint8_t* seam;            // nullptr for the universal table
@@ -60,11 +60,15 @@ struct QuantDev {
   const int32_t* values;
   const uint32_t* map;  // nullptr = identity
   uint32_t num_components;
+  // 3-component values are stored as int4: when value index == vertex index (no point map, no seams, no splits) the unused
+  // w component carries the vertex's rank in the sequence, so that a value gather delivers the rank test's operand as well
+  uint32_t rank_in_w = 0;
 };
 
 // ---- K1/K2: coordinate-wise quantization (quantization_coordinate_wise.rs:24-117) ----
 void launch_minmax(const float* values, uint64_t num_values, uint32_t ncomp, AttrStats* stats, cudaStream_t s);
-void launch_quantize(const float* values, uint64_t num_values, uint32_t ncomp, uint32_t bits, int32_t* out, AttrStats* stats, cudaStream_t s);
+// w_init: what the padding component of 3-component values is set to (0, or 0xFFFFFFFF = "not in the sequence" with rank_in_w)
+void launch_quantize(const float* values, uint64_t num_values, uint32_t ncomp, uint32_t bits, int32_t* out, AttrStats* stats, cudaStream_t s, int32_t w_init = 0);
 void launch_fan_link(const uint32_t* opposite, const uint8_t* seam, const uint32_t* corner_point, uint64_t n, uint2* out, cudaStream_t s);
 void launch_pad3(const uint32_t* in, uint64_t n_tuples, uint4* out, cudaStream_t s);  // 3-wide -> 16-byte tuples
 // ---- K3: octahedral normal quantization (octahedral_quantization.rs:49-64) ----
