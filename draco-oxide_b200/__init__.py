@@ -96,6 +96,31 @@ def encode_batch(meshes, cfg=None, first_gpu=0, num_gpus=1, return_statuses=Fals
     return res
 
 
+def encode_glb(meshes, cfg=None, streams=None, first_gpu=0, num_gpus=1):
+    """The transcoder's output side (io/gltf/encode.rs:932-1097, :362-415): one GLB holding every mesh as a
+    KHR_draco_mesh_compression primitive. streams: already encoded .drc bytes per mesh, or None to encode here
+    (one dxo_encode_batch call)."""
+    cfg = cfg or Config.default()
+    L = _capi.lib()
+    n = len(meshes)
+    cms = [m.as_c() for m in meshes]
+    arr = (_capi.dxo_mesh * max(n, 1))(*cms)
+    cc = cfg.as_c()
+    out = _capi.dxo_bytes()
+    sarr, keep = None, []
+    if streams is not None:
+        sarr = (_capi.dxo_bytes * max(n, 1))()
+        for i, b in enumerate(streams):
+            buf = (C.c_uint8 * max(len(b), 1)).from_buffer_copy(b if b else b"\0")
+            keep.append(buf)
+            sarr[i].data = C.cast(buf, C.POINTER(C.c_uint8))
+            sarr[i].len = len(b)
+    st = L.dxo_encode_glb(arr, n, C.byref(cc), sarr, C.byref(out), first_gpu, num_gpus)
+    data = _take(out)
+    _check(st)
+    return data
+
+
 class Session:
     """Resident session: connectivity done on the host once, every array the
     attribute kernels read kept in HBM. run() executes the device hot path."""

@@ -73,7 +73,7 @@ EXPORTED = [
     "dxo_device_count", "dxo_session_create", "dxo_connectivity_create", "dxo_session_run_steps", "dxo_session_run", "dxo_session_destroy",
     "dxo_set_profiling", "dxo_last_timing", "dxo_session_set_trace", "dxo_session_trace_get",
     "dxo_corner_table_opposites", "dxo_encode_symbols",
-    "dxo_mesh_build", "dxo_built_mesh_view", "dxo_built_mesh_free", "dxo_dedup_values", "dxo_attribute_bounds",
+    "dxo_mesh_build", "dxo_built_mesh_view", "dxo_built_mesh_free", "dxo_dedup_values", "dxo_attribute_bounds", "dxo_encode_glb",
 ]
 
 _lib = None
@@ -137,5 +137,7 @@ def lib():
     L.dxo_dedup_values.restype = C.c_int
     L.dxo_attribute_bounds.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.dxo_attribute_bounds.restype = C.c_int
+    L.dxo_encode_glb.argtypes = [C.POINTER(dxo_mesh), C.c_size_t, C.POINTER(dxo_config), C.POINTER(dxo_bytes), C.POINTER(dxo_bytes), C.c_int, C.c_int]
+    L.dxo_encode_glb.restype = C.c_int
     _lib = L
     return L

@@ -192,6 +192,25 @@ int dxo_encode_batch(const dxo_mesh* meshes, size_t n, const dxo_config* cfg, dx
   return st != DXO_OK ? st : first_error;
 }
 
+int dxo_encode_glb(const dxo_mesh* meshes, size_t n, const dxo_config* cfg, const dxo_bytes* streams, dxo_bytes* glb_out, int first_gpu, int num_gpus) {
+  if (!glb_out || (!meshes && n)) return DXO_ERR_INVALID_ARGUMENT;
+  glb_out->data = nullptr; glb_out->len = 0;
+  std::vector<dxo_bytes> own;
+  int st = DXO_OK;
+  if (!streams) {  // encode here: one batch call
+    own.assign(n, dxo_bytes{nullptr, 0});
+    st = dxo_encode_batch(meshes, n, cfg, own.data(), nullptr, first_gpu, num_gpus);
+    streams = own.data();
+  }
+  if (st == DXO_OK) st = guarded([&] {
+    std::vector<uint8_t> glb;
+    assemble_glb(meshes, streams, n, glb);
+    if (int s2 = give(glb, glb_out)) throw Error(s2, "out of memory");
+  });
+  for (dxo_bytes& b : own) dxo_free_bytes(&b);
+  return st;
+}
+
 void dxo_free_bytes(dxo_bytes* b) {
   if (b && b->data) { free(b->data); b->data = nullptr; b->len = 0; }
 }

@@ -25,6 +25,8 @@ void* pinned_block_take(size_t bytes, size_t* capacity);
 void pinned_block_give(void* p, size_t capacity);
 // one mesh through the per-mesh path (capi.cpp)
 void encode_one_mesh(const dxo_mesh* mesh, const dxo_config& cfg, std::vector<uint8_t>& bytes, dxo_timing& tm, bool parallel_host);
+// GLB assembly around the batch entry (glb.cpp)
+void assemble_glb(const dxo_mesh* meshes, const dxo_bytes* streams, size_t n, std::vector<uint8_t>& out);
 // the batch entry (batch.cpp): groups of meshes through segmented launches, sharded over GPUs
 void encode_batch_grouped(const dxo_mesh* meshes, size_t n, const dxo_config& cfg, dxo_bytes* outs, int* statuses, int first_gpu, int num_gpus);
 

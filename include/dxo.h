@@ -246,6 +246,16 @@ int dxo_dedup_values(const void* values, uint64_t n, uint32_t component_type, ui
 int dxo_attribute_bounds(const float* values, uint64_t num_values, uint32_t num_components, const uint32_t* point_to_value,
                          uint64_t num_points, int device, float* out_min, float* out_max);
 
+/* ---- GLB assembly around the batch entry ----
+ * What the reference's glTF writer does with every encoded primitive (io/gltf/encode.rs:932-1097 add_draco_mesh_internal,
+ * :362-415 write_glb_format): the Draco streams go into the GLB BIN chunk (each padded to 4 bytes, one bufferView per
+ * primitive), indices and POSITION / NORMAL / TEXCOORD_0 get placeholder accessors (POSITION with its true bounds), every
+ * primitive carries KHR_draco_mesh_compression {bufferView, attributes}. streams[i] = the stream of meshes[i] (NULL: the
+ * primitives are encoded here with dxo_encode_batch on GPUs [first_gpu, first_gpu + num_gpus)). The scene is the minimal
+ * one (a mesh and a node per primitive); glTF input parsing, materials and textures stay with the caller. */
+int dxo_encode_glb(const dxo_mesh* meshes, size_t n, const dxo_config* cfg, const dxo_bytes* streams, dxo_bytes* glb_out,
+                   int first_gpu, int num_gpus);
+
 #ifdef __cplusplus
 }
 #endif
