@@ -138,12 +138,13 @@ def oracle_stage_split(orc, mesh):
 
 
 def config4_shard(n_meshes, rank, world):
-    """This rank's primitives of config 4: longest first, dealt round-robin over the ranks."""
+    """This rank's primitives of config 4: the deterministic longest-processing-time-first assignment of
+    draco_oxide_b200.sharding over the ranks, on the vertex counts (known before the meshes exist)."""
     import numpy as np
-    from draco_oxide_b200 import synth
+    from draco_oxide_b200 import sharding, synth
     counts = synth.batch_vertex_counts()[:n_meshes]
-    order = np.argsort(-counts, kind="stable")
-    mine = order[rank::world]
+    mine = np.asarray(sharding.my_shard(counts, rank, world), dtype=np.int64)
+    mine = mine[np.argsort(-counts[mine], kind="stable")]  # longest first inside the shard as well
     procs = max(1, min(16, host_threads() // max(1, world)))
     # a shard is not a consecutive range of primitives: generate by index
     import multiprocessing as mp
@@ -209,7 +210,7 @@ def config4_block(args, shard, rank, world, local_rank, dist, torch, dxo, with_c
     mean = sum(times) / len(times)
     block = {
         "workload": f"config4: {int(tot[3])} synthetic glTF primitives (vertex counts log-uniform in [1k, 100k], alternating grid patches / tori with uv seams), "
-                    f"{int(tot[2])} vertices, through dxo_encode_batch; primitives dealt longest-first round-robin over {world} rank(s), one GPU each",
+                    f"{int(tot[2])} vertices, through dxo_encode_batch; primitives assigned longest-processing-time-first to {world} rank(s) (draco_oxide_b200.sharding), one GPU each",
         "scaling": "strong", "n_gpus": world, "reps": reps,
         "e2e": {"value": tot[2] / mean / 1e6, "unit": "Mvertices/s", "best": tot[2] / best / 1e6, "meshes_per_s": tot[3] / mean, "ms_per_batch": 1e3 * mean,
                 "h2d_bytes_per_batch": int(tot[0]), "d2h_bytes_per_batch": int(tot[1]), "times_s": times,

@@ -308,7 +308,7 @@ void GroupRunner::stage0_copy_inputs(GroupMesh& m) {
     for (size_t i = 0; i < job.plans_.size(); ++i) {
       const AttrView& v = job.plans_[i].view;
       if (v.num_points <= max_p) throw Error(DXO_ERR_INVALID_ARGUMENT, i == 0 ? "face references a point outside the position attribute" : "face references a point outside an attribute");
-      memcpy(hp<uint8_t>(m.atts[i].values), v.raw->values, m.atts[i].value_bytes);
+      memcpy(hp<uint8_t>(m.atts[i].values), job.plans_[i].values32, m.atts[i].value_bytes);
       if (v.map) {
         const uint32_t mx = copy_max_u32(hp<uint32_t>(m.atts[i].map), v.map, v.num_points);
         if (v.num_points && mx >= v.num_unique) throw Error(DXO_ERR_INVALID_ARGUMENT, "point_to_value entry out of range");

@@ -368,7 +368,12 @@ int dxo_encode_symbols(const uint32_t* symbols, uint64_t n, int device, dxo_byte
     if (mx >= (1u << 22)) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "alphabet too large");
     const uint32_t cap = mx + 2;
     uint32_t *d_sym, *d_hist, *d_work; uint4* d_tab; uint8_t *d_tb, *d_pay; gpu::AttrStats* d_st;
-    auto alloc = [&](void** p, size_t b) { cuda_check(cudaMallocAsync(p, b, s), "cudaMallocAsync"); };
+    // every block and event is released on all paths, the error paths included
+    struct Scratch {
+      cudaStream_t s; std::vector<void*> blocks; std::vector<cudaEvent_t> events;
+      ~Scratch() { for (void* p : blocks) cudaFreeAsync(p, s); for (cudaEvent_t e : events) cudaEventDestroy(e); cudaStreamSynchronize(s); cudaGetLastError(); }
+    } scratch{s, {}, {}};
+    auto alloc = [&](void** p, size_t b) { cuda_check(cudaMallocAsync(p, b, s), "cudaMallocAsync"); scratch.blocks.push_back(*p); };
     alloc((void**)&d_sym, n * 4); alloc((void**)&d_hist, cap * 4ull); alloc((void**)&d_work, cap * 12ull); alloc((void**)&d_tab, (cap + 1) * 16ull);
     alloc((void**)&d_tb, cap * 3ull + 16); alloc((void**)&d_pay, n * 3 + 16); alloc((void**)&d_st, sizeof(gpu::AttrStats));
     void* d_scr; alloc(&d_scr, gpu::rans_scratch_bytes(n));
@@ -379,7 +384,7 @@ int dxo_encode_symbols(const uint32_t* symbols, uint64_t n, int device, dxo_byte
     cuda_check(cudaMemcpyAsync(&d_st->nonzero_symbols, &nz, 4, cudaMemcpyHostToDevice, s), "H2D");
     cuda_check(cudaMemcpyAsync(&d_st->max_symbol, &mx, 4, cudaMemcpyHostToDevice, s), "H2D");
     cudaEvent_t ev[4];
-    for (auto& e : ev) cuda_check(cudaEventCreate(&e), "cudaEventCreate");
+    for (auto& e : ev) { cuda_check(cudaEventCreate(&e), "cudaEventCreate"); scratch.events.push_back(e); }
     cuda_check(cudaEventRecord(ev[0], s), "rec");
     gpu::launch_histogram(d_sym, n, d_hist, cap, d_st, s);
     cuda_check(cudaEventRecord(ev[1], s), "rec");
@@ -392,7 +397,6 @@ int dxo_encode_symbols(const uint32_t* symbols, uint64_t n, int device, dxo_byte
     cuda_check(cudaStreamSynchronize(s), "sync");
     if (kernel_ms) for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&kernel_ms[k], ev[k], ev[k + 1]);
     if (getenv("DXO_RANS_DEBUG")) fprintf(stderr, "[dxo] rANS chunks=%u chain misses=%u fixup=%u\n", gpu::rans_num_chunks(n), st.pad[0], st.pad[1]);
-    for (auto& e : ev) cudaEventDestroy(e);
     std::vector<uint8_t> tb(st.table_bytes), pay(st.payload_bytes);
     int status = DXO_OK;
     if (st.error_flags) status = (st.error_flags & gpu::kErrRansFreq) ? DXO_ERR_RANS_FREQ_TABLE : DXO_ERR_UNSUPPORTED_INPUT;
@@ -400,7 +404,6 @@ int dxo_encode_symbols(const uint32_t* symbols, uint64_t n, int device, dxo_byte
       cuda_check(cudaMemcpyAsync(tb.data(), d_tb, tb.size(), cudaMemcpyDeviceToHost, s), "D2H");
       cuda_check(cudaMemcpyAsync(pay.data(), d_pay, pay.size(), cudaMemcpyDeviceToHost, s), "D2H");
     }
-    for (void* p : {(void*)d_sym, (void*)d_hist, (void*)d_work, (void*)d_tab, (void*)d_tb, (void*)d_pay, (void*)d_st, d_scr}) cudaFreeAsync(p, s);
     cuda_check(cudaStreamSynchronize(s), "sync");
     if (status != DXO_OK) throw Error(status, "device reported an entropy coding error");
     ByteSink w;

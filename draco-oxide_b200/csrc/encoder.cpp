@@ -264,10 +264,35 @@ MeshJob::MeshJob(const dxo_mesh* mesh, const dxo_config& cfg) : mesh_(mesh), cfg
         if (a.att_type > DXO_ATT_WEIGHT) throw Error(DXO_ERR_INVALID_ARGUMENT, "unknown attribute type");
         p.scheme = Scheme::Delta; p.transform = Transform::Difference; p.port = Portabilization::Quantize; p.bits = cfg.generic_bits; break;
     }
+    p.values32 = a.values;
     if (p.port == Portabilization::ToBits) {
       if (component_size(a.component_type) != 4) throw Error(DXO_ERR_UNSUPPORTED_DATA_TYPE, "ToBits attributes must have 4-byte components");
     } else if (a.component_type != DXO_F32) {
-      throw Error(DXO_ERR_UNSUPPORTED_DATA_TYPE, "quantized attributes must be f32 on this path");
+      // The reference's quantisers take every component type through DataValue::to_f64 and `as f32`
+      // (quantization_coordinate_wise.rs:30-90; the glTF path creates u8 / u16 / u32 attributes such as JOINTS_0 and COLOR_0).
+      // f64 normals are the exception: their octahedral map runs in f64 (geom.rs:84-88), which this path does not do.
+      if (p.port == Portabilization::Octahedral && a.component_type == DXO_F64)
+        throw Error(DXO_ERR_UNSUPPORTED_DATA_TYPE, "f64 normals are not supported (the reference maps them to the octahedron in f64)");
+      const size_t cnt = (size_t)a.num_unique_values * a.num_components;
+      p.converted.resize(cnt);
+      const uint8_t* src = (const uint8_t*)a.values;
+      for (size_t k = 0; k < cnt; ++k) {
+        double d = 0;
+        switch (a.component_type) {
+          case DXO_U8: d = (double)src[k]; break;
+          case DXO_I8: d = (double)((const int8_t*)src)[k]; break;
+          case DXO_U16: { uint16_t v; memcpy(&v, src + 2 * k, 2); d = (double)v; break; }
+          case DXO_I16: { int16_t v; memcpy(&v, src + 2 * k, 2); d = (double)v; break; }
+          case DXO_U32: { uint32_t v; memcpy(&v, src + 4 * k, 4); d = (double)v; break; }
+          case DXO_I32: { int32_t v; memcpy(&v, src + 4 * k, 4); d = (double)v; break; }
+          case DXO_U64: { uint64_t v; memcpy(&v, src + 8 * k, 8); d = (double)v; break; }
+          case DXO_I64: { int64_t v; memcpy(&v, src + 8 * k, 8); d = (double)v; break; }
+          case DXO_F64: memcpy(&d, src + 8 * k, 8); break;
+          default: break;
+        }
+        p.converted[k] = (float)d;
+      }
+      p.values32 = p.converted.data();
     }
     p.ncomp_q = p.port == Portabilization::Octahedral ? 2 : a.num_components;
     if (p.port == Portabilization::Octahedral && a.num_components != 3) throw Error(DXO_ERR_UNSUPPORTED_INPUT, "normals must have 3 components");
@@ -564,7 +589,8 @@ void MeshJob::upload_inputs(DeviceContext& ctx) {
   for (size_t i = 0; i < plans_.size(); ++i) {
     const AttrPlan& p = plans_[i];
     const dxo_attribute& a = *p.view.raw;
-    dev_[i].values = (float*)dupload((const uint32_t*)a.values, (size_t)p.view.num_unique * p.ncomp_in, s);
+    (void)a;
+    dev_[i].values = (float*)dupload((const uint32_t*)p.values32, (size_t)p.view.num_unique * p.ncomp_in, s);
     if (p.view.map) dev_[i].map = dupload(p.view.map, p.view.num_points, s);
   }
   cuda_check(cudaEventRecord(ctx.ev_inputs, s), "cudaEventRecord");

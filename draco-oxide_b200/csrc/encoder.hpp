@@ -98,6 +98,10 @@ struct AttrPlan {
   uint32_t ncomp_in = 0;      // components of the original values
   uint32_t ncomp_q = 0;       // components after portabilization
   int parent = -1;            // index of the position attribute this one predicts from
+  // 4-byte values as the kernels read them: the caller's buffer, or — for quantised attributes whose components are not
+  // f32 — their `to_f64() as f32` conversion (quantization_coordinate_wise.rs:30-90 converts every component that way)
+  const void* values32 = nullptr;
+  std::vector<float> converted;
   uint32_t hist_capacity = 0; // upper bound of the alphabet
   const TableRef* table = nullptr;
   U32Array sequence;  // empty when shared (see MeshJob::sequence_of)

@@ -3,7 +3,10 @@
 encode() is a pure function of one mesh (no shared tables, no cross-mesh statistics:
 SURVEY.md §8e), so ranks exchange nothing on the data path. Work is balanced by a
 deterministic longest-processing-time-first assignment on a per-mesh cost estimate
-(corners + points); every rank computes the same assignment from the same costs."""
+(corners + points, or the vertex count when the meshes do not exist yet); every rank computes
+the same assignment from the same costs. Used by bench.py to deal config 4's primitives to the
+ranks of a multi-GPU job (one process per GPU, each calling dxo_encode_batch on its shard); inside
+a process the batch entry orders its groups the same way (batch.cpp: longest first, shared queue)."""
 import heapq
 
 import numpy as np

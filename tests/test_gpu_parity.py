@@ -219,6 +219,24 @@ def test_batch_entry_over_all_visible_gpus(orc):
         assert got[k] == orc.encode(ms[k])
 
 
+def test_non_f32_component_types(orc):
+    """Quantised attributes whose components are not f32 (the glTF path creates u8 colours, u16 joints / texcoords): converted
+    with `to_f64() as f32` like the reference's quantiser (quantization_coordinate_wise.rs:30-90), header keeps the original type."""
+    g = synth.grid_mesh(21, 17, 12)
+    n = g.num_points()
+    rng = np.random.default_rng(8)
+    color = dxo.Attribute.from_points(rng.integers(0, 256, (n, 4)).astype(np.uint8), dxo.AttributeType.Color, dxo.AttributeDomain.Corner, (), 3)
+    joints = dxo.Attribute.from_points((np.arange(n)[:, None] // np.array([3, 5, 7, 11])).astype(np.uint16), dxo.AttributeType.Joint, dxo.AttributeDomain.Corner, (), 4)
+    weights = dxo.Attribute.from_points(rng.random((n, 2)), dxo.AttributeType.Weight, dxo.AttributeDomain.Corner, (), 5)  # f64
+    uv16 = dxo.Attribute.from_points((g.attributes[2].values * 1000).astype(np.int16), dxo.AttributeType.TextureCoordinate, dxo.AttributeDomain.Corner, (0,), 2)
+    m = dxo.Mesh(g.faces, [g.attributes[0], g.attributes[1], uv16, color, joints, weights])
+    drc = gpu_encode(m)
+    assert drc == orc.encode(m)
+    orc.assert_decodes(m, drc)
+    got = dxo.encode_batch([m, g])
+    assert got[0] == drc and got[1] == orc.encode(g)
+
+
 def test_zero_normal_error_code():
     m = synth.grid_mesh(6, 6, 3)
     n = m.attributes[1]

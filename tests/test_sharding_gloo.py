@@ -1,7 +1,7 @@
 """CPU, world_size 2 over gloo: the N>1 host logic — deterministic cost-balanced sharding of
 independent meshes, per-rank encoding, and reassembly in input order. The per-rank encoder
-here is the CPU oracle (the device path needs a GPU); the partitioning / gathering code is the
-one bench.py and the batch path use."""
+here is the CPU oracle (the device path needs a GPU); the partitioning is draco_oxide_b200.sharding,
+the function bench.py deals config 4's primitives to its ranks with (bench.config4_shard)."""
 import hashlib
 import os
 import socket
@@ -70,3 +70,22 @@ def test_shard_by_cost_properties():
         loads = [int(costs[s].sum()) for s in shards]
         assert max(loads) - min(loads) <= int(costs.max())          # LPT bound
         assert shards == sharding.shard_by_cost(costs, world)       # deterministic
+
+
+def test_bench_deals_config4_with_the_sharding_module():
+    """bench.py's per-rank shard of config 4 is sharding.my_shard: the shards of all ranks partition the primitives."""
+    import importlib.util
+    from draco_oxide_b200 import sharding, synth
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    n = 64
+    counts = synth.batch_vertex_counts()[:n]
+    seen = []
+    for rank in range(4):
+        meshes, total_vertices, total = bench.config4_shard(n, rank, 4)
+        assert total == n and total_vertices == int(counts.sum())
+        mine = sharding.my_shard(counts, rank, 4)
+        assert sorted(m.num_points() for m in meshes) == sorted(synth.batch_mesh(k, int(counts[k])).num_points() for k in mine)
+        seen += mine
+    assert sorted(seen) == list(range(n))
