@@ -966,10 +966,15 @@ void encode_batch_grouped(const dxo_mesh* meshes, size_t n, const dxo_config& cf
   std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return meshes[a].num_faces > meshes[b].num_faces; });
   std::vector<std::vector<GroupMesh*>> groups;
   {
+    // A group's host stage runs one mesh per worker, so groups of very large meshes are also kept wide enough that the
+    // groups in flight can occupy the workers (up to a hard cap of corners per group: slab memory).
+    const size_t min_meshes = std::max<size_t>(1, ((size_t)num_workers + slots_per_gpu - 2) / std::max(1, slots_per_gpu - 1));
+    const uint64_t hard_cap = 72ull << 20;
     uint64_t corners = 0;
     for (size_t i : order) {
       const uint64_t c = 3ull * meshes[i].num_faces;
-      if (groups.empty() || (corners + c > group_corners && !groups.back().empty()) || groups.back().size() >= group_meshes) { groups.emplace_back(); corners = 0; }
+      const bool full = !groups.empty() && corners + c > group_corners && groups.back().size() >= min_meshes;
+      if (groups.empty() || (!groups.back().empty() && (full || corners + c > hard_cap)) || groups.back().size() >= group_meshes) { groups.emplace_back(); corners = 0; }
       groups.back().push_back(&all[i]);
       corners += c;
     }
