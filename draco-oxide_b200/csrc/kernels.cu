@@ -806,8 +806,130 @@ __global__ void __launch_bounds__(kThreads) histogram_global_kernel(const uint32
   histogram_global_body(symbols, hist, capacity, stats, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, n, (uint64_t)gridDim.x * blockDim.x);
 }
 
+// ---- K8 with bulk-asynchronous staging (TMA, 1-D `cp.async.bulk` completing on an mbarrier) ---------------------------
+// The plain kernel above walks its symbols with one dependent global load per loop iteration: 16 round trips to HBM per
+// thread are what its 14 us consist of, not bandwidth and not the shared-memory atomics. Here the copy engine brings whole
+// tiles of the symbol stream into shared memory — one elected thread arms the stage's mbarrier with the byte count and
+// issues the bulk copy; the next tile is in flight while the CTA bins the current one out of shared memory with 128-bit
+// LDS — so no register or issue slot is spent on the loads and their latency is paid once per tile, not per symbol.
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }  // init visible to the async proxy
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 16-byte aligned source / destination, size a multiple of 16
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+}  // namespace tma
+
+constexpr uint32_t kHistStageBytes = 32u << 10;  // staging area: 2 stages of 4096 symbols (plain launches) or 1 tile of 8192 (segmented)
+constexpr size_t kHistTmaSmem = kSmemBins * 4 + kHistStageBytes + 64;
+
+// Tiles first_tile, first_tile + tile_step, ... of `tile_syms` symbols each (tile_syms * 4 * stages <= kHistStageBytes); symbols is
+// 16-byte aligned. Symbols beyond the last full 16 bytes of the stream are binned by plain loads.
+__device__ __forceinline__ void histogram_tma_body(const uint32_t* __restrict__ symbols, uint64_t n, uint32_t* __restrict__ hist, uint32_t capacity,
+                                                   AttrStats* stats, uint64_t first_tile, uint64_t tile_step, uint64_t num_tiles, uint32_t tile_syms,
+                                                   uint32_t stages, bool takes_tail) {
+  extern __shared__ __align__(128) uint8_t hist_smem[];
+  uint32_t* bins = reinterpret_cast<uint32_t*>(hist_smem);
+  uint32_t* stage_base = reinterpret_cast<uint32_t*>(hist_smem + kSmemBins * 4);
+  uint64_t* full = reinterpret_cast<uint64_t*>(hist_smem + kSmemBins * 4 + kHistStageBytes);
+  const uint64_t bulk_syms = n & ~3ull;  // what the bulk copies may touch
+  auto tile_count = [&](uint64_t t) -> uint32_t {  // symbols of tile t that travel by bulk copy
+    const uint64_t b = t * tile_syms;
+    return b >= bulk_syms ? 0u : (uint32_t)min((uint64_t)tile_syms, bulk_syms - b);
+  };
+  auto issue = [&](uint64_t k) {  // k-th tile of this CTA into stage k % stages (thread 0)
+    const uint64_t t = first_tile + k * tile_step;
+    const uint32_t cnt = t < num_tiles ? tile_count(t) : 0u;
+    if (!cnt) return;
+    uint64_t* bar = full + (k % stages);
+    tma::mbar_expect_tx(bar, cnt * 4u);
+    tma::bulk_load(stage_base + (size_t)(k % stages) * tile_syms, symbols + t * tile_syms, cnt * 4u, bar);
+  };
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < stages; ++s) tma::mbar_init(full + s, 1);
+    tma::fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) for (uint32_t s = 0; s < stages; ++s) issue(s);  // the first tiles travel while the bins are cleared
+  const uint32_t nb = min(stats->max_symbol + 1u, capacity);
+  for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) bins[b] = 0;
+  __syncthreads();
+  for (uint64_t k = 0;; ++k) {
+    const uint64_t t = first_tile + k * tile_step;
+    if (t >= num_tiles) break;
+    const uint32_t cnt = tile_count(t);
+    if (cnt) {
+      tma::mbar_wait(full + (k % stages), (uint32_t)((k / stages) & 1));
+      const uint4* src = reinterpret_cast<const uint4*>(stage_base + (size_t)(k % stages) * tile_syms);
+      for (uint32_t q = threadIdx.x; q < cnt / 4; q += blockDim.x) {
+        const uint4 v = src[q];
+        if (v.x < nb) atomicAdd(&bins[v.x], 1u);
+        if (v.y < nb) atomicAdd(&bins[v.y], 1u);
+        if (v.z < nb) atomicAdd(&bins[v.z], 1u);
+        if (v.w < nb) atomicAdd(&bins[v.w], 1u);
+      }
+    }
+    __syncthreads();  // everyone is done with the stage before it is refilled
+    if (threadIdx.x == 0) issue(k + stages);
+  }
+  if (takes_tail && threadIdx.x < (uint32_t)(n - bulk_syms)) {  // at most 3 symbols
+    const uint32_t s = symbols[bulk_syms + threadIdx.x];
+    if (s < nb) atomicAdd(&bins[s], 1u);
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
+    const uint32_t v = bins[b];
+    if (v) atomicAdd(hist + b, v);
+  }
+}
+constexpr uint32_t kHistTileSyms = 4096;
+__global__ void __launch_bounds__(kThreads) histogram_tma_kernel(const uint32_t* __restrict__ symbols, uint64_t n, uint32_t* __restrict__ hist,
+                                                                 uint32_t capacity, AttrStats* stats) {
+  const uint64_t num_tiles = (n + kHistTileSyms - 1) / kHistTileSyms;
+  histogram_tma_body(symbols, n, hist, capacity, stats, blockIdx.x, gridDim.x, num_tiles, kHistTileSyms, 2, blockIdx.x == 0);
+}
+static void allow_hist_smem(const void* kernel) {
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& d : done) if (d.first == kernel && d.second == dev) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHistTmaSmem);
+  done.push_back({kernel, dev});
+}
+static bool hist_use_tma() { static const bool on = getenv("DXO_NO_TMA") == nullptr; return on; }
+
 void launch_histogram(const uint32_t* symbols, uint64_t num_symbols, uint32_t* hist, uint32_t hist_capacity, AttrStats* stats, cudaStream_t s) {
-  if (hist_capacity <= kSmemBins) {
+  if (hist_capacity <= kSmemBins && hist_use_tma() && ((uintptr_t)symbols & 15) == 0) {
+    // persistent CTAs, two per SM (64 KB of shared memory each), a few tiles each so that the flush of the bins is amortised
+    const uint64_t tiles = (num_symbols + kHistTileSyms - 1) / kHistTileSyms;
+    const int g = (int)std::max<uint64_t>(1, std::min<uint64_t>(tiles, 2ull * 148));
+    allow_hist_smem((const void*)histogram_tma_kernel);
+    histogram_tma_kernel<<<g, kThreads, kHistTmaSmem, s>>>(symbols, num_symbols, hist, hist_capacity, stats);
+  } else if (hist_capacity <= kSmemBins) {
     int g = grid_for(num_symbols, kThreads * 16);
     histogram_smem_kernel<<<g, kThreads, 0, s>>>(symbols, num_symbols, hist, hist_capacity, stats);
   } else {

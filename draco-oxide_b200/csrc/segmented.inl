@@ -397,9 +397,21 @@ __global__ void __launch_bounds__(kThreads) seg_histogram_global_kernel(const At
   const AttrSeg& g = segs[tl.seg];
   histogram_global_body(g.symbols, g.hist, g.hist_capacity, g.stats, (uint64_t)tl.first + threadIdx.x, min(tl.first + kSegHistTile, g.num_symbols), kThreads);
 }
+// one tile of kSegHistTile symbols per CTA, brought in by a single bulk copy (see histogram_tma_body)
+__global__ void __launch_bounds__(kThreads) seg_histogram_tma_kernel(const AttrSeg* __restrict__ segs, const Tile* __restrict__ tiles) {
+  const Tile tl = load_tile(tiles);
+  const AttrSeg& g = segs[tl.seg];
+  const uint32_t t = tl.first / kSegHistTile;
+  histogram_tma_body(g.symbols, g.num_symbols, g.hist, g.hist_capacity, g.stats, t, 1u << 30, ((uint64_t)g.num_symbols + kSegHistTile - 1) / kSegHistTile,
+                     kSegHistTile, 1, (uint64_t)tl.first + kSegHistTile >= g.num_symbols);
+}
 void launch_seg_histogram(const AttrSeg* segs, const Tile* tiles, uint32_t num_tiles, bool smem, cudaStream_t s) {
   if (!num_tiles) return;
-  if (smem) seg_histogram_smem_kernel<<<num_tiles, kThreads, 0, s>>>(segs, tiles);
+  static_assert(kSegHistTile * 4 <= kHistStageBytes, "a segmented histogram tile must fit the staging area");
+  if (smem && hist_use_tma()) {  // the arena slots of the symbol streams are 256-byte aligned
+    allow_hist_smem((const void*)seg_histogram_tma_kernel);
+    seg_histogram_tma_kernel<<<num_tiles, kThreads, kHistTmaSmem, s>>>(segs, tiles);
+  } else if (smem) seg_histogram_smem_kernel<<<num_tiles, kThreads, 0, s>>>(segs, tiles);
   else seg_histogram_global_kernel<<<num_tiles, kThreads, 0, s>>>(segs, tiles);
 }
 
