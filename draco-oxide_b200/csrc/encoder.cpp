@@ -685,6 +685,7 @@ void MeshJob::upload(DeviceContext& ctx) {
       rank_in_w_ = true;
     }
     d.rank = dalloc<uint32_t>(V, s);
+    if (p.transform == Transform::Wrapped) d.used = dalloc<uint8_t>(U, s);
     d.symbols = dalloc<uint32_t>(M * p.ncomp_q, s);
     d.side = dalloc<uint8_t>(M, s);
     if (p.scheme == Scheme::Normal || p.scheme == Scheme::TexCoord) {
@@ -701,6 +702,16 @@ void MeshJob::upload(DeviceContext& ctx) {
     d.rans_scratch = dalloc<uint8_t>(gpu::rans_scratch_bytes((uint64_t)M * p.ncomp_q), s);
     d.stats = dalloc<gpu::AttrStats>(1, s);
   }
+  // rank / used tables of the sequences: functions of the connectivity, computed here once (see launch_sequence_tables)
+  for (size_t i = 0; i < plans_.size(); ++i) {
+    const AttrPlan& p = plans_[i];
+    AttrDevice& d = dev_[i];
+    const bool needs_rank = p.scheme == Scheme::Parallelogram || p.scheme == Scheme::TexCoord;
+    if (!needs_rank && !d.used) continue;
+    if (needs_rank) cuda_check(cudaMemsetAsync(d.rank, 0xFF, sizeof(uint32_t) * p.table->num_vertices, s), "cudaMemsetAsync");
+    if (d.used) cuda_check(cudaMemsetAsync(d.used, 0, p.view.num_unique, s), "cudaMemsetAsync");
+    gpu::launch_sequence_tables(d.seq, (uint32_t)sequence_of(i).size(), table_dev(i), d.map, needs_rank ? d.rank : nullptr, d.used, s);
+  }
   // Layouts derived from the tables alone — per-face corner tuples (one 128-bit load per face in the predictors), the fan
   // links of K5, 3-component ToBits values padded to 4 — are built here, once per mesh, not in every step.
   gpu::launch_pad3(d_faces_, ut_.num_faces, d_faces4_, s);
@@ -713,6 +724,7 @@ void MeshJob::upload(DeviceContext& ctx) {
     if (p.port == Portabilization::ToBits && p.ncomp_q == 3) gpu::launch_pad3((const uint32_t*)d.values, p.view.num_unique, (uint4*)d.quant, s);
   }
   layout_launches_ = 1 + (vertex_is_point_ ? 0 : 1);
+  for (size_t i = 0; i < plans_.size(); ++i) layout_launches_ += (plans_[i].scheme == Scheme::Parallelogram || plans_[i].scheme == Scheme::TexCoord || dev_[i].used) ? 1 : 0;
   for (size_t i = 0; i < plans_.size(); ++i)
     layout_launches_ += (i > 0 ? 1 : 0) + (dev_[i].fan_link ? 1 : 0) + ((plans_[i].port == Portabilization::ToBits && plans_[i].ncomp_q == 3) ? 1 : 0);
   cuda_check(cudaEventRecord(ctx.ev_join[0], s), "cudaEventRecord");
@@ -824,14 +836,14 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     gpu::init_stats(d.stats, s);
     ++prof.launches;
     cuda_check(cudaMemsetAsync(d.hist, 0, sizeof(uint32_t) * p.hist_capacity, s), "cudaMemsetAsync");
-    cuda_check(cudaMemsetAsync(d.rank, 0xFF, sizeof(uint32_t) * V, s), "cudaMemsetAsync");
+    const bool wrapped = p.transform == Transform::Wrapped;
 
     if (p.port == Portabilization::Quantize) {
       prof.begin("K1_minmax", 4 * p.ncomp_in * U, s);
       gpu::launch_minmax(d.values, U, p.ncomp_in, d.stats, s);
       prof.end(s);
       prof.begin("K2_quantize", 8 * p.ncomp_in * U, s);
-      gpu::launch_quantize(d.values, U, p.ncomp_in, p.bits, d.quant, d.stats, s, q.rank_in_w ? -1 : 0);
+      gpu::launch_quantize(d.values, U, p.ncomp_in, p.bits, d.quant, d.stats, s, q.rank_in_w ? -1 : 0, wrapped ? d.used : nullptr, q.rank_in_w ? d.rank : nullptr);
       prof.end(s);
     } else if (p.port == Portabilization::Octahedral) {
       prof.begin("K3_oct_quantize", 20 * U, s);
@@ -841,10 +853,9 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     if (i == 0) cuda_check(cudaEventRecord(ctx.ev_pos_ready, s), "cudaEventRecord");
     if (p.parent >= 0) cuda_check(cudaStreamWaitEvent(s, ctx.ev_pos_ready, 0), "cudaStreamWaitEvent");
 
-    const bool wrapped = p.transform == Transform::Wrapped;
-    if (p.scheme == Scheme::Parallelogram || p.scheme == Scheme::TexCoord) {
-      prof.begin("seq_prepare", 4ull * M + 4 * V + (wrapped ? 4ull * p.ncomp_q * U : 0), s);
-      gpu::launch_seq_prepare(d.seq, M, t, q, d.rank, wrapped, d.stats, s);
+    if (wrapped && p.port != Portabilization::Quantize) {  // ToBits: the values are what they are, only their bounds are needed
+      prof.begin("wrap_minmax", 4ull * p.ncomp_q * U + U, s);
+      gpu::launch_wrap_minmax(d.quant, U, p.ncomp_q, p.ncomp_q == 3 ? 4 : p.ncomp_q, d.used, d.stats, s);
       prof.end(s);
     }
     switch (p.scheme) {

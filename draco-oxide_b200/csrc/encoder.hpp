@@ -115,6 +115,7 @@ struct AttrDevice {
   uint8_t* side_out = nullptr; void* side_scratch = nullptr; size_t side_scratch_bytes = 0;  // [8-byte scalars][flags (+1)] for the host coder
   // intermediates / outputs
   int32_t* quant = nullptr; uint32_t *rank = nullptr, *symbols = nullptr, *hist = nullptr, *work = nullptr;
+  uint8_t* used = nullptr;  // per value: a sequence element refers to it (WrappedDifference bounds); static per mesh, like rank
   uint8_t *side = nullptr, *table_bytes = nullptr, *payload = nullptr, *rans_scratch = nullptr; uint4* rans_table = nullptr;
   gpu::AttrStats* stats = nullptr;
   uint64_t payload_capacity = 0; uint32_t table_capacity = 0;

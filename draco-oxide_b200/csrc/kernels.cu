@@ -160,7 +160,9 @@ void launch_minmax(const float* values, uint64_t num_values, uint32_t ncomp, Att
 // stored with the padded stride of load_q (N = 3 -> int4).
 template <int N>
 __device__ __forceinline__ void quantize_body(const float* __restrict__ values, uint32_t bits, int32_t* __restrict__ out, AttrStats* stats,
-                                              bool writes_range, uint64_t i0, uint64_t i1, uint64_t istep, int32_t w_init = 0) {
+                                              bool writes_range, uint64_t i0, uint64_t i1, uint64_t istep, int32_t w_init = 0,
+                                              const uint8_t* __restrict__ used = nullptr, const uint32_t* __restrict__ rank_w = nullptr) {
+  int32_t wmn = 0x7FFFFFFF, wmx = (int32_t)0x80000000;
   float mn[N];
   float range = 0.0f;
 #pragma unroll
@@ -183,25 +185,72 @@ __device__ __forceinline__ void quantize_body(const float* __restrict__ values, 
       const long long wide = (long long)r;  // cvt.rzi.s64.f32: truncates, saturates, NaN -> 0 (Rust `as i64`)
       q[k] = (int32_t)wide;                 // wrapping `as i32`
     }
+    if (used && __ldcs(used + i)) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) { wmn = min(wmn, q[k]); wmx = max(wmx, q[k]); }
+    }
+    if (N == 3 && rank_w) q[3] = (int32_t)__ldcs(rank_w + i);
     if (N == 1) out[i] = q[0];
     else if (N == 2) reinterpret_cast<int2*>(out)[i] = make_int2(q[0], q[1]);
     else reinterpret_cast<int4*>(out)[i] = make_int4(q[0], q[1], q[2], q[3]);
   }
+  if (used) {  // warp -> CTA -> one global atomic pair per CTA
+    __shared__ int32_t s_wmn, s_wmx;
+    if (threadIdx.x == 0) { s_wmn = 0x7FFFFFFF; s_wmx = (int32_t)0x80000000; }
+    __syncthreads();
+    wmn = __reduce_min_sync(0xFFFFFFFFu, wmn);
+    wmx = __reduce_max_sync(0xFFFFFFFFu, wmx);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&s_wmn, wmn); atomicMax(&s_wmx, wmx); }
+    __syncthreads();
+    if (threadIdx.x == 0) { atomicMin(&stats->wrap_min, s_wmn); atomicMax(&stats->wrap_max, s_wmx); }
+  }
 }
 template <int N>
 __global__ void __launch_bounds__(kThreads) quantize_kernel(const float* __restrict__ values, uint64_t num_values, uint32_t bits,
-                                                            int32_t* __restrict__ out, AttrStats* stats, int32_t w_init) {
-  quantize_body<N>(values, bits, out, stats, blockIdx.x == 0, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, num_values, (uint64_t)gridDim.x * blockDim.x, w_init);
+                                                            int32_t* __restrict__ out, AttrStats* stats, int32_t w_init, const uint8_t* __restrict__ used,
+                                                            const uint32_t* __restrict__ rank_w) {
+  quantize_body<N>(values, bits, out, stats, blockIdx.x == 0, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, num_values, (uint64_t)gridDim.x * blockDim.x, w_init,
+                   used, rank_w);
 }
 
-void launch_quantize(const float* values, uint64_t num_values, uint32_t ncomp, uint32_t bits, int32_t* out, AttrStats* stats, cudaStream_t s, int32_t w_init) {
+void launch_quantize(const float* values, uint64_t num_values, uint32_t ncomp, uint32_t bits, int32_t* out, AttrStats* stats, cudaStream_t s, int32_t w_init,
+                     const uint8_t* used, const uint32_t* rank_w) {
   const int g = grid_for(num_values, kThreads * 2);
   switch (ncomp) {
-    case 1: quantize_kernel<1><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats, 0); break;
-    case 2: quantize_kernel<2><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats, 0); break;
-    case 3: quantize_kernel<3><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats, w_init); break;
-    default: quantize_kernel<4><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats, 0); break;
+    case 1: quantize_kernel<1><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats, 0, used, nullptr); break;
+    case 2: quantize_kernel<2><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats, 0, used, nullptr); break;
+    case 3: quantize_kernel<3><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats, w_init, used, rank_w); break;
+    default: quantize_kernel<4><<<g, kThreads, 0, s>>>(values, num_values, bits, out, stats, 0, used, nullptr); break;
   }
+}
+
+// rank / used tables of a sequence (static per mesh)
+__global__ void __launch_bounds__(kThreads) sequence_tables_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, const uint32_t* __restrict__ map,
+                                                                   uint32_t* __restrict__ rank, uint8_t* __restrict__ used) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t c = ld_stream(seq + i);
+    if (rank) rank[__ldg(t.corner_vertex + c)] = i;
+    if (used) { const uint32_t p = __ldg(t.corner_point + c); used[map ? __ldg(map + p) : p] = 1; }
+  }
+}
+void launch_sequence_tables(const uint32_t* seq, uint32_t n, TableDev t, const uint32_t* map, uint32_t* rank, uint8_t* used, cudaStream_t s) {
+  sequence_tables_kernel<<<grid_for(n, kThreads * 2), kThreads, 0, s>>>(seq, n, t, map, rank, used);
+}
+__global__ void __launch_bounds__(kThreads) wrap_minmax_kernel(const int32_t* __restrict__ values, uint64_t num_values, uint32_t ncomp, uint32_t stride_v,
+                                                               const uint8_t* __restrict__ used, AttrStats* stats) {
+  int32_t mn = 0x7FFFFFFF, mx = (int32_t)0x80000000;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_values; i += stride) {
+    if (!__ldcs(used + i)) continue;
+    for (uint32_t k = 0; k < ncomp; ++k) { const int32_t v = __ldcs(values + i * stride_v + k); mn = min(mn, v); mx = max(mx, v); }
+  }
+  mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+  mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+  if ((threadIdx.x & 31) == 0) { atomicMin(&stats->wrap_min, mn); atomicMax(&stats->wrap_max, mx); }
+}
+void launch_wrap_minmax(const int32_t* values, uint64_t num_values, uint32_t ncomp, uint32_t stride, const uint8_t* used, AttrStats* stats, cudaStream_t s) {
+  wrap_minmax_kernel<<<grid_for(num_values, kThreads * 8), kThreads, 0, s>>>(values, num_values, ncomp, stride, used, stats);
 }
 
 // 3-wide arrays -> 16-byte tuples: faces / corner_vertex (one tuple per face), ToBits values with 3 components.

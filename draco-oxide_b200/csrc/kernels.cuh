@@ -68,7 +68,16 @@ struct QuantDev {
 // ---- K1/K2: coordinate-wise quantization (quantization_coordinate_wise.rs:24-117) ----
 void launch_minmax(const float* values, uint64_t num_values, uint32_t ncomp, AttrStats* stats, cudaStream_t s);
 // w_init: what the padding component of 3-component values is set to (0, or 0xFFFFFFFF = "not in the sequence" with rank_in_w)
-void launch_quantize(const float* values, uint64_t num_values, uint32_t ncomp, uint32_t bits, int32_t* out, AttrStats* stats, cudaStream_t s, int32_t w_init = 0);
+// used (optional): per value, 1 when a sequence element refers to it — the quantised components of those values are folded
+//   into stats->wrap_min / wrap_max (WrappedDifference's bounds over the visited originals, wrapped_difference.rs:41-49);
+// rank_w (optional, 3 components): per value the rank that goes into the padding component (QuantDev::rank_in_w).
+void launch_quantize(const float* values, uint64_t num_values, uint32_t ncomp, uint32_t bits, int32_t* out, AttrStats* stats, cudaStream_t s, int32_t w_init = 0,
+                     const uint8_t* used = nullptr, const uint32_t* rank_w = nullptr);
+// ---- tables derived from the sequence alone (once per mesh, not per step): rank[vertex] = position in the sequence
+// (0xFFFFFFFF = absent; the caller pre-sets it) and used[value] = 1 for every value a sequence element refers to (pre-set to 0)
+void launch_sequence_tables(const uint32_t* seq, uint32_t n, TableDev t, const uint32_t* map, uint32_t* rank, uint8_t* used, cudaStream_t s);
+// WrappedDifference bounds for values that are not quantised on the device (ToBits): min / max over the used values
+void launch_wrap_minmax(const int32_t* values, uint64_t num_values, uint32_t ncomp, uint32_t stride, const uint8_t* used, AttrStats* stats, cudaStream_t s);
 void launch_fan_link(const uint32_t* opposite, const uint8_t* seam, const uint32_t* corner_point, uint64_t n, uint2* out, cudaStream_t s);
 void launch_pad3(const uint32_t* in, uint64_t n_tuples, uint4* out, cudaStream_t s);  // 3-wide -> 16-byte tuples
 // ---- K3: octahedral normal quantization (octahedral_quantization.rs:49-64) ----
