@@ -96,6 +96,11 @@ void dxo::encode_one_mesh(const dxo_mesh* mesh, const dxo_config& cfg, std::vect
   const auto t0 = Clock::now();
   MeshJob job(mesh, cfg);
   job.parallel_host = parallel_host;
+  // encodes in flight in this process: from a few on, every call keeps its host passes on its own thread
+  static std::atomic<int> in_flight{0};
+  struct InFlight { std::atomic<int>& n; int before; explicit InFlight(std::atomic<int>& a) : n(a), before(a.fetch_add(1)) {} ~InFlight() { n.fetch_sub(1); } } guard(in_flight);
+  static const int crowd = getenv("DXO_INLINE_HOST_FROM") ? atoi(getenv("DXO_INLINE_HOST_FROM")) : std::max(2, (int)std::thread::hardware_concurrency() / 4);
+  job.inline_host = parallel_host && guard.before + 1 >= crowd;
   DeviceContext& ctx = DeviceContext::get(cfg.device);
   job.build_connectivity(&ctx);
   tm.host_connectivity_ms = (float)ms_since(t0);

@@ -89,7 +89,7 @@ void UniversalTable::build(const uint32_t* faces, uint32_t nfaces, const AttrVie
   // vertex ids of the corners with the reference's range checks; large meshes split the passes over a few threads
   const uint32_t* map = pos.map;
   auto over_parts = [&](auto&& fn) -> uint32_t {  // max of fn(c0, c1) over the parts
-    if (num_corners < (1u << 20)) return fn(0u, num_corners);
+    if (num_corners < (1u << 20) || single_thread) return fn(0u, num_corners);
     constexpr uint32_t kParts = 4;
     std::future<uint32_t> parts[kParts];
     for (uint32_t k = 0; k < kParts; ++k)

@@ -48,6 +48,7 @@ struct UniversalTable {
   bool has_boundary_list = false;
   void build(const uint32_t* faces, uint32_t nfaces, const AttrView& pos, DeviceMatcher matcher = nullptr, void* matcher_user = nullptr);
   bool matched_on_device = false;
+  bool single_thread = false;  // no helper threads inside build() (many encodes in flight)
 
  private:
   void match_half_edges();

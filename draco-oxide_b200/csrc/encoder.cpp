@@ -433,10 +433,18 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
   match_ctx_ = ctx;
   dev_.assign(plans_.size(), AttrDevice{});
   const bool early_uploads = ctx != nullptr && parallel_host && !getenv("DXO_NO_EARLY_UPLOAD");
-  if (early_uploads)
+  const bool threads = !inline_host;
+  if (early_uploads && threads)
     inputs_upload_ = std::async(std::launch::async, [this, ctx] { cuda_check(cudaSetDevice(ctx->device), "cudaSetDevice"); upload_inputs(*ctx); }).share();
+  else if (early_uploads) {
+    upload_inputs(*ctx);  // asynchronous copies on the upload stream
+    std::promise<void> done;
+    done.set_value();
+    inputs_upload_ = done.get_future().share();
+  }
   if (ctx != nullptr && !getenv("DXO_NO_PINNED_TABLES")) ut_.set_memory_source(&MeshJob::pinned_source, this);
   const bool use_k12 = ctx != nullptr && nfaces >= 4096 && !getenv("DXO_NO_K12");  // tiny meshes: the launch + sync costs more than it saves
+  ut_.single_thread = inline_host;
   ut_.build(mesh_->faces, nfaces, plans_[0].view, use_k12 ? &MeshJob::device_matcher : nullptr, this);
   validate_attribute_indices(ut_.max_point);
   clk.lap("universal corner table");
@@ -465,10 +473,11 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
     // Independent host passes on their own threads: seam tables (one per attribute) next to the
     // CLERS traversal; then the per-attribute sequencers and seam streams next to the symbol packing.
     std::vector<std::future<void>> tasks;
+    auto spawn = [&](std::function<void()> fn) { if (threads) tasks.push_back(std::async(std::launch::async, std::move(fn))); else fn(); };
     auto wait_all = [&] { std::exception_ptr first; for (auto& t : tasks) { try { if (t.valid()) t.get(); } catch (...) { if (!first) first = std::current_exception(); } } tasks.clear(); if (first) std::rethrow_exception(first); };
     try {
       for (size_t i = 1; i < natt; ++i)
-        tasks.push_back(std::async(std::launch::async, [this, i, ctx, early_uploads] {
+        spawn([this, i, ctx, early_uploads] {
           StageClock c;
           if (early_uploads && !getenv("DXO_NO_K14") && device_seam_table(*ctx, i)) c.lap("  (thread) seam table (K14)");
           else {
@@ -489,13 +498,15 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
           interior_[i] = vertex_interior_flags(table_refs_[i]);
           table_refs_[i].interior = interior_[i].data();
           c.lap("  (thread) masked opposites, interior flags");
-        }));
+        });
       table_refs_[0] = table_ref(ut_);
-      tasks.push_back(std::async(std::launch::async, [this] { interior_[0] = vertex_interior_flags(table_refs_[0]); table_refs_[0].interior = interior_[0].data(); }));
+      spawn([this] { interior_[0] = vertex_interior_flags(table_refs_[0]); table_refs_[0].interior = interior_[0].data(); });
       { StageClock c; eb.traverse(); c.lap("  (main) CLERS traversal"); }
       wait_all();  // seam tables, interior flags
       clk.lap("seam tables + traversal");
-      auto seq0 = std::async(std::launch::async, [this] { StageClock c; plans_[0].sequence = attribute_sequence(table_refs_[0], eb_->corner_list()); c.lap("  (thread) position sequence"); });
+      auto seq0_fn = [this] { StageClock c; plans_[0].sequence = attribute_sequence(table_refs_[0], eb_->corner_list()); c.lap("  (thread) position sequence"); };
+      std::future<void> seq0;
+      if (threads) seq0 = std::async(std::launch::async, seq0_fn); else seq0_fn();
       // an attribute whose only seams are mesh boundaries has the universal table (same ids, opposites, left-most
       // corners), hence the position sequence: it is copied instead of recomputed
       auto shares_position_sequence = [this](size_t i) {
@@ -504,10 +515,10 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
       };
       for (size_t i = 1; i < natt; ++i) {
         if (!shares_position_sequence(i))
-          tasks.push_back(std::async(std::launch::async, [this, i] { StageClock c; plans_[i].sequence = attribute_sequence(table_refs_[i], eb_->corner_list()); c.lap("  (thread) attribute sequence"); }));
-        tasks.push_back(std::async(std::launch::async, [this, i, &eb, &seam_bytes] { StageClock c; eb.write_seam_stream(seams_[i - 1], seam_bytes[i - 1]); c.lap("  (thread) seam stream"); }));
+          spawn([this, i] { StageClock c; plans_[i].sequence = attribute_sequence(table_refs_[i], eb_->corner_list()); c.lap("  (thread) attribute sequence"); });
+        spawn([this, i, &eb, &seam_bytes] { StageClock c; eb.write_seam_stream(seams_[i - 1], seam_bytes[i - 1]); c.lap("  (thread) seam stream"); });
       }
-      tasks.push_back(std::move(seq0));
+      if (seq0.valid()) tasks.push_back(std::move(seq0));
       { StageClock c; eb.write_head(head_, seams_.size()); c.lap("  (main) connectivity head"); }
       wait_all();
       for (size_t i = 1; i < natt; ++i) if (shares_position_sequence(i)) plans_[i].shares_sequence_of = 0;

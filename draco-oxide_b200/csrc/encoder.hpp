@@ -163,6 +163,9 @@ class MeshJob {
 
   bool trace = false;
   bool parallel_host = true;  // run independent host passes on their own threads (off inside batch workers)
+  // With a device but many encodes in flight (concurrent callers): the same passes, device tables included, in order on
+  // the calling thread — a dozen helper threads per call only fight each other for the cores.
+  bool inline_host = false;
   std::map<std::string, std::vector<uint8_t>> trace_items;
   uint64_t h2d_bytes = 0, d2h_bytes = 0;
   uint64_t num_position_vertices() const { return plans_.empty() ? 0 : plans_[0].sequence.size(); }
