@@ -821,7 +821,7 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
       case Scheme::Normal: add_tiles(t_nrm, (uint32_t)k, g.n); break;
       case Scheme::TexCoord: add_tiles(t_uv, (uint32_t)k, g.n); break;
     }
-    add_tiles(p.hist_capacity <= 8192 ? t_hs : t_hg, (uint32_t)k, g.num_symbols, 8 * gpu::kSegTile);
+    add_tiles(p.hist_capacity <= gpu::kSmemHistBins ? t_hs : t_hg, (uint32_t)k, g.num_symbols, 8 * gpu::kSegTile);
   }
   // pad3 jobs run as tiles of a tiny descriptor list: reuse AttrSeg-free generic form (seg = job, first = tuple)
   std::vector<gpu::Tile> t_pad;

@@ -818,7 +818,7 @@ void launch_predict_texcoord(const uint32_t* seq, uint32_t n, TableDev t, QuantD
 // K8 — symbol histogram (symbol_coding.rs:149-157). Shared-memory bins when the
 // alphabet fits (always for the default 11/8/10 bits), warp-aggregated through
 // match_any so equal symbols inside a warp cost one atomic; global atomics otherwise.
-constexpr uint32_t kSmemBins = 8192;
+constexpr uint32_t kSmemBins = kSmemHistBins;
 
 __device__ __forceinline__ void histogram_smem_body(const uint32_t* __restrict__ symbols, uint32_t* __restrict__ hist, uint32_t capacity, AttrStats* stats,
                                                     uint64_t i0, uint64_t i1, uint64_t istep) {

@@ -10,6 +10,8 @@ namespace dxo {
 namespace gpu {
 
 constexpr uint32_t kNoneDev = 0xFFFFFFFFu;
+// alphabets up to this many symbols are counted in shared-memory bins (2 * 2^12 + 4: up to 12 quantisation bits), larger ones with global atomics
+constexpr uint32_t kSmemHistBins = 8200;
 
 // error bits accumulated on the device (AttrStats::error_flags)
 enum : uint32_t {
