@@ -190,7 +190,8 @@ def measure_config4(meshes, local_rank, reps, dist, torch, dxo):
 def config4_cpu_baseline(orc, meshes, sample_every=16):
     """The oracle on every host thread over a bounded sample of the shard (every 16th primitive of the size-sorted list)."""
     from concurrent.futures import ThreadPoolExecutor
-    sample = meshes[::sample_every] if len(meshes) >= 4 * sample_every else meshes
+    sample_every = max(1, min(sample_every, len(meshes) // 256))  # about 256 primitives, whatever the shard's size
+    sample = meshes[::sample_every]
     cores = max(1, min(64, host_threads()))
     verts = sum(m.num_points() for m in sample)
     with ThreadPoolExecutor(cores) as ex:
