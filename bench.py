@@ -161,8 +161,9 @@ def measure_config4(meshes, local_rank, reps, dist, torch, dxo):
     """The batch entry on this rank's shard: wall clock of dxo_encode_batch (host buffers in, streams out), max over ranks."""
     sampler = ClockSampler(local_rank)
     sampler.start()
-    out = dxo.encode_batch(meshes, first_gpu=local_rank, num_gpus=1)  # warm-up: slabs, pinned blocks, contexts
-    out = dxo.encode_batch(meshes, first_gpu=local_rank, num_gpus=1)
+    batch = dxo.Batch(meshes)  # the dxo_mesh[] array the C ABI takes (plain pointers into the host buffers), built once
+    out = dxo.encode_batch(batch, first_gpu=local_rank, num_gpus=1)  # warm-up: slabs, pinned blocks, contexts
+    out = dxo.encode_batch(batch, first_gpu=local_rank, num_gpus=1)
     times = []
     if dist is not None:
         dist.barrier()
@@ -172,7 +173,7 @@ def measure_config4(meshes, local_rank, reps, dist, torch, dxo):
         if dist is not None:
             dist.barrier()
         t0 = time.perf_counter()
-        out = dxo.encode_batch(meshes, first_gpu=local_rank, num_gpus=1)
+        out = dxo.encode_batch(batch, first_gpu=local_rank, num_gpus=1)
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if dist is not None:
