@@ -413,6 +413,8 @@ def main():
     if args.sessions <= 0 and default_sessions(world)[1]:
         os.environ.setdefault("DXO_BLOCKING_WAIT", "1")  # read when a thread's device context is created
         os.environ.setdefault("DXO_SIDE_INLINE", "1")
+    # one process per GPU: each rank's batch entry gets its share of the host threads, not all of them
+    os.environ.setdefault("DXO_BATCH_WORKERS", str(max(2, host_threads() // max(1, world))))
     # config 4's primitives are generated by forked numpy workers: before this process holds a CUDA context
     c4_shard = None
     if args.workload == "config4" or (args.workload == "config2" and not args.no_config4):

@@ -941,7 +941,7 @@ void encode_batch_grouped(const dxo_mesh* meshes, size_t n, const dxo_config& cf
   const char* env_w = getenv("DXO_BATCH_WORKERS");
   const int num_workers = env_w ? std::max(1, atoi(env_w)) : std::max(2, hw);
   const char* env_s = getenv("DXO_BATCH_SLOTS");
-  const int slots_per_gpu = env_s ? std::max(1, atoi(env_s)) : 4;
+  const int slots_per_gpu = env_s ? std::max(1, atoi(env_s)) : 6;  // measured on config 4 (16 host threads): 3 / 4 / 6 slots -> 132 / 150 / 159 Mvertices/s
   const char* env_c = getenv("DXO_GROUP_CORNERS");
   uint64_t group_corners = env_c ? std::max<uint64_t>(3, strtoull(env_c, nullptr, 10)) : (12ull << 20);
   const size_t group_meshes = 512;
