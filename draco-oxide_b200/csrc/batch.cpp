@@ -700,7 +700,7 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
   // A binary side stream is a serial chain of ~15 ns per bit on the device (one warp per stream): fine for the many short
   // streams of a group, which then never touch the host, but a 100k-vertex mesh's stream would take longer than all
   // other kernels of the group together — those are coded by the host workers during assembly (~1.5 ns per bit).
-  static const uint32_t device_rabs_max = getenv("DXO_DEVICE_RABS_MAX") ? (uint32_t)atoi(getenv("DXO_DEVICE_RABS_MAX")) : 16384u;
+  static const uint32_t device_rabs_max = getenv("DXO_DEVICE_RABS_MAX") ? (uint32_t)atoi(getenv("DXO_DEVICE_RABS_MAX")) : 8192u;
   const size_t out3_begin = pair_.take(0);
   for (GroupMesh* gm : act)
     for (size_t i = 0; i < gm->atts.size(); ++i) {
