@@ -137,24 +137,40 @@ def oracle_stage_split(orc, mesh):
     return {"host_ms": host, "attribute_ms": attr, "note": "one oracle encode on one thread: host = corner tables + Edgebreaker + sequencers, attribute = quantize + predict + transform + entropy + side streams"}
 
 
-def config4_shard(n_meshes, rank, world):
+class Config4Shard:
     """This rank's primitives of config 4: the deterministic longest-processing-time-first assignment of
-    draco_oxide_b200.sharding over the ranks, on the vertex counts (known before the meshes exist)."""
-    import numpy as np
-    from draco_oxide_b200 import sharding, synth
-    counts = synth.batch_vertex_counts()[:n_meshes]
-    mine = np.asarray(sharding.my_shard(counts, rank, world), dtype=np.int64)
-    mine = mine[np.argsort(-counts[mine], kind="stable")]  # longest first inside the shard as well
-    procs = max(1, min(16, host_threads() // max(1, world)))
-    # a shard is not a consecutive range of primitives: generate by index
-    import multiprocessing as mp
-    jobs = [(int(k), int(counts[k])) for k in mine]
-    if procs > 1 and len(jobs) >= 8:
-        with mp.get_context("fork").Pool(procs) as pool:
-            meshes = pool.map(synth._batch_mesh_job, jobs, chunksize=4)
-    else:
-        meshes = [synth._batch_mesh_job(j) for j in jobs]
-    return meshes, int(counts.sum()), int(counts.size)
+    draco_oxide_b200.sharding over the ranks, on the vertex counts (known before the meshes exist).
+    The numpy worker processes are forked when the object is made — before this process holds a CUDA context — and stay
+    idle until generate() is called, so that neither their memory traffic nor the ~5 GB of generated meshes sit next to the
+    measurements that come first (measured: the config-2 e2e arm loses a quarter with them resident)."""
+
+    def __init__(self, n_meshes, rank, world):
+        import multiprocessing as mp
+        import numpy as np
+        from draco_oxide_b200 import sharding, synth
+        counts = synth.batch_vertex_counts()[:n_meshes]
+        mine = np.asarray(sharding.my_shard(counts, rank, world), dtype=np.int64)
+        mine = mine[np.argsort(-counts[mine], kind="stable")]  # longest first inside the shard as well
+        # a shard is not a consecutive range of primitives: generate by index
+        self.jobs = [(int(k), int(counts[k])) for k in mine]
+        self.total_vertices, self.total_meshes = int(counts.sum()), int(counts.size)
+        procs = max(1, min(16, host_threads() // max(1, world)))
+        self.pool = mp.get_context("fork").Pool(procs) if procs > 1 and len(self.jobs) >= 8 else None
+
+    def generate(self):
+        from draco_oxide_b200 import synth
+        if self.pool is not None:
+            meshes = self.pool.map(synth._batch_mesh_job, self.jobs, chunksize=4)
+            self.pool.close()
+            self.pool.join()
+            self.pool = None
+        else:
+            meshes = [synth._batch_mesh_job(j) for j in self.jobs]
+        return meshes, self.total_vertices, self.total_meshes
+
+
+def config4_shard(n_meshes, rank, world):
+    return Config4Shard(n_meshes, rank, world).generate()
 
 
 def measure_config4(meshes, local_rank, reps, dist, torch, dxo):
@@ -418,7 +434,7 @@ def main():
     # config 4's primitives are generated by forked numpy workers: before this process holds a CUDA context
     c4_shard = None
     if args.workload == "config4" or (args.workload == "config2" and not args.no_config4):
-        c4_shard = config4_shard(args.batch_meshes, rank, world)
+        c4_shard = Config4Shard(args.batch_meshes, rank, world)
     import numpy as np
     import torch
     import draco_oxide_b200 as dxo
@@ -440,7 +456,7 @@ def main():
         torch.cuda.synchronize()
 
     if args.workload == "config4":
-        run_config4(args, c4_shard, rank, world, local_rank, dist, torch, dxo)
+        run_config4(args, c4_shard.generate(), rank, world, local_rank, dist, torch, dxo)
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -571,8 +587,9 @@ def main():
     h2d, d2h = tm["h2d_bytes"], tm["d2h_bytes"]
     T = args.e2e_callers if args.e2e_callers > 0 else max(1, min(32, host_threads() // max(1, world)))  # ~250 MB of pinned tables per caller
     e2e_steps = max(1, min(args.steps, 10))
-    e_ready, e_go = threading.Barrier(T + 1), threading.Barrier(T + 1)
+    e_ready, e_go, e_done = threading.Barrier(T + 1), threading.Barrier(T + 1), threading.Barrier(T + 1)
     e_errors = []
+    e2e_reps = 3  # the arm is host-bound and shares the box's memory system with other tenants: three passes, the median is reported
 
     def caller():
         try:
@@ -581,43 +598,51 @@ def main():
                 o = bytearray(); dxo.encode(pmesh, o, cfg)
         except Exception as e:  # noqa: BLE001
             e_errors.append(e)
-        e_ready.wait()
-        e_go.wait()
-        try:
-            for _ in range(e2e_steps):
-                o = bytearray(); dxo.encode(pmesh, o, cfg)
-            if bytes(o) != ref_bytes:
-                e_errors.append(AssertionError("end-to-end stream differs from the resident session's"))
-        except Exception as e:  # noqa: BLE001
-            e_errors.append(e)
+        for _ in range(e2e_reps):
+            e_ready.wait()
+            e_go.wait()
+            try:
+                for _ in range(e2e_steps):
+                    o = bytearray(); dxo.encode(pmesh, o, cfg)
+                if bytes(o) != ref_bytes:
+                    e_errors.append(AssertionError("end-to-end stream differs from the resident session's"))
+            except Exception as e:  # noqa: BLE001
+                e_errors.append(e)
+            e_done.wait()
 
     callers = [threading.Thread(target=caller) for _ in range(T)]
     for th in callers:
         th.start()
-    e_ready.wait()
     sampler2 = ClockSampler(local_rank)
-    sampler2.start()
-    barrier()
-    sampler2.mark_begin()
-    t0 = time.perf_counter()
-    e_go.wait()
+    e2e_times = []
+    for rep in range(e2e_reps):
+        e_ready.wait()
+        if rep == 0:
+            sampler2.start()
+        barrier()
+        if rep == 0:
+            sampler2.mark_begin()
+        t0 = time.perf_counter()
+        e_go.wait()
+        e_done.wait()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_times.append(float(t.item()))
     for th in callers:
         th.join()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
     if e_errors:
         raise e_errors[0]
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    e2e_s = sorted(e2e_times)[len(e2e_times) // 2]
     clocks_e2e = sampler2.stop()
     barrier()
     sess.close()
     # the sharded batch (config 4) on the same GPUs, before rank 0 spends its host threads on the CPU baseline
     c4 = None
     if args.workload == "config2" and not args.no_config4:
-        c4 = config4_block(args, c4_shard, rank, world, local_rank, dist, torch, dxo, with_cpu=not args.no_cpu_baseline)
+        c4 = config4_block(args, c4_shard.generate(), rank, world, local_rank, dist, torch, dxo, with_cpu=not args.no_cpu_baseline)
         c4_shard = None
 
     if rank == 0:
@@ -638,7 +663,7 @@ def main():
             "e2e": {"value": V * world * T * e2e_steps / e2e_s / 1e6, "unit": "Mvertices/s", "h2d_bytes_per_step": int(h2d) * T, "d2h_bytes_per_step": int(d2h) * T,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "meshes_per_step_per_gpu": T, "caller_threads_per_gpu": T,
                     "single_call_ms": single_call_ms, "single_call_mvertices_per_s": V / single_call_ms / 1e3,
-                    "host_connectivity_ms_per_call": host_ms / lone_calls, "steps": e2e_steps, "clocks": clocks_e2e},
+                    "host_connectivity_ms_per_call": host_ms / lone_calls, "steps": e2e_steps, "passes_s": e2e_times, "reported": "median pass", "clocks": clocks_e2e},
             "roofline": {"bound": "hbm", "kernel": dom["name"], "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
                          "frac": dom["gbs"] / peak if dom["gbs"] else None,
                          "traffic": ncu_traffic(args.workload).get(dom["name"]), "peak_source": peak_src,

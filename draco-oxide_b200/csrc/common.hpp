@@ -2,6 +2,10 @@
 // Reference paths are relative to /root/reference/draco-oxide/src/.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <cstring>
 #include <memory>
 #include <utility>
@@ -175,6 +179,41 @@ static inline uint8_t side_stream_zero_prob(uint64_t zeros, float len_as_f32) {
   if (v < 1) v = 1;
   if (v > 255) v = 255;
   return (uint8_t)v;
+}
+
+// Largest element of an index array (the range checks of faces and point maps). The library is built without -march
+// flags, so the AVX2 body is a per-function target picked at run time.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static inline uint32_t max_u32_avx2(const uint32_t* p, size_t n) {
+  __m256i m0 = _mm256_setzero_si256(), m1 = m0, m2 = m0, m3 = m0;
+  size_t i = 0;
+  for (; i + 32 <= n; i += 32) {
+    m0 = _mm256_max_epu32(m0, _mm256_loadu_si256((const __m256i*)(p + i)));
+    m1 = _mm256_max_epu32(m1, _mm256_loadu_si256((const __m256i*)(p + i + 8)));
+    m2 = _mm256_max_epu32(m2, _mm256_loadu_si256((const __m256i*)(p + i + 16)));
+    m3 = _mm256_max_epu32(m3, _mm256_loadu_si256((const __m256i*)(p + i + 24)));
+  }
+  m0 = _mm256_max_epu32(_mm256_max_epu32(m0, m1), _mm256_max_epu32(m2, m3));
+  alignas(32) uint32_t t[8];
+  _mm256_store_si256((__m256i*)t, m0);
+  uint32_t mx = 0;
+  for (int k = 0; k < 8; ++k) mx = t[k] > mx ? t[k] : mx;
+  for (; i < n; ++i) mx = p[i] > mx ? p[i] : mx;
+  return mx;
+}
+#endif
+static inline uint32_t max_u32(const uint32_t* p, size_t n) {
+#if defined(__x86_64__)
+  static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("DXO_NO_AVX2");
+  if (avx2) return max_u32_avx2(p, n);
+#endif
+  uint32_t m[4] = {0, 0, 0, 0};
+  size_t i = 0;
+  for (; i + 4 <= n; i += 4) for (int k = 0; k < 4; ++k) m[k] = p[i + k] > m[k] ? p[i + k] : m[k];
+  uint32_t mx = 0;
+  for (; i < n; ++i) mx = p[i] > mx ? p[i] : mx;
+  for (int k = 0; k < 4; ++k) mx = m[k] > mx ? m[k] : mx;
+  return mx;
 }
 
 // Binary rANS coder, precision 8, base 4096 (RabsCoder, encode/entropy/rans.rs:71-127).

@@ -98,12 +98,17 @@ void UniversalTable::build(const uint32_t* faces, uint32_t nfaces, const AttrVie
     for (auto& f : parts) mx = std::max(mx, f.get());
     return mx;
   };
-  corner_vertex.resize(num_corners);
-  uint32_t* cvw = corner_vertex.data();
+  // Without a position map the vertex ids ARE the faces' point indices: with a device matcher (which uploads them and
+  // leaves them alone) the array is the caller's own — no 12-byte-per-face copy; the sequential passes, which may
+  // relabel split vertices, get their own copy further down.
+  const bool alias_faces = !map && matcher != nullptr && num_corners > 0;
+  uint32_t* cvw = nullptr;
+  if (alias_faces) corner_vertex.adopt(const_cast<uint32_t*>(faces), num_corners);
+  else { corner_vertex.resize(num_corners); cvw = corner_vertex.data(); }
   const uint32_t max_p = over_parts([&](uint32_t c0, uint32_t c1) {
+    if (map || alias_faces) return max_u32(faces + c0, c1 - c0);
     uint32_t mx = 0;
-    if (map) { for (uint32_t c = c0; c < c1; ++c) mx = std::max(mx, faces[c]); }
-    else { for (uint32_t c = c0; c < c1; ++c) { const uint32_t p = faces[c]; cvw[c] = p; mx = std::max(mx, p); } }
+    for (uint32_t c = c0; c < c1; ++c) { const uint32_t p = faces[c]; cvw[c] = p; mx = std::max(mx, p); }
     return mx;
   });
   if (num_corners && max_p >= pos.num_points) throw Error(DXO_ERR_INVALID_ARGUMENT, "face references a point outside the position attribute");
@@ -128,15 +133,24 @@ void UniversalTable::build(const uint32_t* faces, uint32_t nfaces, const AttrVie
   bool nm = false;
   matched_on_device = false;
   has_boundary_list = false;
+  has_interior = false;
   uint32_t device_done = 0;
   if (matcher) {
     opposite.resize(num_corners);
     left_most.resize(num_vertices);
-    device_done = matcher(matcher_user, corner_vertex.data(), num_faces, num_vertices, opposite.data(), left_most.data(), &boundary_corners);
+    interior.resize(num_vertices);
+    device_done = matcher(matcher_user, corner_vertex.data(), num_faces, num_vertices, opposite.data(), left_most.data(), interior.data(), &boundary_corners);
     if (device_done & kUnusedVertices) throw Error(DXO_ERR_UNUSED_VERTICES, "mesh contains unused vertices");
     matched_on_device = (device_done & kMatchExact) != 0;
     has_boundary_list = matched_on_device && (device_done & kBoundaryListDone);  // opposite[] is final: no non-manifold split follows
+    has_interior = matched_on_device && (device_done & kLeftMostDone);
     lap(matched_on_device ? ((device_done & kLeftMostDone) ? "half edges + left-most (K12, K13)" : "half-edge matching (K12)") : "half-edge matching (K12, not exact)");
+  }
+  if (alias_faces && !(matched_on_device && (device_done & kLeftMostDone))) {  // the passes below may write vertex ids
+    HostArray<uint32_t> own;
+    own.resize(num_corners);
+    memcpy(own.data(), faces, (size_t)num_corners * 4);
+    corner_vertex = std::move(own);
   }
   if (!(matched_on_device && (device_done & kLeftMostDone))) { check_all_used(); lap("unused-vertex check"); }
   if (!matched_on_device) {
@@ -754,7 +768,11 @@ U32Array attribute_sequence(const TableRef& t, const EdgebreakerEncoder::CornerL
   const uint32_t num_corners = t.num_corners;
   static const uint32_t pf_a = getenv("DXO_PF_A") ? (uint32_t)atoi(getenv("DXO_PF_A")) : 6u, pf_b = getenv("DXO_PF_B") ? (uint32_t)atoi(getenv("DXO_PF_B")) : 12u;
   uint32_t c1 = 0, c2 = 0;  // corners of the previous two visited faces (stride prefetch, see EdgebreakerRun::traverse)
+  uint32_t faces_left = t.num_faces;
   while (top || bottom) {
+    // Every face done: whatever is left of the list and the stack names visited faces and would be skipped one by one
+    // (the whole visiting order of the traversal sits in the list: 2 M entries for a 1 M-vertex mesh).
+    if (faces_left == 0) break;
     const uint32_t c = top ? stack[--top] : bottom_list[--bottom];
     const uint32_t face = c / 3u;
     if (face_seen[face]) continue;
@@ -774,6 +792,7 @@ U32Array attribute_sequence(const TableRef& t, const EdgebreakerEncoder::CornerL
       continue;
     }
     face_seen[face] = 1;
+    --faces_left;
     if (!vertex_seen[v]) {
       emit(v, c);
       // is_on_boundary(v): swing_left(left_most_corner(v)) is None (corner_table/mod.rs:36-38)

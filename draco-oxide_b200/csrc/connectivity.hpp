@@ -28,8 +28,9 @@ struct UniversalTable {
   HostArray<uint32_t> corner_vertex;     // vertex_idx(c), non-manifold splits applied
   HostArray<uint32_t> opposite;          // kNone = boundary
   HostArray<uint32_t> left_most;         // per vertex
+  HostArray<uint8_t> interior;           // per vertex: not on a boundary; filled by the device pass (has_interior), else computed by the caller
   void set_memory_source(HostArray<uint32_t>::Source fn, void* user) {  // e.g. pinned blocks for the device passes
-    corner_vertex.set_source(fn, user); opposite.set_source(fn, user); left_most.set_source(fn, user);
+    corner_vertex.set_source(fn, user); opposite.set_source(fn, user); left_most.set_source(fn, user); interior.set_source(fn, user);
   }
 
   uint32_t swing_left(uint32_t c) const { uint32_t o = opposite[corner_next(c)]; return o == kNone ? kNone : corner_next(o); }
@@ -42,8 +43,10 @@ struct UniversalTable {
   // panic. Whatever is not reported as done runs sequentially on the host.
   // With kBoundaryListDone, `boundary_corners` holds the corners without an opposite, ascending.
   enum : uint32_t { kMatchExact = 1u, kLeftMostDone = 2u, kUnusedVertices = 4u, kBoundaryListDone = 8u };
+  // With kLeftMostDone, `interior_out[num_vertices]` holds the per-vertex interior flags as well (see vertex_interior_flags).
   using DeviceMatcher = uint32_t (*)(void* user, const uint32_t* corner_vertex, uint32_t num_faces, uint32_t num_vertices,
-                                     uint32_t* opposite_out, uint32_t* left_most_out, std::vector<uint32_t>* boundary_corners);
+                                     uint32_t* opposite_out, uint32_t* left_most_out, uint8_t* interior_out, std::vector<uint32_t>* boundary_corners);
+  bool has_interior = false;
   std::vector<uint32_t> boundary_corners;  // valid only when has_boundary_list
   bool has_boundary_list = false;
   void build(const uint32_t* faces, uint32_t nfaces, const AttrView& pos, DeviceMatcher matcher = nullptr, void* matcher_user = nullptr);

@@ -358,16 +358,23 @@ struct StageClock {
 // K12 + K13: half-edge matching and left-most corners on the device, one synchronisation. Keeps the device
 // copies of corner_vertex / opposite / left_most for the attribute kernels when the results are exact.
 uint32_t MeshJob::device_matcher(void* user, const uint32_t* corner_vertex, uint32_t num_faces, uint32_t num_vertices, uint32_t* opposite_out,
-                                 uint32_t* left_most_out, std::vector<uint32_t>* boundary_corners) {
+                                 uint32_t* left_most_out, uint8_t* interior_out, std::vector<uint32_t>* boundary_corners) {
   MeshJob* job = (MeshJob*)user;
   DeviceContext& ctx = *job->match_ctx_;
   cudaStream_t s = ctx.stream[0];
   const size_t C = (size_t)num_faces * 3;
   StageClock clk;
-  uint32_t* d_cv = job->dupload(corner_vertex, C, s);
+  // vertex ids = the faces themselves (no position map): they are on their way to the device already
+  uint32_t* d_cv = nullptr;
+  if (corner_vertex == job->mesh_->faces && job->inputs_upload_.valid()) {
+    job->inputs_upload_.wait();
+    if (job->d_faces_) { cuda_check(cudaStreamWaitEvent(s, ctx.ev_inputs, 0), "cudaStreamWaitEvent"); d_cv = job->d_faces_; }
+  }
+  if (!d_cv) d_cv = job->dupload(corner_vertex, C, s);
   clk.lap("    K12 H2D corner_vertex");
   uint32_t* d_opp = job->dalloc<uint32_t>(C, s);
   uint32_t* d_lm = job->dalloc<uint32_t>(num_vertices, s);
+  uint8_t* d_int = job->dalloc<uint8_t>(num_vertices, s);
   uint32_t* d_flag = job->dalloc<uint32_t>(3, s);  // [0] K12 not exact, [1] K13 fan flags, [2] number of boundary corners
   constexpr uint32_t kBoundaryPrefix = 1u << 18;   // boundary corners copied back together with the flags (1 MB)
   const size_t bb = gpu::boundary_list_scratch_bytes(C);
@@ -382,7 +389,7 @@ uint32_t MeshJob::device_matcher(void* user, const uint32_t* corner_vertex, uint
   cuda_check(cudaMemsetAsync(d_flag, 0, 12, s), "cudaMemsetAsync");
   cuda_check(cudaMemsetAsync(d_opp, 0xFF, C * 4, s), "cudaMemsetAsync");
   gpu::launch_corner_table_opposites(d_cv, C, num_vertices, d_opp, d_flag, scratch, sb, s);
-  gpu::launch_left_most(d_cv, d_opp, C, num_vertices, lscratch, d_lm, d_flag + 1, s);
+  gpu::launch_left_most(d_cv, d_opp, C, num_vertices, lscratch, d_lm, d_flag + 1, s, d_int);
   gpu::launch_boundary_list(d_opp, C, bscratch, bb, d_blist, d_flag + 2, s);
   uint32_t flag[3] = {1, 0, 0};
   if (clk.on) { cudaStreamSynchronize(s); clk.lap("    K12 + K13 kernels"); }
@@ -394,6 +401,7 @@ uint32_t MeshJob::device_matcher(void* user, const uint32_t* corner_vertex, uint
   // the results travel with the flags (one synchronisation); they are ignored when a flag is raised
   cuda_check(cudaMemcpyAsync(opposite_out, d_opp, C * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
   cuda_check(cudaMemcpyAsync(left_most_out, d_lm, (size_t)num_vertices * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+  cuda_check(cudaMemcpyAsync(interior_out, d_int, (size_t)num_vertices, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
   cuda_check(cudaFreeAsync(scratch, s), "cudaFreeAsync");
   cuda_check(cudaFreeAsync(lscratch, s), "cudaFreeAsync");
   cuda_check(cudaFreeAsync(bscratch, s), "cudaFreeAsync");
@@ -419,7 +427,7 @@ uint32_t MeshJob::device_matcher(void* user, const uint32_t* corner_vertex, uint
   job->d_opposite_ = d_opp;
   if (flag[1] == 0) {
     done |= UniversalTable::kLeftMostDone;
-    job->d2h_bytes += (size_t)num_vertices * 4;
+    job->d2h_bytes += (size_t)num_vertices * 5;
     job->d_left_most_ = d_lm;
   }
   return done;
@@ -495,12 +503,16 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
             for (uint32_t k = 0; k < C; ++k) mo[k] = sm[k] ? kNone : opp[k];
             table_refs_[i].opposite_masked = mo.data();
           }
-          interior_[i] = vertex_interior_flags(table_refs_[i]);
-          table_refs_[i].interior = interior_[i].data();
+          // the attribute's own sequencer runs only when its table differs from the universal one (see shares_position_sequence)
+          if (seams_[i - 1].has_interior_seam || seams_[i - 1].num_vertices != ut_.num_vertices || getenv("DXO_NO_SHARED_SEQUENCE")) {
+            interior_[i] = vertex_interior_flags(table_refs_[i]);
+            table_refs_[i].interior = interior_[i].data();
+          }
           c.lap("  (thread) masked opposites, interior flags");
         });
       table_refs_[0] = table_ref(ut_);
-      spawn([this] { interior_[0] = vertex_interior_flags(table_refs_[0]); table_refs_[0].interior = interior_[0].data(); });
+      if (ut_.has_interior) table_refs_[0].interior = ut_.interior.data();  // came back with K13's left-most corners
+      else spawn([this] { interior_[0] = vertex_interior_flags(table_refs_[0]); table_refs_[0].interior = interior_[0].data(); });
       { StageClock c; eb.traverse(); c.lap("  (main) CLERS traversal"); }
       wait_all();  // seam tables, interior flags
       clk.lap("seam tables + traversal");
@@ -549,8 +561,7 @@ void MeshJob::validate_attribute_indices(uint32_t max_face_point) const {
     const AttrView& v = plans_[i].view;
     if (v.num_points <= max_face_point) throw Error(DXO_ERR_INVALID_ARGUMENT, "face references a point outside an attribute");
     if (i == 0 || !v.map) continue;  // the position map is checked by the corner-table build
-    uint32_t mx = 0;
-    for (uint32_t p = 0; p < v.num_points; ++p) mx = std::max(mx, v.map[p]);
+    const uint32_t mx = max_u32(v.map, v.num_points);
     if (v.num_points && mx >= v.num_unique) throw Error(DXO_ERR_INVALID_ARGUMENT, "point_to_value entry out of range");
   }
 }
@@ -671,8 +682,10 @@ void MeshJob::upload(DeviceContext& ctx) {
   cuda_check(cudaStreamWaitEvent(s, ctx.ev_uploaded, 0), "cudaStreamWaitEvent");
   if (!d_opposite_) d_opposite_ = dupload(ut_.opposite.data(), C, s);
   if (!d_corner_vertex_) d_corner_vertex_ = dupload(ut_.corner_vertex.data(), C, s);
-  else if (ut_.num_vertices != plans_[0].view.num_unique)  // non-manifold vertices were split after K12 ran: refresh the labels
-    cuda_check(cudaMemcpyAsync(d_corner_vertex_, ut_.corner_vertex.data(), C * 4, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D");
+  else if (ut_.num_vertices != plans_[0].view.num_unique) {  // non-manifold vertices were split after K12 ran: refresh the labels
+    if (d_corner_vertex_ == d_faces_) d_corner_vertex_ = dupload(ut_.corner_vertex.data(), C, s);  // K12 read the faces in place
+    else cuda_check(cudaMemcpyAsync(d_corner_vertex_, ut_.corner_vertex.data(), C * 4, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D");
+  }
   if (!d_left_most_) d_left_most_ = dupload(ut_.left_most.data(), ut_.left_most.size(), s);
   // padded per-face layouts are derived on the device at the start of every launch() (part of the timed step)
   d_faces4_ = dalloc<uint4>(ut_.num_faces, s);

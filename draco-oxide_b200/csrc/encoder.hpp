@@ -226,7 +226,7 @@ class MeshJob {
   void encode_side_stream_from_flags(size_t att, const uint8_t* flags, size_t n);
 
   static uint32_t device_matcher(void* user, const uint32_t* corner_vertex, uint32_t num_faces, uint32_t num_vertices, uint32_t* opposite_out,
-                                 uint32_t* left_most_out, std::vector<uint32_t>* boundary_corners);
+                                 uint32_t* left_most_out, uint8_t* interior_out, std::vector<uint32_t>* boundary_corners);
   DeviceContext* match_ctx_ = nullptr;
   template <class T> T* dalloc(size_t count, cudaStream_t s);
   template <class T> T* dupload(const T* host, size_t count, cudaStream_t s);

@@ -2141,12 +2141,12 @@ __global__ void __launch_bounds__(kThreads) vertex_first_corner_kernel(const uin
 }
 __global__ void __launch_bounds__(kThreads) left_most_kernel(const uint32_t* __restrict__ opposite, const uint32_t* __restrict__ first_corner,
                                                              const uint32_t* __restrict__ valence, uint32_t num_vertices,
-                                                             uint32_t* __restrict__ left_most, uint32_t* flags) {
+                                                             uint32_t* __restrict__ left_most, uint8_t* __restrict__ interior, uint32_t* flags) {
   uint32_t bad = 0;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < num_vertices; v += stride) {
     const uint32_t n = valence[v], c = first_corner[v];
-    if (n == 0) { bad |= kFanUnusedVertex; left_most[v] = kNoneDev; continue; }
+    if (n == 0) { bad |= kFanUnusedVertex; left_most[v] = kNoneDev; if (interior) interior[v] = 0; continue; }
     uint32_t last = c, count = 1, a = c;
     bool open = false;
     for (;;) {  // swing left: opposite(next(a)) -> next
@@ -2168,6 +2168,7 @@ __global__ void __launch_bounds__(kThreads) left_most_kernel(const uint32_t* __r
     }
     if (count != n) bad |= kFanSplitVertex;
     left_most[v] = last;
+    if (interior) interior[v] = __ldg(opposite + cnext(last)) != kNoneDev ? 1 : 0;  // !is_on_boundary(v): swing_left(left_most[v]) exists (corner_table/mod.rs:36-38)
   }
   if (bad) atomicOr(flags, bad);
 }
@@ -2192,13 +2193,13 @@ void launch_boundary_list(const uint32_t* opposite, uint64_t num_corners, void* 
 
 size_t left_most_scratch_bytes(uint32_t num_vertices) { return 2 * (size_t)num_vertices * sizeof(uint32_t) + 256; }
 void launch_left_most(const uint32_t* corner_vertex, const uint32_t* opposite, uint64_t num_corners, uint32_t num_vertices, void* scratch,
-                      uint32_t* left_most, uint32_t* flags, cudaStream_t s) {
+                      uint32_t* left_most, uint32_t* flags, cudaStream_t s, uint8_t* interior) {
   uint32_t* first_corner = (uint32_t*)scratch;
   uint32_t* valence = first_corner + num_vertices;
   cudaMemsetAsync(first_corner, 0xFF, sizeof(uint32_t) * num_vertices, s);
   cudaMemsetAsync(valence, 0, sizeof(uint32_t) * num_vertices, s);
   vertex_first_corner_kernel<<<grid_for(num_corners), kThreads, 0, s>>>(corner_vertex, num_corners, first_corner, valence);
-  left_most_kernel<<<grid_for(num_vertices), kThreads, 0, s>>>(opposite, first_corner, valence, num_vertices, left_most, flags);
+  left_most_kernel<<<grid_for(num_vertices), kThreads, 0, s>>>(opposite, first_corner, valence, num_vertices, left_most, interior, flags);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -125,8 +125,9 @@ size_t left_most_scratch_bytes(uint32_t num_vertices);
 size_t boundary_list_scratch_bytes(uint64_t num_corners);
 void launch_boundary_list(const uint32_t* opposite, uint64_t num_corners, void* scratch, size_t scratch_bytes, uint32_t* list, uint32_t* count,
                           cudaStream_t s);
+// interior (optional, [num_vertices]): 1 when swing_left(left_most[v]) exists, i.e. the vertex is not on a boundary
 void launch_left_most(const uint32_t* corner_vertex, const uint32_t* opposite, uint64_t num_corners, uint32_t num_vertices, void* scratch,
-                      uint32_t* left_most, uint32_t* flags, cudaStream_t s);
+                      uint32_t* left_most, uint32_t* flags, cudaStream_t s, uint8_t* interior = nullptr);
 
 // ---- K14: per-attribute seam table (attribute_corner_table.rs:16-137) from the device-resident universal table ----
 // Outputs: seam[C], corner_vertex[C], left_most_a[<= C] (attribute vertex -> corner), *total = number of attribute
