@@ -255,6 +255,7 @@ int dxo_session_create(const dxo_mesh* mesh, const dxo_config* cfg, dxo_session*
     g_timing = dxo_timing{};
     const auto t0 = Clock::now();
     s->job = std::make_unique<MeshJob>(mesh, s->cfg);
+    s->job->resident = true;
     DeviceContext& ctx = DeviceContext::get(s->cfg.device);
     s->job->build_connectivity(&ctx);
     g_timing.host_connectivity_ms = (float)ms_since(t0);

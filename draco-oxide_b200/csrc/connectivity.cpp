@@ -649,15 +649,15 @@ class EdgebreakerRun {
  public:
   // phase 2b: the seam stream of one non-position attribute (:610-653); independent per attribute
   void write_seam_stream(const SeamTable& st, ByteSink& w) const {
-    // One flag per interior edge: faces are walked in reverse visiting order and an edge is reported by the first
-    // of its two faces met (the init face of an interior-start component is never walked, so its neighbours report
-    // its edges). The reference then feeds the flags to the coder last-to-first (:644); here they are written into
-    // the buffer back to front, so the buffer is already in coding order.
-    const size_t max_flags = ut_.num_corners / 2 + 1;
-    U8Array flags(max_flags);
-    uint8_t* const end = flags.data() + max_flags;
-    uint8_t* head = end;
-    uint64_t zeros = 0;
+    // One flag per interior edge. The reference walks the faces in reverse visiting order, lets the first of an edge's
+    // two faces met report it (the init face of an interior-start component is never walked, so its neighbours report
+    // its edges; corners in the order c, next, prev) and feeds the flags to the coder last-to-first (:610-653). In
+    // coding order that is: faces in visiting order, corners prev, next, c, and a face reports an edge exactly when
+    // the face across it was done BEFORE this face was visited — which the traversal has already decided:
+    //   * the edge opposite to the tip c is the gate the traversal came through (done), or absent for a boundary start;
+    //   * the right (next) / left (prev) neighbours were found done precisely for the symbols R, E / L, E (a C or S
+    //     face has neither: a C tip was unvisited, so no done face contains it).
+    // So the flags come out of one forward pass over (visit order, symbols) without a visited-face table.
     if (!st.has_interior_seam) {
       // only mesh boundaries are seams: every reported flag is 0, and there are (corners - boundary corners) / 2 of them
       size_t boundary = 0;
@@ -671,27 +671,31 @@ class EdgebreakerRun {
       w.varint(bytes.size());
       w.bytes(bytes);
       return;
-    } else {
-      std::vector<uint8_t> face_seen_v(ut_.num_faces, 0);
-      uint8_t* const face_seen = face_seen_v.data();
+    }
+    const size_t max_flags = ut_.num_corners / 2 + 1;
+    U8Array flags(max_flags + 3);
+    uint8_t* const head = flags.data();
+    uint8_t* tail = head;
+    uint8_t* const end = head + max_flags;
+    uint64_t zeros = 0;
+    {
       const uint32_t* const opp = ut_.opposite.data();
       const uint8_t* const seam = st.seam.data();
       const uint32_t* const visit = visit_order_.data();
-      for (size_t i = visit_order_.size(); i-- > 0;) {
-        const uint32_t c = visit[i];
-        const uint32_t tri[3] = {c, corner_next(c), corner_prev(c)};
-        face_seen[c / 3u] = 1;
-        for (uint32_t k : tri) {
-          const uint32_t o = opp[k];
-          if (o == kNone || face_seen[o / 3u]) continue;
-          const uint8_t f = seam[k];
-          if (head == flags.data()) throw Error(DXO_ERR_INTERNAL, "seam stream: more flags than interior edges");
-          *--head = f;
-          zeros += f ? 0 : 1;
-        }
+      const uint8_t* const sym = symbols_.data();
+      const size_t nv = visit_order_.size();
+      uint64_t ones = 0;
+      for (size_t i = 0; i < nv; ++i) {
+        const uint32_t c = visit[i], cn = corner_next(c), cp = corner_prev(c);
+        const uint8_t s = sym[i];
+        if (tail > end) throw Error(DXO_ERR_INTERNAL, "seam stream: more flags than interior edges");
+        if ((s == kL || s == kE) && opp[cp] != kNone) { const uint8_t f = seam[cp] != 0; *tail++ = f; ones += f; }
+        if ((s == kR || s == kE) && opp[cn] != kNone) { const uint8_t f = seam[cn] != 0; *tail++ = f; ones += f; }
+        if (opp[c] != kNone) { const uint8_t f = seam[c] != 0; *tail++ = f; ones += f; }
       }
+      zeros = (uint64_t)(tail - head) - ones;
     }
-    const size_t n = (size_t)(end - head);
+    const size_t n = (size_t)(tail - head);
     const uint8_t p0 = side_stream_zero_prob(zeros, (float)n);
     std::vector<uint8_t> bytes;
     rabs_encode_forward(head, n, p0, bytes);

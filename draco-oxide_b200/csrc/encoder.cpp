@@ -648,6 +648,11 @@ bool MeshJob::device_seam_table(DeviceContext& ctx, size_t att) {
   SeamTable& st = seams_[att - 1];
   st.num_vertices = scalars[0];
   st.has_interior_seam = (scalars[1] & 4u) != 0;
+  d.corner_vertex = d_cv; d.seam = d_seam; d.left_most = d_lm;
+  // Only mesh boundaries are seams and no vertex was split: the table IS the universal one. The host then needs none of
+  // it — the attribute shares the position sequence and its seam stream is a run of zeros — so the 5 bytes per corner
+  // stay on the device (traces and DXO_NO_SHARED_SEQUENCE still fetch them).
+  if (!st.has_interior_seam && st.num_vertices == V && !trace && !getenv("DXO_NO_SHARED_SEQUENCE")) return true;
   st.corner_vertex.resize(C);
   st.seam.resize(C);
   st.left_most.resize(st.num_vertices);
@@ -658,7 +663,6 @@ bool MeshJob::device_seam_table(DeviceContext& ctx, size_t att) {
   cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
   pinned_copy_in_flight_.fetch_sub(1);
   { std::lock_guard<std::mutex> lock(alloc_mu_); d2h_bytes += C * 5 + (size_t)st.num_vertices * 4; }
-  d.corner_vertex = d_cv; d.seam = d_seam; d.left_most = d_lm;
   return true;
 }
 // Seam table of attribute `att` (called by the thread that has just built it).
@@ -702,6 +706,9 @@ void MeshJob::upload(DeviceContext& ctx) {
     else d.quant = dalloc<int32_t>(U * qstride, s);
     if (i > 0) d.corner_vertex4 = dalloc<uint4>(ut_.num_faces, s);
     if (i > 0 && p.scheme == Scheme::Normal) d.fan_link = dalloc<uint2>(C, s);  // fan walks read one link per swing
+    if (i > 0 && p.scheme == Scheme::Normal && resident && !getenv("DXO_NO_RINGS")) {
+      d.ring = dalloc<uint4>(2 * M, s); d.ring_head = dalloc<uint2>(M, s); d.ring_count = dalloc<uint8_t>(M, s);
+    }
     // K4's fast path: {opposite, its point} links and ranks carried in the values' padding component
     if (i == 0) rank_in_w_ = false;
     if (i == 0 && vertex_is_point_ && p.scheme == Scheme::Parallelogram && p.port == Portabilization::Quantize && p.ncomp_q == 3 && !getenv("DXO_NO_K4_FAST")) {
@@ -747,7 +754,18 @@ void MeshJob::upload(DeviceContext& ctx) {
     if (d.fan_link) gpu::launch_fan_link(d_opposite_, i == 0 ? nullptr : d.seam, d_faces_, C, d.fan_link, s);
     if (p.port == Portabilization::ToBits && p.ncomp_q == 3) gpu::launch_pad3((const uint32_t*)d.values, p.view.num_unique, (uint4*)d.quant, s);
   }
-  layout_launches_ = 1 + (vertex_is_point_ ? 0 : 1);
+  uint32_t ring_launches = 0;
+  for (size_t i = 1; i < plans_.size(); ++i) {
+    AttrDevice& d = dev_[i];
+    if (!d.ring) continue;
+    const AttrDevice& pd = dev_[plans_[i].parent];
+    gpu::TableDev t = table_dev(i);
+    t.ring = nullptr;
+    gpu::launch_normal_rings(d.seq, (uint32_t)sequence_of(i).size(), t, gpu::QuantDev{nullptr, d.map, (uint32_t)plans_[i].ncomp_q}, gpu::QuantDev{nullptr, pd.map, 3},
+                             d.ring, d.ring_head, d.ring_count, s);
+    ++ring_launches;
+  }
+  layout_launches_ = 1 + (vertex_is_point_ ? 0 : 1) + ring_launches;
   for (size_t i = 0; i < plans_.size(); ++i) layout_launches_ += (plans_[i].scheme == Scheme::Parallelogram || plans_[i].scheme == Scheme::TexCoord || dev_[i].used) ? 1 : 0;
   for (size_t i = 0; i < plans_.size(); ++i)
     layout_launches_ += (i > 0 ? 1 : 0) + (dev_[i].fan_link ? 1 : 0) + ((plans_[i].port == Portabilization::ToBits && plans_[i].ncomp_q == 3) ? 1 : 0);
@@ -774,6 +792,7 @@ gpu::TableDev MeshJob::table_dev(size_t att) const {
   t.corner_point4 = d_faces4_;
   t.opposite = d_opposite_;
   t.fan_link = dev_[att].fan_link;
+  t.ring = dev_[att].ring; t.ring_head = dev_[att].ring_head; t.ring_count = dev_[att].ring_count;
   t.num_corners = ut_.num_corners;
   if (att == 0) {
     t.corner_vertex = d_corner_vertex_; t.corner_vertex4 = vertex_is_point_ ? d_faces4_ : d_corner_vertex4_; t.vertex_is_point = vertex_is_point_ ? 1 : 0;
@@ -1194,6 +1213,14 @@ void MeshJob::capture_trace(DeviceContext& ctx) {
     if (bytes) cuda_check(cudaMemcpy(v.data(), dptr, bytes, cudaMemcpyDeviceToHost), "cudaMemcpy trace");
   };
   (void)ctx;
+  for (size_t i = 1; i < plans_.size(); ++i) {  // seam tables that stayed on the device (device_seam_table: same as the universal table)
+    const SeamTable& st = seams_[i - 1];
+    if (!st.corner_vertex.empty() || !dev_[i].corner_vertex) continue;
+    const std::string k = "att" + std::to_string(i) + ".";
+    fetch(k + "c2v", dev_[i].corner_vertex, (size_t)ut_.num_corners * 4);
+    fetch(k + "left_most", dev_[i].left_most, (size_t)st.num_vertices * 4);
+    fetch(k + "seam", dev_[i].seam, (size_t)ut_.num_corners);
+  }
   for (size_t i = 0; i < plans_.size(); ++i) {
     const AttrPlan& p = plans_[i];
     const AttrResult& r = results_[i];

@@ -112,6 +112,7 @@ struct AttrDevice {
   // inputs
   float* values = nullptr; uint32_t* map = nullptr;
   uint32_t *corner_vertex = nullptr, *left_most = nullptr, *seq = nullptr; uint8_t* seam = nullptr; uint4* corner_vertex4 = nullptr; uint2* fan_link = nullptr;
+  uint4* ring = nullptr; uint2* ring_head = nullptr; uint8_t* ring_count = nullptr;  // K5's flattened fans (resident sessions)
   uint8_t* side_out = nullptr; void* side_scratch = nullptr; size_t side_scratch_bytes = 0;  // [8-byte scalars][flags (+1)] for the host coder
   // intermediates / outputs
   int32_t* quant = nullptr; uint32_t *rank = nullptr, *symbols = nullptr, *hist = nullptr, *work = nullptr;
@@ -166,6 +167,8 @@ class MeshJob {
   // With a device but many encodes in flight (concurrent callers): the same passes, device tables included, in order on
   // the calling thread — a dozen helper threads per call only fight each other for the cores.
   bool inline_host = false;
+  // The job will run its device phase many times (sessions): upload() also flattens the fans of normal attributes (K5).
+  bool resident = false;
   std::map<std::string, std::vector<uint8_t>> trace_items;
   uint64_t h2d_bytes = 0, d2h_bytes = 0;
   uint64_t num_position_vertices() const { return plans_.empty() ? 0 : plans_[0].sequence.size(); }

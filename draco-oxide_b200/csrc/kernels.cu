@@ -547,11 +547,81 @@ __device__ __forceinline__ void add_cross(const int32_t* pn, const int32_t* pp, 
 __device__ __forceinline__ int32_t isign(int32_t a) { return (a > 0) - (a < 0); }
 __device__ __forceinline__ int32_t iabs_wrap(int32_t a) { return a < 0 ? (int32_t)(0u - (uint32_t)a) : a; }
 
+// Flattens the fan walk of predict_normal_body (same links, same order of faces) into a polyline of position-value indices:
+// [tips met swinging right, last first] + [next(c), prev(c)] + [tips met swinging left]; every pair of neighbours spans one
+// face of the fan, in the orientation add_cross expects. A closed fan ends with the vertex it started with.
+__global__ void __launch_bounds__(kThreads) normal_ring_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos,
+                                                               uint4* __restrict__ ring, uint2* __restrict__ head, uint8_t* __restrict__ count) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t c = __ldg(seq + i);
+    const uint32_t point_c = __ldg(t.corner_point + c);
+    head[i] = make_uint2(value_index(pos, point_c), value_index(q, point_c));
+    const Tri pts = load_tri(t.corner_point4, c);
+    uint32_t left[8], right[8];
+    uint32_t nl = 0, nr = 0;
+    bool over = false, closed = false;
+    left[nl++] = value_index(pos, pts.next);
+    left[nl++] = value_index(pos, pts.prev);
+    uint32_t cur = c, guard = t.num_corners;
+    uint2 l = fan_link(t, cnext(cur));
+    while (l.x != kNoneDev) {
+      cur = cnext(l.x);
+      if (cur == c) { closed = true; break; }
+      if (nl < 8) left[nl++] = value_index(pos, l.y); else { over = true; break; }
+      l = fan_link(t, cnext(cur));
+      if (--guard == 0) { over = true; break; }
+    }
+    if (!closed && !over) {
+      cur = c;
+      guard = t.num_corners;
+      l = fan_link(t, cprev(cur));
+      while (l.x != kNoneDev) {
+        cur = cprev(l.x);
+        if (cur == c) break;
+        if (nr < 8) right[nr++] = value_index(pos, l.y); else { over = true; break; }
+        l = fan_link(t, cprev(cur));
+        if (--guard == 0) { over = true; break; }
+      }
+    }
+    uint32_t out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const uint32_t total = nl + nr;
+    if (over || total > 8) count[i] = 0xFF;
+    else {
+      for (uint32_t k = 0; k < nr; ++k) out[k] = right[nr - 1 - k];
+      for (uint32_t k = 0; k < nl; ++k) out[nr + k] = left[k];
+      count[i] = (uint8_t)total;
+    }
+    ring[2 * (size_t)i] = make_uint4(out[0], out[1], out[2], out[3]);
+    ring[2 * (size_t)i + 1] = make_uint4(out[4], out[5], out[6], out[7]);
+  }
+}
+void launch_normal_rings(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos, uint4* ring, uint2* ring_head, uint8_t* ring_count,
+                         cudaStream_t s) {
+  if (n) normal_ring_kernel<<<grid_for(n), kThreads, 0, s>>>(seq, n, t, q, pos, ring, ring_head, ring_count);
+}
+
 __device__ __forceinline__ void predict_normal_body(const uint32_t* __restrict__ seq, const TableDev& t, const QuantDev& q, const QuantDev& pos,
                                                     uint32_t* __restrict__ symbols, uint8_t* __restrict__ flips, AttrStats* stats, uint32_t i0, uint32_t i1,
                                                     uint32_t istep) {
   uint32_t nz = 0, mxs = 0, err = 0;
   for (uint32_t i = i0; i < i1; i += istep) {
+    long long sum[3] = {0, 0, 0};
+    uint32_t vi;
+    const uint32_t ring_n = t.ring ? (uint32_t)__ldg(t.ring_count + i) : 0xFFu;
+    if (ring_n != 0xFFu) {
+      // Flattened fan (launch_normal_rings): all position gathers are independent of each other.
+      const uint2 h = __ldg(t.ring_head + i);
+      const uint4 ra = __ldg(t.ring + 2 * (size_t)i), rb = __ldg(t.ring + 2 * (size_t)i + 1);
+      const uint32_t idx[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+      int32_t pc[3], p[8][3];
+      load_q<3>(pos, h.x, pc);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) if ((uint32_t)k < ring_n) load_q<3>(pos, idx[k], p[k]);
+#pragma unroll
+      for (int k = 0; k + 1 < 8; ++k) if ((uint32_t)(k + 1) < ring_n) add_cross(p[k], p[k + 1], pc, sum);
+      vi = h.y;
+    } else {
     const uint32_t c = ld_stream(seq + i);
     int32_t pc[3];
     const uint32_t point_c = __ldg(t.corner_point + c);
@@ -561,7 +631,6 @@ __device__ __forceinline__ void predict_normal_body(const uint32_t* __restrict__
     // accumulate while swinging left; only an open fan needs the walk to the right of c as well.
     // Neighbouring faces of the fan share an edge, i.e. one of the two outer vertices: its position is carried
     // over (equal vertex => equal position value), so a swing costs one link and one position load.
-    long long sum[3] = {0, 0, 0};
     const Tri pts = load_tri(t.corner_point4, c);
     int32_t first_next[3], shared[3], tip[3];
     load_q<3>(pos, value_index(pos, pts.next), first_next);
@@ -603,6 +672,8 @@ __device__ __forceinline__ void predict_normal_body(const uint32_t* __restrict__
         if (--guard == 0) { err |= kErrFanWalk; break; }
       }
     }
+    vi = value_index(q, point_c);
+    }
     const long long upper = 1ll << 29;
     const long long abs_sum = llabs(sum[0]) + llabs(sum[1]) + llabs(sum[2]);
     if (abs_sum > upper) {
@@ -615,7 +686,6 @@ __device__ __forceinline__ void predict_normal_body(const uint32_t* __restrict__
       // integer vector -> f32 through f64 (geom.rs:47-52); the normalize() result is discarded there
       oct_quantize_f32((float)(double)nx, (float)(double)ny, (float)(double)nzc, p0, p1);
     }
-    const uint32_t vi = value_index(q, point_c);
     const int2 actual = __ldg(reinterpret_cast<const int2*>(q.values) + vi);
     // choose the sign closer to the actual value, in wrapping i32 (:128-143)
     const uint32_t d10 = (uint32_t)p0 - (uint32_t)actual.x, d11 = (uint32_t)p1 - (uint32_t)actual.y;

@@ -54,6 +54,12 @@ struct TableDev {
   const uint32_t* left_most;      // per vertex
   uint32_t num_corners;
   uint32_t num_vertices;
+  // Optional (K5 of a resident session; launch_normal_rings): the fan of every sequence element flattened into the polyline of
+  // position-value indices around its vertex — consecutive entries span one face — so that the step gathers the positions
+  // with independent loads instead of chasing one link per swing.
+  const uint4* ring = nullptr;         // [2 * n]: up to 8 position-value indices per element
+  const uint2* ring_head = nullptr;    // [n]: {position-value index of the vertex, value index of the attribute at the vertex}
+  const uint8_t* ring_count = nullptr; // [n]: entries in use (2..8), 0xFF = more than 8 or an inconsistent fan: walk it
 };
 
 // Quantized attribute: AoS int32 values with a power-of-two stride (1, 2, 4, 4 ints for 1..4
@@ -81,6 +87,10 @@ void launch_sequence_tables(const uint32_t* seq, uint32_t n, TableDev t, const u
 // WrappedDifference bounds for values that are not quantised on the device (ToBits): min / max over the used values
 void launch_wrap_minmax(const int32_t* values, uint64_t num_values, uint32_t ncomp, uint32_t stride, const uint8_t* used, AttrStats* stats, cudaStream_t s);
 void launch_fan_link(const uint32_t* opposite, const uint8_t* seam, const uint32_t* corner_point, uint64_t n, uint2* out, cudaStream_t s);
+// Fills TableDev::ring / ring_head / ring_count for the sequence of a normal attribute (a function of the connectivity and
+// the point maps alone: once per upload). q / pos: only their point maps are read.
+void launch_normal_rings(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos, uint4* ring, uint2* ring_head, uint8_t* ring_count,
+                         cudaStream_t s);
 void launch_pad3(const uint32_t* in, uint64_t n_tuples, uint4* out, cudaStream_t s);  // 3-wide -> 16-byte tuples
 // ---- K3: octahedral normal quantization (octahedral_quantization.rs:49-64) ----
 void launch_oct_quantize(const float* normals, uint64_t num_values, int32_t* out, AttrStats* stats, cudaStream_t s);

@@ -13,12 +13,16 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     pmesh = bench.pinned_copy(mesh)
     cfg = dxo.Config(device=0)
     ready, go = threading.Barrier(T + 1), threading.Barrier(T + 1)
+    tms, walls = [], []
     def worker():
         for _ in range(2):
             o = bytearray(); dxo.encode(pmesh, o, cfg)
         ready.wait(); go.wait()
         for _ in range(steps):
+            t = time.perf_counter()
             o = bytearray(); dxo.encode(pmesh, o, cfg)
+            walls.append(time.perf_counter() - t)
+            tms.append(dxo.last_timing())
     th = [threading.Thread(target=worker) for _ in range(T)]
     for t in th: t.start()
     ready.wait(); torch.cuda.synchronize()
@@ -26,6 +30,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     t0 = time.perf_counter(); go.wait()
     for t in th: t.join()
     dt = time.perf_counter() - t0
+    keys = [k for k in tms[0] if k.endswith("_ms")]
+    print("[result] per call, from dxo_last_timing: " + "  ".join(f"{k} {sum(t[k] for t in tms) / len(tms):.2f}" for k in keys) + f"  python wall {1e3 * sum(walls) / len(walls):.2f}", file=sys.stderr)
     print(f"[result] {T} callers x {steps} calls: {dt * 1e3:.1f} ms, {mesh.num_points() * T * steps / dt / 1e6:.1f} Mvertices/s, {dt * 1e3 / steps:.1f} ms per call", file=sys.stderr)
     sys.exit(0)
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 16
