@@ -484,8 +484,14 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
     auto spawn = [&](std::function<void()> fn) { if (threads) tasks.push_back(std::async(std::launch::async, std::move(fn))); else fn(); };
     auto wait_all = [&] { std::exception_ptr first; for (auto& t : tasks) { try { if (t.valid()) t.get(); } catch (...) { if (!first) first = std::current_exception(); } } tasks.clear(); if (first) std::rethrow_exception(first); };
     try {
+      // One thread for everything (many encodes in flight): K14 of every attribute is started now and collected after
+      // the traversal, which hides the device's turnaround behind 20+ ms of host work.
+      std::vector<std::function<void()>> after_traversal;
+      const bool defer_k14 = !threads && early_uploads && !getenv("DXO_NO_K14");
+      if (defer_k14) for (size_t i = 1; i < natt; ++i) device_seam_table_begin(*ctx, i);
+      auto spawn_att = [&](std::function<void()> fn) { if (defer_k14) after_traversal.push_back(std::move(fn)); else spawn(std::move(fn)); };
       for (size_t i = 1; i < natt; ++i)
-        spawn([this, i, ctx, early_uploads] {
+        spawn_att([this, i, ctx, early_uploads] {
           StageClock c;
           if (early_uploads && !getenv("DXO_NO_K14") && device_seam_table(*ctx, i)) c.lap("  (thread) seam table (K14)");
           else {
@@ -514,6 +520,7 @@ void MeshJob::build_connectivity(DeviceContext* ctx) {
       if (ut_.has_interior) table_refs_[0].interior = ut_.interior.data();  // came back with K13's left-most corners
       else spawn([this] { interior_[0] = vertex_interior_flags(table_refs_[0]); table_refs_[0].interior = interior_[0].data(); });
       { StageClock c; eb.traverse(); c.lap("  (main) CLERS traversal"); }
+      for (auto& fn : after_traversal) fn();
       wait_all();  // seam tables, interior flags
       clk.lap("seam tables + traversal");
       auto seq0_fn = [this] { StageClock c; plans_[0].sequence = attribute_sequence(table_refs_[0], eb_->corner_list()); c.lap("  (thread) position sequence"); };
@@ -620,7 +627,10 @@ void MeshJob::upload_inputs(DeviceContext& ctx) {
 
 // K14: the seam table of attribute `att` from the device-resident universal table (K12 + K13 results).
 // Runs on the helper thread of that attribute; the host copies are needed by the sequencer and the seam stream.
-bool MeshJob::device_seam_table(DeviceContext& ctx, size_t att) {
+// First half: the kernels only (asynchronous) — a caller that keeps its host passes on one thread starts every attribute's
+// table before the CLERS traversal and collects the results after it.
+bool MeshJob::device_seam_table_begin(DeviceContext& ctx, size_t att) {
+  if (seam_pending_.size() != plans_.size()) seam_pending_.assign(plans_.size(), SeamPending{});
   if (!d_opposite_ || !d_corner_vertex_ || !d_left_most_ || !inputs_upload_.valid()) return false;
   cuda_check(cudaSetDevice(ctx.device), "cudaSetDevice");
   inputs_upload_.wait();
@@ -630,19 +640,36 @@ bool MeshJob::device_seam_table(DeviceContext& ctx, size_t att) {
   const uint32_t V = ut_.num_vertices;
   AttrDevice& d = dev_[att];
   if (!d_faces_) return false;  // the inputs upload failed; upload() reports it
-  uint8_t* d_seam = dalloc<uint8_t>(C, s);
-  uint32_t* d_cv = dalloc<uint32_t>(C, s);
-  uint32_t* d_lm = dalloc<uint32_t>(C, s);  // at most one attribute vertex per corner
-  uint32_t* d_scalars = dalloc<uint32_t>(2, s);  // [0] number of attribute vertices, [1] flags
+  SeamPending& sp = seam_pending_[att];
+  sp.d_seam = dalloc<uint8_t>(C, s);
+  sp.d_cv = dalloc<uint32_t>(C, s);
+  sp.d_lm = dalloc<uint32_t>(C, s);  // at most one attribute vertex per corner
+  sp.d_scalars = dalloc<uint32_t>(2, s);  // [0] number of attribute vertices, [1] flags
   const size_t sb = gpu::seam_table_scratch_bytes(V);
   void* scratch = nullptr;
   cuda_check(cudaMallocAsync(&scratch, sb, s), "cudaMallocAsync");
-  cuda_check(cudaMemsetAsync(d_scalars, 0, 8, s), "cudaMemsetAsync");
-  gpu::launch_seam_table(d_faces_, d.map, plans_[att].view.num_points, d_corner_vertex_, d_opposite_, d_left_most_, C, V, scratch, sb, d_seam, d_cv,
-                         d_lm, d_scalars, d_scalars + 1, s);
+  cuda_check(cudaMemsetAsync(sp.d_scalars, 0, 8, s), "cudaMemsetAsync");
+  gpu::launch_seam_table(d_faces_, d.map, plans_[att].view.num_points, d_corner_vertex_, d_opposite_, d_left_most_, C, V, scratch, sb, sp.d_seam, sp.d_cv,
+                         sp.d_lm, sp.d_scalars, sp.d_scalars + 1, s);
+  cuda_check(cudaFreeAsync(scratch, s), "cudaFreeAsync");
+  sp.begun = true;
+  return true;
+}
+
+bool MeshJob::device_seam_table(DeviceContext& ctx, size_t att) {
+  if (seam_pending_.size() != plans_.size() || !seam_pending_[att].begun) {
+    if (!device_seam_table_begin(ctx, att)) return false;
+  }
+  cuda_check(cudaSetDevice(ctx.device), "cudaSetDevice");
+  cudaStream_t s = ctx.stream[std::min<size_t>(att, 2)];
+  const size_t C = ut_.num_corners;
+  const uint32_t V = ut_.num_vertices;
+  AttrDevice& d = dev_[att];
+  const SeamPending sp = seam_pending_[att];
+  uint8_t* const d_seam = sp.d_seam;
+  uint32_t *const d_cv = sp.d_cv, *const d_lm = sp.d_lm, *const d_scalars = sp.d_scalars;
   uint32_t scalars[2] = {0, 1};
   cuda_check(cudaMemcpyAsync(scalars, d_scalars, 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
-  cuda_check(cudaFreeAsync(scratch, s), "cudaFreeAsync");
   cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
   if ((scalars[1] & 3u) != 0 || scalars[0] > C) return false;  // the sequential pass reports the error
   SeamTable& st = seams_[att - 1];

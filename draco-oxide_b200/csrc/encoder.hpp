@@ -202,6 +202,9 @@ class MeshJob {
   static void* pinned_source(void* user, size_t bytes);
   std::shared_future<void> inputs_upload_;  // faces, values and point maps travel while the host builds the tables
   bool device_seam_table(DeviceContext& ctx, size_t att);  // K14; false = not applicable / flagged, use the host pass
+  bool device_seam_table_begin(DeviceContext& ctx, size_t att);  // its launches alone (device_seam_table then only collects)
+  struct SeamPending { uint8_t* d_seam = nullptr; uint32_t *d_cv = nullptr, *d_lm = nullptr, *d_scalars = nullptr; bool begun = false; };
+  std::vector<SeamPending> seam_pending_;
   void upload_inputs(DeviceContext& ctx);
   void upload_seam_table(DeviceContext& ctx, size_t att);
   cudaStream_t alloc_stream_ = nullptr;

@@ -601,6 +601,7 @@ void launch_normal_rings(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q
   if (n) normal_ring_kernel<<<grid_for(n), kThreads, 0, s>>>(seq, n, t, q, pos, ring, ring_head, ring_count);
 }
 
+template <bool RING = false>
 __device__ __forceinline__ void predict_normal_body(const uint32_t* __restrict__ seq, const TableDev& t, const QuantDev& q, const QuantDev& pos,
                                                     uint32_t* __restrict__ symbols, uint8_t* __restrict__ flips, AttrStats* stats, uint32_t i0, uint32_t i1,
                                                     uint32_t istep) {
@@ -608,7 +609,7 @@ __device__ __forceinline__ void predict_normal_body(const uint32_t* __restrict__
   for (uint32_t i = i0; i < i1; i += istep) {
     long long sum[3] = {0, 0, 0};
     uint32_t vi;
-    const uint32_t ring_n = t.ring ? (uint32_t)__ldg(t.ring_count + i) : 0xFFu;
+    const uint32_t ring_n = RING ? (uint32_t)__ldg(t.ring_count + i) : 0xFFu;
     if (ring_n != 0xFFu) {
       // Flattened fan (launch_normal_rings): all position gathers are independent of each other.
       const uint2 h = __ldg(t.ring_head + i);
@@ -726,11 +727,18 @@ __device__ __forceinline__ void predict_normal_body(const uint32_t* __restrict__
 }
 __global__ void __launch_bounds__(kThreads, 8) predict_normal_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos,
                                                                   uint32_t* __restrict__ symbols, uint8_t* __restrict__ flips, AttrStats* stats) {
-  predict_normal_body(seq, t, q, pos, symbols, flips, stats, blockIdx.x * blockDim.x + threadIdx.x, n, gridDim.x * blockDim.x);
+  predict_normal_body<false>(seq, t, q, pos, symbols, flips, stats, blockIdx.x * blockDim.x + threadIdx.x, n, gridDim.x * blockDim.x);
+}
+// The flattened-fan form keeps eight positions in registers while their loads are in flight: half the occupancy of the
+// walking form, which needs every warp it can get to hide its chain of dependent loads.
+__global__ void __launch_bounds__(kThreads, 4) predict_normal_ring_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos,
+                                                                       uint32_t* __restrict__ symbols, uint8_t* __restrict__ flips, AttrStats* stats) {
+  predict_normal_body<true>(seq, t, q, pos, symbols, flips, stats, blockIdx.x * blockDim.x + threadIdx.x, n, gridDim.x * blockDim.x);
 }
 
 void launch_predict_normal(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos, uint32_t* symbols, uint8_t* flips, AttrStats* stats, cudaStream_t s) {
-  predict_normal_kernel<<<grid_for(n), kThreads, 0, s>>>(seq, n, t, q, pos, symbols, flips, stats);
+  if (t.ring) predict_normal_ring_kernel<<<grid_for(n), kThreads, 0, s>>>(seq, n, t, q, pos, symbols, flips, stats);
+  else predict_normal_kernel<<<grid_for(n), kThreads, 0, s>>>(seq, n, t, q, pos, symbols, flips, stats);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -791,6 +799,45 @@ __device__ __forceinline__ void texcoord_fallback(const uint32_t* seq, uint32_t 
   previous_value<2>(seq, i, t, q, pred);
 }
 
+// The predictor proper (:118-219) for inputs below 2^13 (positions) / 2^12 (texture coordinates), all non-negative.
+// Bounds, with P = 8191, T = 4095: |pn_k|, |cn_k| <= P; pn2, |cn.pn| <= 3 P^2 < 2^28 (i32); |x_uv| < 2^41;
+// |pn_k (cn.pn)| < 2^41 and its quotient by pn2 is at most |cn| (Cauchy-Schwarz), so |cx_k| < 2^15 and cx2 < 2^32;
+// cx2 pn2 < 2^59 (isqrt_fast is exact below 2^62); nrm < 2^30; |cx_uv| < 2^42; every dividend is below 2^52, where the
+// reciprocal division is exact; |a|, |b| < 2^29, so the squared errors stay below 2^60. Nothing wraps, so the wrapping
+// i64 arithmetic of the general path and this one agree; the guards (:139-160) compare against i64::MAX and cannot fire.
+// Returns the orientation flag (1 / 2), or 0 when the reference takes its fallback (degenerate edge).
+__device__ __forceinline__ uint8_t texcoord_small(const int32_t* c3, const int32_t* n3, const int32_t* p3, int2 nu, int2 pu, int2 cur, int32_t* pred) {
+  const int32_t pn[3] = {p3[0] - n3[0], p3[1] - n3[1], p3[2] - n3[2]};
+  const int32_t pn2 = pn[0] * pn[0] + pn[1] * pn[1] + pn[2] * pn[2];
+  if (pn2 == 0) return 0;
+  const int32_t cn[3] = {c3[0] - n3[0], c3[1] - n3[1], c3[2] - n3[2]};
+  const int32_t cn_dot_pn = pn[0] * cn[0] + pn[1] * cn[1] + pn[2] * cn[2];
+  const int32_t pn_uv[2] = {pu.x - nu.x, pu.y - nu.y};  // not both zero: the caller has dealt with nu == pu
+  const long long d = pn2;
+  const double rd = 1.0 / (double)pn2;
+  auto div = [&](long long n) -> long long {  // truncating n / d, |n| < 2^52
+    const long long an = n < 0 ? -n : n;
+    long long q = (long long)((double)an * rd);
+    const long long r = an - q * d;
+    if (r < 0) --q; else if (r >= d) ++q;
+    return n < 0 ? -q : q;
+  };
+  const long long x_uv[2] = {(long long)nu.x * pn2 + (long long)pn_uv[0] * cn_dot_pn, (long long)nu.y * pn2 + (long long)pn_uv[1] * cn_dot_pn};
+  int32_t cx[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) cx[k] = c3[k] - (n3[k] + (int32_t)div((long long)pn[k] * cn_dot_pn));
+  const unsigned long long cx2 = (unsigned long long)((long long)cx[0] * cx[0] + (long long)cx[1] * cx[1] + (long long)cx[2] * cx[2]);
+  const int32_t nrm = (int32_t)isqrt_fast(cx2 * (unsigned long long)pn2);
+  const long long cx_uv[2] = {(long long)pn_uv[1] * nrm, (long long)(-pn_uv[0]) * nrm};
+  const int32_t a0 = (int32_t)div(x_uv[0] + cx_uv[0]), a1 = (int32_t)div(x_uv[1] + cx_uv[1]);
+  const int32_t b0 = (int32_t)div(x_uv[0] - cx_uv[0]), b1 = (int32_t)div(x_uv[1] - cx_uv[1]);
+  const int32_t ea0 = cur.x - a0, ea1 = cur.y - a1, eb0 = cur.x - b0, eb1 = cur.y - b1;
+  const long long da = (long long)ea0 * ea0 + (long long)ea1 * ea1, db = (long long)eb0 * eb0 + (long long)eb1 * eb1;
+  if (da < db) { pred[0] = a0; pred[1] = a1; return 2; }
+  pred[0] = b0; pred[1] = b1;
+  return 1;
+}
+
 __device__ __forceinline__ void predict_texcoord_body(const uint32_t* __restrict__ seq, const TableDev& t, const QuantDev& q, const QuantDev& pos,
                                                       uint32_t pos_num_points, const uint32_t* __restrict__ rank, uint32_t* __restrict__ symbols,
                                                       uint8_t* __restrict__ orient, AttrStats* stats, uint32_t i0, uint32_t i1, uint32_t istep) {
@@ -811,11 +858,20 @@ __device__ __forceinline__ void predict_texcoord_body(const uint32_t* __restrict
       const int2 pu = __ldg(reinterpret_cast<const int2*>(q.values) + value_index(q, prev_pt));
       if (nu.x == pu.x && nu.y == pu.y) { pred[0] = pu.x; pred[1] = pu.y; done = true; }
       else {
-        long long cp[3] = {0, 0, 0}, np[3] = {0, 0, 0}, pp[3] = {0, 0, 0};
-        int32_t tmp[3];
-        if (curr_pt < pos_num_points) { load_q<3>(pos, value_index(pos, curr_pt), tmp); cp[0] = tmp[0]; cp[1] = tmp[1]; cp[2] = tmp[2]; }
-        if (next_pt < pos_num_points) { load_q<3>(pos, value_index(pos, next_pt), tmp); np[0] = tmp[0]; np[1] = tmp[1]; np[2] = tmp[2]; }
-        if (prev_pt < pos_num_points) { load_q<3>(pos, value_index(pos, prev_pt), tmp); pp[0] = tmp[0]; pp[1] = tmp[1]; pp[2] = tmp[2]; }
+        int32_t c3[3] = {0, 0, 0}, n3[3] = {0, 0, 0}, p3[3] = {0, 0, 0};
+        if (curr_pt < pos_num_points) load_q<3>(pos, value_index(pos, curr_pt), c3);
+        if (next_pt < pos_num_points) load_q<3>(pos, value_index(pos, next_pt), n3);
+        if (prev_pt < pos_num_points) load_q<3>(pos, value_index(pos, prev_pt), p3);
+        // Quantised inputs are small non-negative numbers (13 / 12 bits cover the usual settings): then no product of the
+        // reference's i64 arithmetic can wrap and none of its overflow guards can fire, and most of it fits 32 x 32 -> 64
+        // bit multiplies (texcoord_small). Checked per element on the values themselves, not assumed from the settings.
+        const uint32_t pos_bits = (uint32_t)(c3[0] | c3[1] | c3[2] | n3[0] | n3[1] | n3[2] | p3[0] | p3[1] | p3[2]);
+        const uint32_t uv_bits = (uint32_t)(nu.x | nu.y | pu.x | pu.y | cur.x | cur.y);
+        if (pos_bits < 8192u && uv_bits < 4096u) {
+          oflag = texcoord_small(c3, n3, p3, nu, pu, cur, pred);
+          done = oflag != 0;
+        } else {
+        const long long cp[3] = {c3[0], c3[1], c3[2]}, np[3] = {n3[0], n3[1], n3[2]}, pp[3] = {p3[0], p3[1], p3[2]};
         const long long pn[3] = {sub64w(pp[0], np[0]), sub64w(pp[1], np[1]), sub64w(pp[2], np[2])};
         const unsigned long long pn2 = (unsigned long long)add64w(add64w(mul64w(pn[0], pn[0]), mul64w(pn[1], pn[1])), mul64w(pn[2], pn[2]));
         if (pn2 != 0) {
@@ -860,6 +916,7 @@ __device__ __forceinline__ void predict_texcoord_body(const uint32_t* __restrict
             else { oflag = 1; pred[0] = (int32_t)b0; pred[1] = (int32_t)b1; }
             done = true;
           }
+        }
         }
       }
     }
