@@ -70,11 +70,22 @@ def encode(mesh, writer, cfg=None):
     L = _capi.lib()
     cm, cc, out = mesh.as_c(), cfg.as_c(), _capi.dxo_bytes()
     _check(L.dxo_encode(C.byref(cm), C.byref(cc), C.byref(out)))
-    data = _take(out)
-    if hasattr(writer, "extend"):
-        writer.extend(data)
-    else:
-        writer.write(data)
+    _give(out, writer)
+
+
+def _give(b, writer):
+    """Appends a dxo_bytes result to the writer with ONE copy (straight out of the library's buffer), then frees it."""
+    try:
+        if b.len:
+            view = (C.c_char * b.len).from_address(C.addressof(b.data.contents))
+            if isinstance(writer, bytearray):
+                writer += view
+            elif hasattr(writer, "extend"):
+                writer.extend(bytes(view))
+            else:
+                writer.write(memoryview(view))
+    finally:
+        _capi.lib().dxo_free_bytes(C.byref(b))
 
 
 class Batch:
