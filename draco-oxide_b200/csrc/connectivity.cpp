@@ -630,13 +630,23 @@ class EdgebreakerRun {
     {  // CLERS codes, last symbol first, LSB-first bit packing (symbol_encoder.rs:50-58)
       static const uint8_t kBits[5] = {1, 3, 3, 3, 3};
       static const uint8_t kCode[5] = {0b0, 0b001, 0b011, 0b101, 0b111};
-      ByteSink tmp;
-      tmp.data.reserve(symbols_.size() / 3 + 8);
-      BitPacker bits(tmp);
-      for (size_t i = symbols_.size(); i-- > 0;) bits.put(kBits[symbols_[i]], kCode[symbols_[i]]);
-      bits.finish();
-      w.varint(tmp.size());
-      w.bytes(tmp.data);
+      // the LSB-first packer of common.hpp, unrolled onto a raw buffer: a 64-bit accumulator flushed four bytes at a time
+      std::vector<uint8_t, NoInitAllocator<uint8_t>> buf((symbols_.size() * 3 + 7) / 8 + 16);
+      uint8_t* p = buf.data();
+      uint64_t acc = 0;
+      unsigned fill = 0;
+      const uint8_t* const sym = symbols_.data();
+      for (size_t i = symbols_.size(); i-- > 0;) {
+        const uint8_t s = sym[i];
+        acc |= (uint64_t)kCode[s] << fill;
+        fill += kBits[s];
+        if (fill >= 32) { const uint32_t lo = (uint32_t)acc; memcpy(p, &lo, 4); p += 4; acc >>= 32; fill -= 32; }  // little-endian host
+      }
+      while (fill >= 8) { *p++ = (uint8_t)acc; acc >>= 8; fill -= 8; }
+      if (fill) *p++ = (uint8_t)acc;
+      const size_t nbytes = (size_t)(p - buf.data());
+      w.varint(nbytes);
+      w.bytes(buf.data(), nbytes);
     }
     {  // start-face configurations (:592-607)
       uint64_t zeros = 0;
