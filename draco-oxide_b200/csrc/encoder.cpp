@@ -736,6 +736,7 @@ void MeshJob::upload(DeviceContext& ctx) {
     if (i > 0 && p.scheme == Scheme::Normal && resident && !getenv("DXO_NO_RINGS")) {
       d.ring = dalloc<uint4>(2 * M, s); d.ring_head = dalloc<uint2>(M, s); d.ring_count = dalloc<uint8_t>(M, s);
     }
+    if (i > 0 && p.scheme == Scheme::TexCoord && resident && !getenv("DXO_NO_RINGS")) d.tex_records = dalloc<uint4>(2 * M, s);
     // K4's fast path: {opposite, its point} links and ranks carried in the values' padding component
     if (i == 0) rank_in_w_ = false;
     if (i == 0 && vertex_is_point_ && p.scheme == Scheme::Parallelogram && p.port == Portabilization::Quantize && p.ncomp_q == 3 && !getenv("DXO_NO_K4_FAST")) {
@@ -790,6 +791,14 @@ void MeshJob::upload(DeviceContext& ctx) {
     t.ring = nullptr;
     gpu::launch_normal_rings(d.seq, (uint32_t)sequence_of(i).size(), t, gpu::QuantDev{nullptr, d.map, (uint32_t)plans_[i].ncomp_q}, gpu::QuantDev{nullptr, pd.map, 3},
                              d.ring, d.ring_head, d.ring_count, s);
+    ++ring_launches;
+  }
+  for (size_t i = 1; i < plans_.size(); ++i) {
+    AttrDevice& d = dev_[i];
+    if (!d.tex_records) continue;
+    const AttrDevice& pd = dev_[plans_[i].parent];
+    gpu::launch_texcoord_records(d.seq, (uint32_t)sequence_of(i).size(), table_dev(i), gpu::QuantDev{nullptr, d.map, (uint32_t)plans_[i].ncomp_q},
+                                 gpu::QuantDev{nullptr, pd.map, 3}, plans_[plans_[i].parent].view.num_points, d.rank, d.tex_records, s);
     ++ring_launches;
   }
   layout_launches_ = 1 + (vertex_is_point_ ? 0 : 1) + ring_launches;
@@ -946,7 +955,8 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
         const AttrDevice& pd = dev_[p.parent];
         const gpu::QuantDev pos{pd.quant, pd.map, 3};
         prof.begin("K6_predict_texcoord", 4ull * M + 4 * C + 4 * C + 4 * V + 4 * V + 12 * Upos + 8 * U + 4 * S + M, s);
-        gpu::launch_predict_texcoord(d.seq, M, t, q, pos, plans_[p.parent].view.num_points, d.rank, d.symbols, d.side, d.stats, s);
+        if (d.tex_records) gpu::launch_predict_texcoord_records(d.tex_records, M, q, pos, d.symbols, d.side, d.stats, s);
+        else gpu::launch_predict_texcoord(d.seq, M, t, q, pos, plans_[p.parent].view.num_points, d.rank, d.symbols, d.side, d.stats, s);
         prof.end(s);
         break;
       }

@@ -37,6 +37,7 @@ __device__ __forceinline__ uint32_t cprev(uint32_t c) { return (c % 3u == 0u) ? 
 
 // streaming loads (read once): bypass L1 allocation
 __device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) { return __ldcs(p); }
+__device__ __forceinline__ uint4 ld_stream4(const uint4* p) { return __ldcs(p); }
 
 __device__ __forceinline__ uint32_t opp_of(const TableDev& t, uint32_t c) {
   if (t.seam && t.seam[c]) return kNoneDev;
@@ -838,90 +839,163 @@ __device__ __forceinline__ uint8_t texcoord_small(const int32_t* c3, const int32
   return 1;
 }
 
+// The prediction for an element whose next and previous vertices are sequenced (:118-219), from loaded operands.
+// Returns -1 when the reference falls back, 0 when the prediction carries no orientation bit (equal neighbours), 1 / 2 otherwise.
+__device__ __forceinline__ int texcoord_math(int2 cur, int2 nu, int2 pu, const int32_t* c3, const int32_t* n3, const int32_t* p3, int32_t* pred) {
+  if (nu.x == pu.x && nu.y == pu.y) { pred[0] = pu.x; pred[1] = pu.y; return 0; }
+  // Quantised inputs are small non-negative numbers (13 / 12 bits cover the usual settings): then no product of the
+  // reference's i64 arithmetic can wrap and none of its overflow guards can fire, and most of it fits 32 x 32 -> 64
+  // bit multiplies (texcoord_small). Checked per element on the values themselves, not assumed from the settings.
+  const uint32_t pos_bits = (uint32_t)(c3[0] | c3[1] | c3[2] | n3[0] | n3[1] | n3[2] | p3[0] | p3[1] | p3[2]);
+  const uint32_t uv_bits = (uint32_t)(nu.x | nu.y | pu.x | pu.y | cur.x | cur.y);
+  if (pos_bits < 8192u && uv_bits < 4096u) {
+    const uint8_t f = texcoord_small(c3, n3, p3, nu, pu, cur, pred);
+    return f ? (int)f : -1;
+  }
+  const long long I64MAX = 0x7FFFFFFFFFFFFFFFll;
+  uint8_t oflag = 0;
+  bool done = false;
+  const long long cp[3] = {c3[0], c3[1], c3[2]}, np[3] = {n3[0], n3[1], n3[2]}, pp[3] = {p3[0], p3[1], p3[2]};
+  const long long pn[3] = {sub64w(pp[0], np[0]), sub64w(pp[1], np[1]), sub64w(pp[2], np[2])};
+  const unsigned long long pn2 = (unsigned long long)add64w(add64w(mul64w(pn[0], pn[0]), mul64w(pn[1], pn[1])), mul64w(pn[2], pn[2]));
+  if (pn2 != 0) {
+    const long long cn[3] = {sub64w(cp[0], np[0]), sub64w(cp[1], np[1]), sub64w(cp[2], np[2])};
+    const long long cn_dot_pn = add64w(add64w(mul64w(pn[0], cn[0]), mul64w(pn[1], cn[1])), mul64w(pn[2], cn[2]));
+    const long long pn_uv[2] = {(long long)pu.x - (long long)nu.x, (long long)pu.y - (long long)nu.y};
+    const long long n_uv_absmax = max(labs64((long long)nu.x), labs64((long long)nu.y));
+    const long long pn_uv_absmax = max(labs64(pn_uv[0]), labs64(pn_uv[1]));
+    const long long pn_absmax = max(max(labs64(pn[0]), labs64(pn[1])), labs64(pn[2]));
+    // overflow guards (:139-160); a zero / -1 divisor would panic in the reference and cannot occur for
+    // quantized inputs (pn2 > 0 as i64 for < 2^31-bit coordinates, pn_uv != 0, pn != 0)
+    bool fallback = false;
+    if ((long long)pn2 <= 0) fallback = (long long)pn2 == 0 || n_uv_absmax > I64MAX / (long long)pn2;  // unreachable for quantized input
+    else if (exceeds_max_over(n_uv_absmax, (long long)pn2)) fallback = true;
+    if (fallback) {}
+    else if (pn_uv_absmax <= 0) fallback = pn_uv_absmax == 0 || labs64(cn_dot_pn) > I64MAX / pn_uv_absmax;
+    else if (exceeds_max_over(labs64(cn_dot_pn), pn_uv_absmax)) fallback = true;
+    if (fallback) {}
+    else if (pn_absmax <= 0) fallback = pn_absmax == 0 || labs64(cn_dot_pn) > I64MAX / pn_absmax;
+    else if (exceeds_max_over(labs64(cn_dot_pn), pn_absmax)) fallback = true;
+    if (!fallback) {
+      const DivBy div((long long)pn2);
+      const long long d = (long long)pn2;
+      const long long x_uv[2] = {add64w(mul64w((long long)nu.x, d), mul64w(pn_uv[0], cn_dot_pn)),
+                                 add64w(mul64w((long long)nu.y, d), mul64w(pn_uv[1], cn_dot_pn))};
+      long long cx[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const long long x_pos = add64w(np[k], div(mul64w(pn[k], cn_dot_pn)));
+        cx[k] = sub64w(cp[k], x_pos);
+      }
+      const unsigned long long cx2 = (unsigned long long)add64w(add64w(mul64w(cx[0], cx[0]), mul64w(cx[1], cx[1])), mul64w(cx[2], cx[2]));
+      const long long nrm = (long long)isqrt_fast(cx2 * pn2);
+      const long long cx_uv[2] = {mul64w(pn_uv[1], nrm), mul64w((long long)(0ull - (unsigned long long)pn_uv[0]), nrm)};
+      const long long a0 = div(add64w(x_uv[0], cx_uv[0])), a1 = div(add64w(x_uv[1], cx_uv[1]));
+      const long long b0 = div(sub64w(x_uv[0], cx_uv[0])), b1 = div(sub64w(x_uv[1], cx_uv[1]));
+      const long long ea0 = sub64w((long long)cur.x, a0), ea1 = sub64w((long long)cur.y, a1);
+      const long long eb0 = sub64w((long long)cur.x, b0), eb1 = sub64w((long long)cur.y, b1);
+      const long long da = add64w(mul64w(ea0, ea0), mul64w(ea1, ea1));
+      const long long db = add64w(mul64w(eb0, eb0), mul64w(eb1, eb1));
+      if (da < db) { oflag = 2; pred[0] = (int32_t)a0; pred[1] = (int32_t)a1; }
+      else { oflag = 1; pred[0] = (int32_t)b0; pred[1] = (int32_t)b1; }
+      done = true;
+    }
+  }
+  return done ? (int)oflag : -1;
+}
+
+// K6 with everything that depends on the connectivity alone resolved beforehand (launch_texcoord_records): one 32-byte record
+// per sequence element instead of the chain sequence -> corner -> point / vertex tuples -> ranks -> value indices.
+__global__ void __launch_bounds__(kThreads) texcoord_records_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos,
+                                                                    uint32_t pos_num_points, const uint32_t* __restrict__ rank, uint4* __restrict__ rec) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t c = __ldg(seq + i);
+    const Tri pts = load_tri(t.corner_point4, c), vts = load_tri(t.corner_vertex4, c);
+    uint32_t last = 0xFFFFFFFFu;
+    if (i > 0) {  // previous_value
+      const uint32_t last_v = __ldg(t.corner_vertex + __ldg(seq + i - 1));
+      last = value_index(q, __ldg(t.corner_point + __ldg(t.left_most + last_v)));
+    }
+    const uint32_t flags = (__ldg(rank + vts.next) < i ? 1u : 0u) | (__ldg(rank + vts.prev) < i ? 2u : 0u);
+    auto pv = [&](uint32_t pt) { return pt < pos_num_points ? value_index(pos, pt) : 0xFFFFFFFFu; };
+    rec[2 * (size_t)i] = make_uint4(value_index(q, pts.self), value_index(q, pts.next), value_index(q, pts.prev), last);
+    rec[2 * (size_t)i + 1] = make_uint4(pv(pts.self), pv(pts.next), pv(pts.prev), flags);
+  }
+}
+void launch_texcoord_records(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos, uint32_t pos_num_points, const uint32_t* rank,
+                             uint4* records, cudaStream_t s) {
+  if (n) texcoord_records_kernel<<<grid_for(n), kThreads, 0, s>>>(seq, n, t, q, pos, pos_num_points, rank, records);
+}
+
+__global__ void __launch_bounds__(kThreads, 4) predict_texcoord_rec_kernel(const uint4* __restrict__ rec, uint32_t n, QuantDev q, QuantDev pos,
+                                                                        uint32_t* __restrict__ symbols, uint8_t* __restrict__ orient, AttrStats* stats) {
+  const WrapParams w = wrap_params(stats);
+  uint32_t nz = 0, mxs = 0, err = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const int2* const uv = reinterpret_cast<const int2*>(q.values);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint4 ra = ld_stream4(rec + 2 * (size_t)i), rb = ld_stream4(rec + 2 * (size_t)i + 1);
+    const bool next_seen = rb.w & 1u, both = (rb.w & 3u) == 3u;
+    // every gather is independent of the others: issued together
+    const int2 cur = __ldg(uv + ra.x);
+    int2 nu = make_int2(0, 0), pu = make_int2(0, 0), lu = make_int2(0, 0);
+    int32_t c3[3] = {0, 0, 0}, n3[3] = {0, 0, 0}, p3[3] = {0, 0, 0};
+    if (next_seen) nu = __ldg(uv + ra.y);
+    else if (ra.w != 0xFFFFFFFFu) lu = __ldg(uv + ra.w);
+    if (both) {
+      pu = __ldg(uv + ra.z);
+      if (rb.x != 0xFFFFFFFFu) load_q<3>(pos, rb.x, c3);
+      if (rb.y != 0xFFFFFFFFu) load_q<3>(pos, rb.y, n3);
+      if (rb.z != 0xFFFFFFFFu) load_q<3>(pos, rb.z, p3);
+    }
+    int32_t pred[2];
+    int r = -1;
+    if (both) r = texcoord_math(cur, nu, pu, c3, n3, p3, pred);
+    if (r < 0) {  // fallback_predict (:52-82)
+      if (next_seen) { pred[0] = nu.x; pred[1] = nu.y; }
+      else { pred[0] = lu.x; pred[1] = lu.y; }
+    }
+    orient[i] = r > 0 ? (uint8_t)r : 0;
+    const uint32_t s0 = wrapped_symbol(cur.x, pred[0], w), s1 = wrapped_symbol(cur.y, pred[1], w);
+    reinterpret_cast<uint2*>(symbols)[i] = make_uint2(s0, s1);
+    nz += (s0 != 0) + (s1 != 0);
+    mxs = max(mxs, max(s0, s1));
+    err |= ((s0 | s1) & 0x80000000u) ? kErrNegativeSymbol : 0u;
+  }
+  accumulate_symbol_stats(nz, mxs, err, stats);
+}
+void launch_predict_texcoord_records(const uint4* records, uint32_t n, QuantDev q, QuantDev pos, uint32_t* symbols, uint8_t* orient, AttrStats* stats,
+                                     cudaStream_t s) {
+  if (n) predict_texcoord_rec_kernel<<<grid_for(n), kThreads, 0, s>>>(records, n, q, pos, symbols, orient, stats);
+}
+
 __device__ __forceinline__ void predict_texcoord_body(const uint32_t* __restrict__ seq, const TableDev& t, const QuantDev& q, const QuantDev& pos,
                                                       uint32_t pos_num_points, const uint32_t* __restrict__ rank, uint32_t* __restrict__ symbols,
                                                       uint8_t* __restrict__ orient, AttrStats* stats, uint32_t i0, uint32_t i1, uint32_t istep) {
   const WrapParams w = wrap_params(stats);
   uint32_t nz = 0, mxs = 0, err = 0;
-  const long long I64MAX = 0x7FFFFFFFFFFFFFFFll;
   for (uint32_t i = i0; i < i1; i += istep) {
     const uint32_t c = ld_stream(seq + i);
     const Tri pts = load_tri(t.corner_point4, c), vts = load_tri(t.corner_vertex4, c);
     const uint32_t next_pt = pts.next, prev_pt = pts.prev, curr_pt = pts.self;
     const int2 cur = __ldg(reinterpret_cast<const int2*>(q.values) + value_index(q, curr_pt));
     int32_t pred[2];
-    uint8_t oflag = 0;  // 0: no orientation bit, 1: bit = false, 2: bit = true
-    bool done = false;
+    int r = -1;
     const bool next_seen = __ldg(rank + vts.next) < i;
     if (next_seen && __ldg(rank + vts.prev) < i) {
       const int2 nu = __ldg(reinterpret_cast<const int2*>(q.values) + value_index(q, next_pt));
       const int2 pu = __ldg(reinterpret_cast<const int2*>(q.values) + value_index(q, prev_pt));
-      if (nu.x == pu.x && nu.y == pu.y) { pred[0] = pu.x; pred[1] = pu.y; done = true; }
-      else {
-        int32_t c3[3] = {0, 0, 0}, n3[3] = {0, 0, 0}, p3[3] = {0, 0, 0};
+      int32_t c3[3] = {0, 0, 0}, n3[3] = {0, 0, 0}, p3[3] = {0, 0, 0};
+      if (!(nu.x == pu.x && nu.y == pu.y)) {
         if (curr_pt < pos_num_points) load_q<3>(pos, value_index(pos, curr_pt), c3);
         if (next_pt < pos_num_points) load_q<3>(pos, value_index(pos, next_pt), n3);
         if (prev_pt < pos_num_points) load_q<3>(pos, value_index(pos, prev_pt), p3);
-        // Quantised inputs are small non-negative numbers (13 / 12 bits cover the usual settings): then no product of the
-        // reference's i64 arithmetic can wrap and none of its overflow guards can fire, and most of it fits 32 x 32 -> 64
-        // bit multiplies (texcoord_small). Checked per element on the values themselves, not assumed from the settings.
-        const uint32_t pos_bits = (uint32_t)(c3[0] | c3[1] | c3[2] | n3[0] | n3[1] | n3[2] | p3[0] | p3[1] | p3[2]);
-        const uint32_t uv_bits = (uint32_t)(nu.x | nu.y | pu.x | pu.y | cur.x | cur.y);
-        if (pos_bits < 8192u && uv_bits < 4096u) {
-          oflag = texcoord_small(c3, n3, p3, nu, pu, cur, pred);
-          done = oflag != 0;
-        } else {
-        const long long cp[3] = {c3[0], c3[1], c3[2]}, np[3] = {n3[0], n3[1], n3[2]}, pp[3] = {p3[0], p3[1], p3[2]};
-        const long long pn[3] = {sub64w(pp[0], np[0]), sub64w(pp[1], np[1]), sub64w(pp[2], np[2])};
-        const unsigned long long pn2 = (unsigned long long)add64w(add64w(mul64w(pn[0], pn[0]), mul64w(pn[1], pn[1])), mul64w(pn[2], pn[2]));
-        if (pn2 != 0) {
-          const long long cn[3] = {sub64w(cp[0], np[0]), sub64w(cp[1], np[1]), sub64w(cp[2], np[2])};
-          const long long cn_dot_pn = add64w(add64w(mul64w(pn[0], cn[0]), mul64w(pn[1], cn[1])), mul64w(pn[2], cn[2]));
-          const long long pn_uv[2] = {(long long)pu.x - (long long)nu.x, (long long)pu.y - (long long)nu.y};
-          const long long n_uv_absmax = max(labs64((long long)nu.x), labs64((long long)nu.y));
-          const long long pn_uv_absmax = max(labs64(pn_uv[0]), labs64(pn_uv[1]));
-          const long long pn_absmax = max(max(labs64(pn[0]), labs64(pn[1])), labs64(pn[2]));
-          // overflow guards (:139-160); a zero / -1 divisor would panic in the reference and cannot occur for
-          // quantized inputs (pn2 > 0 as i64 for < 2^31-bit coordinates, pn_uv != 0, pn != 0)
-          bool fallback = false;
-          if ((long long)pn2 <= 0) fallback = (long long)pn2 == 0 || n_uv_absmax > I64MAX / (long long)pn2;  // unreachable for quantized input
-          else if (exceeds_max_over(n_uv_absmax, (long long)pn2)) fallback = true;
-          if (fallback) {}
-          else if (pn_uv_absmax <= 0) fallback = pn_uv_absmax == 0 || labs64(cn_dot_pn) > I64MAX / pn_uv_absmax;
-          else if (exceeds_max_over(labs64(cn_dot_pn), pn_uv_absmax)) fallback = true;
-          if (fallback) {}
-          else if (pn_absmax <= 0) fallback = pn_absmax == 0 || labs64(cn_dot_pn) > I64MAX / pn_absmax;
-          else if (exceeds_max_over(labs64(cn_dot_pn), pn_absmax)) fallback = true;
-          if (!fallback) {
-            const DivBy div((long long)pn2);
-            const long long d = (long long)pn2;
-            const long long x_uv[2] = {add64w(mul64w((long long)nu.x, d), mul64w(pn_uv[0], cn_dot_pn)),
-                                       add64w(mul64w((long long)nu.y, d), mul64w(pn_uv[1], cn_dot_pn))};
-            long long cx[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              const long long x_pos = add64w(np[k], div(mul64w(pn[k], cn_dot_pn)));
-              cx[k] = sub64w(cp[k], x_pos);
-            }
-            const unsigned long long cx2 = (unsigned long long)add64w(add64w(mul64w(cx[0], cx[0]), mul64w(cx[1], cx[1])), mul64w(cx[2], cx[2]));
-            const long long nrm = (long long)isqrt_fast(cx2 * pn2);
-            const long long cx_uv[2] = {mul64w(pn_uv[1], nrm), mul64w((long long)(0ull - (unsigned long long)pn_uv[0]), nrm)};
-            const long long a0 = div(add64w(x_uv[0], cx_uv[0])), a1 = div(add64w(x_uv[1], cx_uv[1]));
-            const long long b0 = div(sub64w(x_uv[0], cx_uv[0])), b1 = div(sub64w(x_uv[1], cx_uv[1]));
-            const long long ea0 = sub64w((long long)cur.x, a0), ea1 = sub64w((long long)cur.y, a1);
-            const long long eb0 = sub64w((long long)cur.x, b0), eb1 = sub64w((long long)cur.y, b1);
-            const long long da = add64w(mul64w(ea0, ea0), mul64w(ea1, ea1));
-            const long long db = add64w(mul64w(eb0, eb0), mul64w(eb1, eb1));
-            if (da < db) { oflag = 2; pred[0] = (int32_t)a0; pred[1] = (int32_t)a1; }
-            else { oflag = 1; pred[0] = (int32_t)b0; pred[1] = (int32_t)b1; }
-            done = true;
-          }
-        }
-        }
       }
+      r = texcoord_math(cur, nu, pu, c3, n3, p3, pred);
     }
-    if (!done) texcoord_fallback(seq, i, next_seen, next_pt, t, q, pred);
-    orient[i] = oflag;
+    if (r < 0) texcoord_fallback(seq, i, next_seen, next_pt, t, q, pred);
+    orient[i] = r > 0 ? (uint8_t)r : 0;
     const uint32_t s0 = wrapped_symbol(cur.x, pred[0], w), s1 = wrapped_symbol(cur.y, pred[1], w);
     reinterpret_cast<uint2*>(symbols)[i] = make_uint2(s0, s1);
     nz += (s0 != 0) + (s1 != 0);

@@ -99,6 +99,13 @@ void launch_seq_prepare(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q,
 // ---- K4-K7: prediction + transform + symbolization, one thread per sequence element ----
 void launch_predict_parallelogram(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, const uint32_t* rank, uint32_t* symbols, AttrStats* stats, cudaStream_t s);
 void launch_predict_normal(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos, uint32_t* symbols, uint8_t* flips, AttrStats* stats, cudaStream_t s);
+// K6 from records (resident sessions): launch_texcoord_records resolves, once per upload, everything that depends on the
+// connectivity and the point maps alone — per sequence element two uint4: {value index of the vertex, of next, of prev, of the
+// vertex sequenced just before (0xFFFFFFFF = none)}, {position-value index of the three (0xFFFFFFFF = outside), -, flags}.
+void launch_texcoord_records(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos, uint32_t pos_num_points, const uint32_t* rank,
+                             uint4* records, cudaStream_t s);
+void launch_predict_texcoord_records(const uint4* records, uint32_t n, QuantDev q, QuantDev pos, uint32_t* symbols, uint8_t* orient, AttrStats* stats,
+                                     cudaStream_t s);
 void launch_predict_texcoord(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos, uint32_t pos_num_points, const uint32_t* rank, uint32_t* symbols, uint8_t* orient, AttrStats* stats, cudaStream_t s);
 void launch_predict_delta(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, uint32_t* symbols, AttrStats* stats, cudaStream_t s);
 // ---- K8: symbol histogram (symbol_coding.rs:149-157) ----
