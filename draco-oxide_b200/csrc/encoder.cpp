@@ -732,14 +732,18 @@ void MeshJob::upload(DeviceContext& ctx) {
     if (p.port == Portabilization::ToBits && p.ncomp_q != 3) d.quant = (int32_t*)d.values;
     else d.quant = dalloc<int32_t>(U * qstride, s);
     if (i > 0) d.corner_vertex4 = dalloc<uint4>(ut_.num_faces, s);
+    // Resident sessions resolve the predictors' operand indices once per upload (rings / records, kernels.cu) instead of
+    // chasing them through the tables in every step; DXO_NO_RINGS keeps the per-step forms.
+    const bool records = resident && !getenv("DXO_NO_RINGS");
     if (i > 0 && p.scheme == Scheme::Normal) d.fan_link = dalloc<uint2>(C, s);  // fan walks read one link per swing
-    if (i > 0 && p.scheme == Scheme::Normal && resident && !getenv("DXO_NO_RINGS")) {
+    if (i > 0 && p.scheme == Scheme::Normal && records) {
       d.ring = dalloc<uint4>(2 * M, s); d.ring_head = dalloc<uint2>(M, s); d.ring_count = dalloc<uint8_t>(M, s);
     }
-    if (i > 0 && p.scheme == Scheme::TexCoord && resident && !getenv("DXO_NO_RINGS")) d.tex_records = dalloc<uint4>(2 * M, s);
+    if (i > 0 && p.scheme == Scheme::TexCoord && records) d.tex_records = dalloc<uint4>(2 * M, s);
+    if (p.scheme == Scheme::Parallelogram && records) d.para_records = dalloc<uint4>(M, s);
     // K4's fast path: {opposite, its point} links and ranks carried in the values' padding component
     if (i == 0) rank_in_w_ = false;
-    if (i == 0 && vertex_is_point_ && p.scheme == Scheme::Parallelogram && p.port == Portabilization::Quantize && p.ncomp_q == 3 && !getenv("DXO_NO_K4_FAST")) {
+    if (i == 0 && !records && vertex_is_point_ && p.scheme == Scheme::Parallelogram && p.port == Portabilization::Quantize && p.ncomp_q == 3 && !getenv("DXO_NO_K4_FAST")) {
       d.fan_link = dalloc<uint2>(C, s);
       rank_in_w_ = true;
     }
@@ -799,6 +803,13 @@ void MeshJob::upload(DeviceContext& ctx) {
     const AttrDevice& pd = dev_[plans_[i].parent];
     gpu::launch_texcoord_records(d.seq, (uint32_t)sequence_of(i).size(), table_dev(i), gpu::QuantDev{nullptr, d.map, (uint32_t)plans_[i].ncomp_q},
                                  gpu::QuantDev{nullptr, pd.map, 3}, plans_[plans_[i].parent].view.num_points, d.rank, d.tex_records, s);
+    ++ring_launches;
+  }
+  for (size_t i = 0; i < plans_.size(); ++i) {
+    AttrDevice& d = dev_[i];
+    if (!d.para_records) continue;
+    gpu::launch_parallelogram_records(d.seq, (uint32_t)sequence_of(i).size(), table_dev(i), gpu::QuantDev{nullptr, d.map, (uint32_t)plans_[i].ncomp_q}, d.rank,
+                                      d.para_records, s);
     ++ring_launches;
   }
   layout_launches_ = 1 + (vertex_is_point_ ? 0 : 1) + ring_launches;
@@ -940,7 +951,8 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
     switch (p.scheme) {
       case Scheme::Parallelogram:
         prof.begin("K4_predict_parallelogram", 4ull * M + 4 * C + 4 * C + 4 * V + 4 * V + 4ull * p.ncomp_q * U + 4 * S, s);
-        gpu::launch_predict_parallelogram(d.seq, M, t, q, d.rank, d.symbols, d.stats, s);
+        if (d.para_records) gpu::launch_predict_parallelogram_records(d.para_records, M, q, d.symbols, d.stats, s);
+        else gpu::launch_predict_parallelogram(d.seq, M, t, q, d.rank, d.symbols, d.stats, s);
         prof.end(s);
         break;
       case Scheme::Normal: {

@@ -114,6 +114,7 @@ struct AttrDevice {
   uint32_t *corner_vertex = nullptr, *left_most = nullptr, *seq = nullptr; uint8_t* seam = nullptr; uint4* corner_vertex4 = nullptr; uint2* fan_link = nullptr;
   uint4* ring = nullptr; uint2* ring_head = nullptr; uint8_t* ring_count = nullptr;  // K5's flattened fans (resident sessions)
   uint4* tex_records = nullptr;  // K6's per-element operand indices (resident sessions)
+  uint4* para_records = nullptr;  // K4's per-element operand indices (resident sessions)
   uint8_t* side_out = nullptr; void* side_scratch = nullptr; size_t side_scratch_bytes = 0;  // [8-byte scalars][flags (+1)] for the host coder
   // intermediates / outputs
   int32_t* quant = nullptr; uint32_t *rank = nullptr, *symbols = nullptr, *hist = nullptr, *work = nullptr;

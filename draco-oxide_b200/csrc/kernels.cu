@@ -466,6 +466,80 @@ __global__ void __launch_bounds__(kThreads) predict_parallelogram_kernel(const u
   predict_parallelogram_body<N>(seq, t, q, rank, symbols, stats, blockIdx.x * blockDim.x + threadIdx.x, n, gridDim.x * blockDim.x);
 }
 
+// K4 from records (resident sessions): whether an element has its parallelogram — an opposite corner whose vertex and the
+// two neighbours are sequenced before it — and which values it then reads depend on the connectivity alone, so
+// launch_parallelogram_records resolves them once per upload: {value index of the vertex, next, prev, opposite}, or
+// {vertex, the vertex sequenced just before (0xFFFFFFFF = none), 0xFFFFFFFF, -} for the fallback. The step then costs one
+// 16-byte record and two to four independent value gathers per element.
+constexpr uint32_t kNoRecord = 0xFFFFFFFFu;
+__global__ void __launch_bounds__(kThreads) parallelogram_records_kernel(const uint32_t* __restrict__ seq, uint32_t n, TableDev t, QuantDev q,
+                                                                         const uint32_t* __restrict__ rank, uint4* __restrict__ rec) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t c = __ldg(seq + i);
+    const uint32_t o = opp_of(t, c);
+    const Tri pts = load_tri(t.corner_point4, c);
+    const Tri vts = t.vertex_is_point ? pts : load_tri(t.corner_vertex4, c);
+    bool para = false;
+    uint32_t op = 0;
+    if (o != kNoneDev) {
+      op = __ldg(t.corner_point + o);
+      const uint32_t ov = t.vertex_is_point ? op : __ldg(t.corner_vertex + o);
+      para = __ldg(rank + ov) < i && __ldg(rank + vts.next) < i && __ldg(rank + vts.prev) < i;
+    }
+    const uint32_t self = value_index(q, pts.self);
+    if (para) rec[i] = make_uint4(self, value_index(q, pts.next), value_index(q, pts.prev), value_index(q, op));
+    else {
+      uint32_t last = kNoRecord;
+      if (i > 0) last = value_index(q, __ldg(t.corner_point + __ldg(t.left_most + __ldg(t.corner_vertex + __ldg(seq + i - 1)))));  // previous_value
+      rec[i] = make_uint4(self, last, kNoRecord, 0u);
+    }
+  }
+}
+void launch_parallelogram_records(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, const uint32_t* rank, uint4* records, cudaStream_t s) {
+  if (n) parallelogram_records_kernel<<<grid_for(n), kThreads, 0, s>>>(seq, n, t, q, rank, records);
+}
+template <int N>
+__global__ void __launch_bounds__(kThreads) predict_parallelogram_rec_kernel(const uint4* __restrict__ rec, uint32_t n, QuantDev q,
+                                                                             uint32_t* __restrict__ symbols, AttrStats* stats) {
+  const WrapParams w = wrap_params(stats);
+  uint32_t nz = 0, mxs = 0, err = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint4 r = ld_stream4(rec + i);
+    int32_t orig[N], pred[N];
+    load_q<N>(q, r.x, orig);
+    if (r.z != kNoRecord) {
+      int32_t qa[N], qb[N], qd[N];
+      load_q<N>(q, r.y, qa); load_q<N>(q, r.z, qb); load_q<N>(q, r.w, qd);
+#pragma unroll
+      for (int k = 0; k < N; ++k) pred[k] = (int32_t)((uint32_t)qa[k] + (uint32_t)qb[k] - (uint32_t)qd[k]);
+    } else if (r.y != kNoRecord) {
+      load_q<N>(q, r.y, pred);
+    } else {
+#pragma unroll
+      for (int k = 0; k < N; ++k) pred[k] = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const uint32_t s = wrapped_symbol(orig[k], pred[k], w);
+      symbols[(uint64_t)i * N + k] = s;
+      nz += s != 0; mxs = max(mxs, s); err |= (s & 0x80000000u) ? kErrNegativeSymbol : 0u;
+    }
+  }
+  accumulate_symbol_stats(nz, mxs, err, stats);
+}
+void launch_predict_parallelogram_records(const uint4* records, uint32_t n, QuantDev q, uint32_t* symbols, AttrStats* stats, cudaStream_t s) {
+  if (!n) return;
+  const int g = grid_for(n);
+  switch (q.num_components) {
+    case 1: predict_parallelogram_rec_kernel<1><<<g, kThreads, 0, s>>>(records, n, q, symbols, stats); break;
+    case 2: predict_parallelogram_rec_kernel<2><<<g, kThreads, 0, s>>>(records, n, q, symbols, stats); break;
+    case 3: predict_parallelogram_rec_kernel<3><<<g, kThreads, 0, s>>>(records, n, q, symbols, stats); break;
+    default: predict_parallelogram_rec_kernel<4><<<g, kThreads, 0, s>>>(records, n, q, symbols, stats); break;
+  }
+}
+
 void launch_predict_parallelogram(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, const uint32_t* rank, uint32_t* symbols, AttrStats* stats, cudaStream_t s) {
   const int g = grid_for(n);
   switch (q.num_components) {

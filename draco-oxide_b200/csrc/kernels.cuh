@@ -97,6 +97,10 @@ void launch_oct_quantize(const float* normals, uint64_t num_values, int32_t* out
 // ---- sequence preparation: rank[vertex] = position in the sequence, WrappedDifference min/max ----
 void launch_seq_prepare(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, uint32_t* rank, bool want_minmax, AttrStats* stats, cudaStream_t s);
 // ---- K4-K7: prediction + transform + symbolization, one thread per sequence element ----
+// K4 from records (resident sessions, see kernels.cu): per sequence element {value index of the vertex, next, prev, opposite}
+// when the parallelogram applies, {vertex, vertex sequenced just before or 0xFFFFFFFF, 0xFFFFFFFF, -} otherwise.
+void launch_parallelogram_records(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, const uint32_t* rank, uint4* records, cudaStream_t s);
+void launch_predict_parallelogram_records(const uint4* records, uint32_t n, QuantDev q, uint32_t* symbols, AttrStats* stats, cudaStream_t s);
 void launch_predict_parallelogram(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, const uint32_t* rank, uint32_t* symbols, AttrStats* stats, cudaStream_t s);
 void launch_predict_normal(const uint32_t* seq, uint32_t n, TableDev t, QuantDev q, QuantDev pos, uint32_t* symbols, uint8_t* flips, AttrStats* stats, cudaStream_t s);
 // K6 from records (resident sessions): launch_texcoord_records resolves, once per upload, everything that depends on the
