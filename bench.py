@@ -68,15 +68,15 @@ def host_threads():
 
 
 def default_sessions(world):
-    """(sessions per GPU, scarce host threads?) from the host threads this GPU can count on. With threads to spare a session
-    keeps two side-stream coder threads busy and its main thread spins in the waits (fastest); when host threads are scarce
-    (e.g. 32 threads for 8 GPUs) a session is ONE thread that sleeps in its waits (DXO_BLOCKING_WAIT) and codes both side
-    streams itself in one interleaved loop (DXO_SIDE_INLINE), with a few more sessions than threads so that the device
-    always has a step queued."""
+    """(sessions per GPU, replay the step as a CUDA graph?) from the host threads this GPU can count on. A session is ONE host
+    thread: it replays its step as one CUDA graph, spins in its waits and codes both side streams itself in one interleaved
+    loop (DXO_SIDE_INLINE) — measured on one B200 (tools/session_modes_sweep.sh, Mvertices/s):
+      16 threads: helpers + no graph 8 / 12 / 16 / 24 sessions 1981 / 2053 / 2021 / 2101; inline + graph 2186 / 2255 / 2356 / 2489
+       8 threads: inline + graph, spinning 6 / 12 / 24 sessions 2354 / 2370 / 2363; sleeping waits 1912 / 2349 / 2315
+       4 threads: inline + graph, spinning 1607 / 1564 / 1599; sleeping waits 1317 / 1305 / 1622
+    so: one and a half sessions per thread (6 … 24), spinning waits unless DXO_BLOCKING_WAIT is set by the caller."""
     per_gpu = max(1, host_threads() // max(1, world))
-    if per_gpu >= 15:
-        return max(1, min(12, per_gpu * 3 // 4)), False  # measured on 16 threads (round 2): 6 sessions 1738, 8: 1850, 10: 1900, 12: 1921, 16: 1872 Mvertices/s
-    return max(2, min(8, per_gpu + 2)), True
+    return max(6, min(24, per_gpu * 3 // 2)), True
 
 
 def make_mesh(workload):
@@ -426,9 +426,7 @@ def main():
         run_reference(args, rank, world)
         return
 
-    if args.sessions <= 0 and default_sessions(world)[1]:
-        os.environ.setdefault("DXO_BLOCKING_WAIT", "1")  # read when a thread's device context is created
-        os.environ.setdefault("DXO_SIDE_INLINE", "1")
+    os.environ.setdefault("DXO_SIDE_INLINE", "1")  # read by the library when a session runs; DXO_SIDE_INLINE=0 gives the helper threads back
     # one process per GPU: each rank's batch entry gets its share of the host threads, not all of them
     os.environ.setdefault("DXO_BATCH_WORKERS", str(max(2, host_threads() // max(1, world))))
     # config 4's primitives are generated by forked numpy workers: before this process holds a CUDA context
@@ -652,7 +650,7 @@ def main():
             "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32->i32/u32 (bit-exact integer pipeline)", "data": "synthetic",
             "config": {"workload": desc, "units_per_step_per_gpu": f"{S} meshes ({S} concurrent resident sessions of the workload mesh)",
-                       "host_threads": host_threads(), "host_waits": "blocking" if os.environ.get("DXO_BLOCKING_WAIT") else "spinning", "graph_replay": bool(graph), "side_streams": "inline, interleaved" if os.environ.get("DXO_SIDE_INLINE") else "two helper threads per session",
+                       "host_threads": host_threads(), "host_waits": "blocking" if os.environ.get("DXO_BLOCKING_WAIT") else "spinning", "graph_replay": bool(graph), "side_streams": "inline, interleaved" if os.environ.get("DXO_SIDE_INLINE", "0") != "0" else "two helper threads per session",
                        "parallelism": f"{world} independent replicas, no collective",
                        "l2": (f"no flush needed: between two steps of a session the other {S - 1} sessions run theirs — {S} x "
                               f"{sum(k['algorithmic_bytes_per_launch'] * k['launches_per_step'] for k in kernels) / 1e6:.0f} MB of algorithmic kernel traffic per step "

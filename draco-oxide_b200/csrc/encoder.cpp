@@ -1105,7 +1105,8 @@ void MeshJob::download(DeviceContext& ctx) {
   results_.resize(plans_.size());
   // side streams: start a host worker per stream as soon as its flags have landed — or, with DXO_SIDE_INLINE=1 (hosts with
   // few threads per GPU), code them on this thread, two at a time in one interleaved loop, while the device runs K8-K10
-  static const bool side_inline = getenv("DXO_SIDE_INLINE") != nullptr;
+  static const bool side_inline_env = getenv("DXO_SIDE_INLINE") != nullptr && getenv("DXO_SIDE_INLINE")[0] != '0';
+  const bool side_inline = side_inline_env || inline_host;  // many encodes in flight: no helper threads for this either
   std::vector<std::future<void>> workers;
   std::vector<size_t> inline_streams;
   for (size_t i = 0; i < plans_.size(); ++i) {
