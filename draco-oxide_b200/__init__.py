@@ -12,6 +12,8 @@ calls raise when the library or a CUDA device is missing.
 """
 import ctypes as C
 
+import numpy as np
+
 from . import _capi
 from .mesh import Attribute, AttributeDomain, AttributeType, ComponentDataType, Mesh  # noqa: F401
 
@@ -289,6 +291,14 @@ def last_timing():
         "kernels": [{"name": t.kernels[i].name.decode(), "ms": t.kernels[i].ms,
                      "algorithmic_bytes": t.kernels[i].algorithmic_bytes} for i in range(t.num_kernels)],
     }
+
+
+def encode_bits(bits, zero_prob, mode=1):
+    """The binary rANS coder behind the side streams (host only): mode 0 = bit by bit, 1 = as the encoder runs it."""
+    b = np.ascontiguousarray(bits, dtype=np.uint8)
+    out = _capi.dxo_bytes()
+    _check(_capi.lib().dxo_encode_bits(b.ctypes.data_as(C.POINTER(C.c_uint8)), b.size, int(zero_prob), int(mode), C.byref(out)))
+    return _take(out)
 
 
 def device_count():

@@ -72,7 +72,7 @@ EXPORTED = [
     "dxo_config_default", "dxo_encode", "dxo_encode_batch", "dxo_free_bytes", "dxo_strerror",
     "dxo_device_count", "dxo_session_create", "dxo_connectivity_create", "dxo_session_run_steps", "dxo_session_run", "dxo_session_destroy",
     "dxo_set_profiling", "dxo_last_timing", "dxo_session_set_trace", "dxo_session_trace_get",
-    "dxo_corner_table_opposites", "dxo_encode_symbols",
+    "dxo_corner_table_opposites", "dxo_encode_symbols", "dxo_encode_bits",
     "dxo_mesh_build", "dxo_built_mesh_view", "dxo_built_mesh_free", "dxo_dedup_values", "dxo_attribute_bounds", "dxo_encode_glb",
 ]
 
@@ -126,6 +126,8 @@ def lib():
     L.dxo_corner_table_opposites.restype = C.c_int
     L.dxo_encode_symbols.argtypes = [C.POINTER(C.c_uint32), C.c_uint64, C.c_int, C.POINTER(dxo_bytes), C.POINTER(C.c_float)]
     L.dxo_encode_symbols.restype = C.c_int
+    L.dxo_encode_bits.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.c_uint8, C.c_int, C.POINTER(dxo_bytes)]
+    L.dxo_encode_bits.restype = C.c_int
     L.dxo_mesh_build.argtypes = [C.POINTER(C.c_uint32), C.c_uint64, C.POINTER(dxo_attribute), C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
     L.dxo_mesh_build.restype = C.c_int
     L.dxo_built_mesh_view.argtypes = [C.c_void_p, C.POINTER(dxo_mesh)]

@@ -360,6 +360,17 @@ int dxo_session_trace_get(dxo_session* s, const char* key, const void** data, ui
   return DXO_OK;
 }
 
+int dxo_encode_bits(const uint8_t* bits, uint64_t n, uint8_t zero_prob, int mode, dxo_bytes* out) {
+  if (!out || (!bits && n) || zero_prob == 0) return DXO_ERR_INVALID_ARGUMENT;
+  out->data = nullptr; out->len = 0;
+  return guarded([&] {
+    std::vector<uint8_t> bytes;
+    if (mode == 0) { ByteSink sink; rabs_encode(bits, (size_t)n, false, zero_prob, sink); bytes = std::move(sink.data); }
+    else rabs_encode_forward(bits, (size_t)n, zero_prob, bytes);
+    if (int st = give(bytes, out)) throw Error(st, "out of memory");
+  });
+}
+
 // encode_symbols(symbols, _, SymbolEncodingMethod::DirectCoded, writer) on the device:
 // histogram (K8) -> table (K9) -> rANS (K10). Output = method byte, bit_length byte,
 // leb128 #symbols + table, leb128 payload size, payload — what the reference writes.

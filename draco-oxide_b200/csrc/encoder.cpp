@@ -1016,6 +1016,21 @@ void MeshJob::launch(DeviceContext& ctx, Profile& prof) {
 // normals — flips in sequence order, zero_prob from the zero count (mesh_normal_prediction.rs:147-163);
 // texcoords — order-preserving compaction of the orientation flags, zero_prob from the forward
 // transitions over len + 0.001, backward-delta bits written forward (mesh_prediction_for_texture_coordinates.rs:221-260).
+// bits[k] = (o[k] == o[k + 1]) with o[n] = true (2), coded in order (mesh_prediction_for_texture_coordinates.rs:247-260). A stream skewed
+// enough for the table-driven coder gets its delta bits materialised first (a vectorisable pass) so that the rare ones can
+// be found eight at a time; otherwise they are formed inside the coder's loop.
+static void encode_orientation_deltas(const uint8_t* o, size_t n, uint8_t zero_prob, std::vector<uint8_t>& out) {
+  if (n && rabs_sparse_applies(n, zero_prob, 0)) {
+    U8Array d(n);
+    uint8_t* const dp = d.data();
+    for (size_t k = 0; k + 1 < n; ++k) dp[k] = o[k] == o[k + 1];
+    dp[n - 1] = o[n - 1] == 2;
+    rabs_encode_forward(dp, n, zero_prob, out);
+    return;
+  }
+  rabs_encode_forward_fn(n, zero_prob, out, [o, n](size_t k) { return (uint8_t)(o[k] == (k + 1 < n ? o[k + 1] : (uint8_t)2)); });
+}
+
 void MeshJob::encode_side_stream(size_t att) {
   AttrResult& r = results_[att];
   uint32_t scalars[2];
@@ -1032,8 +1047,7 @@ void MeshJob::encode_side_stream(size_t att) {
     // flags[0..n) = orientation values (1 = false, 2 = true) in order, scalars[1] = forward transitions; the delta bits
     // bits[k] = (o[k] == o[k+1]), o[len] = true, are formed inside the coder's loop
     r.side_zero_prob = side_stream_zero_prob(scalars[1], (float)n + 0.001f);
-    rabs_encode_forward_fn(n, r.side_zero_prob, r.side_payload,
-                           [flags, n](size_t k) { return (uint8_t)(flags[k] == (k + 1 < n ? flags[k + 1] : (uint8_t)2)); });
+    encode_orientation_deltas(flags, n, r.side_zero_prob, r.side_payload);
   }
 }
 
@@ -1057,7 +1071,9 @@ void MeshJob::encode_side_stream_pair(size_t ia, size_t ib) {
     memcpy(sa, results_[ia].side, 8);
     memcpy(sb, results_[ib].side, 8);
     const bool za = a.normal && sa[1] == 0, zb = b.normal && sb[1] == 0;
-    if (za || zb) {
+    // ... and a stream skewed enough for the table-driven coder (rabs.cpp) gains nothing from sharing a loop either
+    const bool sparse = rabs_sparse_applies(a.n, a.p0, 0) || rabs_sparse_applies(b.n, b.p0, 0);
+    if (za || zb || sparse) {
       if (za) rabs_encode_zero_run(a.n, a.p0, results_[ia].side_payload); else encode_side_stream(ia);
       if (zb) rabs_encode_zero_run(b.n, b.p0, results_[ib].side_payload); else encode_side_stream(ib);
       return;
@@ -1095,8 +1111,7 @@ void MeshJob::encode_side_stream_from_flags(size_t att, const uint8_t* flags, si
   }
   r.side_count = (uint32_t)m;
   r.side_zero_prob = side_stream_zero_prob(transitions, (float)m + 0.001f);
-  const uint8_t* v = o.data();
-  rabs_encode_forward_fn(m, r.side_zero_prob, r.side_payload, [v, m](size_t k) { return (uint8_t)(v[k] == (k + 1 < m ? v[k + 1] : (uint8_t)2)); });
+  encode_orientation_deltas(o.data(), m, r.side_zero_prob, r.side_payload);
 }
 
 constexpr size_t kStatsSlot = 1024;  // pinned_buffer slot of the per-attribute scalars (attribute slots are 2i, 2i+1)

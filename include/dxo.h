@@ -208,6 +208,12 @@ int dxo_session_trace_get(dxo_session* s, const char* key, const void** data, ui
  * floats) receives the device time of the histogram, table and rANS kernels. */
 int dxo_encode_symbols(const uint32_t* symbols, uint64_t n, int device, dxo_bytes* out, float* kernel_ms);
 
+/* RabsCoder::new / write / flush (encode/entropy/rans.rs:71-127) over a whole bit sequence, in the order given: the host
+ * coder behind every binary side stream (seam flags, flips, orientations). bits: n bytes, zero / non-zero. zero_prob in
+ * [1, 255]. mode 0 = the bit-by-bit coder, 1 = the coder the encoder uses (table-driven for long, heavily skewed
+ * streams; same bytes). Host only: needs no device. */
+int dxo_encode_bits(const uint8_t* bits, uint64_t n, uint8_t zero_prob, int mode, dxo_bytes* out);
+
 /* Corner-table build on the device (half-edge matching by radix sort;
  * replaces CornerTable::compute_table, core/corner_table/mod.rs:252-340).
  * vertex_of_corner: 3*num_faces vertex ids. opposite_out: 3*num_faces entries,
