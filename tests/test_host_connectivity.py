@@ -85,3 +85,36 @@ def test_random_face_soups(orc):
         _compare(orc, m)
         done += 1
     assert done > 50
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fuzz_irregular_meshes_host_passes(orc, seed):
+    """Random triangle soups (non-manifold edges and vertices, many components, interior-start components) and grids with
+    flipped faces and welded points through the host passes alone: corner tables, traversal, the seam streams derived from
+    the traversal's symbols, the sequencers (which stop once every face is visited) — same bytes and tables as the oracle."""
+    rng = np.random.default_rng(500 + seed)
+    if seed % 2 == 0:
+        n_pts, n_faces = 400 + 150 * seed, 900 + 300 * seed
+        faces = rng.integers(0, n_pts, (n_faces, 3))
+        faces = faces[(faces[:, 0] != faces[:, 1]) & (faces[:, 1] != faces[:, 2]) & (faces[:, 0] != faces[:, 2])].astype(np.uint32)
+        pos = rng.integers(0, 25, (n_pts, 3)).astype(np.float32) * 0.25
+        nrm = rng.normal(size=(n_pts, 3)).astype(np.float32)
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        uv = rng.integers(0, 12, (n_pts, 2)).astype(np.float32) / 12
+    else:
+        g = synth.grid_mesh(30 + seed, 25, 300 + seed)
+        faces = g.faces.copy()
+        flip = rng.random(faces.shape[0]) < 0.04
+        faces[flip] = faces[flip][:, ::-1]
+        pts = [a.values if a.point_to_value is None else a.values[a.point_to_value] for a in g.attributes]
+        pos, nrm, uv = (p.copy() for p in pts)
+        weld = rng.integers(0, pos.shape[0], 25)
+        pos[weld] = pos[(weld + 1) % pos.shape[0]]
+        uv[rng.integers(0, uv.shape[0], 60)] += 0.37  # interior uv seams
+    m = dxo.Mesh(faces, [dxo.Attribute.from_points(pos, 0, 0), dxo.Attribute.from_points(nrm, 1, 1, (0,), 1), dxo.Attribute.from_points(uv, 3, 1, (0,), 2)])
+    m = meshes.drop_unused_points(m)
+    try:
+        orc.encode(m)
+    except Exception:
+        pytest.skip("the reference rejects this input (covered by the error-code tests)")
+    _compare(orc, m)
