@@ -53,3 +53,16 @@ def test_sparse_coder_from_many_threads():
     for t in ts: t.start()
     for t in ts: t.join()
     assert not bad
+
+
+@pytest.mark.parametrize("p0,density", [(255, 0.002), (253, 0.012), (249, 0.02), (3, 0.99), (1, 0.9985)])
+def test_sparse_coder_against_the_oracle_and_its_decoder(orc, p0, density):
+    """Pins both host coders to the oracle's RabsCoder restatement (oracle/orc_core.hpp) and to the oracle's decoder, which
+    returns the bits last-coded-first."""
+    rng = np.random.default_rng(p0)
+    bits = (rng.random(120000) < density).astype(np.uint8)
+    want = orc.rabs_encode(p0, bits)
+    assert dxo.encode_bits(bits, p0, 0) == want
+    got = dxo.encode_bits(bits, p0, 1)
+    assert got == want
+    assert np.array_equal(orc.rabs_decode(p0, got, bits.size), bits[::-1])
