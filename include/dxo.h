@@ -152,7 +152,10 @@ int dxo_device_count(void);
  * bytes, attribute sequences) and the device copies of every array the
  * attribute kernels read. dxo_session_run() executes only the device hot path
  * (quantize -> predict -> symbolize -> histogram -> table -> rANS) plus the
- * D2H of its results, and reassembles the stream. */
+ * D2H of its results, and reassembles the stream. The mesh and the arrays it
+ * points to are borrowed for the life of the session: they must stay valid and
+ * unchanged until dxo_session_destroy (without a position map the faces ARE the
+ * corner -> vertex table the session's traces read). */
 typedef struct dxo_session dxo_session;
 
 int dxo_session_create(const dxo_mesh* mesh, const dxo_config* cfg, dxo_session** out);
