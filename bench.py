@@ -564,6 +564,32 @@ def main():
     attr_bytes = sum(k["algorithmic_bytes_per_launch"] * k["launches_per_step"] for k in hbm_kernels)
     attr_ms = sum(k["ms_per_launch"] * k["launches_per_step"] for k in hbm_kernels)
     rans = [k for k in kernels if k["name"].startswith("K10")]
+    # The same profiled steps with the per-step forms of K4-K6 (what one-shot calls and the batch entry run: they chase the
+    # operand indices through the tables in every step instead of reading a session's records): a second session under
+    # DXO_NO_RINGS, read by the library when the session is uploaded.
+    one_shot = None
+    if args.workload == "config2":
+        os.environ["DXO_NO_RINGS"] = "1"
+        try:
+            plain = dxo.Session(mesh, session_cfg)
+        finally:
+            del os.environ["DXO_NO_RINGS"]
+        plain.run(want_bytes=False)
+        assert plain.run() == ref_bytes
+        dxo.set_profiling(2)
+        agg2 = {}
+        for _ in range(prof_steps):
+            plain.run(want_bytes=False)
+            for k in dxo.last_timing()["kernels"]:
+                a = agg2.setdefault(k["name"], {"ms": 0.0, "bytes": 0, "launches": 0})
+                a["ms"] += k["ms"]; a["bytes"] += k["algorithmic_bytes"]; a["launches"] += 1
+        dxo.set_profiling(False)
+        plain.close()
+        hb = {n: a for n, a in agg2.items() if not n.startswith(("K10", "K9"))}
+        ob, om = sum(a["bytes"] for a in hb.values()) / prof_steps, sum(a["ms"] for a in hb.values()) / prof_steps
+        one_shot = {"ms_per_step": om, "gbs": ob / om / 1e6 if om else None, "frac_of_peak": ob / om / 1e6 / peak if om else None,
+                    "kernels_ms_per_launch": {n: a["ms"] / a["launches"] for n, a in hb.items()},
+                    "note": "per-step forms of K4-K6 (one-shot calls, batch entry); the line's kernels[] / roofline are a resident session's record-based forms"}
     n_sym = sum(len(a) * (2 if a.att_type == dxo.AttributeType.Normal else a.get_num_components()) for a in mesh.attributes)
 
     # ---- end-to-end arm: host buffers in pinned memory -> dxo_encode ---------------------
@@ -669,7 +695,8 @@ def main():
                          "traffic": ncu_traffic(args.workload).get(dom["name"]), "peak_source": peak_src,
                          "note": "dominant HBM-bound attribute kernel; K10 (rANS) is a serial latency-bound loop and is reported under 'rans' (SURVEY.md §8d)"},
             "attribute_kernels": {"algorithmic_bytes_per_step": attr_bytes, "ms_per_step": attr_ms, "gbs": attr_bytes / attr_ms / 1e6 if attr_ms else None,
-                                  "frac_of_peak": attr_bytes / attr_ms / 1e6 / peak if attr_ms else None},
+                                  "frac_of_peak": attr_bytes / attr_ms / 1e6 / peak if attr_ms else None,
+                                  "per_step_forms": one_shot},
             "rans": {"symbols_per_step": n_sym, "streams_in_flight": len(mesh.attributes),
                      "ms_longest_stream": max((k["ms_per_launch"] for k in rans), default=None),
                      "msymbols_per_s_per_stream": (max(len(a) * (2 if a.att_type == dxo.AttributeType.Normal else a.get_num_components()) for a in mesh.attributes)
